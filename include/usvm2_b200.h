@@ -1,0 +1,182 @@
+/* usvm2_b200.h -- C ABI of libusvm2_b200.so: hand-written sm_100a kernels for MedSAM2's per-frame video
+ * propagation path (reference: Joungjimin/US-Video-MedSAM2, config sam2.1_hiera_t512).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`; sizes are element counts;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only enqueue work;
+ *   - return value: 0 on success, <0 on error (USVM_ERR_*); nothing is thrown, nothing is allocated;
+ *   - activations are channels-last ("token major"): [rows, C] with C contiguous; bf16 is raw uint16 storage;
+ *   - no torch types cross this boundary.
+ *
+ * Each entry point names the reference code it replaces (paths relative to the reference repo root).
+ */
+#ifndef USVM2_B200_H
+#define USVM2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USVM_ABI_VERSION 1
+int usvm_abi_version(void);
+/* compute capability major*10+minor of the current device, or <0 */
+int usvm_device_sm(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a14) connected components + hole filling
+ * replaces sam2._C.get_connected_componnets  (sam2/csrc/connected_components.cu:213-282; Python binding
+ * sam2/utils/misc.py:47-63) and fill_holes_in_mask_scores (sam2/utils/misc.py:312-338)
+ * ---------------------------------------------------------------------------------------------- */
+/* img uint8 [N,H,W] (nonzero = foreground, 8-connectivity); labels, counts int32 [N,H,W]; H, W even.
+ * labels = 1 + smallest 2x2-block anchor index of the component, counts = component area; 0 on background. */
+int usvm_cc2d_label_u8(const uint8_t* img, int32_t* labels, int32_t* counts, int N, int H, int W, void* stream);
+/* scores fp32 [N,H,W]: background components (score <= 0) of area <= max_area are set to fill_value; may run in
+ * place.  scratch_* (int32 [N,H,W]) are only needed when the 2x2-block grid exceeds shared memory (H*W > ~128K). */
+int usvm_fill_holes_f32(const float* scores_in, float* scores_out, int32_t* scratch_labels, int32_t* scratch_counts,
+                        int N, int H, int W, int max_area, float fill_value, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM with fused epilogue:  C[M,N] = epi(A[M,K] . W[N,K]^T)
+ * replaces nn.Linear / 1x1 Conv2d / ConvTranspose2d(k2,s2) / im2col convs dispatched to cuBLAS / cuDNN
+ * (hieradet.py:60,77,139,164; image_encoder.py:114; memory_attention.py:36-38; sam/transformer.py:237-240;
+ *  memory_encoder.py:55,94-96,152,157; mask_decoder.py:66-83)
+ * ---------------------------------------------------------------------------------------------- */
+#define USVM_ACT_NONE 0
+#define USVM_ACT_RELU 1
+#define USVM_ACT_GELU 2 /* exact erf form (nn.GELU default) */
+
+typedef struct usvm_gemm_epilogue {
+  const float* bias;      /* [N] or NULL */
+  const float* col_scale; /* [N] or NULL: applied after the activation (CXBlock gamma, memory_encoder.py:113) */
+  const float* residual;  /* fp32 [*, ldr] or NULL: added last; row index = row % res_mod when res_mod > 0 */
+  int ldr;
+  int res_mod;
+  int act;
+  float* out_f32; /* either or both outputs */
+  int ldo_f32;
+  void* out_bf16;
+  int ldo_bf16;
+} usvm_gemm_epilogue;
+
+/* bf16 operands, fp32 accumulation in TMEM: TMA (128B swizzle) -> tcgen05.mma -> tcgen05.ld epilogue.
+ * A bf16 [M,K] row pitch lda, W bf16 [N,K] row pitch ldw (pitches % 8 == 0, bases 16-byte aligned).
+ * block_n: 0 = auto, else 32 / 64 / 128 / 256. */
+int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep_host, int M, int N,
+                       int K, int block_n, void* stream);
+/* fp32-accumulate SIMT GEMM, operands fp32 or bf16 (flags), any shape: fp32 decoder tail + checker. */
+int usvm_gemm_simt(const void* A, int a_is_bf16, int lda, const void* W, int w_is_bf16, int ldw,
+                   const usvm_gemm_epilogue* ep_host, int M, int N, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * attention -- replaces F.scaled_dot_product_attention (hieradet.py:70; sam/transformer.py:270,281,344,355)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct usvm_fmha_params {
+  const void* q; /* bf16; element (b, row, h, c) at q + b*q_bs + row*q_rs + h*q_hs + c */
+  const void* k;
+  const void* v;
+  void* o; /* bf16, same addressing with o_* */
+  long long q_bs, k_bs, v_bs, o_bs;
+  int q_rs, k_rs, v_rs, o_rs;
+  int q_hs, k_hs, v_hs, o_hs;
+  int B, H, Nq, Nk, head_dim; /* head_dim 96 or 256 */
+  int num_splits;             /* >1: keys are split across CTAs (flash-decoding) and merged by a second kernel */
+  float* o_part;              /* fp32 [num_splits, B*H, Nq, head_dim] when num_splits > 1 */
+  float* ml_part;             /* fp32 [num_splits, B*H, Nq, 2] */
+  float scale;                /* 1/sqrt(head_dim) */
+} usvm_fmha_params;
+int usvm_fmha_bf16(const usvm_fmha_params* p_host, void* stream);
+/* fp32, one warp per query; head_dim 16 or 32, Nk <= 1024 (SAM decoder two-way transformer) */
+int usvm_attn_small_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Nq, int Nk,
+                        int head_dim, int q_rs, int k_rs, int v_rs, int o_rs, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * normalisation / position encoding / layout kernels
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm over C (hieradet.py:101,124; memory_attention.py:42-44; transformer.py:162-177) */
+int usvm_layernorm(const float* x, int ldx, const float* w, const float* b, float eps, int gelu, float* out_f32,
+                   int ldo_f32, void* out_bf16, int ldo_bf16, int rows, int C, void* stream);
+/* out = alpha*x[row % x_mod] + beta*y[row % y_mod] (mod 0: same rows); pos-enc adds (memory_attention.py:134-135) */
+int usvm_axpby_rows(const float* x, const float* y, float alpha, float beta, int x_mod, int y_mod, float* out_f32,
+                    void* out_bf16, long long rows, int C, void* stream);
+int usvm_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+/* apply_rotary_enc (position_encoding.py:194-221): rows inside each batch of rows_per_batch with index < n_rope are
+ * rotated with table row (index % table_rows); cos/sin tables [table_rows, dim/2]; output bf16 */
+int usvm_rope_bf16(const float* x, int ldx, const float* cos_t, const float* sin_t, void* out, int ldo, long long rows,
+                   int rows_per_batch, int n_rope, int table_rows, int dim, void* stream);
+/* window_partition + qkv split + q max-pool (backbones/utils.py:17-37, hieradet.py:56-67); qkv bf16 [F,Hg,Wg,3C] */
+int usvm_window_gather(const void* qkv, const float* qkv_bias, void* Qw, void* Kw, void* Vw, int F, int Hg, int Wg,
+                       int ws, int pool, int C, void* stream);
+/* window_unpartition (backbones/utils.py:40-61): [F*nW, wq*wq, C] -> [F, Ho, Wo, C] */
+int usvm_window_scatter(const void* Ow, void* out, int F, int Ho, int Wo, int wq, int C, void* stream);
+/* MaxPool2d(2,2) on NHWC fp32 (hieradet.py:25-36,139-140) */
+int usvm_maxpool2_nhwc(const float* x, float* y, int F, int H, int W, int C, void* stream);
+/* FPN nearest-x2 top-down add (image_encoder.py:116-126): fine += up2(coarse); optional bf16 copy */
+int usvm_upsample2_add(float* fine, const float* coarse, void* fine_bf16, int F, int H, int W, int C, void* stream);
+/* PatchEmbed 7x7/s4/p3 as im2col (backbones/utils.py:64-94): img fp32 [F,3,S,S] -> bf16 [F*(S/4)^2, KP>=147] */
+int usvm_im2col_patch(const float* img, void* A, int F, int S, int KP, void* stream);
+/* frame ingest (sam2/utils/misc.py:253-276): uint8 gray [F,H,W] -> fp32 [F,3,H,W] (x/255 - mean)/std */
+int usvm_normalize_gray_u8(const uint8_t* gray, float* out, int F, int H, int W, const float* mean3_host,
+                           const float* std3_host, void* stream);
+
+/* memory-bank assembly (sam2_base.py:1344-1437) */
+#define USVM_MAX_MEMORY_FRAMES 16
+typedef struct usvm_memory_frames {
+  const void* mem[USVM_MAX_MEMORY_FRAMES]; /* bf16 [B, T, Cm] token-major spatial memories */
+  int tpos_index[USVM_MAX_MEMORY_FRAMES];  /* row of maskmem_tpos_enc to add (num_maskmem - t_pos - 1) */
+  int count;
+} usvm_memory_frames;
+/* k_in = mem + pos + tpos, v_in = mem for rows [row_offset, row_offset + count*T + n_ptr_tokens) of [B, Nk_total, Cm];
+ * pointer tokens fp32 [B, n_ptr_tokens, Cm] with their own pos [n_ptr_tokens, Cm] */
+int usvm_build_memory(const usvm_memory_frames* frames_host, const float* pos, const float* tpos, const float* ptrs,
+                      const float* ptr_pos, void* k_in, void* v_in, int B, int T, int Cm, int n_ptr_tokens,
+                      int Nk_total, int row_offset, void* stream);
+/* memory feature epilogue (sam2_base.py:1488-1496; sam2_video_predictor.py:956): + no_obj_embed_spatial where
+ * score <= 0, rounded to bf16 into the bank slot [B, T, Cm] */
+int usvm_finalize_memory(const float* x, const float* score, const float* no_obj_embed, void* mem_bf16, int B, int T,
+                         int Cm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * small convolutions / resize (memory encoder, prompt encoder)
+ * ---------------------------------------------------------------------------------------------- */
+/* NHWC fp32 direct conv, weights [k][k][Cin][Cout] (<= 48 KB), Cout <= 64, optional LayerNorm2d + GELU
+ * (memory_encoder.py:40-56; prompt_encoder.py:57-66; sam2_base.py:863) */
+int usvm_conv2d_small(const float* x, const float* w_kkio, const float* bias, const float* ln_w, const float* ln_b,
+                      float eps, int gelu, float* out_f32, void* out_bf16, int B, int H, int W, int Cin, int Cout,
+                      int k, int stride, int pad, void* stream);
+int usvm_im2col_nhwc(const float* x, void* A, int B, int H, int W, int C, int k, int stride, int pad, void* stream);
+/* CXBlock depthwise 7x7 + LayerNorm2d (memory_encoder.py:104-108); weights [49][C]; C == 256; bf16 out */
+int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* bias, const float* ln_w, const float* ln_b,
+                    float eps, void* out_bf16, int B, int H, int W, int C, void* stream);
+#define USVM_POST_NONE 0
+#define USVM_POST_SIGMOID_AFFINE 1  /* sigmoid(v)*scale + bias  (sam2_base.py:1477-1484) */
+#define USVM_POST_BINARIZE_AFFINE 2 /* (v > 0)*scale + bias     (sam2_base.py:1472-1474) */
+int usvm_resize_bilinear(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo, int post_mode,
+                         float post_scale, float post_bias, void* stream);
+int usvm_resize_bilinear_aa(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo,
+                            int binarize_half, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SAM mask decoder tail (fp32)
+ * ---------------------------------------------------------------------------------------------- */
+/* feat_shared != 0: feat_s1 / feat_s0 hold ONE frame that every object of the batch shares */
+int usvm_upscale1_ln_gelu(const float* g1, const float* feat_s1, const float* ln_w, const float* ln_b, float eps,
+                          float* out, int B, int Hc, int Wc, int C, int feat_shared, void* stream);
+int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, float* masks, int B, int Hc, int Wc,
+                        int feat_shared, void* stream);
+int usvm_small_mlp3(const float* x, long long x_row_stride, long long x_inst_stride, const int* row_select,
+                    const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                    const float* b3, int out_dim, int sigmoid_out, float* y, long long y_row_stride,
+                    long long y_inst_stride, int rows, int instances, void* stream);
+int usvm_sam_select(const float* masks, const float* iou, const float* score, int multimask, float stab_delta,
+                    float stab_thresh, float no_obj_score, float* low_res, int* token_index, float* iou_out, int B,
+                    int HW, void* stream);
+int usvm_objptr_mix(float* ptr, const float* score, const float* no_obj_ptr, int B, int C, void* stream);
+int usvm_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float image_size,
+                     float* out, int n_points, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USVM2_B200_H */

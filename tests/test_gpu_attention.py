@@ -1,0 +1,61 @@
+"""Attention kernels vs a plain PyTorch fp32 reference (same bf16-rounded operands)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_attn(q, k, v):
+    s = q.float() @ k.float().transpose(-1, -2) / math.sqrt(q.shape[-1])
+    return torch.softmax(s, dim=-1) @ v.float()
+
+
+@pytest.mark.parametrize("D,B,H,Nq,Nk,splits", [
+    (96, 256, 1, 64, 64, 1), (96, 256, 2, 16, 64, 1), (96, 9, 4, 196, 196, 1), (96, 9, 8, 49, 196, 1),
+    (96, 2, 4, 1024, 1024, 1), (96, 256, 4, 4, 16, 1), (256, 1, 1, 1024, 1024, 8), (256, 1, 1, 1024, 7208, 9),
+    (256, 2, 1, 1024, 2068, 4), (256, 1, 1, 1024, 1028, 1), (256, 3, 1, 100, 70, 2),
+])
+def test_fmha_bf16(D, B, H, Nq, Nk, splits):
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(Nq + Nk)
+    q = torch.randn((B, Nq, H, D), generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn((B, Nk, H, D), generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn((B, Nk, H, D), generator=g, device="cuda").to(torch.bfloat16)
+    out = ops.fmha(q, k, v, B, H, Nq, Nk, D, (0, Nq * H * D, H * D, D), (0, Nk * H * D, H * D, D),
+                   (0, Nk * H * D, H * D, D), num_splits=splits)
+    want = _ref_attn(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    err = (out.view(B, Nq, H, D).float() - want).abs().max().item()
+    assert err < 2e-2, err  # bf16 P and bf16 output rounding
+
+
+def test_fmha_strided_qkv_buffer():
+    """Q/K/V read in place from a fused [tokens, 3C] projection (global Hiera blocks)."""
+    from us_video_medsam2_b200 import ops
+
+    F_, T, H, D = 2, 1024, 4, 96
+    C = H * D
+    g = torch.Generator(device="cuda").manual_seed(1)
+    qkv = torch.randn((F_ * T, 3 * C), generator=g, device="cuda").to(torch.bfloat16)
+    out = ops.fmha(qkv, qkv, qkv, F_, H, T, T, D, (0, T * 3 * C, 3 * C, D), (C, T * 3 * C, 3 * C, D),
+                   (2 * C, T * 3 * C, 3 * C, D))
+    x = qkv.view(F_, T, 3, H, D).permute(2, 0, 3, 1, 4)
+    want = _ref_attn(x[0], x[1], x[2]).permute(0, 2, 1, 3).reshape(F_, T, C)
+    assert (out.float() - want).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,Nq,Nk,dh", [(1, 8, 8, 32), (4, 8, 1024, 16), (2, 1024, 8, 16), (3, 9, 9, 32)])
+def test_attn_small_f32(B, Nq, Nk, dh):
+    from us_video_medsam2_b200 import ops
+
+    H = 8
+    g = torch.Generator(device="cuda").manual_seed(2)
+    q = torch.randn((B * Nq, H * dh), generator=g, device="cuda")
+    k = torch.randn((B * Nk, H * dh), generator=g, device="cuda")
+    v = torch.randn((B * Nk, H * dh), generator=g, device="cuda")
+    got = ops.attn_small(q, k, v, B, H, Nq, Nk, dh)
+    sp = lambda t, n: t.view(B, n, H, dh).permute(0, 2, 1, 3)
+    want = _ref_attn(sp(q, Nq), sp(k, Nk), sp(v, Nk)).permute(0, 2, 1, 3).reshape(B * Nq, H * dh)
+    assert (got - want).abs().max().item() < 2e-5

@@ -1,0 +1,95 @@
+"""(a14) connected components / hole filling: CUDA kernel vs the CPU oracle, bit-exact, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.cc_ref import connected_components_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(img_np):
+    from sam2 import _C  # the drop-in op, same spelling as the reference
+
+    x = torch.from_numpy(img_np).cuda()
+    labels, counts = _C.get_connected_componnets(x)
+    torch.cuda.synchronize()
+    return labels.cpu().numpy(), counts.cpu().numpy()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 2, 2), (3, 1, 128, 128), (2, 1, 64, 96), (5, 1, 30, 18), (1, 1, 256, 256),
+                                   (2, 1, 512, 640)])
+@pytest.mark.parametrize("density", [0.0, 0.08, 0.45, 0.6, 0.93, 1.0])
+def test_labels_and_counts_bit_exact(shape, density):
+    rng = np.random.default_rng(hash((shape, density)) % (2 ** 32))
+    img = (rng.random(shape) < density).astype(np.uint8)
+    want_l, want_c = connected_components_ref(img)
+    got_l, got_c = _run(img)
+    assert got_l.dtype == np.int32 and got_c.dtype == np.int32
+    assert np.array_equal(got_l, want_l)
+    assert np.array_equal(got_c, want_c)
+
+
+def test_structured_masks_bit_exact():
+    """Spirals / checkerboards / diagonals: long union-find chains and pure 8-connectivity joins."""
+    H = W = 128
+    imgs = np.zeros((4, 1, H, W), np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    imgs[0, 0] = ((yy + xx) % 2 == 0)                      # checkerboard: one 8-connected component
+    imgs[1, 0] = (yy == xx) | (yy + xx == W - 1)           # two crossing diagonals
+    imgs[2, 0] = ((yy // 2) % 2 == 0) & ~((xx == W - 1) & ((yy // 4) % 2 == 0)) & ~((xx == 0) & ((yy // 4) % 2 == 1))
+    imgs[3, 0] = (yy % 4 == 0) | ((xx % 8 == 0) & (yy % 8 < 4))
+    want_l, want_c = connected_components_ref(imgs)
+    got_l, got_c = _run(imgs)
+    assert np.array_equal(got_l, want_l) and np.array_equal(got_c, want_c)
+
+
+def test_empty_batch_and_argument_errors():
+    from sam2 import _C
+
+    l, c = _C.get_connected_componnets(torch.zeros((0, 1, 8, 8), dtype=torch.uint8, device="cuda"))
+    assert l.shape == (0, 1, 8, 8) and c.shape == (0, 1, 8, 8)
+    with pytest.raises(RuntimeError):
+        _C.get_connected_componnets(torch.zeros((1, 1, 8, 8), dtype=torch.uint8))  # CPU tensor
+    with pytest.raises(RuntimeError):
+        _C.get_connected_componnets(torch.zeros((1, 1, 7, 8), dtype=torch.uint8, device="cuda"))  # odd height
+    with pytest.raises(RuntimeError):
+        _C.get_connected_componnets(torch.zeros((1, 1, 8, 8), dtype=torch.float32, device="cuda"))
+    with pytest.raises(RuntimeError):
+        _C.get_connected_componnets(torch.zeros((1, 2, 8, 8), dtype=torch.uint8, device="cuda"))
+
+
+@pytest.mark.parametrize("shape", [(4, 1, 128, 128), (1, 1, 512, 640)])
+def test_fill_holes_matches_reference_composition(shape):
+    """fused kernel == where((labels > 0) & (areas <= 8), 0.1, mask) with labels/areas of (mask <= 0)."""
+    from sam2.utils.misc import fill_holes_in_mask_scores
+
+    g = torch.Generator().manual_seed(7)
+    scores = torch.randn(shape, generator=g) * 0.07 + 0.02
+    scores[0, 0, :4, :4] = 0.0  # exact zeros count as background
+    labels, areas = connected_components_ref((scores <= 0).numpy().astype(np.uint8))
+    want = torch.where(torch.from_numpy((labels > 0) & (areas <= 8)), torch.full_like(scores, 0.1), scores)
+    got = fill_holes_in_mask_scores(scores.cuda(), 8).cpu()
+    assert torch.equal(got, want)
+    assert int((got != scores).sum()) > 0  # the case really exercises the fill
+
+
+def test_idempotent_and_area_checksum():
+    """Size-independent properties at the full batch of BASELINE config 3 (4 objects x many frames)."""
+    from sam2 import _C
+
+    g = torch.Generator().manual_seed(3)
+    img = (torch.rand((256, 1, 128, 128), generator=g) < 0.5).to(torch.uint8).cuda()
+    labels, counts = _C.get_connected_componnets(img)
+    assert torch.equal((labels > 0), img.bool())
+    # every pixel of a component reports the same area, and the areas of the distinct components sum to #fg
+    flat_l, flat_c = labels.flatten(1), counts.flatten(1)
+    for n in (0, 17, 255):
+        roots, inv = torch.unique(flat_l[n][flat_l[n] > 0], return_inverse=True)
+        area = torch.zeros(len(roots), dtype=torch.int64, device="cuda").scatter_add_(
+            0, inv, torch.ones_like(inv, dtype=torch.int64))
+        assert torch.equal(area[inv], flat_c[n][flat_l[n] > 0].long())
+        assert int(area.sum()) == int(img[n].sum())
+    # labelling the "label > 0" mask again gives the same labels
+    l2, c2 = _C.get_connected_componnets((labels > 0).to(torch.uint8))
+    assert torch.equal(l2, labels) and torch.equal(c2, counts)

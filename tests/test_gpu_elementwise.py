@@ -1,0 +1,294 @@
+"""Bandwidth / layout / small-conv / decoder-tail kernels vs plain PyTorch fp32 references of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _g(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("rows,C,eps", [(1000, 96, 1e-6), (4096, 768, 1e-6), (2048, 256, 1e-5), (7, 64, 1e-6)])
+def test_layernorm(rows, C, eps):
+    from us_video_medsam2_b200 import ops
+
+    g = _g(rows)
+    x = torch.randn((rows, C), generator=g, device="cuda") * 3 + 1
+    w, b = torch.randn(C, generator=g, device="cuda"), torch.randn(C, generator=g, device="cuda")
+    o32, o16 = ops.layernorm(x, w, b, eps, f32=True, bf16=True)
+    want = F.layer_norm(x, (C,), w, b, eps)
+    assert (o32 - want).abs().max().item() < 2e-5
+    assert (o16.float() - want).abs().max().item() < 4e-2
+    o32g, _ = ops.layernorm(x, w, b, eps, f32=True, gelu=True)
+    assert (o32g - F.gelu(want)).abs().max().item() < 2e-5
+
+
+def test_axpby_and_cast():
+    from us_video_medsam2_b200 import ops
+
+    g = _g(1)
+    x = torch.randn((1024, 256), generator=g, device="cuda")
+    y = torch.randn((1024, 256), generator=g, device="cuda")
+    o, _ = ops.axpby(x, y, 1.0, 0.1, rows=3 * 1024, x_mod=1024, y_mod=1024)
+    assert torch.allclose(o, (x + 0.1 * y).repeat(3, 1), atol=1e-6)
+    row = torch.randn((1, 256), generator=g, device="cuda")
+    o, _ = ops.axpby(x, row, rows=1024, y_mod=1)
+    assert torch.allclose(o, x + row, atol=1e-6)
+    assert torch.equal(ops.cast_bf16(x), x.to(BF))
+
+
+def test_rope_matches_complex_multiply():
+    from oracle.medsam2_ref import apply_rope, axial_rope_table
+    from us_video_medsam2_b200 import ops
+    from us_video_medsam2_b200.engine import _rope_tables
+
+    c, s = _rope_tables(256, 32, 32)
+    c2, s2 = axial_rope_table(256, 32, 32)
+    assert torch.equal(c, c2) and torch.equal(s, s2)
+    g = _g(2)
+    B, Nk, n_ptr = 2, 2 * 1024 + 12, 12
+    x = torch.randn((B * Nk, 768), generator=g, device="cuda")
+    got = ops.rope(x, 256, c.cuda(), s.cuda(), Nk, Nk - n_ptr)
+    xv = x[:, 256:512].cpu().view(B, Nk, 256)
+    want = torch.cat([apply_rope(xv[:, : Nk - n_ptr], c.repeat(2, 1), s.repeat(2, 1)), xv[:, Nk - n_ptr:]], dim=1)
+    assert (got.float().cpu().view(B, Nk, 256) - want).abs().max().item() < 2e-2
+    assert torch.equal(got.view(B, Nk, 256)[:, Nk - n_ptr:].cpu(), xv[:, Nk - n_ptr:].to(BF))
+
+
+@pytest.mark.parametrize("Hg,ws,pool,heads", [(128, 8, False, 1), (128, 8, True, 2), (64, 4, False, 2), (64, 4, True, 4),
+                                              (32, 14, False, 4), (32, 14, True, 8), (16, 7, False, 8)])
+def test_window_gather_scatter(Hg, ws, pool, heads):
+    """vs window_partition / q max-pool / window_unpartition restated in oracle/medsam2_ref.py."""
+    from oracle.medsam2_ref import RefModel
+    from us_video_medsam2_b200 import ops
+
+    Fr, C = 2, heads * 96
+    g = _g(Hg + ws)
+    qkv = torch.randn((Fr, Hg, Hg, 3 * C), generator=g, device="cuda").to(BF)
+    bias = torch.randn(3 * C, generator=g, device="cuda")
+    Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, bias, Fr, Hg, Hg, ws, pool, C)
+    # reference: pad positions hold the bias (qkv of a zero row), then partition
+    x = qkv.float().cpu()
+    pad = (ws - Hg % ws) % ws
+    if pad:
+        xp = bias.to(BF).float().cpu().expand(Fr, Hg + pad, Hg + pad, 3 * C).clone()
+        xp[:, :Hg, :Hg] = x
+        x = xp
+    win, _ = RefModel._to_windows(x, ws)
+    q, k, v = win[..., :C], win[..., C:2 * C], win[..., 2 * C:]
+    if pool:
+        q = RefModel._maxpool2(q)
+    assert torch.equal(Kw.float().cpu(), k.reshape(Fr * nw, nk, C))
+    assert torch.equal(Vw.float().cpu(), v.reshape(Fr * nw, nk, C))
+    assert torch.equal(Qw.float().cpu(), q.reshape(Fr * nw, nq, C))
+    wq = ws // 2 if pool else ws
+    Ho = Hg // 2 if pool else Hg
+    out = ops.window_scatter(Qw, Fr, Ho, Ho, wq, C)
+    hp = Ho + (wq - Ho % wq) % wq
+    want = RefModel._from_windows(q, wq, (hp, hp), (Ho, Ho))
+    assert torch.equal(out.float().cpu().view(Fr, Ho, Ho, C), want)
+
+
+def test_maxpool_upsample_im2col():
+    from us_video_medsam2_b200 import ops
+
+    g = _g(4)
+    x = torch.randn((2, 64, 64, 192), generator=g, device="cuda")
+    y = ops.maxpool2(x.view(-1, 192), 2, 64, 64, 192)
+    want = F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(y.view(2, 32, 32, 192), want)
+    fine = torch.randn((2, 32, 32, 256), generator=g, device="cuda")
+    coarse = torch.randn((2, 16, 16, 256), generator=g, device="cuda")
+    want = fine + F.interpolate(coarse.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    f2 = fine.clone().view(-1, 256)
+    b16 = ops.upsample2_add_(f2, coarse.view(-1, 256), 2, 32, 32, 256, bf16=True)
+    assert torch.allclose(f2.view_as(want), want, atol=1e-6) and torch.equal(b16, f2.to(BF))
+    img = torch.randn((2, 3, 512, 512), generator=g, device="cuda")
+    A = ops.im2col_patch(img)
+    cols = F.unfold(img, kernel_size=7, padding=3, stride=4).transpose(1, 2).reshape(-1, 147)
+    assert torch.equal(A[:, :147], cols.to(BF)) and float(A[:, 147:].abs().max()) == 0.0
+
+
+def test_normalize_gray_u8():
+    from us_video_medsam2_b200 import ops, synth
+
+    g = torch.randint(0, 256, (3, 64, 48), dtype=torch.uint8, device="cuda")
+    out = ops.normalize_gray_u8(g, synth.IMG_MEAN, synth.IMG_STD)
+    mean = torch.tensor(synth.IMG_MEAN, device="cuda")[None, :, None, None]
+    std = torch.tensor(synth.IMG_STD, device="cuda")[None, :, None, None]
+    want = (g.float()[:, None] / 255.0 - mean) / std
+    assert torch.allclose(out, want, atol=1e-6)
+
+
+def test_build_memory_and_finalize():
+    from us_video_medsam2_b200 import ops
+
+    g = _g(5)
+    B, T, Cm, P = 2, 1024, 64, 5
+    frames = [torch.randn((B, T, Cm), generator=g, device="cuda").to(BF) for _ in range(3)]
+    pos = torch.randn((T, Cm), generator=g, device="cuda")
+    tpos = torch.randn((7, Cm), generator=g, device="cuda")
+    ptrs = torch.randn((B, P * 4, Cm), generator=g, device="cuda")
+    ppos = torch.randn((P * 4, Cm), generator=g, device="cuda")
+    rows = [6, 0, 3]
+    k_in, v_in, Nk = ops.build_memory(frames, rows, pos, tpos, ptrs, ppos, B)
+    assert Nk == 3 * T + 4 * P
+    wk = torch.cat([f.float() + pos + tpos[r] for f, r in zip(frames, rows)] + [ptrs + ppos], dim=1)
+    wv = torch.cat([f.float() for f in frames] + [ptrs], dim=1)
+    assert torch.equal(k_in, wk.to(BF)) and torch.equal(v_in, wv.to(BF))
+    x = torch.randn((B * T, Cm), generator=g, device="cuda")
+    score = torch.tensor([0.3, -0.2], device="cuda")
+    emb = torch.randn(Cm, generator=g, device="cuda")
+    mem = ops.finalize_memory(x, score, emb, B)
+    want = x.view(B, T, Cm).clone()
+    want[1] += emb
+    assert torch.equal(mem, want.to(BF))
+
+
+@pytest.mark.parametrize("Cin,Cout,k,s,p,H", [(1, 4, 3, 2, 1, 512), (4, 16, 3, 2, 1, 256), (16, 64, 3, 2, 1, 128),
+                                              (1, 4, 2, 2, 0, 128), (4, 16, 2, 2, 0, 64), (1, 1, 4, 4, 0, 512)])
+def test_conv2d_small(Cin, Cout, k, s, p, H):
+    from us_video_medsam2_b200 import ops
+
+    g = _g(Cin * 10 + k)
+    B = 2
+    x = torch.randn((B, Cin, H, H), generator=g, device="cuda")
+    w = torch.randn((Cout, Cin, k, k), generator=g, device="cuda") / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g, device="cuda")
+    lw, lb = torch.randn(Cout, generator=g, device="cuda"), torch.randn(Cout, generator=g, device="cuda")
+    use_ln = Cout > 1
+    out, Ho, Wo = ops.conv2d_small(x.permute(0, 2, 3, 1).contiguous(), w.permute(2, 3, 1, 0).contiguous(), b, B, H, H,
+                                   Cin, Cout, k, s, p, ln=(lw, lb) if use_ln else None, gelu=use_ln)
+    y = F.conv2d(x, w, b, stride=s, padding=p)
+    if use_ln:
+        u = y.mean(1, keepdim=True)
+        v = (y - u).pow(2).mean(1, keepdim=True)
+        y = F.gelu((y - u) / torch.sqrt(v + 1e-6) * lw[None, :, None, None] + lb[None, :, None, None])
+    assert (out.view(B, Ho, Wo, Cout) - y.permute(0, 2, 3, 1)).abs().max().item() < 1e-4
+
+
+def test_im2col_nhwc_and_dwconv():
+    from us_video_medsam2_b200 import ops
+
+    g = _g(6)
+    B = 2
+    x = torch.randn((B, 64, 64, 64), generator=g, device="cuda")
+    A = ops.im2col_nhwc(x.view(-1, 64), B, 64, 64, 64, 3, 2, 1)
+    w = torch.randn((256, 64, 3, 3), generator=g, device="cuda")
+    want = F.conv2d(x.permute(0, 3, 1, 2).to(BF).float(), w, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, 256)
+    got = A.float() @ w.permute(0, 2, 3, 1).reshape(256, 576).t()
+    assert (got - want).abs().max().item() < 2e-3
+    x = torch.randn((B, 256, 32, 32), generator=g, device="cuda")
+    dw = torch.randn((256, 1, 7, 7), generator=g, device="cuda") / 7
+    db = torch.randn(256, generator=g, device="cuda")
+    lw, lb = torch.randn(256, generator=g, device="cuda"), torch.randn(256, generator=g, device="cuda")
+    out = ops.dwconv7_ln(x.permute(0, 2, 3, 1).contiguous().view(-1, 256), dw.reshape(256, 49).t().contiguous(), db, lw,
+                         lb, B, 32, 32)
+    y = F.conv2d(x, dw, db, padding=3, groups=256).permute(0, 2, 3, 1)
+    y = F.layer_norm(y, (256,), lw, lb, 1e-6)
+    assert (out.float().view_as(y) - y).abs().max().item() < 5e-2
+    assert (out.float().view_as(y) - y.to(BF).float()).abs().max().item() < 4e-2
+
+
+@pytest.mark.parametrize("Hi,Ho", [(128, 512), (128, 360), (512, 128), (100, 37)])
+def test_resize_bilinear(Hi, Ho):
+    from us_video_medsam2_b200 import ops
+
+    g = _g(Hi)
+    x = torch.randn((3, 1, Hi, Hi + 8), generator=g, device="cuda")
+    got = ops.resize_bilinear(x, Ho, Ho + 4)
+    want = F.interpolate(x, size=(Ho, Ho + 4), mode="bilinear", align_corners=False)
+    assert (got - want).abs().max().item() < 1e-5
+    got = ops.resize_bilinear(x, Ho, Ho + 4, ops.POST_SIGMOID_AFFINE, 20.0, -10.0)
+    assert (got - (torch.sigmoid(want) * 20 - 10)).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("Hi,Ho", [(512, 128), (720, 512), (300, 512), (128, 128)])
+def test_resize_bilinear_antialias(Hi, Ho):
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator().manual_seed(Hi)
+    x = torch.rand((2, 1, Hi, Hi + 16), generator=g)
+    want = F.interpolate(x, size=(Ho, Ho), mode="bilinear", align_corners=False, antialias=True)  # CPU = oracle side
+    got = ops.resize_bilinear_aa(x.cuda(), Ho, Ho).cpu()
+    assert (got - want).abs().max().item() < 1e-5
+
+
+def test_decoder_tail_kernels():
+    from us_video_medsam2_b200 import ops
+
+    g = _g(8)
+    B = 2
+    # two transposed convs as pixel-shuffle GEMMs + fused epilogues
+    src = torch.randn((B, 256, 32, 32), generator=g, device="cuda")
+    w1 = torch.randn((256, 64, 2, 2), generator=g, device="cuda") / 16
+    b1 = torch.randn(64, generator=g, device="cuda")
+    w2 = torch.randn((64, 32, 2, 2), generator=g, device="cuda") / 8
+    b2 = torch.randn(32, generator=g, device="cuda")
+    lw, lb = torch.randn(64, generator=g, device="cuda"), torch.randn(64, generator=g, device="cuda")
+    s1 = torch.randn((1, 64, 64, 64), generator=g, device="cuda")
+    s0 = torch.randn((1, 32, 128, 128), generator=g, device="cuda")
+    hyper = torch.randn((B, 4, 32), generator=g, device="cuda")
+    y = F.conv_transpose2d(src, w1, b1, stride=2) + s1
+    u = y.mean(1, keepdim=True)
+    v = (y - u).pow(2).mean(1, keepdim=True)
+    y = F.gelu((y - u) / torch.sqrt(v + 1e-6) * lw[None, :, None, None] + lb[None, :, None, None])
+    y2 = F.gelu(F.conv_transpose2d(y, w2, b2, stride=2) + s0)
+    want_masks = (hyper @ y2.view(B, 32, -1)).view(B, 4, 128, 128)
+    keys = src.permute(0, 2, 3, 1).reshape(-1, 256).contiguous()
+    g1 = ops.gemm_f32(keys, w1.permute(2, 3, 1, 0).reshape(256, 256).contiguous(), b1.repeat(4))
+    u1 = ops.upscale1_ln_gelu(g1, s1.permute(0, 2, 3, 1).contiguous(), lw, lb, B, 32, 32, True)
+    assert (u1.view(B, 64, 64, 64) - y.permute(0, 2, 3, 1)).abs().max().item() < 2e-4
+    g2 = ops.gemm_f32(u1, w2.permute(2, 3, 1, 0).reshape(128, 64).contiguous(), b2.repeat(4))
+    masks = ops.upscale2_masks(g2, s0.permute(0, 2, 3, 1).contiguous(), hyper.contiguous(), B, 64, 64, True)
+    assert (masks - want_masks).abs().max().item() < 5e-4
+    # small MLP, instance-stacked + row select
+    Ws = [torch.randn((4, 256, 256), generator=g, device="cuda") / 16, torch.randn((4, 256), generator=g, device="cuda"),
+          torch.randn((4, 256, 256), generator=g, device="cuda") / 16, torch.randn((4, 256), generator=g, device="cuda"),
+          torch.randn((4, 32, 256), generator=g, device="cuda") / 16, torch.randn((4, 32), generator=g, device="cuda")]
+    hs = torch.randn((B, 8, 256), generator=g, device="cuda")
+    got = ops.small_mlp3(hs.data_ptr() + 4 * 2 * 256, 8 * 256, 256, None, tuple(Ws), 32, B, 4, hs)
+    for i in range(4):
+        x = hs[:, 2 + i]
+        want = F.relu(F.relu(x @ Ws[0][i].t() + Ws[1][i]) @ Ws[2][i].t() + Ws[3][i]) @ Ws[4][i].t() + Ws[5][i]
+        assert (got[:, i] - want).abs().max().item() < 1e-4
+    idx = torch.tensor([3, 1], dtype=torch.int32, device="cuda")
+    one = tuple(t[:1].contiguous() for t in Ws)
+    got = ops.small_mlp3(hs.data_ptr() + 4 * 2 * 256, 8 * 256, 256, idx, one, 32, B, 1, hs, sigmoid=True)
+    for b in range(B):
+        x = hs[b, 2 + int(idx[b])]
+        want = torch.sigmoid(F.relu(F.relu(x @ Ws[0][0].t() + Ws[1][0]) @ Ws[2][0].t() + Ws[3][0]) @ Ws[4][0].t() + Ws[5][0])
+        assert (got[b, 0] - want).abs().max().item() < 1e-5
+
+
+def test_sam_select_and_point_embed():
+    from oracle.medsam2_ref import random_fourier_pe
+    from us_video_medsam2_b200 import ops
+
+    g = _g(9)
+    B = 3
+    masks = torch.randn((B, 4, 128, 128), generator=g, device="cuda") * 0.07
+    masks[1, 0] = masks[1, 0].abs() + 0.2  # stable single mask for object 1
+    iou = torch.tensor([[0.9, 0.2, 0.5, 0.4], [0.1, 0.3, 0.3, 0.2], [0.5, 0.1, 0.2, 0.6]], device="cuda")
+    score = torch.tensor([[0.4], [0.2], [-0.1]], device="cuda")
+    low, idx, sel = ops.sam_select(masks, iou, score, True, 0.05, 0.98, -1024.0)
+    assert idx.tolist() == [2, 1, 3] and torch.allclose(sel.flatten(), torch.tensor([0.5, 0.3, 0.6], device="cuda"))
+    assert torch.equal(low[0, 0], masks[0, 2]) and torch.equal(low[1, 0], masks[1, 1])
+    assert float(low[2].max()) == -1024.0 and float(low[2].min()) == -1024.0
+    low, idx, sel = ops.sam_select(masks, iou, score, False, 0.05, 0.98, -1024.0)
+    assert idx.tolist() == [0, 0, 0]
+    assert torch.equal(low[0, 0], masks[0, 2])  # unstable -> best multimask
+    assert torch.equal(low[1, 0], masks[1, 0])  # stable -> single mask
+    gauss = torch.randn((2, 128), generator=g, device="cuda")
+    table = torch.randn((5, 256), generator=g, device="cuda")
+    coords = torch.tensor([[[100.5, 200.5], [30.5, 40.5], [0.0, 0.0]]], device="cuda")
+    labels = torch.tensor([[1, 3, -1]], dtype=torch.int32, device="cuda")
+    got = ops.point_embed(coords, labels, gauss, table, 512)
+    pe = random_fourier_pe(coords.cpu() / 512, gauss.cpu())
+    want = torch.stack([pe[0, 0] + table[1].cpu(), pe[0, 1] + table[3].cpu(), table[4].cpu()])
+    assert (got[0].cpu() - want).abs().max().item() < 1e-4

@@ -1,0 +1,91 @@
+"""GEMM kernels vs a plain PyTorch fp32 reference of the same op (bf16-rounded operands, fp32 accumulate)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias, act, scale, res, res_mod):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = F.relu(y)
+    elif act == 2:
+        y = F.gelu(y)
+    if scale is not None:
+        y = y * scale
+    if res is not None:
+        idx = torch.arange(y.shape[0], device=y.device) % res_mod if res_mod else torch.arange(y.shape[0], device=y.device)
+        y = y + res[idx]
+    return y
+
+
+SHAPES = [  # (M, N, K) -- hot-path shapes + ragged tails
+    (128, 64, 64), (256, 96, 96), (16384, 288, 96), (4096, 768, 192), (1024, 2048, 256), (1024, 256, 2048),
+    (7232, 256, 64), (1000, 100 * 1 + 4, 72), (130, 40, 200), (1024, 1152, 384), (16384, 96, 160), (256, 256, 768),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("block_n", [0, 32, 128])
+def test_tc5_gemm_matches_fp32_reference(M, N, K, block_n):
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn((M, K), generator=g, device="cuda")).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    o32, _ = ops.gemm_bf16(a, w, f32=True, block_n=block_n, simt=False)
+    torch.cuda.synchronize()
+    want = _ref(a, w, None, 0, None, None, 0)
+    err = (o32 - want).abs().max().item()
+    assert err < 2e-3 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_tc5_gemm_fused_epilogue(act):
+    from us_video_medsam2_b200 import ops
+
+    M, N, K = 2048, 256, 1024
+    g = torch.Generator(device="cuda").manual_seed(act)
+    a = torch.randn((M, K), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda")
+    scale = torch.rand(N, generator=g, device="cuda")
+    res = torch.randn((1024, N), generator=g, device="cuda")
+    o32, o16 = ops.gemm_bf16(a, w, bias=bias, act=act, col_scale=scale, residual=res, res_mod=1024, f32=True,
+                             bf16=True, simt=False)
+    want = _ref(a, w, bias, act, scale, res, 1024)
+    assert (o32 - want).abs().max().item() < 3e-3
+    assert (o16.float() - want).abs().max().item() < 3e-2
+    # in-place residual (x = x + f(x)) as used by every transformer block
+    x = torch.randn((M, N), generator=g, device="cuda")
+    want = _ref(a, w, bias, 0, None, x.clone(), 0)
+    ops.gemm_bf16(a, w, bias=bias, residual=x, out_f32=x, simt=False)
+    assert (x - want).abs().max().item() < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 256, 256), (1024, 128, 256), (4096, 128, 64), (37, 19, 53)])
+def test_simt_gemm_fp32(M, N, K):
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn((M, K), generator=g, device="cuda")
+    w = torch.randn((N, K), generator=g, device="cuda") / K ** 0.5
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = torch.randn((M, N), generator=g, device="cuda")
+    got = ops.gemm_f32(a, w, bias, act=1, residual=res)
+    want = F.relu(a @ w.t() + bias) + res
+    assert (got - want).abs().max().item() < 1e-4
+
+
+def test_simt_and_tc5_agree_on_bf16_operands():
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn((1024, 384), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((1536, 384), generator=g, device="cuda") / 20).to(torch.bfloat16)
+    x, _ = ops.gemm_bf16(a, w, f32=True, simt=False)
+    y, _ = ops.gemm_bf16(a, w, f32=True, simt=True)
+    assert (x - y).abs().max().item() < 1e-3

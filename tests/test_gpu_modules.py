@@ -1,0 +1,135 @@
+"""Module-level parity: Engine (CUDA kernels) vs oracle.medsam2_ref.RefModel (CPU fp32) on the same seeded
+weights and inputs.  bf16 stages are held to the emulated-bf16 envelope, the fp32 decoder to rounding level."""
+import pytest
+import torch
+
+from us_video_medsam2_b200 import synth
+
+pytestmark = pytest.mark.gpu
+SEED = 19
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from oracle.medsam2_ref import RefModel
+    from us_video_medsam2_b200.engine import Engine, PackedWeights
+
+    sd = synth.make_state_dict(SEED)
+    eng = Engine(PackedWeights(sd, torch.device("cuda")))
+    ref = RefModel(sd)
+    clip = synth.make_clip(2, kind="speckle")
+    with torch.inference_mode():
+        rf = ref.forward_image(clip[:1])
+    return eng, ref, clip, rf
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def test_image_encoder(setup):
+    eng, ref, clip, rf = setup
+    with torch.inference_mode():
+        out = eng.encode_frames(clip.cuda())
+    feat = out["feat"][0].float().cpu().t().reshape(256, 32, 32)
+    s1 = out["feat_s1"][0].cpu().t().reshape(64, 64, 64)
+    s0 = out["feat_s0"][0].cpu().t().reshape(32, 128, 128)
+    # bf16 tensor-core contractions through 12 blocks: a few 1e-2 relative to the feature range
+    assert _rel(feat, rf["feat"][0]) < 4e-2, _rel(feat, rf["feat"][0])
+    assert _rel(s1, rf["feat_s1"][0]) < 4e-2
+    assert _rel(s0, rf["feat_s0"][0]) < 4e-2
+    assert ((feat - rf["feat"][0]).abs().mean() / rf["feat"][0].abs().mean()).item() < 1e-2
+    # batched encode == per-frame encode (frame-parallel encoder)
+    with torch.inference_mode():
+        one = eng.encode_frames(clip[1:2].cuda())
+    assert torch.equal(one["feat"][0], out["feat"][1])
+
+
+def test_memory_attention(setup):
+    eng, ref, clip, rf = setup
+    g = torch.Generator().manual_seed(3)
+    B = 2
+    mems = [(torch.randn((B, 64, 32, 32), generator=g) * 0.5).to(torch.bfloat16) for _ in range(3)]
+    tpos_rows = [6, 0, 1]
+    P = 3
+    ptr_list = [torch.randn((B, 256), generator=g) * 0.3 for _ in range(P)]
+    pos_list = [2, 1, 3]
+    from oracle.medsam2_ref import linear, sine_pos_1d
+
+    feat = rf["feat"].expand(B, -1, -1, -1)
+    curr = feat.flatten(2).permute(0, 2, 1)
+    curr_pos = rf["pos"].flatten(1).t()[None].expand(B, -1, -1)
+    mem_tok = [m.float().flatten(2).permute(0, 2, 1) for m in mems]
+    pos64 = ref.sine_pos(32, 32, 64).flatten(1).t()
+    tp = ref.p("maskmem_tpos_enc").reshape(7, 64)
+    mem_pos = [pos64[None] + tp[r][None, None] for r in tpos_rows]
+    ptrs = torch.stack(ptr_list, dim=1).reshape(B, P * 4, 64)
+    ppe = linear(sine_pos_1d(torch.tensor(pos_list, dtype=torch.float32) / 15, 256), ref.p("obj_ptr_tpos_proj.weight"),
+                 ref.p("obj_ptr_tpos_proj.bias")).repeat_interleave(4, dim=0)
+    memory = torch.cat(mem_tok + [ptrs], dim=1)
+    memory_pos = torch.cat([p.expand(B, -1, -1) for p in mem_pos] + [ppe[None].expand(B, -1, -1)], dim=1)
+    with torch.inference_mode():
+        want = ref.memory_attention(curr, curr_pos, memory, memory_pos, P * 4)
+        pt, pp = eng.obj_ptr_tokens(pos_list, [p.cuda() for p in ptr_list], 16, B)
+        assert (pp.cpu() - ppe).abs().max().item() < 1e-4
+        frames = [m.cuda().permute(0, 2, 3, 1).reshape(B, 1024, 64).contiguous() for m in mems]
+        got = eng.memory_attention(rf["feat"][0].flatten(1).t().contiguous().cuda(), frames, tpos_rows, pt, pp, B)
+    got = got.cpu().view(B, 1024, 256)
+    assert _rel(got, want) < 4e-2, _rel(got, want)
+    assert ((got - want).abs().mean() / want.abs().mean()).item() < 6e-3
+
+
+def test_sam_heads_fp32(setup):
+    eng, ref, clip, rf = setup
+    B = 2
+    g = torch.Generator().manual_seed(4)
+    pix = rf["feat"].expand(B, -1, -1, -1) + torch.randn((B, 256, 32, 32), generator=g) * 0.1
+    with torch.inference_mode():
+        want = ref.sam_heads(pix, rf["feat_s0"].expand(B, -1, -1, -1), rf["feat_s1"].expand(B, -1, -1, -1),
+                             multimask_output=True)
+        s0 = rf["feat_s0"][0].flatten(1).t().contiguous().cuda()
+        s1 = rf["feat_s1"][0].flatten(1).t().contiguous().cuda()
+        got = eng.sam_heads(pix.flatten(2).permute(0, 2, 1).reshape(B * 1024, 256).contiguous().cuda(), s0, s1, B,
+                            eng.no_point_tokens(B), multimask=True)
+    assert (got["low"].cpu() - want["low"]).abs().max().item() < 2e-4
+    assert (got["obj_ptr"].cpu() - want["obj_ptr"]).abs().max().item() < 2e-4
+    assert (got["score"].cpu() - want["score"]).abs().max().item() < 2e-4
+    assert (got["ious_all"].cpu()[:, 1:] - want["ious"]).abs().max().item() < 2e-4
+    # point prompt + dense mask prompt path, single-mask output with stability fallback
+    pts = dict(point_coords=torch.tensor([[[256.0, 250.0], [100.0, 400.0]]]).expand(B, -1, -1),
+               point_labels=torch.tensor([[1, 0]], dtype=torch.int32).expand(B, -1))
+    prev = torch.randn((B, 1, 128, 128), generator=g)
+    with torch.inference_mode():
+        want = ref.sam_heads(pix, rf["feat_s0"].expand(B, -1, -1, -1), rf["feat_s1"].expand(B, -1, -1, -1),
+                             point_inputs=pts, mask_inputs=prev, multimask_output=False)
+        sparse = eng.embed_points(pts["point_coords"], pts["point_labels"])
+        dense = eng.embed_mask_prompt(prev.cuda(), B)
+        got = eng.sam_heads(pix.flatten(2).permute(0, 2, 1).reshape(B * 1024, 256).contiguous().cuda(), s0, s1, B,
+                            sparse, dense=dense, multimask=False)
+    assert (got["low"].cpu() - want["low"]).abs().max().item() < 3e-4
+    assert (got["obj_ptr"].cpu() - want["obj_ptr"]).abs().max().item() < 3e-4
+
+
+def test_mask_as_output_and_memory_encoder(setup):
+    eng, ref, clip, rf = setup
+    B = 1
+    m = synth.box_mask()[None, None].float()
+    with torch.inference_mode():
+        want = ref.mask_as_output(rf["feat"], rf["feat_s0"], rf["feat_s1"], m)
+        f = rf["feat"][0].flatten(1).t().contiguous().cuda()
+        s0 = rf["feat_s0"][0].flatten(1).t().contiguous().cuda()
+        s1 = rf["feat_s1"][0].flatten(1).t().contiguous().cuda()
+        got = eng.mask_as_output(f, s0, s1, m.cuda(), B)
+    assert (got["low"].cpu() - want["low"]).abs().max().item() < 1e-4
+    assert (got["obj_ptr"].cpu() - want["obj_ptr"]).abs().max().item() < 3e-4
+    assert float(got["score"]) == 10.0
+    g = torch.Generator().manual_seed(6)
+    low = torch.randn((2, 1, 128, 128), generator=g) * 0.5
+    score = torch.tensor([[0.2], [-0.3]])
+    with torch.inference_mode():
+        high = torch.nn.functional.interpolate(low, size=(512, 512), mode="bilinear", align_corners=False)
+        want = ref.encode_memory(rf["feat"].expand(2, -1, -1, -1), high, score, False)
+        mi = eng.mem_mask_input(low.cuda(), False)
+        got = eng.encode_memory(f.to(torch.bfloat16), mi, score.cuda(), 2)
+    got = got.float().cpu().view(2, 32, 32, 64).permute(0, 3, 1, 2)
+    assert _rel(got, want) < 3e-2, _rel(got, want)

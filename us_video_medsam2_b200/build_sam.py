@@ -1,0 +1,121 @@
+"""Builders with the reference's signatures (sam2/build_sam.py:95-173), without Hydra.
+
+`config_file` is accepted as the reference spells it ("configs/sam2.1_hiera_t512.yaml"); only its basename
+selects the architecture.  `hydra_overrides_extra` entries of the form "++model.<key>=<value>" are applied to
+the model keyword arguments the same way the reference's Hydra overrides would be.
+"""
+import logging
+import os
+
+import torch
+import yaml
+
+from .predictor import SAM2VideoPredictor, SAM2VideoPredictorNPZ
+
+_CONFIG_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "configs")
+
+# flags of the flat YAML that select code paths this build implements (all fixed by the shipped config)
+_REQUIRED_TRUE = ("use_mask_input_as_output_without_sam", "directly_add_no_mem_embed", "no_obj_embed_spatial",
+                  "use_high_res_features_in_sam", "multimask_output_in_sam", "iou_prediction_use_sigmoid",
+                  "use_obj_ptrs_in_encoder", "add_tpos_enc_to_obj_ptrs", "proj_tpos_enc_in_obj_ptrs",
+                  "use_signed_tpos_enc_to_obj_ptrs", "only_obj_ptrs_in_the_past_for_eval", "pred_obj_scores",
+                  "pred_obj_scores_mlp", "fixed_no_obj_ptr", "use_multimask_token_for_obj_ptr",
+                  "use_mlp_for_obj_ptr_proj")
+
+
+def get_best_available_device():
+    """CUDA or nothing: this path has no CPU / MPS implementation (reference: build_sam.py:50-60)."""
+    if torch.cuda.is_available():
+        return "cuda"
+    raise RuntimeError("us_video_medsam2_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _parse_value(text):
+    low = text.strip().lower()
+    if low in ("true", "false"):
+        return low == "true"
+    try:
+        return int(text)
+    except ValueError:
+        try:
+            return float(text)
+        except ValueError:
+            return text
+
+
+def _load_model_kwargs(config_file, overrides):
+    name = os.path.basename(str(config_file))
+    path = os.path.join(_CONFIG_DIR, name)
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"unknown config {config_file!r}: this build ships {os.listdir(_CONFIG_DIR)}")
+    cfg = yaml.safe_load(open(path))["model"]
+    for flag in _REQUIRED_TRUE:
+        if not cfg.get(flag, False):
+            raise NotImplementedError(f"config flag {flag}=false selects a code path outside this build")
+    kwargs = {k: v for k, v in cfg.items() if not isinstance(v, dict) and k not in _REQUIRED_TRUE
+              and k not in ("backbone_stride",)}
+    for ov in overrides:
+        key, _, val = ov.lstrip("+").partition("=")
+        parts = key.split(".")
+        if parts[0] != "model" or len(parts) < 2:
+            continue
+        if parts[1] == "_target_":
+            continue
+        if parts[1] == "sam_mask_decoder_extra_args" and len(parts) == 3:
+            kwargs.setdefault("sam_mask_decoder_extra_args", {})[parts[2]] = _parse_value(val)
+        elif len(parts) == 2:
+            kwargs[parts[1]] = _parse_value(val)
+    return kwargs
+
+
+_POSTPROCESSING_OVERRIDES = [
+    "++model.sam_mask_decoder_extra_args.dynamic_multimask_via_stability=true",
+    "++model.sam_mask_decoder_extra_args.dynamic_multimask_stability_delta=0.05",
+    "++model.sam_mask_decoder_extra_args.dynamic_multimask_stability_thresh=0.98",
+    "++model.binarize_mask_from_pts_for_mem_enc=true",
+    "++model.fill_hole_area=8",
+]
+
+
+def _build(cls, config_file, ckpt_path, device, mode, hydra_overrides_extra, apply_postprocessing, **kwargs):
+    device = device or get_best_available_device()
+    logging.info(f"Using device: {device}")
+    overrides = list(hydra_overrides_extra)
+    if apply_postprocessing:
+        overrides = _POSTPROCESSING_OVERRIDES + overrides
+    model_kwargs = _load_model_kwargs(config_file, overrides)
+    model_kwargs.update(kwargs)
+    model = cls(**model_kwargs)
+    _load_checkpoint(model, ckpt_path)
+    model = model.to(device)
+    if mode == "eval":
+        model.eval()
+    return model
+
+
+def build_sam2_video_predictor(config_file, ckpt_path=None, device=None, mode="eval", hydra_overrides_extra=[],
+                               apply_postprocessing=True, **kwargs):
+    """reference: sam2/build_sam.py:95-133"""
+    return _build(SAM2VideoPredictor, config_file, ckpt_path, device, mode, hydra_overrides_extra,
+                  apply_postprocessing, **kwargs)
+
+
+def build_sam2_video_predictor_npz(config_file, ckpt_path=None, device=None, mode="eval", hydra_overrides_extra=[],
+                                   apply_postprocessing=True, **kwargs):
+    """reference: sam2/build_sam.py:135-173"""
+    return _build(SAM2VideoPredictorNPZ, config_file, ckpt_path, device, mode, hydra_overrides_extra,
+                  apply_postprocessing, **kwargs)
+
+
+def _load_checkpoint(model, ckpt_path):
+    """Strict load of ckpt["model"] (reference: build_sam.py:197-207)."""
+    if ckpt_path is not None:
+        sd = torch.load(ckpt_path, map_location="cpu", weights_only=True)["model"]
+        missing_keys, unexpected_keys = model.load_state_dict(sd)
+        if missing_keys:
+            logging.error(missing_keys)
+            raise RuntimeError()
+        if unexpected_keys:
+            logging.error(unexpected_keys)
+            raise RuntimeError()
+        logging.info("Loaded checkpoint sucessfully")

@@ -1,0 +1,255 @@
+// Connected components (8-connectivity) + fused small-hole filling.
+//
+// Replaces sam2._C.get_connected_componnets (reference: sam2/csrc/connected_components.cu:213-282,
+// 6 launches per image, global atomics, three zero-filled int32 scratch maps) and the elementwise
+// wrapper fill_holes_in_mask_scores (sam2/utils/misc.py:312-338).
+//
+// Result contract (bit-exact with the reference): for foreground pixel p
+//   labels[p] = 1 + min{ (r & ~1) * W + (c & ~1) : (r, c) foreground pixel of p's component }
+//   counts[p] = area of p's component;   both 0 on background.
+//
+// Hot-path shape is [B,1,128,128].  One CTA owns one image: the mask, the union-find parents of the
+// 2x2 blocks and the per-root areas all live in shared memory (48 KB at 128^2), so the whole op is one
+// launch for all images and touches HBM exactly once per input byte and once per output word.
+// Images whose block grid does not fit in shared memory take a batched global-memory path (5 launches
+// for all N).  HBM-bound: 1 B in + 8 B out per pixel (labelling) or 4 B in + 4 B out (hole filling).
+#include "common.cuh"
+#include "usvm2_b200.h"
+
+namespace {
+
+__device__ __forceinline__ int uf_find(const volatile int* par, int a) {
+  int p = par[a];
+  while (p != a) {
+    a = p;
+    p = par[a];
+  }
+  return a;
+}
+
+// lock-free union, links always point to the smaller index so the root is the component minimum
+__device__ __forceinline__ void uf_union(int* par, int a, int b) {
+  while (true) {
+    a = uf_find(par, a);
+    b = uf_find(par, b);
+    if (a == b) return;
+    if (a > b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(&par[b], a);  // b was a root when read; if it still is, it now points to a
+    if (old == b) return;
+    b = old;  // somebody re-linked b first: retry from its new parent
+  }
+}
+
+// Foreground test of the two input flavours.
+struct FgU8 {
+  const uint8_t* img;
+  __device__ __forceinline__ bool operator()(long long i) const { return img[i] != 0; }
+};
+struct FgScore {  // hole filling: "foreground" of the CC pass is the mask's background, score <= 0
+  const float* s;
+  __device__ __forceinline__ bool operator()(long long i) const { return s[i] <= 0.0f; }
+};
+
+// Merge rule of one 2x2 block with its TL / T / TR / L neighbour blocks (connected_components.cu:72-117):
+// `px(r,c)` must return false outside the image.
+template <typename PX, typename UN>
+__device__ __forceinline__ void merge_block(int r, int c, PX px, UN unite) {
+  const bool tl = px(r, c), tr = px(r, c + 1), bl = px(r + 1, c);
+  if (!(tl || tr || bl)) return;
+  if (tl && px(r - 1, c - 1)) unite(-1, -1);
+  if ((tl || tr) && (px(r - 1, c) || px(r - 1, c + 1))) unite(-1, 0);
+  if (tr && px(r - 1, c + 2)) unite(-1, 1);
+  if ((tl || bl) && (px(r, c - 1) || px(r + 1, c - 1))) unite(0, -1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory path: one CTA per image
+// ---------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(1024)
+cc_smem_kernel(const uint8_t* __restrict__ img, const float* scores_in, float* scores_out, int32_t* __restrict__ labels,
+               int32_t* __restrict__ counts, int H, int W, int max_area, float fill_value) {
+  extern __shared__ int s_mem[];
+  const int HB = H >> 1, WB = W >> 1, NB = HB * WB, HW = H * W;
+  int* s_par = s_mem;
+  int* s_area = s_mem + NB;
+  uint8_t* s_fg = reinterpret_cast<uint8_t*>(s_mem + 2 * NB);
+  const long long base = (long long)blockIdx.x * HW;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int i = tid; i < HW; i += nt) s_fg[i] = FILL ? (scores_in[base + i] <= 0.0f) : (img[base + i] != 0);
+  for (int b = tid; b < NB; b += nt) {
+    s_par[b] = b;
+    s_area[b] = 0;
+  }
+  __syncthreads();
+  auto px = [&](int r, int c) { return r >= 0 && r < H && c >= 0 && c < W && s_fg[r * W + c]; };
+  for (int b = tid; b < NB; b += nt) {
+    const int by = b / WB, bx = b - by * WB;
+    merge_block(2 * by, 2 * bx, px, [&](int dy, int dx) { uf_union(s_par, b, (by + dy) * WB + (bx + dx)); });
+  }
+  __syncthreads();
+  for (int b = tid; b < NB; b += nt) {
+    const int root = uf_find(s_par, b);
+    const int by = b / WB, bx = b - by * WB;
+    const int p = 2 * by * W + 2 * bx;
+    const int k = s_fg[p] + s_fg[p + 1] + s_fg[p + W] + s_fg[p + W + 1];
+    if (k) atomicAdd(&s_area[root], k);
+    // path compression is deferred to a private write: other threads may still be walking through b
+    // towards the root, and pointing b at the root keeps every chain valid
+    s_par[b] = root;
+  }
+  __syncthreads();
+  for (int i = tid; i < HW; i += nt) {
+    const int r = i / W, c = i - r * W;
+    const bool fg = s_fg[i];
+    const int root = s_par[(r >> 1) * WB + (c >> 1)];
+    if (FILL) {
+      const float v = scores_in[base + i];
+      scores_out[base + i] = (fg && s_area[root] <= max_area) ? fill_value : v;
+    } else {
+      const int ry = root / WB, rx = root - ry * WB;
+      labels[base + i] = fg ? (2 * ry * W + 2 * rx + 1) : 0;
+      counts[base + i] = fg ? s_area[root] : 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// global-memory path for large images (parents live in `labels` at the block anchors, areas in `counts`)
+// ---------------------------------------------------------------------------------------------
+template <typename FG>
+__global__ void cc_g_init(FG fg, int32_t* labels, int32_t* counts, int H, int W) {
+  const long long base = (long long)blockIdx.z * H * W;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+  if (2 * bx >= W || 2 * by >= H) return;
+  const int a = 2 * by * W + 2 * bx;
+  labels[base + a] = a;
+  counts[base + a] = 0;
+}
+template <typename FG>
+__global__ void cc_g_merge(FG fg, int32_t* labels, int H, int W) {
+  const long long base = (long long)blockIdx.z * H * W;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+  if (2 * bx >= W || 2 * by >= H) return;
+  const int r = 2 * by, c = 2 * bx, a = r * W + c;
+  int* par = labels + base;
+  auto px = [&](int rr, int cc) { return rr >= 0 && rr < H && cc >= 0 && cc < W && fg(base + (long long)rr * W + cc); };
+  merge_block(r, c, px, [&](int dy, int dx) { uf_union(par, a, a + 2 * dy * W + 2 * dx); });
+}
+template <typename FG>
+__global__ void cc_g_compress(FG fg, int32_t* labels, int32_t* counts, int H, int W) {
+  const long long base = (long long)blockIdx.z * H * W;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+  if (2 * bx >= W || 2 * by >= H) return;
+  const int a = 2 * by * W + 2 * bx;
+  const int root = uf_find(labels + base, a);
+  labels[base + a] = root;
+  const int k = (int)fg(base + a) + (int)fg(base + a + 1) + (int)fg(base + a + W) + (int)fg(base + a + W + 1);
+  if (k) atomicAdd(&counts[base + root], k);
+}
+// writes everything except the anchor slots of root blocks (they still hold parent / area for readers)
+template <typename FG, bool FILL>
+__global__ void cc_g_final(FG fg, int32_t* labels, int32_t* counts, const float* scores_in, float* scores_out, int H,
+                           int W, int max_area, float fill_value) {
+  const long long base = (long long)blockIdx.z * H * W;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+  if (2 * bx >= W || 2 * by >= H) return;
+  const int a = 2 * by * W + 2 * bx;
+  const int root = labels[base + a];
+  const int area = counts[base + root];
+#pragma unroll
+  for (int d = 3; d >= 0; --d) {
+    const int p = a + (d >> 1) * W + (d & 1);
+    if (d == 0 && root == a) break;  // root anchor: finalised by cc_g_roots
+    const bool f = fg(base + p);
+    if (FILL) {
+      scores_out[base + p] = (f && area <= max_area) ? fill_value : scores_in[base + p];
+    } else {
+      labels[base + p] = f ? root + 1 : 0;
+      counts[base + p] = f ? area : 0;
+    }
+  }
+}
+template <typename FG, bool FILL>
+__global__ void cc_g_roots(FG fg, int32_t* labels, int32_t* counts, const float* scores_in, float* scores_out, int H,
+                           int W, int max_area, float fill_value) {
+  const long long base = (long long)blockIdx.z * H * W;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+  if (2 * bx >= W || 2 * by >= H) return;
+  const int a = 2 * by * W + 2 * bx;
+  if (labels[base + a] != a) return;  // non-root anchors were rewritten to root + 1 (!= a) or 0 (a == 0 is a root)
+  const bool f = fg(base + a);
+  const int area = counts[base + a];
+  if (FILL) {
+    scores_out[base + a] = (f && area <= max_area) ? fill_value : scores_in[base + a];
+  } else {
+    labels[base + a] = f ? a + 1 : 0;
+    counts[base + a] = f ? area : 0;
+  }
+}
+
+size_t smem_bytes(int H, int W) { return (size_t)(H / 2) * (W / 2) * 8 + (size_t)H * W; }
+constexpr size_t kSmemLimit = 200 * 1024;
+
+template <bool FILL>
+int launch_smem(const uint8_t* img, const float* sin, float* sout, int32_t* labels, int32_t* counts, int N, int H,
+                int W, int max_area, float fill, cudaStream_t s) {
+  const size_t bytes = smem_bytes(H, W);
+  static size_t configured = 0;
+  if (bytes > 48 * 1024 && bytes > configured) {
+    if (cudaFuncSetAttribute(cc_smem_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) !=
+        cudaSuccess)
+      return USVM_ERR_CUDA;
+    configured = kSmemLimit;
+  }
+  const int threads = (H * W >= 1024 * 4) ? 1024 : 256;
+  cc_smem_kernel<FILL><<<N, threads, bytes, s>>>(img, sin, sout, labels, counts, H, W, max_area, fill);
+  return usvm_check_launch();
+}
+
+template <typename FG, bool FILL>
+int launch_global(FG fg, int32_t* labels, int32_t* counts, const float* sin, float* sout, int N, int H, int W,
+                  int max_area, float fill, cudaStream_t s) {
+  dim3 block(32, 8);
+  dim3 grid(cdiv(W / 2, 32), cdiv(H / 2, 8), N);
+  cc_g_init<<<grid, block, 0, s>>>(fg, labels, counts, H, W);
+  cc_g_merge<<<grid, block, 0, s>>>(fg, labels, H, W);
+  cc_g_compress<<<grid, block, 0, s>>>(fg, labels, counts, H, W);
+  cc_g_final<FG, FILL><<<grid, block, 0, s>>>(fg, labels, counts, sin, sout, H, W, max_area, fill);
+  cc_g_roots<FG, FILL><<<grid, block, 0, s>>>(fg, labels, counts, sin, sout, H, W, max_area, fill);
+  return usvm_check_launch();
+}
+
+}  // namespace
+
+extern "C" int usvm_cc2d_label_u8(const uint8_t* img, int32_t* labels, int32_t* counts, int N, int H, int W,
+                                  void* stream) {
+  if (N < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return USVM_ERR_ARG;
+  if (N == 0) return USVM_OK;
+  if (!img || !labels || !counts) return USVM_ERR_ARG;
+  if ((long long)H * W >= (1LL << 31) - 1 || N > 65535) return USVM_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (smem_bytes(H, W) <= kSmemLimit)
+    return launch_smem<false>(img, nullptr, nullptr, labels, counts, N, H, W, 0, 0.f, s);
+  return launch_global<FgU8, false>(FgU8{img}, labels, counts, nullptr, nullptr, N, H, W, 0, 0.f, s);
+}
+
+extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, int32_t* scratch_labels,
+                                   int32_t* scratch_counts, int N, int H, int W, int max_area, float fill_value,
+                                   void* stream) {
+  if (N < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || max_area <= 0) return USVM_ERR_ARG;
+  if (N == 0) return USVM_OK;
+  if (!scores_in || !scores_out) return USVM_ERR_ARG;
+  if ((long long)H * W >= (1LL << 31) - 1 || N > 65535) return USVM_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (smem_bytes(H, W) <= kSmemLimit)
+    return launch_smem<true>(nullptr, scores_in, scores_out, nullptr, nullptr, N, H, W, max_area, fill_value, s);
+  if (!scratch_labels || !scratch_counts) return USVM_ERR_ARG;  // the global path needs two int32 [N,H,W] maps
+  return launch_global<FgScore, true>(FgScore{scores_in}, scratch_labels, scratch_counts, scores_in, scores_out, N,
+                                      H, W, max_area, fill_value, s);
+}

@@ -1,0 +1,258 @@
+// Small-convolution, resize and memory-encoder bandwidth kernels (NHWC activations).
+//
+//   usvm_conv2d_small       direct k x k / stride s conv (+ LayerNorm2d + GELU), weights staged in shared
+//                           memory; covers MaskDownSampler's 3x3/s2 stages (memory_encoder.py:40-56),
+//                           PromptEncoder.mask_downscaling 2x2/s2 (prompt_encoder.py:57-66) and
+//                           SAM2Base.mask_downsample 4x4/s4 (sam2_base.py:863)
+//   usvm_im2col_nhwc        im2col for the one mask-downsampler stage big enough for the tensor cores
+//   usvm_dwconv7_ln         CXBlock depthwise 7x7 + LayerNorm2d (memory_encoder.py:104-108), bf16 out
+//   usvm_resize_bilinear    F.interpolate(bilinear, align_corners=False) with optional fused
+//                           sigmoid*scale+bias / binarise (sam2_base.py:1125-1131,1472-1484)
+//   usvm_resize_bilinear_aa antialiased bilinear (sam2_base.py:1079,1177; predictor :342)
+#include "common.cuh"
+#include "usvm2_b200.h"
+
+namespace {
+
+// one warp per output pixel, lanes over output channels (<= 64); weights [k*k*Cin][Cout] in smem
+__global__ void __launch_bounds__(256)
+conv2d_small_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
+                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int gelu,
+                    float* out_f32, bf16* out_bf16, int B, int H, int W, int Cin, int Cout, int k, int s, int pad,
+                    int Ho, int Wo) {
+  extern __shared__ float s_w[];
+  const int K = k * k * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) s_w[i] = wt[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)B * Ho * Wo;
+  for (long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); pix < total; pix += (long long)gridDim.x * 8) {
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+    float acc0 = 0.f, acc1 = 0.f;
+    const int c0 = lane, c1 = lane + 32;
+    for (int ky = 0; ky < k; ++ky) {
+      const int y = oy * s - pad + ky;
+      if (y < 0 || y >= H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int xx = ox * s - pad + kx;
+        if (xx < 0 || xx >= W) continue;
+        const float* xp = x + (((long long)b * H + y) * W + xx) * Cin;
+        const float* wp = s_w + (ky * k + kx) * Cin * Cout;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = xp[ci];
+          if (c0 < Cout) acc0 = fmaf(v, wp[ci * Cout + c0], acc0);
+          if (c1 < Cout) acc1 = fmaf(v, wp[ci * Cout + c1], acc1);
+        }
+      }
+    }
+    if (c0 < Cout) acc0 += bias[c0];
+    if (c1 < Cout) acc1 += bias[c1];
+    if (ln_w) {
+      const float sum = warp_sum((c0 < Cout ? acc0 : 0.f) + (c1 < Cout ? acc1 : 0.f));
+      const float mean = sum / Cout;
+      const float d0 = c0 < Cout ? acc0 - mean : 0.f, d1 = c1 < Cout ? acc1 - mean : 0.f;
+      const float var = warp_sum(d0 * d0 + d1 * d1) / Cout;
+      const float rstd = 1.0f / sqrtf(var + eps);
+      if (c0 < Cout) acc0 = d0 * rstd * ln_w[c0] + ln_b[c0];
+      if (c1 < Cout) acc1 = d1 * rstd * ln_w[c1] + ln_b[c1];
+    }
+    if (gelu) {
+      acc0 = gelu_erf(acc0);
+      acc1 = gelu_erf(acc1);
+    }
+    if (c0 < Cout) {
+      if (out_f32) out_f32[pix * Cout + c0] = acc0;
+      if (out_bf16) out_bf16[pix * Cout + c0] = __float2bfloat16(acc0);
+    }
+    if (c1 < Cout) {
+      if (out_f32) out_f32[pix * Cout + c1] = acc1;
+      if (out_bf16) out_bf16[pix * Cout + c1] = __float2bfloat16(acc1);
+    }
+  }
+}
+
+// A[pix, (ky*k + kx)*C + c] = x[b, oy*s - pad + ky, ox*s - pad + kx, c] (zero outside), bf16
+__global__ void im2col_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ A, int B, int H, int W, int C, int k,
+                                   int s, int pad, int Ho, int Wo) {
+  const int K = k * k * C;
+  const long long total = (long long)B * Ho * Wo * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % K);
+    const long long pix = i / K;
+    const int c = kk % C, tap = kk / C, ky = tap / k, kx = tap - ky * k;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+    const int y = oy * s - pad + ky, xx = ox * s - pad + kx;
+    float v = 0.f;
+    if (y >= 0 && y < H && xx >= 0 && xx < W) v = x[(((long long)b * H + y) * W + xx) * C + c];
+    A[i] = __float2bfloat16(v);
+  }
+}
+
+// depthwise 7x7 (pad 3) + LayerNorm over channels; one warp per pixel, C = 256 -> 8 channels per lane
+template <int CPL>
+__global__ void __launch_bounds__(256)
+dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [49][C] */, const float* __restrict__ bias,
+                  const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, bf16* __restrict__ out,
+                  int B, int H, int W) {
+  constexpr int C = CPL * 32;
+  const int lane = threadIdx.x & 31;
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pix >= (long long)B * H * W) return;
+  const int ox = (int)(pix % W), oy = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  float acc[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) acc[j] = bias[j * 32 + lane];
+  for (int ky = 0; ky < 7; ++ky) {
+    const int y = oy - 3 + ky;
+    if (y < 0 || y >= H) continue;
+    for (int kx = 0; kx < 7; ++kx) {
+      const int xx = ox - 3 + kx;
+      if (xx < 0 || xx >= W) continue;
+      const float* xp = x + (((long long)b * H + y) * W + xx) * C;
+      const float* wp = wt + (ky * 7 + kx) * C;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[j] = fmaf(xp[j * 32 + lane], wp[j * 32 + lane], acc[j]);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) s += acc[j];
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    acc[j] -= mean;
+    q = fmaf(acc[j], acc[j], q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = j * 32 + lane;
+    out[pix * C + c] = __float2bfloat16(acc[j] * rstd * ln_w[c] + ln_b[c]);
+  }
+}
+
+__device__ __forceinline__ float post_op(float v, int mode, float scale, float bias) {
+  if (mode == USVM_POST_SIGMOID_AFFINE) return (1.0f / (1.0f + expf(-v))) * scale + bias;
+  if (mode == USVM_POST_BINARIZE_AFFINE) return (v > 0.f ? 1.0f : 0.0f) * scale + bias;
+  return v;
+}
+
+// F.interpolate(mode="bilinear", align_corners=False); planes = N*C
+__global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int Hi,
+                                       int Wi, int Ho, int Wo, int mode, float pscale, float pbias) {
+  const float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
+  const long long total = planes * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+    const long long pl = i / ((long long)Wo * Ho);
+    float fy = sh * (oy + 0.5f) - 0.5f, fx = sw * (ox + 0.5f) - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = x + pl * Hi * Wi;
+    const float v = hy * (hx * p[(long long)y0 * Wi + x0] + lx * p[(long long)y0 * Wi + x1]) +
+                    ly * (hx * p[(long long)y1 * Wi + x0] + lx * p[(long long)y1 * Wi + x1]);
+    y[i] = post_op(v, mode, pscale, pbias);
+  }
+}
+
+// antialiased bilinear (triangle filter widened by the scale), ATen _upsample_bilinear2d_aa semantics
+__device__ __forceinline__ void aa_span(int o, float scale, int in_size, int& lo, int& size, float& center,
+                                        float& invscale) {
+  const float support = scale >= 1.f ? scale : 1.f;  // interp_size(2) * 0.5 * scale
+  invscale = scale >= 1.f ? 1.f / scale : 1.f;
+  center = scale * (o + 0.5f);
+  lo = max((int)(center - support + 0.5f), 0);
+  size = min((int)(center + support + 0.5f), in_size) - lo;
+}
+__global__ void resize_bilinear_aa_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int Hi,
+                                          int Wi, int Ho, int Wo, int binarize_half) {
+  const float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
+  const long long total = planes * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+    const long long pl = i / ((long long)Wo * Ho);
+    int ylo, ysz, xlo, xsz;
+    float yc, yinv, xc, xinv;
+    aa_span(oy, sh, Hi, ylo, ysz, yc, yinv);
+    aa_span(ox, sw, Wi, xlo, xsz, xc, xinv);
+    float wysum = 0.f, wxsum = 0.f;
+    for (int j = 0; j < ysz; ++j) wysum += fmaxf(0.f, 1.f - fabsf((j + ylo - yc + 0.5f) * yinv));
+    for (int j = 0; j < xsz; ++j) wxsum += fmaxf(0.f, 1.f - fabsf((j + xlo - xc + 0.5f) * xinv));
+    const float* p = x + pl * Hi * Wi;
+    // ATen resamples horizontally first, then vertically; accumulate in the same order
+    float acc = 0.f;
+    for (int jy = 0; jy < ysz; ++jy) {
+      const float wy = fmaxf(0.f, 1.f - fabsf((jy + ylo - yc + 0.5f) * yinv)) / wysum;
+      float row = 0.f;
+      for (int jx = 0; jx < xsz; ++jx) {
+        const float wx = fmaxf(0.f, 1.f - fabsf((jx + xlo - xc + 0.5f) * xinv)) / wxsum;
+        row = fmaf(wx, p[(long long)(ylo + jy) * Wi + xlo + jx], row);
+      }
+      acc = fmaf(wy, row, acc);
+    }
+    y[i] = binarize_half ? (acc >= 0.5f ? 1.f : 0.f) : acc;
+  }
+}
+
+inline int grid_for(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int usvm_conv2d_small(const float* x, const float* w_kkio, const float* bias, const float* ln_w,
+                                 const float* ln_b, float eps, int gelu, float* out_f32, void* out_bf16, int B, int H,
+                                 int W, int Cin, int Cout, int k, int stride, int pad, void* stream) {
+  if (!x || !w_kkio || !bias || (!out_f32 && !out_bf16) || Cout > 64 || Cout <= 0 || Cin <= 0) return USVM_ERR_ARG;
+  const size_t smem = (size_t)k * k * Cin * Cout * sizeof(float);
+  if (smem > 48 * 1024) return USVM_ERR_ARG;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const long long pixels = (long long)B * Ho * Wo;
+  const int grid = (int)min((long long)148 * 8, (pixels + 7) / 8);
+  conv2d_small_kernel<<<grid, 256, smem, STREAM>>>(x, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32,
+                                                   reinterpret_cast<bf16*>(out_bf16), B, H, W, Cin, Cout, k, stride,
+                                                   pad, Ho, Wo);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_im2col_nhwc(const float* x, void* A, int B, int H, int W, int C, int k, int stride, int pad,
+                                void* stream) {
+  if (!x || !A) return USVM_ERR_ARG;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  im2col_nhwc_kernel<<<grid_for((long long)B * Ho * Wo * k * k * C), 256, 0, STREAM>>>(
+      x, reinterpret_cast<bf16*>(A), B, H, W, C, k, stride, pad, Ho, Wo);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* bias, const float* ln_w,
+                               const float* ln_b, float eps, void* out_bf16, int B, int H, int W, int C,
+                               void* stream) {
+  if (!x || !w_49c || !bias || !ln_w || !ln_b || !out_bf16 || C != 256) return USVM_ERR_ARG;
+  dwconv7_ln_kernel<8><<<cdiv((long long)B * H * W, 8), 256, 0, STREAM>>>(x, w_49c, bias, ln_w, ln_b, eps,
+                                                                           reinterpret_cast<bf16*>(out_bf16), B, H, W);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_resize_bilinear(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo,
+                                    int post_mode, float post_scale, float post_bias, void* stream) {
+  if (!x || !y || planes <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return USVM_ERR_ARG;
+  resize_bilinear_kernel<<<grid_for(planes * Ho * Wo), 256, 0, STREAM>>>(x, y, planes, Hi, Wi, Ho, Wo, post_mode,
+                                                                         post_scale, post_bias);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_resize_bilinear_aa(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo,
+                                       int binarize_half, void* stream) {
+  if (!x || !y || planes <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return USVM_ERR_ARG;
+  resize_bilinear_aa_kernel<<<grid_for(planes * Ho * Wo), 256, 0, STREAM>>>(x, y, planes, Hi, Wi, Ho, Wo,
+                                                                            binarize_half);
+  return usvm_check_launch();
+}

@@ -1,0 +1,394 @@
+// Bandwidth kernels around the GEMM / attention tiles: normalisation, rotary encoding, window
+// (un)partition with Hiera's zero-pad and q-pool semantics, pooling, FPN top-down add, im2col for the
+// patch embedding, and memory-bank assembly.  All are coalesced over the channel (innermost) axis,
+// vectorised where the channel count allows, and sized by rows x channels so one launch covers every
+// frame / object in the batch.
+#include "common.cuh"
+#include "usvm2_b200.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the last axis (nn.LayerNorm, hieradet.py:101/124, memory_attention.py:42-44,
+// transformer.py norms): one warp per row, two-pass mean / variance in fp32.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
+                 float eps, int gelu, float* out_f32, int ldo_f32, bf16* out_bf16, int ldo_bf16, int rows, int C) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+  for (int c = lane; c < C; c += 32) {
+    float y = (xr[c] - mean) * rstd * w[c] + b[c];
+    if (gelu) y = gelu_erf(y);
+    if (out_f32) out_f32[row * ldo_f32 + c] = y;
+    if (out_bf16) out_bf16[row * ldo_bf16 + c] = __float2bfloat16(y);
+  }
+}
+
+// out[r, c] = alpha * x[r % x_mod, c] + beta * y[r % y_mod, c]   (fp32 in; fp32 and/or bf16 out)
+__global__ void axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, float beta,
+                                  int x_mod, int y_mod, float* out_f32, bf16* out_bf16, long long rows, int C) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    float v = alpha * x[(x_mod > 0 ? r % x_mod : r) * C + c];
+    if (y) v += beta * y[(y_mod > 0 ? r % y_mod : r) * C + c];
+    if (out_f32) out_f32[i] = v;
+    if (out_bf16) out_bf16[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Axial RoPE (position_encoding.py:174-221): rotate adjacent channel pairs of fp32 rows by the
+// (cos, sin) of token position (row_in_batch % table_rows); rows >= n_rope inside each batch of
+// rows_per_batch are copied unrotated (object-pointer tokens).  Output bf16 (attention operand).
+// ---------------------------------------------------------------------------------------------
+__global__ void rope_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ cs,
+                            const float* __restrict__ sn, bf16* __restrict__ out, int ldo, long long rows,
+                            int rows_per_batch, int n_rope, int table_rows, int half) {
+  const long long total = rows * half;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / half;
+    const int j = (int)(i - r * half);
+    const int rb = (int)(r % rows_per_batch);
+    const float2 v = *reinterpret_cast<const float2*>(x + r * ldx + 2 * j);
+    float a = v.x, b = v.y;
+    if (rb < n_rope) {
+      const int pos = rb % table_rows;
+      const float c = cs[pos * half + j], s = sn[pos * half + j];
+      a = v.x * c - v.y * s;
+      b = v.x * s + v.y * c;
+    }
+    *reinterpret_cast<uint32_t*>(out + r * ldo + 2 * j) = pack_bf16x2(a, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hiera window partition (backbones/utils.py:17-37) fused with the QKV split and the optional 2x2
+// q max-pool (hieradet.py:63-67).  Source: qkv bf16 [F, Hg, Wg, 3*C] in raster order.  Tokens that
+// fall in the zero padding carry qkv = bias (the reference pads *after* norm1, so the padded rows
+// enter the qkv Linear as zeros).  Destination: window-major Q [F*nW, nq, C], K/V [F*nW, nk, C].
+// ---------------------------------------------------------------------------------------------
+__global__ void window_gather_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
+                                     bf16* __restrict__ Qw, bf16* __restrict__ Kw, bf16* __restrict__ Vw, int F,
+                                     int Hg, int Wg, int ws, int pool, int C) {
+  const int nwx = (Wg + ws - 1) / ws, nwy = (Hg + ws - 1) / ws;
+  const int nk = ws * ws;
+  const int wq = pool ? ws / 2 : ws;
+  const int nq = wq * wq;
+  const int C8 = C / 8;
+  const long long per_win = (long long)(nq + 2 * nk) * C8;
+  const long long total = (long long)F * nwy * nwx * per_win;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long win = i / per_win;
+    long long rem = i - win * per_win;
+    const int f = (int)(win / (nwy * nwx));
+    const int wi = (int)(win - (long long)f * nwy * nwx);
+    const int wy = wi / nwx, wx = wi - wy * nwx;
+    const int c8 = (int)(rem % C8);
+    int tok = (int)(rem / C8);
+    int which;  // 0 q, 1 k, 2 v
+    if (tok < nq) which = 0;
+    else if (tok < nq + nk) { which = 1; tok -= nq; }
+    else { which = 2; tok -= nq + nk; }
+    auto fetch = [&](int ly, int lx, float (&o)[8]) {
+      const int y = wy * ws + ly, x = wx * ws + lx;
+      if (y < Hg && x < Wg) {
+        const uint4 u = *reinterpret_cast<const uint4*>(qkv + (((long long)f * Hg + y) * Wg + x) * 3 * C + which * C + c8 * 8);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __bfloat162float(__float2bfloat16(bias[which * C + c8 * 8 + e]));
+      }
+    };
+    float o[8];
+    if (which == 0 && pool) {
+      const int qy = tok / wq, qx = tok - qy * wq;
+      float t[8];
+      fetch(2 * qy, 2 * qx, o);
+      fetch(2 * qy, 2 * qx + 1, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], t[e]);
+      fetch(2 * qy + 1, 2 * qx, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], t[e]);
+      fetch(2 * qy + 1, 2 * qx + 1, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], t[e]);
+    } else {
+      const int w_ = which == 0 ? wq : ws;
+      const int ly = tok / w_, lx = tok - ly * w_;
+      fetch(ly, lx, o);
+    }
+    uint4 pk;
+    pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+    pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+    bf16* dst = which == 0 ? Qw + (win * nq + tok) * C : (which == 1 ? Kw : Vw) + (win * nk + tok) * C;
+    *reinterpret_cast<uint4*>(dst + c8 * 8) = pk;
+  }
+}
+
+// window_unpartition (backbones/utils.py:40-61): window-major [F*nW, wq*wq, C] -> raster [F, Ho, Wo, C]
+__global__ void window_scatter_kernel(const bf16* __restrict__ Ow, bf16* __restrict__ out, int F, int Ho, int Wo,
+                                      int wq, int C) {
+  const int nwx = (Wo + wq - 1) / wq, nwy = (Ho + wq - 1) / wq;
+  const int C8 = C / 8;
+  const long long total = (long long)F * Ho * Wo * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const long long tokid = i / C8;
+    const int x = (int)(tokid % Wo);
+    const int y = (int)((tokid / Wo) % Ho);
+    const int f = (int)(tokid / ((long long)Wo * Ho));
+    const int wy = y / wq, wx = x / wq;
+    const long long win = ((long long)f * nwy + wy) * nwx + wx;
+    const int tok = (y - wy * wq) * wq + (x - wx * wq);
+    *reinterpret_cast<uint4*>(out + tokid * C + c8 * 8) =
+        *reinterpret_cast<const uint4*>(Ow + (win * wq * wq + tok) * C + c8 * 8);
+  }
+}
+
+// 2x2 / stride-2 max pool on NHWC fp32 (do_pool on the projected shortcut, hieradet.py:139-140)
+__global__ void maxpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int F, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const long long total = (long long)F * Ho * Wo * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const long long t = i / C4;
+    const int ox = (int)(t % Wo), oy = (int)((t / Wo) % Ho), f = (int)(t / ((long long)Wo * Ho));
+    const float* p = x + (((long long)f * H + 2 * oy) * W + 2 * ox) * C + c4 * 4;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + C);
+    const float4 c = *reinterpret_cast<const float4*>(p + (long long)W * C), d = *reinterpret_cast<const float4*>(p + (long long)W * C + C);
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
+    m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+    m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+    m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+    *reinterpret_cast<float4*>(y + t * C + c4 * 4) = m;
+  }
+}
+
+// FPN top-down: fine[f,y,x,:] += coarse[f,y/2,x/2,:]  (nearest x2, image_encoder.py:116-126)
+__global__ void upsample2_add_kernel(float* __restrict__ fine, const float* __restrict__ coarse, bf16* fine_bf16,
+                                     int F, int H, int W, int C) {
+  const long long total = (long long)F * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int x = (int)(t % W), y = (int)((t / W) % H), f = (int)(t / ((long long)W * H));
+    const float v = fine[i] + coarse[(((long long)f * (H / 2) + y / 2) * (W / 2) + x / 2) * C + c];
+    fine[i] = v;
+    if (fine_bf16) fine_bf16[i] = __float2bfloat16(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col of the 7x7 / stride 4 / pad 3 patch embedding (backbones/utils.py:64-94):
+// img fp32 NCHW [F,3,S,S] -> A bf16 [F*(S/4)^2, KP], column k = c*49 + ky*7 + kx, zero beyond 147
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_patch_kernel(const float* __restrict__ img, bf16* __restrict__ A, int F, int S, int KP) {
+  const int G = S / 4;
+  const long long total = (long long)F * G * G * KP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % KP);
+    const long long t = i / KP;
+    float v = 0.f;
+    if (k < 147) {
+      const int ox = (int)(t % G), oy = (int)((t / G) % G), f = (int)(t / ((long long)G * G));
+      const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+      const int y = oy * 4 - 3 + ky, x = ox * 4 - 3 + kx;
+      if (y >= 0 && y < S && x >= 0 && x < S) v = img[(((long long)f * 3 + c) * S + y) * S + x];
+    }
+    A[i] = __float2bfloat16(v);
+  }
+}
+
+// uint8 grayscale [F,S,S] -> normalised fp32 [F,3,S,S] ((g/255 - mean_c)/std_c, misc.py:253-276)
+__global__ void normalize_gray_kernel(const uint8_t* __restrict__ g, float* __restrict__ out, long long frames_px,
+                                      long long px, float m0, float m1, float m2, float s0, float s1, float s2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < frames_px; i += (long long)gridDim.x * blockDim.x) {
+    const long long f = i / px, o = i - f * px;
+    const float v = (float)g[i] / 255.0f;
+    out[(f * 3 + 0) * px + o] = (v - m0) / s0;
+    out[(f * 3 + 1) * px + o] = (v - m1) / s1;
+    out[(f * 3 + 2) * px + o] = (v - m2) / s2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Memory-bank assembly (sam2_base.py:1344-1437): for every selected memory frame f (token-major bf16
+// [B, T, 64]) write  k_in = mem + pos + tpos[f]  and  v_in = mem  into the concatenated key/value
+// inputs [B, Nk, 64]; object-pointer tokens (fp32 [B, P, 64], pos [P, 64]) follow at row `ptr_row0`.
+// ---------------------------------------------------------------------------------------------
+__global__ void build_memory_kernel(const usvm_memory_frames fr, const float* __restrict__ pos,
+                                    const float* __restrict__ tpos, const float* __restrict__ ptrs,
+                                    const float* __restrict__ ptr_pos, bf16* __restrict__ k_in, bf16* __restrict__ v_in,
+                                    int B, int T, int Cm, int n_ptr_tokens, int Nk, int Nk_total, int row_offset) {
+  const int ptr_row0 = fr.count * T;
+  const long long total = (long long)B * Nk * Cm;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cm);
+    const long long t = i / Cm;
+    const int row = (int)(t % Nk);
+    const int b = (int)(t / Nk);
+    float m, pe;
+    if (row < ptr_row0) {
+      const int f = row / T, tok = row - f * T;
+      m = __bfloat162float(reinterpret_cast<const bf16*>(fr.mem[f])[((long long)b * T + tok) * Cm + c]);
+      pe = pos[tok * Cm + c] + tpos[fr.tpos_index[f] * Cm + c];
+    } else {
+      const int pr = row - ptr_row0;
+      m = ptrs[((long long)b * n_ptr_tokens + pr) * Cm + c];
+      pe = ptr_pos[pr * Cm + c];
+    }
+    const long long o = ((long long)b * Nk_total + row_offset + row) * Cm + c;
+    k_in[o] = __float2bfloat16(m + pe);
+    v_in[o] = __float2bfloat16(m);
+  }
+}
+
+// memory feature epilogue (sam2_base.py:1488-1496, predictor :956): add no_obj_embed_spatial where the object
+// score is <= 0, round to bf16 into the memory-bank slot
+__global__ void finalize_memory_kernel(const float* __restrict__ x, const float* __restrict__ score,
+                                       const float* __restrict__ no_obj_embed, bf16* __restrict__ mem, int B, int T,
+                                       int Cm) {
+  const long long total = (long long)B * T * Cm;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cm);
+    const int b = (int)(i / ((long long)T * Cm));
+    float v = x[i];
+    if (!(score[b] > 0.f)) v += no_obj_embed[c];
+    mem[i] = __float2bfloat16(v);
+  }
+}
+
+inline int grid_for(long long total, int threads = 256) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const float* b, float eps, int gelu,
+                              float* out_f32, int ldo_f32, void* out_bf16, int ldo_bf16, int rows, int C,
+                              void* stream) {
+  if (!x || !w || !b || rows <= 0 || C <= 0 || (!out_f32 && !out_bf16)) return USVM_ERR_ARG;
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, STREAM>>>(x, ldx, w, b, eps, gelu, out_f32, ldo_f32,
+                                                     reinterpret_cast<bf16*>(out_bf16), ldo_bf16, rows, C);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_axpby_rows(const float* x, const float* y, float alpha, float beta, int x_mod, int y_mod,
+                               float* out_f32, void* out_bf16, long long rows, int C, void* stream) {
+  if (!x || rows <= 0 || C <= 0) return USVM_ERR_ARG;
+  axpby_rows_kernel<<<grid_for(rows * C), 256, 0, STREAM>>>(x, y, alpha, beta, x_mod, y_mod, out_f32,
+                                                            reinterpret_cast<bf16*>(out_bf16), rows, C);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
+  if (!x || !y || n <= 0) return USVM_ERR_ARG;
+  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, STREAM>>>(x, reinterpret_cast<bf16*>(y), n);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_rope_bf16(const float* x, int ldx, const float* cos_t, const float* sin_t, void* out, int ldo,
+                              long long rows, int rows_per_batch, int n_rope, int table_rows, int dim,
+                              void* stream) {
+  if (!x || !cos_t || !sin_t || !out || rows <= 0 || (dim & 1) || (ldx & 1) || (ldo & 1)) return USVM_ERR_ARG;
+  rope_kernel<<<grid_for(rows * (dim / 2)), 256, 0, STREAM>>>(x, ldx, cos_t, sin_t, reinterpret_cast<bf16*>(out), ldo,
+                                                               rows, rows_per_batch, n_rope, table_rows, dim / 2);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_window_gather(const void* qkv, const float* qkv_bias, void* Qw, void* Kw, void* Vw, int F, int Hg,
+                                  int Wg, int ws, int pool, int C, void* stream) {
+  if (!qkv || !qkv_bias || !Qw || !Kw || !Vw || ws <= 0 || (C % 8) || (pool && (ws & 1))) return USVM_ERR_ARG;
+  const int nw = cdiv(Hg, ws) * cdiv(Wg, ws);
+  const int nq = pool ? (ws / 2) * (ws / 2) : ws * ws;
+  const long long total = (long long)F * nw * (nq + 2 * ws * ws) * (C / 8);
+  window_gather_kernel<<<grid_for(total), 256, 0, STREAM>>>(
+      reinterpret_cast<const bf16*>(qkv), qkv_bias, reinterpret_cast<bf16*>(Qw), reinterpret_cast<bf16*>(Kw),
+      reinterpret_cast<bf16*>(Vw), F, Hg, Wg, ws, pool, C);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_window_scatter(const void* Ow, void* out, int F, int Ho, int Wo, int wq, int C, void* stream) {
+  if (!Ow || !out || wq <= 0 || (C % 8)) return USVM_ERR_ARG;
+  window_scatter_kernel<<<grid_for((long long)F * Ho * Wo * (C / 8)), 256, 0, STREAM>>>(
+      reinterpret_cast<const bf16*>(Ow), reinterpret_cast<bf16*>(out), F, Ho, Wo, wq, C);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_maxpool2_nhwc(const float* x, float* y, int F, int H, int W, int C, void* stream) {
+  if (!x || !y || (H & 1) || (W & 1) || (C % 4)) return USVM_ERR_ARG;
+  maxpool2_nhwc_kernel<<<grid_for((long long)F * (H / 2) * (W / 2) * (C / 4)), 256, 0, STREAM>>>(x, y, F, H, W, C);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_upsample2_add(float* fine, const float* coarse, void* fine_bf16, int F, int H, int W, int C,
+                                  void* stream) {
+  if (!fine || !coarse || (H & 1) || (W & 1)) return USVM_ERR_ARG;
+  upsample2_add_kernel<<<grid_for((long long)F * H * W * C), 256, 0, STREAM>>>(
+      fine, coarse, reinterpret_cast<bf16*>(fine_bf16), F, H, W, C);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_im2col_patch(const float* img, void* A, int F, int S, int KP, void* stream) {
+  if (!img || !A || (S % 4) || KP < 147) return USVM_ERR_ARG;
+  im2col_patch_kernel<<<grid_for((long long)F * (S / 4) * (S / 4) * KP), 256, 0, STREAM>>>(
+      img, reinterpret_cast<bf16*>(A), F, S, KP);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_normalize_gray_u8(const uint8_t* gray, float* out, int F, int H, int W, const float* mean3,
+                                      const float* std3, void* stream) {
+  if (!gray || !out || !mean3 || !std3 || F <= 0) return USVM_ERR_ARG;
+  const long long px = (long long)H * W;
+  normalize_gray_kernel<<<grid_for(F * px), 256, 0, STREAM>>>(gray, out, F * px, px, mean3[0], mean3[1], mean3[2],
+                                                              std3[0], std3[1], std3[2]);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_build_memory(const usvm_memory_frames* frames, const float* pos, const float* tpos,
+                                 const float* ptrs, const float* ptr_pos, void* k_in, void* v_in, int B, int T,
+                                 int Cm, int n_ptr_tokens, int Nk_total, int row_offset, void* stream) {
+  if (!frames || frames->count < 0 || frames->count > USVM_MAX_MEMORY_FRAMES || !pos || !tpos || !k_in || !v_in)
+    return USVM_ERR_ARG;
+  if (n_ptr_tokens > 0 && (!ptrs || !ptr_pos)) return USVM_ERR_ARG;
+  const int Nk = frames->count * T + n_ptr_tokens;
+  if (Nk <= 0 || row_offset < 0 || row_offset + Nk > Nk_total) return USVM_ERR_ARG;
+  build_memory_kernel<<<grid_for((long long)B * Nk * Cm), 256, 0, STREAM>>>(
+      *frames, pos, tpos, ptrs, ptr_pos, reinterpret_cast<bf16*>(k_in), reinterpret_cast<bf16*>(v_in), B, T, Cm,
+      n_ptr_tokens, Nk, Nk_total, row_offset);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_finalize_memory(const float* x, const float* score, const float* no_obj_embed, void* mem_bf16,
+                                    int B, int T, int Cm, void* stream) {
+  if (!x || !score || !no_obj_embed || !mem_bf16 || B <= 0) return USVM_ERR_ARG;
+  finalize_memory_kernel<<<grid_for((long long)B * T * Cm), 256, 0, STREAM>>>(x, score, no_obj_embed,
+                                                                             reinterpret_cast<bf16*>(mem_bf16), B, T, Cm);
+  return usvm_check_launch();
+}

@@ -1,0 +1,274 @@
+// bf16 GEMM on the 5th-gen tensor cores:  C[M,N] = epilogue(A[M,K] * W[N,K]^T)
+//
+// Every Linear / 1x1 conv / im2col conv on the propagation path that is run in bf16 goes through
+// this kernel (reference call sites: hieradet.py:60,77,164 qkv/proj/mlp; image_encoder.py:114 FPN
+// laterals; memory_attention.py + sam/transformer.py:257-286 projections and FFN;
+// memory_encoder.py:104-117,170-176 pix_feat_proj / pwconv / out_proj).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D boxes {64 x 128} of A and {64 x BN} of W,
+//              128-byte swizzle, 4-stage mbarrier ring (zero fill beyond M / N / K edges)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16, fp32 accum in
+//              TMEM), tcgen05.commit releases smem stages and finally signals the epilogue
+//   warps 2-5: epilogue -- tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused
+//              bias / activation / per-column scale / residual, fp32 and/or bf16 stores
+#include "common.cuh"
+#include "usvm2_b200.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+};
+
+__host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == USVM_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == USVM_ACT_GELU) return gelu_erf(v);
+  return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const usvm_gemm_epilogue ep, const int M, const int N, const int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using L = SmemLayout<BN>;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x;
+  const int tile_n = blockIdx.y;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tc5_alloc(tmem_slot, tmem_cols(BN));
+  tc5_fence_before();
+  __syncthreads();
+  tc5_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + L::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tile_m * BM);
+        tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, tile_n * BN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc5_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + L::A_BYTES;
+        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          tc5_mma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc5_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+      }
+      tc5_commit(tmem_full_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: thread <-> accumulator row ----
+    mbar_wait(tmem_full_bar, 0);
+    tc5_fence_after();
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, 32*lane_grp + 32) are visible to this warp
+    const int row = tile_m * BM + lane_grp * 32 + lane;
+    const bool row_ok = row < M;
+    const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t acc[32];
+      tc5_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
+      tc5_wait_ld();
+      const int col0 = tile_n * BN + c0;
+      if (!row_ok || col0 >= N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      const int ncol = min(32, N - col0);
+      if (ncol == 32) {
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.act != USVM_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+        }
+        if (ep.col_scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(ep.col_scale + col0 + j);
+            v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
+          }
+        }
+        if (ep.residual) {
+          const float* r = ep.residual + rrow * ep.ldr + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(r + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (ep.out_f32) {
+          float* o = ep.out_f32 + (long long)row * ep.ldo_f32 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (ep.out_bf16) {
+          bf16* o = reinterpret_cast<bf16*>(ep.out_bf16) + (long long)row * ep.ldo_bf16 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 p;
+            p.x = pack_bf16x2(v[j], v[j + 1]);
+            p.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            p.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            p.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = p;
+          }
+        }
+      } else {
+        for (int j = 0; j < ncol; ++j) {
+          float x = v[j];
+          if (ep.bias) x += ep.bias[col0 + j];
+          x = apply_act(x, ep.act);
+          if (ep.col_scale) x *= ep.col_scale[col0 + j];
+          if (ep.residual) x += ep.residual[rrow * ep.ldr + col0 + j];
+          if (ep.out_f32) ep.out_f32[(long long)row * ep.ldo_f32 + col0 + j] = x;
+          if (ep.out_bf16)
+            reinterpret_cast<bf16*>(ep.out_bf16)[(long long)row * ep.ldo_bf16 + col0 + j] = __float2bfloat16(x);
+        }
+      }
+    }
+  }
+  tc5_fence_before();
+  __syncthreads();
+  if (warp == 1) tc5_dealloc(tmem_base, tmem_cols(BN));
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] with row pitch ld (elements); box = {64 cols, box_rows}
+int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return USVM_ERR_DRIVER;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? USVM_OK : USVM_ERR_DRIVER;
+}
+
+template <int BN>
+int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
+           cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc = make_map_bf16(&tmA, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map_bf16(&tmB, W, N, K, ldw, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SmemLayout<BN>::TOTAL) != cudaSuccess)
+      return USVM_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid(cdiv(M, BM), cdiv(N, BN));
+  gemm_bf16_tc5_kernel<BN><<<grid, GEMM_THREADS, SmemLayout<BN>::TOTAL, stream>>>(tmA, tmB, *ep, M, N, K);
+  return usvm_check_launch();
+}
+
+}  // namespace
+
+extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep,
+                                  int M, int N, int K, int block_n, void* stream) {
+  if (!A || !W || !ep || M <= 0 || N <= 0 || K <= 0) return USVM_ERR_ARG;
+  if ((lda % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return USVM_ERR_ARG;  // TMA: 16-byte aligned base and row pitch
+  if (ep->out_f32 && ((ep->ldo_f32 % 4) || (reinterpret_cast<uintptr_t>(ep->out_f32) & 15))) return USVM_ERR_ARG;
+  if (ep->out_bf16 && ((ep->ldo_bf16 % 8) || (reinterpret_cast<uintptr_t>(ep->out_bf16) & 15))) return USVM_ERR_ARG;
+  if (ep->residual && ((ep->ldr % 4) || (reinterpret_cast<uintptr_t>(ep->residual) & 15))) return USVM_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int bn = block_n;
+  if (bn <= 0) {
+    // latency-bound shapes dominate this path: prefer enough CTAs to cover the 148 SMs, then wider tiles
+    const int mt = cdiv(M, BM);
+    bn = 256;
+    while (bn > 32 && (long long)mt * cdiv(N, bn) < 148) bn >>= 1;
+    if (N <= 32) bn = 32;
+    else if (N <= 64 && bn > 64) bn = 64;
+    else if (N <= 128 && bn > 128) bn = 128;
+  }
+  switch (bn) {
+    case 32: return launch<32>(A, lda, W, ldw, ep, M, N, K, s);
+    case 64: return launch<64>(A, lda, W, ldw, ep, M, N, K, s);
+    case 128: return launch<128>(A, lda, W, ldw, ep, M, N, K, s);
+    case 256: return launch<256>(A, lda, W, ldw, ep, M, N, K, s);
+    default: return USVM_ERR_ARG;
+  }
+}

@@ -1,0 +1,488 @@
+"""Device-side model step of the propagation path, composed from the kernels in csrc/.
+
+Mirrors the reference's SAM2Base methods (sam2/modeling/sam2_base.py:764-1681) for the shipped
+configuration sam2.1_hiera_t512, but on packed weights and token-major activations:
+
+  forward_image            -> Engine.encode_frames      (Hiera trunk + FpnNeck + conv_s0/s1)
+  _prepare_memory_conditioned_features / MemoryAttention -> Engine.memory_attention
+  _forward_sam_heads / _use_mask_as_output               -> Engine.sam_heads / Engine.mask_as_output
+  _encode_new_memory / MemoryEncoder                     -> Engine.encode_memory
+
+Precision plan (calibrated with oracle.medsam2_ref.set_matmul_emulation): the image
+encoder, memory attention and memory encoder run their contractions on bf16 tensor cores with fp32
+accumulation, fp32 residual stream, fp32 LayerNorm / softmax statistics; the SAM mask decoder and
+everything after it (mask logits, IoU / object scores, object pointers) stays in fp32.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import ACT_GELU, ACT_RELU, BF16, F32
+
+NO_OBJ_SCORE = -1024.0
+
+
+class ModelConfig:
+    """Hyper-parameters of sam2/configs/sam2.1_hiera_t512.yaml (+ builder overrides, build_sam.py:108-122)."""
+    image_size = 512
+    embed_dim = 96
+    stages = (1, 2, 7, 2)
+    global_att_blocks = (5, 7, 9)
+    window_spec = (8, 4, 14, 7)
+    q_pool = 3
+    d_model = 256
+    mem_dim = 64
+    num_maskmem = 7
+    max_obj_ptrs_in_encoder = 16
+    max_cond_frames_in_attn = -1
+    memory_temporal_stride_for_eval = 1
+    sigmoid_scale_for_mem_enc = 20.0
+    sigmoid_bias_for_mem_enc = -10.0
+    multimask_output_in_sam = True
+    multimask_output_for_tracking = True
+    multimask_min_pt_num = 0
+    multimask_max_pt_num = 1
+    dynamic_multimask_via_stability = True
+    dynamic_multimask_stability_delta = 0.05
+    dynamic_multimask_stability_thresh = 0.98
+    binarize_mask_from_pts_for_mem_enc = True
+    non_overlap_masks_for_mem_enc = False
+    fill_hole_area = 8
+    feat = 32  # 512 / 16
+
+
+def hiera_plan(cfg=ModelConfig):
+    """(dim_in, dim_out, heads, window, pool, emit) per block; window size lags one stage
+    (hieradet.py:201-256)."""
+    ends = [sum(cfg.stages[:i]) - 1 for i in range(1, len(cfg.stages) + 1)]
+    pool_blocks = [e + 1 for e in ends[:-1]][: cfg.q_pool]
+    plan, dim, heads, stage = [], cfg.embed_dim, 1, 1
+    for i in range(sum(cfg.stages)):
+        window = 0 if i in cfg.global_att_blocks else cfg.window_spec[stage - 1]
+        dim_out = dim
+        if i - 1 in ends:
+            dim_out, heads, stage = dim * 2, heads * 2, stage + 1
+        plan.append((dim, dim_out, heads, window, i in pool_blocks, i in ends))
+        dim = dim_out
+    return plan
+
+
+# ------------------------------------------------------------------------------------------------
+# constant tables (computed once on the host at pack time)
+# ------------------------------------------------------------------------------------------------
+def _sine_pos_2d(h, w, feats, temperature=10000.0):
+    """PositionEmbeddingSine (position_encoding.py:79-112), token-major [h*w, feats]."""
+    half = feats // 2
+    y = torch.arange(1, h + 1, dtype=F32)
+    x = torch.arange(1, w + 1, dtype=F32)
+    y = y / (y[-1] + 1e-6) * (2 * math.pi)
+    x = x / (x[-1] + 1e-6) * (2 * math.pi)
+    dim_t = temperature ** (2 * torch.div(torch.arange(half, dtype=F32), 2, rounding_mode="floor") / half)
+    px, py = x[:, None] / dim_t, y[:, None] / dim_t
+    px = torch.stack((px[:, 0::2].sin(), px[:, 1::2].cos()), dim=2).flatten(1)
+    py = torch.stack((py[:, 0::2].sin(), py[:, 1::2].cos()), dim=2).flatten(1)
+    pos = torch.cat((py[:, None, :].expand(h, w, half), px[None, :, :].expand(h, w, half)), dim=2)
+    return pos.reshape(h * w, feats).contiguous()
+
+
+def _rope_tables(dim, end_x, end_y, theta=10000.0):
+    """compute_axial_cis (position_encoding.py:174-183) as cos / sin [end_x*end_y, dim/2]."""
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 4)[: dim // 4].float() / dim))
+    t = torch.arange(end_x * end_y, dtype=F32)
+    ang = torch.cat([torch.outer((t % end_x).float(), freqs),
+                     torch.outer(torch.div(t, end_x, rounding_mode="floor").float(), freqs)], dim=-1)
+    return torch.cos(ang).contiguous(), torch.sin(ang).contiguous()
+
+
+class PackedWeights:
+    """Reference state-dict tensors re-laid-out for the kernels (bf16 [N,K] GEMM weights, fused QKV,
+    conv weights as [k][k][Cin][Cout], ConvTranspose as pixel-shuffle GEMMs, constant tables)."""
+
+    def __init__(self, sd, device, cfg=ModelConfig):
+        self.cfg = cfg
+        self.device = device
+        g = lambda k: sd[k].detach().to(F32)
+        dev = lambda t, dt=F32: t.to(dtype=dt).contiguous().to(device)
+        w16 = lambda k: dev(g(k).reshape(g(k).shape[0], -1), BF16)
+        f32 = lambda k: dev(g(k))
+        self.plan = hiera_plan(cfg)
+
+        # ---- image encoder ----
+        t = "image_encoder.trunk."
+        pw = g(t + "patch_embed.proj.weight").reshape(96, 147)
+        self.patch_w = dev(F.pad(pw, (0, 13)), BF16)  # K 147 -> 160 (TMA row pitch must be 16 B aligned)
+        self.patch_b = f32(t + "patch_embed.proj.bias")
+        pe = F.interpolate(g(t + "pos_embed"), size=(128, 128), mode="bicubic")
+        win = g(t + "pos_embed_window")
+        pe = pe + win.tile(1, 1, 128 // win.shape[2], 128 // win.shape[3])
+        self.hiera_pos = dev(pe[0].permute(1, 2, 0).reshape(128 * 128, 96))
+        self.blocks = []
+        for i, (din, dout, heads, ws, pool, emit) in enumerate(self.plan):
+            p = t + f"blocks.{i}."
+            blk = dict(n1=(f32(p + "norm1.weight"), f32(p + "norm1.bias")),
+                       n2=(f32(p + "norm2.weight"), f32(p + "norm2.bias")),
+                       qkv_w=w16(p + "attn.qkv.weight"), qkv_b=f32(p + "attn.qkv.bias"),
+                       proj_w=w16(p + "attn.proj.weight"), proj_b=f32(p + "attn.proj.bias"),
+                       w1=w16(p + "mlp.layers.0.weight"), b1=f32(p + "mlp.layers.0.bias"),
+                       w2=w16(p + "mlp.layers.1.weight"), b2=f32(p + "mlp.layers.1.bias"))
+            if din != dout:
+                blk["sc_w"], blk["sc_b"] = w16(p + "proj.weight"), f32(p + "proj.bias")
+            self.blocks.append(blk)
+        n = "image_encoder.neck.convs."
+        self.neck = [(w16(n + f"{j}.conv.weight"), f32(n + f"{j}.conv.bias")) for j in range(4)]
+        d = "sam_mask_decoder."
+        self.conv_s0 = (w16(d + "conv_s0.weight"), f32(d + "conv_s0.bias"))
+        self.conv_s1 = (w16(d + "conv_s1.weight"), f32(d + "conv_s1.bias"))
+        self.feat_pos = dev(_sine_pos_2d(32, 32, 256))  # vision_pos_enc of the 32x32 level, [1024, 256]
+
+        # ---- memory attention ----
+        self.ma_layers = []
+        for l in range(4):
+            p = f"memory_attention.layers.{l}."
+            sa, ca = p + "self_attn.", p + "cross_attn_image."
+            self.ma_layers.append(dict(
+                n1=(f32(p + "norm1.weight"), f32(p + "norm1.bias")),
+                n2=(f32(p + "norm2.weight"), f32(p + "norm2.bias")),
+                n3=(f32(p + "norm3.weight"), f32(p + "norm3.bias")),
+                sa_qkv_w=dev(torch.cat([g(sa + "q_proj.weight"), g(sa + "k_proj.weight"), g(sa + "v_proj.weight")]), BF16),
+                sa_qkv_b=dev(torch.cat([g(sa + "q_proj.bias"), g(sa + "k_proj.bias"), g(sa + "v_proj.bias")])),
+                sa_o=(w16(sa + "out_proj.weight"), f32(sa + "out_proj.bias")),
+                ca_q=(w16(ca + "q_proj.weight"), f32(ca + "q_proj.bias")),
+                ca_k=(w16(ca + "k_proj.weight"), f32(ca + "k_proj.bias")),
+                ca_v=(w16(ca + "v_proj.weight"), f32(ca + "v_proj.bias")),
+                ca_o=(w16(ca + "out_proj.weight"), f32(ca + "out_proj.bias")),
+                l1=(w16(p + "linear1.weight"), f32(p + "linear1.bias")),
+                l2=(w16(p + "linear2.weight"), f32(p + "linear2.bias"))))
+        self.ma_norm = (f32("memory_attention.norm.weight"), f32("memory_attention.norm.bias"))
+        c, s = _rope_tables(256, 32, 32)
+        self.rope_cos, self.rope_sin = dev(c), dev(s)
+
+        # ---- memory encoder ----
+        e = "memory_encoder."
+        ds = e + "mask_downsampler.encoder."
+        kkio = lambda k: dev(g(k).permute(2, 3, 1, 0))  # [Cout,Cin,k,k] -> [k][k][Cin][Cout]
+        self.md_convs = [(kkio(ds + f"{3 * i}.weight"), f32(ds + f"{3 * i}.bias"),
+                          f32(ds + f"{3 * i + 1}.weight"), f32(ds + f"{3 * i + 1}.bias")) for i in range(3)]
+        self.md_conv3_w = dev(g(ds + "9.weight").permute(0, 2, 3, 1).reshape(256, 576), BF16)  # k = (ky,kx,ci)
+        self.md_conv3_b = f32(ds + "9.bias")
+        self.md_ln3 = (f32(ds + "10.weight"), f32(ds + "10.bias"))
+        self.md_out = (w16(ds + "12.weight"), f32(ds + "12.bias"))
+        self.pix_proj = (w16(e + "pix_feat_proj.weight"), f32(e + "pix_feat_proj.bias"))
+        self.fuser = []
+        for l in range(2):
+            p = e + f"fuser.layers.{l}."
+            self.fuser.append(dict(dw_w=dev(g(p + "dwconv.weight").reshape(256, 49).t()), dw_b=f32(p + "dwconv.bias"),
+                                   ln=(f32(p + "norm.weight"), f32(p + "norm.bias")),
+                                   pw1=(w16(p + "pwconv1.weight"), f32(p + "pwconv1.bias")),
+                                   pw2=(w16(p + "pwconv2.weight"), f32(p + "pwconv2.bias")),
+                                   gamma=f32(p + "gamma")))
+        self.mem_out = (w16(e + "out_proj.weight"), f32(e + "out_proj.bias"))
+        self.mem_pos = dev(_sine_pos_2d(32, 32, 64))  # [1024, 64]
+        self.maskmem_tpos = dev(g("maskmem_tpos_enc").reshape(cfg.num_maskmem, cfg.mem_dim))
+        self.no_obj_embed_spatial = dev(g("no_obj_embed_spatial").reshape(cfg.mem_dim))
+        self.no_mem_embed = dev(g("no_mem_embed").reshape(1, 256))
+        self.no_obj_ptr = dev(g("no_obj_ptr").reshape(256))
+        self.tpos_proj = (f32("obj_ptr_tpos_proj.weight"), f32("obj_ptr_tpos_proj.bias"))
+
+        # ---- prompt encoder ----
+        pe_ = "sam_prompt_encoder."
+        self.pe_gauss = f32(pe_ + "pe_layer.positional_encoding_gaussian_matrix")
+        self.point_table = dev(torch.cat([g(pe_ + f"point_embeddings.{j}.weight") for j in range(4)]
+                                         + [g(pe_ + "not_a_point_embed.weight")]))
+        self.no_mask_embed = dev(g(pe_ + "no_mask_embed.weight").reshape(1, 256))
+        c01 = (torch.arange(32, dtype=F32) + 0.5) / 32
+        grid = torch.stack([c01[None, :].expand(32, 32), c01[:, None].expand(32, 32)], dim=-1).reshape(1024, 2)
+        ang = 2 * math.pi * ((2 * grid - 1) @ g(pe_ + "pe_layer.positional_encoding_gaussian_matrix"))
+        self.dense_pe = dev(torch.cat([ang.sin(), ang.cos()], dim=-1))  # [1024, 256]
+        md = pe_ + "mask_downscaling."
+        self.pm_convs = [(kkio(md + "0.weight"), f32(md + "0.bias"), f32(md + "1.weight"), f32(md + "1.bias")),
+                         (kkio(md + "3.weight"), f32(md + "3.bias"), f32(md + "4.weight"), f32(md + "4.bias"))]
+        self.pm_out = (dev(g(md + "6.weight").reshape(256, 16)), f32(md + "6.bias"))
+        self.mask_downsample = (kkio("mask_downsample.weight"), f32("mask_downsample.bias"))
+
+        # ---- mask decoder (fp32) ----
+        tr = d + "transformer."
+        lin = lambda p: (f32(p + "weight"), f32(p + "bias"))
+
+        def attn(p):
+            return dict(q=lin(p + "q_proj."), k=lin(p + "k_proj."), v=lin(p + "v_proj."), o=lin(p + "out_proj."))
+
+        self.dec_layers = []
+        for l in range(2):
+            p = tr + f"layers.{l}."
+            sa = attn(p + "self_attn.")
+            sa["qkv_w"] = dev(torch.cat([g(p + "self_attn.q_proj.weight"), g(p + "self_attn.k_proj.weight"),
+                                         g(p + "self_attn.v_proj.weight")]))
+            sa["qkv_b"] = dev(torch.cat([g(p + "self_attn.q_proj.bias"), g(p + "self_attn.k_proj.bias"),
+                                         g(p + "self_attn.v_proj.bias")]))
+            self.dec_layers.append(dict(sa=sa, t2i=attn(p + "cross_attn_token_to_image."),
+                                        i2t=attn(p + "cross_attn_image_to_token."),
+                                        mlp=(lin(p + "mlp.layers.0."), lin(p + "mlp.layers.1.")),
+                                        norms=[lin(p + f"norm{j}.") for j in (1, 2, 3, 4)]))
+        self.dec_final = attn(tr + "final_attn_token_to_image.")
+        self.dec_final_norm = lin(tr + "norm_final_attn.")
+        self.out_tokens = dev(torch.cat([g(d + "obj_score_token.weight"), g(d + "iou_token.weight"),
+                                         g(d + "mask_tokens.weight")]))  # [6, 256]
+        up = d + "output_upscaling."
+        w = g(up + "0.weight")  # ConvTranspose2d [Cin=256, Cout=64, 2, 2] -> rows (dy, dx, co)
+        self.up1_w = dev(w.permute(2, 3, 1, 0).reshape(256, 256))
+        self.up1_b = dev(g(up + "0.bias").repeat(4))
+        self.up1_ln = lin(up + "1.")
+        w = g(up + "3.weight")  # [64, 32, 2, 2]
+        self.up2_w = dev(w.permute(2, 3, 1, 0).reshape(128, 64))
+        self.up2_b = dev(g(up + "3.bias").repeat(4))
+
+        def mlp3(prefixes):
+            return tuple(dev(torch.stack([g(p + f"layers.{j}.{kind}") for p in prefixes]))
+                         for j in range(3) for kind in ("weight", "bias"))
+
+        self.hyper = mlp3([d + f"output_hypernetworks_mlps.{j}." for j in range(4)])
+        self.iou_head = mlp3([d + "iou_prediction_head."])
+        self.score_head = mlp3([d + "pred_obj_score_head."])
+        self.obj_ptr_proj = mlp3(["obj_ptr_proj."])
+
+
+class Engine:
+    def __init__(self, weights: PackedWeights):
+        self.w = weights
+        self.cfg = weights.cfg
+        self.attn_splits = 8  # flash-decoding splits of the memory attention key range (fills the 148 SMs at B=1)
+
+    # ---------------------------------------------------------------- image encoder
+    def encode_frames(self, imgs):
+        """imgs fp32 [F,3,512,512] -> dict(feat [F,1024,256] fp32 (+ bf16 copy), feat_s1 [F,4096,64],
+        feat_s0 [F,16384,32]) -- Hiera.forward + FpnNeck.forward + forward_image
+        (hieradet.py:283-299, image_encoder.py:104-136, sam2_base.py:1220-1232)."""
+        w = self.w
+        Fr = imgs.shape[0]
+        A = ops.im2col_patch(imgs.contiguous())
+        x, _ = ops.gemm_bf16(A, w.patch_w, bias=w.patch_b, residual=w.hiera_pos, res_mod=128 * 128, f32=True)
+        H = W = 128
+        stage_out = []
+        for blk, (din, dout, heads, ws, pool, emit) in zip(w.blocks, w.plan):
+            _, h = ops.layernorm(x, *blk["n1"], 1e-6, bf16=True)
+            if din != dout:
+                sc, _ = ops.gemm_bf16(h, blk["sc_w"], bias=blk["sc_b"], f32=True)
+                shortcut = ops.maxpool2(sc, Fr, H, W, dout)
+            else:
+                shortcut = x
+            _, qkv = ops.gemm_bf16(h, blk["qkv_w"], bias=blk["qkv_b"], bf16=True)
+            Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+            if ws > 0:
+                Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout)
+                Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * dout, dout, 96),
+                              (0, nk * dout, dout, 96), (0, nk * dout, dout, 96))
+                att = ops.window_scatter(Ow, Fr, Ho, Wo, ws // 2 if pool else ws, dout)
+            else:
+                T = H * W
+                att = ops.fmha(qkv, qkv, qkv, Fr, heads, T, T, 96, (0, T * 3 * dout, 3 * dout, 96),
+                               (dout, T * 3 * dout, 3 * dout, 96), (2 * dout, T * 3 * dout, 3 * dout, 96))
+                att = att.reshape(Fr * T, dout)
+            H, W = Ho, Wo
+            x, _ = ops.gemm_bf16(att, blk["proj_w"], bias=blk["proj_b"], residual=shortcut, f32=True)
+            _, h2 = ops.layernorm(x, *blk["n2"], 1e-6, bf16=True)
+            _, m = ops.gemm_bf16(h2, blk["w1"], bias=blk["b1"], act=ACT_GELU, bf16=True)
+            x, xb = ops.gemm_bf16(m, blk["w2"], bias=blk["b2"], residual=x, f32=True, bf16=emit)
+            if emit:
+                stage_out.append(xb)
+        s0, s1, s2, s3 = stage_out  # 128^2x96, 64^2x192, 32^2x384, 16^2x768
+        lat3, _ = ops.gemm_bf16(s3, *self._wb(w.neck[0]), f32=True)
+        lat2, _ = ops.gemm_bf16(s2, *self._wb(w.neck[1]), f32=True)
+        lat2_b = ops.upsample2_add_(lat2, lat3, Fr, 32, 32, 256, bf16=True)
+        _, lat1_b = ops.gemm_bf16(s1, *self._wb(w.neck[2]), bf16=True)
+        _, lat0_b = ops.gemm_bf16(s0, *self._wb(w.neck[3]), bf16=True)
+        feat_s1, _ = ops.gemm_bf16(lat1_b, *self._wb(w.conv_s1), f32=True)
+        feat_s0, _ = ops.gemm_bf16(lat0_b, *self._wb(w.conv_s0), f32=True)
+        return dict(feat=lat2.view(Fr, 1024, 256), feat_bf16=lat2_b.view(Fr, 1024, 256),
+                    feat_s1=feat_s1.view(Fr, 4096, 64), feat_s0=feat_s0.view(Fr, 16384, 32))
+
+    @staticmethod
+    def _wb(pair):
+        return pair[0], pair[1]
+
+    # ---------------------------------------------------------------- memory attention
+    def memory_attention(self, feat, mem_frames, tpos_rows, ptrs, ptr_pos, B):
+        """feat fp32 [1024,256] (one frame, shared by the B objects); mem_frames: list of bf16 [B,1024,64];
+        ptrs fp32 [B,P*4,64] or None.  Returns fp32 [B*1024, 256]
+        (MemoryAttention.forward, memory_attention.py:119-169)."""
+        w = self.w
+        T = 1024
+        x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T)
+        k_in, v_in, Nk = ops.build_memory(mem_frames, tpos_rows, w.mem_pos, w.maskmem_tpos, ptrs, ptr_pos, B)
+        n_ptr = 0 if ptrs is None else ptrs.shape[1]
+        k_in2, v_in2 = k_in.view(B * Nk, 64), v_in.view(B * Nk, 64)
+        for L in w.ma_layers:
+            _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
+            qkv32, qkv16 = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], f32=True, bf16=True)
+            q = ops.rope(qkv32, 0, w.rope_cos, w.rope_sin, T, T)
+            k = ops.rope(qkv32, 256, w.rope_cos, w.rope_sin, T, T)
+            o = ops.fmha(q, k, qkv16, B, 1, T, T, 256, (0, T * 256, 256, 256), (0, T * 256, 256, 256),
+                         (512, T * 768, 768, 256), num_splits=self._splits(B, T))
+            x, _ = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True)
+            _, h = ops.layernorm(x, *L["n2"], 1e-5, bf16=True)
+            q32, _ = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], f32=True)
+            q = ops.rope(q32, 0, w.rope_cos, w.rope_sin, T, T)
+            k32, _ = ops.gemm_bf16(k_in2, L["ca_k"][0], bias=L["ca_k"][1], f32=True)
+            k = ops.rope(k32, 0, w.rope_cos, w.rope_sin, Nk, Nk - n_ptr)
+            _, v = ops.gemm_bf16(v_in2, L["ca_v"][0], bias=L["ca_v"][1], bf16=True)
+            o = ops.fmha(q, k, v, B, 1, T, Nk, 256, (0, T * 256, 256, 256), (0, Nk * 256, 256, 256),
+                         (0, Nk * 256, 256, 256), num_splits=self._splits(B, Nk))
+            x, _ = ops.gemm_bf16(o.view(B * T, 256), L["ca_o"][0], bias=L["ca_o"][1], residual=x, f32=True)
+            _, h = ops.layernorm(x, *L["n3"], 1e-5, bf16=True)
+            _, m = ops.gemm_bf16(h, L["l1"][0], bias=L["l1"][1], act=ACT_RELU, bf16=True)
+            x, _ = ops.gemm_bf16(m, L["l2"][0], bias=L["l2"][1], residual=x, f32=True)
+        out, _ = ops.layernorm(x, *w.ma_norm, 1e-5, f32=True)
+        return out
+
+    def _splits(self, B, Nk):
+        tiles = (Nk + 63) // 64
+        want = max(1, 148 // (16 * B))
+        return max(1, min(want, tiles))
+
+    # ---------------------------------------------------------------- SAM heads
+    def _dec_attn(self, A, q_in, k_in, v_in, B, Nq, Nk, dh):
+        q = ops.gemm_f32(q_in, *A["q"])
+        k = ops.gemm_f32(k_in, *A["k"])
+        v = ops.gemm_f32(v_in, *A["v"])
+        o = ops.attn_small(q, k, v, B, 8, Nq, Nk, dh)
+        return o
+
+    def sam_heads(self, pix_feat, feat_s0, feat_s1, B, sparse, dense=None, multimask=True, feat_shared=True):
+        """pix_feat fp32 [B*1024,256]; sparse fp32 [B,P,256] prompt tokens; dense fp32 [B*1024,256] or None
+        (-> no_mask_embed).  Returns dict(low [B,1,128,128], obj_ptr [B,256], score [B,1], iou [B,1]).
+        (_forward_sam_heads sam2_base.py:1010-1166 + MaskDecoder mask_decoder.py:110-295 +
+        TwoWayTransformer transformer.py:90-212)"""
+        w = self.w
+        T = 1024
+        if dense is None:
+            src, _ = ops.axpby(pix_feat, w.no_mask_embed, rows=B * T, y_mod=1)
+        else:
+            src, _ = ops.axpby(pix_feat, dense, rows=B * T)
+        P = sparse.shape[1]
+        Nt = 6 + P
+        tokens = torch.cat([w.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(B * Nt, 256).contiguous()
+        queries, keys = tokens, src
+        ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
+        for l, Lyr in enumerate(w.dec_layers):
+            sa = Lyr["sa"]
+            if l == 0:
+                qkv = ops.gemm_f32(queries, sa["qkv_w"], sa["qkv_b"])
+                o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
+                queries = ops.gemm_f32(o, *sa["o"])
+            else:
+                qpe, _ = ops.axpby(queries, tokens)
+                qk = ops.gemm_f32(qpe, sa["qkv_w"][:512], sa["qkv_b"][:512])
+                v = ops.gemm_f32(queries, *sa["v"])
+                o = ops.attn_small(qk[:, 0:256], qk[:, 256:512], v, B, 8, Nt, Nt, 32)
+                queries = ops.gemm_f32(o, *sa["o"], residual=queries)
+            queries = ln(queries, Lyr["norms"][0])
+            qpe, _ = ops.axpby(queries, tokens)
+            kpe, _ = ops.axpby(keys, w.dense_pe, rows=B * T, y_mod=T)
+            o = self._dec_attn(Lyr["t2i"], qpe, kpe, keys, B, Nt, T, 16)
+            queries = ln(ops.gemm_f32(o, *Lyr["t2i"]["o"], residual=queries), Lyr["norms"][1])
+            m = ops.gemm_f32(queries, *Lyr["mlp"][0], act=ACT_RELU)
+            queries = ln(ops.gemm_f32(m, *Lyr["mlp"][1], residual=queries), Lyr["norms"][2])
+            qpe, _ = ops.axpby(queries, tokens)
+            o = self._dec_attn(Lyr["i2t"], kpe, qpe, queries, B, T, Nt, 16)
+            keys = ln(ops.gemm_f32(o, *Lyr["i2t"]["o"], residual=keys), Lyr["norms"][3])
+        qpe, _ = ops.axpby(queries, tokens)
+        kpe, _ = ops.axpby(keys, w.dense_pe, rows=B * T, y_mod=T)
+        o = self._dec_attn(w.dec_final, qpe, kpe, keys, B, Nt, T, 16)
+        hs = ln(ops.gemm_f32(o, *w.dec_final["o"], residual=queries), w.dec_final_norm)  # [B*Nt, 256]
+
+        g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b)
+        u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_shared)
+        g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b)
+        base, row = hs.data_ptr(), Nt * 256
+        hyper = ops.small_mlp3(base + 4 * 2 * 256, row, 256, None, w.hyper, 32, B, 4, hs)
+        masks = ops.upscale2_masks(g2, feat_s0, hyper, B, 64, 64, feat_shared)
+        iou = ops.small_mlp3(base + 4 * 256, row, 256, None, w.iou_head, 4, B, 1, hs, sigmoid=True).view(B, 4)
+        score = ops.small_mlp3(base, row, 256, None, w.score_head, 1, B, 1, hs).view(B, 1)
+        low, idx, iou_sel = ops.sam_select(masks, iou, score, multimask, self.cfg.dynamic_multimask_stability_delta,
+                                           self.cfg.dynamic_multimask_stability_thresh, NO_OBJ_SCORE)
+        ptr = ops.small_mlp3(base + 4 * 2 * 256, row, 256, idx, w.obj_ptr_proj, 256, B, 1, hs).view(B, 256)
+        ops.objptr_mix_(ptr, score, w.no_obj_ptr)
+        return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, ious_all=iou)
+
+    def embed_points(self, coords, labels):
+        """PromptEncoder._embed_points with pad=True (prompt_encoder.py:79-103): coords [B,P,2] model pixels."""
+        B = coords.shape[0]
+        dev = self.w.device
+        c = torch.cat([coords.to(dev, F32) + 0.5, torch.zeros(B, 1, 2, device=dev)], dim=1).contiguous()
+        lab = torch.cat([labels.to(dev, torch.int32), -torch.ones(B, 1, dtype=torch.int32, device=dev)], dim=1)
+        return ops.point_embed(c, lab.contiguous(), self.w.pe_gauss, self.w.point_table, self.cfg.image_size)
+
+    def no_point_tokens(self, B):
+        """The two padding tokens used on tracked frames (label -1 point + pad): both not_a_point_embed."""
+        return self.w.point_table[4][None, None].expand(B, 2, 256)
+
+    def embed_mask_prompt(self, m128, B):
+        """PromptEncoder.mask_downscaling on a [B,1,128,128] dense prompt -> fp32 [B*1024, 256]."""
+        w = self.w
+        x = m128.reshape(B, 128, 128, 1).contiguous()
+        (w0, b0, lw0, lb0), (w1, b1, lw1, lb1) = w.pm_convs
+        x, H, W = ops.conv2d_small(x, w0, b0, B, 128, 128, 1, 4, 2, 2, 0, ln=(lw0, lb0), gelu=True)
+        x, H, W = ops.conv2d_small(x, w1, b1, B, H, W, 4, 16, 2, 2, 0, ln=(lw1, lb1), gelu=True)
+        return ops.gemm_f32(x, *w.pm_out)
+
+    def mask_as_output(self, feat, feat_s0, feat_s1, mask512, B):
+        """SAM2Base._use_mask_as_output (sam2_base.py:1168-1218); mask512 fp32 {0,1} [B,1,512,512]."""
+        w = self.w
+        high = mask512 * 20.0 - 10.0
+        low = ops.resize_bilinear_aa(high, 128, 128)
+        md, _, _ = ops.conv2d_small(mask512.reshape(B, 512, 512, 1).contiguous(), *w.mask_downsample, B, 512, 512, 1,
+                                    1, 4, 4, 0)
+        dense = self.embed_mask_prompt(md.view(B, 1, 128, 128), B)
+        pix, _ = ops.axpby(feat, None, rows=B * 1024, x_mod=1024)
+        o = self.sam_heads(pix, feat_s0, feat_s1, B, self.no_point_tokens(B), dense=dense, multimask=False)
+        present = (mask512.flatten(1) > 0).any(dim=1, keepdim=True)
+        score = present.to(F32) * 20.0 - 10.0
+        ptr = torch.where(present, o["obj_ptr"], w.no_obj_ptr[None].expand(B, -1))
+        return dict(low=low, high=high, obj_ptr=ptr, score=score)
+
+    # ---------------------------------------------------------------- memory encoder
+    def encode_memory(self, feat_bf16, mask_in512, score, B):
+        """mask_in512 fp32 [B,512,512]: already sigmoid*20-10 / binarised (see Engine.mem_mask_input);
+        feat_bf16 [1024,256] raw frame features.  Returns bf16 token-major memory [B,1024,64]
+        (_encode_new_memory sam2_base.py:1450-1498, MemoryEncoder memory_encoder.py:158-181)."""
+        w = self.w
+        x, H, W, Cin = mask_in512.reshape(B, 512, 512, 1), 512, 512, 1
+        for (cw, cb, lw, lb), Cout in zip(w.md_convs, (4, 16, 64)):
+            x, H, W = ops.conv2d_small(x, cw, cb, B, H, W, Cin, Cout, 3, 2, 1, ln=(lw, lb), gelu=True)
+            Cin = Cout
+        A4 = ops.im2col_nhwc(x, B, 64, 64, 64, 3, 2, 1)
+        c4, _ = ops.gemm_bf16(A4, w.md_conv3_w, bias=w.md_conv3_b, f32=True)
+        _, c4n = ops.layernorm(c4, *w.md_ln3, 1e-6, bf16=True, gelu=True)
+        pp, _ = ops.gemm_bf16(feat_bf16, *w.pix_proj, f32=True)  # pix_feat_proj, shared by all objects
+        x, _ = ops.gemm_bf16(c4n, w.md_out[0], bias=w.md_out[1], residual=pp, res_mod=1024, f32=True)
+        xb = None
+        for i, Lf in enumerate(w.fuser):
+            h = ops.dwconv7_ln(x, Lf["dw_w"], Lf["dw_b"], Lf["ln"][0], Lf["ln"][1], B, 32, 32)
+            _, t = ops.gemm_bf16(h, Lf["pw1"][0], bias=Lf["pw1"][1], act=ACT_GELU, bf16=True)
+            x, xb = ops.gemm_bf16(t, Lf["pw2"][0], bias=Lf["pw2"][1], col_scale=Lf["gamma"], residual=x, f32=True,
+                                  bf16=(i == len(w.fuser) - 1))
+        out, _ = ops.gemm_bf16(xb, w.mem_out[0], bias=w.mem_out[1], f32=True)
+        return ops.finalize_memory(out, score.reshape(B).contiguous(), w.no_obj_embed_spatial, B)
+
+    def mem_mask_input(self, masks, binarize):
+        """Upsample low-res logits [B,1,h,w] to 512^2 (if needed) fused with sigmoid*20-10 or (x>0)*20-10."""
+        cfg = self.cfg
+        post = ops.POST_BINARIZE_AFFINE if binarize else ops.POST_SIGMOID_AFFINE
+        return ops.resize_bilinear(masks, 512, 512, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)
+
+    # ---------------------------------------------------------------- object pointers
+    def obj_ptr_tokens(self, pos_list, ptr_list, max_ptrs, B):
+        """Object-pointer tokens + temporal pos enc (sam2_base.py:1361-1417).  ptr_list: fp32 [B,256] each.
+        Returns (ptrs fp32 [B, P*4, 64], ptr_pos fp32 [P*4, 64])."""
+        dev = self.w.device
+        P = len(pos_list)
+        ptrs = torch.stack(ptr_list, dim=1).reshape(B, P * 4, 64).contiguous()
+        rel = torch.tensor(pos_list, dtype=F32) / float(max_ptrs - 1)
+        pe_dim = 128
+        dim_t = 10000.0 ** (2 * torch.div(torch.arange(pe_dim, dtype=F32), 2, rounding_mode="floor") / pe_dim)
+        e = rel[:, None] / dim_t
+        tp = torch.cat([e.sin(), e.cos()], dim=-1).to(dev)  # get_1d_sine_pe (sam2_utils.py:64-74), [P, 256]
+        tp = ops.gemm_f32(tp.contiguous(), *self.w.tpos_proj)  # obj_ptr_tpos_proj, [P, 64]
+        return ptrs, tp.repeat_interleave(4, dim=0).contiguous()

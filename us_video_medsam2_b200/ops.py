@@ -1,0 +1,375 @@
+"""Thin torch-tensor wrappers over the C ABI (include/usvm2_b200.h).
+
+PyTorch is used for device memory and streams only: every function here takes CUDA tensors, passes
+raw pointers to a hand-written kernel on torch's current stream and returns tensors.  There is no
+fallback path: a non-CUDA tensor or a missing library raises.
+"""
+import ctypes as C
+import math
+import os
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, POST_BINARIZE_AFFINE, POST_NONE, POST_SIGMOID_AFFINE,  # noqa: F401
+                   FmhaParams, GemmEpilogue, MemoryFrames, call)
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+# bring-up switch: route the bf16 GEMMs through the SIMT kernel (still CUDA, still this library)
+_FORCE_SIMT = os.environ.get("USVM2_GEMM", "") == "simt"
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name):
+    if not (t.is_cuda and t.dtype == dtype):
+        raise TypeError(f"{name}: expected a CUDA {dtype} tensor, got {t.device} {t.dtype}")
+
+
+def empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16, like, out_f32, out_bf16):
+    ep = GemmEpilogue()
+    ep.bias, ep.col_scale = _ptr(bias), _ptr(col_scale)
+    ep.residual = _ptr(residual)
+    ep.ldr = residual.stride(0) if residual is not None else 0
+    ep.res_mod, ep.act = res_mod, act
+    if want_f32 and out_f32 is None:
+        out_f32 = empty((M, N), F32, like)
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = empty((M, N), BF16, like)
+    ep.out_f32, ep.ldo_f32 = _ptr(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
+    ep.out_bf16, ep.ldo_bf16 = _ptr(out_bf16), (out_bf16.stride(0) if out_bf16 is not None else 0)
+    return ep, out_f32, out_bf16
+
+
+def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, f32=False, bf16=False,
+              out_f32=None, out_bf16=None, block_n=0, simt=None):
+    """epi(a[M,K] @ w[N,K]^T) on the tcgen05 kernel; returns (fp32 out or None, bf16 out or None)."""
+    _chk(a, BF16, "a"), _chk(w, BF16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    ep, o32, o16 = _epilogue(M, N, bias, act, col_scale, residual, res_mod, f32 or out_f32 is not None,
+                             bf16 or out_bf16 is not None, a, out_f32, out_bf16)
+    if _FORCE_SIMT if simt is None else simt:
+        call("usvm_gemm_simt", a.data_ptr(), 1, a.stride(0), w.data_ptr(), 1, w.stride(0), C.byref(ep), M, N, K,
+             _stream())
+    else:
+        call("usvm_gemm_bf16_tc5", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), C.byref(ep), M, N, K,
+             block_n, _stream())
+    return o32, o16
+
+
+def gemm_f32(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, out=None):
+    """fp32 SIMT GEMM (decoder tail): epi(a[M,K] @ w[N,K]^T) -> fp32 [M,N]."""
+    _chk(a, F32, "a"), _chk(w, F32, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    ep, o32, _ = _epilogue(M, N, bias, act, col_scale, residual, res_mod, True, False, a, out, None)
+    call("usvm_gemm_simt", a.data_ptr(), 0, a.stride(0), w.data_ptr(), 0, w.stride(0), C.byref(ep), M, N, K,
+         _stream())
+    return o32
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_splits=1):
+    """q/k/v: bf16 tensors; *_addr = (element offset, batch stride, row stride, head stride).
+    Returns bf16 [B, Nq, H*head_dim]."""
+    for t in (q, k, v):
+        _chk(t, BF16, "qkv")
+    if out is None:
+        out = empty((B, Nq, H * head_dim), BF16, q)
+    p = FmhaParams()
+    p.q, p.k, p.v = q.data_ptr() + 2 * q_addr[0], k.data_ptr() + 2 * k_addr[0], v.data_ptr() + 2 * v_addr[0]
+    p.o = out.data_ptr()
+    p.q_bs, p.q_rs, p.q_hs = q_addr[1:]
+    p.k_bs, p.k_rs, p.k_hs = k_addr[1:]
+    p.v_bs, p.v_rs, p.v_hs = v_addr[1:]
+    p.o_bs, p.o_rs, p.o_hs = Nq * H * head_dim, H * head_dim, head_dim
+    p.B, p.H, p.Nq, p.Nk, p.head_dim = B, H, Nq, Nk, head_dim
+    num_splits = max(1, min(num_splits, (Nk + 63) // 64))
+    p.num_splits = num_splits
+    if num_splits > 1:
+        o_part = empty((num_splits, B * H, Nq, head_dim), F32, q)
+        ml_part = empty((num_splits, B * H, Nq, 2), F32, q)
+        p.o_part, p.ml_part = o_part.data_ptr(), ml_part.data_ptr()
+    p.scale = 1.0 / math.sqrt(head_dim)
+    call("usvm_fmha_bf16", C.byref(p), _stream())
+    return out
+
+
+def attn_small(q, k, v, B, H, Nq, Nk, head_dim):
+    """fp32 [B*Nq, H*dh] x [B*Nk, H*dh] -> fp32 [B*Nq, H*dh] (row strides taken from the tensors)."""
+    out = empty((B * Nq, H * head_dim), F32, q)
+    call("usvm_attn_small_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Nq, Nk, head_dim,
+         q.stride(0), k.stride(0), v.stride(0), out.stride(0), 1.0 / math.sqrt(head_dim), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation / layout
+# ------------------------------------------------------------------------------------------------
+def layernorm(x, w, b, eps, f32=False, bf16=False, gelu=False):
+    _chk(x, F32, "x")
+    rows, Cc = x.shape
+    o32 = empty((rows, Cc), F32, x) if f32 else None
+    o16 = empty((rows, Cc), BF16, x) if bf16 else None
+    call("usvm_layernorm", x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), eps, int(gelu), _ptr(o32), Cc,
+         _ptr(o16), Cc, rows, Cc, _stream())
+    return o32, o16
+
+
+def axpby(x, y, alpha=1.0, beta=1.0, rows=None, x_mod=0, y_mod=0, f32=True, bf16=False):
+    """alpha * x[r % x_mod] + beta * y[r % y_mod] over `rows` rows of C channels."""
+    Cc = x.shape[-1]
+    rows = rows if rows is not None else x.numel() // Cc
+    o32 = empty((rows, Cc), F32, x) if f32 else None
+    o16 = empty((rows, Cc), BF16, x) if bf16 else None
+    call("usvm_axpby_rows", x.data_ptr(), _ptr(y), alpha, beta, x_mod, y_mod, _ptr(o32), _ptr(o16), rows, Cc,
+         _stream())
+    return o32, o16
+
+
+def cast_bf16(x):
+    out = empty(x.shape, BF16, x)
+    call("usvm_cast_f32_bf16", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def rope(x, col0, cos_t, sin_t, rows_per_batch, n_rope, dim=256):
+    """Rotate columns [col0, col0+dim) of fp32 x [rows, ld] -> bf16 [rows, dim]."""
+    rows = x.shape[0]
+    out = empty((rows, dim), BF16, x)
+    call("usvm_rope_bf16", x.data_ptr() + 4 * col0, x.stride(0), cos_t.data_ptr(), sin_t.data_ptr(), out.data_ptr(),
+         dim, rows, rows_per_batch, n_rope, cos_t.shape[0], dim, _stream())
+    return out
+
+
+def window_gather(qkv, qkv_bias, F, Hg, Wg, ws, pool, Cc):
+    nw = -(-Hg // ws) * -(-Wg // ws)
+    nk = ws * ws
+    nq = (ws // 2) ** 2 if pool else nk
+    Qw, Kw, Vw = (empty((F * nw, n, Cc), BF16, qkv) for n in (nq, nk, nk))
+    call("usvm_window_gather", qkv.data_ptr(), qkv_bias.data_ptr(), Qw.data_ptr(), Kw.data_ptr(), Vw.data_ptr(), F,
+         Hg, Wg, ws, int(pool), Cc, _stream())
+    return Qw, Kw, Vw, nw, nq, nk
+
+
+def window_scatter(Ow, F, Ho, Wo, wq, Cc):
+    out = empty((F * Ho * Wo, Cc), BF16, Ow)
+    call("usvm_window_scatter", Ow.data_ptr(), out.data_ptr(), F, Ho, Wo, wq, Cc, _stream())
+    return out
+
+
+def maxpool2(x, F, H, W, Cc):
+    out = empty((F * (H // 2) * (W // 2), Cc), F32, x)
+    call("usvm_maxpool2_nhwc", x.data_ptr(), out.data_ptr(), F, H, W, Cc, _stream())
+    return out
+
+
+def upsample2_add_(fine, coarse, F, H, W, Cc, bf16=False):
+    o16 = empty((F * H * W, Cc), BF16, fine) if bf16 else None
+    call("usvm_upsample2_add", fine.data_ptr(), coarse.data_ptr(), _ptr(o16), F, H, W, Cc, _stream())
+    return o16
+
+
+def im2col_patch(img, KP=160):
+    _chk(img, F32, "img")
+    F, _, S, _ = img.shape
+    assert img.is_contiguous()
+    A = empty((F * (S // 4) ** 2, KP), BF16, img)
+    call("usvm_im2col_patch", img.data_ptr(), A.data_ptr(), F, S, KP, _stream())
+    return A
+
+
+def normalize_gray_u8(gray, mean, std):
+    F, H, W = gray.shape
+    out = empty((F, 3, H, W), F32, gray)
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    call("usvm_normalize_gray_u8", gray.data_ptr(), out.data_ptr(), F, H, W, m, s, _stream())
+    return out
+
+
+def build_memory(frames, tpos_rows, pos, tpos, ptrs, ptr_pos, B, T=1024, Cm=64):
+    """frames: list of bf16 [B,T,Cm] tensors; returns (k_in, v_in) bf16 [B, Nk, Cm], Nk."""
+    n_ptr = 0 if ptrs is None else ptrs.shape[1]
+    Nk = len(frames) * T + n_ptr
+    k_in = empty((B, Nk, Cm), BF16, pos)
+    v_in = empty((B, Nk, Cm), BF16, pos)
+    off = 0
+    chunks = [frames[i:i + _lib.MAX_MEMORY_FRAMES] for i in range(0, len(frames), _lib.MAX_MEMORY_FRAMES)] or [[]]
+    done = 0
+    for ci, chunk in enumerate(chunks):
+        mf = MemoryFrames()
+        for i, f in enumerate(chunk):
+            _chk(f, BF16, "memory frame")
+            assert f.is_contiguous() and f.shape == (B, T, Cm)
+            mf.mem[i] = f.data_ptr()
+            mf.tpos_index[i] = tpos_rows[done + i]
+        mf.count = len(chunk)
+        last = ci == len(chunks) - 1
+        np_here = n_ptr if last else 0
+        if len(chunk) * T + np_here > 0:
+            call("usvm_build_memory", C.byref(mf), pos.data_ptr(), tpos.data_ptr(), _ptr(ptrs) if last else 0,
+                 _ptr(ptr_pos) if last else 0, k_in.data_ptr(), v_in.data_ptr(), B, T, Cm, np_here, Nk, off, _stream())
+        off += len(chunk) * T
+        done += len(chunk)
+    return k_in, v_in, Nk
+
+
+def finalize_memory(x, score, no_obj_embed, B, T=1024, Cm=64):
+    mem = empty((B, T, Cm), BF16, x)
+    call("usvm_finalize_memory", x.data_ptr(), score.data_ptr(), no_obj_embed.data_ptr(), mem.data_ptr(), B, T, Cm,
+         _stream())
+    return mem
+
+
+# ------------------------------------------------------------------------------------------------
+# convs / resize
+# ------------------------------------------------------------------------------------------------
+def conv2d_small(x, w_kkio, bias, B, H, W, Cin, Cout, k, stride, pad, ln=None, eps=1e-6, gelu=False, bf16=False):
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = empty((B * Ho * Wo, Cout), BF16 if bf16 else F32, x)
+    call("usvm_conv2d_small", x.data_ptr(), w_kkio.data_ptr(), bias.data_ptr(), _ptr(ln[0]) if ln else 0,
+         _ptr(ln[1]) if ln else 0, eps, int(gelu), 0 if bf16 else out.data_ptr(), out.data_ptr() if bf16 else 0, B, H,
+         W, Cin, Cout, k, stride, pad, _stream())
+    return out, Ho, Wo
+
+
+def im2col_nhwc(x, B, H, W, Cc, k, stride, pad):
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    A = empty((B * Ho * Wo, k * k * Cc), BF16, x)
+    call("usvm_im2col_nhwc", x.data_ptr(), A.data_ptr(), B, H, W, Cc, k, stride, pad, _stream())
+    return A
+
+
+def dwconv7_ln(x, w_49c, bias, ln_w, ln_b, B, H, W, Cc=256, eps=1e-6):
+    out = empty((B * H * W, Cc), BF16, x)
+    call("usvm_dwconv7_ln", x.data_ptr(), w_49c.data_ptr(), bias.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps,
+         out.data_ptr(), B, H, W, Cc, _stream())
+    return out
+
+
+def resize_bilinear(x, Ho, Wo, post=POST_NONE, scale=1.0, bias=0.0):
+    """x fp32 [..., Hi, Wi] -> [..., Ho, Wo] (align_corners=False)."""
+    _chk(x, F32, "x")
+    x = x.contiguous()
+    Hi, Wi = x.shape[-2:]
+    out = empty((*x.shape[:-2], Ho, Wo), F32, x)
+    call("usvm_resize_bilinear", x.data_ptr(), out.data_ptr(), x.numel() // (Hi * Wi), Hi, Wi, Ho, Wo, post, scale,
+         bias, _stream())
+    return out
+
+
+def resize_bilinear_aa(x, Ho, Wo, binarize_half=False):
+    _chk(x, F32, "x")
+    x = x.contiguous()
+    Hi, Wi = x.shape[-2:]
+    out = empty((*x.shape[:-2], Ho, Wo), F32, x)
+    call("usvm_resize_bilinear_aa", x.data_ptr(), out.data_ptr(), x.numel() // (Hi * Wi), Hi, Wi, Ho, Wo,
+         int(binarize_half), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder tail
+# ------------------------------------------------------------------------------------------------
+def upscale1_ln_gelu(g1, feat_s1, ln_w, ln_b, B, Hc, Wc, feat_shared, eps=1e-6):
+    out = empty((B * 4 * Hc * Wc, 64), F32, g1)
+    call("usvm_upscale1_ln_gelu", g1.data_ptr(), feat_s1.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps,
+         out.data_ptr(), B, Hc, Wc, 64, int(feat_shared), _stream())
+    return out
+
+
+def upscale2_masks(g2, feat_s0, hyper, B, Hc, Wc, feat_shared):
+    masks = empty((B, 4, 2 * Hc, 2 * Wc), F32, g2)
+    call("usvm_upscale2_masks", g2.data_ptr(), feat_s0.data_ptr(), hyper.data_ptr(), masks.data_ptr(), B, Hc, Wc,
+         int(feat_shared), _stream())
+    return masks
+
+
+def small_mlp3(x_ptr, x_row_stride, x_inst_stride, row_select, mlp, out_dim, rows, instances, like, sigmoid=False):
+    """mlp = (w1, b1, w2, b2, w3, b3) fp32 stacked over instances; returns fp32 [rows, instances, out_dim]."""
+    y = empty((rows, instances, out_dim), F32, like)
+    call("usvm_small_mlp3", x_ptr, x_row_stride, x_inst_stride, _ptr(row_select), *(t.data_ptr() for t in mlp),
+         out_dim, int(sigmoid), y.data_ptr(), instances * out_dim, out_dim, rows, instances, _stream())
+    return y
+
+
+def sam_select(masks, iou, score, multimask, delta, thresh, no_obj_score):
+    B, _, H, W = masks.shape
+    low = empty((B, 1, H, W), F32, masks)
+    idx = empty((B,), torch.int32, masks)
+    iou_sel = empty((B, 1), F32, masks)
+    call("usvm_sam_select", masks.data_ptr(), iou.data_ptr(), score.data_ptr(), int(multimask), delta, thresh,
+         no_obj_score, low.data_ptr(), idx.data_ptr(), iou_sel.data_ptr(), B, H * W, _stream())
+    return low, idx, iou_sel
+
+
+def objptr_mix_(ptr, score, no_obj_ptr):
+    call("usvm_objptr_mix", ptr.data_ptr(), score.data_ptr(), no_obj_ptr.data_ptr(), ptr.shape[0], ptr.shape[1],
+         _stream())
+    return ptr
+
+
+def point_embed(coords, labels, gauss, table, image_size):
+    n = coords.shape[0] * coords.shape[1]
+    out = empty((*coords.shape[:2], 256), F32, coords)
+    call("usvm_point_embed", coords.data_ptr(), labels.data_ptr(), gauss.data_ptr(), table.data_ptr(),
+         float(image_size), out.data_ptr(), n, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# connected components / hole filling
+# ------------------------------------------------------------------------------------------------
+def connected_components(mask_u8):
+    """uint8 CUDA [N,1,H,W] -> (labels int32, counts int32), the sam2._C contract."""
+    if not mask_u8.is_cuda:
+        raise RuntimeError("inputs must be a CUDA tensor")
+    if mask_u8.dim() != 4 or mask_u8.shape[1] != 1:
+        raise RuntimeError("inputs must be [N, 1, H, W] shape")
+    if mask_u8.dtype != torch.uint8:
+        raise RuntimeError("inputs must be a uint8 type")
+    N, _, H, W = mask_u8.shape
+    if H % 2 or W % 2:
+        raise RuntimeError("height and width must be even numbers")
+    mask_u8 = mask_u8.contiguous()
+    labels = torch.empty((N, 1, H, W), dtype=torch.int32, device=mask_u8.device)
+    counts = torch.empty_like(labels)
+    if N:
+        call("usvm_cc2d_label_u8", mask_u8.data_ptr(), labels.data_ptr(), counts.data_ptr(), N, H, W, _stream())
+    return labels, counts
+
+
+def fill_holes(scores, max_area, fill_value=0.1):
+    """Fused fill_holes_in_mask_scores: fp32 CUDA [N,1,H,W] -> new tensor."""
+    _chk(scores, F32, "scores")
+    scores = scores.contiguous()
+    N, _, H, W = scores.shape
+    out = torch.empty_like(scores)
+    sl = sc = None
+    if (H // 2) * (W // 2) * 8 + H * W > 200 * 1024:
+        sl = torch.empty((N, H, W), dtype=torch.int32, device=scores.device)
+        sc = torch.empty_like(sl)
+    call("usvm_fill_holes_f32", scores.data_ptr(), out.data_ptr(), _ptr(sl), _ptr(sc), N, H, W, int(max_area),
+         float(fill_value), _stream())
+    return out

@@ -1,0 +1,779 @@
+"""Drop-in mirror of the reference's video predictor API on the B200 kernel path.
+
+Same class / method names, argument meaning, return types, error behaviour and `inference_state`
+keys as sam2/sam2_video_predictor.py:18-1172 (and the NPZ variant sam2_video_predictor_npz.py:44-115),
+so a driver written against the reference (`init_state` / `add_new_mask` / `add_new_points_or_box` /
+`propagate_in_video` / `reset_state` / ...) runs unchanged.  The module holds the reference's
+state-dict ABI (471 tensors, state_dict_abi.json) as ordinary nn.Parameters, so `load_state_dict`,
+strict checkpoint loading, `.to(device)` and `.eval()` behave as on the reference; the compute is
+done by `engine.Engine` on weights re-packed for the kernels (re-packed lazily whenever the
+parameters change).  There is no CPU path: the model must live on a CUDA device.
+"""
+import os
+import warnings
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import ops, synth
+from .engine import NO_OBJ_SCORE, Engine, ModelConfig, PackedWeights
+
+try:  # progress bar like the reference (sam2_video_predictor.py:703); optional
+    from tqdm import tqdm as _tqdm
+except Exception:  # pragma: no cover
+    _tqdm = None
+
+
+def _progress(it, desc):
+    if _tqdm is None or os.environ.get("TQDM_DISABLE") == "1":
+        return it
+    return _tqdm(it, desc=desc)
+
+
+class _Node(nn.Module):
+    """Bare container used to rebuild the reference's module tree (names only, no forward)."""
+
+
+def _install_abi_parameters(root):
+    for name, shape in synth.state_dict_abi():
+        *path, leaf = name.split(".")
+        mod = root
+        for p in path:
+            if p not in mod._modules:
+                mod.add_module(p, _Node())
+            mod = mod._modules[p]
+        t = torch.zeros(shape, dtype=torch.float32)
+        if leaf == "positional_encoding_gaussian_matrix":
+            mod.register_buffer(leaf, t)
+        else:
+            mod.register_parameter(leaf, nn.Parameter(t, requires_grad=False))
+
+
+class SAM2VideoPredictor(nn.Module):
+    """The predictor class to handle user interactions and manage inference states."""
+
+    def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
+                 clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False,
+                 encoder_batch=1, **model_kwargs):
+        super().__init__()
+        cfg = type("Cfg", (ModelConfig,), {})
+        for k, v in model_kwargs.items():
+            if k in ("image_encoder", "memory_attention", "memory_encoder", "sam_mask_decoder_extra_args",
+                     "compile_image_encoder"):
+                continue  # architecture blocks are validated by build_sam; decoder args handled below
+            if hasattr(cfg, k):
+                setattr(cfg, k, v)
+        extra = model_kwargs.get("sam_mask_decoder_extra_args") or {}
+        cfg.dynamic_multimask_via_stability = bool(extra.get("dynamic_multimask_via_stability", False))
+        cfg.dynamic_multimask_stability_delta = float(extra.get("dynamic_multimask_stability_delta", 0.05))
+        cfg.dynamic_multimask_stability_thresh = float(extra.get("dynamic_multimask_stability_thresh", 0.98))
+        cfg.fill_hole_area = fill_hole_area
+        self.cfg = cfg
+        self.image_size = cfg.image_size
+        self.num_maskmem = cfg.num_maskmem
+        self.hidden_dim = cfg.d_model
+        self.mem_dim = cfg.mem_dim
+        self.fill_hole_area = fill_hole_area
+        self.non_overlap_masks = non_overlap_masks
+        self.non_overlap_masks_for_mem_enc = cfg.non_overlap_masks_for_mem_enc
+        self.clear_non_cond_mem_around_input = clear_non_cond_mem_around_input
+        self.clear_non_cond_mem_for_multi_obj = clear_non_cond_mem_for_multi_obj
+        self.add_all_frames_to_correct_as_cond = add_all_frames_to_correct_as_cond
+        self.memory_temporal_stride_for_eval = cfg.memory_temporal_stride_for_eval
+        # frames encoded per image-encoder launch group (frame-parallel encoder); 1 = reference order
+        self.encoder_batch = max(1, int(encoder_batch))
+        _install_abi_parameters(self)
+        self._engine = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------ module plumbing
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("Please use the corresponding methods in SAM2VideoPredictor for inference")
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters()) + (str(self.device),)
+
+    def _sync_engine(self):
+        """(Re)pack the kernel weights if the parameters changed (load_state_dict / .to()); called once per
+        public API call so the per-frame loop never pays for the check."""
+        if self.device.type != "cuda":
+            raise RuntimeError("us_video_medsam2_b200 has no CPU path: move the predictor to a CUDA device "
+                               "(the kernels target sm_100a)")
+        key = self._weights_key()
+        if self._engine is None or key != self._engine_key:
+            sd = {k: v for k, v in self.state_dict().items()}
+            self._engine = Engine(PackedWeights(sd, self.device, self.cfg))
+            self._engine_key = key
+        return self._engine
+
+    def engine(self):
+        return self._engine if self._engine is not None else self._sync_engine()
+
+    @classmethod
+    def from_pretrained(cls, model_id, **kwargs):
+        raise RuntimeError("from_pretrained needs network access to the Hugging Face hub, which this build does "
+                           "not use; build with build_sam2_video_predictor(config, ckpt_path) instead")
+
+    # ------------------------------------------------------------------ session state
+    @torch.inference_mode()
+    def init_state(self, video_path, offload_video_to_cpu=False, offload_state_to_cpu=False,
+                   async_loading_frames=False):
+        """Initialize an inference state from a JPEG folder (reference :44-111)."""
+        from .frames import load_video_frames
+
+        images, vh, vw = load_video_frames(video_path, self.image_size, offload_video_to_cpu, self.device)
+        return self._new_state(images, vh, vw, offload_video_to_cpu, offload_state_to_cpu)
+
+    def _new_state(self, images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu):
+        if offload_state_to_cpu:
+            raise NotImplementedError("offload_state_to_cpu: the memory bank is kept resident in HBM on this path")
+        self._sync_engine()
+        dev = self.device
+        st = {}
+        st["images"] = images
+        st["num_frames"] = len(images)
+        st["offload_video_to_cpu"] = offload_video_to_cpu
+        st["offload_state_to_cpu"] = offload_state_to_cpu
+        st["video_height"] = video_height
+        st["video_width"] = video_width
+        st["device"] = dev
+        st["storage_device"] = dev
+        st["point_inputs_per_obj"] = {}
+        st["mask_inputs_per_obj"] = {}
+        st["cached_features"] = {}
+        st["constants"] = {}
+        st["obj_id_to_idx"] = OrderedDict()
+        st["obj_idx_to_id"] = OrderedDict()
+        st["obj_ids"] = []
+        st["output_dict"] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+        st["output_dict_per_obj"] = {}
+        st["temp_output_dict_per_obj"] = {}
+        st["consolidated_frame_inds"] = {"cond_frame_outputs": set(), "non_cond_frame_outputs": set()}
+        st["tracking_has_started"] = False
+        st["frames_already_tracked"] = {}
+        self._get_image_feature(st, 0)  # warm up + cache frame 0 like the reference (:110)
+        return st
+
+    def _obj_id_to_idx(self, st, obj_id):
+        idx = st["obj_id_to_idx"].get(obj_id, None)
+        if idx is not None:
+            return idx
+        if st["tracking_has_started"]:
+            raise RuntimeError(f"Cannot add new object id {obj_id} after tracking starts. "
+                               f"All existing object ids: {st['obj_ids']}. "
+                               f"Please call 'reset_state' to restart from scratch.")
+        idx = len(st["obj_id_to_idx"])
+        st["obj_id_to_idx"][obj_id] = idx
+        st["obj_idx_to_id"][idx] = obj_id
+        st["obj_ids"] = list(st["obj_id_to_idx"])
+        st["point_inputs_per_obj"][idx] = {}
+        st["mask_inputs_per_obj"][idx] = {}
+        st["output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+        st["temp_output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+        return idx
+
+    def _obj_idx_to_id(self, st, obj_idx):
+        return st["obj_idx_to_id"][obj_idx]
+
+    def _get_obj_num(self, st):
+        return len(st["obj_idx_to_id"])
+
+    # ------------------------------------------------------------------ image features
+    def _get_image_feature(self, st, frame_idx, lookahead=None):
+        """Per-frame backbone features (reference :879-910).  On a miss, `encoder_batch` consecutive frames in
+        the tracking direction are encoded in one batched pass (the image encoder is frame-independent)."""
+        cache = st["cached_features"]
+        hit = cache.get(frame_idx)
+        if hit is not None:
+            return hit
+        eng = self.engine()
+        step = lookahead if lookahead is not None else 0
+        n = self.encoder_batch if step != 0 else 1
+        idxs = [frame_idx + i * step for i in range(n)] if step != 0 else [frame_idx]
+        idxs = [t for t in idxs if 0 <= t < st["num_frames"]]
+        imgs = torch.stack([self._frame(st, t) for t in idxs]).contiguous()
+        out = eng.encode_frames(imgs)
+        keep = dict(cache) if len(cache) < 4 * self.encoder_batch else {}
+        for j, t in enumerate(idxs):
+            keep[t] = {k: v[j] for k, v in out.items()}
+        st["cached_features"] = keep
+        return keep[frame_idx]
+
+    def _frame(self, st, t):
+        img = st["images"][t]
+        return img.to(self.device, non_blocking=True).float()
+
+    # ------------------------------------------------------------------ prompts
+    @torch.inference_mode()
+    def add_new_points_or_box(self, inference_state, frame_idx, obj_id, points=None, labels=None,
+                              clear_old_points=True, normalize_coords=True, box=None):
+        """Add new points (and/or a box) to a frame (reference :173-314)."""
+        st = inference_state
+        self._sync_engine()
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        if (points is not None) != (labels is not None):
+            raise ValueError("points and labels must be provided together")
+        if points is None and box is None:
+            raise ValueError("at least one of points or box must be provided as input")
+        if points is None:
+            points = torch.zeros(0, 2, dtype=torch.float32)
+        elif not isinstance(points, torch.Tensor):
+            points = torch.tensor(points, dtype=torch.float32)
+        if labels is None:
+            labels = torch.zeros(0, dtype=torch.int32)
+        elif not isinstance(labels, torch.Tensor):
+            labels = torch.tensor(labels, dtype=torch.int32)
+        points = points.reshape(1, -1, 2).float().cpu()
+        labels = labels.reshape(1, -1).to(torch.int32).cpu()
+        if box is not None:
+            if not clear_old_points:
+                raise ValueError("cannot add box without clearing old points, since box prompt must be provided "
+                                 "before any point prompt (please use clear_old_points=True instead)")
+            if st["tracking_has_started"]:
+                warnings.warn("You are adding a box after tracking starts. SAM 2 may not always be able to "
+                              "incorporate a box prompt for *refinement*. If you intend to use box prompt as an "
+                              "*initial* input before tracking, please call 'reset_state' on the inference state "
+                              "to restart from scratch.", category=UserWarning, stacklevel=2)
+            box = torch.as_tensor(box, dtype=torch.float32).cpu().reshape(1, 2, 2)
+            points = torch.cat([box, points], dim=1)
+            labels = torch.cat([torch.tensor([[2, 3]], dtype=torch.int32), labels], dim=1)
+        if normalize_coords:
+            points = points / torch.tensor([st["video_width"], st["video_height"]], dtype=torch.float32)
+        points = (points * self.image_size).to(self.device)
+        labels = labels.to(self.device)
+        old = None if clear_old_points else st["point_inputs_per_obj"][obj_idx].get(frame_idx, None)
+        if old is not None:
+            points = torch.cat([old["point_coords"], points], dim=1)
+            labels = torch.cat([old["point_labels"], labels], dim=1)
+        point_inputs = {"point_coords": points, "point_labels": labels}
+        st["point_inputs_per_obj"][obj_idx][frame_idx] = point_inputs
+        st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+
+        is_init_cond_frame = frame_idx not in st["frames_already_tracked"]
+        reverse = False if is_init_cond_frame else st["frames_already_tracked"][frame_idx]["reverse"]
+        obj_output_dict = st["output_dict_per_obj"][obj_idx]
+        obj_temp_output_dict = st["temp_output_dict_per_obj"][obj_idx]
+        is_cond = is_init_cond_frame or self.add_all_frames_to_correct_as_cond
+        storage_key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+        prev_out = obj_temp_output_dict[storage_key].get(frame_idx)
+        if prev_out is None:
+            prev_out = obj_output_dict["cond_frame_outputs"].get(frame_idx)
+            if prev_out is None:
+                prev_out = obj_output_dict["non_cond_frame_outputs"].get(frame_idx)
+        prev_sam_mask_logits = None
+        if prev_out is not None and prev_out["pred_masks"] is not None:
+            prev_sam_mask_logits = torch.clamp(prev_out["pred_masks"].to(self.device), -32.0, 32.0)
+        current_out, _ = self._run_single_frame_inference(
+            st, obj_output_dict, frame_idx, 1, is_init_cond_frame, point_inputs, None, reverse,
+            run_mem_encoder=False, prev_sam_mask_logits=prev_sam_mask_logits)
+        obj_temp_output_dict[storage_key][frame_idx] = current_out
+        consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=False,
+                                                                consolidate_at_video_res=True)
+        _, video_res_masks = self._get_orig_video_res_output(st, consolidated["pred_masks_video_res"])
+        return frame_idx, st["obj_ids"], video_res_masks
+
+    def add_new_points(self, *args, **kwargs):
+        """Deprecated alias (reference :316-318)."""
+        return self.add_new_points_or_box(*args, **kwargs)
+
+    @torch.inference_mode()
+    def add_new_mask(self, inference_state, frame_idx, obj_id, mask):
+        """Add new mask to a frame (reference :321-402)."""
+        st = inference_state
+        self._sync_engine()
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        if not isinstance(mask, torch.Tensor):
+            mask = torch.tensor(mask, dtype=torch.bool)
+        assert mask.dim() == 2
+        mask_H, mask_W = mask.shape
+        m = mask[None, None].float().to(self.device)
+        if mask_H != self.image_size or mask_W != self.image_size:
+            m = ops.resize_bilinear_aa(m, self.image_size, self.image_size, binarize_half=True)
+        st["mask_inputs_per_obj"][obj_idx][frame_idx] = m
+        st["point_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        is_init_cond_frame = frame_idx not in st["frames_already_tracked"]
+        reverse = False if is_init_cond_frame else st["frames_already_tracked"][frame_idx]["reverse"]
+        obj_output_dict = st["output_dict_per_obj"][obj_idx]
+        obj_temp_output_dict = st["temp_output_dict_per_obj"][obj_idx]
+        is_cond = is_init_cond_frame or self.add_all_frames_to_correct_as_cond
+        storage_key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+        current_out, _ = self._run_single_frame_inference(
+            st, obj_output_dict, frame_idx, 1, is_init_cond_frame, None, m, reverse, run_mem_encoder=False)
+        obj_temp_output_dict[storage_key][frame_idx] = current_out
+        consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=False,
+                                                                consolidate_at_video_res=True)
+        _, video_res_masks = self._get_orig_video_res_output(st, consolidated["pred_masks_video_res"])
+        return frame_idx, st["obj_ids"], video_res_masks
+
+    # ------------------------------------------------------------------ outputs
+    def _get_orig_video_res_output(self, st, any_res_masks):
+        """Resize to the original video resolution (reference :404-424)."""
+        vh, vw = st["video_height"], st["video_width"]
+        any_res_masks = any_res_masks.to(self.device)
+        if tuple(any_res_masks.shape[-2:]) == (vh, vw):
+            video_res_masks = any_res_masks
+        else:
+            video_res_masks = ops.resize_bilinear(any_res_masks, vh, vw)
+        if self.non_overlap_masks:
+            video_res_masks = self._apply_non_overlapping_constraints(video_res_masks)
+        return any_res_masks, video_res_masks
+
+    @staticmethod
+    def _apply_non_overlapping_constraints(pred_masks):
+        """Keep only the highest-scoring object per pixel (sam2_base.py:1663-1681).  Optional post-step, off in
+        the shipped config; plain tensor ops (not on the per-frame hot path)."""
+        if pred_masks.size(0) == 1:
+            return pred_masks
+        winner = torch.argmax(pred_masks, dim=0, keepdim=True)
+        keep = winner == torch.arange(pred_masks.size(0), device=pred_masks.device)[:, None, None, None]
+        return torch.where(keep, pred_masks, torch.clamp(pred_masks, max=-10.0))
+
+    def _mem_view(self, mem_tok):
+        """token-major bf16 [B,1024,64] -> the reference's [B,64,32,32] layout (a view)."""
+        B = mem_tok.shape[0]
+        return mem_tok.view(B, 32, 32, self.mem_dim).permute(0, 3, 1, 2)
+
+    def _maskmem_pos_enc(self, st, B):
+        """Cached constant, expanded per object (reference :1016-1039)."""
+        c = st["constants"]
+        if "maskmem_pos_enc" not in c:
+            pos = self.engine().w.mem_pos.view(1, 32, 32, self.mem_dim).permute(0, 3, 1, 2)
+            c["maskmem_pos_enc"] = [pos]
+        return [x.expand(B, -1, -1, -1) for x in c["maskmem_pos_enc"]]
+
+    def _consolidate_temp_output_across_obj(self, st, frame_idx, is_cond, run_mem_encoder,
+                                            consolidate_at_video_res=False):
+        """Merge per-object temporary outputs of a frame into one batched output (reference :426-554)."""
+        B = self._get_obj_num(st)
+        storage_key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+        if consolidate_at_video_res:
+            assert not run_mem_encoder, "memory encoder cannot run at video resolution"
+            ch, cw, mask_key = st["video_height"], st["video_width"], "pred_masks_video_res"
+        else:
+            ch = cw = self.image_size // 4
+            mask_key = "pred_masks"
+        dev = self.device
+        out = {"maskmem_features": None, "maskmem_pos_enc": None, "_mem_tok": None,
+               mask_key: torch.full((B, 1, ch, cw), NO_OBJ_SCORE, dtype=torch.float32, device=dev),
+               "obj_ptr": torch.full((B, self.hidden_dim), NO_OBJ_SCORE, dtype=torch.float32, device=dev),
+               "object_score_logits": torch.full((B, 1), 10.0, dtype=torch.float32, device=dev)}
+        empty_mask_ptr = None
+        for obj_idx in range(B):
+            tmp = st["temp_output_dict_per_obj"][obj_idx]
+            perm = st["output_dict_per_obj"][obj_idx]
+            o = tmp[storage_key].get(frame_idx, None)
+            if o is None:
+                o = perm["cond_frame_outputs"].get(frame_idx, None)
+            if o is None:
+                o = perm["non_cond_frame_outputs"].get(frame_idx, None)
+            if o is None:
+                if run_mem_encoder:
+                    if empty_mask_ptr is None:
+                        empty_mask_ptr = self._get_empty_mask_ptr(st, frame_idx)
+                    out["obj_ptr"][obj_idx:obj_idx + 1] = empty_mask_ptr
+                continue
+            m = o["pred_masks"]
+            if tuple(m.shape[-2:]) != (ch, cw):
+                m = ops.resize_bilinear(m, ch, cw)
+            out[mask_key][obj_idx:obj_idx + 1] = m
+            out["obj_ptr"][obj_idx:obj_idx + 1] = o["obj_ptr"]
+            out["object_score_logits"][obj_idx:obj_idx + 1] = o["object_score_logits"]
+        if run_mem_encoder:
+            masks = out["pred_masks"]
+            if self.non_overlap_masks_for_mem_enc:
+                masks = self._apply_non_overlapping_constraints(ops.resize_bilinear(masks, 512, 512))
+            mem_tok = self._run_memory_encoder(st, frame_idx, B, masks, out["object_score_logits"], True)
+            out["_mem_tok"] = mem_tok
+            out["maskmem_features"] = self._mem_view(mem_tok)
+            out["maskmem_pos_enc"] = self._maskmem_pos_enc(st, B)
+        return out
+
+    def _get_empty_mask_ptr(self, st, frame_idx):
+        """Dummy object pointer from an empty mask (reference :556-590)."""
+        eng = self.engine()
+        f = self._get_image_feature(st, frame_idx)
+        z = torch.zeros((1, 1, self.image_size, self.image_size), dtype=torch.float32, device=self.device)
+        return eng.mask_as_output(f["feat"], f["feat_s0"], f["feat_s1"], z, 1)["obj_ptr"]
+
+    # ------------------------------------------------------------------ propagation
+    @torch.inference_mode()
+    def propagate_in_video_preflight(self, inference_state):
+        """Consolidate temporary outputs before tracking (reference :593-660)."""
+        st = inference_state
+        self._sync_engine()
+        st["tracking_has_started"] = True
+        B = self._get_obj_num(st)
+        temp = st["temp_output_dict_per_obj"]
+        output_dict = st["output_dict"]
+        cfi = st["consolidated_frame_inds"]
+        for is_cond in (False, True):
+            storage_key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
+            temp_frame_inds = set()
+            for obj_temp in temp.values():
+                temp_frame_inds.update(obj_temp[storage_key].keys())
+            cfi[storage_key].update(temp_frame_inds)
+            for frame_idx in temp_frame_inds:
+                consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=True)
+                output_dict[storage_key][frame_idx] = consolidated
+                self._add_output_per_object(st, frame_idx, consolidated, storage_key)
+                if self.clear_non_cond_mem_around_input and (self.clear_non_cond_mem_for_multi_obj or B <= 1):
+                    self._clear_non_cond_mem_around_input(st, frame_idx)
+            for obj_temp in temp.values():
+                obj_temp[storage_key].clear()
+        for frame_idx in output_dict["cond_frame_outputs"]:
+            output_dict["non_cond_frame_outputs"].pop(frame_idx, None)
+        for obj_out in st["output_dict_per_obj"].values():
+            for frame_idx in obj_out["cond_frame_outputs"]:
+                obj_out["non_cond_frame_outputs"].pop(frame_idx, None)
+        for frame_idx in cfi["cond_frame_outputs"]:
+            assert frame_idx in output_dict["cond_frame_outputs"]
+            cfi["non_cond_frame_outputs"].discard(frame_idx)
+        all_consolidated = cfi["cond_frame_outputs"] | cfi["non_cond_frame_outputs"]
+        input_frames = set()
+        for d in st["point_inputs_per_obj"].values():
+            input_frames.update(d.keys())
+        for d in st["mask_inputs_per_obj"].values():
+            input_frames.update(d.keys())
+        assert all_consolidated == input_frames
+
+    @torch.inference_mode()
+    def propagate_in_video(self, inference_state, start_frame_idx=None, max_frame_num_to_track=None, reverse=False):
+        """Propagate the prompts across the video; generator of (frame_idx, obj_ids, video_res_masks)
+        (reference :663-745)."""
+        st = inference_state
+        self.propagate_in_video_preflight(st)
+        output_dict = st["output_dict"]
+        cfi = st["consolidated_frame_inds"]
+        obj_ids = st["obj_ids"]
+        num_frames = st["num_frames"]
+        B = self._get_obj_num(st)
+        if len(output_dict["cond_frame_outputs"]) == 0:
+            raise RuntimeError("No points are provided; please add points first")
+        clear_non_cond_mem = self.clear_non_cond_mem_around_input and (self.clear_non_cond_mem_for_multi_obj or B <= 1)
+        if start_frame_idx is None:
+            start_frame_idx = min(output_dict["cond_frame_outputs"])
+        if max_frame_num_to_track is None:
+            max_frame_num_to_track = num_frames
+        if reverse:
+            end_frame_idx = max(start_frame_idx - max_frame_num_to_track, 0)
+            order = range(start_frame_idx, end_frame_idx - 1, -1) if start_frame_idx > 0 else []
+        else:
+            end_frame_idx = min(start_frame_idx + max_frame_num_to_track, num_frames - 1)
+            order = range(start_frame_idx, end_frame_idx + 1)
+        for frame_idx in _progress(order, "propagate in video"):
+            if frame_idx in cfi["cond_frame_outputs"]:
+                storage_key = "cond_frame_outputs"
+                current_out = output_dict[storage_key][frame_idx]
+                pred_masks = current_out["pred_masks"]
+                if clear_non_cond_mem:
+                    self._clear_non_cond_mem_around_input(st, frame_idx)
+            elif frame_idx in cfi["non_cond_frame_outputs"]:
+                storage_key = "non_cond_frame_outputs"
+                current_out = output_dict[storage_key][frame_idx]
+                pred_masks = current_out["pred_masks"]
+            else:
+                storage_key = "non_cond_frame_outputs"
+                current_out, pred_masks = self._run_single_frame_inference(
+                    st, output_dict, frame_idx, B, False, None, None, reverse, run_mem_encoder=True)
+                output_dict[storage_key][frame_idx] = current_out
+            self._add_output_per_object(st, frame_idx, current_out, storage_key)
+            st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
+            _, video_res_masks = self._get_orig_video_res_output(st, pred_masks)
+            yield frame_idx, obj_ids, video_res_masks
+
+    def _add_output_per_object(self, st, frame_idx, current_out, storage_key):
+        """Per-object views of a batched output (reference :747-774)."""
+        mem = current_out["maskmem_features"]
+        pos = current_out["maskmem_pos_enc"]
+        for obj_idx, obj_output_dict in st["output_dict_per_obj"].items():
+            s = slice(obj_idx, obj_idx + 1)
+            o = {"maskmem_features": None, "maskmem_pos_enc": None, "_mem_tok": None,
+                 "pred_masks": current_out["pred_masks"][s], "obj_ptr": current_out["obj_ptr"][s],
+                 "object_score_logits": current_out["object_score_logits"][s]}
+            if mem is not None:
+                o["maskmem_features"] = mem[s]
+                o["_mem_tok"] = current_out["_mem_tok"][s]
+            if pos is not None:
+                o["maskmem_pos_enc"] = [x[s] for x in pos]
+            obj_output_dict[storage_key][frame_idx] = o
+
+    # ------------------------------------------------------------------ one frame
+    def _memory_inputs(self, st, frame_idx, output_dict, reverse):
+        """Memory-bank selection (sam2_base.py:1296-1394): returns (frames, tpos_rows, pos_list, ptr_list,
+        max_ptrs)."""
+        cfg = self.cfg
+        cond = output_dict["cond_frame_outputs"]
+        assert len(cond) > 0
+        selected, unselected = _select_closest_cond_frames(frame_idx, cond, cfg.max_cond_frames_in_attn)
+        entries = [(0, o) for o in selected.values()]
+        r = cfg.memory_temporal_stride_for_eval
+        for t_pos in range(1, cfg.num_maskmem):
+            t_rel = cfg.num_maskmem - t_pos
+            if t_rel == 1:
+                prev = frame_idx + t_rel if reverse else frame_idx - t_rel
+            elif not reverse:
+                prev = ((frame_idx - 2) // r) * r - (t_rel - 2) * r
+            else:
+                prev = -(-(frame_idx + 2) // r) * r + (t_rel - 2) * r
+            o = output_dict["non_cond_frame_outputs"].get(prev, None)
+            if o is None:
+                o = unselected.get(prev, None)
+            entries.append((t_pos, o))
+        frames, tpos_rows = [], []
+        for t_pos, o in entries:
+            if o is None:
+                continue
+            frames.append(o["_mem_tok"])
+            tpos_rows.append(cfg.num_maskmem - t_pos - 1)
+        num_frames = st["num_frames"]
+        max_ptrs = min(num_frames, cfg.max_obj_ptrs_in_encoder)
+        sign = -1 if reverse else 1
+        pos_list, ptr_list = [], []
+        for t, o in selected.items():
+            if (t >= frame_idx) if reverse else (t <= frame_idx):
+                pos_list.append((frame_idx - t) * sign)
+                ptr_list.append(o["obj_ptr"])
+        for t_diff in range(1, max_ptrs):
+            t = frame_idx + t_diff if reverse else frame_idx - t_diff
+            if t < 0 or t >= num_frames:
+                break
+            o = output_dict["non_cond_frame_outputs"].get(t, unselected.get(t, None))
+            if o is not None:
+                pos_list.append(t_diff)
+                ptr_list.append(o["obj_ptr"])
+        return frames, tpos_rows, pos_list, ptr_list, max_ptrs
+
+    def _run_single_frame_inference(self, st, output_dict, frame_idx, batch_size, is_init_cond_frame, point_inputs,
+                                    mask_inputs, reverse, run_mem_encoder, prev_sam_mask_logits=None):
+        """track_step + compact output (reference :912-978, sam2_base.py:1500-1651)."""
+        eng = self.engine()
+        cfg = self.cfg
+        B = batch_size
+        assert point_inputs is None or mask_inputs is None
+        look = (-1 if reverse else 1) if (st["tracking_has_started"] and mask_inputs is None and point_inputs is None) \
+            else None
+        f = self._get_image_feature(st, frame_idx, lookahead=look)
+        if mask_inputs is not None:
+            o = eng.mask_as_output(f["feat"], f["feat_s0"], f["feat_s1"], mask_inputs, B)
+        else:
+            if is_init_cond_frame:
+                pix, _ = ops.axpby(f["feat"], eng.w.no_mem_embed, rows=B * 1024, x_mod=1024, y_mod=1)
+            else:
+                frames, tpos_rows, pos_list, ptr_list, max_ptrs = self._memory_inputs(st, frame_idx, output_dict,
+                                                                                      reverse)
+                ptrs = ptr_pos = None
+                if pos_list:
+                    ptrs, ptr_pos = eng.obj_ptr_tokens(pos_list, ptr_list, max_ptrs, B)
+                pix = eng.memory_attention(f["feat"], frames, tpos_rows, ptrs, ptr_pos, B)
+            n_pts = 0 if point_inputs is None else point_inputs["point_labels"].size(1)
+            multimask = (cfg.multimask_output_in_sam
+                         and (is_init_cond_frame or cfg.multimask_output_for_tracking)
+                         and (cfg.multimask_min_pt_num <= n_pts <= cfg.multimask_max_pt_num))
+            if point_inputs is not None:
+                sparse = eng.embed_points(point_inputs["point_coords"], point_inputs["point_labels"])
+            else:
+                sparse = eng.no_point_tokens(B)
+            dense = None
+            if prev_sam_mask_logits is not None:
+                assert point_inputs is not None
+                m = prev_sam_mask_logits
+                if tuple(m.shape[-2:]) != (128, 128):
+                    m = ops.resize_bilinear_aa(m.float(), 128, 128)
+                dense = eng.embed_mask_prompt(m.contiguous(), B)
+            if not multimask and not cfg.dynamic_multimask_via_stability:
+                raise NotImplementedError("single-mask output without the stability fallback "
+                                          "(apply_postprocessing=False) is not wired on this path")
+            o = eng.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, sparse, dense=dense, multimask=multimask)
+        low = o["low"]
+        mem_tok = None
+        if run_mem_encoder and cfg.num_maskmem > 0:
+            binarize = cfg.binarize_mask_from_pts_for_mem_enc and (point_inputs is not None)
+            src = o.get("high", None)
+            if src is None or self.non_overlap_masks_for_mem_enc:
+                src = low
+                if self.non_overlap_masks_for_mem_enc:
+                    src = self._apply_non_overlapping_constraints(ops.resize_bilinear(low, 512, 512))
+            mask_in = eng.mem_mask_input(src, binarize)
+            mem_tok = eng.encode_memory(f["feat_bf16"], mask_in, o["score"], B)
+        pred_masks = low
+        if self.fill_hole_area > 0:
+            pred_masks = ops.fill_holes(low, self.fill_hole_area)
+        compact = {"maskmem_features": None if mem_tok is None else self._mem_view(mem_tok),
+                   "maskmem_pos_enc": None if mem_tok is None else self._maskmem_pos_enc(st, B),
+                   "_mem_tok": mem_tok, "pred_masks": pred_masks, "obj_ptr": o["obj_ptr"],
+                   "object_score_logits": o["score"]}
+        return compact, pred_masks
+
+    def _run_memory_encoder(self, st, frame_idx, batch_size, masks, object_score_logits, is_mask_from_pts):
+        """Memory encoder on consolidated masks (reference :980-1014); `masks` are low-res or 512^2 logits."""
+        eng = self.engine()
+        f = self._get_image_feature(st, frame_idx)
+        binarize = self.cfg.binarize_mask_from_pts_for_mem_enc and is_mask_from_pts
+        mask_in = eng.mem_mask_input(masks, binarize)
+        return eng.encode_memory(f["feat_bf16"], mask_in, object_score_logits, batch_size)
+
+    # ------------------------------------------------------------------ editing surface
+    @torch.inference_mode()
+    def clear_all_prompts_in_frame(self, inference_state, frame_idx, obj_id, need_output=True):
+        """Remove all prompts of an object on a frame (reference :776-846)."""
+        st = inference_state
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        st["point_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        temp = st["temp_output_dict_per_obj"]
+        temp[obj_idx]["cond_frame_outputs"].pop(frame_idx, None)
+        temp[obj_idx]["non_cond_frame_outputs"].pop(frame_idx, None)
+        B = self._get_obj_num(st)
+        frame_has_input = any(frame_idx in st["point_inputs_per_obj"][i] or frame_idx in st["mask_inputs_per_obj"][i]
+                              for i in range(B))
+        if not frame_has_input:
+            output_dict = st["output_dict"]
+            cfi = st["consolidated_frame_inds"]
+            cfi["cond_frame_outputs"].discard(frame_idx)
+            cfi["non_cond_frame_outputs"].discard(frame_idx)
+            out = output_dict["cond_frame_outputs"].pop(frame_idx, None)
+            if out is not None:
+                output_dict["non_cond_frame_outputs"][frame_idx] = out
+                st["frames_already_tracked"].pop(frame_idx, None)
+            for i in range(B):
+                od = st["output_dict_per_obj"][i]
+                o = od["cond_frame_outputs"].pop(frame_idx, None)
+                if o is not None:
+                    od["non_cond_frame_outputs"][frame_idx] = o
+            if len(output_dict["cond_frame_outputs"]) == 0:
+                self._reset_tracking_results(st)
+        if not need_output:
+            return
+        is_cond = any(frame_idx in t["cond_frame_outputs"] for t in temp.values())
+        consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=False,
+                                                                consolidate_at_video_res=True)
+        _, video_res_masks = self._get_orig_video_res_output(st, consolidated["pred_masks_video_res"])
+        return frame_idx, st["obj_ids"], video_res_masks
+
+    @torch.inference_mode()
+    def reset_state(self, inference_state):
+        """Remove all prompts and results (reference :848-860)."""
+        st = inference_state
+        self._reset_tracking_results(st)
+        st["obj_id_to_idx"].clear()
+        st["obj_idx_to_id"].clear()
+        st["obj_ids"].clear()
+        st["point_inputs_per_obj"].clear()
+        st["mask_inputs_per_obj"].clear()
+        st["output_dict_per_obj"].clear()
+        st["temp_output_dict_per_obj"].clear()
+
+    def _reset_tracking_results(self, st):
+        for v in st["point_inputs_per_obj"].values():
+            v.clear()
+        for v in st["mask_inputs_per_obj"].values():
+            v.clear()
+        for v in st["output_dict_per_obj"].values():
+            v["cond_frame_outputs"].clear()
+            v["non_cond_frame_outputs"].clear()
+        for v in st["temp_output_dict_per_obj"].values():
+            v["cond_frame_outputs"].clear()
+            v["non_cond_frame_outputs"].clear()
+        st["output_dict"]["cond_frame_outputs"].clear()
+        st["output_dict"]["non_cond_frame_outputs"].clear()
+        st["consolidated_frame_inds"]["cond_frame_outputs"].clear()
+        st["consolidated_frame_inds"]["non_cond_frame_outputs"].clear()
+        st["tracking_has_started"] = False
+        st["frames_already_tracked"].clear()
+
+    @torch.inference_mode()
+    def remove_object(self, inference_state, obj_id, strict=False, need_output=True):
+        """Remove an object id from the tracking state (reference :1041-1150)."""
+        st = inference_state
+        old_idx = st["obj_id_to_idx"].get(obj_id, None)
+        updated_frames = []
+        if old_idx is None:
+            if not strict:
+                return st["obj_ids"], updated_frames
+            raise RuntimeError(f"Cannot remove object id {obj_id} as it doesn't exist. "
+                               f"All existing object ids: {st['obj_ids']}.")
+        if len(st["obj_id_to_idx"]) == 1:
+            self.reset_state(st)
+            return st["obj_ids"], updated_frames
+        input_frames = set(st["point_inputs_per_obj"][old_idx]) | set(st["mask_inputs_per_obj"][old_idx])
+        for frame_idx in input_frames:
+            self.clear_all_prompts_in_frame(st, frame_idx, obj_id, need_output=False)
+        old_ids = st["obj_ids"]
+        old_inds = list(range(len(old_ids)))
+        remain = [i for i in old_inds if i != old_idx]
+        new_ids = [old_ids[i] for i in remain]
+        new_inds = list(range(len(new_ids)))
+        old_to_new = dict(zip(remain, new_inds))
+        st["obj_id_to_idx"] = dict(zip(new_ids, new_inds))
+        st["obj_idx_to_id"] = dict(zip(new_inds, new_ids))
+        st["obj_ids"] = new_ids
+
+        def remap(container):
+            kvs = []
+            for k in old_inds:
+                v = container.pop(k)
+                if k in old_to_new:
+                    kvs.append((old_to_new[k], v))
+            container.update(kvs)
+
+        for key in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj"):
+            remap(st[key])
+        for storage_key in ("cond_frame_outputs", "non_cond_frame_outputs"):
+            for frame_idx, out in st["output_dict"][storage_key].items():
+                out["_mem_tok"] = out["_mem_tok"][remain].contiguous()
+                out["maskmem_features"] = self._mem_view(out["_mem_tok"])
+                out["maskmem_pos_enc"] = self._maskmem_pos_enc(st, len(remain))
+                out["pred_masks"] = out["pred_masks"][remain]
+                out["obj_ptr"] = out["obj_ptr"][remain]
+                out["object_score_logits"] = out["object_score_logits"][remain]
+                self._add_output_per_object(st, frame_idx, out, storage_key)
+        if need_output:
+            temp = st["temp_output_dict_per_obj"]
+            for frame_idx in input_frames:
+                is_cond = any(frame_idx in t["cond_frame_outputs"] for t in temp.values())
+                consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=False,
+                                                                        consolidate_at_video_res=True)
+                _, video_res_masks = self._get_orig_video_res_output(st, consolidated["pred_masks_video_res"])
+                updated_frames.append((frame_idx, video_res_masks))
+        return st["obj_ids"], updated_frames
+
+    def _clear_non_cond_mem_around_input(self, st, frame_idx):
+        """Drop non-conditioning memories around an edited frame (reference :1152-1172)."""
+        r = self.memory_temporal_stride_for_eval
+        lo, hi = frame_idx - r * self.num_maskmem, frame_idx + r * self.num_maskmem
+        for t in range(lo, hi + 1):
+            st["output_dict"]["non_cond_frame_outputs"].pop(t, None)
+            for od in st["output_dict_per_obj"].values():
+                od["non_cond_frame_outputs"].pop(t, None)
+
+
+class SAM2VideoPredictorNPZ(SAM2VideoPredictor):
+    """Variant whose `init_state` takes pre-normalised frames (sam2_video_predictor_npz.py:44-115)."""
+
+    @torch.inference_mode()
+    def init_state(self, images, video_height, video_width, offload_video_to_cpu=False, offload_state_to_cpu=False,
+                   async_loading_frames=False):
+        return self._new_state(images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu)
+
+
+def _select_closest_cond_frames(frame_idx, cond_frame_outputs, max_cond_frame_num):
+    """Conditioning frames closest in time (sam2_utils.py:19-61)."""
+    if max_cond_frame_num == -1 or len(cond_frame_outputs) <= max_cond_frame_num:
+        return cond_frame_outputs, {}
+    assert max_cond_frame_num >= 2, "we should allow using 2+ conditioning frames"
+    chosen = {}
+    before = max((t for t in cond_frame_outputs if t < frame_idx), default=None)
+    if before is not None:
+        chosen[before] = cond_frame_outputs[before]
+    after = min((t for t in cond_frame_outputs if t >= frame_idx), default=None)
+    if after is not None:
+        chosen[after] = cond_frame_outputs[after]
+    rest = sorted((t for t in cond_frame_outputs if t not in chosen), key=lambda t: abs(t - frame_idx))
+    for t in rest[: max_cond_frame_num - len(chosen)]:
+        chosen[t] = cond_frame_outputs[t]
+    return chosen, {t: v for t, v in cond_frame_outputs.items() if t not in chosen}
