@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the MedSAM2 per-frame propagation path (BASELINE.json metric: propagated frames/s).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+  python bench.py --impl reference ...                   # the reference algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json configs[1]): sam2.1_hiera_t512 `propagate_in_video` over a 512-frame synthetic
+512x512 grayscale echo clip, 1 object, mask prompt on frame 0, 7-frame memory bank, random-init weights.
+One *step* = one full propagation pass over the clip.  With N > 1 every rank tracks its own clip (independent
+videos shard with no communication -> weak scaling); the value is the aggregate frames/s over all ranks, timed
+on the device (CUDA events), barrier + synchronize on both sides, max over ranks.
+
+JSON keys beyond the base contract:
+  e2e          same metric through the public API from HOST buffers: per step the uint8 clip is copied from
+               pinned host memory, normalised on the device, tracked, and every frame's binary mask is copied back
+  roofline     dominant kernel (memory-attention cross-attention flash kernel): algorithmic FLOPs / CUDA-event
+               time inside the timed region vs the measured bf16 peak
+  cpu_baseline the oracle port of the reference timed on the host cores on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")
+
+import torch  # noqa: E402
+
+METRIC = "propagated frames/sec (sam2.1_hiera_t512, 512x512, 1 object, 7-frame memory bank)"
+SEED = 19
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=512, help="clip length T (BASELINE config 2: 512)")
+    ap.add_argument("--objects", type=int, default=1)
+    ap.add_argument("--encoder-batch", type=int, default=8, help="frames per batched image-encoder pass")
+    ap.add_argument("--cpu-sample-frames", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16_sustained=p.get("bf16_tflops_sustained", 1405.3), bf16_burst=p.get("bf16_tflops", 1685.0),
+                    hbm=p.get("hbm_gbs", 6447.2), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_sustained=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_fps(frames, objects, passes=1):
+    """frames/s of the CPU port of the reference (oracle/medsam2_ref.py) on a `frames`-long sample of the
+    workload: same weights, same clip generator, same prompt, fill-holes skipped as the reference does on CPU."""
+    from oracle.medsam2_ref import RefPredictor
+    from us_video_medsam2_b200 import synth
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_state_dict(SEED)
+    clip = synth.make_clip(frames, kind="speckle")
+    masks = [synth.box_mask()] if objects == 1 else synth.multi_object_masks(objects)
+    pred = RefPredictor(sd, fill_holes=False)
+    best = None
+    with torch.inference_mode():
+        for _ in range(passes):
+            st = pred.init_state(clip, 512, 512)
+            for i, m in enumerate(masks):
+                pred.add_new_mask(st, 0, i + 1, m)
+            t0 = time.perf_counter()
+            n = sum(1 for _ in pred.propagate_in_video(st))
+            dt = time.perf_counter() - t0
+            fps = n / dt
+            best = fps if best is None else max(best, fps)
+    return best, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = max(4, min(args.frames, args.cpu_sample_frames))
+    times = []
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup + args.steps):
+        fps, cores = cpu_reference_fps(sample, args.objects)
+        if i >= args.warmup:
+            times.append(sample / fps)
+    ms = 1000.0 * sum(times) / len(times)
+    value = sample / (ms / 1000.0)
+    unit = "frames/s"
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"sam2.1_hiera_t512 propagate_in_video, CPU port of the reference, {sample}-frame sample "
+                               f"of the {args.frames}-frame synthetic echo clip, {args.objects} object(s)",
+                   "frames_per_step": sample, "objects": args.objects},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": f"{sample} frames per step, torch {torch.__version__} CPU fp32, fill-holes skipped "
+                                   "(CUDA-only op in the reference)"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """CUDA-event timing of one entry point inside the timed region (same stream the kernel is launched on)."""
+
+    def __init__(self, lib_mod, ops_mod, name, predicate):
+        self.name, self.pred = name, predicate
+        self.pairs, self.flops, self.enabled = [], [], False
+        self._orig = lib_mod.call
+        lib_mod.call = self._call
+        ops_mod.call = self._call  # ops.py binds `call` by name at import time
+
+    def _call(self, name, *a):
+        if self.enabled and name == self.name:
+            work = self.pred(*a)
+            if work:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                self._orig(name, *a)
+                e.record()
+                self.pairs.append((s, e))
+                self.flops.append(work)
+                return
+        self._orig(name, *a)
+
+    def summary(self):
+        if not self.pairs:
+            return None
+        ms = [s.elapsed_time(e) for s, e in self.pairs]
+        return dict(launches=len(ms), avg_ms=sum(ms) / len(ms), flops_per_launch=sum(self.flops) / len(self.flops))
+
+
+def run_b200(args, rank, world):
+    import torch.distributed as dist
+
+    from us_video_medsam2_b200 import _lib, ops, synth
+    from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, B = args.frames, args.objects
+    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=args.encoder_batch)
+    pred.load_state_dict(synth.make_state_dict(SEED), strict=True)
+    masks = [synth.box_mask()] if B == 1 else synth.multi_object_masks(B)
+    gray_host = synth.make_clip_u8(T, seed=1234 + rank).pin_memory()      # [T,512,512] uint8, pinned host
+    out_host = torch.empty((T, B, 512, 512), dtype=torch.uint8).pin_memory()
+    clip_dev = ops.normalize_gray_u8(gray_host.to(dev), synth.IMG_MEAN, synth.IMG_STD)  # resident copy for `value`
+
+    def fwd_flops(p_ref, stream):
+        p = p_ref._obj  # the FmhaParams struct behind ctypes.byref
+        if p.head_dim == 256 and p.Nk > 1024:  # cross-attention over the memory bank (QK^T + PV)
+            return 4.0 * p.B * p.H * p.Nq * p.Nk * p.head_dim
+        return 0
+
+    timer = KernelTimer(_lib, ops, "usvm_fmha_bf16", fwd_flops)
+
+    def one_pass(images, sink=None):
+        st = pred.init_state(images, 512, 512)
+        for i, m in enumerate(masks):
+            pred.add_new_mask(st, 0, i + 1, m)
+        n = 0
+        for t, ids, logits in pred.propagate_in_video(st):
+            if sink is not None:
+                sink[t].copy_((logits[:, 0] > 0).to(torch.uint8), non_blocking=True)
+            n += 1
+        return n
+
+    def step_resident():
+        return one_pass(clip_dev)
+
+    def step_e2e():
+        g = gray_host.to(dev, non_blocking=True)
+        imgs = ops.normalize_gray_u8(g, synth.IMG_MEAN, synth.IMG_STD)
+        return one_pass(imgs, out_host)
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        timer.enabled = profile
+        l0 = _lib.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        frames = 0
+        for _ in range(steps):
+            frames += fn()
+        e1.record()
+        torch.cuda.synchronize()
+        timer.enabled = False
+        launches = _lib.launch_count - l0
+        clocks = sampler.stop() if rank == 0 else None
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        fr = torch.tensor([float(frames)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+        return float(ms), float(fr), launches, clocks
+
+    with torch.inference_mode():
+        ms, frames, launches, clocks = timed(step_resident, args.steps, args.warmup, profile=True)
+        ms_e2e, frames_e2e, _, _ = timed(step_e2e, max(1, args.steps), 1)
+    value = frames / (ms / 1000.0)
+    e2e = frames_e2e / (ms_e2e / 1000.0)
+
+    peaks = measured_peaks()
+    ks = timer.summary()
+    roofline = None
+    if ks:
+        ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "kernel": "fmha_bf16_kernel<256> (memory-attention cross-attention, split-KV)",
+                    "launches_timed": ks["launches"], "avg_us": ks["avg_ms"] * 1e3, "peak_source": peaks["source"]}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = max(4, min(T, args.cpu_sample_frames))
+        fps, cores = cpu_reference_fps(sample, B)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{sample}-frame sample of the same clip, oracle port of the reference, torch "
+                         f"{torch.__version__} CPU fp32"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"sam2.1_hiera_t512 propagate_in_video, {T}-frame synthetic echo clip per GPU, "
+                                   f"{B} object(s), 7-frame memory bank, mask prompt on frame 0",
+                       "frames": T, "objects": B, "encoder_batch": args.encoder_batch, "parallelism": f"videos x{world}",
+                       "precision": "bf16 tensor-core contractions (encoder / memory attention / memory encoder), "
+                                    "fp32 mask decoder",
+                       "l2": f"inputs larger than L2: {T * 3 * 512 * 512 * 4 / 1e6:.0f} MB clip streamed once per step"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": T * 512 * 512,
+                    "d2h_bytes_per_step": T * B * 512 * 512},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    run_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

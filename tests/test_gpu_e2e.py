@@ -48,7 +48,9 @@ def test_matches_reference_fixture(golden_dir, name):
             continue
         assert float(d.max()) <= LOGIT_TOL, (t, float(d.max()))
         assert dice(got[i], want[i]) >= DICE_BAR, (t, dice(got[i], want[i]))
-        assert dice(got[i], want_plain[i]) >= 0.98  # sanity vs the CPU-reference variant without hole filling
+        # vs the stock CPU reference (which skips hole filling): identical wherever no hole was filled
+        unfilled = (got[i] != 0.1)
+        assert float((got[i] - want_plain[i]).abs()[unfilled & same].max()) <= LOGIT_TOL
     sfx = "_filled"
     assert np.abs(out["score"].numpy() - g["score" + sfx]).max() < 2e-2
     assert np.sign(out["score"].numpy()).tolist() == np.sign(g["score" + sfx]).tolist()
@@ -101,6 +103,7 @@ def test_video_resolution_resize_and_state_api():
     assert st["obj_ids"] == [] and not st["tracking_has_started"]
     with pytest.raises(RuntimeError):
         next(pred.propagate_in_video(st))  # "No points are provided"
+    pred.reset_state(st)  # like the reference, the failed call above already marked tracking as started
     pred.add_new_points_or_box(st, 2, 1, box=np.array([100, 80, 300, 250], np.float32))
     rev = [o[0] for o in pred.propagate_in_video(st, reverse=True)]
     assert rev == [2, 1, 0]

@@ -138,7 +138,7 @@ def test_build_memory_and_finalize():
     rows = [6, 0, 3]
     k_in, v_in, Nk = ops.build_memory(frames, rows, pos, tpos, ptrs, ppos, B)
     assert Nk == 3 * T + 4 * P
-    wk = torch.cat([f.float() + pos + tpos[r] for f, r in zip(frames, rows)] + [ptrs + ppos], dim=1)
+    wk = torch.cat([f.float() + (pos + tpos[r]) for f, r in zip(frames, rows)] + [ptrs + ppos], dim=1)
     wv = torch.cat([f.float() for f in frames] + [ptrs], dim=1)
     assert torch.equal(k_in, wk.to(BF)) and torch.equal(v_in, wv.to(BF))
     x = torch.randn((B * T, Cm), generator=g, device="cuda")
@@ -179,7 +179,7 @@ def test_im2col_nhwc_and_dwconv():
     B = 2
     x = torch.randn((B, 64, 64, 64), generator=g, device="cuda")
     A = ops.im2col_nhwc(x.view(-1, 64), B, 64, 64, 64, 3, 2, 1)
-    w = torch.randn((256, 64, 3, 3), generator=g, device="cuda")
+    w = torch.randn((256, 64, 3, 3), generator=g, device="cuda") / 24
     want = F.conv2d(x.permute(0, 3, 1, 2).to(BF).float(), w, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, 256)
     got = A.float() @ w.permute(0, 2, 3, 1).reshape(256, 576).t()
     assert (got - want).abs().max().item() < 2e-3

@@ -103,7 +103,7 @@ class PackedWeights:
     def __init__(self, sd, device, cfg=ModelConfig):
         self.cfg = cfg
         self.device = device
-        g = lambda k: sd[k].detach().to(F32)
+        g = lambda k: sd[k].detach().to("cpu", F32)  # pack on the host, upload once
         dev = lambda t, dt=F32: t.to(dtype=dt).contiguous().to(device)
         w16 = lambda k: dev(g(k).reshape(g(k).shape[0], -1), BF16)
         f32 = lambda k: dev(g(k))
