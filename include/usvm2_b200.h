@@ -58,6 +58,13 @@ typedef struct usvm_gemm_epilogue {
   int ldo_f32;
   void* out_bf16;
   int ldo_bf16;
+  /* optional fused axial RoPE (position_encoding.py:194-221) on output columns [0, rope_cols): applied after the bias
+   * to adjacent column pairs of rows whose index inside their batch of rope_rows_per_batch is < rope_n_rope, with
+   * table row (index % rope_table_rows) and table column ((col % 256) / 2); tables fp32 [rope_table_rows, 128].
+   * tensor-core kernel only; rope_cos == NULL disables it */
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_cols, rope_rows_per_batch, rope_n_rope, rope_table_rows;
 } usvm_gemm_epilogue;
 
 /* bf16 operands, fp32 accumulation in TMEM: TMA (128B swizzle) -> tcgen05.mma -> tcgen05.ld epilogue.
@@ -132,10 +139,42 @@ typedef struct usvm_memory_frames {
 int usvm_build_memory(const usvm_memory_frames* frames_host, const float* pos, const float* tpos, const float* ptrs,
                       const float* ptr_pos, void* k_in, void* v_in, int B, int T, int Cm, int n_ptr_tokens,
                       int Nk_total, int row_offset, void* stream);
+/* Per-frame control block kept in DEVICE memory: everything that varies from frame to frame (and from session to
+ * session) on the steady-state tracking path -- where the frame store lives, which stored frames feed the memory bank
+ * (sam2_base.py:1296-1394) and which slot this frame writes.  Kernels read it through a pointer, so ONE captured CUDA
+ * graph serves every frame of every session with the same (objects, #memories, #pointers) signature. */
+#define USVM_MAX_PTRS 32
+typedef struct usvm_frame_ctrl {
+  void* mem_store;   /* bf16 [slots][B][T][Cm]   spatial memories            */
+  float* ptr_store;  /* fp32 [slots][B][4*Cm]    object pointers             */
+  float* score_store; /* fp32 [slots][B]         object score logits         */
+  float* mask_store; /* fp32 [slots][B][h*w]     low-res mask logits (hole-filled) */
+  long long mem_slot_stride, ptr_slot_stride, score_slot_stride, mask_slot_stride; /* elements per slot */
+  int cur_frame; /* slot written by this frame */
+  int n_mem, n_ptr, reserved;
+  int mem_frame[USVM_MAX_MEMORY_FRAMES]; /* slot of each spatial memory, in concatenation order */
+  int mem_tpos[USVM_MAX_MEMORY_FRAMES];  /* row of maskmem_tpos_enc for each */
+  int ptr_frame[USVM_MAX_PTRS];          /* slot of each object pointer */
+  float ptr_rel[USVM_MAX_PTRS];          /* signed temporal distance / (max_obj_ptrs - 1) */
+} usvm_frame_ctrl;
+/* writes *ctrl_host into device memory through a by-value kernel parameter (asynchronous, no staging copy) */
+int usvm_set_frame_ctrl(usvm_frame_ctrl* ctrl_dev, const usvm_frame_ctrl* ctrl_host, void* stream);
 /* memory feature epilogue (sam2_base.py:1488-1496; sam2_video_predictor.py:956): + no_obj_embed_spatial where
- * score <= 0, rounded to bf16 into the bank slot [B, T, Cm] */
-int usvm_finalize_memory(const float* x, const float* score, const float* no_obj_embed, void* mem_bf16, int B, int T,
-                         int Cm, void* stream);
+ * score <= 0 (score stride in elements), rounded to bf16 into mem_bf16 [B, T, Cm], or -- when mem_bf16 is NULL --
+ * into slot ctrl_dev->cur_frame of ctrl_dev->mem_store */
+int usvm_finalize_memory(const float* x, const float* score, int score_stride, const float* no_obj_embed,
+                         void* mem_bf16, int B, int T, int Cm, const usvm_frame_ctrl* ctrl_dev, void* stream);
+/* get_1d_sine_pe + obj_ptr_tpos_proj (sam2_utils.py:64-74, sam2_base.py:1402-1408) from ctrl->ptr_rel:
+ * out fp32 [n_ptr*4, 64] */
+int usvm_ptr_tpos(const usvm_frame_ctrl* ctrl_dev, const float* W, const float* bias, float* out, int n_ptr,
+                  void* stream);
+/* usvm_build_memory reading the frame store through the control block;
+ * k_in / v_in bf16 [B, n_mem*T + n_ptr*4, Cm] */
+int usvm_build_memory_store(const usvm_frame_ctrl* ctrl_dev, const float* pos, const float* tpos, const float* ptr_pos,
+                            void* k_in, void* v_in, int B, int T, int Cm, int n_mem, int n_ptr, void* stream);
+/* slot ctrl->cur_frame of the pointer / score / mask stores <- obj_ptr [B,256], score (stride score_stride), masks [B,hw] */
+int usvm_store_outputs(const usvm_frame_ctrl* ctrl_dev, const float* obj_ptr, const float* score, int score_stride,
+                       const float* masks, int B, int ptr_dim, int hw, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * small convolutions / resize (memory encoder, prompt encoder)
@@ -163,16 +202,46 @@ int usvm_resize_bilinear_aa(const float* x, float* y, long long planes, int Hi, 
 /* feat_shared != 0: feat_s1 / feat_s0 hold ONE frame that every object of the batch shares */
 int usvm_upscale1_ln_gelu(const float* g1, const float* feat_s1, const float* ln_w, const float* ln_b, float eps,
                           float* out, int B, int Hc, int Wc, int C, int feat_shared, void* stream);
-int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, float* masks, int B, int Hc, int Wc,
-                        int feat_shared, void* stream);
+int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, int hyper_bs, float* masks, int B,
+                        int Hc, int Wc, int feat_shared, void* stream);
 int usvm_small_mlp3(const float* x, long long x_row_stride, long long x_inst_stride, const int* row_select,
                     const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                     const float* b3, int out_dim, int sigmoid_out, float* y, long long y_row_stride,
                     long long y_inst_stride, int rows, int instances, void* stream);
-int usvm_sam_select(const float* masks, const float* iou, const float* score, int multimask, float stab_delta,
-                    float stab_thresh, float no_obj_score, float* low_res, int* token_index, float* iou_out, int B,
-                    int HW, void* stream);
-int usvm_objptr_mix(float* ptr, const float* score, const float* no_obj_ptr, int B, int C, void* stream);
+/* Latency-oriented fp32 GEMM for a handful of rows (the 8 decoder tokens per object, the stacked 3-layer heads):
+ * out[i][m][n] = act((x + x2)[i][m] . w[i][n] + bias[i][n]) + residual[i][m][n];  strides in elements;
+ * row_select (int32 [M], optional) adds row_select[m] * x_sel_stride to the x row address (token picked on device). */
+typedef struct usvm_skinny_params {
+  const float* x;
+  long long x_is, x_rs;
+  const float* x2; /* optional second addend, NULL = none */
+  long long x2_is, x2_rs;
+  const int* row_select;
+  long long x_sel_stride;
+  const float* w; /* [instances][N][K] */
+  long long w_is;
+  const float* bias; /* [instances][N] or NULL */
+  long long b_is;
+  const float* residual;
+  long long r_is, r_rs;
+  float* out;
+  long long o_is, o_rs;
+  int M, N, K, instances, act;
+} usvm_skinny_params;
+int usvm_gemm_skinny_f32(const usvm_skinny_params* p_host, void* stream);
+/* token -> image attention (transformer.py:194-198): q [B*Nt, H*16], k/v rows of stride kv_rs, Nt <= 16 */
+int usvm_attn_t2i_f32(const float* q, int q_rs, const float* k, const float* v, int kv_rs, float* out, int o_rs, int B,
+                      int H, int Nt, int Nk, float scale, void* stream);
+/* image -> token attention (transformer.py:205-210): q [B*Nq, .] row stride q_rs, k/v [B*Nt, .] row stride kv_rs */
+int usvm_attn_i2t_f32(const float* q, int q_rs, const float* k, const float* v, int kv_rs, float* out, int o_rs, int B,
+                      int H, int Nq, int Nt, float scale, void* stream);
+/* multimask argmax-IoU / stability fallback + NO_OBJ_SCORE gating (mask_decoder.py:146-153,247-295;
+ * sam2_base.py:1112-1141); iou: 4 values per object (logits when iou_is_logit), score: 1 value per object */
+int usvm_sam_select(const float* masks, const float* iou, int iou_stride, int iou_is_logit, const float* score,
+                    int score_stride, int multimask, float stab_delta, float stab_thresh, float no_obj_score,
+                    float* low_res, int* token_index, float* iou_out, int B, int HW, void* stream);
+int usvm_objptr_mix(float* ptr, const float* score, int score_stride, const float* no_obj_ptr, int B, int C,
+                    void* stream);
 int usvm_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float image_size,
                      float* out, int n_points, void* stream);
 

@@ -109,3 +109,23 @@ def test_video_resolution_resize_and_state_api():
     assert rev == [2, 1, 0]
     with pytest.raises(ValueError):
         pred.add_new_points_or_box(st, 0, 1, points=np.zeros((1, 2), np.float32))
+
+
+def test_cuda_graph_replay_equals_eager():
+    """Steady-state frames replayed from the captured CUDA graph must reproduce the eager kernel sequence bit for
+    bit (same kernels, same order), for 2 objects on a clip long enough to reach the steady state (frame >= 16)."""
+    T = 26
+    clip = synth.make_clip(T, kind="speckle").cuda()
+    outs = []
+    for graphs in (False, True):
+        pred = _predictor(19, use_cuda_graphs=graphs, encoder_batch=4)
+        st = pred.init_state(clip, 512, 512)
+        for i, m in enumerate(synth.multi_object_masks(2)):
+            pred.add_new_mask(st, 0, i + 1, m)
+        outs.append([lg.clone() for _, _, lg in pred.propagate_in_video(st)])
+        if graphs:
+            assert len(pred._graphs) >= 1  # the steady state was captured
+            ptr = st["output_dict"]["non_cond_frame_outputs"][T - 1]["obj_ptr"].clone()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert ptr.shape == (2, 256) and bool(torch.isfinite(ptr).all())

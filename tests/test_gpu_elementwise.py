@@ -292,3 +292,88 @@ def test_sam_select_and_point_embed():
     pe = random_fourier_pe(coords.cpu() / 512, gauss.cpu())
     want = torch.stack([pe[0, 0] + table[1].cpu(), pe[0, 1] + table[3].cpu(), table[4].cpu()])
     assert (got[0].cpu() - want).abs().max().item() < 1e-4
+
+
+def test_skinny_gemm_and_decoder_attention():
+    from us_video_medsam2_b200 import ops
+
+    g = _g(21)
+    B, Nt = 3, 8
+    x = torch.randn((B * Nt, 256), generator=g, device="cuda")
+    x2 = torch.randn((B * Nt, 256), generator=g, device="cuda")
+    w = torch.randn((2048, 256), generator=g, device="cuda") / 16
+    b = torch.randn(2048, generator=g, device="cuda")
+    got = ops.gemm_skinny(x, w, b, x2=x2, act=ops.ACT_RELU)
+    want = F.relu((x + x2) @ w.t() + b)
+    assert (got - want).abs().max().item() < 1e-4
+    w2 = torch.randn((256, 2048), generator=g, device="cuda") / 45
+    res = torch.randn((B * Nt, 256), generator=g, device="cuda")
+    got2 = ops.gemm_skinny(got, w2, None, residual=res)
+    assert (got2 - (want @ w2.t() + res)).abs().max().item() < 2e-4
+    # stacked instances reading consecutive token rows, odd N
+    hs = torch.randn((B, Nt, 256), generator=g, device="cuda")
+    W = torch.randn((6, 30, 256), generator=g, device="cuda") / 16
+    bb = torch.randn((6, 30), generator=g, device="cuda")
+    y = ops.gemm_skinny(None, W, bb, M=B, x_ptr=hs.data_ptr(), x_rs=Nt * 256, x_is=256, instances=6)
+    want = torch.einsum("bik,ink->bin", hs[:, :6], W) + bb
+    assert (y.view(B, 6, 30) - want).abs().max().item() < 1e-4
+    idx = torch.tensor([3, 0, 2], dtype=torch.int32, device="cuda")
+    y = ops.gemm_skinny(None, W[0], bb[0], M=B, x_ptr=hs.data_ptr() + 4 * 2 * 256, x_rs=Nt * 256, row_select=idx,
+                        x_sel_stride=256)
+    want = torch.stack([hs[i, 2 + int(idx[i])] @ W[0].t() + bb[0] for i in range(B)])
+    assert (y - want).abs().max().item() < 1e-4
+    # token->image and image->token attention (8 heads x 16) on column views of a fused buffer
+    for Nt_ in (8, 11):
+        q = torch.randn((B * Nt_, 128), generator=g, device="cuda")
+        img = torch.randn((B * 1024, 384), generator=g, device="cuda")
+        o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt_, 1024)
+        sp = lambda t, n: t.reshape(B, n, 8, 16).permute(0, 2, 1, 3)
+        att = torch.softmax(sp(q, Nt_) @ sp(img[:, 0:128], 1024).transpose(-1, -2) / 4.0, dim=-1) @ sp(img[:, 128:256], 1024)
+        assert (o - att.permute(0, 2, 1, 3).reshape(B * Nt_, 128)).abs().max().item() < 2e-5
+        k2 = torch.randn((B * Nt_, 128), generator=g, device="cuda")
+        v2 = torch.randn((B * Nt_, 128), generator=g, device="cuda")
+        o = ops.attn_i2t(img[:, 256:384], k2, v2, B, 1024, Nt_)
+        att = torch.softmax(sp(img[:, 256:384], 1024) @ sp(k2, Nt_).transpose(-1, -2) / 4.0, dim=-1) @ sp(v2, Nt_)
+        assert (o - att.permute(0, 2, 1, 3).reshape(B * 1024, 128)).abs().max().item() < 2e-5
+
+
+def test_frame_store_kernels():
+    from oracle.medsam2_ref import sine_pos_1d
+    from us_video_medsam2_b200 import ops
+
+    g = _g(22)
+    B, T, Cm, S = 2, 1024, 64, 12
+    store = ops.FrameStore(S, B, torch.device("cuda"))
+    store.mem.copy_(torch.randn((S, B, T, Cm), generator=g, device="cuda"))
+    store.ptr.copy_(torch.randn((S, B, 256), generator=g, device="cuda"))
+    pos = torch.randn((T, Cm), generator=g, device="cuda")
+    tpos = torch.randn((7, Cm), generator=g, device="cuda")
+    W = torch.randn((64, 256), generator=g, device="cuda") / 16
+    bias = torch.randn(64, generator=g, device="cuda")
+    ctrl = ops.new_frame_ctrl(torch.device("cuda"))
+    mem_frames, mem_tpos = [0, 9, 10, 11], [6, 2, 1, 0]
+    ptr_frames, ptr_rel = [0, 11, 10, 9, 8], [11 / 15, 1 / 15, 2 / 15, 3 / 15, 4 / 15]
+    want_pp = (sine_pos_1d(torch.tensor(ptr_rel), 256).cuda() @ W.t() + bias).repeat_interleave(4, dim=0)
+    for obj0, Bq in ((0, 2), (1, 1)):
+        ops.set_frame_ctrl(ctrl, store, obj0, 5, mem_frames, mem_tpos, ptr_frames, ptr_rel)
+        pp = ops.ptr_tpos(ctrl, W, bias, len(ptr_frames))
+        assert (pp - want_pp).abs().max().item() < 1e-4
+        k_in, v_in, Nk = ops.build_memory_store(ctrl, pos, tpos, pp, Bq, 4, 5)
+        sl = slice(obj0, obj0 + Bq)
+        pt = torch.stack([store.ptr[f, sl] for f in ptr_frames], 1).reshape(Bq, 20, 64)
+        wk = torch.cat([store.mem[f, sl].float() + (pos + tpos[r]) for f, r in zip(mem_frames, mem_tpos)] + [pt + pp], dim=1)
+        wv = torch.cat([store.mem[f, sl].float() for f in mem_frames] + [pt], dim=1)
+        assert Nk == 4 * T + 20 and torch.equal(k_in, wk.to(BF)) and torch.equal(v_in, wv.to(BF))
+    ops.set_frame_ctrl(ctrl, store, 0, 5, mem_frames, mem_tpos, ptr_frames, ptr_rel)
+    x = torch.randn((B * T, Cm), generator=g, device="cuda")
+    score = torch.tensor([[0.3], [-0.2]], device="cuda")
+    emb = torch.randn(Cm, generator=g, device="cuda")
+    before = store.mem.clone()
+    assert ops.finalize_memory(x, score, emb, B, ctrl=ctrl) is None
+    want = x.view(B, T, Cm).clone()
+    want[1] += emb
+    assert torch.equal(store.mem[5], want.to(BF)) and torch.equal(store.mem[4], before[4]) and torch.equal(store.mem[6], before[6])
+    a, c = torch.randn((B, 256), generator=g, device="cuda"), torch.randn((B, 1, 128, 128), generator=g, device="cuda")
+    ops.store_outputs(ctrl, a, score, c)
+    assert torch.equal(store.ptr[5], a) and torch.equal(store.score[5], score) and torch.equal(store.masks[5], c)
+    assert float(store.masks[4].abs().max()) == 0

@@ -20,7 +20,9 @@ POST_NONE, POST_SIGMOID_AFFINE, POST_BINARIZE_AFFINE = 0, 1, 2
 class GemmEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("col_scale", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int),
                 ("res_mod", C.c_int), ("act", C.c_int), ("out_f32", C.c_void_p), ("ldo_f32", C.c_int),
-                ("out_bf16", C.c_void_p), ("ldo_bf16", C.c_int)]
+                ("out_bf16", C.c_void_p), ("ldo_bf16", C.c_int),
+                ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_cols", C.c_int),
+                ("rope_rows_per_batch", C.c_int), ("rope_n_rope", C.c_int), ("rope_table_rows", C.c_int)]
 
 
 class FmhaParams(C.Structure):
@@ -30,6 +32,28 @@ class FmhaParams(C.Structure):
                 ("q_hs", C.c_int), ("k_hs", C.c_int), ("v_hs", C.c_int), ("o_hs", C.c_int),
                 ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("head_dim", C.c_int),
                 ("num_splits", C.c_int), ("o_part", C.c_void_p), ("ml_part", C.c_void_p), ("scale", C.c_float)]
+
+
+MAX_PTRS = 32
+
+
+class SkinnyParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_is", C.c_longlong), ("x_rs", C.c_longlong),
+                ("x2", C.c_void_p), ("x2_is", C.c_longlong), ("x2_rs", C.c_longlong),
+                ("row_select", C.c_void_p), ("x_sel_stride", C.c_longlong),
+                ("w", C.c_void_p), ("w_is", C.c_longlong), ("bias", C.c_void_p), ("b_is", C.c_longlong),
+                ("residual", C.c_void_p), ("r_is", C.c_longlong), ("r_rs", C.c_longlong),
+                ("out", C.c_void_p), ("o_is", C.c_longlong), ("o_rs", C.c_longlong),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("instances", C.c_int), ("act", C.c_int)]
+
+
+class FrameCtrl(C.Structure):
+    _fields_ = [("mem_store", C.c_void_p), ("ptr_store", C.c_void_p), ("score_store", C.c_void_p),
+                ("mask_store", C.c_void_p), ("mem_slot_stride", C.c_longlong), ("ptr_slot_stride", C.c_longlong),
+                ("score_slot_stride", C.c_longlong), ("mask_slot_stride", C.c_longlong),
+                ("cur_frame", C.c_int), ("n_mem", C.c_int), ("n_ptr", C.c_int), ("reserved", C.c_int),
+                ("mem_frame", C.c_int * MAX_MEMORY_FRAMES), ("mem_tpos", C.c_int * MAX_MEMORY_FRAMES),
+                ("ptr_frame", C.c_int * MAX_PTRS), ("ptr_rel", C.c_float * MAX_PTRS)]
 
 
 class MemoryFrames(C.Structure):
@@ -66,11 +90,18 @@ _SIGNATURES = {
     "usvm_resize_bilinear": [_P, _P, _LL, _I, _I, _I, _I, _I, _F, _F, _P],
     "usvm_resize_bilinear_aa": [_P, _P, _LL, _I, _I, _I, _I, _I, _P],
     "usvm_upscale1_ln_gelu": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
-    "usvm_upscale2_masks": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "usvm_finalize_memory": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "usvm_upscale2_masks": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P],
+    "usvm_finalize_memory": [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P],
+    "usvm_set_frame_ctrl": [_P, C.POINTER(FrameCtrl), _P],
+    "usvm_ptr_tpos": [_P, _P, _P, _P, _I, _P],
+    "usvm_build_memory_store": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "usvm_store_outputs": [_P, _P, _P, _I, _P, _I, _I, _I, _P],
     "usvm_small_mlp3": [_P, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _LL, _LL, _I, _I, _P],
-    "usvm_sam_select": [_P, _P, _P, _I, _F, _F, _F, _P, _P, _P, _I, _I, _P],
-    "usvm_objptr_mix": [_P, _P, _P, _I, _I, _P],
+    "usvm_gemm_skinny_f32": [C.POINTER(SkinnyParams), _P],
+    "usvm_attn_t2i_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
+    "usvm_attn_i2t_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
+    "usvm_sam_select": [_P, _P, _I, _I, _P, _I, _I, _F, _F, _F, _P, _P, _P, _I, _I, _P],
+    "usvm_objptr_mix": [_P, _P, _I, _P, _I, _I, _P],
     "usvm_point_embed": [_P, _P, _P, _P, _F, _P, _I, _P],
 }
 

@@ -14,7 +14,8 @@
 
 namespace {
 
-// one warp per output pixel, lanes over output channels (<= 64); weights [k*k*Cin][Cout] in smem
+// lanes cover (pixel, output channel) pairs: a warp handles 32 / Cout pixels when Cout < 32 (Cout a power of two),
+// one pixel with 2 channels per lane when Cout == 64; weights [k*k*Cin][Cout] staged in shared memory
 __global__ void __launch_bounds__(256)
 conv2d_small_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int gelu,
@@ -25,48 +26,58 @@ conv2d_small_kernel(const float* __restrict__ x, const float* __restrict__ wt, c
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) s_w[i] = wt[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int grp = Cout < 32 ? Cout : 32;       // lanes per pixel
+  const int ppw = 32 / grp;                    // pixels per warp
+  const int cpl = Cout > 32 ? Cout / 32 : 1;   // channels per lane (1 or 2)
+  const int c0 = lane % grp;
   const long long total = (long long)B * Ho * Wo;
-  for (long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); pix < total; pix += (long long)gridDim.x * 8) {
-    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+  const long long warp_id = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (long long base = warp_id * ppw; base < total; base += (long long)gridDim.x * 8 * ppw) {
+    const long long pix = base + lane / grp;
+    const bool live = pix < total;
     float acc0 = 0.f, acc1 = 0.f;
-    const int c0 = lane, c1 = lane + 32;
-    for (int ky = 0; ky < k; ++ky) {
-      const int y = oy * s - pad + ky;
-      if (y < 0 || y >= H) continue;
-      for (int kx = 0; kx < k; ++kx) {
-        const int xx = ox * s - pad + kx;
-        if (xx < 0 || xx >= W) continue;
-        const float* xp = x + (((long long)b * H + y) * W + xx) * Cin;
-        const float* wp = s_w + (ky * k + kx) * Cin * Cout;
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float v = xp[ci];
-          if (c0 < Cout) acc0 = fmaf(v, wp[ci * Cout + c0], acc0);
-          if (c1 < Cout) acc1 = fmaf(v, wp[ci * Cout + c1], acc1);
+    if (live) {
+      const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+      for (int ky = 0; ky < k; ++ky) {
+        const int y = oy * s - pad + ky;
+        if (y < 0 || y >= H) continue;
+        for (int kx = 0; kx < k; ++kx) {
+          const int xx = ox * s - pad + kx;
+          if (xx < 0 || xx >= W) continue;
+          const float* xp = x + (((long long)b * H + y) * W + xx) * Cin;
+          const float* wp = s_w + (ky * k + kx) * Cin * Cout;
+          for (int ci = 0; ci < Cin; ++ci) {
+            const float v = xp[ci];
+            acc0 = fmaf(v, wp[ci * Cout + c0], acc0);
+            if (cpl == 2) acc1 = fmaf(v, wp[ci * Cout + c0 + 32], acc1);
+          }
         }
       }
+      acc0 += bias[c0];
+      if (cpl == 2) acc1 += bias[c0 + 32];
     }
-    if (c0 < Cout) acc0 += bias[c0];
-    if (c1 < Cout) acc1 += bias[c1];
     if (ln_w) {
-      const float sum = warp_sum((c0 < Cout ? acc0 : 0.f) + (c1 < Cout ? acc1 : 0.f));
+      float sum = acc0 + (cpl == 2 ? acc1 : 0.f);
+      for (int o = grp >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       const float mean = sum / Cout;
-      const float d0 = c0 < Cout ? acc0 - mean : 0.f, d1 = c1 < Cout ? acc1 - mean : 0.f;
-      const float var = warp_sum(d0 * d0 + d1 * d1) / Cout;
-      const float rstd = 1.0f / sqrtf(var + eps);
-      if (c0 < Cout) acc0 = d0 * rstd * ln_w[c0] + ln_b[c0];
-      if (c1 < Cout) acc1 = d1 * rstd * ln_w[c1] + ln_b[c1];
+      const float d0 = acc0 - mean, d1 = cpl == 2 ? acc1 - mean : 0.f;
+      float var = d0 * d0 + d1 * d1;
+      for (int o = grp >> 1; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+      const float rstd = 1.0f / sqrtf(var / Cout + eps);
+      acc0 = d0 * rstd * ln_w[c0] + ln_b[c0];
+      if (cpl == 2) acc1 = d1 * rstd * ln_w[c0 + 32] + ln_b[c0 + 32];
     }
     if (gelu) {
       acc0 = gelu_erf(acc0);
       acc1 = gelu_erf(acc1);
     }
-    if (c0 < Cout) {
+    if (live) {
       if (out_f32) out_f32[pix * Cout + c0] = acc0;
       if (out_bf16) out_bf16[pix * Cout + c0] = __float2bfloat16(acc0);
-    }
-    if (c1 < Cout) {
-      if (out_f32) out_f32[pix * Cout + c1] = acc1;
-      if (out_bf16) out_bf16[pix * Cout + c1] = __float2bfloat16(acc1);
+      if (cpl == 2) {
+        if (out_f32) out_f32[pix * Cout + c0 + 32] = acc1;
+        if (out_bf16) out_bf16[pix * Cout + c0 + 32] = __float2bfloat16(acc1);
+      }
     }
   }
 }
@@ -211,12 +222,14 @@ inline int grid_for(long long total, int threads = 256) {
 extern "C" int usvm_conv2d_small(const float* x, const float* w_kkio, const float* bias, const float* ln_w,
                                  const float* ln_b, float eps, int gelu, float* out_f32, void* out_bf16, int B, int H,
                                  int W, int Cin, int Cout, int k, int stride, int pad, void* stream) {
-  if (!x || !w_kkio || !bias || (!out_f32 && !out_bf16) || Cout > 64 || Cout <= 0 || Cin <= 0) return USVM_ERR_ARG;
+  if (!x || !w_kkio || !bias || (!out_f32 && !out_bf16) || Cin <= 0) return USVM_ERR_ARG;
+  if (!(Cout == 1 || Cout == 2 || Cout == 4 || Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64)) return USVM_ERR_ARG;
   const size_t smem = (size_t)k * k * Cin * Cout * sizeof(float);
   if (smem > 48 * 1024) return USVM_ERR_ARG;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const long long pixels = (long long)B * Ho * Wo;
-  const int grid = (int)min((long long)148 * 8, (pixels + 7) / 8);
+  const int ppw = Cout < 32 ? 32 / Cout : 1;
+  const int grid = (int)max(1LL, min((long long)148 * 8, (pixels + 8LL * ppw - 1) / (8LL * ppw)));
   conv2d_small_kernel<<<grid, 256, smem, STREAM>>>(x, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32,
                                                    reinterpret_cast<bf16*>(out_bf16), B, H, W, Cin, Cout, k, stride,
                                                    pad, Ho, Wo);

@@ -57,7 +57,7 @@ upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, co
 // g2: [B*Hc*Wc, 4*32]; feat_s0: [B, 2Hc, 2Wc, 32]; hyper: [B, 4, 32]; masks: [B, 4, 2Hc, 2Wc]
 __global__ void __launch_bounds__(256)
 upscale2_masks_kernel(const float* __restrict__ g2, const float* __restrict__ feat, const float* __restrict__ hyper,
-                      float* __restrict__ masks, int B, int Hc, int Wc, int feat_shared) {
+                      int hyper_bs, float* __restrict__ masks, int B, int Hc, int Wc, int feat_shared) {
   const int lane = threadIdx.x & 31;
   const int Ho = 2 * Hc, Wo = 2 * Wc;
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -67,7 +67,7 @@ upscale2_masks_kernel(const float* __restrict__ g2, const float* __restrict__ fe
   const int q = (Y & 1) * 2 + (X & 1);
   const long long fpix = feat_shared ? (long long)Y * Wo + X : pix;
   const float v = gelu_erf(g2[src * 128 + q * 32 + lane] + feat[fpix * 32 + lane]);
-  const float* hp = hyper + (long long)b * 128;
+  const float* hp = hyper + (long long)b * hyper_bs;
   const float m0 = warp_sum(v * hp[lane]);
   const float m1 = warp_sum(v * hp[32 + lane]);
   const float m2 = warp_sum(v * hp[64 + lane]);
@@ -121,15 +121,16 @@ small_mlp3_kernel(const float* __restrict__ x, long long x_row_stride, long long
 
 // One block per object.  masks [B,4,HW]; iou [B,4]; score [B].  Writes the chosen low-res mask (gated),
 // the chosen token index (for the object pointer) and the chosen IoU.
-__global__ void __launch_bounds__(256)
-sam_select_kernel(const float* __restrict__ masks, const float* __restrict__ iou, const float* __restrict__ score,
-                  int multimask, float stab_delta, float stab_thresh, float no_obj_score, float* __restrict__ low_res,
-                  int* __restrict__ token_index, float* __restrict__ iou_out, int HW) {
+__global__ void __launch_bounds__(1024)
+sam_select_kernel(const float* __restrict__ masks, const float* __restrict__ iou, int iou_stride, int iou_is_logit,
+                  const float* __restrict__ score, int score_stride, int multimask, float stab_delta, float stab_thresh,
+                  float no_obj_score, float* __restrict__ low_res, int* __restrict__ token_index,
+                  float* __restrict__ iou_out, int HW) {
   __shared__ int s_cnt[2];
   __shared__ int s_pick;
   const int b = blockIdx.x;
   const float* mb = masks + (long long)b * 4 * HW;
-  const float* ib = iou + b * 4;
+  const float* ib = iou + (long long)b * iou_stride;
   if (threadIdx.x == 0) {
     s_cnt[0] = 0;
     s_cnt[1] = 0;
@@ -161,11 +162,11 @@ sam_select_kernel(const float* __restrict__ masks, const float* __restrict__ iou
   }
   __syncthreads();
   const int pick = s_pick;
-  const bool present = score[b] > 0.f;
+  const bool present = score[(long long)b * score_stride] > 0.f;
   if (threadIdx.x == 0) {
     // object pointer token: the multimask token when multimask output is on, else always token 0
     token_index[b] = multimask ? pick : 0;
-    iou_out[b] = ib[pick];
+    iou_out[b] = iou_is_logit ? 1.0f / (1.0f + expf(-ib[pick])) : ib[pick];
   }
   const float* src = mb + (long long)pick * HW;
   float* dst = low_res + (long long)b * HW;
@@ -173,12 +174,12 @@ sam_select_kernel(const float* __restrict__ masks, const float* __restrict__ iou
 }
 
 // obj_ptr = lam * ptr + (1 - lam) * no_obj_ptr, lam = score > 0  (sam2_base.py:1146-1156)
-__global__ void objptr_mix_kernel(float* __restrict__ ptr, const float* __restrict__ score,
+__global__ void objptr_mix_kernel(float* __restrict__ ptr, const float* __restrict__ score, int score_stride,
                                   const float* __restrict__ no_obj_ptr, int B, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
-  if (!(score[b] > 0.f)) ptr[i] = no_obj_ptr[c];
+  if (!(score[(long long)b * score_stride] > 0.f)) ptr[i] = no_obj_ptr[c];
 }
 
 // coords [B,P,2] in model pixels (+0.5 applied by the caller; padding point = 0), labels [B,P] int32
@@ -215,10 +216,10 @@ extern "C" int usvm_upscale1_ln_gelu(const float* g1, const float* feat_s1, cons
   return usvm_check_launch();
 }
 
-extern "C" int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, float* masks, int B,
-                                   int Hc, int Wc, int feat_shared, void* stream) {
+extern "C" int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, int hyper_bs,
+                                   float* masks, int B, int Hc, int Wc, int feat_shared, void* stream) {
   if (!g2 || !feat_s0 || !hyper || !masks) return USVM_ERR_ARG;
-  upscale2_masks_kernel<<<cdiv((long long)B * 4 * Hc * Wc, 8), 256, 0, STREAM>>>(g2, feat_s0, hyper, masks, B, Hc, Wc, feat_shared);
+  upscale2_masks_kernel<<<cdiv((long long)B * 4 * Hc * Wc, 8), 256, 0, STREAM>>>(g2, feat_s0, hyper, hyper_bs, masks, B, Hc, Wc, feat_shared);
   return usvm_check_launch();
 }
 
@@ -234,18 +235,20 @@ extern "C" int usvm_small_mlp3(const float* x, long long x_row_stride, long long
   return usvm_check_launch();
 }
 
-extern "C" int usvm_sam_select(const float* masks, const float* iou, const float* score, int multimask,
-                               float stab_delta, float stab_thresh, float no_obj_score, float* low_res,
-                               int* token_index, float* iou_out, int B, int HW, void* stream) {
+extern "C" int usvm_sam_select(const float* masks, const float* iou, int iou_stride, int iou_is_logit,
+                               const float* score, int score_stride, int multimask, float stab_delta,
+                               float stab_thresh, float no_obj_score, float* low_res, int* token_index, float* iou_out,
+                               int B, int HW, void* stream) {
   if (!masks || !iou || !score || !low_res || !token_index || !iou_out || B <= 0) return USVM_ERR_ARG;
-  sam_select_kernel<<<B, 256, 0, STREAM>>>(masks, iou, score, multimask, stab_delta, stab_thresh, no_obj_score,
-                                           low_res, token_index, iou_out, HW);
+  sam_select_kernel<<<B, 1024, 0, STREAM>>>(masks, iou, iou_stride, iou_is_logit, score, score_stride, multimask,
+                                            stab_delta, stab_thresh, no_obj_score, low_res, token_index, iou_out, HW);
   return usvm_check_launch();
 }
 
-extern "C" int usvm_objptr_mix(float* ptr, const float* score, const float* no_obj_ptr, int B, int C, void* stream) {
+extern "C" int usvm_objptr_mix(float* ptr, const float* score, int score_stride, const float* no_obj_ptr, int B, int C,
+                               void* stream) {
   if (!ptr || !score || !no_obj_ptr || B <= 0) return USVM_ERR_ARG;
-  objptr_mix_kernel<<<cdiv((long long)B * C, 256), 256, 0, STREAM>>>(ptr, score, no_obj_ptr, B, C);
+  objptr_mix_kernel<<<cdiv((long long)B * C, 256), 256, 0, STREAM>>>(ptr, score, score_stride, no_obj_ptr, B, C);
   return usvm_check_launch();
 }
 

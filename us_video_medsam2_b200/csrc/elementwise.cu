@@ -36,6 +36,41 @@ layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__
   }
 }
 
+// single-read variant: the row lives in registers (NV = C / 32 values per lane)
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
+                     float eps, int gelu, float* out_f32, int ldo_f32, bf16* out_bf16, int ldo_bf16, int rows) {
+  constexpr int C = NV * 32;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j] = xr[j * 32 + lane];
+    s += v[j];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j] -= mean;
+    q = fmaf(v[j], v[j], q);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = j * 32 + lane;
+    float y = v[j] * rstd * w[c] + b[c];
+    if (gelu) y = gelu_erf(y);
+    if (out_f32) out_f32[row * ldo_f32 + c] = y;
+    if (out_bf16) out_bf16[row * ldo_bf16 + c] = __float2bfloat16(y);
+  }
+}
+
 // out[r, c] = alpha * x[r % x_mod, c] + beta * y[r % y_mod, c]   (fp32 in; fp32 and/or bf16 out)
 __global__ void axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, float beta,
                                   int x_mod, int y_mod, float* out_f32, bf16* out_bf16, long long rows, int C) {
@@ -267,16 +302,94 @@ __global__ void build_memory_kernel(const usvm_memory_frames fr, const float* __
 
 // memory feature epilogue (sam2_base.py:1488-1496, predictor :956): add no_obj_embed_spatial where the object
 // score is <= 0, round to bf16 into the memory-bank slot
-__global__ void finalize_memory_kernel(const float* __restrict__ x, const float* __restrict__ score,
+__global__ void finalize_memory_kernel(const float* __restrict__ x, const float* __restrict__ score, int score_stride,
                                        const float* __restrict__ no_obj_embed, bf16* __restrict__ mem, int B, int T,
-                                       int Cm) {
+                                       int Cm, const usvm_frame_ctrl* __restrict__ ctrl) {
   const long long total = (long long)B * T * Cm;
+  if (!mem) mem = reinterpret_cast<bf16*>(ctrl->mem_store) + (long long)ctrl->cur_frame * ctrl->mem_slot_stride;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cm);
     const int b = (int)(i / ((long long)T * Cm));
     float v = x[i];
-    if (!(score[b] > 0.f)) v += no_obj_embed[c];
+    if (!(score[(long long)b * score_stride] > 0.f)) v += no_obj_embed[c];
     mem[i] = __float2bfloat16(v);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Device-indexed variants for the CUDA-graph steady-state frame: which stored frames feed the memory
+// bank is read from a small control block in device memory, so one captured graph serves every frame.
+// ---------------------------------------------------------------------------------------------
+// temporal position encoding of the object pointers (get_1d_sine_pe + obj_ptr_tpos_proj,
+// sam2_utils.py:64-74, sam2_base.py:1402-1408): out[p*4 + q, c] = W[c, :] . [sin(rel/dim_t), cos(rel/dim_t)] + b[c]
+__global__ void __launch_bounds__(64)
+ptr_tpos_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ W, const float* __restrict__ bias,
+                float* __restrict__ out) {
+  __shared__ float pe[256];
+  const int p = blockIdx.x, c = threadIdx.x;
+  const float rel = ctrl->ptr_rel[p];
+  for (int j = c; j < 128; j += 64) {
+    const float dim_t = powf(10000.0f, (float)(2 * (j / 2)) / 128.0f);
+    const float e = rel / dim_t;
+    pe[j] = sinf(e);
+    pe[128 + j] = cosf(e);
+  }
+  __syncthreads();
+  float acc = bias[c];
+  const float* wr = W + c * 256;
+  for (int j = 0; j < 256; ++j) acc = fmaf(wr[j], pe[j], acc);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) out[(p * 4 + q) * 64 + c] = acc;
+}
+
+__global__ void build_memory_store_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ pos,
+                                          const float* __restrict__ tpos, const float* __restrict__ ptr_pos,
+                                          bf16* __restrict__ k_in, bf16* __restrict__ v_in, int B, int T, int Cm,
+                                          int n_mem, int n_ptr) {
+  const bf16* __restrict__ mem_store = reinterpret_cast<const bf16*>(ctrl->mem_store);
+  const float* __restrict__ ptr_store = ctrl->ptr_store;
+  const long long mem_frame_stride = ctrl->mem_slot_stride, ptr_frame_stride = ctrl->ptr_slot_stride;
+  const int ptr_row0 = n_mem * T;
+  const int Nk = ptr_row0 + n_ptr * 4;
+  const long long total = (long long)B * Nk * Cm;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cm);
+    const long long t = i / Cm;
+    const int row = (int)(t % Nk);
+    const int b = (int)(t / Nk);
+    float m, pe;
+    if (row < ptr_row0) {
+      const int f = row / T, tok = row - f * T;
+      m = __bfloat162float(mem_store[(long long)ctrl->mem_frame[f] * mem_frame_stride + ((long long)b * T + tok) * Cm + c]);
+      pe = pos[tok * Cm + c] + tpos[ctrl->mem_tpos[f] * Cm + c];
+    } else {
+      const int pr = row - ptr_row0;  // pointer p = pr / 4 contributes channels [(pr % 4) * Cm, +Cm)
+      m = ptr_store[(long long)ctrl->ptr_frame[pr >> 2] * ptr_frame_stride + (long long)b * (4 * Cm) + (pr & 3) * Cm + c];
+      pe = ptr_pos[pr * Cm + c];
+    }
+    k_in[i] = __float2bfloat16(m + pe);
+    v_in[i] = __float2bfloat16(m);
+  }
+}
+
+__global__ void set_frame_ctrl_kernel(usvm_frame_ctrl* dst, const usvm_frame_ctrl v) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
+}
+
+// slot ctrl->cur_frame of the pointer / score / mask stores <- this frame's outputs
+__global__ void store_outputs_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ obj_ptr,
+                                     const float* __restrict__ score, int score_stride, const float* __restrict__ masks,
+                                     int B, int ptr_dim, int hw) {
+  const long long slot = ctrl->cur_frame;
+  const long long n0 = (long long)B * ptr_dim, n1 = B, n2 = (long long)B * hw;
+  float* d0 = ctrl->ptr_store + slot * ctrl->ptr_slot_stride;
+  float* d1 = ctrl->score_store + slot * ctrl->score_slot_stride;
+  float* d2 = ctrl->mask_store + slot * ctrl->mask_slot_stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1 + n2; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n0) d0[i] = obj_ptr[i];
+    else if (i < n0 + n1) d1[i - n0] = score[(i - n0) * score_stride];
+    else d2[i - n0 - n1] = masks[i - n0 - n1];
   }
 }
 
@@ -294,8 +407,18 @@ extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const flo
                               float* out_f32, int ldo_f32, void* out_bf16, int ldo_bf16, int rows, int C,
                               void* stream) {
   if (!x || !w || !b || rows <= 0 || C <= 0 || (!out_f32 && !out_bf16)) return USVM_ERR_ARG;
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, STREAM>>>(x, ldx, w, b, eps, gelu, out_f32, ldo_f32,
-                                                     reinterpret_cast<bf16*>(out_bf16), ldo_bf16, rows, C);
+  bf16* ob = reinterpret_cast<bf16*>(out_bf16);
+#define LN_CASE(NV)                                                                                              \
+  case NV * 32:                                                                                                  \
+    layernorm_reg_kernel<NV><<<cdiv(rows, 8), 256, 0, STREAM>>>(x, ldx, w, b, eps, gelu, out_f32, ldo_f32, ob,   \
+                                                                ldo_bf16, rows);                                 \
+    break;
+  switch (C) {
+    LN_CASE(2) LN_CASE(3) LN_CASE(6) LN_CASE(8) LN_CASE(12) LN_CASE(24)
+    default:
+      layernorm_kernel<<<cdiv(rows, 8), 256, 0, STREAM>>>(x, ldx, w, b, eps, gelu, out_f32, ldo_f32, ob, ldo_bf16, rows, C);
+  }
+#undef LN_CASE
   return usvm_check_launch();
 }
 
@@ -385,10 +508,46 @@ extern "C" int usvm_build_memory(const usvm_memory_frames* frames, const float* 
   return usvm_check_launch();
 }
 
-extern "C" int usvm_finalize_memory(const float* x, const float* score, const float* no_obj_embed, void* mem_bf16,
-                                    int B, int T, int Cm, void* stream) {
-  if (!x || !score || !no_obj_embed || !mem_bf16 || B <= 0) return USVM_ERR_ARG;
-  finalize_memory_kernel<<<grid_for((long long)B * T * Cm), 256, 0, STREAM>>>(x, score, no_obj_embed,
-                                                                             reinterpret_cast<bf16*>(mem_bf16), B, T, Cm);
+extern "C" int usvm_finalize_memory(const float* x, const float* score, int score_stride, const float* no_obj_embed,
+                                    void* mem_bf16, int B, int T, int Cm, const usvm_frame_ctrl* ctrl_dev,
+                                    void* stream) {
+  if (!x || !score || !no_obj_embed || (!mem_bf16 && !ctrl_dev) || B <= 0) return USVM_ERR_ARG;
+  finalize_memory_kernel<<<grid_for((long long)B * T * Cm), 256, 0, STREAM>>>(
+      x, score, score_stride, no_obj_embed, reinterpret_cast<bf16*>(mem_bf16), B, T, Cm, ctrl_dev);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_ptr_tpos(const usvm_frame_ctrl* ctrl_dev, const float* W, const float* bias, float* out, int n_ptr,
+                             void* stream) {
+  if (!ctrl_dev || !W || !bias || !out || n_ptr <= 0 || n_ptr > USVM_MAX_PTRS) return USVM_ERR_ARG;
+  ptr_tpos_kernel<<<n_ptr, 64, 0, STREAM>>>(ctrl_dev, W, bias, out);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_build_memory_store(const usvm_frame_ctrl* ctrl_dev, const float* pos, const float* tpos,
+                                       const float* ptr_pos, void* k_in, void* v_in, int B, int T, int Cm, int n_mem,
+                                       int n_ptr, void* stream) {
+  if (!ctrl_dev || !pos || !tpos || !k_in || !v_in || n_mem < 0 || n_mem > USVM_MAX_MEMORY_FRAMES || n_ptr < 0 ||
+      n_ptr > USVM_MAX_PTRS || Cm != 64)
+    return USVM_ERR_ARG;
+  if (n_ptr > 0 && !ptr_pos) return USVM_ERR_ARG;
+  const long long total = (long long)B * (n_mem * T + n_ptr * 4) * Cm;
+  if (total <= 0) return USVM_ERR_ARG;
+  build_memory_store_kernel<<<grid_for(total), 256, 0, STREAM>>>(
+      ctrl_dev, pos, tpos, ptr_pos, reinterpret_cast<bf16*>(k_in), reinterpret_cast<bf16*>(v_in), B, T, Cm, n_mem, n_ptr);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_store_outputs(const usvm_frame_ctrl* ctrl_dev, const float* obj_ptr, const float* score,
+                                  int score_stride, const float* masks, int B, int ptr_dim, int hw, void* stream) {
+  if (!ctrl_dev || !obj_ptr || !score || !masks || B <= 0) return USVM_ERR_ARG;
+  store_outputs_kernel<<<grid_for((long long)B * (ptr_dim + 1 + hw)), 256, 0, STREAM>>>(ctrl_dev, obj_ptr, score,
+                                                                                       score_stride, masks, B, ptr_dim, hw);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_set_frame_ctrl(usvm_frame_ctrl* ctrl_dev, const usvm_frame_ctrl* ctrl_host, void* stream) {
+  if (!ctrl_dev || !ctrl_host) return USVM_ERR_ARG;
+  set_frame_ctrl_kernel<<<1, 32, 0, STREAM>>>(ctrl_dev, *ctrl_host);  // by-value kernel parameter: no H2D copy, no sync
   return usvm_check_launch();
 }

@@ -88,6 +88,7 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
 extern "C" int usvm_gemm_simt(const void* A, int a_is_bf16, int lda, const void* W, int w_is_bf16, int ldw,
                               const usvm_gemm_epilogue* ep, int M, int N, int K, void* stream) {
   if (!A || !W || !ep || M <= 0 || N <= 0 || K <= 0) return USVM_ERR_ARG;
+  if (ep->rope_cos) return USVM_ERR_ARG;  // fused RoPE exists on the tensor-core kernel only
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a_is_bf16 && w_is_bf16) return launch<bf16, bf16>(A, lda, W, ldw, ep, M, N, K, s);
   if (!a_is_bf16 && !w_is_bf16) return launch<float, float>(A, lda, W, ldw, ep, M, N, K, s);

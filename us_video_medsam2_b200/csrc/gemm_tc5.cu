@@ -136,6 +136,24 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
+        if (ep.rope_cos && col0 < ep.rope_cols) {
+          const int rb = row % ep.rope_rows_per_batch;
+          if (rb < ep.rope_n_rope) {
+            const long long t0 = (long long)(rb % ep.rope_table_rows) * 128 + ((col0 & 255) >> 1);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float4 c4 = *reinterpret_cast<const float4*>(ep.rope_cos + t0 + (j >> 1));
+              const float4 s4 = *reinterpret_cast<const float4*>(ep.rope_sin + t0 + (j >> 1));
+              const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float a = v[j + 2 * q], b = v[j + 2 * q + 1];
+                v[j + 2 * q] = a * cs[q] - b * sn[q];
+                v[j + 2 * q + 1] = a * sn[q] + b * cs[q];
+              }
+            }
+          }
+        }
         if (ep.act != USVM_ACT_NONE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
@@ -253,6 +271,10 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
   if (ep->out_f32 && ((ep->ldo_f32 % 4) || (reinterpret_cast<uintptr_t>(ep->out_f32) & 15))) return USVM_ERR_ARG;
   if (ep->out_bf16 && ((ep->ldo_bf16 % 8) || (reinterpret_cast<uintptr_t>(ep->out_bf16) & 15))) return USVM_ERR_ARG;
   if (ep->residual && ((ep->ldr % 4) || (reinterpret_cast<uintptr_t>(ep->residual) & 15))) return USVM_ERR_ARG;
+  if (ep->rope_cos && (!ep->rope_sin || (N % 32) || (ep->rope_cols % 32) || ep->rope_rows_per_batch <= 0 ||
+                       ep->rope_table_rows <= 0 || (reinterpret_cast<uintptr_t>(ep->rope_cos) & 15) ||
+                       (reinterpret_cast<uintptr_t>(ep->rope_sin) & 15)))
+    return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = block_n;
   if (bn <= 0) {

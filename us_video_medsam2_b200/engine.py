@@ -156,6 +156,12 @@ class PackedWeights:
                 l1=(w16(p + "linear1.weight"), f32(p + "linear1.bias")),
                 l2=(w16(p + "linear2.weight"), f32(p + "linear2.bias"))))
         self.ma_norm = (f32("memory_attention.norm.weight"), f32("memory_attention.norm.bias"))
+        # the cross-attention key / value inputs are the same for all 4 layers: project them with ONE GEMM each
+        ca = "memory_attention.layers.{}.cross_attn_image."
+        self.ca_k_all = (dev(torch.cat([g(ca.format(l) + "k_proj.weight") for l in range(4)]), BF16),
+                         dev(torch.cat([g(ca.format(l) + "k_proj.bias") for l in range(4)])))
+        self.ca_v_all = (dev(torch.cat([g(ca.format(l) + "v_proj.weight") for l in range(4)]), BF16),
+                         dev(torch.cat([g(ca.format(l) + "v_proj.bias") for l in range(4)])))
         c, s = _rope_tables(256, 32, 32)
         self.rope_cos, self.rope_sin = dev(c), dev(s)
 
@@ -223,6 +229,24 @@ class PackedWeights:
                                         norms=[lin(p + f"norm{j}.") for j in (1, 2, 3, 4)]))
         self.dec_final = attn(tr + "final_attn_token_to_image.")
         self.dec_final_norm = lin(tr + "norm_final_attn.")
+        # image-side projections of one layer share their input (`keys`): fuse [t2i.k | t2i.v | i2t.q] into one
+        # GEMM; the `+ key_pe` of k and q becomes a constant additive table  dense_pe @ W^T  (linearity)
+        dpe = self.dense_pe.detach().cpu().double()
+
+        def pe_table(key, zero_cols=0):
+            return (dpe @ g(key).double().t()).float()
+
+        for l, Lyr in enumerate(self.dec_layers):
+            p = tr + f"layers.{l}."
+            t2i, i2t = p + "cross_attn_token_to_image.", p + "cross_attn_image_to_token."
+            Lyr["img_w"] = dev(torch.cat([g(t2i + "k_proj.weight"), g(t2i + "v_proj.weight"), g(i2t + "q_proj.weight")]))
+            Lyr["img_b"] = dev(torch.cat([g(t2i + "k_proj.bias"), g(t2i + "v_proj.bias"), g(i2t + "q_proj.bias")]))
+            Lyr["img_pe"] = dev(torch.cat([pe_table(t2i + "k_proj.weight"), torch.zeros(1024, 128),
+                                           pe_table(i2t + "q_proj.weight")], dim=1))
+        fin = tr + "final_attn_token_to_image."
+        self.dec_final["img_w"] = dev(torch.cat([g(fin + "k_proj.weight"), g(fin + "v_proj.weight")]))
+        self.dec_final["img_b"] = dev(torch.cat([g(fin + "k_proj.bias"), g(fin + "v_proj.bias")]))
+        self.dec_final["img_pe"] = dev(torch.cat([pe_table(fin + "k_proj.weight"), torch.zeros(1024, 128)], dim=1))
         self.out_tokens = dev(torch.cat([g(d + "obj_score_token.weight"), g(d + "iou_token.weight"),
                                          g(d + "mask_tokens.weight")]))  # [6, 256]
         up = d + "output_upscaling."
@@ -239,6 +263,22 @@ class PackedWeights:
                          for j in range(3) for kind in ("weight", "bias"))
 
         self.hyper = mlp3([d + f"output_hypernetworks_mlps.{j}." for j in range(4)])
+        # the six token heads [object score, IoU, hyper 0..3] read token rows 0..5 in that order: one stacked MLP
+        # (last layer zero-padded to 32 outputs)
+        heads = [d + "pred_obj_score_head.", d + "iou_prediction_head."] + [d + f"output_hypernetworks_mlps.{j}."
+                                                                            for j in range(4)]
+
+        def pad32(t):
+            out = torch.zeros((32,) + tuple(t.shape[1:]))
+            out[: t.shape[0]] = t
+            return out
+
+        self.heads6 = [dev(torch.stack([g(p + "layers.0.weight") for p in heads])),
+                       dev(torch.stack([g(p + "layers.0.bias") for p in heads])),
+                       dev(torch.stack([g(p + "layers.1.weight") for p in heads])),
+                       dev(torch.stack([g(p + "layers.1.bias") for p in heads])),
+                       dev(torch.stack([pad32(g(p + "layers.2.weight")) for p in heads])),
+                       dev(torch.stack([pad32(g(p + "layers.2.bias")) for p in heads]))]
         self.iou_head = mlp3([d + "iou_prediction_head."])
         self.score_head = mlp3([d + "pred_obj_score_head."])
         self.obj_ptr_proj = mlp3(["obj_ptr_proj."])
@@ -303,32 +343,30 @@ class Engine:
         return pair[0], pair[1]
 
     # ---------------------------------------------------------------- memory attention
-    def memory_attention(self, feat, mem_frames, tpos_rows, ptrs, ptr_pos, B):
-        """feat fp32 [1024,256] (one frame, shared by the B objects); mem_frames: list of bf16 [B,1024,64];
-        ptrs fp32 [B,P*4,64] or None.  Returns fp32 [B*1024, 256]
-        (MemoryAttention.forward, memory_attention.py:119-169)."""
+    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B):
+        """feat fp32 [1024,256] (one frame, shared by the B objects); k_in / v_in bf16 [B, Nk, 64] assembled memory
+        (k_in already carries the position encodings), the last n_ptr_tok rows are object-pointer tokens (no RoPE).
+        Returns fp32 [B*1024, 256]  (MemoryAttention.forward, memory_attention.py:119-169; RoPEAttention,
+        sam/transformer.py:311-360).  RoPE is fused into the q / k projection epilogues; the key / value
+        projections of the 4 layers are batched into one GEMM each."""
         w = self.w
         T = 1024
+        cs, sn = w.rope_cos, w.rope_sin
         x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T)
-        k_in, v_in, Nk = ops.build_memory(mem_frames, tpos_rows, w.mem_pos, w.maskmem_tpos, ptrs, ptr_pos, B)
-        n_ptr = 0 if ptrs is None else ptrs.shape[1]
         k_in2, v_in2 = k_in.view(B * Nk, 64), v_in.view(B * Nk, 64)
-        for L in w.ma_layers:
+        _, k_all = ops.gemm_bf16(k_in2, w.ca_k_all[0], bias=w.ca_k_all[1], bf16=True,
+                                 rope=(cs, sn, 1024, Nk, Nk - n_ptr_tok))          # [B*Nk, 4*256], rotated
+        _, v_all = ops.gemm_bf16(v_in2, w.ca_v_all[0], bias=w.ca_v_all[1], bf16=True)  # [B*Nk, 4*256]
+        for li, L in enumerate(w.ma_layers):
             _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
-            qkv32, qkv16 = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], f32=True, bf16=True)
-            q = ops.rope(qkv32, 0, w.rope_cos, w.rope_sin, T, T)
-            k = ops.rope(qkv32, 256, w.rope_cos, w.rope_sin, T, T)
-            o = ops.fmha(q, k, qkv16, B, 1, T, T, 256, (0, T * 256, 256, 256), (0, T * 256, 256, 256),
+            _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
+            o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
                          (512, T * 768, 768, 256), num_splits=self._splits(B, T))
             x, _ = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True)
             _, h = ops.layernorm(x, *L["n2"], 1e-5, bf16=True)
-            q32, _ = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], f32=True)
-            q = ops.rope(q32, 0, w.rope_cos, w.rope_sin, T, T)
-            k32, _ = ops.gemm_bf16(k_in2, L["ca_k"][0], bias=L["ca_k"][1], f32=True)
-            k = ops.rope(k32, 0, w.rope_cos, w.rope_sin, Nk, Nk - n_ptr)
-            _, v = ops.gemm_bf16(v_in2, L["ca_v"][0], bias=L["ca_v"][1], bf16=True)
-            o = ops.fmha(q, k, v, B, 1, T, Nk, 256, (0, T * 256, 256, 256), (0, Nk * 256, 256, 256),
-                         (0, Nk * 256, 256, 256), num_splits=self._splits(B, Nk))
+            _, q = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], bf16=True, rope=(cs, sn, 256, T, T))
+            o = ops.fmha(q, k_all, v_all, B, 1, T, Nk, 256, (0, T * 256, 256, 256), (li * 256, Nk * 1024, 1024, 256),
+                         (li * 256, Nk * 1024, 1024, 256), num_splits=self._splits(B, Nk))
             x, _ = ops.gemm_bf16(o.view(B * T, 256), L["ca_o"][0], bias=L["ca_o"][1], residual=x, f32=True)
             _, h = ops.layernorm(x, *L["n3"], 1e-5, bf16=True)
             _, m = ops.gemm_bf16(h, L["l1"][0], bias=L["l1"][1], act=ACT_RELU, bf16=True)
@@ -341,19 +379,38 @@ class Engine:
         want = max(1, 148 // (16 * B))
         return max(1, min(want, tiles))
 
-    # ---------------------------------------------------------------- SAM heads
-    def _dec_attn(self, A, q_in, k_in, v_in, B, Nq, Nk, dh):
-        q = ops.gemm_f32(q_in, *A["q"])
-        k = ops.gemm_f32(k_in, *A["k"])
-        v = ops.gemm_f32(v_in, *A["v"])
-        o = ops.attn_small(q, k, v, B, 8, Nq, Nk, dh)
-        return o
+    def assemble_memory(self, ctrl, B, n_mem, n_ptr):
+        """Memory-bank assembly from the frame store named by the device control block
+        (sam2_base.py:1344-1437): returns (k_in, v_in, Nk, n_ptr_tokens)."""
+        w = self.w
+        ptr_pos = ops.ptr_tpos(ctrl, *w.tpos_proj, n_ptr) if n_ptr > 0 else None
+        k_in, v_in, Nk = ops.build_memory_store(ctrl, w.mem_pos, w.maskmem_tpos, ptr_pos, B, n_mem, n_ptr)
+        return k_in, v_in, Nk, 4 * n_ptr
 
+    def track_frame(self, f, ctrl, B, n_mem, n_ptr, video_hw, fill_hole_area):
+        """One steady-state tracked frame, entirely on the device and free of host-dependent control flow (so it can
+        be captured in a CUDA graph): memory attention over the bank named by `ctrl`, SAM heads with multimask
+        output, memory encoder, hole filling, video-resolution resize.  Everything the frame leaves behind is
+        written into slot ctrl->cur_frame of the frame store.  f: dict(feat, feat_bf16, feat_s0, feat_s1) of this
+        frame.  Returns (video_res logits [B,1,H,W], hole-filled low-res logits [B,1,128,128])."""
+        k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
+        pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B)
+        o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, self.no_point_tokens(B), multimask=True)
+        mask_in = self.mem_mask_input(o["low"], False)
+        self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl)
+        pm = ops.fill_holes(o["low"], fill_hole_area) if fill_hole_area > 0 else o["low"]
+        ops.store_outputs(ctrl, o["obj_ptr"], o["score"], pm)
+        vh, vw = video_hw
+        video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
+        return video, pm
+
+    # ---------------------------------------------------------------- SAM heads
     def sam_heads(self, pix_feat, feat_s0, feat_s1, B, sparse, dense=None, multimask=True, feat_shared=True):
         """pix_feat fp32 [B*1024,256]; sparse fp32 [B,P,256] prompt tokens; dense fp32 [B*1024,256] or None
         (-> no_mask_embed).  Returns dict(low [B,1,128,128], obj_ptr [B,256], score [B,1], iou [B,1]).
         (_forward_sam_heads sam2_base.py:1010-1166 + MaskDecoder mask_decoder.py:110-295 +
-        TwoWayTransformer transformer.py:90-212)"""
+        TwoWayTransformer transformer.py:90-212).  Token-side linears (8 rows per object) run on the skinny
+        GEMM, image-side projections of a layer are one fused GEMM, attention on the t2i / i2t kernels."""
         w = self.w
         T = 1024
         if dense is None:
@@ -365,46 +422,55 @@ class Engine:
         tokens = torch.cat([w.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(B * Nt, 256).contiguous()
         queries, keys = tokens, src
         ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
+        sk = ops.gemm_skinny
         for l, Lyr in enumerate(w.dec_layers):
-            sa = Lyr["sa"]
+            sa, t2i, i2t = Lyr["sa"], Lyr["t2i"], Lyr["i2t"]
             if l == 0:
-                qkv = ops.gemm_f32(queries, sa["qkv_w"], sa["qkv_b"])
+                qkv = sk(queries, sa["qkv_w"], sa["qkv_b"])
                 o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
-                queries = ops.gemm_f32(o, *sa["o"])
+                queries = sk(o, *sa["o"])
             else:
-                qpe, _ = ops.axpby(queries, tokens)
-                qk = ops.gemm_f32(qpe, sa["qkv_w"][:512], sa["qkv_b"][:512])
-                v = ops.gemm_f32(queries, *sa["v"])
+                qk = sk(queries, sa["qkv_w"][:512], sa["qkv_b"][:512], x2=tokens)
+                v = sk(queries, *sa["v"])
                 o = ops.attn_small(qk[:, 0:256], qk[:, 256:512], v, B, 8, Nt, Nt, 32)
-                queries = ops.gemm_f32(o, *sa["o"], residual=queries)
+                queries = sk(o, *sa["o"], residual=queries)
             queries = ln(queries, Lyr["norms"][0])
-            qpe, _ = ops.axpby(queries, tokens)
-            kpe, _ = ops.axpby(keys, w.dense_pe, rows=B * T, y_mod=T)
-            o = self._dec_attn(Lyr["t2i"], qpe, kpe, keys, B, Nt, T, 16)
-            queries = ln(ops.gemm_f32(o, *Lyr["t2i"]["o"], residual=queries), Lyr["norms"][1])
-            m = ops.gemm_f32(queries, *Lyr["mlp"][0], act=ACT_RELU)
-            queries = ln(ops.gemm_f32(m, *Lyr["mlp"][1], residual=queries), Lyr["norms"][2])
-            qpe, _ = ops.axpby(queries, tokens)
-            o = self._dec_attn(Lyr["i2t"], kpe, qpe, queries, B, T, Nt, 16)
-            keys = ln(ops.gemm_f32(o, *Lyr["i2t"]["o"], residual=keys), Lyr["norms"][3])
-        qpe, _ = ops.axpby(queries, tokens)
-        kpe, _ = ops.axpby(keys, w.dense_pe, rows=B * T, y_mod=T)
-        o = self._dec_attn(w.dec_final, qpe, kpe, keys, B, Nt, T, 16)
-        hs = ln(ops.gemm_f32(o, *w.dec_final["o"], residual=queries), w.dec_final_norm)  # [B*Nt, 256]
+            q = sk(queries, *t2i["q"], x2=tokens)
+            img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T)  # [B*T, 384]
+            o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
+            queries = ln(sk(o, *t2i["o"], residual=queries), Lyr["norms"][1])
+            m = sk(queries, *Lyr["mlp"][0], act=ACT_RELU)
+            queries = ln(sk(m, *Lyr["mlp"][1], residual=queries), Lyr["norms"][2])
+            k2 = sk(queries, *i2t["k"], x2=tokens)
+            v2 = sk(queries, *i2t["v"])
+            o = ops.attn_i2t(img[:, 256:384], k2, v2, B, T, Nt)
+            keys = ln(ops.gemm_f32(o, *i2t["o"], residual=keys), Lyr["norms"][3])
+        fin = w.dec_final
+        q = sk(queries, *fin["q"], x2=tokens)
+        img = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T)  # [B*T, 256]
+        o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
+        hs = ln(sk(o, *fin["o"], residual=queries), w.dec_final_norm)  # [B*Nt, 256]
 
         g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b)
         u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_shared)
         g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b)
-        base, row = hs.data_ptr(), Nt * 256
-        hyper = ops.small_mlp3(base + 4 * 2 * 256, row, 256, None, w.hyper, 32, B, 4, hs)
-        masks = ops.upscale2_masks(g2, feat_s0, hyper, B, 64, 64, feat_shared)
-        iou = ops.small_mlp3(base + 4 * 256, row, 256, None, w.iou_head, 4, B, 1, hs, sigmoid=True).view(B, 4)
-        score = ops.small_mlp3(base, row, 256, None, w.score_head, 1, B, 1, hs).view(B, 1)
-        low, idx, iou_sel = ops.sam_select(masks, iou, score, multimask, self.cfg.dynamic_multimask_stability_delta,
-                                           self.cfg.dynamic_multimask_stability_thresh, NO_OBJ_SCORE)
-        ptr = ops.small_mlp3(base + 4 * 2 * 256, row, 256, idx, w.obj_ptr_proj, 256, B, 1, hs).view(B, 256)
+        # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
+        W1, b1, W2, b2, W3, b3 = w.heads6
+        h1 = sk(None, W1, b1, M=B, x_ptr=hs.data_ptr(), x_rs=Nt * 256, x_is=256, act=ACT_RELU, instances=6)
+        h2 = sk(h1, W2, b2, M=B, x_rs=6 * 256, x_is=256, act=ACT_RELU, instances=6)
+        y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
+        masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 64, 64, feat_shared, hyper_bs=192)
+        low, idx, iou_sel = ops.sam_select(masks, y[:, 32:], y, multimask, self.cfg.dynamic_multimask_stability_delta,
+                                           self.cfg.dynamic_multimask_stability_thresh, NO_OBJ_SCORE, iou_stride=192,
+                                           score_stride=192, iou_is_logit=True)
+        score = y[:, 0:1].contiguous()
+        P1, pb1, P2, pb2, P3, pb3 = w.obj_ptr_proj
+        t1 = sk(None, P1[0], pb1[0], M=B, x_ptr=hs.data_ptr() + 4 * 2 * 256, x_rs=Nt * 256, row_select=idx,
+                x_sel_stride=256, act=ACT_RELU)
+        t2 = sk(t1, P2[0], pb2[0], act=ACT_RELU)
+        ptr = sk(t2, P3[0], pb3[0])
         ops.objptr_mix_(ptr, score, w.no_obj_ptr)
-        return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, ious_all=iou)
+        return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36])
 
     def embed_points(self, coords, labels):
         """PromptEncoder._embed_points with pad=True (prompt_encoder.py:79-103): coords [B,P,2] model pixels."""
@@ -443,9 +509,10 @@ class Engine:
         return dict(low=low, high=high, obj_ptr=ptr, score=score)
 
     # ---------------------------------------------------------------- memory encoder
-    def encode_memory(self, feat_bf16, mask_in512, score, B):
+    def encode_memory(self, feat_bf16, mask_in512, score, B, ctrl=None):
         """mask_in512 fp32 [B,512,512]: already sigmoid*20-10 / binarised (see Engine.mem_mask_input);
-        feat_bf16 [1024,256] raw frame features.  Returns bf16 token-major memory [B,1024,64]
+        feat_bf16 [1024,256] raw frame features.  Returns bf16 token-major memory [B,1024,64], or writes it into the
+        frame store slot named by `ctrl`
         (_encode_new_memory sam2_base.py:1450-1498, MemoryEncoder memory_encoder.py:158-181)."""
         w = self.w
         x, H, W, Cin = mask_in512.reshape(B, 512, 512, 1), 512, 512, 1
@@ -464,13 +531,19 @@ class Engine:
             x, xb = ops.gemm_bf16(t, Lf["pw2"][0], bias=Lf["pw2"][1], col_scale=Lf["gamma"], residual=x, f32=True,
                                   bf16=(i == len(w.fuser) - 1))
         out, _ = ops.gemm_bf16(xb, w.mem_out[0], bias=w.mem_out[1], f32=True)
-        return ops.finalize_memory(out, score.reshape(B).contiguous(), w.no_obj_embed_spatial, B)
+        return ops.finalize_memory(out, score, w.no_obj_embed_spatial, B, ctrl=ctrl)
 
     def mem_mask_input(self, masks, binarize):
         """Upsample low-res logits [B,1,h,w] to 512^2 (if needed) fused with sigmoid*20-10 or (x>0)*20-10."""
         cfg = self.cfg
         post = ops.POST_BINARIZE_AFFINE if binarize else ops.POST_SIGMOID_AFFINE
         return ops.resize_bilinear(masks, 512, 512, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)
+
+    def memory_attention_from_tensors(self, feat, mem_frames, tpos_rows, ptrs, ptr_pos, B):
+        """Convenience for tests / one-off calls: assemble the bank from explicit tensors (usvm_build_memory)."""
+        w = self.w
+        k_in, v_in, Nk = ops.build_memory(mem_frames, tpos_rows, w.mem_pos, w.maskmem_tpos, ptrs, ptr_pos, B)
+        return self.memory_attention(feat, k_in, v_in, Nk, 0 if ptrs is None else ptrs.shape[1], B)
 
     # ---------------------------------------------------------------- object pointers
     def obj_ptr_tokens(self, pos_list, ptr_list, max_ptrs, B):

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, POST_BINARIZE_AFFINE, POST_NONE, POST_SIGMOID_AFFINE,  # noqa: F401
-                   FmhaParams, GemmEpilogue, MemoryFrames, call)
+                   FmhaParams, FrameCtrl, GemmEpilogue, MemoryFrames, SkinnyParams, call)
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -41,8 +41,11 @@ def empty(shape, dtype, like):
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
-def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16, like, out_f32, out_bf16):
+def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16, like, out_f32, out_bf16, rope=None):
     ep = GemmEpilogue()
+    if rope is not None:  # (cos, sin, cols, rows_per_batch, n_rope)
+        ep.rope_cos, ep.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
+        ep.rope_cols, ep.rope_rows_per_batch, ep.rope_n_rope, ep.rope_table_rows = rope[2], rope[3], rope[4], rope[0].shape[0]
     ep.bias, ep.col_scale = _ptr(bias), _ptr(col_scale)
     ep.residual = _ptr(residual)
     ep.ldr = residual.stride(0) if residual is not None else 0
@@ -57,14 +60,15 @@ def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16
 
 
 def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, f32=False, bf16=False,
-              out_f32=None, out_bf16=None, block_n=0, simt=None):
-    """epi(a[M,K] @ w[N,K]^T) on the tcgen05 kernel; returns (fp32 out or None, bf16 out or None)."""
+              out_f32=None, out_bf16=None, block_n=0, simt=None, rope=None):
+    """epi(a[M,K] @ w[N,K]^T) on the tcgen05 kernel; returns (fp32 out or None, bf16 out or None).
+    rope = (cos, sin, cols, rows_per_batch, n_rope): fused rotary encoding of output columns [0, cols)."""
     _chk(a, BF16, "a"), _chk(w, BF16, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
     ep, o32, o16 = _epilogue(M, N, bias, act, col_scale, residual, res_mod, f32 or out_f32 is not None,
-                             bf16 or out_bf16 is not None, a, out_f32, out_bf16)
+                             bf16 or out_bf16 is not None, a, out_f32, out_bf16, rope)
     if _FORCE_SIMT if simt is None else simt:
         call("usvm_gemm_simt", a.data_ptr(), 1, a.stride(0), w.data_ptr(), 1, w.stride(0), C.byref(ep), M, N, K,
              _stream())
@@ -235,11 +239,82 @@ def build_memory(frames, tpos_rows, pos, tpos, ptrs, ptr_pos, B, T=1024, Cm=64):
     return k_in, v_in, Nk
 
 
-def finalize_memory(x, score, no_obj_embed, B, T=1024, Cm=64):
-    mem = empty((B, T, Cm), BF16, x)
-    call("usvm_finalize_memory", x.data_ptr(), score.data_ptr(), no_obj_embed.data_ptr(), mem.data_ptr(), B, T, Cm,
-         _stream())
-    return mem
+class FrameStore:
+    """Per-session device store of everything a tracked frame leaves behind, indexed by frame number:
+    spatial memory (bf16 token-major), object pointer, object score, hole-filled low-res mask logits."""
+
+    def __init__(self, num_frames, B, device, T=1024, Cm=64, ptr_dim=256, hw=128 * 128):
+        self.num_frames, self.B = num_frames, B
+        self.mem = torch.zeros((num_frames, B, T, Cm), dtype=BF16, device=device)
+        self.ptr = torch.zeros((num_frames, B, ptr_dim), dtype=F32, device=device)
+        self.score = torch.zeros((num_frames, B, 1), dtype=F32, device=device)
+        self.masks = torch.zeros((num_frames, B, 1, 128, 128), dtype=F32, device=device)
+
+    def select_objects(self, keep):
+        self.mem, self.ptr = self.mem[:, keep].contiguous(), self.ptr[:, keep].contiguous()
+        self.score, self.masks = self.score[:, keep].contiguous(), self.masks[:, keep].contiguous()
+        self.B = len(keep)
+
+
+def new_frame_ctrl(device):
+    """Device buffer holding one usvm_frame_ctrl."""
+    return torch.zeros(C.sizeof(FrameCtrl) // 8 + 1, dtype=torch.int64, device=device)
+
+
+def set_frame_ctrl(ctrl_dev, store, obj0, cur_frame, mem_frames, mem_tpos, ptr_frames, ptr_rel):
+    """Fill the device control block through a by-value kernel parameter (async, no staging copy).  `obj0` offsets the
+    store bases so that a per-object run (B = 1) addresses object obj0 of a multi-object store."""
+    c = FrameCtrl()
+    c.mem_store = store.mem.data_ptr() + 2 * obj0 * store.mem.stride(1)
+    c.ptr_store = store.ptr.data_ptr() + 4 * obj0 * store.ptr.stride(1)
+    c.score_store = store.score.data_ptr() + 4 * obj0 * store.score.stride(1)
+    c.mask_store = store.masks.data_ptr() + 4 * obj0 * store.masks.stride(1)
+    c.mem_slot_stride, c.ptr_slot_stride = store.mem.stride(0), store.ptr.stride(0)
+    c.score_slot_stride, c.mask_slot_stride = store.score.stride(0), store.masks.stride(0)
+    c.cur_frame, c.n_mem, c.n_ptr = cur_frame, len(mem_frames), len(ptr_frames)
+    assert len(mem_frames) <= _lib.MAX_MEMORY_FRAMES and len(ptr_frames) <= _lib.MAX_PTRS
+    for i, (f, t) in enumerate(zip(mem_frames, mem_tpos)):
+        c.mem_frame[i], c.mem_tpos[i] = f, t
+    for i, (f, r) in enumerate(zip(ptr_frames, ptr_rel)):
+        c.ptr_frame[i], c.ptr_rel[i] = f, r
+    call("usvm_set_frame_ctrl", ctrl_dev.data_ptr(), C.byref(c), _stream())
+
+
+def finalize_memory(x, score, no_obj_embed, B, T=1024, Cm=64, ctrl=None):
+    """-> bf16 [B,T,Cm]; with a device control block the result is written in place into slot ctrl->cur_frame of the
+    frame store (returns None).  `score`: one value per object (any stride)."""
+    sstride = score.stride(0) if score.dim() > 1 else 1
+    if ctrl is None:
+        mem = empty((B, T, Cm), BF16, x)
+        call("usvm_finalize_memory", x.data_ptr(), score.data_ptr(), sstride, no_obj_embed.data_ptr(), mem.data_ptr(),
+             B, T, Cm, 0, _stream())
+        return mem
+    call("usvm_finalize_memory", x.data_ptr(), score.data_ptr(), sstride, no_obj_embed.data_ptr(), 0, B, T, Cm,
+         ctrl.data_ptr(), _stream())
+    return None
+
+
+def ptr_tpos(ctrl, W, bias, n_ptr):
+    out = empty((n_ptr * 4, 64), F32, W)
+    call("usvm_ptr_tpos", ctrl.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), n_ptr, _stream())
+    return out
+
+
+def build_memory_store(ctrl, pos, tpos, ptr_pos, B, n_mem, n_ptr, T=1024, Cm=64):
+    """k_in / v_in bf16 [B, Nk, Cm] gathered from the frame store named by the control block."""
+    Nk = n_mem * T + n_ptr * 4
+    k_in = empty((B, Nk, Cm), BF16, pos)
+    v_in = empty((B, Nk, Cm), BF16, pos)
+    call("usvm_build_memory_store", ctrl.data_ptr(), pos.data_ptr(), tpos.data_ptr(), _ptr(ptr_pos), k_in.data_ptr(),
+         v_in.data_ptr(), B, T, Cm, n_mem, n_ptr, _stream())
+    return k_in, v_in, Nk
+
+
+def store_outputs(ctrl, obj_ptr, score, masks):
+    """slot ctrl->cur_frame of the pointer / score / mask stores <- obj_ptr [B,256], score [B,(1)], masks [B,1,h,w]."""
+    B = obj_ptr.shape[0]
+    call("usvm_store_outputs", ctrl.data_ptr(), obj_ptr.data_ptr(), score.data_ptr(),
+         score.stride(0) if score.dim() > 1 else 1, masks.data_ptr(), B, obj_ptr.shape[1], masks.numel() // B, _stream())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -299,10 +374,11 @@ def upscale1_ln_gelu(g1, feat_s1, ln_w, ln_b, B, Hc, Wc, feat_shared, eps=1e-6):
     return out
 
 
-def upscale2_masks(g2, feat_s0, hyper, B, Hc, Wc, feat_shared):
+def upscale2_masks(g2, feat_s0, hyper, B, Hc, Wc, feat_shared, hyper_bs=128):
+    """hyper: [B, 4, 32] hyper-network outputs, object stride hyper_bs elements."""
     masks = empty((B, 4, 2 * Hc, 2 * Wc), F32, g2)
-    call("usvm_upscale2_masks", g2.data_ptr(), feat_s0.data_ptr(), hyper.data_ptr(), masks.data_ptr(), B, Hc, Wc,
-         int(feat_shared), _stream())
+    call("usvm_upscale2_masks", g2.data_ptr(), feat_s0.data_ptr(), hyper.data_ptr(), hyper_bs, masks.data_ptr(), B, Hc,
+         Wc, int(feat_shared), _stream())
     return masks
 
 
@@ -314,19 +390,69 @@ def small_mlp3(x_ptr, x_row_stride, x_inst_stride, row_select, mlp, out_dim, row
     return y
 
 
-def sam_select(masks, iou, score, multimask, delta, thresh, no_obj_score):
+def gemm_skinny(x, w, bias=None, M=None, x_rs=None, x_is=0, x2=None, x2_rs=None, x2_is=0, act=ACT_NONE,
+                residual=None, r_rs=None, r_is=0, instances=1, row_select=None, x_sel_stride=0, x_ptr=None, out=None):
+    """fp32 GEMM for a few rows: out[i, m, :] = act((x + x2)[i, m] @ w[i].T + bias[i]) + residual[i, m].
+    x: tensor [M, K] (or raw address via x_ptr with explicit strides); w: [N, K] or [instances, N, K]."""
+    N, K = w.shape[-2], w.shape[-1]
+    if M is None:
+        M = x.shape[0]
+    p = SkinnyParams()
+    p.x = x_ptr if x_ptr is not None else x.data_ptr()
+    p.x_rs = x_rs if x_rs is not None else x.stride(0)
+    p.x_is = x_is
+    p.x2 = _ptr(x2)
+    p.x2_rs = (x2_rs if x2_rs is not None else x2.stride(0)) if x2 is not None else 0
+    p.x2_is = x2_is
+    p.row_select, p.x_sel_stride = _ptr(row_select), x_sel_stride
+    p.w, p.w_is = w.data_ptr(), (N * K if instances > 1 else 0)
+    p.bias, p.b_is = _ptr(bias), (N if instances > 1 else 0)
+    if out is None:
+        out = empty((M, instances * N) if instances > 1 else (M, N), F32, w)
+    p.residual = _ptr(residual)
+    p.r_rs = (r_rs if r_rs is not None else residual.stride(0)) if residual is not None else 0
+    p.r_is = r_is
+    p.out, p.o_rs, p.o_is = out.data_ptr(), out.stride(0), (N if instances > 1 else 0)
+    p.M, p.N, p.K, p.instances, p.act = M, N, K, instances, act
+    call("usvm_gemm_skinny_f32", C.byref(p), _stream())
+    return out
+
+
+def attn_t2i(q, k, v, B, Nt, Nk, H=8):
+    """token->image attention, head_dim 16: q [B*Nt, H*16]; k, v column views of an image-side buffer."""
+    out = empty((B * Nt, H * 16), F32, q)
+    assert k.stride(0) == v.stride(0)
+    call("usvm_attn_t2i_f32", q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
+         out.stride(0), B, H, Nt, Nk, 0.25, _stream())
+    return out
+
+
+def attn_i2t(q, k, v, B, Nq, Nt, H=8):
+    """image->token attention, head_dim 16: q [B*Nq, .] (column view), k, v [B*Nt, H*16]."""
+    out = empty((B * Nq, H * 16), F32, q)
+    assert k.stride(0) == v.stride(0)
+    call("usvm_attn_i2t_f32", q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
+         out.stride(0), B, H, Nq, Nt, 0.25, _stream())
+    return out
+
+
+def sam_select(masks, iou, score, multimask, delta, thresh, no_obj_score, iou_stride=4, score_stride=1,
+               iou_is_logit=False):
+    """iou: 4 values per object at stride iou_stride (sigmoid applied in-kernel when iou_is_logit);
+    score: one value per object at stride score_stride."""
     B, _, H, W = masks.shape
     low = empty((B, 1, H, W), F32, masks)
     idx = empty((B,), torch.int32, masks)
     iou_sel = empty((B, 1), F32, masks)
-    call("usvm_sam_select", masks.data_ptr(), iou.data_ptr(), score.data_ptr(), int(multimask), delta, thresh,
-         no_obj_score, low.data_ptr(), idx.data_ptr(), iou_sel.data_ptr(), B, H * W, _stream())
+    call("usvm_sam_select", masks.data_ptr(), iou.data_ptr(), iou_stride, int(iou_is_logit), score.data_ptr(),
+         score_stride, int(multimask), delta, thresh, no_obj_score, low.data_ptr(), idx.data_ptr(), iou_sel.data_ptr(),
+         B, H * W, _stream())
     return low, idx, iou_sel
 
 
 def objptr_mix_(ptr, score, no_obj_ptr):
-    call("usvm_objptr_mix", ptr.data_ptr(), score.data_ptr(), no_obj_ptr.data_ptr(), ptr.shape[0], ptr.shape[1],
-         _stream())
+    call("usvm_objptr_mix", ptr.data_ptr(), score.data_ptr(), score.stride(0), no_obj_ptr.data_ptr(), ptr.shape[0],
+         ptr.shape[1], _stream())
     return ptr
 
 

@@ -55,7 +55,7 @@ class SAM2VideoPredictor(nn.Module):
 
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False,
-                 encoder_batch=1, **model_kwargs):
+                 encoder_batch=1, use_cuda_graphs=True, **model_kwargs):
         super().__init__()
         cfg = type("Cfg", (ModelConfig,), {})
         for k, v in model_kwargs.items():
@@ -83,9 +83,12 @@ class SAM2VideoPredictor(nn.Module):
         self.memory_temporal_stride_for_eval = cfg.memory_temporal_stride_for_eval
         # frames encoded per image-encoder launch group (frame-parallel encoder); 1 = reference order
         self.encoder_batch = max(1, int(encoder_batch))
+        # steady-state tracked frames are replayed from a CUDA graph keyed by (objects, #memories, #pointers, H, W)
+        self.use_cuda_graphs = bool(use_cuda_graphs)
         _install_abi_parameters(self)
         self._engine = None
         self._engine_key = None
+        self._graphs, self._graph_seen, self._ctrl = {}, {}, None
 
     # ------------------------------------------------------------------ module plumbing
     @property
@@ -109,6 +112,8 @@ class SAM2VideoPredictor(nn.Module):
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = Engine(PackedWeights(sd, self.device, self.cfg))
             self._engine_key = key
+            self._graphs, self._graph_seen = {}, {}  # captured graphs bake the old weight pointers
+            self._ctrl = ops.new_frame_ctrl(self.device)
         return self._engine
 
     def engine(self):
@@ -182,6 +187,37 @@ class SAM2VideoPredictor(nn.Module):
 
     def _get_obj_num(self, st):
         return len(st["obj_idx_to_id"])
+
+    # ------------------------------------------------------------------ frame store
+    def _ensure_store(self, st):
+        """Device store of per-frame results (memory, pointer, score, masks), indexed by frame number."""
+        B = self._get_obj_num(st)
+        store = st.get("_store")
+        if store is None or store.B != B or store.num_frames != st["num_frames"]:
+            store = ops.FrameStore(st["num_frames"], B, self.device)
+            st["_store"] = store
+        return store
+
+    def _slot_views(self, st, t, with_memory=True):
+        """The `inference_state` entry of frame t as views into the frame store (reference keys :971-977)."""
+        store = st["_store"]
+        B = store.B
+        out = {"maskmem_features": None, "maskmem_pos_enc": None, "_mem_tok": None, "_slot": t,
+               "pred_masks": store.masks[t], "obj_ptr": store.ptr[t], "object_score_logits": store.score[t]}
+        if with_memory:
+            out["_mem_tok"] = store.mem[t]
+            out["maskmem_features"] = self._mem_view(store.mem[t])
+            out["maskmem_pos_enc"] = self._maskmem_pos_enc(st, B)
+        return out
+
+    def _commit(self, st, t, out):
+        """Copy a consolidated output (fresh tensors) into slot t of the store and return the store-backed entry."""
+        store = self._ensure_store(st)
+        store.mem[t].copy_(out["_mem_tok"])
+        store.ptr[t].copy_(out["obj_ptr"])
+        store.score[t].copy_(out["object_score_logits"])
+        store.masks[t].copy_(out["pred_masks"])
+        return self._slot_views(st, t)
 
     # ------------------------------------------------------------------ image features
     def _get_image_feature(self, st, frame_idx, lookahead=None):
@@ -270,7 +306,7 @@ class SAM2VideoPredictor(nn.Module):
             prev_sam_mask_logits = torch.clamp(prev_out["pred_masks"].to(self.device), -32.0, 32.0)
         current_out, _ = self._run_single_frame_inference(
             st, obj_output_dict, frame_idx, 1, is_init_cond_frame, point_inputs, None, reverse,
-            run_mem_encoder=False, prev_sam_mask_logits=prev_sam_mask_logits)
+            run_mem_encoder=False, prev_sam_mask_logits=prev_sam_mask_logits, obj0=obj_idx)
         obj_temp_output_dict[storage_key][frame_idx] = current_out
         consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=False,
                                                                 consolidate_at_video_res=True)
@@ -303,7 +339,8 @@ class SAM2VideoPredictor(nn.Module):
         is_cond = is_init_cond_frame or self.add_all_frames_to_correct_as_cond
         storage_key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
         current_out, _ = self._run_single_frame_inference(
-            st, obj_output_dict, frame_idx, 1, is_init_cond_frame, None, m, reverse, run_mem_encoder=False)
+            st, obj_output_dict, frame_idx, 1, is_init_cond_frame, None, m, reverse, run_mem_encoder=False,
+            obj0=obj_idx)
         obj_temp_output_dict[storage_key][frame_idx] = current_out
         consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=False,
                                                                 consolidate_at_video_res=True)
@@ -408,6 +445,7 @@ class SAM2VideoPredictor(nn.Module):
         self._sync_engine()
         st["tracking_has_started"] = True
         B = self._get_obj_num(st)
+        self._ensure_store(st)
         temp = st["temp_output_dict_per_obj"]
         output_dict = st["output_dict"]
         cfi = st["consolidated_frame_inds"]
@@ -419,6 +457,7 @@ class SAM2VideoPredictor(nn.Module):
             cfi[storage_key].update(temp_frame_inds)
             for frame_idx in temp_frame_inds:
                 consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=True)
+                consolidated = self._commit(st, frame_idx, consolidated)
                 output_dict[storage_key][frame_idx] = consolidated
                 self._add_output_per_object(st, frame_idx, consolidated, storage_key)
                 if self.clear_non_cond_mem_around_input and (self.clear_non_cond_mem_for_multi_obj or B <= 1):
@@ -478,12 +517,15 @@ class SAM2VideoPredictor(nn.Module):
                 pred_masks = current_out["pred_masks"]
             else:
                 storage_key = "non_cond_frame_outputs"
-                current_out, pred_masks = self._run_single_frame_inference(
-                    st, output_dict, frame_idx, B, False, None, None, reverse, run_mem_encoder=True)
+                current_out, video_res_masks = self._track_frame(st, frame_idx, B, reverse, output_dict)
                 output_dict[storage_key][frame_idx] = current_out
+                pred_masks = None
             self._add_output_per_object(st, frame_idx, current_out, storage_key)
             st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
-            _, video_res_masks = self._get_orig_video_res_output(st, pred_masks)
+            if pred_masks is not None:
+                _, video_res_masks = self._get_orig_video_res_output(st, pred_masks)
+            elif self.non_overlap_masks:
+                video_res_masks = self._apply_non_overlapping_constraints(video_res_masks)
             yield frame_idx, obj_ids, video_res_masks
 
     def _add_output_per_object(self, st, frame_idx, current_out, storage_key):
@@ -493,6 +535,7 @@ class SAM2VideoPredictor(nn.Module):
         for obj_idx, obj_output_dict in st["output_dict_per_obj"].items():
             s = slice(obj_idx, obj_idx + 1)
             o = {"maskmem_features": None, "maskmem_pos_enc": None, "_mem_tok": None,
+                 "_slot": current_out.get("_slot"),
                  "pred_masks": current_out["pred_masks"][s], "obj_ptr": current_out["obj_ptr"][s],
                  "object_score_logits": current_out["object_score_logits"][s]}
             if mem is not None:
@@ -504,14 +547,15 @@ class SAM2VideoPredictor(nn.Module):
 
     # ------------------------------------------------------------------ one frame
     def _memory_inputs(self, st, frame_idx, output_dict, reverse):
-        """Memory-bank selection (sam2_base.py:1296-1394): returns (frames, tpos_rows, pos_list, ptr_list,
-        max_ptrs)."""
+        """Memory-bank selection (sam2_base.py:1296-1394) as store slots:
+        (mem_slots, tpos_rows, ptr_slots, ptr_rel)."""
         cfg = self.cfg
         cond = output_dict["cond_frame_outputs"]
         assert len(cond) > 0
         selected, unselected = _select_closest_cond_frames(frame_idx, cond, cfg.max_cond_frames_in_attn)
         entries = [(0, o) for o in selected.values()]
         r = cfg.memory_temporal_stride_for_eval
+        non_cond = output_dict["non_cond_frame_outputs"]
         for t_pos in range(1, cfg.num_maskmem):
             t_rel = cfg.num_maskmem - t_pos
             if t_rel == 1:
@@ -520,56 +564,94 @@ class SAM2VideoPredictor(nn.Module):
                 prev = ((frame_idx - 2) // r) * r - (t_rel - 2) * r
             else:
                 prev = -(-(frame_idx + 2) // r) * r + (t_rel - 2) * r
-            o = output_dict["non_cond_frame_outputs"].get(prev, None)
+            o = non_cond.get(prev, None)
             if o is None:
                 o = unselected.get(prev, None)
             entries.append((t_pos, o))
-        frames, tpos_rows = [], []
+        mem_slots, tpos_rows = [], []
         for t_pos, o in entries:
             if o is None:
                 continue
-            frames.append(o["_mem_tok"])
+            mem_slots.append(o["_slot"])
             tpos_rows.append(cfg.num_maskmem - t_pos - 1)
         num_frames = st["num_frames"]
         max_ptrs = min(num_frames, cfg.max_obj_ptrs_in_encoder)
         sign = -1 if reverse else 1
-        pos_list, ptr_list = [], []
+        denom = float(max_ptrs - 1)
+        ptr_slots, ptr_rel = [], []
         for t, o in selected.items():
             if (t >= frame_idx) if reverse else (t <= frame_idx):
-                pos_list.append((frame_idx - t) * sign)
-                ptr_list.append(o["obj_ptr"])
+                ptr_slots.append(o["_slot"])
+                ptr_rel.append((frame_idx - t) * sign / denom)
         for t_diff in range(1, max_ptrs):
             t = frame_idx + t_diff if reverse else frame_idx - t_diff
             if t < 0 or t >= num_frames:
                 break
-            o = output_dict["non_cond_frame_outputs"].get(t, unselected.get(t, None))
+            o = non_cond.get(t, unselected.get(t, None))
             if o is not None:
-                pos_list.append(t_diff)
-                ptr_list.append(o["obj_ptr"])
-        return frames, tpos_rows, pos_list, ptr_list, max_ptrs
+                ptr_slots.append(o["_slot"])
+                ptr_rel.append(t_diff / denom)
+        return mem_slots, tpos_rows, ptr_slots, ptr_rel
+
+    def _track_frame(self, st, frame_idx, B, reverse, output_dict):
+        """One tracked (unprompted) frame of all B objects: results go straight into the frame store; the steady
+        state is replayed from a CUDA graph (one graph per (B, #memories, #pointers, video size) signature)."""
+        eng = self.engine()
+        store = st["_store"]
+        look = -1 if reverse else 1
+        f = self._get_image_feature(st, frame_idx, lookahead=look)
+        mem_slots, tpos_rows, ptr_slots, ptr_rel = self._memory_inputs(st, frame_idx, output_dict, reverse)
+        ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
+        hw = (st["video_height"], st["video_width"])
+        key = (B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
+        ent = self._graphs.get(key) if self.use_cuda_graphs else None
+        if self.use_cuda_graphs and ent is None:
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            if seen >= 3:  # a signature that keeps recurring is the steady state: capture it
+                ent = self._capture_graph(key, f)
+        if ent is not None:
+            graph, static_f, video = ent
+            for k, v in static_f.items():
+                v.copy_(f[k])
+            graph.replay()
+            video = video.clone()
+        else:
+            video, _ = eng.track_frame(f, self._ctrl, B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
+        return self._slot_views(st, frame_idx), video
+
+    def _capture_graph(self, key, f):
+        B, n_mem, n_ptr, hw, fill = key
+        eng = self.engine()
+        static_f = {k: f[k].clone() for k in ("feat", "feat_bf16", "feat_s0", "feat_s1")}
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            video, _ = eng.track_frame(static_f, self._ctrl, B, n_mem, n_ptr, hw, fill)
+        ent = (graph, static_f, video)
+        self._graphs[key] = ent
+        return ent
 
     def _run_single_frame_inference(self, st, output_dict, frame_idx, batch_size, is_init_cond_frame, point_inputs,
-                                    mask_inputs, reverse, run_mem_encoder, prev_sam_mask_logits=None):
-        """track_step + compact output (reference :912-978, sam2_base.py:1500-1651)."""
+                                    mask_inputs, reverse, run_mem_encoder, prev_sam_mask_logits=None, obj0=0):
+        """track_step + compact output for PROMPTED frames and per-object interaction
+        (reference :912-978, sam2_base.py:1500-1651).  Unprompted tracking of all objects goes through _track_frame."""
         eng = self.engine()
         cfg = self.cfg
         B = batch_size
         assert point_inputs is None or mask_inputs is None
-        look = (-1 if reverse else 1) if (st["tracking_has_started"] and mask_inputs is None and point_inputs is None) \
-            else None
-        f = self._get_image_feature(st, frame_idx, lookahead=look)
+        f = self._get_image_feature(st, frame_idx)
         if mask_inputs is not None:
             o = eng.mask_as_output(f["feat"], f["feat_s0"], f["feat_s1"], mask_inputs, B)
         else:
             if is_init_cond_frame:
                 pix, _ = ops.axpby(f["feat"], eng.w.no_mem_embed, rows=B * 1024, x_mod=1024, y_mod=1)
             else:
-                frames, tpos_rows, pos_list, ptr_list, max_ptrs = self._memory_inputs(st, frame_idx, output_dict,
-                                                                                      reverse)
-                ptrs = ptr_pos = None
-                if pos_list:
-                    ptrs, ptr_pos = eng.obj_ptr_tokens(pos_list, ptr_list, max_ptrs, B)
-                pix = eng.memory_attention(f["feat"], frames, tpos_rows, ptrs, ptr_pos, B)
+                # correction clicks on an already tracked frame: condition on this object's memories in the store
+                mem_slots, tpos_rows, ptr_slots, ptr_rel = self._memory_inputs(st, frame_idx, output_dict, reverse)
+                ops.set_frame_ctrl(self._ctrl, st["_store"], obj0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
+                k_in, v_in, Nk, n_tok = eng.assemble_memory(self._ctrl, B, len(mem_slots), len(ptr_slots))
+                pix = eng.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B)
             n_pts = 0 if point_inputs is None else point_inputs["point_labels"].size(1)
             multimask = (cfg.multimask_output_in_sam
                          and (is_init_cond_frame or cfg.multimask_output_for_tracking)
@@ -723,14 +805,12 @@ class SAM2VideoPredictor(nn.Module):
 
         for key in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj"):
             remap(st[key])
+        if st.get("_store") is not None:
+            st["_store"].select_objects(remain)
         for storage_key in ("cond_frame_outputs", "non_cond_frame_outputs"):
-            for frame_idx, out in st["output_dict"][storage_key].items():
-                out["_mem_tok"] = out["_mem_tok"][remain].contiguous()
-                out["maskmem_features"] = self._mem_view(out["_mem_tok"])
-                out["maskmem_pos_enc"] = self._maskmem_pos_enc(st, len(remain))
-                out["pred_masks"] = out["pred_masks"][remain]
-                out["obj_ptr"] = out["obj_ptr"][remain]
-                out["object_score_logits"] = out["object_score_logits"][remain]
+            for frame_idx in list(st["output_dict"][storage_key]):
+                out = self._slot_views(st, frame_idx)
+                st["output_dict"][storage_key][frame_idx] = out
                 self._add_output_per_object(st, frame_idx, out, storage_key)
         if need_output:
             temp = st["temp_output_dict_per_obj"]
