@@ -16,7 +16,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from . import ops, synth
+from . import _lib, ops, synth
 from .engine import NO_OBJ_SCORE, Engine, ModelConfig, PackedWeights
 
 try:  # progress bar like the reference (sam2_video_predictor.py:703); optional
@@ -611,10 +611,11 @@ class SAM2VideoPredictor(nn.Module):
             if seen >= 3:  # a signature that keeps recurring is the steady state: capture it
                 ent = self._capture_graph(key, f)
         if ent is not None:
-            graph, static_f, video = ent
+            graph, static_f, video, n_kernels = ent
             for k, v in static_f.items():
                 v.copy_(f[k])
             graph.replay()
+            _lib.launch_count += n_kernels  # kernels of this library replayed by the graph
             video = video.clone()
         else:
             video, _ = eng.track_frame(f, self._ctrl, B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
@@ -626,9 +627,12 @@ class SAM2VideoPredictor(nn.Module):
         static_f = {k: f[k].clone() for k in ("feat", "feat_bf16", "feat_s0", "feat_s1")}
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
+        before = _lib.launch_count
         with torch.cuda.graph(graph):
             video, _ = eng.track_frame(static_f, self._ctrl, B, n_mem, n_ptr, hw, fill)
-        ent = (graph, static_f, video)
+        n_kernels = _lib.launch_count - before
+        _lib.launch_count = before  # capturing launches nothing
+        ent = (graph, static_f, video, n_kernels)
         self._graphs[key] = ent
         return ent
 
