@@ -94,6 +94,11 @@ typedef struct usvm_fmha_params {
   float scale;                /* 1/sqrt(head_dim) */
 } usvm_fmha_params;
 int usvm_fmha_bf16(const usvm_fmha_params* p_host, void* stream);
+/* tcgen05 / TMEM / TMA flash attention for the memory-attention shapes: head_dim 256, H == 1, Nq % 128 == 0, batches
+ * contiguous (x_bs == N * x_rs).  S = QK^T (double buffered) and O accumulate in TMEM, V is consumed in place as an
+ * MN-major operand.  With num_splits > 1 it writes partials only: follow with usvm_fmha_combine. */
+int usvm_fmha_tc5(const usvm_fmha_params* p_host, void* stream);
+int usvm_fmha_combine(const usvm_fmha_params* p_host, void* stream);
 /* fp32, one warp per query; head_dim 16 or 32, Nk <= 1024 (SAM decoder two-way transformer) */
 int usvm_attn_small_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Nq, int Nk,
                         int head_dim, int q_rs, int k_rs, int v_rs, int o_rs, float scale, void* stream);

@@ -31,6 +31,33 @@ def test_fmha_bf16(D, B, H, Nq, Nk, splits):
     assert err < 2e-2, err  # bf16 P and bf16 output rounding
 
 
+@pytest.mark.parametrize("B,Nq,Nk,splits", [(1, 128, 64, 1), (1, 128, 256, 1), (1, 1024, 1024, 1), (1, 1024, 1024, 8),
+                                            (1, 1024, 7232, 9), (2, 1024, 2068, 4), (1, 256, 1000, 3),
+                                            (3, 128, 70, 2)])
+@pytest.mark.parametrize("scale_up", [1.0, 6.0])
+def test_fmha_tc5_matches_reference_and_mma_kernel(B, Nq, Nk, splits, scale_up):
+    """tcgen05 kernel (TMEM accumulators, MN-major V, lazy rescaling) vs fp32 reference and vs the mma.sync kernel;
+    `scale_up` makes the scores large enough to trigger the O rescaling path."""
+    from us_video_medsam2_b200 import ops
+
+    D = 256
+    g = torch.Generator(device="cuda").manual_seed(Nq * 3 + Nk)
+    q = (torch.randn((B, Nq, D), generator=g, device="cuda") * scale_up).to(torch.bfloat16)
+    # keys / values live in a wider fused buffer (4 layers x 256), as on the memory-attention path
+    kv = torch.randn((B * Nk, 4 * D), generator=g, device="cuda").to(torch.bfloat16)
+    kv[:, D:2 * D] *= scale_up
+    args = (B, 1, Nq, Nk, D, (0, Nq * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D))
+    out = ops.fmha(q, kv, kv, *args, num_splits=splits, impl="tc5")
+    torch.cuda.synchronize()
+    k = kv.view(B, Nk, 4 * D)[:, :, D:2 * D]
+    v = kv.view(B, Nk, 4 * D)[:, :, 2 * D:3 * D]
+    want = _ref_attn(q, k, v)
+    err = (out.float() - want).abs().max().item()
+    assert err < 2e-2, err
+    legacy = ops.fmha(q, kv, kv, *args, num_splits=splits, impl="mma")
+    assert (out.float() - legacy.float()).abs().max().item() < 2e-2
+
+
 def test_fmha_strided_qkv_buffer():
     """Q/K/V read in place from a fused [tokens, 3C] projection (global Hiera blocks)."""
     from us_video_medsam2_b200 import ops

@@ -59,8 +59,9 @@ def test_empty_batch_and_argument_errors():
         _C.get_connected_componnets(torch.zeros((1, 2, 8, 8), dtype=torch.uint8, device="cuda"))
 
 
-@pytest.mark.parametrize("shape", [(4, 1, 128, 128), (1, 1, 512, 640)])
-def test_fill_holes_matches_reference_composition(shape):
+@pytest.mark.parametrize("max_area", [8, 3, 40])
+@pytest.mark.parametrize("shape", [(4, 1, 128, 128), (1, 1, 512, 640), (3, 1, 64, 96)])
+def test_fill_holes_matches_reference_composition(shape, max_area):
     """fused kernel == where((labels > 0) & (areas <= 8), 0.1, mask) with labels/areas of (mask <= 0)."""
     from sam2.utils.misc import fill_holes_in_mask_scores
 
@@ -68,10 +69,37 @@ def test_fill_holes_matches_reference_composition(shape):
     scores = torch.randn(shape, generator=g) * 0.07 + 0.02
     scores[0, 0, :4, :4] = 0.0  # exact zeros count as background
     labels, areas = connected_components_ref((scores <= 0).numpy().astype(np.uint8))
-    want = torch.where(torch.from_numpy((labels > 0) & (areas <= 8)), torch.full_like(scores, 0.1), scores)
-    got = fill_holes_in_mask_scores(scores.cuda(), 8).cpu()
+    want = torch.where(torch.from_numpy((labels > 0) & (areas <= max_area)), torch.full_like(scores, 0.1), scores)
+    got = fill_holes_in_mask_scores(scores.cuda(), max_area).cpu()
     assert torch.equal(got, want)
     assert int((got != scores).sum()) > 0  # the case really exercises the fill
+
+
+def test_fill_holes_structured_masks():
+    """Thin / diagonal / ring-shaped background structures around the max_area threshold (local-propagation kernel)."""
+    from sam2.utils.misc import fill_holes_in_mask_scores
+
+    H = W = 128
+    s = torch.ones((5, 1, H, W))
+    s[0, 0, 10, 10:18] = -1          # horizontal bar, area 8  -> filled
+    s[0, 0, 20, 10:19] = -1          # area 9                  -> kept
+    for i in range(8):
+        s[1, 0, 30 + i, 40 + i] = -1  # diagonal, area 8 (8-connected) -> filled
+    for i in range(9):
+        s[1, 0, 60 + i, 40 - i] = -1  # anti-diagonal, area 9 -> kept
+    s[2, 0, 50:53, 50:53] = -1
+    s[2, 0, 51, 51] = 1              # ring of 8 around a foreground pixel -> filled
+    s[3, 0] = -1                     # everything background: one huge component -> kept
+    s[3, 0, 64, 64] = 1
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    s[4, 0][((yy + xx) % 2 == 0)] = -1  # checkerboard: one giant 8-connected background component
+    s[4, 0, 0:2, :] = 1
+    s[4, 0, 0, 5] = -1               # isolated single pixel in the cleared band -> filled
+    labels, areas = connected_components_ref((s <= 0).numpy().astype(np.uint8))
+    want = torch.where(torch.from_numpy((labels > 0) & (areas <= 8)), torch.full_like(s, 0.1), s)
+    got = fill_holes_in_mask_scores(s.cuda(), 8).cpu()
+    assert torch.equal(got, want)
+    assert float(got[0, 0, 10, 12]) == pytest.approx(0.1) and float(got[0, 0, 20, 12]) == -1.0
 
 
 def test_idempotent_and_area_checksum():

@@ -72,6 +72,8 @@ _SIGNATURES = {
     "usvm_gemm_bf16_tc5": [_P, _I, _P, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _I, _P],
     "usvm_gemm_simt": [_P, _I, _I, _P, _I, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _P],
     "usvm_fmha_bf16": [C.POINTER(FmhaParams), _P],
+    "usvm_fmha_tc5": [C.POINTER(FmhaParams), _P],
+    "usvm_fmha_combine": [C.POINTER(FmhaParams), _P],
     "usvm_attn_small_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "usvm_layernorm": [_P, _I, _P, _P, _F, _I, _P, _I, _P, _I, _I, _I, _P],
     "usvm_axpby_rows": [_P, _P, _F, _F, _I, _I, _P, _P, _LL, _I, _P],

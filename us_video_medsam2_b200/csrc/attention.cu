@@ -236,41 +236,41 @@ fmha_bf16_kernel(const usvm_fmha_params p) {
   }
 }
 
-// merge split partials: one warp per (bh, query row)
+// merge split partials: one thread per (row, 4 channels); the loads of all splits are independent and coalesced
 template <int D>
-__global__ void fmha_combine_kernel(const usvm_fmha_params p) {
-  const int warps_per_block = blockDim.x >> 5;
-  const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)p.B * p.H * p.Nq;
-  if (row >= total) return;
+__global__ void __launch_bounds__(256)
+fmha_combine_kernel(const usvm_fmha_params p) {
+  constexpr int C4 = D / 4;
+  const long long total_rows = (long long)p.B * p.H * p.Nq;
+  const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= total_rows * C4) return;
+  const long long row = item / C4;
+  const int c4 = (int)(item - row * C4) * 4;
   const int bh = (int)(row / p.Nq);
   const int qi = (int)(row - (long long)bh * p.Nq);
   const int b = bh / p.H, h = bh - b * p.H;
   const float sl2 = p.scale * 1.4426950408889634f;
   float M = -INFINITY;
   for (int s = 0; s < p.num_splits; ++s) {
-    const float2 ml = *reinterpret_cast<const float2*>(p.ml_part + ((long long)s * p.B * p.H * p.Nq + row) * 2);
+    const float2 ml = *reinterpret_cast<const float2*>(p.ml_part + ((long long)s * total_rows + row) * 2);
     if (ml.y > 0.f) M = fmaxf(M, ml.x);
   }
   float L = 0.f;
-  float acc[D / 32];
-#pragma unroll
-  for (int i = 0; i < D / 32; ++i) acc[i] = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < p.num_splits; ++s) {
-    const long long pr = (long long)s * p.B * p.H * p.Nq + row;
+    const long long pr = (long long)s * total_rows + row;
     const float2 ml = *reinterpret_cast<const float2*>(p.ml_part + pr * 2);
-    if (!(ml.y > 0.f)) continue;
-    const float w = exp2f((ml.x - M) * sl2);
+    const float4 o = *reinterpret_cast<const float4*>(p.o_part + pr * D + c4);
+    const float w = ml.y > 0.f ? exp2f((ml.x - M) * sl2) : 0.f;
     L += ml.y * w;
-    const float* op = p.o_part + pr * D;
-#pragma unroll
-    for (int i = 0; i < D / 32; ++i) acc[i] += op[i * 32 + lane] * w;
+    acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
   }
   const float inv = L > 0.f ? 1.f / L : 0.f;
-  bf16* O = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)qi * p.o_rs;
-#pragma unroll
-  for (int i = 0; i < D / 32; ++i) O[i * 32 + lane] = __float2bfloat16(acc[i] * inv);
+  bf16* O = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)qi * p.o_rs + c4;
+  uint2 pk;
+  pk.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+  pk.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(O) = pk;
 }
 
 template <int D>
@@ -286,7 +286,7 @@ int launch_fmha(const usvm_fmha_params* p, cudaStream_t s) {
   fmha_bf16_kernel<D><<<grid, FTHREADS, FmhaSmem<D>::BYTES, s>>>(*p);
   if (p->num_splits > 1) {
     const long long rows = (long long)p->B * p->H * p->Nq;
-    fmha_combine_kernel<D><<<cdiv(rows, 8), 256, 0, s>>>(*p);
+    fmha_combine_kernel<D><<<cdiv(rows * (D / 4), 256), 256, 0, s>>>(*p);
   }
   return usvm_check_launch();
 }
@@ -356,6 +356,19 @@ extern "C" int usvm_fmha_bf16(const usvm_fmha_params* p, void* stream) {
   if (p->head_dim == 96) return launch_fmha<96>(p, s);
   if (p->head_dim == 256) return launch_fmha<256>(p, s);
   return USVM_ERR_ARG;
+}
+
+// merge the split-KV partials written by usvm_fmha_bf16 / usvm_fmha_tc5 (head_dim 96 or 256)
+extern "C" int usvm_fmha_combine(const usvm_fmha_params* p, void* stream) {
+  if (!p || !p->o || !p->o_part || !p->ml_part || p->num_splits < 1 || p->B <= 0 || p->H <= 0 || p->Nq <= 0)
+    return USVM_ERR_ARG;
+  const long long rows = (long long)p->B * p->H * p->Nq;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if ((p->o_rs % 4) || (p->o_hs % 4) || (p->o_bs % 4)) return USVM_ERR_ARG;
+  if (p->head_dim == 96) fmha_combine_kernel<96><<<cdiv(rows * 24, 256), 256, 0, s>>>(*p);
+  else if (p->head_dim == 256) fmha_combine_kernel<256><<<cdiv(rows * 64, 256), 256, 0, s>>>(*p);
+  else return USVM_ERR_ARG;
+  return usvm_check_launch();
 }
 
 extern "C" int usvm_attn_small_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Nq,

@@ -193,6 +193,84 @@ __global__ void cc_g_roots(FG fg, int32_t* labels, int32_t* counts, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Hole filling without global labelling.  Only components of area <= max_area matter, and such a component has
+// diameter < max_area, so `max_area` rounds of min-label propagation over the 3x3 neighbourhood make every small
+// component converge to its minimum pixel index.  A label group that is (a) closed -- no member touches a
+// background pixel carrying a different label -- and (b) of size <= max_area is exactly one small component: a
+// closed group is a whole component, and an unconverged larger component always contains an adjacent pair of
+// different labels, which marks both groups open.  One CTA per image, everything in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kOpenFlag = 0x40000000;
+
+__global__ void __launch_bounds__(1024)
+fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W, int max_area, float fill_value) {
+  extern __shared__ int s_mem[];
+  const int HW = H * W;
+  int* s_lab = s_mem;        // label (pixel index) or -1 on foreground of the mask
+  int* s_cnt = s_mem + HW;   // per-label size | open flag
+  const long long base = (long long)blockIdx.x * HW;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < HW; i += nt) {
+    s_lab[i] = scores_in[base + i] <= 0.0f ? i : -1;
+    s_cnt[i] = 0;
+  }
+  __syncthreads();
+  for (int round = 0; round < max_area; ++round) {
+    for (int i = tid; i < HW; i += nt) {
+      int me = s_lab[i];
+      if (me < 0) continue;
+      const int r = i / W, c = i - r * W;
+      int m = me;
+#pragma unroll
+      for (int dr = -1; dr <= 1; ++dr) {
+        const int rr = r + dr;
+        if (rr < 0 || rr >= H) continue;
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+          const int cc = c + dc;
+          if (cc < 0 || cc >= W) continue;
+          const int q = s_lab[rr * W + cc];
+          if (q >= 0 && q < m) m = q;
+        }
+      }
+      if (m < me) s_lab[i] = m;  // in place: labels only decrease towards the component minimum
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < HW; i += nt) {
+    const int me = s_lab[i];
+    if (me < 0) continue;
+    const int r = i / W, c = i - r * W;
+    bool open = false;
+#pragma unroll
+    for (int dr = -1; dr <= 1; ++dr) {
+      const int rr = r + dr;
+      if (rr < 0 || rr >= H) continue;
+#pragma unroll
+      for (int dc = -1; dc <= 1; ++dc) {
+        const int cc = c + dc;
+        if (cc < 0 || cc >= W) continue;
+        const int q = s_lab[rr * W + cc];
+        open |= (q >= 0 && q != me);
+      }
+    }
+    atomicAdd(&s_cnt[me], 1);  // sizes stay far below the flag bit
+    if (open) atomicOr(&s_cnt[me], kOpenFlag);
+  }
+  __syncthreads();
+  for (int i = tid; i < HW; i += nt) {
+    const int me = s_lab[i];
+    const float v = scores_in[base + i];
+    bool hole = false;
+    if (me >= 0) {
+      const int cnt = s_cnt[me];
+      hole = !(cnt & kOpenFlag) && cnt <= max_area;
+    }
+    scores_out[base + i] = hole ? fill_value : v;
+  }
+}
+
 size_t smem_bytes(int H, int W) { return (size_t)(H / 2) * (W / 2) * 8 + (size_t)H * W; }
 constexpr size_t kSmemLimit = 200 * 1024;
 
@@ -247,6 +325,18 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
   if (!scores_in || !scores_out) return USVM_ERR_ARG;
   if ((long long)H * W >= (1LL << 31) - 1 || N > 65535) return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t local_bytes = (size_t)H * W * 8;
+  if (max_area <= 32 && local_bytes <= kSmemLimit) {  // the propagation path's case: 128 x 128, max_area 8
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(fill_holes_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) !=
+          cudaSuccess)
+        return USVM_ERR_CUDA;
+      configured = true;
+    }
+    fill_holes_local_kernel<<<N, 1024, local_bytes, s>>>(scores_in, scores_out, H, W, max_area, fill_value);
+    return usvm_check_launch();
+  }
   if (smem_bytes(H, W) <= kSmemLimit)
     return launch_smem<true>(nullptr, scores_in, scores_out, nullptr, nullptr, N, H, W, max_area, fill_value, s);
   if (!scratch_labels || !scratch_counts) return USVM_ERR_ARG;  // the global path needs two int32 [N,H,W] maps

@@ -13,63 +13,83 @@
 namespace {
 
 constexpr int SK_ROWS = 8;       // rows per pass
-constexpr int SK_COLS_WARP = 4;  // output columns per warp
+constexpr int SK_COLS = 4;       // output columns per warp group
 constexpr int SK_WARPS = 8;
 
+// KSPLIT = 1: each warp owns 4 output columns (CTA = 32 columns), lanes stride K.
+// KSPLIT = 8: the 8 warps of a CTA share 4 output columns and split K (long reductions, e.g. K = 2048), partial sums
+//             are combined through shared memory.
+template <int KSPLIT>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const usvm_skinny_params p) {
-  extern __shared__ __align__(16) float xs[];  // [rows][K]
+  extern __shared__ __align__(16) float xs[];  // [rows][K] (+ [8][32] partials when KSPLIT > 1)
   const int inst = blockIdx.y;
   const int m0 = blockIdx.z * SK_ROWS;
   const int rows = min(SK_ROWS, p.M - m0);
-  const int K = p.K;
-  // stage (x + x2) rows
-  for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
-    const int m = i / K, k = i - m * K;
+  const int K = p.K, K4 = K >> 2;
+  for (int i = threadIdx.x; i < rows * K4; i += blockDim.x) {
+    const int m = i / K4, k = (i - m * K4) << 2;
     const long long sel = p.row_select ? (long long)p.row_select[m0 + m] * p.x_sel_stride : 0;
-    float v = p.x[(long long)inst * p.x_is + (long long)(m0 + m) * p.x_rs + sel + k];
-    if (p.x2) v += p.x2[(long long)inst * p.x2_is + (long long)(m0 + m) * p.x2_rs + k];
-    xs[i] = v;
+    const float* xp = p.x + (long long)inst * p.x_is + (long long)(m0 + m) * p.x_rs + sel + k;
+    float4 v = make_float4(xp[0], xp[1], xp[2], xp[3]);
+    if (p.x2) {
+      const float* x2 = p.x2 + (long long)inst * p.x2_is + (long long)(m0 + m) * p.x2_rs + k;
+      v.x += x2[0]; v.y += x2[1]; v.z += x2[2]; v.w += x2[3];
+    }
+    *reinterpret_cast<float4*>(xs + m * K + k) = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = (blockIdx.x * SK_WARPS + warp) * SK_COLS_WARP;
-  if (n0 >= p.N) return;
-  float acc[SK_COLS_WARP][SK_ROWS];
+  const int n0 = (KSPLIT == 1 ? (blockIdx.x * SK_WARPS + warp) : blockIdx.x) * SK_COLS;
+  float acc[SK_COLS][SK_ROWS];
 #pragma unroll
-  for (int c = 0; c < SK_COLS_WARP; ++c)
+  for (int c = 0; c < SK_COLS; ++c)
 #pragma unroll
     for (int m = 0; m < SK_ROWS; ++m) acc[c][m] = 0.f;
-  const float* Wb = p.w + (long long)inst * p.w_is;
-  for (int k = lane * 4; k < K; k += 128) {
-    float4 wv[SK_COLS_WARP];
+  if (n0 < p.N) {
+    const float* Wb = p.w + (long long)inst * p.w_is;
+    const int kchunk = KSPLIT == 1 ? K : (((K + KSPLIT - 1) / KSPLIT + 3) & ~3);
+    const int kbeg = KSPLIT == 1 ? 0 : warp * kchunk;
+    const int kend = min(K, kbeg + kchunk);
+    for (int k = kbeg + lane * 4; k < kend; k += 128) {
+      float4 wv[SK_COLS];
 #pragma unroll
-    for (int c = 0; c < SK_COLS_WARP; ++c) {
-      const int n = min(n0 + c, p.N - 1);
-      wv[c] = *reinterpret_cast<const float4*>(Wb + (long long)n * K + k);
-    }
+      for (int c = 0; c < SK_COLS; ++c) {
+        const int n = min(n0 + c, p.N - 1);
+        wv[c] = *reinterpret_cast<const float4*>(Wb + (long long)n * K + k);
+      }
 #pragma unroll
-    for (int m = 0; m < SK_ROWS; ++m) {
-      if (m < rows) {
-        const float4 xv = *reinterpret_cast<const float4*>(xs + m * K + k);
+      for (int m = 0; m < SK_ROWS; ++m) {
+        if (m < rows) {
+          const float4 xv = *reinterpret_cast<const float4*>(xs + m * K + k);
 #pragma unroll
-        for (int c = 0; c < SK_COLS_WARP; ++c)
-          acc[c][m] += xv.x * wv[c].x + xv.y * wv[c].y + xv.z * wv[c].z + xv.w * wv[c].w;
+          for (int c = 0; c < SK_COLS; ++c)
+            acc[c][m] += xv.x * wv[c].x + xv.y * wv[c].y + xv.z * wv[c].z + xv.w * wv[c].w;
+        }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < SK_COLS_WARP; ++c)
+  for (int c = 0; c < SK_COLS; ++c)
 #pragma unroll
     for (int m = 0; m < SK_ROWS; ++m) acc[c][m] = warp_sum(acc[c][m]);
-  // lane (c * 8 + m) writes element (m, n0 + c)
+  // lane (c * 8 + m) holds element (m, n0 + c)
   const int c = lane >> 3, m = lane & 7;
   float v = 0.f;
 #pragma unroll
-  for (int cc = 0; cc < SK_COLS_WARP; ++cc)
+  for (int cc = 0; cc < SK_COLS; ++cc)
 #pragma unroll
     for (int mm = 0; mm < SK_ROWS; ++mm)
       if (cc == c && mm == m) v = acc[cc][mm];
+  if (KSPLIT > 1) {
+    float* part = xs + SK_ROWS * K;  // [8 warps][32]
+    part[warp * 32 + lane] = v;
+    __syncthreads();
+    if (warp != 0) return;
+    v = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_WARPS; ++w) v += part[w * 32 + lane];
+  }
   const int n = n0 + c;
   if (m < rows && n < p.N) {
     if (p.bias) v += p.bias[(long long)inst * p.b_is + n];
@@ -83,30 +103,39 @@ gemm_skinny_kernel(const usvm_skinny_params p) {
 // ---- token -> image attention --------------------------------------------------------------------
 constexpr int T2I_DH = 16;
 constexpr int T2I_MAX_NT = 16;
+constexpr int T2I_LD = 17;  // padded row (16 channels + 1) -> conflict-free per-thread row reads
 
+// one CTA per (object, head): the head's K and V slices ([Nk x 16] each) are first staged in shared memory with
+// independent 16-byte loads (all in flight at once), then scores / softmax / P.V run entirely out of shared memory
 __global__ void __launch_bounds__(256)
 attn_t2i_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__ k, const float* __restrict__ v,
                 int kv_rs, float* __restrict__ out, int o_rs, int H, int Nt, int Nk, float scale) {
   extern __shared__ float sm[];
-  float* s_p = sm;                       // [Nt][Nk]
-  float* s_q = sm + Nt * Nk;             // [Nt][16]
-  float* s_red = s_q + Nt * T2I_DH;      // [16 slices][Nt][16]
+  float* s_k = sm;                         // [Nk][17]
+  float* s_v = s_k + Nk * T2I_LD;          // [Nk][17]
+  float* s_p = s_v + Nk * T2I_LD;          // [Nt][Nk]
+  float* s_q = s_p + Nt * Nk;              // [Nt][16]
+  float* s_red = s_q + Nt * T2I_DH;        // [16 slices][Nt][16]
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int tid = threadIdx.x;
   const float* qb = q + (long long)b * Nt * q_rs + h * T2I_DH;
   const float* kb = k + (long long)b * Nk * kv_rs + h * T2I_DH;
   const float* vb = v + (long long)b * Nk * kv_rs + h * T2I_DH;
+  for (int i = tid; i < Nk * 4; i += blockDim.x) {  // 4 float4 per key row, K and V
+    const int j = i >> 2, c4 = (i & 3) << 2;
+    const float4 kk = *reinterpret_cast<const float4*>(kb + (long long)j * kv_rs + c4);
+    const float4 vv = *reinterpret_cast<const float4*>(vb + (long long)j * kv_rs + c4);
+    float* dk = s_k + j * T2I_LD + c4;
+    float* dv = s_v + j * T2I_LD + c4;
+    dk[0] = kk.x; dk[1] = kk.y; dk[2] = kk.z; dk[3] = kk.w;
+    dv[0] = vv.x; dv[1] = vv.y; dv[2] = vv.z; dv[3] = vv.w;
+  }
   for (int i = tid; i < Nt * T2I_DH; i += blockDim.x) s_q[i] = qb[(i / T2I_DH) * q_rs + (i % T2I_DH)] * scale;
   __syncthreads();
-  // scores: thread per key
   for (int j = tid; j < Nk; j += blockDim.x) {
     float kr[T2I_DH];
-    const float4* kp = reinterpret_cast<const float4*>(kb + (long long)j * kv_rs);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t4 = kp[i];
-      kr[4 * i] = t4.x; kr[4 * i + 1] = t4.y; kr[4 * i + 2] = t4.z; kr[4 * i + 3] = t4.w;
-    }
+    for (int c = 0; c < T2I_DH; ++c) kr[c] = s_k[j * T2I_LD + c];
     for (int t = 0; t < Nt; ++t) {
       float d = 0.f;
 #pragma unroll
@@ -115,7 +144,6 @@ attn_t2i_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__
     }
   }
   __syncthreads();
-  // softmax per token: one warp per token row (looping if Nt > 8 warps)
   const int warp = tid >> 5, lane = tid & 31;
   for (int t = warp; t < Nt; t += 8) {
     float mx = -INFINITY;
@@ -138,7 +166,7 @@ attn_t2i_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__
 #pragma unroll
   for (int t = 0; t < T2I_MAX_NT; ++t) acc[t] = 0.f;
   for (int j = slice; j < Nk; j += 16) {
-    const float vv = vb[(long long)j * kv_rs + c];
+    const float vv = s_v[j * T2I_LD + c];
 #pragma unroll
     for (int t = 0; t < T2I_MAX_NT; ++t)
       if (t < Nt) acc[t] = fmaf(s_p[t * Nk + j], vv, acc[t]);
@@ -223,23 +251,29 @@ attn_i2t_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__
 extern "C" int usvm_gemm_skinny_f32(const usvm_skinny_params* p, void* stream) {
   if (!p || !p->x || !p->w || !p->out || p->M <= 0 || p->N <= 0 || p->K <= 0 || p->instances <= 0) return USVM_ERR_ARG;
   if ((p->K % 4) || (reinterpret_cast<uintptr_t>(p->w) & 15) || (p->w_is % 4)) return USVM_ERR_ARG;
-  const size_t smem = (size_t)SK_ROWS * p->K * sizeof(float);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    if (smem > 200 * 1024) return USVM_ERR_ARG;
-    if (cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+  const size_t smem = ((size_t)SK_ROWS * p->K + SK_WARPS * 32) * sizeof(float);
+  if (smem > 200 * 1024) return USVM_ERR_ARG;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_skinny_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return USVM_ERR_CUDA;
-    configured = 200 * 1024;
+    configured = true;
   }
-  dim3 grid(cdiv(p->N, SK_WARPS * SK_COLS_WARP), p->instances, cdiv(p->M, SK_ROWS));
-  gemm_skinny_kernel<<<grid, 256, smem, STREAM>>>(*p);
+  if (p->K >= 1024) {  // long reduction: the CTA's 8 warps split K, one CTA per 4 columns
+    dim3 grid(cdiv(p->N, SK_COLS), p->instances, cdiv(p->M, SK_ROWS));
+    gemm_skinny_kernel<8><<<grid, 256, smem, STREAM>>>(*p);
+  } else {
+    dim3 grid(cdiv(p->N, SK_WARPS * SK_COLS), p->instances, cdiv(p->M, SK_ROWS));
+    gemm_skinny_kernel<1><<<grid, 256, smem, STREAM>>>(*p);
+  }
   return usvm_check_launch();
 }
 
 extern "C" int usvm_attn_t2i_f32(const float* q, int q_rs, const float* k, const float* v, int kv_rs, float* out,
                                  int o_rs, int B, int H, int Nt, int Nk, float scale, void* stream) {
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || Nt <= 0 || Nt > T2I_MAX_NT || Nk <= 0 || (kv_rs % 4)) return USVM_ERR_ARG;
-  const size_t smem = ((size_t)Nt * Nk + Nt * T2I_DH + 16 * Nt * T2I_DH) * sizeof(float);
+  const size_t smem = ((size_t)2 * Nk * T2I_LD + (size_t)Nt * Nk + Nt * T2I_DH + 16 * Nt * T2I_DH) * sizeof(float);
   static size_t configured = 48 * 1024;
   if (smem > configured) {
     if (smem > 200 * 1024) return USVM_ERR_ARG;

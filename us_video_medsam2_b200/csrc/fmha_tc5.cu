@@ -1,0 +1,343 @@
+// Flash attention on the 5th-gen tensor cores for the memory-attention path: one head of 256, 1024 queries per
+// object, up to 7 x 1024 + 64 keys (RoPEAttention self- and cross-attention, sam/transformer.py:311-360).
+//
+// One CTA owns 128 queries and a contiguous range of 64-key tiles (split-KV; partials are merged by
+// fmha_combine_kernel in attention.cu).  Accumulators live in TMEM:
+//     columns [0,64) / [64,128)   S = Q K^T, double buffered (fp32, 128 lanes x 64)
+//     columns [128,384)           O           (fp32, 128 lanes x 256)
+// Warp roles (192 threads):
+//   warp 0   TMA producer: Q once (4 boxes of 128 x 64), then K / V tiles (4 + 4 boxes of 64 x 64) through a
+//            2-stage mbarrier ring, 128-byte swizzle
+//   warp 1   tcgen05.mma issuer: S_{j+1} = Q K_{j+1}^T is issued before waiting for the softmax of tile j, so the
+//            QK^T half of the tensor work overlaps the softmax; O += P_j V_j uses V in place as an MN-major operand
+//   warps 2-5 softmax: thread <-> query row (no cross-thread reductions): tcgen05.ld S, online softmax in base 2
+//            with lazy rescaling (O in TMEM is only rescaled when the running max grows by more than 2^8),
+//            P written as bf16 into the swizzled K-major smem tile that feeds the second MMA
+#include "common.cuh"
+#include "usvm2_b200.h"
+
+namespace {
+
+constexpr int QM = 128;   // queries per CTA
+constexpr int KN = 64;    // keys per tile
+constexpr int HD = 256;   // head dim
+constexpr int NCH = HD / 64;  // 64-column (128-byte) chunks per row
+constexpr int THREADS = 192;
+
+constexpr int Q_BYTES = NCH * QM * 128;     // 65536
+constexpr int KV_BYTES = NCH * KN * 128;    // 32768 per operand per stage
+constexpr int P_BYTES = QM * 128;           // 16384
+constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + P_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tc5_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+        "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc5_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// MN-major operand (rows = K index, 128 bytes = 64 consecutive N elements per row, 128B swizzle):
+// 8-row groups 1024 B apart (SBO), 64-element N chunks `lbo_bytes` apart (LBO)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t lo = ((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16);
+  uint64_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return lo | (hi << 32);
+}
+// D fp32, A/B bf16, A K-major, B K-major (b_mn = 0) or MN-major (b_mn = 1)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const usvm_fmha_params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;                 // 2 stages
+  uint8_t* sV = sK + 2 * KV_BYTES;            // 2 stages
+  uint8_t* sP = sV + 2 * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // 2
+  uint64_t* kv_empty = bars + 3;      // 2
+  uint64_t* s_full = bars + 5;        // 2
+  uint64_t* p_full = bars + 7;        // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 8;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QM;
+  const int b = blockIdx.y;  // batch (object); one head
+  const int split = blockIdx.z;
+  const int ntiles = (p.Nk + KN - 1) / KN;
+  const int per = (ntiles + p.num_splits - 1) / p.num_splits;
+  const int t_begin = split * per;
+  const int t_end = min(ntiles, t_begin + per);
+  const int n = max(0, t_end - t_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tc5_alloc(tmem_slot, 512);
+  tc5_fence_before();
+  __syncthreads();
+  tc5_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_O = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0 && n > 0) {
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      for (int c = 0; c < NCH; ++c) tma_load_2d(sQ + c * (QM * 128), &tmQ, q_full, c * 64, b * p.Nq + q0);
+      for (int j = 0; j < n; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES);
+        const int row = b * p.Nk + (t_begin + j) * KN;
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_2d(sK + st * KV_BYTES + c * (KN * 128), &tmK, &kv_full[st], c * 64, row);
+          tma_load_2d(sV + st * KV_BYTES + c * (KN * 128), &tmV, &kv_full[st], c * 64, row);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && n > 0) {
+      constexpr uint32_t idesc_s = idesc_bf16(QM, KN, 0);
+      constexpr uint32_t idesc_o = idesc_bf16(QM, HD, 1);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc5_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * (QM * 128) + (kk & 3) * 32;
+          const uint32_t koff = (kk >> 2) * (KN * 128) + (kk & 3) * 32;
+          tc5_mma_f16(tmem + st * KN, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + koff), idesc_s,
+                      kk > 0 ? 1u : 0u);
+        }
+        tc5_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n; ++j) {
+        if (j + 1 < n) issue_s(j + 1);
+        mbar_wait(p_full, j & 1);
+        tc5_fence_after();
+        const uint32_t v_addr = smem_u32(sV + (j & 1) * KV_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < KN / 16; ++kk) {
+          tc5_mma_f16(tmem_O, umma_desc_k_sw128(p_addr + kk * 32), umma_desc_mn_sw128(v_addr + kk * 2048, KN * 128),
+                      idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc5_commit(&kv_empty[j & 1]);
+        tc5_commit(pv_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lane_grp = warp & 3;
+    const int r = lane_grp * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc5_fence_after();
+      uint32_t sa[32], sb[32];
+      tc5_ld_32x32(tmem + lane_addr + st * KN, sa);
+      tc5_ld_32x32(tmem + lane_addr + st * KN + 32, sb);
+      tc5_wait_ld();
+      float s[64];
+      const int key0 = (t_begin + j) * KN;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float v = __uint_as_float(i < 32 ? sa[i] : sb[i - 32]) * sl2;
+        if (key0 + i >= p.Nk) v = -INFINITY;
+        s[i] = v;
+        mx = fmaxf(mx, v);
+      }
+      float corr = 1.f;
+      bool rescale = false;
+      if (j == 0) {
+        m_ref = mx;
+      } else if (mx > m_ref + 8.0f) {  // lazy rescaling: keep the stale max while exp2(s - m_ref) <= 2^8
+        corr = exp2f(m_ref - mx);
+        m_ref = mx;
+        l *= corr;
+        rescale = true;
+      }
+      float sum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const float p0 = exp2f(s[i] - m_ref), p1 = exp2f(s[i + 1] - m_ref);
+        sum += p0 + p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      l += sum;
+      if (j > 0) {  // O += P_{j-1} V_{j-1} must have completed before O is rescaled and P is overwritten
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc5_fence_after();
+        if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 32) {
+            uint32_t o[32];
+            tc5_ld_32x32(tmem_O + lane_addr + c, o);
+            tc5_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tc5_st_32x32(tmem_O + lane_addr + c, o);
+          }
+          tc5_wait_st();
+        }
+      }
+      // P row r -> swizzled K-major tile: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
+      uint8_t* prow = sP + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 v4 = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = v4;
+      }
+      fence_proxy_async();
+      tc5_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue ----
+    const int row = q0 + r;
+    const int bh = b;  // H == 1
+    if (n > 0) {
+      mbar_wait(pv_done, (n - 1) & 1);
+      tc5_fence_after();
+    }
+    const float inv = (p.num_splits == 1 && l > 0.f) ? 1.f / l : 1.f;
+#pragma unroll 1
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t o[32];
+      if (n > 0) {
+        tc5_ld_32x32(tmem_O + lane_addr + c, o);
+        tc5_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      if (row >= p.Nq) continue;
+      if (p.num_splits == 1) {
+        bf16* O = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs + (long long)row * p.o_rs + c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v4;
+          v4.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          v4.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          v4.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          v4.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(O + i) = v4;
+        }
+      } else {
+        float* OP = p.o_part + (((long long)split * gridDim.y + bh) * p.Nq + row) * HD + c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(OP + i) = make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]),
+                                                           __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+      }
+    }
+    if (p.num_splits > 1 && row < p.Nq) {
+      // (m, l) in the convention of fmha_combine_kernel: m in raw score units, weights exp2((m - M) * scale * log2e)
+      float* ML = p.ml_part + (((long long)split * gridDim.y + bh) * p.Nq + row) * 2;
+      ML[0] = n > 0 ? m_ref / sl2 : -INFINITY;
+      ML[1] = l;
+    }
+  }
+  tc5_fence_before();
+  __syncthreads();
+  if (warp == 1) tc5_dealloc(tmem, 512);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const void* base, long long rows, int cols, long long pitch_elems, int box_rows) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) return USVM_ERR_DRIVER;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? USVM_OK : USVM_ERR_DRIVER;
+}
+
+}  // namespace
+
+// Same parameter block as usvm_fmha_bf16.  Requirements: head_dim 256, H == 1, Nq % 128 == 0, contiguous batches
+// (q_bs == Nq * q_rs, k_bs == Nk * k_rs, v_bs == Nk * v_rs), 16-byte aligned bases, row strides % 8 == 0.
+// Partials (num_splits > 1) use the o_part / ml_part layout of usvm_fmha_bf16; call usvm_fmha_combine afterwards.
+extern "C" int usvm_fmha_tc5(const usvm_fmha_params* p, void* stream) {
+  if (!p || !p->q || !p->k || !p->v || !p->o || p->B <= 0 || p->Nq <= 0 || p->Nk <= 0) return USVM_ERR_ARG;
+  if (p->head_dim != HD || p->H != 1 || (p->Nq % QM) || p->num_splits < 1) return USVM_ERR_ARG;
+  if (p->q_bs != (long long)p->Nq * p->q_rs || p->k_bs != (long long)p->Nk * p->k_rs ||
+      p->v_bs != (long long)p->Nk * p->v_rs)
+    return USVM_ERR_ARG;
+  if ((p->q_rs % 8) || (p->k_rs % 8) || (p->v_rs % 8) || (p->o_rs % 8)) return USVM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(p->q) & 15) || (reinterpret_cast<uintptr_t>(p->k) & 15) ||
+      (reinterpret_cast<uintptr_t>(p->v) & 15) || (reinterpret_cast<uintptr_t>(p->o) & 15))
+    return USVM_ERR_ARG;
+  if (p->num_splits > 1 && (!p->o_part || !p->ml_part)) return USVM_ERR_ARG;
+  if (p->num_splits > (p->Nk + KN - 1) / KN) return USVM_ERR_ARG;
+  CUtensorMap tq, tk, tv;
+  int rc = make_map(&tq, p->q, (long long)p->B * p->Nq, HD, p->q_rs, QM);
+  if (rc) return rc;
+  rc = make_map(&tk, p->k, (long long)p->B * p->Nk, HD, p->k_rs, KN);
+  if (rc) return rc;
+  rc = make_map(&tv, p->v, (long long)p->B * p->Nk, HD, p->v_rs, KN);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(fmha_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      return USVM_ERR_CUDA;
+    attr = true;
+  }
+  dim3 grid(p->Nq / QM, p->B, p->num_splits);
+  fmha_tc5_kernel<<<grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, *p);
+  return usvm_check_launch();
+}

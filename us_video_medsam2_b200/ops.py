@@ -93,9 +93,13 @@ def gemm_f32(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_m
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_splits=1):
+_FMHA_IMPL = os.environ.get("USVM2_FMHA", "tc5")  # "tc5" (tcgen05 where the shape allows) | "mma" (mma.sync only)
+
+
+def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_splits=1, impl=None):
     """q/k/v: bf16 tensors; *_addr = (element offset, batch stride, row stride, head stride).
-    Returns bf16 [B, Nq, H*head_dim]."""
+    Returns bf16 [B, Nq, H*head_dim].  head_dim 256 / one head / Nq % 128 == 0 / contiguous batches run on the
+    tcgen05 kernel (usvm_fmha_tc5), everything else on the mma.sync kernel (usvm_fmha_bf16)."""
     for t in (q, k, v):
         _chk(t, BF16, "qkv")
     if out is None:
@@ -115,7 +119,14 @@ def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_
         ml_part = empty((num_splits, B * H, Nq, 2), F32, q)
         p.o_part, p.ml_part = o_part.data_ptr(), ml_part.data_ptr()
     p.scale = 1.0 / math.sqrt(head_dim)
-    call("usvm_fmha_bf16", C.byref(p), _stream())
+    use_tc5 = ((impl or _FMHA_IMPL) == "tc5" and head_dim == 256 and H == 1 and Nq % 128 == 0
+               and q_addr[1] == Nq * q_addr[2] and k_addr[1] == Nk * k_addr[2] and v_addr[1] == Nk * v_addr[2])
+    if use_tc5:
+        call("usvm_fmha_tc5", C.byref(p), _stream())
+        if num_splits > 1:
+            call("usvm_fmha_combine", C.byref(p), _stream())
+    else:
+        call("usvm_fmha_bf16", C.byref(p), _stream())
     return out
 
 
