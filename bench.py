@@ -67,6 +67,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -78,16 +85,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        # only samples taken inside the timed region count (nvidia-smi is started before the warm-up so that its
+        # start-up cost -- it briefly stalls CUDA calls of other processes -- stays outside the timed region)
+        lo = self.t0 if self.t0 is not None else 0.0
+        hi = self.t1 if self.t1 is not None else float("inf")
+        rows = [r for t, r in self.rows if lo <= t <= hi + 0.25] or [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
                     samples=len(sm))
 
@@ -223,15 +235,16 @@ def run_b200(args, rank, world):
         return one_pass(imgs, out_host)
 
     def timed(fn, steps, warmup):
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
+        sampler.mark_begin()
         l0 = _lib.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -240,6 +253,7 @@ def run_b200(args, rank, world):
             frames += fn()
         e1.record()
         torch.cuda.synchronize()
+        sampler.mark_end()
         launches = _lib.launch_count - l0
         clocks = sampler.stop() if rank == 0 else None
         if world > 1:
@@ -253,7 +267,7 @@ def run_b200(args, rank, world):
 
     with torch.inference_mode():
         ms, frames, launches, clocks = timed(step_resident, args.steps, args.warmup)
-        ms_e2e, frames_e2e, _, _ = timed(step_e2e, max(1, args.steps), 1)
+        ms_e2e, frames_e2e, _, _ = timed(step_e2e, max(1, args.steps), max(1, min(args.warmup, 2)))
     value = frames / (ms / 1000.0)
     e2e = frames_e2e / (ms_e2e / 1000.0)
 

@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of individual kernels at their propagation-path shapes (CUDA events on the launching stream,
+L2-warm like in the real frame where producers and consumers are back to back).  Prints one line per case."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from us_video_medsam2_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(0)
+
+
+def timeit(fn, iters=50, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e3  # us
+
+
+def rnd(*shape, dtype=torch.float32, scale=1.0):
+    return (torch.randn(shape, generator=g, device=dev) * scale).to(dtype)
+
+
+def attention():
+    T, D = 1024, 256
+    for B in (1, 4):
+        for Nk in (1024, 7232):
+            q = rnd(B * T, D, dtype=torch.bfloat16)
+            kv = rnd(B * Nk, 4 * D, dtype=torch.bfloat16)
+            args = (B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D))
+            flops = 4.0 * B * T * Nk * D
+            for impl in ("tc5", "mma"):
+                for splits in (1, 2, 4, 9, 18):
+                    if splits > (Nk + 63) // 64:
+                        continue
+                    us = timeit(lambda: ops.fmha(q, kv, kv, *args, num_splits=splits, impl=impl))
+                    print(f"fmha {impl} B={B} Nk={Nk} splits={splits:2d}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
+
+
+def gemms():
+    for (M, N, K) in [(1024, 256, 256), (1024, 768, 256), (1024, 2048, 256), (1024, 256, 2048), (7232, 1024, 64),
+                      (1024, 1024, 256), (1024, 256, 1024), (1024, 64, 256), (131072, 288, 96), (131072, 384, 96),
+                      (131072, 96, 384), (32768, 768, 192), (8192, 1536, 384), (8192, 384, 1536), (8192, 1152, 384)]:
+        a = rnd(M, K, dtype=torch.bfloat16)
+        w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5)
+        for bn in (0, 32, 64, 128, 256):
+            if bn > max(32, N):
+                continue
+            us = timeit(lambda: ops.gemm_bf16(a, w, f32=True, block_n=bn), iters=30)
+            print(f"gemm_tc5 M={M} N={N} K={K} bn={bn:3d}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
+    for (M, N, K) in [(1024, 384, 256), (1024, 256, 128), (1024, 256, 256), (4096, 128, 64)]:
+        a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+        us = timeit(lambda: ops.gemm_f32(a, w))
+        print(f"gemm_f32 M={M} N={N} K={K}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.2f} TFLOP/s", flush=True)
+    for (M, N, K) in [(8, 768, 256), (8, 256, 256), (8, 2048, 256), (8, 256, 2048), (8, 128, 256)]:
+        a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+        us = timeit(lambda: ops.gemm_skinny(a, w))
+        print(f"gemm_skinny M={M} N={N} K={K}: {us:8.1f} us", flush=True)
+
+
+def misc():
+    B, Nt = 1, 8
+    q = rnd(B * Nt, 128)
+    img = rnd(B * 1024, 384)
+    print(f"attn_t2i: {timeit(lambda: ops.attn_t2i(q, img[:, :128], img[:, 128:256], B, Nt, 1024)):8.1f} us")
+    k2, v2 = rnd(B * Nt, 128), rnd(B * Nt, 128)
+    print(f"attn_i2t: {timeit(lambda: ops.attn_i2t(img[:, 256:], k2, v2, B, 1024, Nt)):8.1f} us")
+    s = rnd(B, 1, 128, 128, scale=0.07)
+    print(f"fill_holes (local, area 8): {timeit(lambda: ops.fill_holes(s, 8)):8.1f} us")
+    print(f"fill_holes (union-find, area 40): {timeit(lambda: ops.fill_holes(s, 40)):8.1f} us")
+    x = rnd(1024, 256)
+    w, b = rnd(256), rnd(256)
+    print(f"layernorm 1024x256: {timeit(lambda: ops.layernorm(x, w, b, 1e-5, bf16=True)):8.1f} us")
+    xm = rnd(B * 1024, 256)
+    dw, db = rnd(49, 256), rnd(256)
+    print(f"dwconv7_ln: {timeit(lambda: ops.dwconv7_ln(xm, dw, db, w, b, B, 32, 32)):8.1f} us")
+    m = rnd(B, 512, 512, 1)
+    cw, cb, lw, lb = rnd(3, 3, 1, 4), rnd(4), rnd(4), rnd(4)
+    print(f"conv2d_small 1->4 @512: {timeit(lambda: ops.conv2d_small(m, cw, cb, B, 512, 512, 1, 4, 3, 2, 1, ln=(lw, lb), gelu=True)):8.1f} us")
+    m3 = rnd(B, 128, 128, 16)
+    cw3, cb3, lw3, lb3 = rnd(3, 3, 16, 64), rnd(64), rnd(64), rnd(64)
+    print(f"conv2d_small 16->64 @128: {timeit(lambda: ops.conv2d_small(m3, cw3, cb3, B, 128, 128, 16, 64, 3, 2, 1, ln=(lw3, lb3), gelu=True)):8.1f} us")
+    e = torch.empty(0, device=dev)
+    print(f"empty-ish launch (axpby 1 row): {timeit(lambda: ops.axpby(x[:1], None)):8.1f} us")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["attention", "gemms", "misc"]
+    for w_ in which:
+        globals()[w_]()

@@ -74,6 +74,75 @@ gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, in
   }
 }
 
+// fp32 x fp32 fast path: 16-byte global loads, register prefetch of the next k-tile while the current one is
+// multiplied (double-buffered shared memory), 64 x 64 x 16 tiles, 4 x 4 outputs per thread.
+// Requires K % 4 == 0, lda % 4 == 0, ldw % 4 == 0 and 16-byte aligned bases.
+__global__ void __launch_bounds__(256)
+gemm_simt_f32_pipelined_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                               const usvm_gemm_epilogue ep, int M, int N, int K) {
+  __shared__ __align__(16) float As[2][TK][TM + 4];
+  __shared__ __align__(16) float Ws[2][TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const int lr = tid >> 2, lk = (tid & 3) << 2;  // this thread's load slot: row lr, k offset lk..lk+3
+  const bool a_ok = m0 + lr < M, w_ok = n0 + lr < N;
+  const float* ap = A + (long long)(a_ok ? m0 + lr : 0) * lda + lk;
+  const float* wp = W + (long long)(w_ok ? n0 + lr : 0) * ldw + lk;
+  auto fetch = [&](int k0, float4& a, float4& w) {
+    const bool k_ok = k0 + lk < K;  // K % 4 == 0: a float4 is entirely inside or outside
+    a = (a_ok && k_ok) ? *reinterpret_cast<const float4*>(ap + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w = (w_ok && k_ok) ? *reinterpret_cast<const float4*>(wp + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto stash = [&](int buf, const float4& a, const float4& w) {
+    As[buf][lk][lr] = a.x; As[buf][lk + 1][lr] = a.y; As[buf][lk + 2][lr] = a.z; As[buf][lk + 3][lr] = a.w;
+    Ws[buf][lk][lr] = w.x; Ws[buf][lk + 1][lr] = w.y; Ws[buf][lk + 2][lr] = w.z; Ws[buf][lk + 3][lr] = w.w;
+  };
+  float acc[4][4] = {};
+  float4 a_next, w_next;
+  fetch(0, a_next, w_next);
+  stash(0, a_next, w_next);
+  __syncthreads();
+  const int nk = (K + TK - 1) / TK;
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) fetch((t + 1) * TK, a_next, w_next);  // in flight while this tile is multiplied
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    if (t + 1 < nk) {
+      stash(buf ^ 1, a_next, w_next);  // the other buffer was last read in iteration t - 1, before the barrier below
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+    const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= N) continue;
+      float x = acc[i][j];
+      if (ep.bias) x += ep.bias[col];
+      x = act_fn(x, ep.act);
+      if (ep.col_scale) x *= ep.col_scale[col];
+      if (ep.residual) x += ep.residual[rrow * ep.ldr + col];
+      if (ep.out_f32) ep.out_f32[(long long)row * ep.ldo_f32 + col] = x;
+      if (ep.out_bf16) reinterpret_cast<bf16*>(ep.out_bf16)[(long long)row * ep.ldo_bf16 + col] = __float2bfloat16(x);
+    }
+  }
+}
+
 template <typename TA, typename TW>
 int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
            cudaStream_t s) {
@@ -91,7 +160,17 @@ extern "C" int usvm_gemm_simt(const void* A, int a_is_bf16, int lda, const void*
   if (ep->rope_cos) return USVM_ERR_ARG;  // fused RoPE exists on the tensor-core kernel only
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a_is_bf16 && w_is_bf16) return launch<bf16, bf16>(A, lda, W, ldw, ep, M, N, K, s);
-  if (!a_is_bf16 && !w_is_bf16) return launch<float, float>(A, lda, W, ldw, ep, M, N, K, s);
+  if (!a_is_bf16 && !w_is_bf16) {
+    const bool vec_ok = (K % 4 == 0) && (lda % 4 == 0) && (ldw % 4 == 0) &&
+                        !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(W) & 15);
+    if (vec_ok) {
+      dim3 grid(cdiv(M, TM), cdiv(N, TN));
+      gemm_simt_f32_pipelined_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(A), lda,
+                                                           static_cast<const float*>(W), ldw, *ep, M, N, K);
+      return usvm_check_launch();
+    }
+    return launch<float, float>(A, lda, W, ldw, ep, M, N, K, s);
+  }
   if (a_is_bf16) return launch<bf16, float>(A, lda, W, ldw, ep, M, N, K, s);
   return launch<float, bf16>(A, lda, W, ldw, ep, M, N, K, s);
 }
