@@ -14,17 +14,25 @@ dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 
 
-def timeit(fn, iters=50, warm=5):
+def timeit(fn, iters=20, warm=3, replays=5):
+    """GPU time per call: `iters` calls are captured in one CUDA graph (no host launch overhead between kernels, as on
+    the real steady-state frame) and the graph is replayed `replays` times between two events."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(iters):
+            fn()
+    graph.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(replays):
+        graph.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e3  # us
+    return s.elapsed_time(e) / (iters * replays) * 1e3  # us
 
 
 def rnd(*shape, dtype=torch.float32, scale=1.0):
@@ -56,7 +64,7 @@ def gemms():
         for bn in (0, 32, 64, 128, 256):
             if bn > max(32, N):
                 continue
-            us = timeit(lambda: ops.gemm_bf16(a, w, f32=True, block_n=bn), iters=30)
+            us = timeit(lambda: ops.gemm_bf16(a, w, f32=True, block_n=bn), iters=10)
             print(f"gemm_tc5 M={M} N={N} K={K} bn={bn:3d}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
     for (M, N, K) in [(1024, 384, 256), (1024, 256, 128), (1024, 256, 256), (4096, 128, 64)]:
         a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)

@@ -98,7 +98,11 @@ cc_smem_kernel(const uint8_t* __restrict__ img, const float* scores_in, float* s
     const int by = b / WB, bx = b - by * WB;
     const int p = 2 * by * W + 2 * bx;
     const int k = s_fg[p] + s_fg[p + 1] + s_fg[p + W] + s_fg[p + W + 1];
-    if (k) atomicAdd(&s_area[root], k);
+    {  // warp-aggregated: lanes that share a root (a giant component!) issue one atomic instead of 32
+      const unsigned peers = __match_any_sync(__activemask(), root);
+      const int total = __reduce_add_sync(peers, k);
+      if (total && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&s_area[root], total);
+    }
     // path compression is deferred to a private write: other threads may still be walking through b
     // towards the root, and pointing b at the root keeps every chain valid
     s_par[b] = root;
@@ -195,78 +199,70 @@ __global__ void cc_g_roots(FG fg, int32_t* labels, int32_t* counts, const float*
 
 // ---------------------------------------------------------------------------------------------
 // Hole filling without global labelling.  Only components of area <= max_area matter, and such a component has
-// diameter < max_area, so `max_area` rounds of min-label propagation over the 3x3 neighbourhood make every small
-// component converge to its minimum pixel index.  A label group that is (a) closed -- no member touches a
-// background pixel carrying a different label -- and (b) of size <= max_area is exactly one small component: a
-// closed group is a whole component, and an unconverged larger component always contains an adjacent pair of
-// different labels, which marks both groups open.  One CTA per image, everything in shared memory.
+// graph diameter < max_area, so `max_area` SYNCHRONOUS rounds of min-label propagation over the 3x3 neighbourhood
+// make every small component converge to its minimum pixel index.  A label group that is (a) closed -- no member
+// touches a background pixel carrying a different label -- and (b) of size <= max_area is exactly one small
+// component: a closed group is a whole component, and an unconverged larger component always contains an adjacent
+// pair of different labels, which marks both groups open.  Synchronous (ping-pong) rounds also bound every group to
+// the (2 max_area + 1)^2 window around its label, so the per-label atomic counters never see more than a few hundred
+// increments (a giant component would otherwise serialise thousands of atomics on one address).
+// One CTA per image, everything in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kOpenFlag = 0x40000000;
-
 __global__ void __launch_bounds__(1024)
 fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W, int max_area, float fill_value) {
   extern __shared__ int s_mem[];
   const int HW = H * W;
-  int* s_lab = s_mem;        // label (pixel index) or -1 on foreground of the mask
-  int* s_cnt = s_mem + HW;   // per-label size | open flag
+  int* s_a = s_mem;           // labels, ping
+  int* s_b = s_mem + HW;      // labels, pong
+  int* s_cnt = s_mem + 2 * HW;  // per-label size (<0: open group)
   const long long base = (long long)blockIdx.x * HW;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < HW; i += nt) {
-    s_lab[i] = scores_in[base + i] <= 0.0f ? i : -1;
+    s_a[i] = scores_in[base + i] <= 0.0f ? i : -1;  // -1: foreground of the mask (not part of any hole)
     s_cnt[i] = 0;
   }
   __syncthreads();
+  int* cur = s_a;
+  int* nxt = s_b;
   for (int round = 0; round < max_area; ++round) {
     for (int i = tid; i < HW; i += nt) {
-      int me = s_lab[i];
-      if (me < 0) continue;
-      const int r = i / W, c = i - r * W;
+      const int me = cur[i];
       int m = me;
-#pragma unroll
-      for (int dr = -1; dr <= 1; ++dr) {
-        const int rr = r + dr;
-        if (rr < 0 || rr >= H) continue;
-#pragma unroll
-        for (int dc = -1; dc <= 1; ++dc) {
-          const int cc = c + dc;
-          if (cc < 0 || cc >= W) continue;
-          const int q = s_lab[rr * W + cc];
-          if (q >= 0 && q < m) m = q;
-        }
+      if (me >= 0) {
+        const int r = i / W, c = i - r * W;
+        const int r0 = max(r - 1, 0), r1 = min(r + 1, H - 1), c0 = max(c - 1, 0), c1 = min(c + 1, W - 1);
+        for (int rr = r0; rr <= r1; ++rr)
+          for (int cc = c0; cc <= c1; ++cc) {
+            const int q = cur[rr * W + cc];
+            if (q >= 0 && q < m) m = q;
+          }
       }
-      if (m < me) s_lab[i] = m;  // in place: labels only decrease towards the component minimum
+      nxt[i] = m;
     }
     __syncthreads();
+    int* t = cur;
+    cur = nxt;
+    nxt = t;
   }
   for (int i = tid; i < HW; i += nt) {
-    const int me = s_lab[i];
+    const int me = cur[i];
     if (me < 0) continue;
     const int r = i / W, c = i - r * W;
+    const int r0 = max(r - 1, 0), r1 = min(r + 1, H - 1), c0 = max(c - 1, 0), c1 = min(c + 1, W - 1);
     bool open = false;
-#pragma unroll
-    for (int dr = -1; dr <= 1; ++dr) {
-      const int rr = r + dr;
-      if (rr < 0 || rr >= H) continue;
-#pragma unroll
-      for (int dc = -1; dc <= 1; ++dc) {
-        const int cc = c + dc;
-        if (cc < 0 || cc >= W) continue;
-        const int q = s_lab[rr * W + cc];
+    for (int rr = r0; rr <= r1; ++rr)
+      for (int cc = c0; cc <= c1; ++cc) {
+        const int q = cur[rr * W + cc];
         open |= (q >= 0 && q != me);
       }
-    }
-    atomicAdd(&s_cnt[me], 1);  // sizes stay far below the flag bit
-    if (open) atomicOr(&s_cnt[me], kOpenFlag);
+    // closed members count +1; an open member poisons the counter (sizes are <= (2 max_area + 1)^2 << 2^20)
+    atomicAdd(&s_cnt[me], open ? (1 << 20) : 1);
   }
   __syncthreads();
   for (int i = tid; i < HW; i += nt) {
-    const int me = s_lab[i];
+    const int me = cur[i];
     const float v = scores_in[base + i];
-    bool hole = false;
-    if (me >= 0) {
-      const int cnt = s_cnt[me];
-      hole = !(cnt & kOpenFlag) && cnt <= max_area;
-    }
+    const bool hole = me >= 0 && s_cnt[me] <= max_area;
     scores_out[base + i] = hole ? fill_value : v;
   }
 }
@@ -325,7 +321,7 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
   if (!scores_in || !scores_out) return USVM_ERR_ARG;
   if ((long long)H * W >= (1LL << 31) - 1 || N > 65535) return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const size_t local_bytes = (size_t)H * W * 8;
+  const size_t local_bytes = (size_t)H * W * 12;
   if (max_area <= 32 && local_bytes <= kSmemLimit) {  // the propagation path's case: 128 x 128, max_area 8
     static bool configured = false;
     if (!configured) {

@@ -8,8 +8,9 @@
 // Warp roles (192 threads):
 //   warp 0   TMA producer: Q once (4 boxes of 128 x 64), then K / V tiles (4 + 4 boxes of 64 x 64) through a
 //            2-stage mbarrier ring, 128-byte swizzle
-//   warp 1   tcgen05.mma issuer: S_{j+1} = Q K_{j+1}^T is issued before waiting for the softmax of tile j, so the
-//            QK^T half of the tensor work overlaps the softmax; O += P_j V_j uses V in place as an MN-major operand
+//   warp 1   tcgen05.mma issuer: S_{j+1} = Q K_{j+1}^T is issued before waiting for the softmax of tile j, and P is
+//            double buffered, so both MMAs of a tile overlap the softmax of the next one; O += P_j V_j uses V in
+//            place as an MN-major operand
 //   warps 2-5 softmax: thread <-> query row (no cross-thread reductions): tcgen05.ld S, online softmax in base 2
 //            with lazy rescaling (O in TMEM is only rescaled when the running max grows by more than 2^8),
 //            P written as bf16 into the swizzled K-major smem tile that feeds the second MMA
@@ -27,7 +28,7 @@ constexpr int THREADS = 192;
 constexpr int Q_BYTES = NCH * QM * 128;     // 65536
 constexpr int KV_BYTES = NCH * KN * 128;    // 32768 per operand per stage
 constexpr int P_BYTES = QM * 128;           // 16384
-constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + P_BYTES + 1024 + 256;
+constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;
 
 __device__ __forceinline__ void tc5_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -64,15 +65,15 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;                 // 2 stages
   uint8_t* sV = sK + 2 * KV_BYTES;            // 2 stages
-  uint8_t* sP = sV + 2 * KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint8_t* sP = sV + 2 * KV_BYTES;            // 2 buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
   uint64_t* q_full = bars;            // 1
   uint64_t* kv_full = bars + 1;       // 2
   uint64_t* kv_empty = bars + 3;      // 2
   uint64_t* s_full = bars + 5;        // 2
-  uint64_t* p_full = bars + 7;        // 1 (128 arrivals)
-  uint64_t* pv_done = bars + 8;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* p_full = bars + 7;        // 2 (128 arrivals each)
+  uint64_t* pv_done = bars + 9;       // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * QM;
@@ -93,9 +94,9 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
     }
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
     mbar_fence_init();
   }
   if (warp == 1) tc5_alloc(tmem_slot, 512);
@@ -144,16 +145,17 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_s(0);
       for (int j = 0; j < n; ++j) {
         if (j + 1 < n) issue_s(j + 1);
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc5_fence_after();
         const uint32_t v_addr = smem_u32(sV + (j & 1) * KV_BYTES);
+        const uint32_t pj_addr = p_addr + (j & 1) * P_BYTES;
 #pragma unroll
         for (int kk = 0; kk < KN / 16; ++kk) {
-          tc5_mma_f16(tmem_O, umma_desc_k_sw128(p_addr + kk * 32), umma_desc_mn_sw128(v_addr + kk * 2048, KN * 128),
+          tc5_mma_f16(tmem_O, umma_desc_k_sw128(pj_addr + kk * 32), umma_desc_mn_sw128(v_addr + kk * 2048, KN * 128),
                       idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         tc5_commit(&kv_empty[j & 1]);
-        tc5_commit(pv_done);
+        tc5_commit(&pv_done[j & 1]);
       }
     }
     __syncwarp();
@@ -200,10 +202,13 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
       l += sum;
-      if (j > 0) {  // O += P_{j-1} V_{j-1} must have completed before O is rescaled and P is overwritten
-        mbar_wait(pv_done, (j - 1) & 1);
+      // P buffer j&1 was last read by O += P_{j-2} V_{j-2}
+      if (j >= 2) mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);
+      if (j > 0 && __any_sync(0xffffffffu, rescale)) {
+        // rare (lazy rescaling): O may only be touched once O += P_{j-1} V_{j-1} has completed
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc5_fence_after();
-        if (__any_sync(0xffffffffu, rescale)) {
+        {
 #pragma unroll 1
           for (int c = 0; c < HD; c += 32) {
             uint32_t o[32];
@@ -217,7 +222,7 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       // P row r -> swizzled K-major tile: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
-      uint8_t* prow = sP + r * 128;
+      uint8_t* prow = sP + st * P_BYTES + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const uint4 v4 = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
@@ -225,13 +230,13 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async();
       tc5_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[st]);
     }
     // ---- epilogue ----
     const int row = q0 + r;
     const int bh = b;  // H == 1
     if (n > 0) {
-      mbar_wait(pv_done, (n - 1) & 1);
+      mbar_wait(&pv_done[(n - 1) & 1], ((n - 1) >> 1) & 1);
       tc5_fence_after();
     }
     const float inv = (p.num_splits == 1 && l > 0.f) ? 1.f / l : 1.f;
