@@ -249,8 +249,12 @@ def run_b200(args, rank, world):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         frames = 0
-        for _ in range(steps):
+        for i in range(steps):
+            t_host = time.perf_counter()
             frames += fn()
+            if os.environ.get("USVM2_BENCH_DEBUG"):
+                print(f"[bench debug] {fn.__name__} step {i}: host loop {1e3 * (time.perf_counter() - t_host):.1f} ms",
+                      file=sys.stderr, flush=True)
         e1.record()
         torch.cuda.synchronize()
         sampler.mark_end()

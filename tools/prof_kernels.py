@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Tiny driver for `ncu --set full`: launches the hot kernels a few times at their propagation-path shapes."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from us_video_medsam2_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(0)
+rnd = lambda *s, dt=torch.bfloat16, sc=1.0: (torch.randn(s, generator=g, device=dev) * sc).to(dt)
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "gemm_enc"):
+    a, w = rnd(131072, 96), rnd(288, 96, sc=0.1)
+    b = rnd(288, dt=torch.float32)
+    for _ in range(4):
+        ops.gemm_bf16(a, w, bias=b, bf16=True)
+if which in ("all", "gemm_ma"):
+    a, w = rnd(1024, 2048), rnd(256, 2048, sc=0.02)
+    r = rnd(1024, 256, dt=torch.float32)
+    for _ in range(4):
+        ops.gemm_bf16(a, w, residual=r, f32=True)
+if which in ("all", "fmha"):
+    B, T, Nk, D = 1, 1024, 7232, 256
+    q, kv = rnd(B * T, D), rnd(B * Nk, 4 * D)
+    for _ in range(4):
+        ops.fmha(q, kv, kv, B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D),
+                 num_splits=9)
+torch.cuda.synchronize()
+print("done")

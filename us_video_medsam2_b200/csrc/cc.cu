@@ -208,67 +208,95 @@ __global__ void cc_g_roots(FG fg, int32_t* labels, int32_t* counts, const float*
 // increments (a giant component would otherwise serialise thousands of atomics on one address).
 // One CTA per image, everything in shared memory.
 // ---------------------------------------------------------------------------------------------
+constexpr int kNoLabel = 0x7fffffff;
+
+// Each thread owns a 4 x 4 pixel tile (labels in registers, 6 x 6 halo read from shared memory once per round), the
+// label planes carry a one-pixel border of kNoLabel so the stencil needs no bounds checks.
 __global__ void __launch_bounds__(1024)
 fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W, int max_area, float fill_value) {
   extern __shared__ int s_mem[];
-  const int HW = H * W;
-  int* s_a = s_mem;           // labels, ping
-  int* s_b = s_mem + HW;      // labels, pong
-  int* s_cnt = s_mem + 2 * HW;  // per-label size (<0: open group)
+  const int HW = H * W, Wp = W + 2, plane = (H + 2) * Wp;
+  int* s_a = s_mem;             // labels, ping   [(H+2) x (W+2)]
+  int* s_b = s_mem + plane;     // labels, pong
+  int* s_cnt = s_mem + 2 * plane;  // per-label closed-member count (open members add 2^20)
   const long long base = (long long)blockIdx.x * HW;
   const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < plane; i += nt) {
+    s_a[i] = kNoLabel;
+    s_b[i] = kNoLabel;
+  }
+  for (int i = tid; i < HW; i += nt) s_cnt[i] = 0;
+  __syncthreads();
   for (int i = tid; i < HW; i += nt) {
-    s_a[i] = scores_in[base + i] <= 0.0f ? i : -1;  // -1: foreground of the mask (not part of any hole)
-    s_cnt[i] = 0;
+    const int r = i / W, c = i - r * W;
+    if (scores_in[base + i] <= 0.0f) s_a[(r + 1) * Wp + c + 1] = i;
   }
   __syncthreads();
+  const int tiles_x = W >> 2, tiles = (H >> 2) * tiles_x;
   int* cur = s_a;
   int* nxt = s_b;
   for (int round = 0; round < max_area; ++round) {
-    for (int i = tid; i < HW; i += nt) {
-      const int me = cur[i];
-      int m = me;
-      if (me >= 0) {
-        const int r = i / W, c = i - r * W;
-        const int r0 = max(r - 1, 0), r1 = min(r + 1, H - 1), c0 = max(c - 1, 0), c1 = min(c + 1, W - 1);
-        for (int rr = r0; rr <= r1; ++rr)
-          for (int cc = c0; cc <= c1; ++cc) {
-            const int q = cur[rr * W + cc];
-            if (q >= 0 && q < m) m = q;
-          }
-      }
-      nxt[i] = m;
+    for (int t = tid; t < tiles; t += nt) {
+      const int ty = t / tiles_x, tx = t - ty * tiles_x;
+      const int* src = cur + (4 * ty) * Wp + 4 * tx;  // top-left of the 6 x 6 halo window
+      int v[6][6];
+#pragma unroll
+      for (int y = 0; y < 6; ++y)
+#pragma unroll
+        for (int x = 0; x < 6; ++x) v[y][x] = src[y * Wp + x];
+      int* dst = nxt + (4 * ty + 1) * Wp + 4 * tx + 1;
+#pragma unroll
+      for (int y = 1; y <= 4; ++y)
+#pragma unroll
+        for (int x = 1; x <= 4; ++x) {
+          int m = min(min(min(v[y - 1][x - 1], v[y - 1][x]), min(v[y - 1][x + 1], v[y][x - 1])),
+                      min(min(v[y][x + 1], v[y + 1][x - 1]), min(v[y + 1][x], v[y + 1][x + 1])));
+          m = min(m, v[y][x]);
+          dst[(y - 1) * Wp + (x - 1)] = v[y][x] == kNoLabel ? kNoLabel : m;
+        }
     }
     __syncthreads();
-    int* t = cur;
+    int* tswap = cur;
     cur = nxt;
-    nxt = t;
+    nxt = tswap;
   }
-  for (int i = tid; i < HW; i += nt) {
-    const int me = cur[i];
-    if (me < 0) continue;
-    const int r = i / W, c = i - r * W;
-    const int r0 = max(r - 1, 0), r1 = min(r + 1, H - 1), c0 = max(c - 1, 0), c1 = min(c + 1, W - 1);
-    bool open = false;
-    for (int rr = r0; rr <= r1; ++rr)
-      for (int cc = c0; cc <= c1; ++cc) {
-        const int q = cur[rr * W + cc];
-        open |= (q >= 0 && q != me);
+  for (int t = tid; t < tiles; t += nt) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int* src = cur + (4 * ty) * Wp + 4 * tx;
+    int v[6][6];
+#pragma unroll
+    for (int y = 0; y < 6; ++y)
+#pragma unroll
+      for (int x = 0; x < 6; ++x) v[y][x] = src[y * Wp + x];
+#pragma unroll
+    for (int y = 1; y <= 4; ++y)
+#pragma unroll
+      for (int x = 1; x <= 4; ++x) {
+        const int me = v[y][x];
+        if (me == kNoLabel) continue;
+        bool open = false;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int q = v[y + dy][x + dx];
+            open |= (q != kNoLabel && q != me);
+          }
+        atomicAdd(&s_cnt[me], open ? (1 << 20) : 1);
       }
-    // closed members count +1; an open member poisons the counter (sizes are <= (2 max_area + 1)^2 << 2^20)
-    atomicAdd(&s_cnt[me], open ? (1 << 20) : 1);
   }
   __syncthreads();
   for (int i = tid; i < HW; i += nt) {
-    const int me = cur[i];
+    const int r = i / W, c = i - r * W;
+    const int me = cur[(r + 1) * Wp + c + 1];
     const float v = scores_in[base + i];
-    const bool hole = me >= 0 && s_cnt[me] <= max_area;
+    const bool hole = me != kNoLabel && s_cnt[me] <= max_area;
     scores_out[base + i] = hole ? fill_value : v;
   }
 }
 
 size_t smem_bytes(int H, int W) { return (size_t)(H / 2) * (W / 2) * 8 + (size_t)H * W; }
-constexpr size_t kSmemLimit = 200 * 1024;
+constexpr size_t kSmemLimit = 224 * 1024;
 
 template <bool FILL>
 int launch_smem(const uint8_t* img, const float* sin, float* sout, int32_t* labels, int32_t* counts, int N, int H,
@@ -321,8 +349,8 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
   if (!scores_in || !scores_out) return USVM_ERR_ARG;
   if ((long long)H * W >= (1LL << 31) - 1 || N > 65535) return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const size_t local_bytes = (size_t)H * W * 12;
-  if (max_area <= 32 && local_bytes <= kSmemLimit) {  // the propagation path's case: 128 x 128, max_area 8
+  const size_t local_bytes = ((size_t)2 * (H + 2) * (W + 2) + (size_t)H * W) * 4;
+  if (max_area <= 32 && local_bytes <= kSmemLimit && (H % 4) == 0 && (W % 4) == 0) {  // the propagation path's case: 128 x 128, max_area 8
     static bool configured = false;
     if (!configured) {
       if (cudaFuncSetAttribute(fill_holes_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) !=

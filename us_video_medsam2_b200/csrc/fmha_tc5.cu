@@ -5,15 +5,16 @@
 // fmha_combine_kernel in attention.cu).  Accumulators live in TMEM:
 //     columns [0,64) / [64,128)   S = Q K^T, double buffered (fp32, 128 lanes x 64)
 //     columns [128,384)           O           (fp32, 128 lanes x 256)
-// Warp roles (192 threads):
+// Warp roles (320 threads):
 //   warp 0   TMA producer: Q once (4 boxes of 128 x 64), then K / V tiles (4 + 4 boxes of 64 x 64) through a
 //            2-stage mbarrier ring, 128-byte swizzle
 //   warp 1   tcgen05.mma issuer: S_{j+1} = Q K_{j+1}^T is issued before waiting for the softmax of tile j, and P is
 //            double buffered, so both MMAs of a tile overlap the softmax of the next one; O += P_j V_j uses V in
 //            place as an MN-major operand
-//   warps 2-5 softmax: thread <-> query row (no cross-thread reductions): tcgen05.ld S, online softmax in base 2
-//            with lazy rescaling (O in TMEM is only rescaled when the running max grows by more than 2^8),
-//            P written as bf16 into the swizzled K-major smem tile that feeds the second MMA
+//   warps 2-9 softmax: thread <-> (query row, half of the tile's 64 key columns); the row max is exchanged between the
+//            two halves through shared memory + a 64-thread named barrier; tcgen05.ld S, online softmax in base 2
+//            (ex2.approx) with lazy rescaling (O in TMEM is only rescaled when the running max grows by more than
+//            2^8), P written as bf16 into the swizzled K-major smem tile that feeds the second MMA
 #include "common.cuh"
 #include "usvm2_b200.h"
 
@@ -23,12 +24,14 @@ constexpr int QM = 128;   // queries per CTA
 constexpr int KN = 64;    // keys per tile
 constexpr int HD = 256;   // head dim
 constexpr int NCH = HD / 64;  // 64-column (128-byte) chunks per row
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps
 
 constexpr int Q_BYTES = NCH * QM * 128;     // 65536
 constexpr int KV_BYTES = NCH * KN * 128;    // 32768 per operand per stage
 constexpr int P_BYTES = QM * 128;           // 16384
-constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;
+constexpr int XCH_BYTES = 4 * QM * 4;  // row max exchange between the two column halves, double buffered
+constexpr int ALIGN_SLACK = 512;  // the dynamic smem base is 1024-aligned in practice; trap if it is not
+constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + 2 * P_BYTES + XCH_BYTES + ALIGN_SLACK + 256;
 
 __device__ __forceinline__ void tc5_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -42,6 +45,11 @@ __device__ __forceinline__ void tc5_st_32x32(uint32_t taddr, const uint32_t (&r)
       : "memory");
 }
 __device__ __forceinline__ void tc5_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // MN-major operand (rows = K index, 128 bytes = 64 consecutive N elements per row, 128B swizzle):
@@ -60,13 +68,15 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn) {
 __global__ void __launch_bounds__(THREADS, 1)
 fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const usvm_fmha_params p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (smem - smem_raw > ALIGN_SLACK) __trap();
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;                 // 2 stages
   uint8_t* sV = sK + 2 * KV_BYTES;            // 2 stages
   uint8_t* sP = sV + 2 * KV_BYTES;            // 2 buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  float* s_xch = reinterpret_cast<float*>(sP + 2 * P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES + XCH_BYTES);
   uint64_t* q_full = bars;            // 1
   uint64_t* kv_full = bars + 1;       // 2
   uint64_t* kv_empty = bars + 3;      // 2
@@ -94,7 +104,7 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&p_full[s], 256);
       mbar_init(&pv_done[s], 1);
     }
     mbar_fence_init();
@@ -160,29 +170,34 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     __syncwarp();
   } else {
+    // ---- softmax: 8 warps; warps w and w + 4 share the 32 query rows of TMEM lane group (w & 3) and split the 64
+    //      key columns of a tile in halves (two warps per scheduler hide each other's latencies) ----
     const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = lane_grp * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
     const float sl2 = p.scale * 1.4426950408889634f;
-    float m_ref = -INFINITY, l = 0.f;
+    float m_ref = -INFINITY, l = 0.f;  // m_ref in log2 units (raw score * sl2); l = this half's partial row sum
     for (int j = 0; j < n; ++j) {
       const int st = j & 1;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc5_fence_after();
-      uint32_t sa[32], sb[32];
-      tc5_ld_32x32(tmem + lane_addr + st * KN, sa);
-      tc5_ld_32x32(tmem + lane_addr + st * KN + 32, sb);
+      uint32_t sa[32];
+      tc5_ld_32x32(tmem + lane_addr + st * KN + half * 32, sa);
       tc5_wait_ld();
-      float s[64];
-      const int key0 = (t_begin + j) * KN;
+      const int key0 = (t_begin + j) * KN + half * 32;
       float mx = -INFINITY;
+      if (key0 + 32 > p.Nk) {  // ragged last tile only
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float v = __uint_as_float(i < 32 ? sa[i] : sb[i - 32]) * sl2;
-        if (key0 + i >= p.Nk) v = -INFINITY;
-        s[i] = v;
-        mx = fmaxf(mx, v);
+        for (int i = 0; i < 32; ++i)
+          if (key0 + i >= p.Nk) sa[i] = 0xff800000u;  // -inf
       }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sa[i]));
+      // row max across the two column halves (partner warp = same lane group, other half)
+      s_xch[(st * 2 + half) * QM + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");
+      mx = fmaxf(mx, s_xch[(st * 2 + (half ^ 1)) * QM + r]) * sl2;
       float corr = 1.f;
       bool rescale = false;
       if (j == 0) {
@@ -194,10 +209,11 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         rescale = true;
       }
       float sum = 0.f;
-      uint32_t pk[32];
+      uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        const float p0 = exp2f(s[i] - m_ref), p1 = exp2f(s[i + 1] - m_ref);
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sa[i]), sl2, -m_ref));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sa[i + 1]), sl2, -m_ref));
         sum += p0 + p1;
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
@@ -205,34 +221,37 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // P buffer j&1 was last read by O += P_{j-2} V_{j-2}
       if (j >= 2) mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);
       if (j > 0 && __any_sync(0xffffffffu, rescale)) {
-        // rare (lazy rescaling): O may only be touched once O += P_{j-1} V_{j-1} has completed
+        // rare (lazy rescaling): O may only be touched once O += P_{j-1} V_{j-1} has completed; each half owns
+        // 128 of the 256 output columns
         mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
         tc5_fence_after();
-        {
 #pragma unroll 1
-          for (int c = 0; c < HD; c += 32) {
-            uint32_t o[32];
-            tc5_ld_32x32(tmem_O + lane_addr + c, o);
-            tc5_wait_ld();
+        for (int c = half * 128; c < half * 128 + 128; c += 32) {
+          uint32_t o[32];
+          tc5_ld_32x32(tmem_O + lane_addr + c, o);
+          tc5_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-            tc5_st_32x32(tmem_O + lane_addr + c, o);
-          }
-          tc5_wait_st();
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+          tc5_st_32x32(tmem_O + lane_addr + c, o);
         }
+        tc5_wait_st();
       }
       // P row r -> swizzled K-major tile: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
       uint8_t* prow = sP + st * P_BYTES + r * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const uint4 v4 = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = v4;
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (r & 7)) << 4)) = v4;
       }
       fence_proxy_async();
       tc5_fence_before();
       mbar_arrive(&p_full[st]);
     }
-    // ---- epilogue ----
+    // ---- epilogue: total row sum = both halves; each half stores 128 of the 256 output columns ----
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");  // partner is done with s_xch
+    s_xch[half * QM + r] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");
+    l += s_xch[(half ^ 1) * QM + r];
     const int row = q0 + r;
     const int bh = b;  // H == 1
     if (n > 0) {
@@ -241,7 +260,7 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     const float inv = (p.num_splits == 1 && l > 0.f) ? 1.f / l : 1.f;
 #pragma unroll 1
-    for (int c = 0; c < HD; c += 32) {
+    for (int c = half * 128; c < half * 128 + 128; c += 32) {
       uint32_t o[32];
       if (n > 0) {
         tc5_ld_32x32(tmem_O + lane_addr + c, o);
@@ -270,7 +289,7 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                                            __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
       }
     }
-    if (p.num_splits > 1 && row < p.Nq) {
+    if (p.num_splits > 1 && row < p.Nq && half == 0) {
       // (m, l) in the convention of fmha_combine_kernel: m in raw score units, weights exp2((m - M) * scale * log2e)
       float* ML = p.ml_part + (((long long)split * gridDim.y + bh) * p.Nq + row) * 2;
       ML[0] = n > 0 ? m_ref / sl2 : -INFINITY;

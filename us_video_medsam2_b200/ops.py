@@ -21,7 +21,14 @@ F32 = torch.float32
 _FORCE_SIMT = os.environ.get("USVM2_GEMM", "") == "simt"
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """cudaStream_t of torch's current stream on the current device (raw handle: the Python Stream wrapper costs
+    ~15 us per call, more than most of the kernels launched here)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

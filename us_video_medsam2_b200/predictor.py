@@ -232,13 +232,44 @@ class SAM2VideoPredictor(nn.Module):
         n = self.encoder_batch if step != 0 else 1
         idxs = [frame_idx + i * step for i in range(n)] if step != 0 else [frame_idx]
         idxs = [t for t in idxs if 0 <= t < st["num_frames"]]
-        imgs = torch.stack([self._frame(st, t) for t in idxs]).contiguous()
-        out = eng.encode_frames(imgs)
-        keep = dict(cache) if len(cache) < 4 * self.encoder_batch else {}
+        if self.use_cuda_graphs and len(idxs) == self.encoder_batch and self.encoder_batch > 1:
+            # full look-ahead batch: replay the captured image-encoder graph.  Its outputs are static buffers that the
+            # next replay overwrites, so the cache holds exactly the frames of the latest batch.
+            ent = self._graphs.get(("encoder", len(idxs)))
+            if ent is None:
+                ent = self._capture_encoder_graph(len(idxs))
+            graph, static_in, out, n_kernels = ent
+            for j, t in enumerate(idxs):
+                static_in[j].copy_(self._frame(st, t), non_blocking=True)
+            graph.replay()
+            _lib.launch_count += n_kernels
+            keep = {}
+        else:
+            imgs = torch.stack([self._frame(st, t) for t in idxs]).contiguous()
+            out = eng.encode_frames(imgs)
+            keep = {t: v for t, v in cache.items() if not v.get("_static")} if len(cache) < 4 * self.encoder_batch else {}
         for j, t in enumerate(idxs):
             keep[t] = {k: v[j] for k, v in out.items()}
+        if self.use_cuda_graphs and len(idxs) == self.encoder_batch and self.encoder_batch > 1:
+            for t in idxs:
+                keep[t]["_static"] = True
         st["cached_features"] = keep
         return keep[frame_idx]
+
+    def _capture_encoder_graph(self, n):
+        eng = self.engine()
+        static_in = torch.zeros((n, 3, self.image_size, self.image_size), dtype=torch.float32, device=self.device)
+        eng.encode_frames(static_in)  # warm-up: one-time kernel attribute setup must not happen during capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count
+        with torch.cuda.graph(graph):
+            out = eng.encode_frames(static_in)
+        n_kernels = _lib.launch_count - before
+        _lib.launch_count = before
+        ent = (graph, static_in, out, n_kernels)
+        self._graphs[("encoder", n)] = ent
+        return ent
 
     def _frame(self, st, t):
         img = st["images"][t]
@@ -613,7 +644,7 @@ class SAM2VideoPredictor(nn.Module):
         if ent is not None:
             graph, static_f, video, n_kernels = ent
             for k, v in static_f.items():
-                v.copy_(f[k])
+                v.copy_(f[k], non_blocking=True)
             graph.replay()
             _lib.launch_count += n_kernels  # kernels of this library replayed by the graph
             video = video.clone()
