@@ -7,11 +7,14 @@
 //
 // Structure (one 128 x BN output tile per CTA, 192 threads):
 //   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D boxes {64 x 128} of A and {64 x BN} of W,
-//              128-byte swizzle, 4-stage mbarrier ring (zero fill beyond M / N / K edges)
+//              128-byte swizzle, mbarrier ring of min(4, K/64) stages (zero fill beyond M / N / K edges)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16, fp32 accum in
 //              TMEM), tcgen05.commit releases smem stages and finally signals the epilogue
 //   warps 2-5: epilogue -- tcgen05.ld 32x32b.x32 (one accumulator row per thread), fused
-//              bias / activation / per-column scale / residual, fp32 and/or bf16 stores
+//              bias / RoPE / activation / per-column scale / residual, then each warp stages its 32 x 32 block in
+//              shared memory and writes it with ONE TMA store (coalesced, edge clipping for free)
+// The ring depth follows K, so short-K GEMMs (the Hiera blocks: K = 96 ... 768) use little shared memory and 2-3 CTAs
+// share an SM: one CTA's epilogue overlaps another's loads and MMAs without a persistent scheduler.
 #include "common.cuh"
 #include "usvm2_b200.h"
 
@@ -22,13 +25,28 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 
+constexpr int STG_F32 = 32 * 128;  // per-warp staging of a 32 x 32 fp32 block (128-byte rows, 128B swizzle)
+constexpr int STG_BF16 = 32 * 64;  // per-warp staging of a 32 x 32 bf16 block (64-byte rows)
+constexpr int STG_BYTES = 4 * (STG_F32 + STG_BF16);
+
 template <int BN>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+  static constexpr int total(int stages) {
+    return stages * STAGE_BYTES + STG_BYTES + 1024 /* alignment slack */ + 128 /* barriers */;
+  }
 };
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
@@ -39,13 +57,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const usvm_gemm_epilogue ep, const int M, const int N, const int K) {
-  extern __shared__ uint8_t smem_raw[];
+                     const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
+                     const usvm_gemm_epilogue ep, const int M, const int N, const int K, const int stages) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = SmemLayout<BN>;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint8_t* staging = smem + stages * L::STAGE_BYTES;  // 1024-aligned: STAGE_BYTES is a multiple of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -59,7 +79,9 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    if (ep.out_f32) tma_prefetch_desc(&tmO32);
+    if (ep.out_bf16) tma_prefetch_desc(&tmO16);
+    for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -75,8 +97,8 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_dst = smem + s * L::STAGE_BYTES;
         uint8_t* b_dst = a_dst + L::A_BYTES;
@@ -90,8 +112,8 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc5_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
@@ -110,20 +132,24 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     __syncwarp();
   } else {
-    // ---- epilogue: thread <-> accumulator row ----
+    // ---- epilogue: thread <-> accumulator row; warp <-> 32-row slab written by TMA ----
     mbar_wait(tmem_full_bar, 0);
     tc5_fence_after();
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, 32*lane_grp + 32) are visible to this warp
-    const int row = tile_m * BM + lane_grp * 32 + lane;
+    const int row0 = tile_m * BM + lane_grp * 32;
+    const int row = row0 + lane;
     const bool row_ok = row < M;
     const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+    uint8_t* stg32 = staging + lane_grp * STG_F32;
+    uint8_t* stg16 = staging + 4 * STG_F32 + lane_grp * STG_BF16;
+    bool pending = false;  // this warp has a TMA store in flight that still reads its staging buffers
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int col0 = tile_n * BN + c0;
+      if (col0 >= N || row0 >= M) break;  // warp-uniform
       uint32_t acc[32];
       tc5_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
       tc5_wait_ld();
-      const int col0 = tile_n * BN + c0;
-      if (!row_ok || col0 >= N) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
@@ -165,7 +191,7 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
           }
         }
-        if (ep.residual) {
+        if (ep.residual && row_ok) {
           const float* r = ep.residual + rrow * ep.ldr + col0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -173,36 +199,53 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
         }
-        if (ep.out_f32) {
-          float* o = ep.out_f32 + (long long)row * ep.ldo_f32 + col0;
+      } else {  // ragged last column block: columns >= N are clipped by the TMA store, never read
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        if (ep.out_bf16) {
-          bf16* o = reinterpret_cast<bf16*>(ep.out_bf16) + (long long)row * ep.ldo_bf16 + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 p;
-            p.x = pack_bf16x2(v[j], v[j + 1]);
-            p.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            p.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            p.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = p;
+        for (int j = 0; j < 32; ++j) {
+          if (j < ncol) {
+            float x = v[j];
+            if (ep.bias) x += ep.bias[col0 + j];
+            x = apply_act(x, ep.act);
+            if (ep.col_scale) x *= ep.col_scale[col0 + j];
+            if (ep.residual && row_ok) x += ep.residual[rrow * ep.ldr + col0 + j];
+            v[j] = x;
           }
         }
-      } else {
-        for (int j = 0; j < ncol; ++j) {
-          float x = v[j];
-          if (ep.bias) x += ep.bias[col0 + j];
-          x = apply_act(x, ep.act);
-          if (ep.col_scale) x *= ep.col_scale[col0 + j];
-          if (ep.residual) x += ep.residual[rrow * ep.ldr + col0 + j];
-          if (ep.out_f32) ep.out_f32[(long long)row * ep.ldo_f32 + col0 + j] = x;
-          if (ep.out_bf16)
-            reinterpret_cast<bf16*>(ep.out_bf16)[(long long)row * ep.ldo_bf16 + col0 + j] = __float2bfloat16(x);
+      }
+      if (pending) {  // the previous block's TMA store must have finished reading the staging buffers
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      if (ep.out_f32) {  // 128-byte rows, 16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) * 16)
+        uint8_t* prow = stg32 + lane * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<float4*>(prow + ((c ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      if (ep.out_bf16) {  // 64-byte rows, no swizzle
+        uint8_t* prow = stg16 + lane * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+          pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+          pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+          pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+          *reinterpret_cast<uint4*>(prow + (c << 4)) = pk;
         }
       }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (ep.out_f32) tma_store_2d(&tmO32, stg32, col0, row0);
+        if (ep.out_bf16) tma_store_2d(&tmO16, stg16, col0, row0);
+        tma_store_commit();
+      }
+      pending = true;
     }
+    if (pending && lane == 0) tma_store_wait_read();  // smem must outlive the bulk reads
+    __syncwarp();
   }
   tc5_fence_before();
   __syncthreads();
@@ -227,37 +270,56 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 row-major [rows, cols] with row pitch ld (elements); box = {64 cols, box_rows}
-int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+// 2D row-major [rows, cols] with row pitch ld (elements); box = {box_cols, box_rows}
+int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const void* base, long long rows, long long cols,
+             long long ld, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return USVM_ERR_DRIVER;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? USVM_OK : USVM_ERR_DRIVER;
+}
+int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  return make_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, BK, box_rows,
+                  CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <int BN>
 int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
            cudaStream_t stream) {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO32, tmO16;
   int rc = make_map_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
   rc = make_map_bf16(&tmB, W, N, K, ldw, BN);
   if (rc) return rc;
+  tmO32 = tmA;  // placeholders keep the kernel parameters valid when an output is absent
+  tmO16 = tmA;
+  if (ep->out_f32) {
+    rc = make_map(&tmO32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep->out_f32, M, N, ep->ldo_f32, 32, 32,
+                  CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  if (ep->out_bf16) {
+    rc = make_map(&tmO16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep->out_bf16, M, N, ep->ldo_bf16, 32, 32,
+                  CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SmemLayout<BN>::TOTAL) != cudaSuccess)
+                             SmemLayout<BN>::total(STAGES)) != cudaSuccess)
       return USVM_ERR_CUDA;
     attr_set = true;
   }
+  const int num_kb = cdiv(K, BK);
+  const int stages = num_kb < STAGES ? num_kb : STAGES;
   dim3 grid(cdiv(M, BM), cdiv(N, BN));
-  gemm_bf16_tc5_kernel<BN><<<grid, GEMM_THREADS, SmemLayout<BN>::TOTAL, stream>>>(tmA, tmB, *ep, M, N, K);
+  gemm_bf16_tc5_kernel<BN><<<grid, GEMM_THREADS, SmemLayout<BN>::total(stages), stream>>>(tmA, tmB, tmO32, tmO16, *ep, M,
+                                                                                         N, K, stages);
   return usvm_check_launch();
 }
 
@@ -280,7 +342,7 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
   if (bn <= 0) {
     // latency-bound shapes dominate this path: prefer enough CTAs to cover the 148 SMs, then wider tiles
     const int mt = cdiv(M, BM);
-    bn = 256;
+    bn = 128;  // 128-wide tiles leave room for 2-3 CTAs per SM (TMEM 128 columns, <= 80 KB smem with short K)
     while (bn > 32 && (long long)mt * cdiv(N, bn) < 148) bn >>= 1;
     if (N <= 32) bn = 32;
     else if (N <= 64 && bn > 64) bn = 64;
