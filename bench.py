@@ -175,7 +175,7 @@ def time_dominant_kernel(dev, B, iters=20):
     q = torch.randn((B * T, D), generator=g, device=dev).to(torch.bfloat16)
     kv = torch.randn((B * Nk, 4 * D), generator=g, device=dev).to(torch.bfloat16)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    splits = max(1, min(max(1, 148 // (16 * B)), (Nk + 63) // 64))
+    splits = max(1, min(max(1, 148 // (8 * B)), (Nk + 63) // 64))  # same rule as Engine._splits
 
     def run():
         return ops.fmha(q, kv, kv, B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D),
@@ -282,7 +282,7 @@ def run_b200(args, rank, world):
         ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_sustained"], "traffic": None,
-                    "kernel": "fmha_bf16_kernel<256> + fmha_combine_kernel<256> (memory-attention cross-attention, "
+                    "kernel": "fmha_tc5_ts_kernel + fmha_combine_kernel<256> (memory-attention cross-attention, "
                               f"1024 x 7232 keys, d=256, {ks['splits']}-way split-KV)",
                     "launches_timed": ks["launches"], "avg_us": ks["avg_ms"] * 1e3, "peak_source": peaks["source"],
                     "how": "CUDA events around the kernel at its steady-state shape, L2 flushed between iterations "

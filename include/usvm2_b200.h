@@ -98,6 +98,8 @@ int usvm_fmha_bf16(const usvm_fmha_params* p_host, void* stream);
  * contiguous (x_bs == N * x_rs).  S = QK^T (double buffered) and O accumulate in TMEM, V is consumed in place as an
  * MN-major operand.  With num_splits > 1 it writes partials only: follow with usvm_fmha_combine. */
 int usvm_fmha_tc5(const usvm_fmha_params* p_host, void* stream);
+/* 0 (default): Q and P in tensor memory, A-from-TMEM MMAs;  1: Q and P in shared memory (first implementation) */
+int usvm_fmha_tc5_set_variant(int variant);
 int usvm_fmha_combine(const usvm_fmha_params* p_host, void* stream);
 /* fp32, one warp per query; head_dim 16 or 32, Nk <= 1024 (SAM decoder two-way transformer) */
 int usvm_attn_small_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Nq, int Nk,

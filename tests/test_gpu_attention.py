@@ -35,7 +35,8 @@ def test_fmha_bf16(D, B, H, Nq, Nk, splits):
                                             (1, 1024, 7232, 9), (2, 1024, 2068, 4), (1, 256, 1000, 3),
                                             (3, 128, 70, 2)])
 @pytest.mark.parametrize("scale_up", [1.0, 6.0])
-def test_fmha_tc5_matches_reference_and_mma_kernel(B, Nq, Nk, splits, scale_up):
+@pytest.mark.parametrize("variant", ["tc5", "tc5ss"])
+def test_fmha_tc5_matches_reference_and_mma_kernel(B, Nq, Nk, splits, scale_up, variant):
     """tcgen05 kernel (TMEM accumulators, MN-major V, lazy rescaling) vs fp32 reference and vs the mma.sync kernel;
     `scale_up` makes the scores large enough to trigger the O rescaling path."""
     from us_video_medsam2_b200 import ops
@@ -47,7 +48,7 @@ def test_fmha_tc5_matches_reference_and_mma_kernel(B, Nq, Nk, splits, scale_up):
     kv = torch.randn((B * Nk, 4 * D), generator=g, device="cuda").to(torch.bfloat16)
     kv[:, D:2 * D] *= scale_up
     args = (B, 1, Nq, Nk, D, (0, Nq * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D))
-    out = ops.fmha(q, kv, kv, *args, num_splits=splits, impl="tc5")
+    out = ops.fmha(q, kv, kv, *args, num_splits=splits, impl=variant)
     torch.cuda.synchronize()
     k = kv.view(B, Nk, 4 * D)[:, :, D:2 * D]
     v = kv.view(B, Nk, 4 * D)[:, :, 2 * D:3 * D]

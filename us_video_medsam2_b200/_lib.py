@@ -74,6 +74,7 @@ _SIGNATURES = {
     "usvm_fmha_bf16": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_tc5": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_combine": [C.POINTER(FmhaParams), _P],
+    "usvm_fmha_tc5_set_variant": [_I],
     "usvm_attn_small_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "usvm_layernorm": [_P, _I, _P, _P, _F, _I, _P, _I, _P, _I, _I, _I, _P],
     "usvm_axpby_rows": [_P, _P, _F, _F, _I, _I, _P, _P, _LL, _I, _P],

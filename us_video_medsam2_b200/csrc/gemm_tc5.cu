@@ -22,7 +22,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int STAGES = 4;
+constexpr int STAGES = 8;  // maximum ring depth (barrier storage); the launch picks the depth per problem
 constexpr int GEMM_THREADS = 192;
 
 constexpr int STG_F32 = 32 * 128;  // per-warp staging of a 32 x 32 fp32 block (128-byte rows, 128B swizzle)
@@ -310,14 +310,21 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
   }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             SmemLayout<BN>::total(STAGES)) != cudaSuccess)
+    const int want = SmemLayout<BN>::total(STAGES) < 227 * 1024 ? SmemLayout<BN>::total(STAGES) : 227 * 1024;
+    if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) !=
+        cudaSuccess)
       return USVM_ERR_CUDA;
     attr_set = true;
   }
   const int num_kb = cdiv(K, BK);
-  const int stages = num_kb < STAGES ? num_kb : STAGES;
   dim3 grid(cdiv(M, BM), cdiv(N, BN));
+  // Ring depth: a problem with fewer CTAs than ~2 per SM is latency bound -> as deep as shared memory allows (the
+  // k-loop then streams at TMA issue rate instead of TMA latency); big problems keep <= 4 stages so that 2-3 CTAs
+  // share an SM and overlap each other's epilogues.
+  const long long ctas = (long long)grid.x * grid.y;
+  int max_stages = ctas <= 2 * 148 ? STAGES : 4;
+  while (max_stages > 1 && SmemLayout<BN>::total(max_stages) > 200 * 1024) --max_stages;
+  const int stages = num_kb < max_stages ? num_kb : max_stages;
   gemm_bf16_tc5_kernel<BN><<<grid, GEMM_THREADS, SmemLayout<BN>::total(stages), stream>>>(tmA, tmB, tmO32, tmO16, *ep, M,
                                                                                          N, K, stages);
   return usvm_check_launch();

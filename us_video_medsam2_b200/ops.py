@@ -126,7 +126,10 @@ def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_
         ml_part = empty((num_splits, B * H, Nq, 2), F32, q)
         p.o_part, p.ml_part = o_part.data_ptr(), ml_part.data_ptr()
     p.scale = 1.0 / math.sqrt(head_dim)
-    use_tc5 = ((impl or _FMHA_IMPL) == "tc5" and head_dim == 256 and H == 1 and Nq % 128 == 0
+    which = impl or _FMHA_IMPL
+    if which in ("tc5", "tc5ss"):
+        _lib.lib().usvm_fmha_tc5_set_variant(1 if which == "tc5ss" else 0)
+    use_tc5 = (which in ("tc5", "tc5ss") and head_dim == 256 and H == 1 and Nq % 128 == 0
                and q_addr[1] == Nq * q_addr[2] and k_addr[1] == Nk * k_addr[2] and v_addr[1] == Nk * v_addr[2])
     if use_tc5:
         call("usvm_fmha_tc5", C.byref(p), _stream())
