@@ -69,7 +69,10 @@ typedef struct usvm_gemm_epilogue {
 
 /* bf16 operands, fp32 accumulation in TMEM: TMA (128B swizzle) -> tcgen05.mma -> tcgen05.ld epilogue.
  * A bf16 [M,K] row pitch lda, W bf16 [N,K] row pitch ldw (pitches % 8 == 0, bases 16-byte aligned).
- * block_n: 0 = auto, else 32 / 64 / 128 / 256. */
+ * block_n: 0 = auto; 32 / 64 / 128 / 256 = one 128 x block_n tile per CTA (latency-bound shapes); negative = the
+ * persistent kernel (one CTA per SM walks the tiles, accumulator double-buffered in TMEM so the epilogue of tile i
+ * overlaps the mainloop of tile i+1) with tile width -block_n (a multiple of 32, <= 256), -1 = its own choice.
+ * Auto picks the persistent kernel when the problem has more than two waves of 128 x 128 tiles. */
 int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep_host, int M, int N,
                        int K, int block_n, void* stream);
 /* fp32-accumulate SIMT GEMM, operands fp32 or bf16 (flags), any shape: fp32 decoder tail + checker. */

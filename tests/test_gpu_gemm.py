@@ -66,6 +66,54 @@ def test_tc5_gemm_fused_epilogue(act):
     assert (x - want).abs().max().item() < 3e-3
 
 
+PERSISTENT_SHAPES = [  # (M, N, K, block_n): block_n < 0 selects the persistent kernel, -1 = its own tile choice
+    (16384, 288, 96, -1), (8192, 1152, 384, -1), (8192, 1536, 384, -256), (8192, 384, 1536, -1), (7232, 1024, 64, -1),
+    (2048, 3072, 768, -1), (131072, 96, 384, -1), (5000, 200, 72, -1), (300, 104, 200, -64), (40000, 288, 96, -96),
+    (8192, 1152, 384, -192), (8192, 1152, 384, -32),
+]
+
+
+@pytest.mark.parametrize("M,N,K,block_n", PERSISTENT_SHAPES)
+def test_tc5_persistent_gemm_matches_fp32_reference(M, N, K, block_n):
+    """Persistent double-buffered-accumulator kernel: many tiles per CTA, ragged M / N / K edges, every tile width."""
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N * 3 + K * 5)
+    a = (torch.randn((M, K), generator=g, device="cuda")).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    o32, o16 = ops.gemm_bf16(a, w, f32=True, bf16=True, block_n=block_n, simt=False)
+    torch.cuda.synchronize()
+    want = _ref(a, w, None, 0, None, None, 0)
+    tol = 2e-3 * max(1.0, want.abs().max().item())
+    assert (o32 - want).abs().max().item() < tol
+    assert (o16.float() - want).abs().max().item() < 16 * tol
+    # the one-tile-per-CTA kernel accumulates the same bf16 products in the same order: bit-identical results
+    p32, _ = ops.gemm_bf16(a, w, f32=True, block_n=128, simt=False)
+    assert torch.equal(o32, p32)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_tc5_persistent_gemm_fused_epilogue(act):
+    from us_video_medsam2_b200 import ops
+
+    M, N, K = 8192 + 64, 384, 256
+    g = torch.Generator(device="cuda").manual_seed(100 + act)
+    a = torch.randn((M, K), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda")
+    scale = torch.rand(N, generator=g, device="cuda")
+    res = torch.randn((1024, N), generator=g, device="cuda")
+    o32, o16 = ops.gemm_bf16(a, w, bias=bias, act=act, col_scale=scale, residual=res, res_mod=1024, f32=True,
+                             bf16=True, simt=False, block_n=-1)
+    want = _ref(a, w, bias, act, scale, res, 1024)
+    assert (o32 - want).abs().max().item() < 3e-3
+    assert (o16.float() - want).abs().max().item() < 3e-2
+    x = torch.randn((M, N), generator=g, device="cuda")
+    want = _ref(a, w, bias, 0, None, x.clone(), 0)
+    ops.gemm_bf16(a, w, bias=bias, residual=x, out_f32=x, simt=False, block_n=-1)
+    assert (x - want).abs().max().item() < 3e-3
+
+
 @pytest.mark.parametrize("M,N,K", [(8, 256, 256), (1024, 128, 256), (4096, 128, 64), (37, 19, 53)])
 def test_simt_gemm_fp32(M, N, K):
     from us_video_medsam2_b200 import ops

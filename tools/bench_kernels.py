@@ -61,11 +61,26 @@ def gemms():
                       (131072, 96, 384), (32768, 768, 192), (8192, 1536, 384), (8192, 384, 1536), (8192, 1152, 384)]:
         a = rnd(M, K, dtype=torch.bfloat16)
         w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5)
-        for bn in (0, 32, 64, 128, 256):
-            if bn > max(32, N):
+        for bn in (0, 32, 64, 128, 256, -1, -128, -256):
+            if abs(bn) > max(32, N) or (bn < 0 and M < 2048):
                 continue
             us = timeit(lambda: ops.gemm_bf16(a, w, f32=True, block_n=bn), iters=10)
             print(f"gemm_tc5 M={M} N={N} K={K} bn={bn:3d}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
+    # the encoder's real epilogues: bias + exact GELU -> bf16 (mlp1), bias + fp32 residual -> fp32 (mlp2 / proj)
+    for (M, N, K) in [(131072, 384, 96), (32768, 768, 192), (8192, 1536, 384), (2048, 3072, 768)]:
+        a = rnd(M, K, dtype=torch.bfloat16)
+        w = rnd(N, K, dtype=torch.bfloat16, scale=K ** -0.5)
+        w2 = rnd(K, N, dtype=torch.bfloat16, scale=N ** -0.5)
+        b1, b2, x = rnd(N), rnd(K), rnd(M, K)
+        for bn in (128, 256, -1):
+            us = timeit(lambda: ops.gemm_bf16(a, w, bias=b1, act=2, bf16=True, block_n=bn), iters=10)
+            print(f"gemm_tc5 mlp1 gelu->bf16 M={M} N={N} K={K} bn={bn:3d}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
+        h = rnd(M, N, dtype=torch.bfloat16)
+        for bn in (128, 256, -1):
+            if abs(bn) > K and bn > 0:
+                continue
+            us = timeit(lambda: ops.gemm_bf16(h, w2, bias=b2, residual=x, out_f32=x, block_n=bn), iters=10)
+            print(f"gemm_tc5 mlp2 +res->f32 M={M} N={K} K={N} bn={bn:3d}: {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
     for (M, N, K) in [(1024, 384, 256), (1024, 256, 128), (1024, 256, 256), (4096, 128, 64)]:
         a, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
         us = timeit(lambda: ops.gemm_f32(a, w))

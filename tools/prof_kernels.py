@@ -29,6 +29,15 @@ if which in ("all", "fmha"):
     q, kv = rnd(B * T, D), rnd(B * Nk, 4 * D)
     for _ in range(4):
         ops.fmha(q, kv, kv, B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D),
-                 num_splits=9)
+                 num_splits=18)
+if which == "encoder":  # one batched image-encoder pass (8 frames), twice: read the second pass from the launch list
+    from us_video_medsam2_b200 import synth
+    from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
+    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=8)
+    pred.load_state_dict(synth.make_state_dict(19), strict=True)
+    eng = pred.engine()
+    imgs = ops.normalize_gray_u8(synth.make_clip_u8(8, seed=1).to(dev), synth.IMG_MEAN, synth.IMG_STD)
+    for _ in range(2):
+        eng.encode_frames(imgs)
 torch.cuda.synchronize()
 print("done")

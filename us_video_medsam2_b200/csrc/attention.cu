@@ -70,6 +70,7 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, int row_stride
 template <int D>
 __global__ void __launch_bounds__(FTHREADS)
 fmha_bf16_kernel(const usvm_fmha_params p) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t fsm[];
   using S = FmhaSmem<D>;
   bf16* sQ = reinterpret_cast<bf16*>(fsm);
@@ -240,6 +241,7 @@ fmha_bf16_kernel(const usvm_fmha_params p) {
 template <int D>
 __global__ void __launch_bounds__(256)
 fmha_combine_kernel(const usvm_fmha_params p) {
+  PDL_ENTRY();
   constexpr int C4 = D / 4;
   const long long total_rows = (long long)p.B * p.H * p.Nq;
   const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,10 +285,10 @@ int launch_fmha(const usvm_fmha_params* p, cudaStream_t s) {
     attr = true;
   }
   dim3 grid(cdiv(p->Nq, FM), p->B * p->H, p->num_splits);
-  fmha_bf16_kernel<D><<<grid, FTHREADS, FmhaSmem<D>::BYTES, s>>>(*p);
+  usvm_launch(fmha_bf16_kernel<D>, dim3(grid), dim3(FTHREADS), FmhaSmem<D>::BYTES, s, *p);
   if (p->num_splits > 1) {
     const long long rows = (long long)p->B * p->H * p->Nq;
-    fmha_combine_kernel<D><<<cdiv(rows * (D / 4), 256), 256, 0, s>>>(*p);
+    usvm_launch(fmha_combine_kernel<D>, dim3(cdiv(rows * (D / 4), 256)), dim3(256), 0, s, *p);
   }
   return usvm_check_launch();
 }
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(128)
 attn_small_f32_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                       float* __restrict__ out, int B, int H, int Nq, int Nk, int dh, int q_rs, int k_rs, int v_rs,
                       int o_rs, float scale) {
+  PDL_ENTRY();
   __shared__ float s_scores[4][SMALL_MAX_NK];
   __shared__ float s_q[4][32];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -365,8 +368,8 @@ extern "C" int usvm_fmha_combine(const usvm_fmha_params* p, void* stream) {
   const long long rows = (long long)p->B * p->H * p->Nq;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if ((p->o_rs % 4) || (p->o_hs % 4) || (p->o_bs % 4)) return USVM_ERR_ARG;
-  if (p->head_dim == 96) fmha_combine_kernel<96><<<cdiv(rows * 24, 256), 256, 0, s>>>(*p);
-  else if (p->head_dim == 256) fmha_combine_kernel<256><<<cdiv(rows * 64, 256), 256, 0, s>>>(*p);
+  if (p->head_dim == 96) usvm_launch(fmha_combine_kernel<96>, dim3(cdiv(rows * 24, 256)), dim3(256), 0, s, *p);
+  else if (p->head_dim == 256) usvm_launch(fmha_combine_kernel<256>, dim3(cdiv(rows * 64, 256)), dim3(256), 0, s, *p);
   else return USVM_ERR_ARG;
   return usvm_check_launch();
 }
@@ -377,7 +380,7 @@ extern "C" int usvm_attn_small_f32(const float* q, const float* k, const float* 
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || Nq <= 0 || Nk <= 0) return USVM_ERR_ARG;
   if (Nk > SMALL_MAX_NK || (head_dim != 16 && head_dim != 32)) return USVM_ERR_ARG;
   const long long total = (long long)B * H * Nq;
-  attn_small_f32_kernel<<<cdiv(total, 4), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  usvm_launch(attn_small_f32_kernel, dim3(cdiv(total, 4)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), 
       q, k, v, out, B, H, Nq, Nk, head_dim, q_rs, k_rs, v_rs, o_rs, scale);
   return usvm_check_launch();
 }

@@ -73,6 +73,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(1024)
 cc_smem_kernel(const uint8_t* __restrict__ img, const float* scores_in, float* scores_out, int32_t* __restrict__ labels,
                int32_t* __restrict__ counts, int H, int W, int max_area, float fill_value) {
+  PDL_ENTRY();
   extern __shared__ int s_mem[];
   const int HB = H >> 1, WB = W >> 1, NB = HB * WB, HW = H * W;
   int* s_par = s_mem;
@@ -128,6 +129,7 @@ cc_smem_kernel(const uint8_t* __restrict__ img, const float* scores_in, float* s
 // ---------------------------------------------------------------------------------------------
 template <typename FG>
 __global__ void cc_g_init(FG fg, int32_t* labels, int32_t* counts, int H, int W) {
+  PDL_ENTRY();
   const long long base = (long long)blockIdx.z * H * W;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
   if (2 * bx >= W || 2 * by >= H) return;
@@ -137,6 +139,7 @@ __global__ void cc_g_init(FG fg, int32_t* labels, int32_t* counts, int H, int W)
 }
 template <typename FG>
 __global__ void cc_g_merge(FG fg, int32_t* labels, int H, int W) {
+  PDL_ENTRY();
   const long long base = (long long)blockIdx.z * H * W;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
   if (2 * bx >= W || 2 * by >= H) return;
@@ -147,6 +150,7 @@ __global__ void cc_g_merge(FG fg, int32_t* labels, int H, int W) {
 }
 template <typename FG>
 __global__ void cc_g_compress(FG fg, int32_t* labels, int32_t* counts, int H, int W) {
+  PDL_ENTRY();
   const long long base = (long long)blockIdx.z * H * W;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
   if (2 * bx >= W || 2 * by >= H) return;
@@ -160,6 +164,7 @@ __global__ void cc_g_compress(FG fg, int32_t* labels, int32_t* counts, int H, in
 template <typename FG, bool FILL>
 __global__ void cc_g_final(FG fg, int32_t* labels, int32_t* counts, const float* scores_in, float* scores_out, int H,
                            int W, int max_area, float fill_value) {
+  PDL_ENTRY();
   const long long base = (long long)blockIdx.z * H * W;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
   if (2 * bx >= W || 2 * by >= H) return;
@@ -182,6 +187,7 @@ __global__ void cc_g_final(FG fg, int32_t* labels, int32_t* counts, const float*
 template <typename FG, bool FILL>
 __global__ void cc_g_roots(FG fg, int32_t* labels, int32_t* counts, const float* scores_in, float* scores_out, int H,
                            int W, int max_area, float fill_value) {
+  PDL_ENTRY();
   const long long base = (long long)blockIdx.z * H * W;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
   if (2 * bx >= W || 2 * by >= H) return;
@@ -214,6 +220,7 @@ constexpr int kNoLabel = 0x7fffffff;
 // label planes carry a one-pixel border of kNoLabel so the stencil needs no bounds checks.
 __global__ void __launch_bounds__(1024)
 fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W, int max_area, float fill_value) {
+  PDL_ENTRY();
   extern __shared__ int s_mem[];
   const int HW = H * W, Wp = W + 2, plane = (H + 2) * Wp;
   int* s_a = s_mem;             // labels, ping   [(H+2) x (W+2)]
@@ -310,7 +317,7 @@ int launch_smem(const uint8_t* img, const float* sin, float* sout, int32_t* labe
     configured = kSmemLimit;
   }
   const int threads = (H * W >= 1024 * 4) ? 1024 : 256;
-  cc_smem_kernel<FILL><<<N, threads, bytes, s>>>(img, sin, sout, labels, counts, H, W, max_area, fill);
+  usvm_launch(cc_smem_kernel<FILL>, dim3(N), dim3(threads), bytes, s, img, sin, sout, labels, counts, H, W, max_area, fill);
   return usvm_check_launch();
 }
 
@@ -319,11 +326,11 @@ int launch_global(FG fg, int32_t* labels, int32_t* counts, const float* sin, flo
                   int max_area, float fill, cudaStream_t s) {
   dim3 block(32, 8);
   dim3 grid(cdiv(W / 2, 32), cdiv(H / 2, 8), N);
-  cc_g_init<<<grid, block, 0, s>>>(fg, labels, counts, H, W);
-  cc_g_merge<<<grid, block, 0, s>>>(fg, labels, H, W);
-  cc_g_compress<<<grid, block, 0, s>>>(fg, labels, counts, H, W);
-  cc_g_final<FG, FILL><<<grid, block, 0, s>>>(fg, labels, counts, sin, sout, H, W, max_area, fill);
-  cc_g_roots<FG, FILL><<<grid, block, 0, s>>>(fg, labels, counts, sin, sout, H, W, max_area, fill);
+  usvm_launch(cc_g_init<FG>, dim3(grid), dim3(block), 0, s, fg, labels, counts, H, W);
+  usvm_launch(cc_g_merge<FG>, dim3(grid), dim3(block), 0, s, fg, labels, H, W);
+  usvm_launch(cc_g_compress<FG>, dim3(grid), dim3(block), 0, s, fg, labels, counts, H, W);
+  usvm_launch(cc_g_final<FG, FILL>, dim3(grid), dim3(block), 0, s, fg, labels, counts, sin, sout, H, W, max_area, fill);
+  usvm_launch(cc_g_roots<FG, FILL>, dim3(grid), dim3(block), 0, s, fg, labels, counts, sin, sout, H, W, max_area, fill);
   return usvm_check_launch();
 }
 
@@ -358,7 +365,7 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
         return USVM_ERR_CUDA;
       configured = true;
     }
-    fill_holes_local_kernel<<<N, 1024, local_bytes, s>>>(scores_in, scores_out, H, W, max_area, fill_value);
+    usvm_launch(fill_holes_local_kernel, dim3(N), dim3(1024), local_bytes, s, scores_in, scores_out, H, W, max_area, fill_value);
     return usvm_check_launch();
   }
   if (smem_bytes(H, W) <= kSmemLimit)

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #define USVM_OK 0
 #define USVM_ERR_ARG (-1)
@@ -20,6 +22,49 @@ static inline int usvm_check_launch() {
   return e == cudaSuccess ? USVM_OK : USVM_ERR_CUDA;
 }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Every kernel of the library is launched with programmatic stream serialization (PDL): the next kernel of the stream
+// (or of the captured graph) is scheduled while the current one is still running and parks in `griddepcontrol.wait`
+// until its predecessor has completed and flushed, so its launch latency and prologue leave the critical path of the
+// ~130-kernel tracked frame.  USVM2_PDL=0 turns the attribute off (plain stream order) for A/B timing.
+static inline bool usvm_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USVM2_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t usvm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = usvm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Device side of PDL.  Rules every kernel here follows (they make the chain transitively ordered and deadlock-free):
+//  * every thread executes pdl_wait() before it reads or writes global memory and before the kernel can finish, so
+//    "my predecessor completed" implies "all earlier kernels completed";
+//  * pdl_trigger() comes after pdl_wait(), so at most one successor is parked at a time;
+//  * kernels that allocate TMEM do it BEFORE pdl_wait() and trigger only afterwards: a parked successor can then
+//    never hold TMEM columns a not-yet-allocated CTA of the running kernel still needs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define PDL_ENTRY() \
+  do {              \
+    pdl_wait();     \
+    pdl_trigger();  \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // small math

@@ -21,6 +21,7 @@ conv2d_small_kernel(const float* __restrict__ x, const float* __restrict__ wt, c
                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int gelu,
                     float* out_f32, bf16* out_bf16, int B, int H, int W, int Cin, int Cout, int k, int s, int pad,
                     int Ho, int Wo) {
+  PDL_ENTRY();
   extern __shared__ float s_w[];
   const int K = k * k * Cin;
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) s_w[i] = wt[i];
@@ -85,6 +86,7 @@ conv2d_small_kernel(const float* __restrict__ x, const float* __restrict__ wt, c
 // A[pix, (ky*k + kx)*C + c] = x[b, oy*s - pad + ky, ox*s - pad + kx, c] (zero outside), bf16
 __global__ void im2col_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ A, int B, int H, int W, int C, int k,
                                    int s, int pad, int Ho, int Wo) {
+  PDL_ENTRY();
   const int K = k * k * C;
   const long long total = (long long)B * Ho * Wo * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(256)
 dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [49][C] */, const float* __restrict__ bias,
                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, bf16* __restrict__ out,
                   int B, int H, int W) {
+  PDL_ENTRY();
   constexpr int C = CPL * 32;
   const int lane = threadIdx.x & 31;
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -152,6 +155,7 @@ __device__ __forceinline__ float post_op(float v, int mode, float scale, float b
 // F.interpolate(mode="bilinear", align_corners=False); planes = N*C
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int Hi,
                                        int Wi, int Ho, int Wo, int mode, float pscale, float pbias) {
+  PDL_ENTRY();
   const float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
   const long long total = planes * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -181,6 +185,7 @@ __device__ __forceinline__ void aa_span(int o, float scale, int in_size, int& lo
 }
 __global__ void resize_bilinear_aa_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int Hi,
                                           int Wi, int Ho, int Wo, int binarize_half) {
+  PDL_ENTRY();
   const float sh = (float)Hi / Ho, sw = (float)Wi / Wo;
   const long long total = planes * Ho * Wo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -230,7 +235,7 @@ extern "C" int usvm_conv2d_small(const float* x, const float* w_kkio, const floa
   const long long pixels = (long long)B * Ho * Wo;
   const int ppw = Cout < 32 ? 32 / Cout : 1;
   const int grid = (int)max(1LL, min((long long)148 * 8, (pixels + 8LL * ppw - 1) / (8LL * ppw)));
-  conv2d_small_kernel<<<grid, 256, smem, STREAM>>>(x, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32,
+  usvm_launch(conv2d_small_kernel, dim3(grid), dim3(256), smem, STREAM, x, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32,
                                                    reinterpret_cast<bf16*>(out_bf16), B, H, W, Cin, Cout, k, stride,
                                                    pad, Ho, Wo);
   return usvm_check_launch();
@@ -240,7 +245,7 @@ extern "C" int usvm_im2col_nhwc(const float* x, void* A, int B, int H, int W, in
                                 void* stream) {
   if (!x || !A) return USVM_ERR_ARG;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  im2col_nhwc_kernel<<<grid_for((long long)B * Ho * Wo * k * k * C), 256, 0, STREAM>>>(
+  usvm_launch(im2col_nhwc_kernel, dim3(grid_for((long long)B * Ho * Wo * k * k * C)), dim3(256), 0, STREAM, 
       x, reinterpret_cast<bf16*>(A), B, H, W, C, k, stride, pad, Ho, Wo);
   return usvm_check_launch();
 }
@@ -249,7 +254,7 @@ extern "C" int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* 
                                const float* ln_b, float eps, void* out_bf16, int B, int H, int W, int C,
                                void* stream) {
   if (!x || !w_49c || !bias || !ln_w || !ln_b || !out_bf16 || C != 256) return USVM_ERR_ARG;
-  dwconv7_ln_kernel<8><<<cdiv((long long)B * H * W, 8), 256, 0, STREAM>>>(x, w_49c, bias, ln_w, ln_b, eps,
+  usvm_launch(dwconv7_ln_kernel<8>, dim3(cdiv((long long)B * H * W, 8)), dim3(256), 0, STREAM, x, w_49c, bias, ln_w, ln_b, eps,
                                                                            reinterpret_cast<bf16*>(out_bf16), B, H, W);
   return usvm_check_launch();
 }
@@ -257,7 +262,7 @@ extern "C" int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* 
 extern "C" int usvm_resize_bilinear(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo,
                                     int post_mode, float post_scale, float post_bias, void* stream) {
   if (!x || !y || planes <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return USVM_ERR_ARG;
-  resize_bilinear_kernel<<<grid_for(planes * Ho * Wo), 256, 0, STREAM>>>(x, y, planes, Hi, Wi, Ho, Wo, post_mode,
+  usvm_launch(resize_bilinear_kernel, dim3(grid_for(planes * Ho * Wo)), dim3(256), 0, STREAM, x, y, planes, Hi, Wi, Ho, Wo, post_mode,
                                                                          post_scale, post_bias);
   return usvm_check_launch();
 }
@@ -265,7 +270,7 @@ extern "C" int usvm_resize_bilinear(const float* x, float* y, long long planes, 
 extern "C" int usvm_resize_bilinear_aa(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo,
                                        int binarize_half, void* stream) {
   if (!x || !y || planes <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return USVM_ERR_ARG;
-  resize_bilinear_aa_kernel<<<grid_for(planes * Ho * Wo), 256, 0, STREAM>>>(x, y, planes, Hi, Wi, Ho, Wo,
+  usvm_launch(resize_bilinear_aa_kernel, dim3(grid_for(planes * Ho * Wo)), dim3(256), 0, STREAM, x, y, planes, Hi, Wi, Ho, Wo,
                                                                             binarize_half);
   return usvm_check_launch();
 }

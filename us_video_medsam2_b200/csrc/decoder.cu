@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256)
 upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, const float* __restrict__ ln_w,
                 const float* __restrict__ ln_b, float eps, float* __restrict__ out, int B, int Hc, int Wc,
                 int feat_shared) {
+  PDL_ENTRY();
   constexpr int CPL = C / 32;
   const int lane = threadIdx.x & 31;
   const int Ho = 2 * Hc, Wo = 2 * Wc;
@@ -58,6 +59,7 @@ upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, co
 __global__ void __launch_bounds__(256)
 upscale2_masks_kernel(const float* __restrict__ g2, const float* __restrict__ feat, const float* __restrict__ hyper,
                       int hyper_bs, float* __restrict__ masks, int B, int Hc, int Wc, int feat_shared) {
+  PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int Ho = 2 * Hc, Wo = 2 * Wc;
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -85,6 +87,7 @@ small_mlp3_kernel(const float* __restrict__ x, long long x_row_stride, long long
                   const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                   const float* __restrict__ b3, int out_dim, int sigmoid_out, float* __restrict__ y,
                   long long y_row_stride, long long y_inst_stride) {
+  PDL_ENTRY();
   __shared__ float h0[256], h1[256];
   const int row = blockIdx.x, inst = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,6 +129,7 @@ sam_select_kernel(const float* __restrict__ masks, const float* __restrict__ iou
                   const float* __restrict__ score, int score_stride, int multimask, float stab_delta, float stab_thresh,
                   float no_obj_score, float* __restrict__ low_res, int* __restrict__ token_index,
                   float* __restrict__ iou_out, int HW) {
+  PDL_ENTRY();
   __shared__ int s_cnt[2];
   __shared__ int s_pick;
   const int b = blockIdx.x;
@@ -176,6 +180,7 @@ sam_select_kernel(const float* __restrict__ masks, const float* __restrict__ iou
 // obj_ptr = lam * ptr + (1 - lam) * no_obj_ptr, lam = score > 0  (sam2_base.py:1146-1156)
 __global__ void objptr_mix_kernel(float* __restrict__ ptr, const float* __restrict__ score, int score_stride,
                                   const float* __restrict__ no_obj_ptr, int B, int C) {
+  PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
@@ -187,6 +192,7 @@ __global__ void objptr_mix_kernel(float* __restrict__ ptr, const float* __restri
 __global__ void point_embed_kernel(const float* __restrict__ coords, const int* __restrict__ labels,
                                    const float* __restrict__ gauss, const float* __restrict__ table, float inv_size,
                                    float* __restrict__ out, int n_points) {
+  PDL_ENTRY();
   const int p = blockIdx.x;
   if (p >= n_points) return;
   const int c = threadIdx.x;  // 256
@@ -212,14 +218,14 @@ extern "C" int usvm_upscale1_ln_gelu(const float* g1, const float* feat_s1, cons
                                      float eps, float* out, int B, int Hc, int Wc, int C, int feat_shared,
                                      void* stream) {
   if (!g1 || !feat_s1 || !ln_w || !ln_b || !out || C != 64) return USVM_ERR_ARG;
-  upscale1_kernel<64><<<cdiv((long long)B * 4 * Hc * Wc, 8), 256, 0, STREAM>>>(g1, feat_s1, ln_w, ln_b, eps, out, B, Hc, Wc, feat_shared);
+  usvm_launch(upscale1_kernel<64>, dim3(cdiv((long long)B * 4 * Hc * Wc, 8)), dim3(256), 0, STREAM, g1, feat_s1, ln_w, ln_b, eps, out, B, Hc, Wc, feat_shared);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, int hyper_bs,
                                    float* masks, int B, int Hc, int Wc, int feat_shared, void* stream) {
   if (!g2 || !feat_s0 || !hyper || !masks) return USVM_ERR_ARG;
-  upscale2_masks_kernel<<<cdiv((long long)B * 4 * Hc * Wc, 8), 256, 0, STREAM>>>(g2, feat_s0, hyper, hyper_bs, masks, B, Hc, Wc, feat_shared);
+  usvm_launch(upscale2_masks_kernel, dim3(cdiv((long long)B * 4 * Hc * Wc, 8)), dim3(256), 0, STREAM, g2, feat_s0, hyper, hyper_bs, masks, B, Hc, Wc, feat_shared);
   return usvm_check_launch();
 }
 
@@ -229,7 +235,7 @@ extern "C" int usvm_small_mlp3(const float* x, long long x_row_stride, long long
                                long long y_inst_stride, int rows, int instances, void* stream) {
   if (!x || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !y || rows <= 0 || instances <= 0 || out_dim <= 0)
     return USVM_ERR_ARG;
-  small_mlp3_kernel<<<dim3(rows, instances), 256, 0, STREAM>>>(x, x_row_stride, x_inst_stride, row_select, w1, b1, w2,
+  usvm_launch(small_mlp3_kernel, dim3(dim3(rows, instances)), dim3(256), 0, STREAM, x, x_row_stride, x_inst_stride, row_select, w1, b1, w2,
                                                                b2, w3, b3, out_dim, sigmoid_out, y, y_row_stride,
                                                                y_inst_stride);
   return usvm_check_launch();
@@ -240,7 +246,7 @@ extern "C" int usvm_sam_select(const float* masks, const float* iou, int iou_str
                                float stab_thresh, float no_obj_score, float* low_res, int* token_index, float* iou_out,
                                int B, int HW, void* stream) {
   if (!masks || !iou || !score || !low_res || !token_index || !iou_out || B <= 0) return USVM_ERR_ARG;
-  sam_select_kernel<<<B, 1024, 0, STREAM>>>(masks, iou, iou_stride, iou_is_logit, score, score_stride, multimask,
+  usvm_launch(sam_select_kernel, dim3(B), dim3(1024), 0, STREAM, masks, iou, iou_stride, iou_is_logit, score, score_stride, multimask,
                                             stab_delta, stab_thresh, no_obj_score, low_res, token_index, iou_out, HW);
   return usvm_check_launch();
 }
@@ -248,13 +254,13 @@ extern "C" int usvm_sam_select(const float* masks, const float* iou, int iou_str
 extern "C" int usvm_objptr_mix(float* ptr, const float* score, int score_stride, const float* no_obj_ptr, int B, int C,
                                void* stream) {
   if (!ptr || !score || !no_obj_ptr || B <= 0) return USVM_ERR_ARG;
-  objptr_mix_kernel<<<cdiv((long long)B * C, 256), 256, 0, STREAM>>>(ptr, score, score_stride, no_obj_ptr, B, C);
+  usvm_launch(objptr_mix_kernel, dim3(cdiv((long long)B * C, 256)), dim3(256), 0, STREAM, ptr, score, score_stride, no_obj_ptr, B, C);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_point_embed(const float* coords, const int* labels, const float* gauss, const float* table,
                                 float image_size, float* out, int n_points, void* stream) {
   if (!coords || !labels || !gauss || !table || !out || n_points <= 0) return USVM_ERR_ARG;
-  point_embed_kernel<<<n_points, 256, 0, STREAM>>>(coords, labels, gauss, table, 1.0f / image_size, out, n_points);
+  usvm_launch(point_embed_kernel, dim3(n_points), dim3(256), 0, STREAM, coords, labels, gauss, table, 1.0f / image_size, out, n_points);
   return usvm_check_launch();
 }

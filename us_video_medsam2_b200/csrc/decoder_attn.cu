@@ -22,6 +22,7 @@ constexpr int SK_WARPS = 8;
 template <int KSPLIT>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const usvm_skinny_params p) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) float xs[];  // [rows][K] (+ [8][32] partials when KSPLIT > 1)
   const int inst = blockIdx.y;
   const int m0 = blockIdx.z * SK_ROWS;
@@ -110,6 +111,7 @@ constexpr int T2I_LD = 17;  // padded row (16 channels + 1) -> conflict-free per
 __global__ void __launch_bounds__(256)
 attn_t2i_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__ k, const float* __restrict__ v,
                 int kv_rs, float* __restrict__ out, int o_rs, int H, int Nt, int Nk, float scale) {
+  PDL_ENTRY();
   extern __shared__ float sm[];
   float* s_k = sm;                         // [Nk][17]
   float* s_v = s_k + Nk * T2I_LD;          // [Nk][17]
@@ -188,6 +190,7 @@ attn_t2i_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__
 __global__ void __launch_bounds__(256)
 attn_i2t_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__ k, const float* __restrict__ v,
                 int kv_rs, float* __restrict__ out, int o_rs, int H, int Nq, int Nt, float scale) {
+  PDL_ENTRY();
   extern __shared__ float sm[];  // k [Nt][H*16], v [Nt][H*16]
   const int C = H * T2I_DH;
   float* s_k = sm;
@@ -262,10 +265,10 @@ extern "C" int usvm_gemm_skinny_f32(const usvm_skinny_params* p, void* stream) {
   }
   if (p->K >= 1024) {  // long reduction: the CTA's 8 warps split K, one CTA per 4 columns
     dim3 grid(cdiv(p->N, SK_COLS), p->instances, cdiv(p->M, SK_ROWS));
-    gemm_skinny_kernel<8><<<grid, 256, smem, STREAM>>>(*p);
+    usvm_launch(gemm_skinny_kernel<8>, dim3(grid), dim3(256), smem, STREAM, *p);
   } else {
     dim3 grid(cdiv(p->N, SK_WARPS * SK_COLS), p->instances, cdiv(p->M, SK_ROWS));
-    gemm_skinny_kernel<1><<<grid, 256, smem, STREAM>>>(*p);
+    usvm_launch(gemm_skinny_kernel<1>, dim3(grid), dim3(256), smem, STREAM, *p);
   }
   return usvm_check_launch();
 }
@@ -281,7 +284,7 @@ extern "C" int usvm_attn_t2i_f32(const float* q, int q_rs, const float* k, const
       return USVM_ERR_CUDA;
     configured = 200 * 1024;
   }
-  attn_t2i_kernel<<<B * H, 256, smem, STREAM>>>(q, q_rs, k, v, kv_rs, out, o_rs, H, Nt, Nk, scale);
+  usvm_launch(attn_t2i_kernel, dim3(B * H), dim3(256), smem, STREAM, q, q_rs, k, v, kv_rs, out, o_rs, H, Nt, Nk, scale);
   return usvm_check_launch();
 }
 
@@ -290,7 +293,7 @@ extern "C" int usvm_attn_i2t_f32(const float* q, int q_rs, const float* k, const
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || Nt <= 0 || Nt > T2I_MAX_NT || Nq <= 0 || (q_rs % 4) || (o_rs % 4))
     return USVM_ERR_ARG;
   const size_t smem = (size_t)2 * Nt * H * T2I_DH * sizeof(float);
-  attn_i2t_kernel<<<dim3(cdiv((long long)Nq * H, 256), B), 256, smem, STREAM>>>(q, q_rs, k, v, kv_rs, out, o_rs, H, Nq,
+  usvm_launch(attn_i2t_kernel, dim3(dim3(cdiv((long long)Nq * H, 256), B)), dim3(256), smem, STREAM, q, q_rs, k, v, kv_rs, out, o_rs, H, Nq,
                                                                                  Nt, scale);
   return usvm_check_launch();
 }

@@ -15,6 +15,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
                  float eps, int gelu, float* out_f32, int ldo_f32, bf16* out_bf16, int ldo_bf16, int rows, int C) {
+  PDL_ENTRY();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -41,6 +42,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
                      float eps, int gelu, float* out_f32, int ldo_f32, bf16* out_bf16, int ldo_bf16, int rows) {
+  PDL_ENTRY();
   constexpr int C = NV * 32;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -74,6 +76,7 @@ layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restri
 // out[r, c] = alpha * x[r % x_mod, c] + beta * y[r % y_mod, c]   (fp32 in; fp32 and/or bf16 out)
 __global__ void axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, float beta,
                                   int x_mod, int y_mod, float* out_f32, bf16* out_bf16, long long rows, int C) {
+  PDL_ENTRY();
   const long long total = rows * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C;
@@ -86,6 +89,7 @@ __global__ void axpby_rows_kernel(const float* __restrict__ x, const float* __re
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
 }
@@ -98,6 +102,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
 __global__ void rope_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ cs,
                             const float* __restrict__ sn, bf16* __restrict__ out, int ldo, long long rows,
                             int rows_per_batch, int n_rope, int table_rows, int half) {
+  PDL_ENTRY();
   const long long total = rows * half;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / half;
@@ -124,6 +129,7 @@ __global__ void rope_kernel(const float* __restrict__ x, int ldx, const float* _
 __global__ void window_gather_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
                                      bf16* __restrict__ Qw, bf16* __restrict__ Kw, bf16* __restrict__ Vw, int F,
                                      int Hg, int Wg, int ws, int pool, int C) {
+  PDL_ENTRY();
   const int nwx = (Wg + ws - 1) / ws, nwy = (Hg + ws - 1) / ws;
   const int nk = ws * ws;
   const int wq = pool ? ws / 2 : ws;
@@ -184,6 +190,7 @@ __global__ void window_gather_kernel(const bf16* __restrict__ qkv, const float* 
 // window_unpartition (backbones/utils.py:40-61): window-major [F*nW, wq*wq, C] -> raster [F, Ho, Wo, C]
 __global__ void window_scatter_kernel(const bf16* __restrict__ Ow, bf16* __restrict__ out, int F, int Ho, int Wo,
                                       int wq, int C) {
+  PDL_ENTRY();
   const int nwx = (Wo + wq - 1) / wq, nwy = (Ho + wq - 1) / wq;
   const int C8 = C / 8;
   const long long total = (long long)F * Ho * Wo * C8;
@@ -203,6 +210,7 @@ __global__ void window_scatter_kernel(const bf16* __restrict__ Ow, bf16* __restr
 
 // 2x2 / stride-2 max pool on NHWC fp32 (do_pool on the projected shortcut, hieradet.py:139-140)
 __global__ void maxpool2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int F, int H, int W, int C) {
+  PDL_ENTRY();
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const long long total = (long long)F * Ho * Wo * C4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -224,6 +232,7 @@ __global__ void maxpool2_nhwc_kernel(const float* __restrict__ x, float* __restr
 // FPN top-down: fine[f,y,x,:] += coarse[f,y/2,x/2,:]  (nearest x2, image_encoder.py:116-126)
 __global__ void upsample2_add_kernel(float* __restrict__ fine, const float* __restrict__ coarse, bf16* fine_bf16,
                                      int F, int H, int W, int C) {
+  PDL_ENTRY();
   const long long total = (long long)F * H * W * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -240,6 +249,7 @@ __global__ void upsample2_add_kernel(float* __restrict__ fine, const float* __re
 // img fp32 NCHW [F,3,S,S] -> A bf16 [F*(S/4)^2, KP], column k = c*49 + ky*7 + kx, zero beyond 147
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col_patch_kernel(const float* __restrict__ img, bf16* __restrict__ A, int F, int S, int KP) {
+  PDL_ENTRY();
   const int G = S / 4;
   const long long total = (long long)F * G * G * KP;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -259,6 +269,7 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, bf16* __restr
 // uint8 grayscale [F,S,S] -> normalised fp32 [F,3,S,S] ((g/255 - mean_c)/std_c, misc.py:253-276)
 __global__ void normalize_gray_kernel(const uint8_t* __restrict__ g, float* __restrict__ out, long long frames_px,
                                       long long px, float m0, float m1, float m2, float s0, float s1, float s2) {
+  PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < frames_px; i += (long long)gridDim.x * blockDim.x) {
     const long long f = i / px, o = i - f * px;
     const float v = (float)g[i] / 255.0f;
@@ -277,6 +288,7 @@ __global__ void build_memory_kernel(const usvm_memory_frames fr, const float* __
                                     const float* __restrict__ tpos, const float* __restrict__ ptrs,
                                     const float* __restrict__ ptr_pos, bf16* __restrict__ k_in, bf16* __restrict__ v_in,
                                     int B, int T, int Cm, int n_ptr_tokens, int Nk, int Nk_total, int row_offset) {
+  PDL_ENTRY();
   const int ptr_row0 = fr.count * T;
   const long long total = (long long)B * Nk * Cm;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -305,6 +317,7 @@ __global__ void build_memory_kernel(const usvm_memory_frames fr, const float* __
 __global__ void finalize_memory_kernel(const float* __restrict__ x, const float* __restrict__ score, int score_stride,
                                        const float* __restrict__ no_obj_embed, bf16* __restrict__ mem, int B, int T,
                                        int Cm, const usvm_frame_ctrl* __restrict__ ctrl) {
+  PDL_ENTRY();
   const long long total = (long long)B * T * Cm;
   if (!mem) mem = reinterpret_cast<bf16*>(ctrl->mem_store) + (long long)ctrl->cur_frame * ctrl->mem_slot_stride;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -326,6 +339,7 @@ __global__ void finalize_memory_kernel(const float* __restrict__ x, const float*
 __global__ void __launch_bounds__(64)
 ptr_tpos_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ W, const float* __restrict__ bias,
                 float* __restrict__ out) {
+  PDL_ENTRY();
   __shared__ float pe[256];
   const int p = blockIdx.x, c = threadIdx.x;
   const float rel = ctrl->ptr_rel[p];
@@ -347,6 +361,7 @@ __global__ void build_memory_store_kernel(const usvm_frame_ctrl* __restrict__ ct
                                           const float* __restrict__ tpos, const float* __restrict__ ptr_pos,
                                           bf16* __restrict__ k_in, bf16* __restrict__ v_in, int B, int T, int Cm,
                                           int n_mem, int n_ptr) {
+  PDL_ENTRY();
   const bf16* __restrict__ mem_store = reinterpret_cast<const bf16*>(ctrl->mem_store);
   const float* __restrict__ ptr_store = ctrl->ptr_store;
   const long long mem_frame_stride = ctrl->mem_slot_stride, ptr_frame_stride = ctrl->ptr_slot_stride;
@@ -374,6 +389,7 @@ __global__ void build_memory_store_kernel(const usvm_frame_ctrl* __restrict__ ct
 }
 
 __global__ void set_frame_ctrl_kernel(usvm_frame_ctrl* dst, const usvm_frame_ctrl v) {
+  PDL_ENTRY();
   if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
 }
 
@@ -381,6 +397,7 @@ __global__ void set_frame_ctrl_kernel(usvm_frame_ctrl* dst, const usvm_frame_ctr
 __global__ void store_outputs_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ obj_ptr,
                                      const float* __restrict__ score, int score_stride, const float* __restrict__ masks,
                                      int B, int ptr_dim, int hw) {
+  PDL_ENTRY();
   const long long slot = ctrl->cur_frame;
   const long long n0 = (long long)B * ptr_dim, n1 = B, n2 = (long long)B * hw;
   float* d0 = ctrl->ptr_store + slot * ctrl->ptr_slot_stride;
@@ -410,13 +427,13 @@ extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const flo
   bf16* ob = reinterpret_cast<bf16*>(out_bf16);
 #define LN_CASE(NV)                                                                                              \
   case NV * 32:                                                                                                  \
-    layernorm_reg_kernel<NV><<<cdiv(rows, 8), 256, 0, STREAM>>>(x, ldx, w, b, eps, gelu, out_f32, ldo_f32, ob,   \
+    usvm_launch(layernorm_reg_kernel<NV>, dim3(cdiv(rows, 8)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu, out_f32, ldo_f32, ob,   \
                                                                 ldo_bf16, rows);                                 \
     break;
   switch (C) {
     LN_CASE(2) LN_CASE(3) LN_CASE(6) LN_CASE(8) LN_CASE(12) LN_CASE(24)
     default:
-      layernorm_kernel<<<cdiv(rows, 8), 256, 0, STREAM>>>(x, ldx, w, b, eps, gelu, out_f32, ldo_f32, ob, ldo_bf16, rows, C);
+      usvm_launch(layernorm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu, out_f32, ldo_f32, ob, ldo_bf16, rows, C);
   }
 #undef LN_CASE
   return usvm_check_launch();
@@ -425,14 +442,14 @@ extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const flo
 extern "C" int usvm_axpby_rows(const float* x, const float* y, float alpha, float beta, int x_mod, int y_mod,
                                float* out_f32, void* out_bf16, long long rows, int C, void* stream) {
   if (!x || rows <= 0 || C <= 0) return USVM_ERR_ARG;
-  axpby_rows_kernel<<<grid_for(rows * C), 256, 0, STREAM>>>(x, y, alpha, beta, x_mod, y_mod, out_f32,
+  usvm_launch(axpby_rows_kernel, dim3(grid_for(rows * C)), dim3(256), 0, STREAM, x, y, alpha, beta, x_mod, y_mod, out_f32,
                                                             reinterpret_cast<bf16*>(out_bf16), rows, C);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
   if (!x || !y || n <= 0) return USVM_ERR_ARG;
-  cast_f32_bf16_kernel<<<grid_for(n), 256, 0, STREAM>>>(x, reinterpret_cast<bf16*>(y), n);
+  usvm_launch(cast_f32_bf16_kernel, dim3(grid_for(n)), dim3(256), 0, STREAM, x, reinterpret_cast<bf16*>(y), n);
   return usvm_check_launch();
 }
 
@@ -440,7 +457,7 @@ extern "C" int usvm_rope_bf16(const float* x, int ldx, const float* cos_t, const
                               long long rows, int rows_per_batch, int n_rope, int table_rows, int dim,
                               void* stream) {
   if (!x || !cos_t || !sin_t || !out || rows <= 0 || (dim & 1) || (ldx & 1) || (ldo & 1)) return USVM_ERR_ARG;
-  rope_kernel<<<grid_for(rows * (dim / 2)), 256, 0, STREAM>>>(x, ldx, cos_t, sin_t, reinterpret_cast<bf16*>(out), ldo,
+  usvm_launch(rope_kernel, dim3(grid_for(rows * (dim / 2))), dim3(256), 0, STREAM, x, ldx, cos_t, sin_t, reinterpret_cast<bf16*>(out), ldo,
                                                                rows, rows_per_batch, n_rope, table_rows, dim / 2);
   return usvm_check_launch();
 }
@@ -451,7 +468,7 @@ extern "C" int usvm_window_gather(const void* qkv, const float* qkv_bias, void* 
   const int nw = cdiv(Hg, ws) * cdiv(Wg, ws);
   const int nq = pool ? (ws / 2) * (ws / 2) : ws * ws;
   const long long total = (long long)F * nw * (nq + 2 * ws * ws) * (C / 8);
-  window_gather_kernel<<<grid_for(total), 256, 0, STREAM>>>(
+  usvm_launch(window_gather_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, 
       reinterpret_cast<const bf16*>(qkv), qkv_bias, reinterpret_cast<bf16*>(Qw), reinterpret_cast<bf16*>(Kw),
       reinterpret_cast<bf16*>(Vw), F, Hg, Wg, ws, pool, C);
   return usvm_check_launch();
@@ -459,28 +476,28 @@ extern "C" int usvm_window_gather(const void* qkv, const float* qkv_bias, void* 
 
 extern "C" int usvm_window_scatter(const void* Ow, void* out, int F, int Ho, int Wo, int wq, int C, void* stream) {
   if (!Ow || !out || wq <= 0 || (C % 8)) return USVM_ERR_ARG;
-  window_scatter_kernel<<<grid_for((long long)F * Ho * Wo * (C / 8)), 256, 0, STREAM>>>(
+  usvm_launch(window_scatter_kernel, dim3(grid_for((long long)F * Ho * Wo * (C / 8))), dim3(256), 0, STREAM, 
       reinterpret_cast<const bf16*>(Ow), reinterpret_cast<bf16*>(out), F, Ho, Wo, wq, C);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_maxpool2_nhwc(const float* x, float* y, int F, int H, int W, int C, void* stream) {
   if (!x || !y || (H & 1) || (W & 1) || (C % 4)) return USVM_ERR_ARG;
-  maxpool2_nhwc_kernel<<<grid_for((long long)F * (H / 2) * (W / 2) * (C / 4)), 256, 0, STREAM>>>(x, y, F, H, W, C);
+  usvm_launch(maxpool2_nhwc_kernel, dim3(grid_for((long long)F * (H / 2) * (W / 2) * (C / 4))), dim3(256), 0, STREAM, x, y, F, H, W, C);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_upsample2_add(float* fine, const float* coarse, void* fine_bf16, int F, int H, int W, int C,
                                   void* stream) {
   if (!fine || !coarse || (H & 1) || (W & 1)) return USVM_ERR_ARG;
-  upsample2_add_kernel<<<grid_for((long long)F * H * W * C), 256, 0, STREAM>>>(
+  usvm_launch(upsample2_add_kernel, dim3(grid_for((long long)F * H * W * C)), dim3(256), 0, STREAM, 
       fine, coarse, reinterpret_cast<bf16*>(fine_bf16), F, H, W, C);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_im2col_patch(const float* img, void* A, int F, int S, int KP, void* stream) {
   if (!img || !A || (S % 4) || KP < 147) return USVM_ERR_ARG;
-  im2col_patch_kernel<<<grid_for((long long)F * (S / 4) * (S / 4) * KP), 256, 0, STREAM>>>(
+  usvm_launch(im2col_patch_kernel, dim3(grid_for((long long)F * (S / 4) * (S / 4) * KP)), dim3(256), 0, STREAM, 
       img, reinterpret_cast<bf16*>(A), F, S, KP);
   return usvm_check_launch();
 }
@@ -489,7 +506,7 @@ extern "C" int usvm_normalize_gray_u8(const uint8_t* gray, float* out, int F, in
                                       const float* std3, void* stream) {
   if (!gray || !out || !mean3 || !std3 || F <= 0) return USVM_ERR_ARG;
   const long long px = (long long)H * W;
-  normalize_gray_kernel<<<grid_for(F * px), 256, 0, STREAM>>>(gray, out, F * px, px, mean3[0], mean3[1], mean3[2],
+  usvm_launch(normalize_gray_kernel, dim3(grid_for(F * px)), dim3(256), 0, STREAM, gray, out, F * px, px, mean3[0], mean3[1], mean3[2],
                                                               std3[0], std3[1], std3[2]);
   return usvm_check_launch();
 }
@@ -502,7 +519,7 @@ extern "C" int usvm_build_memory(const usvm_memory_frames* frames, const float* 
   if (n_ptr_tokens > 0 && (!ptrs || !ptr_pos)) return USVM_ERR_ARG;
   const int Nk = frames->count * T + n_ptr_tokens;
   if (Nk <= 0 || row_offset < 0 || row_offset + Nk > Nk_total) return USVM_ERR_ARG;
-  build_memory_kernel<<<grid_for((long long)B * Nk * Cm), 256, 0, STREAM>>>(
+  usvm_launch(build_memory_kernel, dim3(grid_for((long long)B * Nk * Cm)), dim3(256), 0, STREAM, 
       *frames, pos, tpos, ptrs, ptr_pos, reinterpret_cast<bf16*>(k_in), reinterpret_cast<bf16*>(v_in), B, T, Cm,
       n_ptr_tokens, Nk, Nk_total, row_offset);
   return usvm_check_launch();
@@ -512,7 +529,7 @@ extern "C" int usvm_finalize_memory(const float* x, const float* score, int scor
                                     void* mem_bf16, int B, int T, int Cm, const usvm_frame_ctrl* ctrl_dev,
                                     void* stream) {
   if (!x || !score || !no_obj_embed || (!mem_bf16 && !ctrl_dev) || B <= 0) return USVM_ERR_ARG;
-  finalize_memory_kernel<<<grid_for((long long)B * T * Cm), 256, 0, STREAM>>>(
+  usvm_launch(finalize_memory_kernel, dim3(grid_for((long long)B * T * Cm)), dim3(256), 0, STREAM, 
       x, score, score_stride, no_obj_embed, reinterpret_cast<bf16*>(mem_bf16), B, T, Cm, ctrl_dev);
   return usvm_check_launch();
 }
@@ -520,7 +537,7 @@ extern "C" int usvm_finalize_memory(const float* x, const float* score, int scor
 extern "C" int usvm_ptr_tpos(const usvm_frame_ctrl* ctrl_dev, const float* W, const float* bias, float* out, int n_ptr,
                              void* stream) {
   if (!ctrl_dev || !W || !bias || !out || n_ptr <= 0 || n_ptr > USVM_MAX_PTRS) return USVM_ERR_ARG;
-  ptr_tpos_kernel<<<n_ptr, 64, 0, STREAM>>>(ctrl_dev, W, bias, out);
+  usvm_launch(ptr_tpos_kernel, dim3(n_ptr), dim3(64), 0, STREAM, ctrl_dev, W, bias, out);
   return usvm_check_launch();
 }
 
@@ -533,7 +550,7 @@ extern "C" int usvm_build_memory_store(const usvm_frame_ctrl* ctrl_dev, const fl
   if (n_ptr > 0 && !ptr_pos) return USVM_ERR_ARG;
   const long long total = (long long)B * (n_mem * T + n_ptr * 4) * Cm;
   if (total <= 0) return USVM_ERR_ARG;
-  build_memory_store_kernel<<<grid_for(total), 256, 0, STREAM>>>(
+  usvm_launch(build_memory_store_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, 
       ctrl_dev, pos, tpos, ptr_pos, reinterpret_cast<bf16*>(k_in), reinterpret_cast<bf16*>(v_in), B, T, Cm, n_mem, n_ptr);
   return usvm_check_launch();
 }
@@ -541,13 +558,13 @@ extern "C" int usvm_build_memory_store(const usvm_frame_ctrl* ctrl_dev, const fl
 extern "C" int usvm_store_outputs(const usvm_frame_ctrl* ctrl_dev, const float* obj_ptr, const float* score,
                                   int score_stride, const float* masks, int B, int ptr_dim, int hw, void* stream) {
   if (!ctrl_dev || !obj_ptr || !score || !masks || B <= 0) return USVM_ERR_ARG;
-  store_outputs_kernel<<<grid_for((long long)B * (ptr_dim + 1 + hw)), 256, 0, STREAM>>>(ctrl_dev, obj_ptr, score,
+  usvm_launch(store_outputs_kernel, dim3(grid_for((long long)B * (ptr_dim + 1 + hw))), dim3(256), 0, STREAM, ctrl_dev, obj_ptr, score,
                                                                                        score_stride, masks, B, ptr_dim, hw);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_set_frame_ctrl(usvm_frame_ctrl* ctrl_dev, const usvm_frame_ctrl* ctrl_host, void* stream) {
   if (!ctrl_dev || !ctrl_host) return USVM_ERR_ARG;
-  set_frame_ctrl_kernel<<<1, 32, 0, STREAM>>>(ctrl_dev, *ctrl_host);  // by-value kernel parameter: no H2D copy, no sync
+  usvm_launch(set_frame_ctrl_kernel, dim3(1), dim3(32), 0, STREAM, ctrl_dev, *ctrl_host);  // by-value kernel parameter: no H2D copy, no sync
   return usvm_check_launch();
 }

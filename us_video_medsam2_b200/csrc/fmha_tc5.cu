@@ -113,6 +113,8 @@ fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc5_fence_before();
   __syncthreads();
   tc5_fence_after();
+  pdl_wait();  // barriers, descriptors and TMEM were set up under the previous kernel's tail
+  pdl_trigger();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_O = tmem + 128;
 
@@ -378,6 +380,8 @@ fmha_tc5_ts_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   tc5_fence_before();
   __syncthreads();
   tc5_fence_after();
+  pdl_wait();  // barriers, descriptors and TMEM were set up under the previous kernel's tail
+  pdl_trigger();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_Q = tmem, tmem_S = tmem + 128, tmem_O = tmem + 256;
 
@@ -635,8 +639,8 @@ extern "C" int usvm_fmha_tc5(const usvm_fmha_params* p, void* stream) {
   }
   dim3 grid(p->Nq / QM, p->B, p->num_splits);
   if (fmha_tc5_variant == 0)
-    fmha_tc5_ts_kernel<<<grid, THREADS, TS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tk, tv, *p);
+    usvm_launch(fmha_tc5_ts_kernel, dim3(grid), dim3(THREADS), TS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tk, tv, *p);
   else
-    fmha_tc5_kernel<<<grid, THREADS, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tk, tv, *p);
+    usvm_launch(fmha_tc5_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, *p);
   return usvm_check_launch();
 }

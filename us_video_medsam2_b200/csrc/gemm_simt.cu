@@ -24,6 +24,7 @@ template <typename TA, typename TW>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, int ldw, const usvm_gemm_epilogue ep,
                  int M, int N, int K) {
+  PDL_ENTRY();
   __shared__ float As[TK][TM + 4];
   __shared__ float Ws[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -80,6 +81,7 @@ gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, in
 __global__ void __launch_bounds__(256)
 gemm_simt_f32_pipelined_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                const usvm_gemm_epilogue ep, int M, int N, int K) {
+  PDL_ENTRY();
   __shared__ __align__(16) float As[2][TK][TM + 4];
   __shared__ __align__(16) float Ws[2][TK][TN + 4];
   const int tid = threadIdx.x;
@@ -147,7 +149,7 @@ template <typename TA, typename TW>
 int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
            cudaStream_t s) {
   dim3 grid(cdiv(M, TM), cdiv(N, TN));
-  gemm_simt_kernel<TA, TW><<<grid, 256, 0, s>>>(static_cast<const TA*>(A), lda, static_cast<const TW*>(W), ldw, *ep,
+  usvm_launch(gemm_simt_kernel<TA, TW>, dim3(grid), dim3(256), 0, s, static_cast<const TA*>(A), lda, static_cast<const TW*>(W), ldw, *ep,
                                                 M, N, K);
   return usvm_check_launch();
 }
@@ -165,7 +167,7 @@ extern "C" int usvm_gemm_simt(const void* A, int a_is_bf16, int lda, const void*
                         !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(W) & 15);
     if (vec_ok) {
       dim3 grid(cdiv(M, TM), cdiv(N, TN));
-      gemm_simt_f32_pipelined_kernel<<<grid, 256, 0, s>>>(static_cast<const float*>(A), lda,
+      usvm_launch(gemm_simt_f32_pipelined_kernel, dim3(grid), dim3(256), 0, s, static_cast<const float*>(A), lda,
                                                            static_cast<const float*>(W), ldw, *ep, M, N, K);
       return usvm_check_launch();
     }

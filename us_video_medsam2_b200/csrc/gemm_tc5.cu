@@ -56,6 +56,72 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Fused epilogue of one 32-column block of one accumulator row: bias -> RoPE -> activation -> per-column scale ->
+// residual (skipped when the caller adds a prefetched residual itself).
+__device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_epilogue& ep, const int row,
+                                               const bool row_ok, const long long rrow, const int col0, const int N,
+                                               const bool add_residual) {
+  const int ncol = min(32, N - col0);
+  if (ncol == 32) {
+    if (ep.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (ep.rope_cos && col0 < ep.rope_cols) {
+      const int rb = row % ep.rope_rows_per_batch;
+      if (rb < ep.rope_n_rope) {
+        const long long t0 = (long long)(rb % ep.rope_table_rows) * 128 + ((col0 & 255) >> 1);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 c4 = *reinterpret_cast<const float4*>(ep.rope_cos + t0 + (j >> 1));
+          const float4 s4 = *reinterpret_cast<const float4*>(ep.rope_sin + t0 + (j >> 1));
+          const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = v[j + 2 * q], b = v[j + 2 * q + 1];
+            v[j + 2 * q] = a * cs[q] - b * sn[q];
+            v[j + 2 * q + 1] = a * sn[q] + b * cs[q];
+          }
+        }
+      }
+    }
+    if (ep.act != USVM_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+    }
+    if (ep.col_scale) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(ep.col_scale + col0 + j);
+        v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
+      }
+    }
+    if (add_residual && ep.residual && row_ok) {
+      const float* r = ep.residual + rrow * ep.ldr + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(r + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+  } else {  // ragged last column block: columns >= N are clipped by the TMA store, never read
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncol) {
+        float x = v[j];
+        if (ep.bias) x += ep.bias[col0 + j];
+        x = apply_act(x, ep.act);
+        if (ep.col_scale) x *= ep.col_scale[col0 + j];
+        if (add_residual && ep.residual && row_ok) x += ep.residual[rrow * ep.ldr + col0 + j];
+        v[j] = x;
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -92,6 +158,9 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc5_fence_before();
   __syncthreads();
   tc5_fence_after();
+  // everything above (barriers, descriptor prefetch, TMEM) overlapped the previous kernel's tail
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -153,65 +222,7 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      const int ncol = min(32, N - col0);
-      if (ncol == 32) {
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (ep.rope_cos && col0 < ep.rope_cols) {
-          const int rb = row % ep.rope_rows_per_batch;
-          if (rb < ep.rope_n_rope) {
-            const long long t0 = (long long)(rb % ep.rope_table_rows) * 128 + ((col0 & 255) >> 1);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const float4 c4 = *reinterpret_cast<const float4*>(ep.rope_cos + t0 + (j >> 1));
-              const float4 s4 = *reinterpret_cast<const float4*>(ep.rope_sin + t0 + (j >> 1));
-              const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float a = v[j + 2 * q], b = v[j + 2 * q + 1];
-                v[j + 2 * q] = a * cs[q] - b * sn[q];
-                v[j + 2 * q + 1] = a * sn[q] + b * cs[q];
-              }
-            }
-          }
-        }
-        if (ep.act != USVM_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-        }
-        if (ep.col_scale) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(ep.col_scale + col0 + j);
-            v[j] *= b.x; v[j + 1] *= b.y; v[j + 2] *= b.z; v[j + 3] *= b.w;
-          }
-        }
-        if (ep.residual && row_ok) {
-          const float* r = ep.residual + rrow * ep.ldr + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(r + j);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-      } else {  // ragged last column block: columns >= N are clipped by the TMA store, never read
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < ncol) {
-            float x = v[j];
-            if (ep.bias) x += ep.bias[col0 + j];
-            x = apply_act(x, ep.act);
-            if (ep.col_scale) x *= ep.col_scale[col0 + j];
-            if (ep.residual && row_ok) x += ep.residual[rrow * ep.ldr + col0 + j];
-            v[j] = x;
-          }
-        }
-      }
+      epilogue_block(v, ep, row, row_ok, rrow, col0, N, true);
       if (pending) {  // the previous block's TMA store must have finished reading the staging buffers
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
@@ -250,6 +261,203 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc5_fence_before();
   __syncthreads();
   if (warp == 1) tc5_dealloc(tmem_base, tmem_cols(BN));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant for the throughput-bound GEMMs (the batched Hiera encoder, the memory-bank K/V projections):
+// one CTA per SM walks output tiles of 128 x BN (BN a runtime multiple of 32, <= 256, chosen to divide N), the
+// accumulator is double-buffered in TMEM (columns [0,256) and [256,512)), and eight epilogue warps drain tile i while
+// the TMA / MMA warps are already running tile i+1 -- with K of only 96..1536 the epilogue (bias, exact-erf GELU,
+// residual, bf16 pack, TMA store) costs as much as the mainloop, so overlapping the two is what doubles the rate.
+//   warp 0    : TMA producer, one continuous smem ring across tiles
+//   warp 1    : MMA issuer; waits acc_empty[buf], issues K/16 tcgen05.mma, commits acc_full[buf]
+//   warps 2-9 : epilogue; warp w owns TMEM lanes 32*(w%4).. and every second 32-column block of the tile
+// Tiles are ordered n-fastest so the CTAs that run concurrently share the same A rows in L2.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int P_THREADS = 320;
+constexpr int P_EPI_WARPS = 8;
+constexpr int P_STG_BYTES = P_EPI_WARPS * (STG_F32 + STG_BF16);
+constexpr int P_A_BYTES = BM * BK * 2;
+
+__host__ __device__ constexpr int p_stage_bytes(int bn) { return P_A_BYTES + bn * BK * 2; }
+__host__ __device__ constexpr int p_smem_total(int bn, int stages) {
+  return stages * p_stage_bytes(bn) + P_STG_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+}
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
+                                const usvm_gemm_epilogue ep, const int M, const int N, const int K, const int BN,
+                                const int stages, const int tiles_n, const int num_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = p_stage_bytes(BN);
+  uint8_t* staging = smem + stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + P_STG_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (ep.out_f32) tma_prefetch_desc(&tmO32);
+    if (ep.out_bf16) tma_prefetch_desc(&tmO16);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], P_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tc5_alloc(tmem_slot, 512);
+  tc5_fence_before();
+  __syncthreads();
+  tc5_fence_after();
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)stages;
+          const uint32_t ph = (it / (uint32_t)stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* a_dst = smem + s * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tile_m * BM);
+          tma_load_2d(a_dst + P_A_BYTES, &tmB, &full_bar[s], kb * BK, tile_n * BN);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u;
+        mbar_wait(&acc_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+        tc5_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 256u;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % (uint32_t)stages;
+          const uint32_t ph = (it / (uint32_t)stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc5_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_k_sw128(a_addr + P_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc5_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          tc5_commit(&empty_bar[s]);
+        }
+        tc5_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int ew = warp - 2;        // 0..7
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+    const int half = ew >> 2;       // which 32-column blocks of the tile: half, half+2, ...
+    uint8_t* stg32 = staging + ew * STG_F32;
+    uint8_t* stg16 = staging + P_EPI_WARPS * STG_F32 + ew * STG_BF16;
+    bool pending = false;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+      const uint32_t buf = lt & 1u;
+      mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
+      tc5_fence_after();
+      const int row0 = tile_m * BM + lane_grp * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < M;
+      const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+      if (row0 < M) {
+#pragma unroll 1
+        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+          const int col0 = tile_n * BN + c0;
+          if (col0 >= N) break;  // warp-uniform
+          uint32_t acc[32];
+          tc5_ld_32x32(tmem_base + buf * 256u + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
+          // the residual row segment is fetched while the TMEM load is in flight
+          const bool full_blk = (N - col0) >= 32;
+          const bool pre = full_blk && ep.residual != nullptr && row_ok;
+          float4 rs[8];
+          if (pre) {
+            const float4* r = reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rs[j] = __ldg(r + j);
+          }
+          tc5_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+          epilogue_block(v, ep, row, row_ok, rrow, col0, N, !full_blk);
+          if (pre) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w;
+            }
+          }
+          if (pending) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+          if (ep.out_f32) {
+            uint8_t* prow = stg32 + lane * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(prow + ((c ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+          if (ep.out_bf16) {
+            uint8_t* prow = stg16 + lane * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 pk;
+              pk.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+              pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+              pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+              pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+              *reinterpret_cast<uint4*>(prow + (c << 4)) = pk;
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (ep.out_f32) tma_store_2d(&tmO32, stg32, col0, row0);
+            if (ep.out_bf16) tma_store_2d(&tmO16, stg16, col0, row0);
+            tma_store_commit();
+          }
+          pending = true;
+        }
+      }
+      // all of this warp's TMEM reads of `buf` are complete (wait::ld above): hand the accumulator back
+      tc5_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    if (pending && lane == 0) tma_store_wait_read();
+    __syncwarp();
+  }
+  tc5_fence_before();
+  __syncthreads();
+  if (warp == 1) tc5_dealloc(tmem_base, 512);
 }
 
 // ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
@@ -325,8 +533,61 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
   int max_stages = ctas <= 2 * 148 ? STAGES : 4;
   while (max_stages > 1 && SmemLayout<BN>::total(max_stages) > 200 * 1024) --max_stages;
   const int stages = num_kb < max_stages ? num_kb : max_stages;
-  gemm_bf16_tc5_kernel<BN><<<grid, GEMM_THREADS, SmemLayout<BN>::total(stages), stream>>>(tmA, tmB, tmO32, tmO16, *ep, M,
+  usvm_launch(gemm_bf16_tc5_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), SmemLayout<BN>::total(stages), stream, tmA, tmB, tmO32, tmO16, *ep, M,
                                                                                          N, K, stages);
+  return usvm_check_launch();
+}
+
+int persistent_block_n(int N) {
+  // the widest multiple of 32 (<= 256) that wastes the fewest padded columns
+  int best = 32, best_waste = 1 << 30;
+  for (int bn = 32; bn <= 256; bn += 32) {
+    const int waste = cdiv(N, bn) * bn - N;
+    if (waste < best_waste || (waste == best_waste && bn > best)) {
+      best = bn;
+      best_waste = waste;
+    }
+  }
+  return best;
+}
+
+int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
+                      int bn, cudaStream_t stream) {
+  if (bn <= 0 || bn > 256 || (bn % 32)) return USVM_ERR_ARG;
+  CUtensorMap tmA, tmB, tmO32, tmO16;
+  int rc = make_map_bf16(&tmA, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map_bf16(&tmB, W, N, K, ldw, bn);
+  if (rc) return rc;
+  tmO32 = tmA;
+  tmO16 = tmA;
+  if (ep->out_f32) {
+    rc = make_map(&tmO32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ep->out_f32, M, N, ep->ldo_f32, 32, 32,
+                  CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  if (ep->out_bf16) {
+    rc = make_map(&tmO16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ep->out_bf16, M, N, ep->ldo_bf16, 32, 32,
+                  CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+      return USVM_ERR_CUDA;
+    if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess)
+      return USVM_ERR_CUDA;
+  }
+  int stages = STAGES;
+  while (stages > 1 && p_smem_total(bn, stages) > 227 * 1024) --stages;
+  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn);
+  const int num_tiles = tiles_m * tiles_n;
+  const int grid = num_tiles < sm_count ? num_tiles : sm_count;
+  usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, stages), stream, tmA, tmB,
+              tmO32, tmO16, *ep, M, N, K, bn, stages, tiles_n, num_tiles);
   return usvm_check_launch();
 }
 
@@ -346,6 +607,9 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
     return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = block_n;
+  if (bn < 0) return launch_persistent(A, lda, W, ldw, ep, M, N, K, bn == -1 ? persistent_block_n(N) : -bn, s);
+  if (bn == 0 && (long long)cdiv(M, BM) * cdiv(N, 128) >= 2 * 148)  // throughput-bound: more than one wave of tiles
+    return launch_persistent(A, lda, W, ldw, ep, M, N, K, persistent_block_n(N), s);
   if (bn <= 0) {
     // latency-bound shapes dominate this path: prefer enough CTAs to cover the 148 SMs, then wider tiles
     const int mt = cdiv(M, BM);

@@ -289,6 +289,7 @@ class Engine:
         self.w = weights
         self.cfg = weights.cfg
         self.attn_splits = 8  # flash-decoding splits of the memory attention key range (fills the 148 SMs at B=1)
+        self._tail_stream = None
 
     # ---------------------------------------------------------------- image encoder
     def encode_frames(self, imgs):
@@ -397,12 +398,21 @@ class Engine:
         k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
         pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B)
         o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, self.no_point_tokens(B), multimask=True)
+        # The user-facing tail (single-CTA hole filling, store write, video-resolution resize) is independent of the
+        # memory encoder: it runs on a forked stream -- a parallel branch of the captured graph -- and joins at the end.
+        main = torch.cuda.current_stream()
+        if self._tail_stream is None:
+            self._tail_stream = torch.cuda.Stream()
+        tail = self._tail_stream
+        tail.wait_stream(main)
+        with torch.cuda.stream(tail):
+            pm = ops.fill_holes(o["low"], fill_hole_area) if fill_hole_area > 0 else o["low"]
+            ops.store_outputs(ctrl, o["obj_ptr"], o["score"], pm)
+            vh, vw = video_hw
+            video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
         mask_in = self.mem_mask_input(o["low"], False)
         self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl)
-        pm = ops.fill_holes(o["low"], fill_hole_area) if fill_hole_area > 0 else o["low"]
-        ops.store_outputs(ctrl, o["obj_ptr"], o["score"], pm)
-        vh, vw = video_hw
-        video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
+        main.wait_stream(tail)
         return video, pm
 
     # ---------------------------------------------------------------- SAM heads
