@@ -75,6 +75,12 @@ typedef struct usvm_gemm_epilogue {
  * Auto picks the persistent kernel when the problem has more than two waves of 128 x 128 tiles. */
 int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep_host, int M, int N,
                        int K, int block_n, void* stream);
+/* Same kernel on fp32 operands as tf32 (10-bit mantissa products, fp32 accumulate): image-side projections of the SAM
+ * mask decoder's two-way transformer (sam/transformer.py:257-286) and its upscaling convolutions, where bf16 operands
+ * are too coarse.  A fp32 [M,K] pitch lda, W fp32 [N,K] pitch ldw (pitches % 4 == 0, 16-byte aligned); no fused RoPE.
+ * block_n: 0 = auto, 32 / 64 / 128. */
+int usvm_gemm_tf32_tc5(const float* A, int lda, const float* W, int ldw, const usvm_gemm_epilogue* ep_host, int M, int N,
+                       int K, int block_n, void* stream);
 /* fp32-accumulate SIMT GEMM, operands fp32 or bf16 (flags), any shape: fp32 decoder tail + checker. */
 int usvm_gemm_simt(const void* A, int a_is_bf16, int lda, const void* W, int w_is_bf16, int ldw,
                    const usvm_gemm_epilogue* ep_host, int M, int N, int K, void* stream);

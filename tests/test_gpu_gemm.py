@@ -137,3 +137,25 @@ def test_simt_and_tc5_agree_on_bf16_operands():
     x, _ = ops.gemm_bf16(a, w, f32=True, simt=False)
     y, _ = ops.gemm_bf16(a, w, f32=True, simt=True)
     assert (x - y).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 384, 256), (1024, 256, 128), (4096, 128, 64), (1000, 100, 72), (130, 40, 36)])
+@pytest.mark.parametrize("block_n", [0, 32, 128])
+def test_tc5_tf32_gemm(M, N, K, block_n):
+    """fp32 operands on the tf32 tensor-core path: within tf32 rounding (10-bit mantissa products) of the fp32 result,
+    and exact when the operands are representable in tf32."""
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn((M, K), generator=g, device="cuda")
+    w = torch.randn((N, K), generator=g, device="cuda") / K ** 0.5
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = torch.randn((M, N), generator=g, device="cuda")
+    got = ops.gemm_f32(a, w, bias, act=1, residual=res, tf32=True, block_n=block_n)
+    want = F.relu(a @ w.t() + bias) + res
+    assert (got - want).abs().max().item() < 8e-3
+    # operands that are exact in tf32 (bf16-representable): the only error left is fp32 accumulation order
+    a16, w16 = a.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
+    got = ops.gemm_f32(a16, w16, bias, residual=res, tf32=True, block_n=block_n)
+    want = a16 @ w16.t() + bias + res
+    assert (got - want).abs().max().item() < 2e-5 * K ** 0.5

@@ -91,10 +91,12 @@ def test_sam_heads_fp32(setup):
         s1 = rf["feat_s1"][0].flatten(1).t().contiguous().cuda()
         got = eng.sam_heads(pix.flatten(2).permute(0, 2, 1).reshape(B * 1024, 256).contiguous().cuda(), s0, s1, B,
                             eng.no_point_tokens(B), multimask=True)
-    assert (got["low"].cpu() - want["low"]).abs().max().item() < 2e-4
-    assert (got["obj_ptr"].cpu() - want["obj_ptr"]).abs().max().item() < 2e-4
-    assert (got["score"].cpu() - want["score"]).abs().max().item() < 2e-4
-    assert (torch.sigmoid(got["iou_logits"]).cpu()[:, 1:] - want["ious"]).abs().max().item() < 2e-4
+    # token side: exact fp32 products; image-side projections / upscaling GEMMs: tf32 products (10-bit mantissa), so the
+    # tolerance is tf32 rounding through two transformer layers (outputs here are O(0.1 .. 1))
+    assert (got["low"].cpu() - want["low"]).abs().max().item() < 2e-3
+    assert (got["obj_ptr"].cpu() - want["obj_ptr"]).abs().max().item() < 2e-3
+    assert (got["score"].cpu() - want["score"]).abs().max().item() < 2e-3
+    assert (torch.sigmoid(got["iou_logits"]).cpu()[:, 1:] - want["ious"]).abs().max().item() < 1e-3
     # point prompt + dense mask prompt path, single-mask output with stability fallback
     pts = dict(point_coords=torch.tensor([[[256.0, 250.0], [100.0, 400.0]]]).expand(B, -1, -1),
                point_labels=torch.tensor([[1, 0]], dtype=torch.int32).expand(B, -1))
@@ -106,8 +108,8 @@ def test_sam_heads_fp32(setup):
         dense = eng.embed_mask_prompt(prev.cuda(), B)
         got = eng.sam_heads(pix.flatten(2).permute(0, 2, 1).reshape(B * 1024, 256).contiguous().cuda(), s0, s1, B,
                             sparse, dense=dense, multimask=False)
-    assert (got["low"].cpu() - want["low"]).abs().max().item() < 3e-4
-    assert (got["obj_ptr"].cpu() - want["obj_ptr"]).abs().max().item() < 3e-4
+    assert (got["low"].cpu() - want["low"]).abs().max().item() < 3e-3
+    assert (got["obj_ptr"].cpu() - want["obj_ptr"]).abs().max().item() < 3e-3
 
 
 def test_mask_as_output_and_memory_encoder(setup):

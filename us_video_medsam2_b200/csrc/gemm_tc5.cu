@@ -122,7 +122,9 @@ __device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_e
   }
 }
 
-template <int BN>
+// TF32 = true: the same kernel on fp32 operands (tf32 tensor-core math, fp32 accumulate) -- a k-block is then 32
+// floats (still one 128-byte swizzle row) and each tcgen05.mma covers K = 8.
+template <int BN, bool TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
@@ -140,7 +142,8 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x;
   const int tile_n = blockIdx.y;
-  const int num_kb = (K + BK - 1) / BK;
+  constexpr int BKE = TF32 ? BK / 2 : BK;  // elements per k-block (128 bytes)
+  const int num_kb = (K + BKE - 1) / BKE;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -172,14 +175,14 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* a_dst = smem + s * L::STAGE_BYTES;
         uint8_t* b_dst = a_dst + L::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tile_m * BM);
-        tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BK, tile_n * BN);
+        tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BKE, tile_m * BM);
+        tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BKE, tile_n * BN);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_bf16(BM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % stages;
         const uint32_t ph = (kb / stages) & 1;
@@ -191,9 +194,13 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint64_t b_desc = umma_desc_k_sw128(b_addr);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          tc5_mma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+          // advance 16 bf16 (8 tf32) = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          if (TF32)
+            tc5_mma_tf32(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          else
+            tc5_mma_f16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
         }
         tc5_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
       }
@@ -202,8 +209,6 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncwarp();
   } else {
     // ---- epilogue: thread <-> accumulator row; warp <-> 32-row slab written by TMA ----
-    mbar_wait(tmem_full_bar, 0);
-    tc5_fence_after();
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, 32*lane_grp + 32) are visible to this warp
     const int row0 = tile_m * BM + lane_grp * 32;
     const int row = row0 + lane;
@@ -212,17 +217,42 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* stg32 = staging + lane_grp * STG_F32;
     uint8_t* stg16 = staging + 4 * STG_F32 + lane_grp * STG_BF16;
     bool pending = false;  // this warp has a TMA store in flight that still reads its staging buffers
+    // The residual segment of a column block does not depend on the accumulator: it is fetched while the mainloop
+    // (first block) or the TMEM load (later blocks) is still in flight, which takes an L2 round trip off the tail.
+    float4 rs[8];
+    auto fetch_residual = [&](int c0, float4 (&dst)[8]) -> bool {
+      const int col0 = tile_n * BN + c0;
+      if (!(ep.residual != nullptr && row_ok && c0 < BN && col0 + 32 <= N)) return false;
+      const float4* r = reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = __ldg(r + j);
+      return true;
+    };
+    bool have = fetch_residual(0, rs);
+    mbar_wait(tmem_full_bar, 0);
+    tc5_fence_after();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int col0 = tile_n * BN + c0;
       if (col0 >= N || row0 >= M) break;  // warp-uniform
       uint32_t acc[32];
       tc5_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
+      float4 rn[8];
+      const bool have_next = fetch_residual(c0 + 32, rn);
       tc5_wait_ld();
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-      epilogue_block(v, ep, row, row_ok, rrow, col0, N, true);
+      epilogue_block(v, ep, row, row_ok, rrow, col0, N, !have);
+      if (have) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j] += rs[j].x; v[4 * j + 1] += rs[j].y; v[4 * j + 2] += rs[j].z; v[4 * j + 3] += rs[j].w;
+        }
+      }
+      have = have_next;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rs[j] = rn[j];
       if (pending) {  // the previous block's TMA store must have finished reading the staging buffers
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
@@ -496,13 +526,15 @@ int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long 
                   CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN>
+template <int BN, bool TF32>
 int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
            cudaStream_t stream) {
   CUtensorMap tmA, tmB, tmO32, tmO16;
-  int rc = make_map_bf16(&tmA, A, M, K, lda, BM);
+  int rc = TF32 ? make_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_map_bf16(&tmB, W, N, K, ldw, BN);
+  rc = TF32 ? make_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, W, N, K, ldw, BK / 2, BN, CU_TENSOR_MAP_SWIZZLE_128B)
+            : make_map_bf16(&tmB, W, N, K, ldw, BN);
   if (rc) return rc;
   tmO32 = tmA;  // placeholders keep the kernel parameters valid when an output is absent
   tmO16 = tmA;
@@ -519,12 +551,12 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
   static bool attr_set = false;
   if (!attr_set) {
     const int want = SmemLayout<BN>::total(STAGES) < 227 * 1024 ? SmemLayout<BN>::total(STAGES) : 227 * 1024;
-    if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) !=
+    if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) !=
         cudaSuccess)
       return USVM_ERR_CUDA;
     attr_set = true;
   }
-  const int num_kb = cdiv(K, BK);
+  const int num_kb = cdiv(K, TF32 ? BK / 2 : BK);
   dim3 grid(cdiv(M, BM), cdiv(N, BN));
   // Ring depth: a problem with fewer CTAs than ~2 per SM is latency bound -> as deep as shared memory allows (the
   // k-loop then streams at TMA issue rate instead of TMA latency); big problems keep <= 4 stages so that 2-3 CTAs
@@ -533,7 +565,7 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
   int max_stages = ctas <= 2 * 148 ? STAGES : 4;
   while (max_stages > 1 && SmemLayout<BN>::total(max_stages) > 200 * 1024) --max_stages;
   const int stages = num_kb < max_stages ? num_kb : max_stages;
-  usvm_launch(gemm_bf16_tc5_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), SmemLayout<BN>::total(stages), stream, tmA, tmB, tmO32, tmO16, *ep, M,
+  usvm_launch(gemm_bf16_tc5_kernel<BN, TF32>, dim3(grid), dim3(GEMM_THREADS), SmemLayout<BN>::total(stages), stream, tmA, tmB, tmO32, tmO16, *ep, M,
                                                                                          N, K, stages);
   return usvm_check_launch();
 }
@@ -620,10 +652,36 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
     else if (N <= 128 && bn > 128) bn = 128;
   }
   switch (bn) {
-    case 32: return launch<32>(A, lda, W, ldw, ep, M, N, K, s);
-    case 64: return launch<64>(A, lda, W, ldw, ep, M, N, K, s);
-    case 128: return launch<128>(A, lda, W, ldw, ep, M, N, K, s);
-    case 256: return launch<256>(A, lda, W, ldw, ep, M, N, K, s);
+    case 32: return launch<32, false>(A, lda, W, ldw, ep, M, N, K, s);
+    case 64: return launch<64, false>(A, lda, W, ldw, ep, M, N, K, s);
+    case 128: return launch<128, false>(A, lda, W, ldw, ep, M, N, K, s);
+    case 256: return launch<256, false>(A, lda, W, ldw, ep, M, N, K, s);
+    default: return USVM_ERR_ARG;
+  }
+}
+
+extern "C" int usvm_gemm_tf32_tc5(const float* A, int lda, const float* W, int ldw, const usvm_gemm_epilogue* ep,
+                                  int M, int N, int K, int block_n, void* stream) {
+  if (!A || !W || !ep || M <= 0 || N <= 0 || K <= 0) return USVM_ERR_ARG;
+  if ((lda % 4) || (ldw % 4) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+    return USVM_ERR_ARG;
+  if (ep->out_f32 && ((ep->ldo_f32 % 4) || (reinterpret_cast<uintptr_t>(ep->out_f32) & 15))) return USVM_ERR_ARG;
+  if (ep->out_bf16 && ((ep->ldo_bf16 % 8) || (reinterpret_cast<uintptr_t>(ep->out_bf16) & 15))) return USVM_ERR_ARG;
+  if (ep->residual && ((ep->ldr % 4) || (reinterpret_cast<uintptr_t>(ep->residual) & 15))) return USVM_ERR_ARG;
+  if (ep->rope_cos) return USVM_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int bn = block_n;
+  if (bn <= 0) {
+    const int mt = cdiv(M, BM);
+    bn = 128;
+    while (bn > 32 && (long long)mt * cdiv(N, bn) < 148) bn >>= 1;
+    if (N <= 32) bn = 32;
+    else if (N <= 64 && bn > 64) bn = 64;
+  }
+  switch (bn) {
+    case 32: return launch<32, true>(A, lda, W, ldw, ep, M, N, K, s);
+    case 64: return launch<64, true>(A, lda, W, ldw, ep, M, N, K, s);
+    case 128: return launch<128, true>(A, lda, W, ldw, ep, M, N, K, s);
     default: return USVM_ERR_ARG;
   }
 }

@@ -447,7 +447,7 @@ class Engine:
                 queries = sk(o, *sa["o"], residual=queries)
             queries = ln(queries, Lyr["norms"][0])
             q = sk(queries, *t2i["q"], x2=tokens)
-            img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T)  # [B*T, 384]
+            img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T, tf32=True)  # [B*T, 384]
             o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
             queries = ln(sk(o, *t2i["o"], residual=queries), Lyr["norms"][1])
             m = sk(queries, *Lyr["mlp"][0], act=ACT_RELU)
@@ -455,16 +455,16 @@ class Engine:
             k2 = sk(queries, *i2t["k"], x2=tokens)
             v2 = sk(queries, *i2t["v"])
             o = ops.attn_i2t(img[:, 256:384], k2, v2, B, T, Nt)
-            keys = ln(ops.gemm_f32(o, *i2t["o"], residual=keys), Lyr["norms"][3])
+            keys = ln(ops.gemm_f32(o, *i2t["o"], residual=keys, tf32=True), Lyr["norms"][3])
         fin = w.dec_final
         q = sk(queries, *fin["q"], x2=tokens)
-        img = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T)  # [B*T, 256]
+        img = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T, tf32=True)  # [B*T, 256]
         o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
         hs = ln(sk(o, *fin["o"], residual=queries), w.dec_final_norm)  # [B*Nt, 256]
 
-        g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b)
+        g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=True)
         u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_shared)
-        g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b)
+        g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=True)
         # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
         W1, b1, W2, b2, W3, b3 = w.heads6
         h1 = sk(None, W1, b1, M=B, x_ptr=hs.data_ptr(), x_rs=Nt * 256, x_is=256, act=ACT_RELU, instances=6)

@@ -85,13 +85,19 @@ def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_
     return o32, o16
 
 
-def gemm_f32(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, out=None):
-    """fp32 SIMT GEMM (decoder tail): epi(a[M,K] @ w[N,K]^T) -> fp32 [M,N]."""
+def gemm_f32(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, out=None, tf32=False,
+             block_n=0):
+    """fp32-operand GEMM (decoder tail): epi(a[M,K] @ w[N,K]^T) -> fp32 [M,N].  tf32=True runs the tcgen05 kernel with
+    tf32 products (image-side projections, >= 128 rows); otherwise the SIMT kernel with exact fp32 products."""
     _chk(a, F32, "a"), _chk(w, F32, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
     ep, o32, _ = _epilogue(M, N, bias, act, col_scale, residual, res_mod, True, False, a, out, None)
+    if tf32 and not _FORCE_SIMT:
+        call("usvm_gemm_tf32_tc5", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), C.byref(ep), M, N, K, block_n,
+             _stream())
+        return o32
     call("usvm_gemm_simt", a.data_ptr(), 0, a.stride(0), w.data_ptr(), 0, w.stride(0), C.byref(ep), M, N, K,
          _stream())
     return o32
