@@ -261,6 +261,51 @@ int usvm_objptr_mix(float* ptr, const float* score, int score_stride, const floa
 int usvm_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float image_size,
                      float* out, int n_points, void* stream);
 
+/* ---- token-side chains of the mask decoder (csrc/token_chain.cu) ------------------------------------------------
+ * One thread-block cluster per object runs up to USVM_CHAIN_MAX_STEPS dependent steps on that object's <= 8 rows
+ * (decoder tokens, or stacked head instances); steps are separated by cluster barriers instead of kernel launches.
+ * Replaces, per tracked frame, the per-layer launches of TwoWayAttentionBlock's token side (sam/transformer.py:137-212),
+ * the hyper-network / IoU / object-score heads (mask_decoder.py:215-253) and obj_ptr_proj (sam2_base.py:1143-1156).
+ * All strides in elements; *_os = stride between objects. */
+#define USVM_CHAIN_MAX_STEPS 10
+#define USVM_CHAIN_ROWS 8
+#define USVM_CHAIN_LINEAR 0      /* out[m,n] = act((T(x)[m] (+ x2[m] if n < x2_cols)) . w[n] + bias[n]) (+ residual[m,n]) */
+#define USVM_CHAIN_T2I_PARTIAL 1 /* token->image attention partials of this CTA's key range -> params.scratch */
+#define USVM_CHAIN_IN_ROWS 0      /* T = identity, or LayerNorm over K when ln_w != NULL (also stored to ln_out) */
+#define USVM_CHAIN_IN_SELF_ATTN 1 /* T = 8-head self-attention of the rows; q | k | v at columns attn_q/k/v of x (K = 256) */
+#define USVM_CHAIN_IN_T2I_MERGE 2 /* T = softmax merge of the preceding T2I_PARTIAL step (K = 128) */
+typedef struct usvm_chain_step {
+  const float* x;
+  long long x_os, x_rs;
+  const int* row_select; /* optional int32 [n_obj]: x += row_select[obj] * sel_stride (token chosen on the device) */
+  long long sel_stride;
+  const float* ln_w;
+  const float* ln_b;
+  float* ln_out;
+  long long ln_os, ln_rs;
+  const float* x2;
+  long long x2_os, x2_rs;
+  const float* w; /* [N,K] row-major, 16-byte aligned; w_is != 0: row m uses matrix m (stride w_is), bias stride b_is */
+  long long w_is;
+  const float* bias;
+  long long b_is;
+  const float* residual;
+  long long r_os, r_rs;
+  float* out;
+  long long o_os, o_rs;
+  const float* k; /* T2I_PARTIAL: keys / values [Nk, 8 heads x 16] with row pitch kv_rs; queries = x [rows, 128] */
+  const float* v;
+  long long kv_os, kv_rs;
+  int kind, in_kind, rows, N, K, act, x2_cols, Nk, attn_q, attn_k, attn_v;
+  float ln_eps;
+} usvm_chain_step;
+typedef struct usvm_chain_params {
+  float* scratch; /* n_obj * cluster * 8 * 144 floats (T2I partials); may be NULL when no step needs it */
+  int n_steps, n_obj, cluster /* CTAs per object: 8 or 16 */, reserved;
+  usvm_chain_step steps[USVM_CHAIN_MAX_STEPS];
+} usvm_chain_params;
+int usvm_token_chain(const usvm_chain_params* p_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,29 @@ class SkinnyParams(C.Structure):
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("instances", C.c_int), ("act", C.c_int)]
 
 
+CHAIN_MAX_STEPS = 10
+
+
+class ChainStep(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_os", C.c_longlong), ("x_rs", C.c_longlong),
+                ("row_select", C.c_void_p), ("sel_stride", C.c_longlong),
+                ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("ln_out", C.c_void_p), ("ln_os", C.c_longlong),
+                ("ln_rs", C.c_longlong),
+                ("x2", C.c_void_p), ("x2_os", C.c_longlong), ("x2_rs", C.c_longlong),
+                ("w", C.c_void_p), ("w_is", C.c_longlong), ("bias", C.c_void_p), ("b_is", C.c_longlong),
+                ("residual", C.c_void_p), ("r_os", C.c_longlong), ("r_rs", C.c_longlong),
+                ("out", C.c_void_p), ("o_os", C.c_longlong), ("o_rs", C.c_longlong),
+                ("k", C.c_void_p), ("v", C.c_void_p), ("kv_os", C.c_longlong), ("kv_rs", C.c_longlong),
+                ("kind", C.c_int), ("in_kind", C.c_int), ("rows", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("act", C.c_int), ("x2_cols", C.c_int), ("Nk", C.c_int), ("attn_q", C.c_int), ("attn_k", C.c_int),
+                ("attn_v", C.c_int), ("ln_eps", C.c_float)]
+
+
+class ChainParams(C.Structure):
+    _fields_ = [("scratch", C.c_void_p), ("n_steps", C.c_int), ("n_obj", C.c_int), ("cluster", C.c_int),
+                ("reserved", C.c_int), ("steps", ChainStep * CHAIN_MAX_STEPS)]
+
+
 class FrameCtrl(C.Structure):
     _fields_ = [("mem_store", C.c_void_p), ("ptr_store", C.c_void_p), ("score_store", C.c_void_p),
                 ("mask_store", C.c_void_p), ("mem_slot_stride", C.c_longlong), ("ptr_slot_stride", C.c_longlong),
@@ -102,6 +125,7 @@ _SIGNATURES = {
     "usvm_store_outputs": [_P, _P, _P, _I, _P, _I, _I, _I, _P],
     "usvm_small_mlp3": [_P, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _LL, _LL, _I, _I, _P],
     "usvm_gemm_skinny_f32": [C.POINTER(SkinnyParams), _P],
+    "usvm_token_chain": [C.POINTER(ChainParams), _P],
     "usvm_attn_t2i_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "usvm_attn_i2t_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "usvm_sam_select": [_P, _P, _I, _I, _P, _I, _I, _F, _F, _F, _P, _P, _P, _I, _I, _P],

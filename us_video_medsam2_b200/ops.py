@@ -445,6 +445,72 @@ def gemm_skinny(x, w, bias=None, M=None, x_rs=None, x_is=0, x2=None, x2_rs=None,
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# token-side chains of the mask decoder (one cluster kernel per dependency chain)
+# ------------------------------------------------------------------------------------------------
+def chain_linear(x, w, bias, out, rows=8, x_os=None, x_rs=None, x_off=0, ln=None, ln_eps=1e-5, ln_out=None, ln_os=None,
+                 x2=None,
+                 x2_cols=None, act=ACT_NONE, residual=None, stacked=False, o_os=None, o_rs=None, row_select=None,
+                 sel_stride=0, in_kind=0, attn_cols=(0, 0, 0)):
+    """One LINEAR step of a token chain (see include/usvm2_b200.h: usvm_chain_step).  x / x2 / residual / out / ln_out
+    are [n_obj * rows, width]-shaped fp32 tensors unless explicit strides are given; `stacked`: w is [rows, N, K] and
+    row m uses matrix m; in_kind 1 = self-attention over q|k|v columns `attn_cols` of x, 2 = merge of T2I partials."""
+    st = _lib.ChainStep()
+    N, K = w.shape[-2], w.shape[-1]
+    st.kind, st.in_kind, st.rows, st.N, st.K, st.act = 0, in_kind, rows, N, K, act
+    st.x = x.data_ptr() + 4 * x_off
+    st.x_rs = x_rs if x_rs is not None else x.stride(0)
+    st.x_os = x_os if x_os is not None else rows * st.x_rs
+    if row_select is not None:
+        st.row_select, st.sel_stride = row_select.data_ptr(), sel_stride
+    if ln is not None:
+        st.ln_w, st.ln_b, st.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln_eps
+        if ln_out is not None:
+            st.ln_out, st.ln_rs = ln_out.data_ptr(), ln_out.stride(0)
+            st.ln_os = ln_os if ln_os is not None else rows * ln_out.stride(0)
+    if x2 is not None:
+        st.x2, st.x2_rs, st.x2_os = x2.data_ptr(), x2.stride(0), rows * x2.stride(0)
+        st.x2_cols = N if x2_cols is None else x2_cols
+    st.w, st.w_is = w.data_ptr(), (N * K if stacked else 0)
+    st.bias, st.b_is = _ptr(bias), (N if stacked else 0)
+    if residual is not None:
+        st.residual, st.r_rs, st.r_os = residual.data_ptr(), residual.stride(0), rows * residual.stride(0)
+    st.out = out.data_ptr()
+    st.o_rs = o_rs if o_rs is not None else out.stride(0)
+    st.o_os = o_os if o_os is not None else rows * st.o_rs
+    st.attn_q, st.attn_k, st.attn_v = attn_cols
+    return st
+
+
+def chain_t2i(q, k, v, rows=8, Nk=1024, q_off=0):
+    """T2I_PARTIAL step: q [n_obj*rows, >=128] (8 heads x 16, starting at column q_off); k, v column views [n_obj*Nk, 128]
+    of one image-side buffer."""
+    st = _lib.ChainStep()
+    st.kind, st.rows, st.Nk = 1, rows, Nk
+    st.x, st.x_rs, st.x_os = q.data_ptr() + 4 * q_off, q.stride(0), rows * q.stride(0)
+    assert k.stride(0) == v.stride(0)
+    st.k, st.v, st.kv_rs, st.kv_os = k.data_ptr(), v.data_ptr(), k.stride(0), Nk * k.stride(0)
+    return st
+
+
+_CHAIN_CLUSTER = int(os.environ.get("USVM2_CHAIN_CLUSTER", "8"))
+
+
+def token_chain(steps, n_obj, like, cluster=None):
+    """Runs the steps back to back in one cluster kernel (usvm_token_chain)."""
+    cl = cluster or _CHAIN_CLUSTER
+    p = _lib.ChainParams()
+    p.n_steps, p.n_obj, p.cluster = len(steps), n_obj, cl
+    scratch = None
+    if any(st.kind == 1 for st in steps):
+        scratch = empty((n_obj * cl * 8 * 144,), F32, like)
+        p.scratch = scratch.data_ptr()
+    for i, st in enumerate(steps):
+        p.steps[i] = st
+    call("usvm_token_chain", C.byref(p), _stream())
+    return scratch
+
+
 def attn_t2i(q, k, v, B, Nt, Nk, H=8):
     """token->image attention, head_dim 16: q [B*Nt, H*16]; k, v column views of an image-side buffer."""
     out = empty((B * Nt, H * 16), F32, q)
