@@ -301,7 +301,11 @@ typedef struct usvm_chain_step {
 } usvm_chain_step;
 typedef struct usvm_chain_params {
   float* scratch; /* n_obj * cluster * 8 * 144 floats (T2I partials); may be NULL when no step needs it */
-  int n_steps, n_obj, cluster /* CTAs per object: 8 or 16 */, reserved;
+  unsigned long long* timing; /* optional profiling aid: [n_steps][8] SM-clock stamps (cycles) of object 0 / CTA 0:
+                                 step start, input ready, step done, cluster barrier passed, first weight chunk
+                                 landed, first row block's products done, its k-slices met, unused; NULL = off */
+  int n_steps, n_obj, cluster /* CTAs per object: 8 or 16 */;
+  int precise; /* 1: products as 3 x tf32 on (hi, lo) splits (fp32-level accuracy); 0: one round-to-nearest tf32 product */
   usvm_chain_step steps[USVM_CHAIN_MAX_STEPS];
 } usvm_chain_params;
 int usvm_token_chain(const usvm_chain_params* p_host, void* stream);

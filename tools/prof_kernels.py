@@ -39,5 +39,22 @@ if which == "encoder":  # one batched image-encoder pass (8 frames), twice: read
     imgs = ops.normalize_gray_u8(synth.make_clip_u8(8, seed=1).to(dev), synth.IMG_MEAN, synth.IMG_STD)
     for _ in range(2):
         eng.encode_frames(imgs)
+if which == "decoder":  # SAM heads of a tracked frame (8 tokens), three times: read the last pass from the launch list
+    from us_video_medsam2_b200 import synth
+    from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
+    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=8)
+    pred.load_state_dict(synth.make_state_dict(19), strict=True)
+    eng = pred.engine()
+    pix = rnd(1024, 256, dt=torch.float32, sc=0.5)
+    s0, s1 = rnd(16384, 32, dt=torch.float32), rnd(4096, 64, dt=torch.float32)
+    for _ in range(3):
+        eng.sam_heads(pix, s0, s1, 1, eng.no_point_tokens(1), multimask=True)
+if which == "chain":  # nine identical small LINEAR steps in one cluster launch (per-step latency study)
+    x = rnd(8, 256, dt=torch.float32)
+    w, b = rnd(128, 256, dt=torch.float32, sc=1 / 16), rnd(128, dt=torch.float32)
+    bufs = [rnd(8, 256, dt=torch.float32) for _ in range(2)]
+    steps = [ops.chain_linear(bufs[i & 1], w, b, bufs[(i + 1) & 1][:, :128], o_rs=256) for i in range(9)]
+    for _ in range(4):
+        ops.token_chain(steps, 1, x, cluster=8)
 torch.cuda.synchronize()
 print("done")

@@ -66,8 +66,8 @@ class ChainStep(C.Structure):
 
 
 class ChainParams(C.Structure):
-    _fields_ = [("scratch", C.c_void_p), ("n_steps", C.c_int), ("n_obj", C.c_int), ("cluster", C.c_int),
-                ("reserved", C.c_int), ("steps", ChainStep * CHAIN_MAX_STEPS)]
+    _fields_ = [("scratch", C.c_void_p), ("timing", C.c_void_p), ("n_steps", C.c_int), ("n_obj", C.c_int), ("cluster", C.c_int),
+                ("precise", C.c_int), ("steps", ChainStep * CHAIN_MAX_STEPS)]
 
 
 class FrameCtrl(C.Structure):

@@ -299,7 +299,7 @@ class Engine:
         self.cfg = weights.cfg
         self.attn_splits = 8  # flash-decoding splits of the memory attention key range (fills the 148 SMs at B=1)
         self._tail_stream = None
-        self.use_token_chain = os.environ.get("USVM2_TOKEN_CHAIN", "1") != "0"
+        self.use_token_chain = os.environ.get("USVM2_TOKEN_CHAIN", "0") == "1"
 
     # ---------------------------------------------------------------- image encoder
     def encode_frames(self, imgs):

@@ -493,14 +493,18 @@ def chain_t2i(q, k, v, rows=8, Nk=1024, q_off=0):
     return st
 
 
-_CHAIN_CLUSTER = int(os.environ.get("USVM2_CHAIN_CLUSTER", "8"))
+_CHAIN_CLUSTER = int(os.environ.get("USVM2_CHAIN_CLUSTER", "16"))
+_CHAIN_PRECISE = os.environ.get("USVM2_CHAIN_PRECISE", "0") == "1"
 
 
-def token_chain(steps, n_obj, like, cluster=None):
-    """Runs the steps back to back in one cluster kernel (usvm_token_chain)."""
+def token_chain(steps, n_obj, like, cluster=None, timing=None, precise=None):
+    """Runs the steps back to back in one cluster kernel (usvm_token_chain).  timing: optional int64 [n_steps, 8] device
+    tensor that receives %globaltimer stamps of CTA 0 (profiling aid)."""
     cl = cluster or _CHAIN_CLUSTER
     p = _lib.ChainParams()
     p.n_steps, p.n_obj, p.cluster = len(steps), n_obj, cl
+    p.precise = int(_CHAIN_PRECISE if precise is None else precise)
+    p.timing = _ptr(timing)
     scratch = None
     if any(st.kind == 1 for st in steps):
         scratch = empty((n_obj * cl * 8 * 144,), F32, like)
