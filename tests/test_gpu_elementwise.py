@@ -193,6 +193,12 @@ def test_im2col_nhwc_and_dwconv():
     y = F.layer_norm(y, (256,), lw, lb, 1e-6)
     assert (out.float().view_as(y) - y).abs().max().item() < 5e-2
     assert (out.float().view_as(y) - y.to(BF).float()).abs().max().item() < 4e-2
+    # width not a multiple of the 8-pixel tile: the one-warp-per-pixel kernel
+    x = torch.randn((1, 256, 12, 20), generator=g, device="cuda")
+    out = ops.dwconv7_ln(x.permute(0, 2, 3, 1).contiguous().view(-1, 256), dw.reshape(256, 49).t().contiguous(), db, lw,
+                         lb, 1, 12, 20)
+    y = F.layer_norm(F.conv2d(x, dw, db, padding=3, groups=256).permute(0, 2, 3, 1), (256,), lw, lb, 1e-6)
+    assert (out.float().view_as(y) - y).abs().max().item() < 5e-2
 
 
 @pytest.mark.parametrize("Hi,Ho", [(128, 512), (128, 360), (512, 128), (100, 37)])

@@ -48,7 +48,7 @@ def attention():
             args = (B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D))
             flops = 4.0 * B * T * Nk * D
             for impl in ("tc5", "mma"):
-                for splits in (1, 2, 4, 9, 18):
+                for splits in (1, 2, 4, 8, 9, 16, 18):
                     if splits > (Nk + 63) // 64:
                         continue
                     us = timeit(lambda: ops.fmha(q, kv, kv, *args, num_splits=splits, impl=impl))

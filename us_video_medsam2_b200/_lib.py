@@ -127,6 +127,7 @@ _SIGNATURES = {
     "usvm_gemm_skinny_f32": [C.POINTER(SkinnyParams), _P],
     "usvm_token_chain": [C.POINTER(ChainParams), _P],
     "usvm_attn_t2i_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
+    "usvm_attn_t2i_split_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "usvm_attn_i2t_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "usvm_sam_select": [_P, _P, _I, _I, _P, _I, _I, _F, _F, _F, _P, _P, _P, _I, _I, _P],
     "usvm_objptr_mix": [_P, _P, _I, _P, _I, _I, _P],

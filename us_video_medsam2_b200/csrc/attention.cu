@@ -237,7 +237,10 @@ fmha_bf16_kernel(const usvm_fmha_params p) {
   }
 }
 
-// merge split partials: one thread per (row, 4 channels); the loads of all splits are independent and coalesced
+// merge split partials: one thread per (row, 4 channels).  The kernel is pure latency / bandwidth (up to 18 partials of
+// 128 KB per query tile), so all (max, sum) pairs are fetched up front and the partial rows in register batches of 8:
+// every load of a batch is in flight before the first one is consumed.
+constexpr int COMBINE_MAX_SPLITS = 32;
 template <int D>
 __global__ void __launch_bounds__(256)
 fmha_combine_kernel(const usvm_fmha_params p) {
@@ -252,20 +255,35 @@ fmha_combine_kernel(const usvm_fmha_params p) {
   const int qi = (int)(row - (long long)bh * p.Nq);
   const int b = bh / p.H, h = bh - b * p.H;
   const float sl2 = p.scale * 1.4426950408889634f;
+  const int ns = p.num_splits;
+  const float2* mlp = reinterpret_cast<const float2*>(p.ml_part) + row;
+  const float* op = p.o_part + row * D + c4;
+  const long long ostride = total_rows * D;
+  float2 ml[COMBINE_MAX_SPLITS];
+#pragma unroll
+  for (int s = 0; s < COMBINE_MAX_SPLITS; ++s) ml[s] = s < ns ? __ldg(mlp + (long long)s * total_rows) : make_float2(0.f, 0.f);
   float M = -INFINITY;
-  for (int s = 0; s < p.num_splits; ++s) {
-    const float2 ml = *reinterpret_cast<const float2*>(p.ml_part + ((long long)s * total_rows + row) * 2);
-    if (ml.y > 0.f) M = fmaxf(M, ml.x);
-  }
+#pragma unroll
+  for (int s = 0; s < COMBINE_MAX_SPLITS; ++s)
+    if (ml[s].y > 0.f) M = fmaxf(M, ml[s].x);
   float L = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < p.num_splits; ++s) {
-    const long long pr = (long long)s * total_rows + row;
-    const float2 ml = *reinterpret_cast<const float2*>(p.ml_part + pr * 2);
-    const float4 o = *reinterpret_cast<const float4*>(p.o_part + pr * D + c4);
-    const float w = ml.y > 0.f ? exp2f((ml.x - M) * sl2) : 0.f;
-    L += ml.y * w;
-    acc.x += o.x * w; acc.y += o.y * w; acc.z += o.z * w; acc.w += o.w * w;
+#pragma unroll
+  for (int s0 = 0; s0 < COMBINE_MAX_SPLITS; s0 += 8) {
+    if (s0 < ns) {
+      float4 o[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        o[u] = s0 + u < ns ? __ldg(reinterpret_cast<const float4*>(op + (long long)(s0 + u) * ostride))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float2 m = ml[s0 + u];
+        const float w = m.y > 0.f ? exp2f((m.x - M) * sl2) : 0.f;
+        L += m.y * w;
+        acc.x += o[u].x * w; acc.y += o[u].y * w; acc.z += o[u].z * w; acc.w += o[u].w * w;
+      }
+    }
   }
   const float inv = L > 0.f ? 1.f / L : 0.f;
   bf16* O = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs + (long long)h * p.o_hs + (long long)qi * p.o_rs + c4;
@@ -349,7 +367,7 @@ attn_small_f32_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 extern "C" int usvm_fmha_bf16(const usvm_fmha_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->o || p->B <= 0 || p->H <= 0 || p->Nq <= 0 || p->Nk <= 0)
     return USVM_ERR_ARG;
-  if (p->num_splits < 1) return USVM_ERR_ARG;
+  if (p->num_splits < 1 || p->num_splits > COMBINE_MAX_SPLITS) return USVM_ERR_ARG;
   if (p->num_splits > 1 && (!p->o_part || !p->ml_part)) return USVM_ERR_ARG;
   if (p->num_splits > cdiv(p->Nk, FN)) return USVM_ERR_ARG;
   if ((p->q_rs % 8) || (p->k_rs % 8) || (p->v_rs % 8) || (p->o_rs % 2) || (p->q_hs % 8) || (p->k_hs % 8) ||
@@ -363,7 +381,7 @@ extern "C" int usvm_fmha_bf16(const usvm_fmha_params* p, void* stream) {
 
 // merge the split-KV partials written by usvm_fmha_bf16 / usvm_fmha_tc5 (head_dim 96 or 256)
 extern "C" int usvm_fmha_combine(const usvm_fmha_params* p, void* stream) {
-  if (!p || !p->o || !p->o_part || !p->ml_part || p->num_splits < 1 || p->B <= 0 || p->H <= 0 || p->Nq <= 0)
+  if (!p || !p->o || !p->o_part || !p->ml_part || p->num_splits < 1 || p->num_splits > COMBINE_MAX_SPLITS || p->B <= 0 || p->H <= 0 || p->Nq <= 0)
     return USVM_ERR_ARG;
   const long long rows = (long long)p->B * p->H * p->Nq;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

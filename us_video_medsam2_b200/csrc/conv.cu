@@ -146,6 +146,102 @@ dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [
   }
 }
 
+
+// Tiled variant (C = 256, W % 8 == 0): one CTA per 8 consecutive pixels of an image row, thread <-> channel.  The
+// 7 x 14 input footprint of the tile is staged in shared memory with all loads in flight at once (the one-warp-per-pixel
+// kernel above re-reads every input 49 times and waits for L2 tap by tap); the thread keeps its channel's 49 weights
+// in registers, so the inner loop is 98 conflict-free LDS and 392 FMA.  LayerNorm statistics are block reductions.
+constexpr int DW_TILE = 8;
+constexpr int DW_FOOT = DW_TILE + 6;
+__global__ void __launch_bounds__(256)
+dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [49][256] */,
+                       const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                       float eps, bf16* __restrict__ out, int B, int H, int W) {
+  PDL_ENTRY();
+  constexpr int C = 256;
+  extern __shared__ __align__(16) float dw_smem[];
+  float* xs = dw_smem;                       // [7][14][256]
+  float* red = dw_smem + 7 * DW_FOOT * C;    // [8 warps][8 pixels]
+  const int c = threadIdx.x, warp = c >> 5, lane = c & 31;
+  const int tiles_x = W / DW_TILE;
+  const int tile = blockIdx.x;
+  const int ox0 = (tile % tiles_x) * DW_TILE, oy = (tile / tiles_x) % H, b = tile / (tiles_x * H);
+  // stage the footprint: 7 * 14 * 64 float4, zero outside the image
+  constexpr int NV = 7 * DW_FOOT * (C / 4);
+  for (int i0 = c; i0 < NV; i0 += 256 * 7) {
+    float4 v[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const int i = i0 + u * 256;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < NV) {
+        const int r = i / (DW_FOOT * 64), rem = i - r * (DW_FOOT * 64), px = rem >> 6, c4 = rem & 63;
+        const int y = oy - 3 + r, xx = ox0 - 3 + px;
+        if (y >= 0 && y < H && xx >= 0 && xx < W)
+          v[u] = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + y) * W + xx) * C) + c4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const int i = i0 + u * 256;
+      if (i < NV) *reinterpret_cast<float4*>(xs + 4 * i) = v[u];
+    }
+  }
+  float w[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) w[k] = __ldg(wt + k * C + c);
+  float acc[DW_TILE];
+  const float bc = __ldg(bias + c);
+#pragma unroll
+  for (int o = 0; o < DW_TILE; ++o) acc[o] = bc;
+  const float lw = __ldg(ln_w + c), lb = __ldg(ln_b + c);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+#pragma unroll
+    for (int px = 0; px < DW_FOOT; ++px) {
+      const float xv = xs[(r * DW_FOOT + px) * C + c];
+#pragma unroll
+      for (int o = 0; o < DW_TILE; ++o) {
+        const int kx = px - o;
+        if (kx >= 0 && kx < 7) acc[o] = fmaf(xv, w[r * 7 + kx], acc[o]);
+      }
+    }
+  }
+  // LayerNorm over the 256 channels of each of the 8 pixels (two-pass)
+  float mean[DW_TILE];
+#pragma unroll
+  for (int o = 0; o < DW_TILE; ++o) {
+    const float s = warp_sum(acc[o]);
+    if (lane == 0) red[warp * DW_TILE + o] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < DW_TILE; ++o) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv * DW_TILE + o];
+    mean[o] = s / C;
+    acc[o] -= mean[o];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < DW_TILE; ++o) {
+    const float s = warp_sum(acc[o] * acc[o]);
+    if (lane == 0) red[warp * DW_TILE + o] = s;
+  }
+  __syncthreads();
+  const long long pix0 = ((long long)b * H + oy) * W + ox0;
+#pragma unroll
+  for (int o = 0; o < DW_TILE; ++o) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv * DW_TILE + o];
+    const float rstd = 1.0f / sqrtf(s / C + eps);
+    out[(pix0 + o) * C + c] = __float2bfloat16(acc[o] * rstd * lw + lb);
+  }
+}
+
 __device__ __forceinline__ float post_op(float v, int mode, float scale, float bias) {
   if (mode == USVM_POST_SIGMOID_AFFINE) return (1.0f / (1.0f + expf(-v))) * scale + bias;
   if (mode == USVM_POST_BINARIZE_AFFINE) return (v > 0.f ? 1.0f : 0.0f) * scale + bias;
@@ -254,6 +350,18 @@ extern "C" int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* 
                                const float* ln_b, float eps, void* out_bf16, int B, int H, int W, int C,
                                void* stream) {
   if (!x || !w_49c || !bias || !ln_w || !ln_b || !out_bf16 || C != 256) return USVM_ERR_ARG;
+  if (W % DW_TILE == 0 && !(reinterpret_cast<uintptr_t>(x) & 15)) {
+    const int smem = (7 * DW_FOOT * 256 + 8 * DW_TILE) * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(dwconv7_ln_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return USVM_ERR_CUDA;
+      configured = true;
+    }
+    usvm_launch(dwconv7_ln_tile_kernel, dim3(B * H * (W / DW_TILE)), dim3(256), smem, STREAM, x, w_49c, bias, ln_w, ln_b,
+                eps, reinterpret_cast<bf16*>(out_bf16), B, H, W);
+    return usvm_check_launch();
+  }
   usvm_launch(dwconv7_ln_kernel<8>, dim3(cdiv((long long)B * H * W, 8)), dim3(256), 0, STREAM, x, w_49c, bias, ln_w, ln_b, eps,
                                                                            reinterpret_cast<bf16*>(out_bf16), B, H, W);
   return usvm_check_launch();

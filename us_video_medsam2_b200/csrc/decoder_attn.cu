@@ -186,6 +186,128 @@ attn_t2i_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__
   }
 }
 
+
+// ---- token -> image attention, split over the keys ------------------------------------------------------------------
+// grid (object x head, key split): each CTA scores its 128 keys for all tokens and writes an unnormalised partial
+// (max, sum, P.V); the CTA that finishes last for a head (ticket counter) merges the partials in split order, so the
+// result does not depend on arrival order.  8 heads x 8 splits = 64 CTAs instead of 8 for one object.
+constexpr int T2S_KEYS = 128;
+__global__ void __launch_bounds__(T2S_KEYS)
+attn_t2i_split_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__ k, const float* __restrict__ v,
+                      int kv_rs, float* __restrict__ out, int o_rs, int H, int Nt, int Nk, float scale,
+                      float* __restrict__ part, int* __restrict__ counters) {
+  PDL_ENTRY();
+  __shared__ float s_q[T2I_MAX_NT * T2I_DH];
+  __shared__ float s_p[T2I_MAX_NT * T2S_KEYS];
+  __shared__ float s_v[T2S_KEYS * T2I_LD];
+  __shared__ float s_ml[T2I_MAX_NT * 2];
+  __shared__ int s_last;
+  const int bh = blockIdx.x, split = blockIdx.y, S = gridDim.y;
+  const int b = bh / H, h = bh - b * H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = split * T2S_KEYS + tid;
+  const bool live = j < Nk;
+  float4 kr[4], vr[4];
+  if (live) {
+    const float* kp = k + ((long long)b * Nk + j) * kv_rs + h * T2I_DH;
+    const float* vp = v + ((long long)b * Nk + j) * kv_rs + h * T2I_DH;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      kr[i] = __ldg(reinterpret_cast<const float4*>(kp) + i);
+      vr[i] = __ldg(reinterpret_cast<const float4*>(vp) + i);
+    }
+  }
+  for (int i = tid; i < Nt * T2I_DH; i += T2S_KEYS)
+    s_q[i] = q[((long long)b * Nt + i / T2I_DH) * q_rs + h * T2I_DH + (i % T2I_DH)] * scale;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float* dv = s_v + tid * T2I_LD + 4 * i;
+    const float4 x = live ? vr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    dv[0] = x.x; dv[1] = x.y; dv[2] = x.z; dv[3] = x.w;
+  }
+  for (int t = 0; t < Nt; ++t) {
+    float d = -INFINITY;
+    if (live) {
+      d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 qq = *reinterpret_cast<const float4*>(s_q + t * T2I_DH + 4 * i);
+        d = fmaf(qq.x, kr[i].x, d); d = fmaf(qq.y, kr[i].y, d); d = fmaf(qq.z, kr[i].z, d); d = fmaf(qq.w, kr[i].w, d);
+      }
+    }
+    s_p[t * T2S_KEYS + tid] = d;
+  }
+  __syncthreads();
+  for (int t = warp; t < Nt; t += T2S_KEYS / 32) {  // local max / exp / sum of one token's 128 scores
+    float e[4], mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      e[u] = s_p[t * T2S_KEYS + lane + 32 * u];
+      mx = fmaxf(mx, e[u]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      e[u] = mx == -INFINITY ? 0.f : __expf(e[u] - mx);
+      s_p[t * T2S_KEYS + lane + 32 * u] = e[u];
+      sum += e[u];
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      s_ml[2 * t] = mx;
+      s_ml[2 * t + 1] = sum;
+    }
+  }
+  __syncthreads();
+  // partial layout: [bh][split][Nt][16 + 2]
+  float* mypart = part + ((long long)bh * S + split) * Nt * (T2I_DH + 2);
+  for (int i = tid; i < Nt * T2I_DH; i += T2S_KEYS) {
+    const int t = i / T2I_DH, c = i - t * T2I_DH;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int jj = 0; jj < T2S_KEYS; ++jj) acc = fmaf(s_p[t * T2S_KEYS + jj], s_v[jj * T2I_LD + c], acc);
+    mypart[t * (T2I_DH + 2) + c] = acc;
+  }
+  for (int i = tid; i < Nt * 2; i += T2S_KEYS) mypart[(i >> 1) * (T2I_DH + 2) + T2I_DH + (i & 1)] = s_ml[i];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&counters[bh], 1) == S - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* hp = part + (long long)bh * S * Nt * (T2I_DH + 2);
+  for (int i = tid; i < Nt * T2I_DH; i += T2S_KEYS) {
+    const int t = i / T2I_DH, c = i - t * T2I_DH;
+    float m[16], l[16], o[16];
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) {
+      if (s2 < S) {
+        const float* pp = hp + ((long long)s2 * Nt + t) * (T2I_DH + 2);
+        m[s2] = __ldcg(pp + T2I_DH);
+        l[s2] = __ldcg(pp + T2I_DH + 1);
+        o[s2] = __ldcg(pp + c);
+      }
+    }
+    float M = -INFINITY;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2)
+      if (s2 < S) M = fmaxf(M, m[s2]);
+    float L = 0.f, acc = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; ++s2) {
+      if (s2 < S) {
+        const float w = __expf(m[s2] - M);
+        L = fmaf(l[s2], w, L);
+        acc = fmaf(o[s2], w, acc);
+      }
+    }
+    out[((long long)b * Nt + t) * o_rs + h * T2I_DH + c] = acc / L;
+  }
+  if (tid == 0) counters[bh] = 0;  // ready for the next launch (stream-ordered)
+}
+
 // ---- image -> token attention --------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn_i2t_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__ k, const float* __restrict__ v,
@@ -285,6 +407,19 @@ extern "C" int usvm_attn_t2i_f32(const float* q, int q_rs, const float* k, const
     configured = 200 * 1024;
   }
   usvm_launch(attn_t2i_kernel, dim3(B * H), dim3(256), smem, STREAM, q, q_rs, k, v, kv_rs, out, o_rs, H, Nt, Nk, scale);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_attn_t2i_split_f32(const float* q, int q_rs, const float* k, const float* v, int kv_rs, float* out,
+                                       int o_rs, int B, int H, int Nt, int Nk, float scale, float* partials,
+                                       int* counters, void* stream) {
+  if (!q || !k || !v || !out || !partials || !counters || B <= 0 || H <= 0 || Nt <= 0 || Nt > T2I_MAX_NT || Nk <= 0 ||
+      (kv_rs % 4) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
+    return USVM_ERR_ARG;
+  const int S = cdiv(Nk, T2S_KEYS);
+  if (S > 16) return USVM_ERR_ARG;
+  usvm_launch(attn_t2i_split_kernel, dim3(B * H, S), dim3(T2S_KEYS), 0, STREAM, q, q_rs, k, v, kv_rs, out, o_rs, H, Nt, Nk,
+              scale, partials, counters);
   return usvm_check_launch();
 }
 

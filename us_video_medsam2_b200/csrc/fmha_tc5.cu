@@ -612,7 +612,7 @@ extern "C" int usvm_fmha_tc5_set_variant(int v) {
 
 extern "C" int usvm_fmha_tc5(const usvm_fmha_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->o || p->B <= 0 || p->Nq <= 0 || p->Nk <= 0) return USVM_ERR_ARG;
-  if (p->head_dim != HD || p->H != 1 || (p->Nq % QM) || p->num_splits < 1) return USVM_ERR_ARG;
+  if (p->head_dim != HD || p->H != 1 || (p->Nq % QM) || p->num_splits < 1 || p->num_splits > 32) return USVM_ERR_ARG;
   if (p->q_bs != (long long)p->Nq * p->q_rs || p->k_bs != (long long)p->Nk * p->k_rs ||
       p->v_bs != (long long)p->Nk * p->v_rs)
     return USVM_ERR_ARG;

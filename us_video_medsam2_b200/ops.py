@@ -515,10 +515,22 @@ def token_chain(steps, n_obj, like, cluster=None, timing=None, precise=None):
     return scratch
 
 
+_T2I_COUNTERS = {}
+
+
 def attn_t2i(q, k, v, B, Nt, Nk, H=8):
     """token->image attention, head_dim 16: q [B*Nt, H*16]; k, v column views of an image-side buffer."""
     out = empty((B * Nt, H * 16), F32, q)
     assert k.stride(0) == v.stride(0)
+    splits = (Nk + 127) // 128
+    if 1 < splits <= 16:  # key-split kernel: B*H*splits CTAs, the last one per head merges the partials
+        key = (q.device, B * H)
+        if key not in _T2I_COUNTERS:
+            _T2I_COUNTERS[key] = torch.zeros(B * H, dtype=torch.int32, device=q.device)
+        part = empty((B * H * splits * Nt * 18,), F32, q)
+        call("usvm_attn_t2i_split_f32", q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+             out.data_ptr(), out.stride(0), B, H, Nt, Nk, 0.25, part.data_ptr(), _T2I_COUNTERS[key].data_ptr(), _stream())
+        return out
     call("usvm_attn_t2i_f32", q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), out.data_ptr(),
          out.stride(0), B, H, Nt, Nk, 0.25, _stream())
     return out
