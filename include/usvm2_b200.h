@@ -65,6 +65,14 @@ typedef struct usvm_gemm_epilogue {
   const float* rope_cos;
   const float* rope_sin;
   int rope_cols, rope_rows_per_batch, rope_n_rope, rope_table_rows;
+  /* optional fused LayerNorm over the output row (N == 256 only, tensor-core bf16 kernel): out_f32 receives the
+   * epilogue result x as usual and out_bf16 receives LayerNorm(x) * ln_w + ln_b (then exact GELU when ln_gelu != 0)
+   * instead of a bf16 copy of x -- the "residual GEMM followed by the next block's norm" pair of every transformer
+   * layer as one launch.  ln_w == NULL disables it. */
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
+  int ln_gelu;
 } usvm_gemm_epilogue;
 
 /* bf16 operands, fp32 accumulation in TMEM: TMA (128B swizzle) -> tcgen05.mma -> tcgen05.ld epilogue.

@@ -159,3 +159,30 @@ def test_tc5_tf32_gemm(M, N, K, block_n):
     got = ops.gemm_f32(a16, w16, bias, residual=res, tf32=True, block_n=block_n)
     want = a16 @ w16.t() + bias + res
     assert (got - want).abs().max().item() < 2e-5 * K ** 0.5
+
+
+@pytest.mark.parametrize("M,K,gelu", [(1024, 256, False), (2048 + 40, 576, True), (128, 2048, False)])
+def test_tc5_gemm_fused_layernorm(M, K, gelu):
+    """Residual GEMM + LayerNorm of the result row (N = 256) in one launch: fp32 output = epilogue result,
+    bf16 output = LayerNorm (then GELU) of it."""
+    from us_video_medsam2_b200 import ops
+
+    N = 256
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn((M, K), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda")
+    res = torch.randn((M, N), generator=g, device="cuda") * 2 + 0.5
+    lw, lb = torch.randn(N, generator=g, device="cuda"), torch.randn(N, generator=g, device="cuda")
+    x, h = ops.gemm_bf16(a, w, bias=bias, residual=res, f32=True, ln=(lw, lb, 1e-5, gelu), simt=False, ln_fused=True)
+    want_x = _ref(a, w, bias, 0, None, res, 0)
+    want_h = F.layer_norm(want_x, (N,), lw, lb, 1e-5)
+    if gelu:
+        want_h = F.gelu(want_h)
+    assert (x - want_x).abs().max().item() < 3e-3
+    assert (h.float() - want_h).abs().max().item() < 4e-2
+    # agrees with the unfused pair of kernels to bf16 rounding
+    x2, _ = ops.gemm_bf16(a, w, bias=bias, residual=res, f32=True, simt=False)
+    _, h2 = ops.layernorm(x2, lw, lb, 1e-5, bf16=True, gelu=gelu)
+    assert torch.equal(x, x2)
+    assert (h.float() - h2.float()).abs().max().item() < 4e-2

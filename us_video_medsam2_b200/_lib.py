@@ -22,7 +22,8 @@ class GemmEpilogue(C.Structure):
                 ("res_mod", C.c_int), ("act", C.c_int), ("out_f32", C.c_void_p), ("ldo_f32", C.c_int),
                 ("out_bf16", C.c_void_p), ("ldo_bf16", C.c_int),
                 ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_cols", C.c_int),
-                ("rope_rows_per_batch", C.c_int), ("rope_n_rope", C.c_int), ("rope_table_rows", C.c_int)]
+                ("rope_rows_per_batch", C.c_int), ("rope_n_rope", C.c_int), ("rope_table_rows", C.c_int),
+                ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("ln_eps", C.c_float), ("ln_gelu", C.c_int)]
 
 
 class FmhaParams(C.Structure):

@@ -336,25 +336,47 @@ __global__ void finalize_memory_kernel(const float* __restrict__ x, const float*
 // ---------------------------------------------------------------------------------------------
 // temporal position encoding of the object pointers (get_1d_sine_pe + obj_ptr_tpos_proj,
 // sam2_utils.py:64-74, sam2_base.py:1402-1408): out[p*4 + q, c] = W[c, :] . [sin(rel/dim_t), cos(rel/dim_t)] + b[c]
-__global__ void __launch_bounds__(64)
+// one CTA per pointer; warp w owns output channels 8w .. 8w+7: the lanes stride the 256-long reduction with float4 loads
+// (coalesced, all 16 in flight at once) and the channel sums are warp reductions
+__global__ void __launch_bounds__(256)
 ptr_tpos_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ W, const float* __restrict__ bias,
                 float* __restrict__ out) {
   PDL_ENTRY();
-  __shared__ float pe[256];
-  const int p = blockIdx.x, c = threadIdx.x;
+  __shared__ __align__(16) float pe[256];
+  const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float4 wv[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float* wr = W + (warp * 8 + i) * 256 + lane * 4;
+    wv[i][0] = __ldg(reinterpret_cast<const float4*>(wr));
+    wv[i][1] = __ldg(reinterpret_cast<const float4*>(wr + 128));
+  }
   const float rel = ctrl->ptr_rel[p];
-  for (int j = c; j < 128; j += 64) {
-    const float dim_t = powf(10000.0f, (float)(2 * (j / 2)) / 128.0f);
+  if (tid < 128) {
+    const float dim_t = powf(10000.0f, (float)(2 * (tid / 2)) / 128.0f);
     const float e = rel / dim_t;
-    pe[j] = sinf(e);
-    pe[128 + j] = cosf(e);
+    pe[tid] = sinf(e);
+    pe[128 + tid] = cosf(e);
   }
   __syncthreads();
-  float acc = bias[c];
-  const float* wr = W + c * 256;
-  for (int j = 0; j < 256; ++j) acc = fmaf(wr[j], pe[j], acc);
+  const float4 p0 = *reinterpret_cast<const float4*>(pe + lane * 4);
+  const float4 p1 = *reinterpret_cast<const float4*>(pe + 128 + lane * 4);
+  float mine = 0.f;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) out[(p * 4 + q) * 64 + c] = acc;
+  for (int i = 0; i < 8; ++i) {
+    // same summation tree for every channel: fixed order inside the lane, then the warp butterfly
+    float a = wv[i][0].x * p0.x;
+    a = fmaf(wv[i][0].y, p0.y, a); a = fmaf(wv[i][0].z, p0.z, a); a = fmaf(wv[i][0].w, p0.w, a);
+    a = fmaf(wv[i][1].x, p1.x, a); a = fmaf(wv[i][1].y, p1.y, a); a = fmaf(wv[i][1].z, p1.z, a); a = fmaf(wv[i][1].w, p1.w, a);
+    a = warp_sum(a);
+    if (lane == i) mine = a;
+  }
+  if (lane < 8) {
+    const int c = warp * 8 + lane;
+    const float v = mine + bias[c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out[(p * 4 + q) * 64 + c] = v;
+  }
 }
 
 __global__ void build_memory_store_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ pos,
@@ -537,7 +559,7 @@ extern "C" int usvm_finalize_memory(const float* x, const float* score, int scor
 extern "C" int usvm_ptr_tpos(const usvm_frame_ctrl* ctrl_dev, const float* W, const float* bias, float* out, int n_ptr,
                              void* stream) {
   if (!ctrl_dev || !W || !bias || !out || n_ptr <= 0 || n_ptr > USVM_MAX_PTRS) return USVM_ERR_ARG;
-  usvm_launch(ptr_tpos_kernel, dim3(n_ptr), dim3(64), 0, STREAM, ctrl_dev, W, bias, out);
+  usvm_launch(ptr_tpos_kernel, dim3(n_ptr), dim3(256), 0, STREAM, ctrl_dev, W, bias, out);
   return usvm_check_launch();
 }
 

@@ -229,6 +229,10 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       return true;
     };
     bool have = fetch_residual(0, rs);
+    // fused LayerNorm (full 256-wide rows in this tile): pass 1 below also sums the row and parks the epilogue result
+    // back in TMEM; the statistics and the normalised bf16 output follow after the loop
+    const bool ln_mode = BN == 256 && ep.ln_w != nullptr;
+    float ln_sum = 0.f;
     mbar_wait(tmem_full_bar, 0);
     tc5_fence_after();
 #pragma unroll 1
@@ -253,6 +257,14 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       have = have_next;
 #pragma unroll
       for (int j = 0; j < 8; ++j) rs[j] = rn[j];
+      if (ln_mode) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          ln_sum += v[j];
+          acc[j] = __float_as_uint(v[j]);
+        }
+        tc5_st_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
+      }
       if (pending) {  // the previous block's TMA store must have finished reading the staging buffers
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
@@ -264,7 +276,7 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           *reinterpret_cast<float4*>(prow + ((c ^ (lane & 7)) << 4)) =
               make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       }
-      if (ep.out_bf16) {  // 64-byte rows, no swizzle
+      if (ep.out_bf16 && !ln_mode) {  // 64-byte rows, no swizzle
         uint8_t* prow = stg16 + lane * 64;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -280,10 +292,72 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) {
         if (ep.out_f32) tma_store_2d(&tmO32, stg32, col0, row0);
-        if (ep.out_bf16) tma_store_2d(&tmO16, stg16, col0, row0);
+        if (ep.out_bf16 && !ln_mode) tma_store_2d(&tmO16, stg16, col0, row0);
         tma_store_commit();
       }
       pending = true;
+    }
+    if (ln_mode && row0 < M) {
+      tc5_wait_st_all();
+      const float mean = ln_sum * (1.0f / 256.0f);
+      float sq = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t acc[32];
+        tc5_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
+        tc5_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d = __uint_as_float(acc[j]) - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+      const float rstd = 1.0f / sqrtf(sq * (1.0f / 256.0f) + ep.ln_eps);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t acc[32];
+        tc5_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
+        float4 lw[8], lb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          lw[j] = __ldg(reinterpret_cast<const float4*>(ep.ln_w + c0) + j);
+          lb[j] = __ldg(reinterpret_cast<const float4*>(ep.ln_b + c0) + j);
+        }
+        tc5_wait_ld();
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          y[4 * j] = (__uint_as_float(acc[4 * j]) - mean) * rstd * lw[j].x + lb[j].x;
+          y[4 * j + 1] = (__uint_as_float(acc[4 * j + 1]) - mean) * rstd * lw[j].y + lb[j].y;
+          y[4 * j + 2] = (__uint_as_float(acc[4 * j + 2]) - mean) * rstd * lw[j].z + lb[j].z;
+          y[4 * j + 3] = (__uint_as_float(acc[4 * j + 3]) - mean) * rstd * lw[j].w + lb[j].w;
+        }
+        if (ep.ln_gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
+        }
+        if (pending) {
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
+        uint8_t* prow = stg16 + lane * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16x2(y[8 * c], y[8 * c + 1]);
+          pk.y = pack_bf16x2(y[8 * c + 2], y[8 * c + 3]);
+          pk.z = pack_bf16x2(y[8 * c + 4], y[8 * c + 5]);
+          pk.w = pack_bf16x2(y[8 * c + 6], y[8 * c + 7]);
+          *reinterpret_cast<uint4*>(prow + (c << 4)) = pk;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO16, stg16, tile_n * BN + c0, row0);
+          tma_store_commit();
+        }
+        pending = true;
+      }
     }
     if (pending && lane == 0) tma_store_wait_read();  // smem must outlive the bulk reads
     __syncwarp();
@@ -638,6 +712,12 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
                        (reinterpret_cast<uintptr_t>(ep->rope_sin) & 15)))
     return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (ep->ln_w) {  // fused LayerNorm: one 128 x 256 tile per CTA holds whole rows
+    if (N != 256 || !ep->ln_b || !ep->out_bf16 || ep->rope_cos || (reinterpret_cast<uintptr_t>(ep->ln_w) & 15) ||
+        (reinterpret_cast<uintptr_t>(ep->ln_b) & 15))
+      return USVM_ERR_ARG;
+    return launch<256, false>(A, lda, W, ldw, ep, M, N, K, s);
+  }
   int bn = block_n;
   if (bn < 0) return launch_persistent(A, lda, W, ldw, ep, M, N, K, bn == -1 ? persistent_block_n(N) : -bn, s);
   if (bn == 0 && (long long)cdiv(M, BM) * cdiv(N, 128) >= 2 * 148)  // throughput-bound: more than one wave of tiles

@@ -373,13 +373,14 @@ class Engine:
             _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
             o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
                          (512, T * 768, 768, 256), num_splits=self._splits(B, T))
-            x, _ = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True)
-            _, h = ops.layernorm(x, *L["n2"], 1e-5, bf16=True)
+            # out-projection + residual and the next sub-block's LayerNorm in one launch (whole rows per tile)
+            x, h = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True,
+                                 ln=(L["n2"][0], L["n2"][1], 1e-5))
             _, q = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], bf16=True, rope=(cs, sn, 256, T, T))
             o = ops.fmha(q, k_all, v_all, B, 1, T, Nk, 256, (0, T * 256, 256, 256), (li * 256, Nk * 1024, 1024, 256),
                          (li * 256, Nk * 1024, 1024, 256), num_splits=self._splits(B, Nk))
-            x, _ = ops.gemm_bf16(o.view(B * T, 256), L["ca_o"][0], bias=L["ca_o"][1], residual=x, f32=True)
-            _, h = ops.layernorm(x, *L["n3"], 1e-5, bf16=True)
+            x, h = ops.gemm_bf16(o.view(B * T, 256), L["ca_o"][0], bias=L["ca_o"][1], residual=x, f32=True,
+                                 ln=(L["n3"][0], L["n3"][1], 1e-5))
             _, m = ops.gemm_bf16(h, L["l1"][0], bias=L["l1"][1], act=ACT_RELU, bf16=True)
             x, _ = ops.gemm_bf16(m, L["l2"][0], bias=L["l2"][1], residual=x, f32=True)
         out, _ = ops.layernorm(x, *w.ma_norm, 1e-5, f32=True)
@@ -614,8 +615,7 @@ class Engine:
             x, H, W = ops.conv2d_small(x, cw, cb, B, H, W, Cin, Cout, 3, 2, 1, ln=(lw, lb), gelu=True)
             Cin = Cout
         A4 = ops.im2col_nhwc(x, B, 64, 64, 64, 3, 2, 1)
-        c4, _ = ops.gemm_bf16(A4, w.md_conv3_w, bias=w.md_conv3_b, f32=True)
-        _, c4n = ops.layernorm(c4, *w.md_ln3, 1e-6, bf16=True, gelu=True)
+        _, c4n = ops.gemm_bf16(A4, w.md_conv3_w, bias=w.md_conv3_b, ln=(w.md_ln3[0], w.md_ln3[1], 1e-6, True))
         pp, _ = ops.gemm_bf16(feat_bf16, *w.pix_proj, f32=True)  # pix_feat_proj, shared by all objects
         x, _ = ops.gemm_bf16(c4n, w.md_out[0], bias=w.md_out[1], residual=pp, res_mod=1024, f32=True)
         xb = None

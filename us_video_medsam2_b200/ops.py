@@ -48,8 +48,12 @@ def empty(shape, dtype, like):
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------
-def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16, like, out_f32, out_bf16, rope=None):
+def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16, like, out_f32, out_bf16, rope=None,
+              ln=None):
     ep = GemmEpilogue()
+    if ln is not None:  # (weight, bias, eps[, gelu])
+        ep.ln_w, ep.ln_b, ep.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln[2]
+        ep.ln_gelu = int(len(ln) > 3 and bool(ln[3]))
     if rope is not None:  # (cos, sin, cols, rows_per_batch, n_rope)
         ep.rope_cos, ep.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
         ep.rope_cols, ep.rope_rows_per_batch, ep.rope_n_rope, ep.rope_table_rows = rope[2], rope[3], rope[4], rope[0].shape[0]
@@ -67,15 +71,25 @@ def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16
 
 
 def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, f32=False, bf16=False,
-              out_f32=None, out_bf16=None, block_n=0, simt=None, rope=None):
+              out_f32=None, out_bf16=None, block_n=0, simt=None, rope=None, ln=None, ln_fused=None):
     """epi(a[M,K] @ w[N,K]^T) on the tcgen05 kernel; returns (fp32 out or None, bf16 out or None).
-    rope = (cos, sin, cols, rows_per_batch, n_rope): fused rotary encoding of output columns [0, cols)."""
+    rope = (cos, sin, cols, rows_per_batch, n_rope): fused rotary encoding of output columns [0, cols).
+    ln = (weight, bias, eps[, gelu]): the bf16 output becomes LayerNorm(row) (then GELU) of the result.  With N == 256
+    the norm can run inside the GEMM epilogue (one 128 x 256 tile per CTA owns whole rows); that pays off once there are
+    enough row tiles to occupy the GPU (measured: 8 tiles at M = 1024 lose to GEMM + LayerNorm launches, which spread
+    over 64 + 128 CTAs), so ln_fused=None fuses from M >= 4096 on; True / False force it."""
     _chk(a, BF16, "a"), _chk(w, BF16, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if ln is not None and ((_FORCE_SIMT if simt is None else simt) or N != 256 or
+                           not (M >= 4096 if ln_fused is None else ln_fused)):  # GEMM, then the LayerNorm kernel
+        o32, _ = gemm_bf16(a, w, bias, act, col_scale, residual, res_mod, f32=True, out_f32=out_f32, block_n=block_n,
+                           simt=simt, rope=rope)
+        _, o16 = layernorm(o32, ln[0], ln[1], ln[2], bf16=True, gelu=len(ln) > 3 and bool(ln[3]))
+        return o32, o16
     ep, o32, o16 = _epilogue(M, N, bias, act, col_scale, residual, res_mod, f32 or out_f32 is not None,
-                             bf16 or out_bf16 is not None, a, out_f32, out_bf16, rope)
+                             bf16 or out_bf16 is not None or ln is not None, a, out_f32, out_bf16, rope, ln)
     if _FORCE_SIMT if simt is None else simt:
         call("usvm_gemm_simt", a.data_ptr(), 1, a.stride(0), w.data_ptr(), 1, w.stride(0), C.byref(ep), M, N, K,
              _stream())
