@@ -281,7 +281,11 @@ def run_b200(args, rank, world):
     if ks:
         ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "frac": ach / peaks["bf16_sustained"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of fmha_tc5_ts_kernel at this shape from the
+                    # `ncu --set full` capture summarised in profiles/r1_fmha_tc5_ts_ncu_full.md (B = 1, 18 splits):
+                    # 7.96 MB read (K/V once + Q) + 2 KB written -- the split partials stay in L2 for the combine
+                    "traffic": 7.966e6 if B == 1 else None,
                     "kernel": "fmha_tc5_ts_kernel + fmha_combine_kernel<256> (memory-attention cross-attention, "
                               f"1024 x 7232 keys, d=256, {ks['splits']}-way split-KV)",
                     "launches_timed": ks["launches"], "avg_us": ks["avg_ms"] * 1e3, "peak_source": peaks["source"],

@@ -80,7 +80,7 @@ typedef struct usvm_gemm_epilogue {
  * block_n: 0 = auto; 32 / 64 / 128 / 256 = one 128 x block_n tile per CTA (latency-bound shapes); negative = the
  * persistent kernel (one CTA per SM walks the tiles, accumulator double-buffered in TMEM so the epilogue of tile i
  * overlaps the mainloop of tile i+1) with tile width -block_n (a multiple of 32, <= 256), -1 = its own choice.
- * Auto picks the persistent kernel when the problem has more than two waves of 128 x 128 tiles. */
+ * Auto picks the persistent kernel when the problem has at least one full wave (148) of 128 x 128 tiles. */
 int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep_host, int M, int N,
                        int K, int block_n, void* stream);
 /* Same kernel on fp32 operands as tf32 (10-bit mantissa products, fp32 accumulate): image-side projections of the SAM

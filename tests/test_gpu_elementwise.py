@@ -151,7 +151,8 @@ def test_build_memory_and_finalize():
 
 
 @pytest.mark.parametrize("Cin,Cout,k,s,p,H", [(1, 4, 3, 2, 1, 512), (4, 16, 3, 2, 1, 256), (16, 64, 3, 2, 1, 128),
-                                              (1, 4, 2, 2, 0, 128), (4, 16, 2, 2, 0, 64), (1, 1, 4, 4, 0, 512)])
+                                              (1, 4, 2, 2, 0, 128), (4, 16, 2, 2, 0, 64), (1, 1, 4, 4, 0, 512),
+                                              (4, 16, 3, 2, 1, 36), (16, 64, 3, 1, 1, 20)])
 def test_conv2d_small(Cin, Cout, k, s, p, H):
     from us_video_medsam2_b200 import ops
 

@@ -83,6 +83,133 @@ conv2d_small_kernel(const float* __restrict__ x, const float* __restrict__ wt, c
   }
 }
 
+
+// Tiled variant for the mask down-sampler stages (Cout in {4, 16, 64}, square output tile of 1024 / Cout pixels per
+// CTA): the input footprint and the weights are staged in shared memory with all global loads of a thread in flight at
+// once (the kernel above walks taps x channels with one dependent global load per multiply); a thread then produces
+// four consecutive output channels of one pixel (float4 weights, broadcast input), LayerNorm statistics are shuffles
+// inside the pixel's Cout / 4 lanes, and the store is one float4.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+conv2d_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
+                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int gelu,
+                   float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int H, int W, int k, int s, int pad, int Ho,
+                   int Wo) {
+  PDL_ENTRY();
+  constexpr int LPP = COUT / 4;           // lanes per pixel
+  constexpr int PIX = 256 / LPP;          // pixels per CTA
+  constexpr int TW = PIX == 256 ? 16 : PIX == 64 ? 8 : 4;  // square tile
+  extern __shared__ __align__(16) float cv_smem[];
+  const int K = k * k * CIN;
+  float* s_w = cv_smem;                   // [K][COUT]
+  float* s_x = cv_smem + K * COUT;        // [IH][IW][CIN]
+  const int IW = (TW - 1) * s + k;
+  const int tiles_x = Wo / TW, tiles_y = Ho / TW;
+  const int tile = blockIdx.x;
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+  const int iy0 = ty * TW * s - pad, ix0 = tx * TW * s - pad;
+  const int tid = threadIdx.x;
+  {  // weights: K * COUT / 4 float4, batches of 8 per thread
+    const int nv = K * COUT / 4;
+    for (int i0 = tid; i0 < nv; i0 += 256 * 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * 256 < nv) v[u] = __ldg(reinterpret_cast<const float4*>(wt) + i0 + u * 256);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i0 + u * 256 < nv) reinterpret_cast<float4*>(s_w)[i0 + u * 256] = v[u];
+    }
+  }
+  {  // input footprint, zero outside the image; a row of the footprint is contiguous in memory (IW * CIN floats)
+    const int row_f = IW * CIN, nf = IW * row_f;
+    for (int i0 = tid; i0 < nf; i0 += 256 * 6) {
+      float v[6];
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        const int i = i0 + u * 256;
+        v[u] = 0.f;
+        if (i < nf) {
+          const int r = i / row_f, c = i - r * row_f;
+          const int y = iy0 + r, xx = ix0 + c / CIN;
+          if (y >= 0 && y < H && xx >= 0 && xx < W) v[u] = __ldg(x + (((long long)b * H + y) * W + ix0) * CIN + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 6; ++u)
+        if (i0 + u * 256 < nf) s_x[i0 + u * 256] = v[u];
+    }
+  }
+  const int p = tid / LPP, c4 = (tid % LPP) * 4;
+  const int py = p / TW, px = p - py * TW;
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c4));
+  float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ln_w) {
+    lw = __ldg(reinterpret_cast<const float4*>(ln_w + c4));
+    lb = __ldg(reinterpret_cast<const float4*>(ln_b + c4));
+  }
+  __syncthreads();
+  float4 acc = b4;
+  for (int ky = 0; ky < k; ++ky) {
+    for (int kx = 0; kx < k; ++kx) {
+      const float* xp = s_x + ((py * s + ky) * IW + px * s + kx) * CIN;
+      const float* wp = s_w + (ky * k + kx) * CIN * COUT + c4;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float v = xp[ci];
+        const float4 w4 = *reinterpret_cast<const float4*>(wp + ci * COUT);
+        acc.x = fmaf(v, w4.x, acc.x); acc.y = fmaf(v, w4.y, acc.y);
+        acc.z = fmaf(v, w4.z, acc.z); acc.w = fmaf(v, w4.w, acc.w);
+      }
+    }
+  }
+  if (ln_w) {
+    float sum = (acc.x + acc.y) + (acc.z + acc.w);
+#pragma unroll
+    for (int o = LPP >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / COUT;
+    acc.x -= mean; acc.y -= mean; acc.z -= mean; acc.w -= mean;
+    float var = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+#pragma unroll
+    for (int o = LPP >> 1; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / COUT + eps);
+    acc.x = acc.x * rstd * lw.x + lb.x; acc.y = acc.y * rstd * lw.y + lb.y;
+    acc.z = acc.z * rstd * lw.z + lb.z; acc.w = acc.w * rstd * lw.w + lb.w;
+  }
+  if (gelu) {
+    acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w);
+  }
+  const long long pix = ((long long)b * Ho + ty * TW + py) * Wo + tx * TW + px;
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + pix * COUT + c4) = acc;
+  if (out_bf16) {
+    uint2 pk;
+    pk.x = pack_bf16x2(acc.x, acc.y);
+    pk.y = pack_bf16x2(acc.z, acc.w);
+    *reinterpret_cast<uint2*>(out_bf16 + pix * COUT + c4) = pk;
+  }
+}
+
+template <int CIN, int COUT>
+int launch_conv_tile(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                     int gelu, float* out_f32, bf16* out_bf16, int B, int H, int W, int k, int s, int pad, int Ho, int Wo,
+                     cudaStream_t stream) {
+  constexpr int PIX = 256 / (COUT / 4);
+  constexpr int TW = PIX == 256 ? 16 : PIX == 64 ? 8 : 4;
+  const int IW = (TW - 1) * s + k;
+  const size_t smem = ((size_t)k * k * CIN * COUT + (size_t)IW * IW * CIN) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(conv2d_tile_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
+        cudaSuccess)
+      return USVM_ERR_CUDA;
+    configured = true;
+  }
+  if (smem > 96 * 1024) return USVM_ERR_ARG;
+  usvm_launch(conv2d_tile_kernel<CIN, COUT>, dim3(B * (Ho / TW) * (Wo / TW)), dim3(256), smem, stream, x, w, bias, ln_w, ln_b,
+              eps, gelu, out_f32, out_bf16, H, W, k, s, pad, Ho, Wo);
+  return usvm_check_launch();
+}
+
 // A[pix, (ky*k + kx)*C + c] = x[b, oy*s - pad + ky, ox*s - pad + kx, c] (zero outside), bf16
 __global__ void im2col_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ A, int B, int H, int W, int C, int k,
                                    int s, int pad, int Ho, int Wo) {
@@ -328,6 +455,21 @@ extern "C" int usvm_conv2d_small(const float* x, const float* w_kkio, const floa
   const size_t smem = (size_t)k * k * Cin * Cout * sizeof(float);
   if (smem > 48 * 1024) return USVM_ERR_ARG;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  {  // mask down-sampler shapes: shared-memory tiled kernel
+    bf16* ob = reinterpret_cast<bf16*>(out_bf16);
+    const bool aligned = !(reinterpret_cast<uintptr_t>(w_kkio) & 15) && !(reinterpret_cast<uintptr_t>(bias) & 15) &&
+                         !(reinterpret_cast<uintptr_t>(out_f32) & 15) && !(reinterpret_cast<uintptr_t>(out_bf16) & 7) &&
+                         (!ln_w || (!(reinterpret_cast<uintptr_t>(ln_w) & 15) && !(reinterpret_cast<uintptr_t>(ln_b) & 15)));
+    cudaStream_t st = STREAM;
+    if (aligned && k <= 4 && stride <= 4) {
+      if (Cin == 1 && Cout == 4 && Ho % 16 == 0 && Wo % 16 == 0)
+        return launch_conv_tile<1, 4>(x, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32, ob, B, H, W, k, stride, pad, Ho, Wo, st);
+      if (Cin == 4 && Cout == 16 && Ho % 8 == 0 && Wo % 8 == 0)
+        return launch_conv_tile<4, 16>(x, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32, ob, B, H, W, k, stride, pad, Ho, Wo, st);
+      if (Cin == 16 && Cout == 64 && Ho % 4 == 0 && Wo % 4 == 0)
+        return launch_conv_tile<16, 64>(x, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32, ob, B, H, W, k, stride, pad, Ho, Wo, st);
+    }
+  }
   const long long pixels = (long long)B * Ho * Wo;
   const int ppw = Cout < 32 ? 32 / Cout : 1;
   const int grid = (int)max(1LL, min((long long)148 * 8, (pixels + 8LL * ppw - 1) / (8LL * ppw)));

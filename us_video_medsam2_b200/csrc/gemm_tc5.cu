@@ -720,7 +720,7 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
   }
   int bn = block_n;
   if (bn < 0) return launch_persistent(A, lda, W, ldw, ep, M, N, K, bn == -1 ? persistent_block_n(N) : -bn, s);
-  if (bn == 0 && (long long)cdiv(M, BM) * cdiv(N, 128) >= 2 * 148)  // throughput-bound: more than one wave of tiles
+  if (bn == 0 && (long long)cdiv(M, BM) * cdiv(N, 128) >= 148)  // throughput-bound: a full wave of 128 x 128 tiles or more
     return launch_persistent(A, lda, W, ldw, ep, M, N, K, persistent_block_n(N), s);
   if (bn <= 0) {
     // latency-bound shapes dominate this path: prefer enough CTAs to cover the 148 SMs, then wider tiles

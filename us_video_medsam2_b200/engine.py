@@ -371,8 +371,11 @@ class Engine:
         for li, L in enumerate(w.ma_layers):
             _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
             _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
+            # 1024 keys are 16 key tiles: with one or two objects the mma.sync kernel (64-row query tiles, so twice the
+            # CTAs per split) beats the tcgen05 kernel, whose fixed prologue / epilogue dominates such short ranges
+            sa_impl, sa_splits = ("mma", max(1, 8 // B)) if B <= 2 else (None, self._splits(B, T))
             o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
-                         (512, T * 768, 768, 256), num_splits=self._splits(B, T))
+                         (512, T * 768, 768, 256), num_splits=sa_splits, impl=sa_impl)
             # out-projection + residual and the next sub-block's LayerNorm in one launch (whole rows per tile)
             x, h = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True,
                                  ln=(L["n2"][0], L["n2"][1], 1e-5))
