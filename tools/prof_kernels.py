@@ -56,5 +56,15 @@ if which == "chain":  # nine identical small LINEAR steps in one cluster launch 
     steps = [ops.chain_linear(bufs[i & 1], w, b, bufs[(i + 1) & 1][:, :128], o_rs=256) for i in range(9)]
     for _ in range(4):
         ops.token_chain(steps, 1, x, cluster=8)
+if which == "frames":  # a short clip without CUDA graphs: every kernel of a tracked frame shows up in the launch list
+    from us_video_medsam2_b200 import synth
+    from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
+    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=8, use_cuda_graphs=False)
+    pred.load_state_dict(synth.make_state_dict(19), strict=True)
+    clip = ops.normalize_gray_u8(synth.make_clip_u8(12, seed=1).to(dev), synth.IMG_MEAN, synth.IMG_STD)
+    st = pred.init_state(clip, 512, 512)
+    pred.add_new_mask(st, 0, 1, synth.box_mask())
+    for _ in pred.propagate_in_video(st):
+        pass
 torch.cuda.synchronize()
 print("done")

@@ -48,6 +48,18 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_shared_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 __host__ __device__ constexpr int tmem_cols(int bn) { return bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256; }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -128,7 +140,8 @@ template <int BN, bool TF32>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
-                     const usvm_gemm_epilogue ep, const int M, const int N, const int K, const int stages) {
+                     const usvm_gemm_epilogue ep, const int M, const int N, const int K, const int stages,
+                     const int ksplit) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using L = SmemLayout<BN>;
@@ -137,13 +150,20 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  // split-K (ksplit CTAs of one cluster share an output tile, blockIdx.z = k-slice): the leader (slice 0) receives the
+  // other slices' accumulators here through distributed shared memory; [slice - 1][column / 4][row] float4
+  float4* partials = reinterpret_cast<float4*>(staging + STG_BYTES + 256);  // past the barrier block
+  const int kslice = blockIdx.z;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x;
   const int tile_n = blockIdx.y;
   constexpr int BKE = TF32 ? BK / 2 : BK;  // elements per k-block (128 bytes)
-  const int num_kb = (K + BKE - 1) / BKE;
+  const int num_kb_all = (K + BKE - 1) / BKE;
+  const int kb_per = (num_kb_all + ksplit - 1) / ksplit;
+  const int kb_lo = kslice * kb_per;
+  const int num_kb = max(0, min(num_kb_all, kb_lo + kb_per) - kb_lo);  // k-blocks of this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -175,11 +195,12 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint8_t* a_dst = smem + s * L::STAGE_BYTES;
         uint8_t* b_dst = a_dst + L::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BKE, tile_m * BM);
-        tma_load_2d(b_dst, &tmB, &full_bar[s], kb * BKE, tile_n * BN);
+        tma_load_2d(a_dst, &tmA, &full_bar[s], (kb_lo + kb) * BKE, tile_m * BM);
+        tma_load_2d(b_dst, &tmB, &full_bar[s], (kb_lo + kb) * BKE, tile_n * BN);
       }
     }
     __syncwarp();
+    if (ksplit > 1) cluster_sync_all();
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_bf16(BM, BN);
@@ -207,6 +228,7 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc5_commit(tmem_full_bar);  // accumulator complete
     }
     __syncwarp();
+    if (ksplit > 1) cluster_sync_all();
   } else {
     // ---- epilogue: thread <-> accumulator row; warp <-> 32-row slab written by TMA ----
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, 32*lane_grp + 32) are visible to this warp
@@ -235,10 +257,28 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     float ln_sum = 0.f;
     mbar_wait(tmem_full_bar, 0);
     tc5_fence_after();
+    if (ksplit > 1) {
+      if (kslice > 0) {  // hand this slice's accumulator to the leader CTA of the cluster
+        const uint32_t remote = mapa_shared(smem_u32(partials), 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t acc[32];
+          tc5_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
+          tc5_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            st_shared_cluster_v4(remote + (uint32_t)((((kslice - 1) * (BN / 4) + (c0 >> 2) + c) * BM + lane_grp * 32 + lane) * 16),
+                                 acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        }
+      }
+      tc5_fence_before();
+      cluster_sync_all();  // release / acquire at cluster scope: the partials are visible to the leader
+      tc5_fence_after();
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int col0 = tile_n * BN + c0;
-      if (col0 >= N || row0 >= M) break;  // warp-uniform
+      if (col0 >= N || row0 >= M || kslice > 0) break;  // warp-uniform
       uint32_t acc[32];
       tc5_ld_32x32(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
       float4 rn[8];
@@ -247,6 +287,13 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+      for (int sl = 0; sl + 1 < ksplit; ++sl) {  // split-K: add the other slices (fixed order: deterministic)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 pv = partials[((sl * (BN / 4) + (c0 >> 2) + c) * BM) + lane_grp * 32 + lane];
+          v[4 * c] += pv.x; v[4 * c + 1] += pv.y; v[4 * c + 2] += pv.z; v[4 * c + 3] += pv.w;
+        }
+      }
       epilogue_block(v, ep, row, row_ok, rrow, col0, N, !have);
       if (have) {
 #pragma unroll
@@ -602,7 +649,7 @@ int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long 
 
 template <int BN, bool TF32>
 int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
-           cudaStream_t stream) {
+           cudaStream_t stream, int ksplit = 1) {
   CUtensorMap tmA, tmB, tmO32, tmO16;
   int rc = TF32 ? make_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_128B)
                 : make_map_bf16(&tmA, A, M, K, lda, BM);
@@ -624,7 +671,7 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
   }
   static bool attr_set = false;
   if (!attr_set) {
-    const int want = SmemLayout<BN>::total(STAGES) < 227 * 1024 ? SmemLayout<BN>::total(STAGES) : 227 * 1024;
+    const int want = 227 * 1024;  // ring + staging (+ split-K partials) are sized per launch, always below this
     if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) !=
         cudaSuccess)
       return USVM_ERR_CUDA;
@@ -636,11 +683,36 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
   // k-loop then streams at TMA issue rate instead of TMA latency); big problems keep <= 4 stages so that 2-3 CTAs
   // share an SM and overlap each other's epilogues.
   const long long ctas = (long long)grid.x * grid.y;
-  int max_stages = ctas <= 2 * 148 ? STAGES : 4;
-  while (max_stages > 1 && SmemLayout<BN>::total(max_stages) > 200 * 1024) --max_stages;
-  const int stages = num_kb < max_stages ? num_kb : max_stages;
-  usvm_launch(gemm_bf16_tc5_kernel<BN, TF32>, dim3(grid), dim3(GEMM_THREADS), SmemLayout<BN>::total(stages), stream, tmA, tmB, tmO32, tmO16, *ep, M,
-                                                                                         N, K, stages);
+  int max_stages = ctas * ksplit <= 2 * 148 ? STAGES : 4;
+  const int part_bytes = ksplit > 1 ? 256 + (ksplit - 1) * BM * BN * 4 : 0;
+  while (max_stages > 1 && SmemLayout<BN>::total(max_stages) + part_bytes > 200 * 1024) --max_stages;
+  const int kb_per = cdiv(num_kb, ksplit);
+  const int stages = kb_per < max_stages ? kb_per : max_stages;
+  const size_t smem = SmemLayout<BN>::total(stages) + part_bytes;
+  if (ksplit == 1) {
+    usvm_launch(gemm_bf16_tc5_kernel<BN, TF32>, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmO32, tmO16, *ep,
+                M, N, K, stages, 1);
+    return usvm_check_launch();
+  }
+  // split-K: the ksplit CTAs of an output tile form a thread-block cluster along z
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid.x, grid.y, ksplit);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = ksplit;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = usvm_pdl_enabled() ? 2 : 1;
+  if (cudaLaunchKernelEx(&cfg, gemm_bf16_tc5_kernel<BN, TF32>, tmA, tmB, tmO32, tmO16, *ep, M, N, K, stages, ksplit) !=
+      cudaSuccess)
+    return USVM_ERR_CUDA;
   return usvm_check_launch();
 }
 
@@ -726,14 +798,24 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
     // latency-bound shapes dominate this path: prefer enough CTAs to cover the 148 SMs, then wider tiles
     const int mt = cdiv(M, BM);
     bn = 128;  // 128-wide tiles leave room for 2-3 CTAs per SM (TMEM 128 columns, <= 80 KB smem with short K)
-    while (bn > 32 && (long long)mt * cdiv(N, bn) < 148) bn >>= 1;
+    while (bn > 32 && (long long)mt * cdiv(N, bn) < 96) bn >>= 1;  // measured: 128 CTAs of 128x128 beat 256 of 128x64
     if (N <= 32) bn = 32;
     else if (N <= 64 && bn > 64) bn = 64;
     else if (N <= 128 && bn > 128) bn = 128;
   }
+  // long reductions on few tiles (the FFN's second linear: K = 2048 on 64 tiles): split K over a cluster of 2 or 4 CTAs
+  int ksplit = 1;
+  if (block_n <= 0 || block_n == bn) {
+    const long long ctas = (long long)cdiv(M, BM) * cdiv(N, bn);
+    const int num_kb = cdiv(K, BK);
+    // (N <= 256 keeps every image-encoder GEMM out: its results must not depend on how many frames are batched)
+    if (!ep->ln_w && bn <= 64 && N <= 256 && ctas <= 74 && num_kb >= 16)
+      ksplit = (num_kb >= 32 && ctas * 4 <= 2 * 148) ? 4 : 2;
+    if (const char* e = getenv("USVM2_GEMM_KSPLIT")) ksplit = (e[0] == '0' || e[0] == '1') ? 1 : ksplit;
+  }
   switch (bn) {
-    case 32: return launch<32, false>(A, lda, W, ldw, ep, M, N, K, s);
-    case 64: return launch<64, false>(A, lda, W, ldw, ep, M, N, K, s);
+    case 32: return launch<32, false>(A, lda, W, ldw, ep, M, N, K, s, ksplit);
+    case 64: return launch<64, false>(A, lda, W, ldw, ep, M, N, K, s, ksplit);
     case 128: return launch<128, false>(A, lda, W, ldw, ep, M, N, K, s);
     case 256: return launch<256, false>(A, lda, W, ldw, ep, M, N, K, s);
     default: return USVM_ERR_ARG;
