@@ -795,10 +795,18 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
   if (bn == 0 && (long long)cdiv(M, BM) * cdiv(N, 128) >= 148)  // throughput-bound: a full wave of 128 x 128 tiles or more
     return launch_persistent(A, lda, W, ldw, ep, M, N, K, persistent_block_n(N), s);
   if (bn <= 0) {
-    // latency-bound shapes dominate this path: prefer enough CTAs to cover the 148 SMs, then wider tiles
-    const int mt = cdiv(M, BM);
-    bn = 128;  // 128-wide tiles leave room for 2-3 CTAs per SM (TMEM 128 columns, <= 80 KB smem with short K)
-    while (bn > 32 && (long long)mt * cdiv(N, bn) < 96) bn >>= 1;  // measured: 128 CTAs of 128x128 beat 256 of 128x64
+    // latency-bound shapes: the narrowest tile (most CTAs) that still runs as a single wave -- a second wave costs a
+    // whole extra tile time.  Slots per SM follow from the shared memory of the k-deep ring (<= 2 by launch bounds).
+    const int mt = cdiv(M, BM), num_kb = cdiv(K, BK);
+    const int ring = num_kb < STAGES ? num_kb : STAGES;
+    auto one_wave = [&](int b, int total_smem) {
+      const int occ = total_smem * 2 <= 227 * 1024 ? 2 : 1;
+      return (long long)mt * cdiv(N, b) <= 148LL * occ;
+    };
+    bn = 128;
+    if (one_wave(32, SmemLayout<32>::total(ring))) bn = 32;
+    else if (one_wave(64, SmemLayout<64>::total(ring))) bn = 64;
+    if (num_kb >= 32 && N >= 64 && bn == 32) bn = 64;  // long K: halve the re-reads of A (split-K restores the CTA count)
     if (N <= 32) bn = 32;
     else if (N <= 64 && bn > 64) bn = 64;
     else if (N <= 128 && bn > 128) bn = 128;
