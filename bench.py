@@ -307,7 +307,8 @@ def run_b200(args, rank, world):
                                    f"{B} object(s), 7-frame memory bank, mask prompt on frame 0",
                        "frames": T, "objects": B, "encoder_batch": args.encoder_batch, "parallelism": f"videos x{world}",
                        "precision": "bf16 tensor-core contractions (encoder / memory attention / memory encoder), "
-                                    "fp32 mask decoder",
+                                    "fp32-operand mask decoder (tf32 tensor-core products on its image-side GEMMs, "
+                                    "exact fp32 on the token side)",
                        "l2": f"inputs larger than L2: {T * 3 * 512 * 512 * 4 / 1e6:.0f} MB clip streamed once per step"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": T * 512 * 512,
                     "d2h_bytes_per_step": T * B * 512 * 512},

@@ -109,6 +109,9 @@ typedef struct usvm_fmha_params {
   float* o_part;              /* fp32 [num_splits, B*H, Nq, head_dim] when num_splits > 1 */
   float* ml_part;             /* fp32 [num_splits, B*H, Nq, 2] */
   float scale;                /* 1/sqrt(head_dim) */
+  int part_bf16;              /* 1: o_part holds bf16 instead of fp32 (usvm_fmha_tc5 TS variant + usvm_fmha_combine only):
+                                 halves the L2 traffic of the split partials; each partial is rounded once, like the
+                                 bf16 output itself */
 } usvm_fmha_params;
 int usvm_fmha_bf16(const usvm_fmha_params* p_host, void* stream);
 /* tcgen05 / TMEM / TMA flash attention for the memory-attention shapes: head_dim 256, H == 1, Nq % 128 == 0, batches
@@ -251,6 +254,7 @@ typedef struct usvm_skinny_params {
   float* out;
   long long o_is, o_rs;
   int M, N, K, instances, act;
+  int x2_cols; /* x2 is added for output columns < x2_cols only (a multiple of 4); 0 or >= N: for all columns */
 } usvm_skinny_params;
 int usvm_gemm_skinny_f32(const usvm_skinny_params* p_host, void* stream);
 /* token -> image attention (transformer.py:194-198): q [B*Nt, H*16], k/v rows of stride kv_rs, Nt <= 16 */

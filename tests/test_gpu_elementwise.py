@@ -311,6 +311,9 @@ def test_skinny_gemm_and_decoder_attention():
     w = torch.randn((2048, 256), generator=g, device="cuda") / 16
     b = torch.randn(2048, generator=g, device="cuda")
     got = ops.gemm_skinny(x, w, b, x2=x2, act=ops.ACT_RELU)
+    part = ops.gemm_skinny(x, w, b, x2=x2, x2_cols=8)  # positional add on the first 8 output columns only
+    want_part = torch.cat([(x + x2) @ w[:8].t(), x @ w[8:].t()], dim=1) + b
+    assert (part - want_part).abs().max().item() < 1e-4
     want = F.relu((x + x2) @ w.t() + b)
     assert (got - want).abs().max().item() < 1e-4
     w2 = torch.randn((256, 2048), generator=g, device="cuda") / 45

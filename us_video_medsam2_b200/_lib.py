@@ -32,7 +32,8 @@ class FmhaParams(C.Structure):
                 ("q_rs", C.c_int), ("k_rs", C.c_int), ("v_rs", C.c_int), ("o_rs", C.c_int),
                 ("q_hs", C.c_int), ("k_hs", C.c_int), ("v_hs", C.c_int), ("o_hs", C.c_int),
                 ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("head_dim", C.c_int),
-                ("num_splits", C.c_int), ("o_part", C.c_void_p), ("ml_part", C.c_void_p), ("scale", C.c_float)]
+                ("num_splits", C.c_int), ("o_part", C.c_void_p), ("ml_part", C.c_void_p), ("scale", C.c_float),
+                ("part_bf16", C.c_int)]
 
 
 MAX_PTRS = 32
@@ -45,7 +46,8 @@ class SkinnyParams(C.Structure):
                 ("w", C.c_void_p), ("w_is", C.c_longlong), ("bias", C.c_void_p), ("b_is", C.c_longlong),
                 ("residual", C.c_void_p), ("r_is", C.c_longlong), ("r_rs", C.c_longlong),
                 ("out", C.c_void_p), ("o_is", C.c_longlong), ("o_rs", C.c_longlong),
-                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("instances", C.c_int), ("act", C.c_int)]
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("instances", C.c_int), ("act", C.c_int),
+                ("x2_cols", C.c_int)]
 
 
 CHAIN_MAX_STEPS = 10

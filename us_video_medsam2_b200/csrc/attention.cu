@@ -272,10 +272,23 @@ fmha_combine_kernel(const usvm_fmha_params p) {
   for (int s0 = 0; s0 < COMBINE_MAX_SPLITS; s0 += 8) {
     if (s0 < ns) {
       float4 o[8];
+      if (p.part_bf16) {
+        const bf16* opb = reinterpret_cast<const bf16*>(p.o_part) + row * D + c4;
+        uint2 raw[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        o[u] = s0 + u < ns ? __ldg(reinterpret_cast<const float4*>(op + (long long)(s0 + u) * ostride))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < 8; ++u)
+          raw[u] = s0 + u < ns ? __ldg(reinterpret_cast<const uint2*>(opb + (long long)(s0 + u) * ostride)) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float2 lo = unpack_bf16x2(raw[u].x), hi = unpack_bf16x2(raw[u].y);
+          o[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          o[u] = s0 + u < ns ? __ldg(reinterpret_cast<const float4*>(op + (long long)(s0 + u) * ostride))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float2 m = ml[s0 + u];
@@ -367,7 +380,7 @@ attn_small_f32_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 extern "C" int usvm_fmha_bf16(const usvm_fmha_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->o || p->B <= 0 || p->H <= 0 || p->Nq <= 0 || p->Nk <= 0)
     return USVM_ERR_ARG;
-  if (p->num_splits < 1 || p->num_splits > COMBINE_MAX_SPLITS) return USVM_ERR_ARG;
+  if (p->num_splits < 1 || p->num_splits > COMBINE_MAX_SPLITS || p->part_bf16) return USVM_ERR_ARG;
   if (p->num_splits > 1 && (!p->o_part || !p->ml_part)) return USVM_ERR_ARG;
   if (p->num_splits > cdiv(p->Nk, FN)) return USVM_ERR_ARG;
   if ((p->q_rs % 8) || (p->k_rs % 8) || (p->v_rs % 8) || (p->o_rs % 2) || (p->q_hs % 8) || (p->k_hs % 8) ||

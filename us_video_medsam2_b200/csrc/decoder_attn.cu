@@ -23,16 +23,21 @@ template <int KSPLIT>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const usvm_skinny_params p) {
   PDL_ENTRY();
-  extern __shared__ __align__(16) float xs[];  // [rows][K] (+ [8][32] partials when KSPLIT > 1)
+  extern __shared__ __align__(16) float xs[];  // [8][K] x + x2, [8][32] partials, then [8][K] plain x when x2_cols < N
   const int inst = blockIdx.y;
   const int m0 = blockIdx.z * SK_ROWS;
   const int rows = min(SK_ROWS, p.M - m0);
   const int K = p.K, K4 = K >> 2;
+  // x2 (the positional tokens) applies to output columns < x2_cols only: projections that read `queries + pe` and
+  // projections that read `queries` share one launch, with both variants of the input staged
+  const bool two = p.x2 && p.x2_cols > 0 && p.x2_cols < p.N;
+  float* xs_plain = xs + SK_ROWS * K + SK_WARPS * 32;
   for (int i = threadIdx.x; i < rows * K4; i += blockDim.x) {
     const int m = i / K4, k = (i - m * K4) << 2;
     const long long sel = p.row_select ? (long long)p.row_select[m0 + m] * p.x_sel_stride : 0;
     const float* xp = p.x + (long long)inst * p.x_is + (long long)(m0 + m) * p.x_rs + sel + k;
     float4 v = make_float4(xp[0], xp[1], xp[2], xp[3]);
+    if (two) *reinterpret_cast<float4*>(xs_plain + m * K + k) = v;
     if (p.x2) {
       const float* x2 = p.x2 + (long long)inst * p.x2_is + (long long)(m0 + m) * p.x2_rs + k;
       v.x += x2[0]; v.y += x2[1]; v.z += x2[2]; v.w += x2[3];
@@ -49,6 +54,7 @@ gemm_skinny_kernel(const usvm_skinny_params p) {
     for (int m = 0; m < SK_ROWS; ++m) acc[c][m] = 0.f;
   if (n0 < p.N) {
     const float* Wb = p.w + (long long)inst * p.w_is;
+    const float* xin = (two && n0 >= p.x2_cols) ? xs_plain : xs;
     const int kchunk = KSPLIT == 1 ? K : (((K + KSPLIT - 1) / KSPLIT + 3) & ~3);
     const int kbeg = KSPLIT == 1 ? 0 : warp * kchunk;
     const int kend = min(K, kbeg + kchunk);
@@ -62,7 +68,7 @@ gemm_skinny_kernel(const usvm_skinny_params p) {
 #pragma unroll
       for (int m = 0; m < SK_ROWS; ++m) {
         if (m < rows) {
-          const float4 xv = *reinterpret_cast<const float4*>(xs + m * K + k);
+          const float4 xv = *reinterpret_cast<const float4*>(xin + m * K + k);
 #pragma unroll
           for (int c = 0; c < SK_COLS; ++c)
             acc[c][m] += xv.x * wv[c].x + xv.y * wv[c].y + xv.z * wv[c].z + xv.w * wv[c].w;
@@ -376,7 +382,8 @@ attn_i2t_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__
 extern "C" int usvm_gemm_skinny_f32(const usvm_skinny_params* p, void* stream) {
   if (!p || !p->x || !p->w || !p->out || p->M <= 0 || p->N <= 0 || p->K <= 0 || p->instances <= 0) return USVM_ERR_ARG;
   if ((p->K % 4) || (reinterpret_cast<uintptr_t>(p->w) & 15) || (p->w_is % 4)) return USVM_ERR_ARG;
-  const size_t smem = ((size_t)SK_ROWS * p->K + SK_WARPS * 32) * sizeof(float);
+  if (p->x2_cols % SK_COLS) return USVM_ERR_ARG;
+  const size_t smem = ((size_t)SK_ROWS * p->K * 2 + SK_WARPS * 32) * sizeof(float);
   if (smem > 200 * 1024) return USVM_ERR_ARG;
   static bool configured = false;
   if (!configured) {

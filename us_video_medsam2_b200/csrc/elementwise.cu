@@ -248,21 +248,31 @@ __global__ void upsample2_add_kernel(float* __restrict__ fine, const float* __re
 // im2col of the 7x7 / stride 4 / pad 3 patch embedding (backbones/utils.py:64-94):
 // img fp32 NCHW [F,3,S,S] -> A bf16 [F*(S/4)^2, KP], column k = c*49 + ky*7 + kx, zero beyond 147
 // ---------------------------------------------------------------------------------------------
+// one thread per 8 consecutive columns of a token row: eight scattered (L1-resident) 4-byte reads, one 16-byte store
 __global__ void im2col_patch_kernel(const float* __restrict__ img, bf16* __restrict__ A, int F, int S, int KP) {
   PDL_ENTRY();
-  const int G = S / 4;
-  const long long total = (long long)F * G * G * KP;
+  const int G = S / 4, KP8 = KP >> 3;
+  const long long total = (long long)F * G * G * KP8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % KP);
-    const long long t = i / KP;
-    float v = 0.f;
-    if (k < 147) {
-      const int ox = (int)(t % G), oy = (int)((t / G) % G), f = (int)(t / ((long long)G * G));
-      const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
-      const int y = oy * 4 - 3 + ky, x = ox * 4 - 3 + kx;
-      if (y >= 0 && y < S && x >= 0 && x < S) v = img[(((long long)f * 3 + c) * S + y) * S + x];
+    const int k0 = (int)(i % KP8) << 3;
+    const long long t = i / KP8;
+    const int ox = (int)(t % G), oy = (int)((t / G) % G), f = (int)(t / ((long long)G * G));
+    const float* base = img + (long long)f * 3 * S * S;
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int k = k0 + u;
+      v[u] = 0.f;
+      if (k < 147) {
+        const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+        const int y = oy * 4 - 3 + ky, x = ox * 4 - 3 + kx;
+        if (y >= 0 && y < S && x >= 0 && x < S) v[u] = __ldg(base + ((long long)c * S + y) * S + x);
+      }
     }
-    A[i] = __float2bfloat16(v);
+    uint4 pk;
+    pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+    pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(A + t * KP + k0) = pk;
   }
 }
 
@@ -518,8 +528,8 @@ extern "C" int usvm_upsample2_add(float* fine, const float* coarse, void* fine_b
 }
 
 extern "C" int usvm_im2col_patch(const float* img, void* A, int F, int S, int KP, void* stream) {
-  if (!img || !A || (S % 4) || KP < 147) return USVM_ERR_ARG;
-  usvm_launch(im2col_patch_kernel, dim3(grid_for((long long)F * (S / 4) * (S / 4) * KP)), dim3(256), 0, STREAM, 
+  if (!img || !A || (S % 4) || KP < 147 || (KP % 8) || (reinterpret_cast<uintptr_t>(A) & 15)) return USVM_ERR_ARG;
+  usvm_launch(im2col_patch_kernel, dim3(grid_for((long long)F * (S / 4) * (S / 4) * (KP / 8))), dim3(256), 0, STREAM, 
       img, reinterpret_cast<bf16*>(A), F, S, KP);
   return usvm_check_launch();
 }

@@ -550,6 +550,17 @@ fmha_tc5_ts_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
           v4.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
           *reinterpret_cast<uint4*>(O + i) = v4;
         }
+      } else if (p.part_bf16) {
+        bf16* OP = reinterpret_cast<bf16*>(p.o_part) + (((long long)split * gridDim.y + b) * p.Nq + row) * HD + c;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v4;
+          v4.x = pack_bf16x2(__uint_as_float(o[i]), __uint_as_float(o[i + 1]));
+          v4.y = pack_bf16x2(__uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
+          v4.z = pack_bf16x2(__uint_as_float(o[i + 4]), __uint_as_float(o[i + 5]));
+          v4.w = pack_bf16x2(__uint_as_float(o[i + 6]), __uint_as_float(o[i + 7]));
+          *reinterpret_cast<uint4*>(OP + i) = v4;
+        }
       } else {
         float* OP = p.o_part + (((long long)split * gridDim.y + b) * p.Nq + row) * HD + c;
 #pragma unroll
@@ -622,6 +633,7 @@ extern "C" int usvm_fmha_tc5(const usvm_fmha_params* p, void* stream) {
     return USVM_ERR_ARG;
   if (p->num_splits > 1 && (!p->o_part || !p->ml_part)) return USVM_ERR_ARG;
   if (p->num_splits > (p->Nk + KN - 1) / KN) return USVM_ERR_ARG;
+  if (p->part_bf16 && fmha_tc5_variant != 0) return USVM_ERR_ARG;  // only the TS kernel writes bf16 partials
   CUtensorMap tq, tk, tv;
   int rc = make_map(&tq, p->q, (long long)p->B * p->Nq, HD, p->q_rs, QM);
   if (rc) return rc;

@@ -228,6 +228,9 @@ class PackedWeights:
                                         i2t=attn(p + "cross_attn_image_to_token."),
                                         mlp=(lin(p + "mlp.layers.0."), lin(p + "mlp.layers.1.")),
                                         norms=[lin(p + f"norm{j}.") for j in (1, 2, 3, 4)]))
+        for Lyr in self.dec_layers:  # image->token attention: k and v projections of the tokens as one [256, 256] matrix
+            Lyr["i2t"]["kv_w"] = torch.cat([Lyr["i2t"]["k"][0], Lyr["i2t"]["v"][0]]).contiguous()
+            Lyr["i2t"]["kv_b"] = torch.cat([Lyr["i2t"]["k"][1], Lyr["i2t"]["v"][1]]).contiguous()
         self.dec_final = attn(tr + "final_attn_token_to_image.")
         self.dec_final_norm = lin(tr + "norm_final_attn.")
         # token-chain packing: the projections that read the queries leaving a layer share one step -- columns that take
@@ -498,9 +501,9 @@ class Engine:
                 o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
                 queries = sk(o, *sa["o"])
             else:
-                qk = sk(queries, sa["qkv_w"][:512], sa["qkv_b"][:512], x2=tokens)
-                v = sk(queries, *sa["v"])
-                o = ops.attn_small(qk[:, 0:256], qk[:, 256:512], v, B, 8, Nt, Nt, 32)
+                # q, k read queries + token_pe, v reads queries: one launch, the positional add limited to 512 columns
+                qkv = sk(queries, sa["qkv_w"], sa["qkv_b"], x2=tokens, x2_cols=512)
+                o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
                 queries = sk(o, *sa["o"], residual=queries)
             queries = ln(queries, Lyr["norms"][0])
             q = sk(queries, *t2i["q"], x2=tokens)
@@ -509,9 +512,8 @@ class Engine:
             queries = ln(sk(o, *t2i["o"], residual=queries), Lyr["norms"][1])
             m = sk(queries, *Lyr["mlp"][0], act=ACT_RELU)
             queries = ln(sk(m, *Lyr["mlp"][1], residual=queries), Lyr["norms"][2])
-            k2 = sk(queries, *i2t["k"], x2=tokens)
-            v2 = sk(queries, *i2t["v"])
-            o = ops.attn_i2t(img[:, 256:384], k2, v2, B, T, Nt)
+            kv2 = sk(queries, i2t["kv_w"], i2t["kv_b"], x2=tokens, x2_cols=128)  # [k (with pe) | v]
+            o = ops.attn_i2t(img[:, 256:384], kv2[:, 0:128], kv2[:, 128:256], B, T, Nt)
             keys = ln(ops.gemm_f32(o, *i2t["o"], residual=keys, tf32=True), Lyr["norms"][3])
         fin = w.dec_final
         q = sk(queries, *fin["q"], x2=tokens)

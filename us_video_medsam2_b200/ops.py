@@ -120,6 +120,7 @@ def gemm_f32(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_m
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
+_FMHA_PART_BF16 = os.environ.get("USVM2_FMHA_PART_BF16", "1") != "0"
 _FMHA_IMPL = os.environ.get("USVM2_FMHA", "tc5")  # "tc5" (tcgen05 where the shape allows) | "mma" (mma.sync only)
 
 
@@ -141,16 +142,17 @@ def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_
     p.B, p.H, p.Nq, p.Nk, p.head_dim = B, H, Nq, Nk, head_dim
     num_splits = max(1, min(num_splits, (Nk + 63) // 64))
     p.num_splits = num_splits
-    if num_splits > 1:
-        o_part = empty((num_splits, B * H, Nq, head_dim), F32, q)
-        ml_part = empty((num_splits, B * H, Nq, 2), F32, q)
-        p.o_part, p.ml_part = o_part.data_ptr(), ml_part.data_ptr()
     p.scale = 1.0 / math.sqrt(head_dim)
     which = impl or _FMHA_IMPL
     if which in ("tc5", "tc5ss"):
         _lib.lib().usvm_fmha_tc5_set_variant(1 if which == "tc5ss" else 0)
     use_tc5 = (which in ("tc5", "tc5ss") and head_dim == 256 and H == 1 and Nq % 128 == 0
                and q_addr[1] == Nq * q_addr[2] and k_addr[1] == Nk * k_addr[2] and v_addr[1] == Nk * v_addr[2])
+    if num_splits > 1:
+        p.part_bf16 = int(use_tc5 and which == "tc5" and _FMHA_PART_BF16)  # split partials in bf16 (TS kernel only)
+        o_part = empty((num_splits, B * H, Nq, head_dim), BF16 if p.part_bf16 else F32, q)
+        ml_part = empty((num_splits, B * H, Nq, 2), F32, q)
+        p.o_part, p.ml_part = o_part.data_ptr(), ml_part.data_ptr()
     if use_tc5:
         call("usvm_fmha_tc5", C.byref(p), _stream())
         if num_splits > 1:
@@ -432,7 +434,8 @@ def small_mlp3(x_ptr, x_row_stride, x_inst_stride, row_select, mlp, out_dim, row
 
 
 def gemm_skinny(x, w, bias=None, M=None, x_rs=None, x_is=0, x2=None, x2_rs=None, x2_is=0, act=ACT_NONE,
-                residual=None, r_rs=None, r_is=0, instances=1, row_select=None, x_sel_stride=0, x_ptr=None, out=None):
+                residual=None, r_rs=None, r_is=0, instances=1, row_select=None, x_sel_stride=0, x_ptr=None, out=None,
+                x2_cols=0):
     """fp32 GEMM for a few rows: out[i, m, :] = act((x + x2)[i, m] @ w[i].T + bias[i]) + residual[i, m].
     x: tensor [M, K] (or raw address via x_ptr with explicit strides); w: [N, K] or [instances, N, K]."""
     N, K = w.shape[-2], w.shape[-1]
@@ -455,6 +458,7 @@ def gemm_skinny(x, w, bias=None, M=None, x_rs=None, x_is=0, x2=None, x2_rs=None,
     p.r_is = r_is
     p.out, p.o_rs, p.o_is = out.data_ptr(), out.stride(0), (N if instances > 1 else 0)
     p.M, p.N, p.K, p.instances, p.act = M, N, K, instances, act
+    p.x2_cols = x2_cols  # x2 only for output columns < x2_cols (0: all)
     call("usvm_gemm_skinny_f32", C.byref(p), _stream())
     return out
 
