@@ -114,6 +114,12 @@ typedef struct usvm_fmha_params {
                                  bf16 output itself */
 } usvm_fmha_params;
 int usvm_fmha_bf16(const usvm_fmha_params* p_host, void* stream);
+/* Fused Hiera window attention for windows of <= 64 keys (hieradet.py:46-95 + backbones/utils.py:17-58): window
+ * partition, QKV split, optional 2x2 query max-pool, attention per (window, head of 96) and window un-partition in one
+ * kernel.  qkv bf16 [F, Hg, Wg, 3*C] raster order (C = heads*96), qkv_bias fp32 [3*C] (value of the tokens in the zero
+ * padding of partial windows), out bf16 [F, Ho, Wo, C] raster order (Ho = Hg/2 when pool). */
+int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, void* out, int F, int Hg, int Wg, int ws, int pool,
+                          int C, int heads, void* stream);
 /* tcgen05 / TMEM / TMA flash attention for the memory-attention shapes: head_dim 256, H == 1, Nq % 128 == 0, batches
  * contiguous (x_bs == N * x_rs).  S = QK^T (double buffered) and O accumulate in TMEM, V is consumed in place as an
  * MN-major operand.  With num_splits > 1 it writes partials only: follow with usvm_fmha_combine. */

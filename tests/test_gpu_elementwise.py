@@ -202,6 +202,31 @@ def test_im2col_nhwc_and_dwconv():
     assert (out.float().view_as(y) - y).abs().max().item() < 5e-2
 
 
+@pytest.mark.parametrize("Hg,ws,pool,heads", [(64, 8, False, 1), (64, 8, True, 2), (32, 4, False, 2), (32, 4, True, 4),
+                                              (16, 7, False, 8), (24, 8, True, 5), (20, 6, False, 1)])
+def test_fused_window_attention(Hg, ws, pool, heads):
+    """One-kernel window attention == gather -> flash attention -> scatter (the generic path), incl. partial windows
+    (bias-valued padding tokens), pooled queries and more heads than one shared-memory pass holds."""
+    from us_video_medsam2_b200 import ops
+
+    Fr, C = 2, heads * 96
+    g = _g(Hg * 3 + ws)
+    qkv = torch.randn((Fr * Hg * Hg, 3 * C), generator=g, device="cuda").to(BF)
+    bias = torch.randn(3 * C, generator=g, device="cuda")
+    got = ops.window_attn(qkv, bias, Fr, Hg, Hg, ws, pool, C, heads)
+    Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, bias, Fr, Hg, Hg, ws, pool, C)
+    Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * C, C, 96), (0, nk * C, C, 96), (0, nk * C, C, 96))
+    Ho = Hg // 2 if pool else Hg
+    want = ops.window_scatter(Ow, Fr, Ho, Ho, ws // 2 if pool else ws, C)
+    # same bf16 inputs, fp32 accumulation, bf16 output: differences are summation order only
+    assert (got.float() - want.float()).abs().max().item() < 2e-2
+    # and against plain fp32 attention on the gathered windows
+    q, k, v = (t.float().view(Fr * nw, -1, heads, 96).transpose(1, 2) for t in (Qw, Kw, Vw))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 96 ** 0.5, dim=-1) @ v).transpose(1, 2).reshape(Fr * nw, nq, C)
+    ref = ops.window_scatter(ref.to(BF).contiguous(), Fr, Ho, Ho, ws // 2 if pool else ws, C)
+    assert (got.float() - ref.float()).abs().max().item() < 3e-2
+
+
 @pytest.mark.parametrize("Hi,Ho", [(128, 512), (128, 360), (512, 128), (100, 37)])
 def test_resize_bilinear(Hi, Ho):
     from us_video_medsam2_b200 import ops

@@ -127,6 +127,7 @@ _SIGNATURES = {
     "usvm_build_memory_store": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "usvm_store_outputs": [_P, _P, _P, _I, _P, _I, _I, _I, _P],
     "usvm_small_mlp3": [_P, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _LL, _LL, _I, _I, _P],
+    "usvm_window_attn_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "usvm_gemm_skinny_f32": [C.POINTER(SkinnyParams), _P],
     "usvm_token_chain": [C.POINTER(ChainParams), _P],
     "usvm_attn_t2i_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],

@@ -1,0 +1,245 @@
+// Fused Hiera window attention for the small windows (<= 64 keys): window partition, QKV split, optional 2x2 max-pool
+// of the queries, per-(window, head) attention and window un-partition in ONE kernel, reading the raster-order fused qkv
+// tensor in place and writing the raster-order output (hieradet.py:46-95 MultiScaleAttention / MultiScaleBlock,
+// backbones/utils.py:17-58 window_partition / window_unpartition).
+//
+// The generic path (usvm_window_gather -> usvm_fmha_bf16 -> usvm_window_scatter) moves q, k and v through HBM twice
+// more than necessary and runs a 64 x 64-tile flash kernel on 16 x 16 problems; for the four stage-1/2 blocks that is
+// 487 us per 8-frame pass against ~70 us of unavoidable traffic.  Here one CTA owns one window:
+//   * rows of q / k / v are fetched with cp.async straight from qkv[f, y, x, which*C + h*96 ...]; tokens that fall into
+//     the zero padding of a partial window carry qkv = bias (the reference pads after norm1, before the qkv Linear);
+//     pooled queries are the element-wise max of their 2 x 2 source tokens;
+//   * a work unit is (head, 16-query slab): S = Q K^T with mma.sync m16n8k16 bf16 over <= 64 keys in registers, row
+//     softmax in base 2, O = P V with P re-used as the A fragment (FlashAttention-2 register pipeline, one key tile);
+//   * the slab's rows go back to out[f, oy, ox, h*96 ...] -- raster order, padding rows dropped.
+// Heads are processed in passes of 4 (shared memory: 3 x 64 x (4*96 + 8) bf16 = 147 KB).
+#include "common.cuh"
+#include "usvm2_b200.h"
+
+namespace {
+
+constexpr int WA_THREADS = 128;
+constexpr int WA_ROWS = 64;  // max keys (and max queries) per window
+constexpr int WA_D = 96;     // Hiera head dim
+constexpr int WA_HC = 4;     // heads per pass
+
+__device__ __forceinline__ void wa_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void wa_ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void wa_ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void wa_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint4 bias_chunk(const float* b) {  // 8 fp32 -> 8 bf16
+  uint4 u;
+  u.x = pack_bf16x2(b[0], b[1]); u.y = pack_bf16x2(b[2], b[3]);
+  u.z = pack_bf16x2(b[4], b[5]); u.w = pack_bf16x2(b[6], b[7]);
+  return u;
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  const float2 x = unpack_bf16x2(a), y = unpack_bf16x2(b);
+  return pack_bf16x2(fmaxf(x.x, y.x), fmaxf(x.y, y.y));
+}
+
+// one (head, 16-query slab) unit; NKT = key n-tiles of 8 (2 -> 16 keys, 8 -> up to 64 keys)
+template <int NKT>
+__device__ __forceinline__ void attend_unit(const bf16* sQ, const bf16* sK, const bf16* sV, int LD, int hoff, int slab,
+                                            int nk, float sl2, float (&o)[WA_D / 8][4], float (&inv)[2]) {
+  const int lane = threadIdx.x & 31, t = lane & 3;
+  float s[NKT][4];
+#pragma unroll
+  for (int i = 0; i < NKT; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < WA_D / 16; ++ks) {
+    uint32_t a[4];
+    wa_ldsm_x4(a, sQ + (slab * 16 + (lane & 15)) * LD + hoff + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int nt = 0; nt < NKT; nt += 2) {
+      uint32_t kb[4];
+      wa_ldsm_x4(kb, sK + (nt * 8 + (lane & 7) + (lane >> 4) * 8) * LD + hoff + ks * 16 + ((lane >> 3) & 1) * 8);
+      wa_mma(s[nt], a, kb[0], kb[1]);
+      wa_mma(s[nt + 1], a, kb[2], kb[3]);
+    }
+  }
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < NKT; ++nt) {
+    const int kc = nt * 8 + 2 * t;
+    if (kc >= nk) s[nt][0] = s[nt][2] = -INFINITY;
+    if (kc + 1 >= nk) s[nt][1] = s[nt][3] = -INFINITY;
+    mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+    mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+  uint32_t pf[NKT / 2][4];
+  float rs[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < NKT; ++nt) {
+    const float p0 = exp2f((s[nt][0] - mx[0]) * sl2);
+    const float p1 = exp2f((s[nt][1] - mx[0]) * sl2);
+    const float p2 = exp2f((s[nt][2] - mx[1]) * sl2);
+    const float p3 = exp2f((s[nt][3] - mx[1]) * sl2);
+    rs[0] += p0 + p1;
+    rs[1] += p2 + p3;
+    pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+    pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+    rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+    inv[r] = 1.0f / rs[r];  // at least one key is valid
+  }
+#pragma unroll
+  for (int i = 0; i < WA_D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < NKT / 2; ++kk) {
+#pragma unroll
+    for (int dt = 0; dt < WA_D / 8; dt += 2) {
+      uint32_t vb[4];
+      wa_ldsm_x4_t(vb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + hoff + dt * 8 + (lane >> 4) * 8);
+      wa_mma(o[dt], pf[kk], vb[0], vb[1]);
+      wa_mma(o[dt + 1], pf[kk], vb[2], vb[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WA_THREADS)
+window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias, bf16* __restrict__ out, int F, int Hg,
+                   int Wg, int ws, int pool, int C, int H, float scale, int rows_alloc) {
+  PDL_ENTRY();
+  extern __shared__ __align__(16) uint8_t wa_smem[];
+  const int nwx = (Wg + ws - 1) / ws, nwy = (Hg + ws - 1) / ws;
+  const int nk = ws * ws;
+  const int wq = pool ? ws / 2 : ws, nq = wq * wq;
+  const int Ho = pool ? Hg / 2 : Hg, Wo = pool ? Wg / 2 : Wg;
+  const int win = blockIdx.x;
+  const int f = win / (nwy * nwx), wi = win - f * (nwy * nwx);
+  const int wy = wi / nwx, wx = wi - wy * nwx;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const float sl2 = scale * 1.4426950408889634f;
+  const int nk_pad = nk <= 16 ? 16 : WA_ROWS;
+  const int nslab = (nq + 15) >> 4;
+  const bf16* fbase = qkv + (long long)f * Hg * Wg * 3 * C;
+
+  for (int h0 = 0; h0 < H; h0 += WA_HC) {
+    const int hc = min(WA_HC, H - h0);
+    const int Cc = hc * WA_D, LD = Cc + 8, CH = Cc / 8;  // channels / padded row / 16-byte chunks of this pass
+    bf16* sQ = reinterpret_cast<bf16*>(wa_smem);
+    bf16* sK = sQ + rows_alloc * LD;  // rows_alloc = max(padded keys, padded queries) of this window size
+    bf16* sV = sK + rows_alloc * LD;
+    // ---- keys and values: rows < nk from the window (bias where the window hangs over the image), zeros up to nk_pad
+    for (int i = tid; i < 2 * nk_pad * CH; i += WA_THREADS) {
+      const int which = i >= nk_pad * CH ? 2 : 1;
+      const int j = i - (which - 1) * nk_pad * CH;
+      const int r = j / CH, c8 = j - r * CH;
+      bf16* dst = (which == 1 ? sK : sV) + r * LD + c8 * 8;
+      const int col = which * C + h0 * WA_D + c8 * 8;
+      if (r < nk) {
+        const int ly = r / ws, lx = r - ly * ws;
+        const int y = wy * ws + ly, x = wx * ws + lx;
+        if (y < Hg && x < Wg) wa_cp_async16(dst, fbase + ((long long)y * Wg + x) * 3 * C + col);
+        else *reinterpret_cast<uint4*>(dst) = bias_chunk(bias + col);
+      } else {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    // ---- queries: rows < nq (max over the 2 x 2 source tokens when pooling), zeros up to the end of the last slab
+    for (int i = tid; i < nslab * 16 * CH; i += WA_THREADS) {
+      const int r = i / CH, c8 = i - r * CH;
+      bf16* dst = sQ + r * LD + c8 * 8;
+      const int col = h0 * WA_D + c8 * 8;
+      if (r >= nq) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      } else if (!pool) {
+        const int ly = r / ws, lx = r - ly * ws;
+        const int y = wy * ws + ly, x = wx * ws + lx;
+        if (y < Hg && x < Wg) wa_cp_async16(dst, fbase + ((long long)y * Wg + x) * 3 * C + col);
+        else *reinterpret_cast<uint4*>(dst) = bias_chunk(bias + col);
+      } else {
+        const int qy = r / wq, qx = r - qy * wq;
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int y = wy * ws + 2 * qy + (d >> 1), x = wx * ws + 2 * qx + (d & 1);
+          const uint4 u = (y < Hg && x < Wg) ? __ldg(reinterpret_cast<const uint4*>(fbase + ((long long)y * Wg + x) * 3 * C + col))
+                                             : bias_chunk(bias + col);
+          if (d == 0) m = u;
+          else {
+            m.x = max_bf16x2(m.x, u.x); m.y = max_bf16x2(m.y, u.y);
+            m.z = max_bf16x2(m.z, u.z); m.w = max_bf16x2(m.w, u.w);
+          }
+        }
+        *reinterpret_cast<uint4*>(dst) = m;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- units: (head of this pass, 16-query slab), dealt to the warps
+    for (int u = warp; u < hc * nslab; u += WA_THREADS / 32) {
+      const int hh = u / nslab, slab = u - hh * nslab;
+      float o[WA_D / 8][4], inv[2];
+      if (nk_pad == 16) attend_unit<2>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      else attend_unit<8>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = slab * 16 + g + half * 8;
+        if (r < nq) {
+          const int oy = wy * wq + r / wq, ox = wx * wq + r % wq;
+          if (oy < Ho && ox < Wo) {
+            bf16* dst = out + (((long long)f * Ho + oy) * Wo + ox) * C + (h0 + hh) * WA_D + 2 * t;
+#pragma unroll
+            for (int dt = 0; dt < WA_D / 8; ++dt)
+              *reinterpret_cast<uint32_t*>(dst + dt * 8) =
+                  pack_bf16x2(o[dt][half * 2] * inv[half], o[dt][half * 2 + 1] * inv[half]);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the next pass overwrites the tiles
+  }
+}
+
+}  // namespace
+
+extern "C" int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, void* out, int F, int Hg, int Wg, int ws,
+                                     int pool, int C, int heads, void* stream) {
+  if (!qkv || !qkv_bias || !out || F <= 0 || Hg <= 0 || Wg <= 0 || ws <= 0 || heads <= 0) return USVM_ERR_ARG;
+  if (C != heads * WA_D || ws * ws > WA_ROWS || (pool && ((ws & 1) || (Hg & 1) || (Wg & 1)))) return USVM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 3) ||
+      (reinterpret_cast<uintptr_t>(qkv_bias) & 3))
+    return USVM_ERR_ARG;
+  const int hc = heads < WA_HC ? heads : WA_HC;
+  const int nk = ws * ws, nq = pool ? nk / 4 : nk;
+  const int nk_pad = nk <= 16 ? 16 : WA_ROWS, nq_pad = (nq + 15) & ~15;
+  const int rows_alloc = nk_pad > nq_pad ? nk_pad : nq_pad;
+  const size_t smem = (size_t)3 * rows_alloc * (hc * WA_D + 8) * sizeof(bf16);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+      return USVM_ERR_CUDA;
+    configured = true;
+  }
+  const int nw = cdiv(Hg, ws) * cdiv(Wg, ws);
+  usvm_launch(window_attn_kernel, dim3(F * nw), dim3(WA_THREADS), smem, reinterpret_cast<cudaStream_t>(stream),
+              reinterpret_cast<const bf16*>(qkv), qkv_bias, reinterpret_cast<bf16*>(out), F, Hg, Wg, ws, pool, C, heads,
+              1.0f / sqrtf((float)WA_D), rows_alloc);
+  return usvm_check_launch();
+}

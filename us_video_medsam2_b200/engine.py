@@ -302,6 +302,7 @@ class Engine:
         self.cfg = weights.cfg
         self.attn_splits = 8  # flash-decoding splits of the memory attention key range (fills the 148 SMs at B=1)
         self._tail_stream = None
+        self.fused_windows = os.environ.get("USVM2_FUSED_WINDOWS", "1") != "0"
         self.use_token_chain = os.environ.get("USVM2_TOKEN_CHAIN", "0") == "1"
 
     # ---------------------------------------------------------------- image encoder
@@ -324,7 +325,9 @@ class Engine:
                 shortcut = x
             _, qkv = ops.gemm_bf16(h, blk["qkv_w"], bias=blk["qkv_b"], bf16=True)
             Ho, Wo = (H // 2, W // 2) if pool else (H, W)
-            if ws > 0:
+            if 0 < ws * ws <= 64 and self.fused_windows:
+                att = ops.window_attn(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout, heads)
+            elif ws > 0:
                 Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout)
                 Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * dout, dout, 96),
                               (0, nk * dout, dout, 96), (0, nk * dout, dout, 96))

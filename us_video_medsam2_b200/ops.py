@@ -219,6 +219,16 @@ def window_gather(qkv, qkv_bias, F, Hg, Wg, ws, pool, Cc):
     return Qw, Kw, Vw, nw, nq, nk
 
 
+def window_attn(qkv, qkv_bias, F, Hg, Wg, ws, pool, Cc, heads):
+    """Fused Hiera window attention (windows of <= 64 keys): qkv bf16 [F*Hg*Wg, 3*Cc] raster order -> bf16
+    [F*Ho*Wo, Cc] raster order; partition, q max-pool, attention and un-partition in one kernel."""
+    Ho, Wo = (Hg // 2, Wg // 2) if pool else (Hg, Wg)
+    out = empty((F * Ho * Wo, Cc), BF16, qkv)
+    call("usvm_window_attn_bf16", qkv.data_ptr(), qkv_bias.data_ptr(), out.data_ptr(), F, Hg, Wg, ws, int(pool), Cc,
+         heads, _stream())
+    return out
+
+
 def window_scatter(Ow, F, Ho, Wo, wq, Cc):
     out = empty((F * Ho * Wo, Cc), BF16, Ow)
     call("usvm_window_scatter", Ow.data_ptr(), out.data_ptr(), F, Ho, Wo, wq, Cc, _stream())
