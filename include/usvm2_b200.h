@@ -114,7 +114,7 @@ typedef struct usvm_fmha_params {
                                  bf16 output itself */
 } usvm_fmha_params;
 int usvm_fmha_bf16(const usvm_fmha_params* p_host, void* stream);
-/* Fused Hiera window attention for windows of <= 64 keys (hieradet.py:46-95 + backbones/utils.py:17-58): window
+/* Fused Hiera window attention for windows of <= 256 keys (hieradet.py:46-95 + backbones/utils.py:17-58): window
  * partition, QKV split, optional 2x2 query max-pool, attention per (window, head of 96) and window un-partition in one
  * kernel.  qkv bf16 [F, Hg, Wg, 3*C] raster order (C = heads*96), qkv_bias fp32 [3*C] (value of the tokens in the zero
  * padding of partial windows), out bf16 [F, Ho, Wo, C] raster order (Ho = Hg/2 when pool). */

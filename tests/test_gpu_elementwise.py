@@ -203,7 +203,8 @@ def test_im2col_nhwc_and_dwconv():
 
 
 @pytest.mark.parametrize("Hg,ws,pool,heads", [(64, 8, False, 1), (64, 8, True, 2), (32, 4, False, 2), (32, 4, True, 4),
-                                              (16, 7, False, 8), (24, 8, True, 5), (20, 6, False, 1)])
+                                              (16, 7, False, 8), (24, 8, True, 5), (20, 6, False, 1), (32, 14, False, 4),
+                                              (32, 14, True, 8), (30, 10, False, 2)])
 def test_fused_window_attention(Hg, ws, pool, heads):
     """One-kernel window attention == gather -> flash attention -> scatter (the generic path), incl. partial windows
     (bias-valued padding tokens), pooled queries and more heads than one shared-memory pass holds."""

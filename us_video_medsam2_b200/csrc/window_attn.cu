@@ -1,4 +1,4 @@
-// Fused Hiera window attention for the small windows (<= 64 keys): window partition, QKV split, optional 2x2 max-pool
+// Fused Hiera window attention (windows of up to 256 keys): window partition, QKV split, optional 2x2 max-pool
 // of the queries, per-(window, head) attention and window un-partition in ONE kernel, reading the raster-order fused qkv
 // tensor in place and writing the raster-order output (hieradet.py:46-95 MultiScaleAttention / MultiScaleBlock,
 // backbones/utils.py:17-58 window_partition / window_unpartition).
@@ -12,7 +12,9 @@
 //   * a work unit is (head, 16-query slab): S = Q K^T with mma.sync m16n8k16 bf16 over <= 64 keys in registers, row
 //     softmax in base 2, O = P V with P re-used as the A fragment (FlashAttention-2 register pipeline, one key tile);
 //   * the slab's rows go back to out[f, oy, ox, h*96 ...] -- raster order, padding rows dropped.
-// Heads are processed in passes of 4 (shared memory: 3 x 64 x (4*96 + 8) bf16 = 147 KB).
+// Windows of <= 64 keys: one CTA per window, 4 heads per shared-memory pass (3 x 64 x (4*96 + 8) bf16 = 147 KB).
+// Larger windows (14 x 14 = 196 keys): one CTA per (window, head); the keys are walked in tiles of 64 with the online
+// softmax of the flash kernel (720 x 104 bf16 = 146 KB).
 #include "common.cuh"
 #include "usvm2_b200.h"
 
@@ -120,9 +122,92 @@ __device__ __forceinline__ void attend_unit(const bf16* sQ, const bf16* sK, cons
   }
 }
 
+
+// the same unit over several 64-key tiles (online softmax, FlashAttention-2 recurrence)
+__device__ __forceinline__ void attend_unit_tiles(const bf16* sQ, const bf16* sK, const bf16* sV, int LD, int hoff,
+                                                  int slab, int nk, float sl2, float (&o)[WA_D / 8][4], float (&inv)[2]) {
+  const int lane = threadIdx.x & 31, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < WA_D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t aq[WA_D / 16][4];
+#pragma unroll
+  for (int ks = 0; ks < WA_D / 16; ++ks)
+    wa_ldsm_x4(aq[ks], sQ + (slab * 16 + (lane & 15)) * LD + hoff + ks * 16 + (lane >> 4) * 8);
+  for (int key0 = 0; key0 < nk; key0 += 64) {
+    const bf16* cK = sK + key0 * LD;
+    const bf16* cV = sV + key0 * LD;
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < WA_D / 16; ++ks) {
+#pragma unroll
+      for (int nt = 0; nt < 8; nt += 2) {
+        uint32_t kb[4];
+        wa_ldsm_x4(kb, cK + (nt * 8 + (lane & 7) + (lane >> 4) * 8) * LD + hoff + ks * 16 + ((lane >> 3) & 1) * 8);
+        wa_mma(s[nt], aq[ks], kb[0], kb[1]);
+        wa_mma(s[nt + 1], aq[ks], kb[2], kb[3]);
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int kc = key0 + nt * 8 + 2 * t;
+      if (kc >= nk) s[nt][0] = s[nt][2] = -INFINITY;
+      if (kc + 1 >= nk) s[nt][1] = s[nt][3] = -INFINITY;
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mnew[r] = fmaxf(m_run[r], mx[r]);  // finite: every tile holds at least one valid key
+      corr[r] = exp2f((m_run[r] - mnew[r]) * sl2);
+      m_run[r] = mnew[r];
+      l_run[r] *= corr[r];
+    }
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f((s[nt][0] - mnew[0]) * sl2);
+      const float p1 = exp2f((s[nt][1] - mnew[0]) * sl2);
+      const float p2 = exp2f((s[nt][2] - mnew[1]) * sl2);
+      const float p3 = exp2f((s[nt][3] - mnew[1]) * sl2);
+      l_run[0] += p0 + p1;
+      l_run[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int i = 0; i < WA_D / 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dt = 0; dt < WA_D / 8; dt += 2) {
+        uint32_t vb[4];
+        wa_ldsm_x4_t(vb, cV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + hoff + dt * 8 + (lane >> 4) * 8);
+        wa_mma(o[dt], pf[kk], vb[0], vb[1]);
+        wa_mma(o[dt + 1], pf[kk], vb[2], vb[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    inv[r] = 1.0f / l_run[r];
+  }
+}
+
 __global__ void __launch_bounds__(WA_THREADS)
 window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias, bf16* __restrict__ out, int F, int Hg,
-                   int Wg, int ws, int pool, int C, int H, float scale, int rows_alloc) {
+                   int Wg, int ws, int pool, int C, int H, float scale, int rows_q, int rows_k, int heads_per_cta) {
   PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t wa_smem[];
   const int nwx = (Wg + ws - 1) / ws, nwy = (Hg + ws - 1) / ws;
@@ -134,16 +219,18 @@ window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
   const int wy = wi / nwx, wx = wi - wy * nwx;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const float sl2 = scale * 1.4426950408889634f;
-  const int nk_pad = nk <= 16 ? 16 : WA_ROWS;
+  const int nk_pad = nk <= 16 ? 16 : (nk + 63) & ~63;
   const int nslab = (nq + 15) >> 4;
   const bf16* fbase = qkv + (long long)f * Hg * Wg * 3 * C;
 
-  for (int h0 = 0; h0 < H; h0 += WA_HC) {
-    const int hc = min(WA_HC, H - h0);
+  const int h_begin = blockIdx.y * heads_per_cta, h_end = min(H, h_begin + heads_per_cta);
+  const int pass = nk > WA_ROWS ? 1 : WA_HC;  // heads per shared-memory pass
+  for (int h0 = h_begin; h0 < h_end; h0 += pass) {
+    const int hc = min(pass, h_end - h0);
     const int Cc = hc * WA_D, LD = Cc + 8, CH = Cc / 8;  // channels / padded row / 16-byte chunks of this pass
     bf16* sQ = reinterpret_cast<bf16*>(wa_smem);
-    bf16* sK = sQ + rows_alloc * LD;  // rows_alloc = max(padded keys, padded queries) of this window size
-    bf16* sV = sK + rows_alloc * LD;
+    bf16* sK = sQ + rows_q * LD;  // rows_q / rows_k: padded query / key rows of this window size
+    bf16* sV = sK + rows_k * LD;
     // ---- keys and values: rows < nk from the window (bias where the window hangs over the image), zeros up to nk_pad
     for (int i = tid; i < 2 * nk_pad * CH; i += WA_THREADS) {
       const int which = i >= nk_pad * CH ? 2 : 1;
@@ -197,7 +284,8 @@ window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
       const int hh = u / nslab, slab = u - hh * nslab;
       float o[WA_D / 8][4], inv[2];
       if (nk_pad == 16) attend_unit<2>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
-      else attend_unit<8>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      else if (nk_pad == 64) attend_unit<8>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      else attend_unit_tiles(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int r = slab * 16 + g + half * 8;
@@ -222,24 +310,27 @@ window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
 extern "C" int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, void* out, int F, int Hg, int Wg, int ws,
                                      int pool, int C, int heads, void* stream) {
   if (!qkv || !qkv_bias || !out || F <= 0 || Hg <= 0 || Wg <= 0 || ws <= 0 || heads <= 0) return USVM_ERR_ARG;
-  if (C != heads * WA_D || ws * ws > WA_ROWS || (pool && ((ws & 1) || (Hg & 1) || (Wg & 1)))) return USVM_ERR_ARG;
+  if (C != heads * WA_D || ws * ws > 256 || (pool && ((ws & 1) || (Hg & 1) || (Wg & 1)))) return USVM_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 3) ||
       (reinterpret_cast<uintptr_t>(qkv_bias) & 3))
     return USVM_ERR_ARG;
-  const int hc = heads < WA_HC ? heads : WA_HC;
   const int nk = ws * ws, nq = pool ? nk / 4 : nk;
-  const int nk_pad = nk <= 16 ? 16 : WA_ROWS, nq_pad = (nq + 15) & ~15;
-  const int rows_alloc = nk_pad > nq_pad ? nk_pad : nq_pad;
-  const size_t smem = (size_t)3 * rows_alloc * (hc * WA_D + 8) * sizeof(bf16);
+  const bool big = nk > WA_ROWS;                 // several key tiles: one CTA per (window, head)
+  const int heads_per_cta = big ? 1 : heads;
+  const int hc = big ? 1 : (heads < WA_HC ? heads : WA_HC);
+  const int rows_k = nk <= 16 ? 16 : (nk + 63) & ~63, rows_q = (nq + 15) & ~15;
+  const size_t smem = (size_t)(rows_q + 2 * rows_k) * (hc * WA_D + 8) * sizeof(bf16);
+  if (smem > 200 * 1024) return USVM_ERR_ARG;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return USVM_ERR_CUDA;
     configured = true;
   }
   const int nw = cdiv(Hg, ws) * cdiv(Wg, ws);
-  usvm_launch(window_attn_kernel, dim3(F * nw), dim3(WA_THREADS), smem, reinterpret_cast<cudaStream_t>(stream),
-              reinterpret_cast<const bf16*>(qkv), qkv_bias, reinterpret_cast<bf16*>(out), F, Hg, Wg, ws, pool, C, heads,
-              1.0f / sqrtf((float)WA_D), rows_alloc);
+  usvm_launch(window_attn_kernel, dim3(F * nw, cdiv(heads, heads_per_cta)), dim3(WA_THREADS), smem,
+              reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(qkv), qkv_bias,
+              reinterpret_cast<bf16*>(out), F, Hg, Wg, ws, pool, C, heads, 1.0f / sqrtf((float)WA_D), rows_q, rows_k,
+              heads_per_cta);
   return usvm_check_launch();
 }

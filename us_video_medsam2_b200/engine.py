@@ -325,6 +325,8 @@ class Engine:
                 shortcut = x
             _, qkv = ops.gemm_bf16(h, blk["qkv_w"], bias=blk["qkv_b"], bf16=True)
             Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+            # windows of <= 64 keys: one fused kernel.  (It also handles the 14 x 14 windows of stage 3, but one CTA per
+            # (window, head) walking 13 query slabs is slower there than gather + flash kernel + scatter: measured.)
             if 0 < ws * ws <= 64 and self.fused_windows:
                 att = ops.window_attn(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout, heads)
             elif ws > 0:

@@ -220,7 +220,7 @@ def window_gather(qkv, qkv_bias, F, Hg, Wg, ws, pool, Cc):
 
 
 def window_attn(qkv, qkv_bias, F, Hg, Wg, ws, pool, Cc, heads):
-    """Fused Hiera window attention (windows of <= 64 keys): qkv bf16 [F*Hg*Wg, 3*Cc] raster order -> bf16
+    """Fused Hiera window attention (windows of <= 256 keys): qkv bf16 [F*Hg*Wg, 3*Cc] raster order -> bf16
     [F*Ho*Wo, Cc] raster order; partition, q max-pool, attention and un-partition in one kernel."""
     Ho, Wo = (Hg // 2, Wg // 2) if pool else (Hg, Wg)
     out = empty((F * Ho * Wo, Cc), BF16, qkv)
