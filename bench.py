@@ -44,6 +44,12 @@ def parse():
     ap.add_argument("--frames", type=int, default=512, help="clip length T (BASELINE config 2: 512)")
     ap.add_argument("--objects", type=int, default=1)
     ap.add_argument("--encoder-batch", type=int, default=32, help="frames per batched image-encoder pass")
+    ap.add_argument("--encoder-sms", type=int, default=0,
+                    help="> 0: look-ahead encoder batches run concurrently with tracking on an SM partition of this size")
+    ap.add_argument("--mode", default="videos", choices=["videos", "clip"],
+                    help="N > 1: 'videos' = one independent clip per GPU (weak scaling, no communication); 'clip' = ONE "
+                         "clip, rank 0 propagates, the other ranks run the frame-parallel encoder and send features over "
+                         "NCCL point-to-point (strong scaling, bounded by the sequential propagation)")
     ap.add_argument("--cpu-sample-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -208,10 +214,17 @@ def run_b200(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.frames, args.objects
-    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=args.encoder_batch)
+    clip_mode = args.mode == "clip" and world > 1
+    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=args.encoder_batch,
+                                          encoder_sms=0 if clip_mode else args.encoder_sms)
     pred.load_state_dict(synth.make_state_dict(SEED), strict=True)
     masks = [synth.box_mask()] if B == 1 else synth.multi_object_masks(B)
-    gray_host = synth.make_clip_u8(T, seed=1234 + rank).pin_memory()      # [T,512,512] uint8, pinned host
+    # 'clip' mode: every rank holds the SAME clip (rank 0 tracks it, the others encode their share of its frames)
+    gray_host = synth.make_clip_u8(T, seed=1234 + (0 if clip_mode else rank)).pin_memory()  # [T,512,512] uint8, pinned
+    if clip_mode and rank == 0:
+        from us_video_medsam2_b200.pipeline import RemoteEncoders
+
+        pred.attach_remote_encoders(RemoteEncoders(list(range(1, world)), dev))
     out_host = torch.empty((T, B, 512, 512), dtype=torch.uint8).pin_memory()
     clip_dev = ops.normalize_gray_u8(gray_host.to(dev), synth.IMG_MEAN, synth.IMG_STD)  # resident copy for `value`
 
@@ -227,11 +240,17 @@ def run_b200(args, rank, world):
         return n
 
     def step_resident():
+        if clip_mode and rank > 0:  # encoder rank: serve the one plan rank 0 announces for this pass
+            pred.serve_encoder(clip_dev, rank - 1, world - 1, dst=0, max_plans=1)
+            return 0
         return one_pass(clip_dev)
 
     def step_e2e():
         g = gray_host.to(dev, non_blocking=True)
         imgs = ops.normalize_gray_u8(g, synth.IMG_MEAN, synth.IMG_STD)
+        if clip_mode and rank > 0:
+            pred.serve_encoder(imgs, rank - 1, world - 1, dst=0, max_plans=1)
+            return 0
         return one_pass(imgs, out_host)
 
     def timed(fn, steps, warmup):
@@ -301,11 +320,16 @@ def run_b200(args, rank, world):
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if clip_mode else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"sam2.1_hiera_t512 propagate_in_video, {T}-frame synthetic echo clip per GPU, "
+            "config": {"workload": f"sam2.1_hiera_t512 propagate_in_video, {T}-frame synthetic echo clip "
+                                   f"{'(one clip for all GPUs)' if clip_mode else 'per GPU'}, "
                                    f"{B} object(s), 7-frame memory bank, mask prompt on frame 0",
-                       "frames": T, "objects": B, "encoder_batch": args.encoder_batch, "parallelism": f"videos x{world}",
+                       "frames": T, "objects": B, "encoder_batch": args.encoder_batch,
+                       "parallelism": (f"one clip: propagation on rank 0, frame-parallel encoder on {world - 1} rank(s), "
+                                       "features sent point-to-point over NCCL") if clip_mode else f"videos x{world}",
+                       "encoder_sms": (pred._partition_obj.sms if pred._partition_obj is not None else 0),
                        "precision": "bf16 tensor-core contractions (encoder / memory attention / memory encoder), "
                                     "fp32-operand mask decoder (tf32 tensor-core products on its image-side GEMMs, "
                                     "exact fp32 on the token side)",
@@ -314,6 +338,8 @@ def run_b200(args, rank, world):
                     "d2h_bytes_per_step": T * B * 512 * 512},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }))
+    if clip_mode and rank == 0:
+        pred._remote.shutdown()  # (encoder ranks are not inside a service loop any more: harmless broadcast)
     if world > 1:
         dist.destroy_process_group()
 

@@ -23,6 +23,9 @@ extern "C" {
 int usvm_abi_version(void);
 /* compute capability major*10+minor of the current device, or <0 */
 int usvm_device_sm(void);
+/* Number of SMs persistent kernels may occupy (0 = all of the device).  Host-side launch heuristic only: set before
+ * launching / capturing work that runs on an SM partition (CUDA green context); grids are baked into captured graphs. */
+int usvm_set_sm_budget(int sms);
 
 /* ------------------------------------------------------------------------------------------------
  * (a14) connected components + hole filling

@@ -166,6 +166,48 @@ def chain():
         print(f"sam_heads token_chain={use} precise={precise}: {us:7.1f} us", flush=True)
 
 
+def phases():
+    """GPU time of the three phases of a tracked frame (graph-captured, L2-warm), one object, full memory bank."""
+    from us_video_medsam2_b200 import synth
+    from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
+    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=8)
+    pred.load_state_dict(synth.make_state_dict(19), strict=True)
+    eng = pred.engine()
+    B, T, Nk = 1, 1024, 7 * 1024 + 64
+    feat = rnd(T, 256, scale=0.5)
+    k_in, v_in = rnd(B, Nk, 64, dtype=torch.bfloat16), rnd(B, Nk, 64, dtype=torch.bfloat16)
+    print(f"memory_attention: {timeit(lambda: eng.memory_attention(feat, k_in, v_in, Nk, 64, B), iters=4):7.1f} us", flush=True)
+    pix = rnd(B * T, 256, scale=0.5)
+    s0, s1 = rnd(16384, 32), rnd(4096, 64)
+    print(f"sam_heads: {timeit(lambda: eng.sam_heads(pix, s0, s1, B, eng.no_point_tokens(B), multimask=True), iters=4):7.1f} us", flush=True)
+    low = rnd(B, 1, 128, 128, scale=0.07)
+    score = rnd(B, 1)
+    fb = rnd(T, 256, dtype=torch.bfloat16)
+    print(f"mem_mask_input + encode_memory: "
+          f"{timeit(lambda: eng.encode_memory(fb, eng.mem_mask_input(low, False), score, B), iters=4):7.1f} us", flush=True)
+    x = rnd(T, 256)
+    L = eng.w.ma_layers[0]
+    cs, sn = eng.w.rope_cos, eng.w.rope_sin
+
+    def sa_block():
+        _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
+        _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
+        o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
+                     (512, T * 768, 768, 256), num_splits=8, impl="mma")
+        return ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True)
+
+    def ffn_block():
+        _, h = ops.layernorm(x, *L["n3"], 1e-5, bf16=True)
+        _, m = ops.gemm_bf16(h, L["l1"][0], bias=L["l1"][1], act=1, bf16=True)
+        return ops.gemm_bf16(m, L["l2"][0], bias=L["l2"][1], residual=x, f32=True)
+
+    print(f"  self-attention sub-block (LN, qkv, fmha+combine, out-proj): {timeit(sa_block, iters=8):7.1f} us", flush=True)
+    print(f"  FFN sub-block (LN, linear1, linear2): {timeit(ffn_block, iters=8):7.1f} us", flush=True)
+    print(f"  layernorm alone: {timeit(lambda: ops.layernorm(x, *L['n1'], 1e-5, bf16=True), iters=20):7.1f} us", flush=True)
+    hb = rnd(T, 256, dtype=torch.bfloat16)
+    print(f"  qkv gemm alone: {timeit(lambda: ops.gemm_bf16(hb, L['sa_qkv_w'], bias=L['sa_qkv_b'], bf16=True, rope=(cs, sn, 512, T, T)), iters=20):7.1f} us", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["attention", "gemms", "misc"]
     for w_ in which:

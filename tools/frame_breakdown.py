@@ -51,7 +51,7 @@ def main():
         for _ in pred.propagate_in_video(st):
             pass
     torch.cuda.synchronize()
-    enc = pred._graphs[("encoder", nb)]
+    enc = pred._graphs[("encoder", nb, 0, False)]
     track_keys = [k for k in pred._graphs if k[0] != "encoder"]
     steady = max(track_keys, key=lambda k: (k[1], k[2]))
     trk = pred._graphs[steady]
@@ -68,6 +68,38 @@ def main():
     s_enc, s_trk = torch.cuda.Stream(), torch.cuda.Stream()
     t_ovl = replay_ms([(enc[0], 1), (trk[0], nb)], streams=[s_enc, s_trk])
     print(f"two streams     : {t_ovl:7.3f} ms per {nb} frames = {t_ovl / nb:6.3f} ms/frame (equal priority)")
+    # encoder on a green-context SM partition, tracked frames (captured for the remaining SMs) on an ordinary stream
+    for sms in [int(x) for x in os.environ.get("PARTITION_SMS", "48,64").split(",") if x]:
+        p2 = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=nb, encoder_sms=sms)
+        p2.load_state_dict(synth.make_state_dict(19), strict=True)
+        for _ in range(3):
+            st = p2.init_state(clip, 512, 512)
+            p2.add_new_mask(st, 0, 1, synth.box_mask())
+            for _ in p2.propagate_in_video(st):
+                pass
+        torch.cuda.synchronize()
+        part = p2._partition_obj
+        if part is None:
+            print(f"partition {sms}: unavailable ({p2._partition_error})")
+            continue
+        enc2 = p2._graphs[("encoder", nb, 0, True)]
+        steady2 = max([k for k in p2._graphs if k[0] != "encoder"], key=lambda k: (k[1], k[2]))
+        trk2 = p2._graphs[steady2]
+        t_e = replay_ms([(enc2[0], 1)], streams=[part.stream])
+        t_t = replay_ms([(trk2[0], nb)])
+        t_o = replay_ms([(enc2[0], 1), (trk2[0], nb)], streams=[part.stream, torch.cuda.Stream()])
+        print(f"partition {part.sms:3d} SMs: encoder alone {t_e / nb:6.3f}, tracking alone (budget {part.total_sms - part.sms}) "
+              f"{t_t / nb:6.3f}, concurrent {t_o / nb:6.3f} ms/frame", flush=True)
+        # the same tracked frame captured on the COMPLEMENT partition (disjoint SM sets)
+        try:
+            p2.engine()._tail_stream = part.rest_stream2  # the forked user-facing tail stays in the same green context
+            trk3 = p2._capture_graph(steady2, trk2[1], stream=part.rest_stream)
+            t_t3 = replay_ms([(trk3[0], nb)], streams=[part.rest_stream])
+            t_o3 = replay_ms([(enc2[0], 1), (trk3[0], nb)], streams=[part.stream, part.rest_stream])
+            print(f"              tracking on the complement ({part.rest_sms} SMs) alone {t_t3 / nb:6.3f}, concurrent "
+                  f"{t_o3 / nb:6.3f} ms/frame", flush=True)
+        except Exception as e:
+            print("              complement capture failed:", repr(e))
 
 
 if __name__ == "__main__":

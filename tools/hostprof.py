@@ -1,10 +1,11 @@
 import os, sys, time, cProfile, pstats
-sys.path.insert(0, "/root/repo"); os.environ["TQDM_DISABLE"]="1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); os.environ["TQDM_DISABLE"]="1"
 import torch
 from us_video_medsam2_b200 import synth, ops
 from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
 T=int(sys.argv[1]) if len(sys.argv)>1 else 128
-pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", encoder_batch=8)
+pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", encoder_batch=int(os.environ.get("ENCODER_BATCH", 8)),
+                                      encoder_sms=int(os.environ.get("ENCODER_SMS", 0)))
 pred.load_state_dict(synth.make_state_dict(19))
 clip = synth.make_clip(T).cuda()
 def one():

@@ -716,6 +716,10 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
   return usvm_check_launch();
 }
 
+// SMs a persistent grid may occupy (0 = all): set while the image encoder is captured on an SM partition (green
+// context) so that one CTA per *partition* SM walks the tiles instead of 148 CTAs queueing in waves.
+int g_sm_budget = 0;
+
 int persistent_block_n(int N) {
   // the widest multiple of 32 (<= 256) that wastes the fewest padded columns
   int best = 32, best_waste = 1 << 30;
@@ -763,13 +767,19 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
   while (stages > 1 && p_smem_total(bn, stages) > 227 * 1024) --stages;
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn);
   const int num_tiles = tiles_m * tiles_n;
-  const int grid = num_tiles < sm_count ? num_tiles : sm_count;
+  const int sm_limit = (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
+  const int grid = num_tiles < sm_limit ? num_tiles : sm_limit;
   usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, stages), stream, tmA, tmB,
               tmO32, tmO16, *ep, M, N, K, bn, stages, tiles_n, num_tiles);
   return usvm_check_launch();
 }
 
 }  // namespace
+
+extern "C" int usvm_set_sm_budget(int sms) {
+  g_sm_budget = sms > 0 ? sms : 0;
+  return 0;
+}
 
 extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep,
                                   int M, int N, int K, int block_n, void* stream) {

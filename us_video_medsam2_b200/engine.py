@@ -300,7 +300,7 @@ class Engine:
     def __init__(self, weights: PackedWeights):
         self.w = weights
         self.cfg = weights.cfg
-        self.attn_splits = 8  # flash-decoding splits of the memory attention key range (fills the 148 SMs at B=1)
+        self.sm_budget = 148  # SMs the tracked frame may count on (fewer while the encoder owns an SM partition)
         self._tail_stream = None
         self.fused_windows = os.environ.get("USVM2_FUSED_WINDOWS", "1") != "0"
         self.use_token_chain = os.environ.get("USVM2_TOKEN_CHAIN", "0") == "1"
@@ -400,7 +400,7 @@ class Engine:
     def _splits(self, B, Nk):
         """Split-KV factor: the tcgen05 kernel runs 8 query tiles of 128 per object; fill the 148 SMs."""
         tiles = (Nk + 63) // 64
-        want = max(1, 148 // (8 * B))
+        want = max(1, self.sm_budget // (8 * B))
         return max(1, min(want, tiles))
 
     def assemble_memory(self, ctrl, B, n_mem, n_ptr):

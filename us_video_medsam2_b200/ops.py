@@ -41,6 +41,11 @@ def _chk(t, dtype, name):
         raise TypeError(f"{name}: expected a CUDA {dtype} tensor, got {t.device} {t.dtype}")
 
 
+def set_sm_budget(sms):
+    """SMs that persistent kernels launched (or captured) from now on may occupy; 0 = the whole device."""
+    _lib.lib().usvm_set_sm_budget(int(sms))
+
+
 def empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 

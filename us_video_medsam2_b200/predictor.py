@@ -55,7 +55,7 @@ class SAM2VideoPredictor(nn.Module):
 
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False,
-                 encoder_batch=1, use_cuda_graphs=True, **model_kwargs):
+                 encoder_batch=1, use_cuda_graphs=True, encoder_sms=0, **model_kwargs):
         super().__init__()
         cfg = type("Cfg", (ModelConfig,), {})
         for k, v in model_kwargs.items():
@@ -85,6 +85,10 @@ class SAM2VideoPredictor(nn.Module):
         self.encoder_batch = max(1, int(encoder_batch))
         # steady-state tracked frames are replayed from a CUDA graph keyed by (objects, #memories, #pointers, H, W)
         self.use_cuda_graphs = bool(use_cuda_graphs)
+        # > 0: during propagate_in_video the look-ahead encoder batches run CONCURRENTLY with the tracked frames, on a
+        # green-context stream that owns this many SMs (pipeline.SmPartition); 0 = encoder and tracking alternate
+        self.encoder_sms = int(os.environ.get("USVM2_ENCODER_SMS", encoder_sms))
+        self._partition_obj, self._partition_error, self._remote = None, None, None
         _install_abi_parameters(self)
         self._engine = None
         self._engine_key = None
@@ -111,6 +115,8 @@ class SAM2VideoPredictor(nn.Module):
         if self._engine is None or key != self._engine_key:
             sd = {k: v for k, v in self.state_dict().items()}
             self._engine = Engine(PackedWeights(sd, self.device, self.cfg))
+            if self._partition_obj is not None:
+                self._engine.sm_budget = self._partition_obj.total_sms - self._partition_obj.sms
             self._engine_key = key
             self._graphs, self._graph_seen = {}, {}  # captured graphs bake the old weight pointers
             self._ctrl = ops.new_frame_ctrl(self.device)
@@ -222,11 +228,17 @@ class SAM2VideoPredictor(nn.Module):
     # ------------------------------------------------------------------ image features
     def _get_image_feature(self, st, frame_idx, lookahead=None):
         """Per-frame backbone features (reference :879-910).  On a miss, `encoder_batch` consecutive frames in
-        the tracking direction are encoded in one batched pass (the image encoder is frame-independent)."""
+        the tracking direction are encoded in one batched pass (the image encoder is frame-independent); during
+        propagate_in_video a FeaturePipeline may already hold them (encoded ahead on an SM partition or another GPU)."""
         cache = st["cached_features"]
         hit = cache.get(frame_idx)
         if hit is not None:
             return hit
+        pipe = st.get("_pipeline")
+        if pipe is not None and lookahead is not None:
+            got = pipe.get(frame_idx)
+            if got is not None:
+                return got
         eng = self.engine()
         step = lookahead if lookahead is not None else 0
         n = self.encoder_batch if step != 0 else 1
@@ -235,12 +247,8 @@ class SAM2VideoPredictor(nn.Module):
         if self.use_cuda_graphs and len(idxs) == self.encoder_batch and self.encoder_batch > 1:
             # full look-ahead batch: replay the captured image-encoder graph.  Its outputs are static buffers that the
             # next replay overwrites, so the cache holds exactly the frames of the latest batch.
-            ent = self._graphs.get(("encoder", len(idxs)))
-            if ent is None:
-                ent = self._capture_encoder_graph(len(idxs))
-            graph, static_in, out, n_kernels = ent
-            for j, t in enumerate(idxs):
-                static_in[j].copy_(self._frame(st, t), non_blocking=True)
+            graph, static_in, out, n_kernels = self._encoder_graph(len(idxs))
+            self._load_frames(st, idxs, static_in)
             graph.replay()
             _lib.launch_count += n_kernels
             keep = {}
@@ -256,20 +264,127 @@ class SAM2VideoPredictor(nn.Module):
         st["cached_features"] = keep
         return keep[frame_idx]
 
-    def _capture_encoder_graph(self, n):
+    def _encoder_graph(self, n, slot=0, partition=None):
+        """Captured image-encoder pass over n frames -> (graph, static input [n,3,S,S], static outputs, #kernels).
+        With `partition` the graph is captured on (and must be replayed from) that SM partition's stream, persistent
+        kernels sized to its SM count; `slot` names one of several independent sets of static buffers."""
+        key = ("encoder", n, slot, partition is not None)
+        ent = self._graphs.get(key)
+        if ent is not None:
+            return ent
         eng = self.engine()
         static_in = torch.zeros((n, 3, self.image_size, self.image_size), dtype=torch.float32, device=self.device)
-        eng.encode_frames(static_in)  # warm-up: one-time kernel attribute setup must not happen during capture
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        before = _lib.launch_count
-        with torch.cuda.graph(graph):
-            out = eng.encode_frames(static_in)
-        n_kernels = _lib.launch_count - before
-        _lib.launch_count = before
+        stream = partition.stream if partition is not None else None
+        try:
+            if partition is not None:
+                ops.set_sm_budget(partition.sms)
+                stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(stream):
+                    eng.encode_frames(static_in)
+            else:
+                eng.encode_frames(static_in)  # warm-up: one-time kernel attribute setup must not happen during capture
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count
+            with torch.cuda.graph(graph, stream=stream):
+                out = eng.encode_frames(static_in)
+            n_kernels = _lib.launch_count - before
+            _lib.launch_count = before
+        finally:
+            if partition is not None:
+                ops.set_sm_budget(partition.total_sms - partition.sms)
         ent = (graph, static_in, out, n_kernels)
-        self._graphs[("encoder", n)] = ent
+        self._graphs[key] = ent
         return ent
+
+    def _load_frames(self, st, idxs, static_in):
+        """Copy the listed frames into a static encoder input (one copy when they are a contiguous ascending run)."""
+        images = st["images"]
+        if (torch.is_tensor(images) and images.is_cuda and images.dtype == torch.float32 and len(idxs) > 1
+                and all(b - a == 1 for a, b in zip(idxs, idxs[1:]))):
+            static_in[: len(idxs)].copy_(images[idxs[0]: idxs[-1] + 1], non_blocking=True)
+            return
+        for j, t in enumerate(idxs):
+            static_in[j].copy_(self._frame(st, t), non_blocking=True)
+
+    # ------------------------------------------------------------------ encoder running ahead of the propagation
+    def _partition(self):
+        """The encoder's SM partition (created on first use), or None when disabled / not available on this driver."""
+        if self.encoder_sms <= 0 or not self.use_cuda_graphs or self._partition_error is not None:
+            return None
+        if self._partition_obj is None:
+            from .pipeline import SmPartition
+
+            try:
+                part = SmPartition(self.device, self.encoder_sms)
+            except Exception as e:  # no green contexts on this driver / cuda-python missing: alternate as before
+                self._partition_error = repr(e)
+                warnings.warn(f"encoder SM partition unavailable ({e!r}); encoder and tracking will alternate")
+                return None
+            self._partition_obj = part
+            self.engine().sm_budget = part.total_sms - part.sms
+            ops.set_sm_budget(part.total_sms - part.sms)
+            # graphs captured so far assumed the whole device for the tracked frame
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] == "encoder"}
+            self._graph_seen = {}
+        return self._partition_obj
+
+    def attach_remote_encoders(self, remote):
+        """Single clip on several GPUs: `remote` (pipeline.RemoteEncoders) names the ranks that run
+        `serve_encoder`; propagate_in_video then receives every look-ahead batch from them instead of encoding it."""
+        self._remote = remote
+
+    @torch.inference_mode()
+    def serve_encoder(self, images, my_index, num_encoders, dst=0, group=None, max_plans=None):
+        """Encoder-rank side of the single-clip mode: encode the batches of each announced plan that fall to this rank
+        and send their features to rank `dst`.  `images`: the normalised clip [T,3,S,S] resident on this GPU."""
+        from .pipeline import serve_clip_encoder
+
+        self._sync_engine()
+        st = {"images": images, "num_frames": len(images)}
+        eng = self.engine()
+
+        def encode(frames, slot):
+            if self.use_cuda_graphs and len(frames) == self.encoder_batch and self.encoder_batch > 1:
+                graph, static_in, out, n_kernels = self._encoder_graph(len(frames), slot)
+                self._load_frames(st, frames, static_in)
+                graph.replay()
+                _lib.launch_count += n_kernels
+                return out
+            imgs = torch.stack([self._frame(st, t) for t in frames]).contiguous()
+            return eng.encode_frames(imgs)
+
+        return serve_clip_encoder(encode, my_index, num_encoders, self.device, dst=dst, group=group,
+                                  max_plans=max_plans)
+
+    def _begin_pipeline(self, st, order, reverse):
+        """Set up the look-ahead encoder for the frames `order` still has to track (None: nothing to overlap)."""
+        from .pipeline import BatchPlan, FeaturePipeline, PartitionProducer, RemoteProducer
+
+        cfi = st["consolidated_frame_inds"]
+        done = cfi["cond_frame_outputs"] | cfi["non_cond_frame_outputs"]
+        tracked = [t for t in order if t not in done]
+        if not tracked:
+            return None
+        first, last, step, n = tracked[0], tracked[-1], (-1 if reverse else 1), self.encoder_batch
+        if self._remote is not None:
+            plan = BatchPlan(first, last, step, n, include_tail=True)
+            self._remote.announce(plan)
+            return FeaturePipeline(plan, RemoteProducer(self._remote, n, self.device), depth=len(self._remote.ranks))
+        if n < 2 or len(tracked) < 2 * n:
+            return None
+        part = self._partition()
+        if part is None:
+            return None
+        plan = BatchPlan(first, last, step, n, include_tail=False)
+        try:
+            for slot in range(2):
+                self._encoder_graph(n, slot, part)
+        except Exception as e:  # the partition exists but the encoder cannot run on it: alternate as before
+            self._partition_error = repr(e)
+            warnings.warn(f"image encoder could not be captured on the SM partition ({e!r}); alternating instead")
+            return None
+        return FeaturePipeline(plan, PartitionProducer(self, st, part, n), depth=1)
 
     def _frame(self, st, t):
         img = st["images"][t]
@@ -535,6 +650,18 @@ class SAM2VideoPredictor(nn.Module):
         else:
             end_frame_idx = min(start_frame_idx + max_frame_num_to_track, num_frames - 1)
             order = range(start_frame_idx, end_frame_idx + 1)
+        st["_pipeline"] = self._begin_pipeline(st, list(order), reverse)
+        try:
+            yield from self._propagate_loop(st, order, reverse, clear_non_cond_mem, B)
+        finally:
+            pipe = st.pop("_pipeline", None)
+            if pipe is not None:
+                pipe.close()
+
+    def _propagate_loop(self, st, order, reverse, clear_non_cond_mem, B):
+        output_dict = st["output_dict"]
+        cfi = st["consolidated_frame_inds"]
+        obj_ids = st["obj_ids"]
         for frame_idx in _progress(order, "propagate in video"):
             if frame_idx in cfi["cond_frame_outputs"]:
                 storage_key = "cond_frame_outputs"
@@ -652,14 +779,14 @@ class SAM2VideoPredictor(nn.Module):
             video, _ = eng.track_frame(f, self._ctrl, B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
         return self._slot_views(st, frame_idx), video
 
-    def _capture_graph(self, key, f):
+    def _capture_graph(self, key, f, stream=None):
         B, n_mem, n_ptr, hw, fill = key
         eng = self.engine()
         static_f = {k: f[k].clone() for k in ("feat", "feat_bf16", "feat_s0", "feat_s1")}
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         before = _lib.launch_count
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=stream):
             video, _ = eng.track_frame(static_f, self._ctrl, B, n_mem, n_ptr, hw, fill)
         n_kernels = _lib.launch_count - before
         _lib.launch_count = before  # capturing launches nothing
