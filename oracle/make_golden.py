@@ -48,6 +48,11 @@ CASES = {
         seed=26, T=5,
         prompts=[("points", 4, 7, dict(points=[[256.0, 250.0], [100.0, 400.0]], labels=[1, 0]))],
         prop=dict(reverse=True)),
+    # apply_postprocessing=False (build_sam.py:108-122 overrides absent): a box prompt is 2 points, so the prompt frame
+    # takes the single-mask branch WITHOUT the stability fallback (mask_decoder.py:160-166), memory-encoder input is
+    # sigmoid-scaled instead of binarised, no hole filling
+    "t512_box_nopost": dict(seed=19, T=4, prompts=[("box", 0, 3, dict(box=[220.0, 200.0, 330.0, 300.0]))],
+                            prop=dict(), post=False),
 }
 
 
@@ -98,8 +103,15 @@ def run_case(model, cfg, fill):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    model = load_reference_predictor()
+    only = sys.argv[1:]
+    models = {}
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
+        post = cfg.get("post", True)
+        if post not in models:
+            models[post] = load_reference_predictor(apply_postprocessing=post)
+        model = models[post]
         plain, clip, _ = run_case(model, cfg, fill=False)
         filled, _, _ = run_case(model, cfg, fill=True)
         n_holes = int((plain["low"] != filled["low"]).sum())

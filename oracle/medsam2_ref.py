@@ -101,10 +101,19 @@ class Cfg:
     multimask_max_pt_num = 1
     fill_hole_area = 8
     binarize_mask_from_pts_for_mem_enc = True
+    dynamic_multimask_via_stability = True  # builder override (build_sam.py:108-122); False with apply_postprocessing=False
     dynamic_multimask_stability_delta = 0.05
     dynamic_multimask_stability_thresh = 0.98
     non_overlap_masks = False
     non_overlap_masks_for_mem_enc = False
+
+
+class CfgNoPost(Cfg):
+    """build_sam2_video_predictor(..., apply_postprocessing=False): none of the builder's overrides
+    (build_sam.py:108-122), i.e. the class defaults of SAM2Base / MaskDecoder / SAM2VideoPredictor."""
+    dynamic_multimask_via_stability = False
+    binarize_mask_from_pts_for_mem_enc = False
+    fill_hole_area = 0
 
 
 def hiera_block_plan(cfg=Cfg):
@@ -441,7 +450,10 @@ class RefModel:
         score = self._mlp(d + "pred_obj_score_head.", hs[:, 0], 3)
         if multimask_output:
             return masks[:, 1:], iou[:, 1:], mask_tokens_out[:, 1:], score
-        masks, iou = self._stability_select(masks, iou)
+        if self.cfg.dynamic_multimask_via_stability:  # mask_decoder.py:160-166
+            masks, iou = self._stability_select(masks, iou)
+        else:
+            masks, iou = masks[:, 0:1], iou[:, 0:1]
         return masks, iou, mask_tokens_out[:, 0:1], score
 
     def _stability_select(self, masks, iou):

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle.make_golden import CASES
-from oracle.medsam2_ref import RefPredictor
+from oracle.medsam2_ref import Cfg, CfgNoPost, RefPredictor
 from tests.golden_cases import dice, replay
 from us_video_medsam2_b200 import synth
 
@@ -15,13 +15,14 @@ FP32_TOL = 2e-4  # |logit| difference between two fp32 CPU evaluations with diff
 
 
 @pytest.mark.parametrize("name", ["t512_mask_fwd", "t512_absent_fwd", "t512_two_obj_mask_box",
-                                  "t512_points_reverse"])
+                                  "t512_points_reverse", "t512_box_nopost"])
 @pytest.mark.parametrize("fill", [False, True])
 def test_oracle_matches_reference_fixture(golden_dir, name, fill):
-    if fill and name in ("t512_mask_fwd",):
+    if fill and name in ("t512_mask_fwd", "t512_box_nopost"):
         pytest.skip("covered by the unfilled variant + the two fill-heavy cases (keeps CPU suite short)")
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    pred = RefPredictor(synth.make_state_dict(CASES[name]["seed"]), fill_holes=fill)
+    cfg = Cfg if CASES[name].get("post", True) else CfgNoPost
+    pred = RefPredictor(synth.make_state_dict(CASES[name]["seed"]), cfg=cfg, fill_holes=fill)
     with torch.inference_mode():
         out = replay(pred, name)
     assert out["frames"] == g["frames"].tolist()

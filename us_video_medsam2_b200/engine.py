@@ -26,7 +26,9 @@ NO_OBJ_SCORE = -1024.0
 
 
 class ModelConfig:
-    """Hyper-parameters of sam2/configs/sam2.1_hiera_t512.yaml (+ builder overrides, build_sam.py:108-122)."""
+    """Hyper-parameters of sam2/configs/sam2.1_hiera_t512.yaml (+ builder overrides, build_sam.py:108-122, i.e. the
+    apply_postprocessing=True configuration; the predictor resets the three post-processing switches to the
+    reference's class defaults when the builder does not pass them)."""
     image_size = 512
     embed_dim = 96
     stages = (1, 2, 7, 2)
@@ -471,8 +473,11 @@ class Engine:
             h2 = sk(h1, W2, b2, M=B, x_rs=6 * 256, x_is=256, act=ACT_RELU, instances=6)
             y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
         masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 64, 64, feat_shared, hyper_bs=192)
+        # single-mask output without the stability fallback (apply_postprocessing=False, mask_decoder.py:160-166): a
+        # threshold no stability score can miss keeps mask token 0
+        stab_thresh = self.cfg.dynamic_multimask_stability_thresh if self.cfg.dynamic_multimask_via_stability else -1.0
         low, idx, iou_sel = ops.sam_select(masks, y[:, 32:], y, multimask, self.cfg.dynamic_multimask_stability_delta,
-                                           self.cfg.dynamic_multimask_stability_thresh, NO_OBJ_SCORE, iou_stride=192,
+                                           stab_thresh, NO_OBJ_SCORE, iou_stride=192,
                                            score_stride=192, iou_is_logit=True)
         score = y[:, 0:1].contiguous()
         P1, pb1, P2, pb2, P3, pb3 = w.obj_ptr_proj

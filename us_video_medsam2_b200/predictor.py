@@ -69,6 +69,8 @@ class SAM2VideoPredictor(nn.Module):
         cfg.dynamic_multimask_stability_delta = float(extra.get("dynamic_multimask_stability_delta", 0.05))
         cfg.dynamic_multimask_stability_thresh = float(extra.get("dynamic_multimask_stability_thresh", 0.98))
         cfg.fill_hole_area = fill_hole_area
+        # class default of SAM2Base (sam2_base.py:60-62) unless the builder's post-processing override passes it
+        cfg.binarize_mask_from_pts_for_mem_enc = bool(model_kwargs.get("binarize_mask_from_pts_for_mem_enc", False))
         self.cfg = cfg
         self.image_size = cfg.image_size
         self.num_maskmem = cfg.num_maskmem
@@ -142,7 +144,10 @@ class SAM2VideoPredictor(nn.Module):
 
     def _new_state(self, images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu):
         if offload_state_to_cpu:
-            raise NotImplementedError("offload_state_to_cpu: the memory bank is kept resident in HBM on this path")
+            # the reference moves per-frame outputs to host memory to fit long videos on small GPUs
+            # (sam2_video_predictor.py:70-75); here the whole session state of a 512-frame, 4-object clip is < 400 MB
+            # of the 180 GB of HBM, so the flag is accepted and the state simply stays resident
+            warnings.warn("offload_state_to_cpu is accepted but has no effect: the session state stays in HBM")
         self._sync_engine()
         dev = self.device
         st = {}
@@ -829,9 +834,6 @@ class SAM2VideoPredictor(nn.Module):
                 if tuple(m.shape[-2:]) != (128, 128):
                     m = ops.resize_bilinear_aa(m.float(), 128, 128)
                 dense = eng.embed_mask_prompt(m.contiguous(), B)
-            if not multimask and not cfg.dynamic_multimask_via_stability:
-                raise NotImplementedError("single-mask output without the stability fallback "
-                                          "(apply_postprocessing=False) is not wired on this path")
             o = eng.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, sparse, dense=dense, multimask=multimask)
         low = o["low"]
         mem_tok = None
