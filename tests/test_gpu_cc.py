@@ -121,3 +121,53 @@ def test_idempotent_and_area_checksum():
     # labelling the "label > 0" mask again gives the same labels
     l2, c2 = _C.get_connected_componnets((labels > 0).to(torch.uint8))
     assert torch.equal(l2, labels) and torch.equal(c2, counts)
+
+
+# ------------------------------------------------------------------------------------------------
+# against the REFERENCE's own CUDA kernel (oracle/_ref/ref_sam2_C.so, compiled for sm_100a from
+# /root/reference/sam2/csrc/connected_components.cu by oracle/build_ref_cc.py in the build container)
+# ------------------------------------------------------------------------------------------------
+def _reference_op():
+    from oracle.build_ref_cc import load
+
+    op = load()
+    if op is None:
+        pytest.skip("oracle/_ref/ref_sam2_C.so not built (python oracle/build_ref_cc.py in the build container)")
+    return op
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 2, 2), (4, 1, 128, 128), (2, 1, 64, 96), (3, 1, 30, 18), (1, 1, 256, 256),
+                                   (2, 1, 512, 640), (64, 1, 128, 128)])
+@pytest.mark.parametrize("density", [0.0, 0.1, 0.45, 0.6, 0.9, 1.0])
+def test_bit_exact_against_reference_kernel(shape, density):
+    ref = _reference_op()
+    rng = np.random.default_rng(hash(("ref", shape, density)) % (2 ** 32))
+    img = (rng.random(shape) < density).astype(np.uint8)
+    x = torch.from_numpy(img).cuda()
+    want_l, want_c = ref(x)
+    torch.cuda.synchronize()
+    got_l, got_c = _run(img)
+    assert np.array_equal(got_l, want_l.cpu().numpy())
+    assert np.array_equal(got_c, want_c.cpu().numpy())
+    # ... and the CPU oracle used by every GPU-less test is pinned to the same kernel
+    o_l, o_c = connected_components_ref(img)
+    assert np.array_equal(o_l, want_l.cpu().numpy()) and np.array_equal(o_c, want_c.cpu().numpy())
+
+
+def test_fill_holes_against_reference_kernel_composition():
+    """fill_holes_in_mask_scores (sam2/utils/misc.py:312-338) composed from the reference kernel vs the fused kernel."""
+    from us_video_medsam2_b200.cc import fill_holes_in_mask_scores
+
+    ref = _reference_op()
+    g = torch.Generator().manual_seed(5)
+    for n, scale in ((1, 0.05), (4, 0.5), (16, 1.0)):
+        mask = (torch.randn((n, 1, 128, 128), generator=g) * scale + 0.3 * scale).cuda()
+        mask[:, :, 40:60, 40:60] = mask[:, :, 40:60, 40:60].abs() + 0.01   # a solid blob with a few punched holes
+        mask[:, :, 45, 45] = -1.0
+        mask[:, :, 50:52, 50:53] = -0.5
+        labels, areas = ref((mask <= 0).to(torch.uint8))
+        is_hole = (labels > 0) & (areas <= 8)
+        want = torch.where(is_hole, torch.full_like(mask, 0.1), mask)
+        got = fill_holes_in_mask_scores(mask, 8)
+        assert torch.equal(got, want)
+        assert int(is_hole.sum()) > 0

@@ -163,3 +163,45 @@ def test_encoder_on_sm_partition_matches_alternating_schedule():
         assert dice(a, b) >= 0.999
         same = (a != 0.1) & (b != 0.1)  # a hole filled on one side only legitimately differs (threshold at 0)
         assert float((a - b).abs()[same].max()) <= 2e-3
+
+
+def test_partition_pipeline_reverse_multi_object_and_early_exit():
+    """The look-ahead pipeline under the less common drivers of propagate_in_video: reverse tracking from a point prompt
+    in the middle of the clip, two objects, a ragged tail batch, max_frame_num_to_track, and a generator abandoned half
+    way followed by a fresh pass on the same predictor.  Reference behaviour = the alternating schedule (encoder_sms=0)."""
+    T = 30
+    clip = synth.make_clip(T, kind="speckle").cuda()
+
+    def run(sms):
+        pred = _predictor(19, encoder_batch=4, encoder_sms=sms)
+        res = {}
+        st = pred.init_state(clip, 512, 512)
+        for i, m in enumerate(synth.multi_object_masks(2)):
+            pred.add_new_mask(st, T - 1, i + 1, m)
+        res["rev"] = [(t, lg.clone()) for t, _, lg in pred.propagate_in_video(st, reverse=True)]
+        pred.reset_state(st)
+        pred.add_new_points_or_box(st, 3, 9, points=np.array([[256.0, 250.0]], np.float32), labels=np.array([1], np.int32))
+        res["fwd_limited"] = [(t, lg.clone()) for t, _, lg in pred.propagate_in_video(st, max_frame_num_to_track=14)]
+        pred.reset_state(st)
+        pred.add_new_mask(st, 0, 1, synth.box_mask())
+        gen = pred.propagate_in_video(st)
+        for _ in range(7):
+            next(gen)
+        gen.close()  # abandoned: the pipeline must be torn down without leaving work that corrupts the next pass
+        assert "_pipeline" not in st
+        pred.reset_state(st)
+        pred.add_new_mask(st, 0, 1, synth.box_mask())
+        res["fwd"] = [(t, lg.clone()) for t, _, lg in pred.propagate_in_video(st)]
+        return res, pred
+
+    base, _ = run(0)
+    got, pred = run(48)
+    if pred._partition_error is not None:
+        pytest.skip(f"no SM partition on this driver: {pred._partition_error}")
+    assert [t for t, _ in base["rev"]] == list(range(T - 1, -1, -1)) == [t for t, _ in got["rev"]]
+    assert [t for t, _ in base["fwd_limited"]] == list(range(3, 18)) == [t for t, _ in got["fwd_limited"]]
+    assert [t for t, _ in got["fwd"]] == list(range(T))
+    for key in base:
+        for (t, a), (_, b) in zip(base[key], got[key]):
+            assert a.shape == b.shape
+            assert dice(a.cpu(), b.cpu()) >= 0.998, (key, t)

@@ -100,6 +100,48 @@ def main():
                   f"{t_o3 / nb:6.3f} ms/frame", flush=True)
         except Exception as e:
             print("              complement capture failed:", repr(e))
+    # the other way round: the TRACKED FRAME on the first-class SM group (cluster-friendly), encoder on the remainder
+    from us_video_medsam2_b200.pipeline import SmPartition
+    for sms in [int(x) for x in os.environ.get("TRACK_SMS", "96,104,112").split(",") if x]:
+        try:
+            part = SmPartition(dev, sms)
+            p3 = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=nb)
+            p3.load_state_dict(synth.make_state_dict(19), strict=True)
+            eng = p3._sync_engine()
+            eng.sm_budget = part.sms
+            for _ in range(2):
+                st = p3.init_state(clip, 512, 512)
+                p3.add_new_mask(st, 0, 1, synth.box_mask())
+                for _ in p3.propagate_in_video(st):
+                    pass
+            torch.cuda.synchronize()
+            steady3 = max([k for k in p3._graphs if k[0] != "encoder"], key=lambda k: (k[1], k[2]))
+            base = p3._graphs[steady3]
+            ops.set_sm_budget(part.sms)
+            eng._tail_stream = None
+            # second stream of the same green context for the forked tail: reuse rest_stream2's constructor path
+            from cuda.bindings import driver as drv
+            err, raw2 = drv.cuGreenCtxStreamCreate(part._ctx, drv.CUstream_flags.CU_STREAM_NON_BLOCKING, 0)
+            eng._tail_stream = torch.cuda.ExternalStream(int(raw2), device=dev)
+            trk = p3._capture_graph(steady3, base[1], stream=part.stream)
+            ops.set_sm_budget(part.rest_sms)
+            # encoder captured on the remainder green context
+            class _P:  # duck-typed partition view for _encoder_graph
+                pass
+            rp = _P()
+            rp.stream, rp.sms, rp.total_sms = part.rest_stream, part.rest_sms, part.total_sms
+            enc3 = p3._encoder_graph(nb, 0, rp)
+            t_t = replay_ms([(trk[0], nb)], streams=[part.stream])
+            t_e = replay_ms([(enc3[0], 1)], streams=[part.rest_stream])
+            t_o = replay_ms([(enc3[0], 1), (trk[0], nb)], streams=[part.rest_stream, part.stream])
+            print(f"tracking on group {part.sms:3d} SMs alone {t_t / nb:6.3f}, encoder on remainder {part.rest_sms} alone "
+                  f"{t_e / nb:6.3f}, concurrent {t_o / nb:6.3f} ms/frame", flush=True)
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            print(f"swap {sms}: failed {e!r}", flush=True)
+        finally:
+            ops.set_sm_budget(0)
 
 
 if __name__ == "__main__":

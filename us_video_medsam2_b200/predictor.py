@@ -376,12 +376,13 @@ class SAM2VideoPredictor(nn.Module):
             plan = BatchPlan(first, last, step, n, include_tail=True)
             self._remote.announce(plan)
             return FeaturePipeline(plan, RemoteProducer(self._remote, n, self.device), depth=len(self._remote.ranks))
-        if n < 2 or len(tracked) < 2 * n:
-            return None
+        if n < 2 or len(tracked) <= n:
+            return None  # a single batch: nothing to overlap with
         part = self._partition()
         if part is None:
             return None
-        plan = BatchPlan(first, last, step, n, include_tail=False)
+        # a final partial batch replays the same n-frame graph (stale inputs in the unused rows, outputs ignored)
+        plan = BatchPlan(first, last, step, n, include_tail=True)
         try:
             for slot in range(2):
                 self._encoder_graph(n, slot, part)
