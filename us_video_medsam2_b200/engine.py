@@ -304,8 +304,29 @@ class Engine:
         self.cfg = weights.cfg
         self.sm_budget = 148  # SMs the tracked frame may count on (fewer while the encoder owns an SM partition)
         self._tail_stream = None
+        self._side_streams = {}
+        # independent sub-chains of a frame (memory-bank projections || first self-attention block; token side || image
+        # side of the two-way decoder; pix_feat projection || mask down-sampler) run on forked streams, i.e. as parallel
+        # branches of the captured frame graph -- the frame is a latency chain of ~125 small kernels, not throughput bound
+        self.fork_branches = os.environ.get("USVM2_FORK", "1") != "0"
         self.fused_windows = os.environ.get("USVM2_FUSED_WINDOWS", "1") != "0"
         self.use_token_chain = os.environ.get("USVM2_TOKEN_CHAIN", "0") == "1"
+
+    # ---------------------------------------------------------------- forked branches
+    def _side(self, i):
+        st = self._side_streams.get(i)
+        if st is None:
+            st = self._side_streams[i] = torch.cuda.Stream()
+        return st
+
+    @staticmethod
+    def _handoff(dst, src, *tensors):
+        """Make stream `dst` wait for everything enqueued on `src`; the listed tensors (allocated on one of the two) are
+        from now on used on `dst` as well, which the caching allocator must know before it recycles their blocks."""
+        dst.wait_stream(src)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(dst)
 
     # ---------------------------------------------------------------- image encoder
     def encode_frames(self, imgs):
@@ -364,20 +385,21 @@ class Engine:
         return pair[0], pair[1]
 
     # ---------------------------------------------------------------- memory attention
-    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B):
+    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None):
         """feat fp32 [1024,256] (one frame, shared by the B objects); k_in / v_in bf16 [B, Nk, 64] assembled memory
         (k_in already carries the position encodings), the last n_ptr_tok rows are object-pointer tokens (no RoPE).
         Returns fp32 [B*1024, 256]  (MemoryAttention.forward, memory_attention.py:119-169; RoPEAttention,
         sam/transformer.py:311-360).  RoPE is fused into the q / k projection epilogues; the key / value
-        projections of the 4 layers are batched into one GEMM each."""
+        projections of the 4 layers are batched into one GEMM each (`project_memory`).
+        `bank`: callable returning (k_all, v_all) -- lets the caller produce the projected bank on a forked stream; it is
+        called right before the first cross-attention, after the first self-attention block has been enqueued."""
         w = self.w
         T = 1024
         cs, sn = w.rope_cos, w.rope_sin
         x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T)
-        k_in2, v_in2 = k_in.view(B * Nk, 64), v_in.view(B * Nk, 64)
-        _, k_all = ops.gemm_bf16(k_in2, w.ca_k_all[0], bias=w.ca_k_all[1], bf16=True,
-                                 rope=(cs, sn, 1024, Nk, Nk - n_ptr_tok))          # [B*Nk, 4*256], rotated
-        _, v_all = ops.gemm_bf16(v_in2, w.ca_v_all[0], bias=w.ca_v_all[1], bf16=True)  # [B*Nk, 4*256]
+        k_all = v_all = None
+        if bank is None:
+            k_all, v_all = self.project_memory(k_in, v_in, Nk, n_ptr_tok, B)
         for li, L in enumerate(w.ma_layers):
             _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
             _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
@@ -390,6 +412,8 @@ class Engine:
             x, h = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True,
                                  ln=(L["n2"][0], L["n2"][1], 1e-5))
             _, q = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], bf16=True, rope=(cs, sn, 256, T, T))
+            if k_all is None:
+                k_all, v_all = bank()
             o = ops.fmha(q, k_all, v_all, B, 1, T, Nk, 256, (0, T * 256, 256, 256), (li * 256, Nk * 1024, 1024, 256),
                          (li * 256, Nk * 1024, 1024, 256), num_splits=self._splits(B, Nk))
             x, h = ops.gemm_bf16(o.view(B * T, 256), L["ca_o"][0], bias=L["ca_o"][1], residual=x, f32=True,
@@ -398,6 +422,15 @@ class Engine:
             x, _ = ops.gemm_bf16(m, L["l2"][0], bias=L["l2"][1], residual=x, f32=True)
         out, _ = ops.layernorm(x, *w.ma_norm, 1e-5, f32=True)
         return out
+
+    def project_memory(self, k_in, v_in, Nk, n_ptr_tok, B):
+        """Key / value projections of the assembled bank for all 4 layers at once: ([B*Nk, 4*256] rotated keys, values)."""
+        w = self.w
+        k_in2, v_in2 = k_in.view(B * Nk, 64), v_in.view(B * Nk, 64)
+        _, k_all = ops.gemm_bf16(k_in2, w.ca_k_all[0], bias=w.ca_k_all[1], bf16=True,
+                                 rope=(w.rope_cos, w.rope_sin, 1024, Nk, Nk - n_ptr_tok))
+        _, v_all = ops.gemm_bf16(v_in2, w.ca_v_all[0], bias=w.ca_v_all[1], bf16=True)
+        return k_all, v_all
 
     def _splits(self, B, Nk):
         """Split-KV factor: the tcgen05 kernel runs 8 query tiles of 128 per object; fill the 148 SMs."""
@@ -419,12 +452,28 @@ class Engine:
         output, memory encoder, hole filling, video-resolution resize.  Everything the frame leaves behind is
         written into slot ctrl->cur_frame of the frame store.  f: dict(feat, feat_bf16, feat_s0, feat_s1) of this
         frame.  Returns (video_res logits [B,1,H,W], hole-filled low-res logits [B,1,128,128])."""
-        k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
-        pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B)
+        main = torch.cuda.current_stream()
+        if self.fork_branches:
+            # the bank (gather + temporal encodings + K/V projections of ~7 k rows) does not depend on this frame's
+            # features, the first self-attention block does not depend on the bank: two branches, joined before the
+            # first cross-attention
+            side = self._side(0)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
+                kv = self.project_memory(k_in, v_in, Nk, n_tok, B)
+
+            def bank():
+                self._handoff(main, side, *kv)
+                return kv
+
+            pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank)
+        else:
+            k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
+            pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B)
         o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, self.no_point_tokens(B), multimask=True)
         # The user-facing tail (single-CTA hole filling, store write, video-resolution resize) is independent of the
         # memory encoder: it runs on a forked stream -- a parallel branch of the captured graph -- and joins at the end.
-        main = torch.cuda.current_stream()
         if self._tail_stream is None:
             self._tail_stream = torch.cuda.Stream()
         tail = self._tail_stream
@@ -459,19 +508,25 @@ class Engine:
         ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
         sk = ops.gemm_skinny
         chain = Nt == 8 and self.use_token_chain
+        tok = torch.cuda.current_stream()
+        img_s = self._side(1) if (self.fork_branches and not chain) else None
         if chain:
             hs, y, keys = self._two_way_transformer_chain(tokens, keys, B)
         else:
-            hs, keys = self._two_way_transformer(tokens, keys, B, Nt)
-        g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=True)
-        u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_shared)
-        g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=True)
+            hs, keys = self._two_way_transformer(tokens, keys, B, Nt, img_stream=img_s)
+        # output upscaling (image side) || the six token heads (token side); they meet in the mask product
+        with torch.cuda.stream(img_s if img_s is not None else tok):
+            g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=True)
+            u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_shared)
+            g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=True)
         if not chain:
             # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
             W1, b1, W2, b2, W3, b3 = w.heads6
             h1 = sk(None, W1, b1, M=B, x_ptr=hs.data_ptr(), x_rs=Nt * 256, x_is=256, act=ACT_RELU, instances=6)
             h2 = sk(h1, W2, b2, M=B, x_rs=6 * 256, x_is=256, act=ACT_RELU, instances=6)
             y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
+        if img_s is not None:
+            self._handoff(tok, img_s, g2, keys)
         masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 64, 64, feat_shared, hyper_bs=192)
         # single-mask output without the stability fallback (apply_postprocessing=False, mask_decoder.py:160-166): a
         # threshold no stability score can miss keeps mask token 0
@@ -497,15 +552,26 @@ class Engine:
         ops.objptr_mix_(ptr, score, w.no_obj_ptr)
         return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36])
 
-    def _two_way_transformer(self, tokens, keys, B, Nt):
-        """TwoWayTransformer (sam/transformer.py:90-135) with one launch per token-side layer: any token count."""
+    def _two_way_transformer(self, tokens, keys, B, Nt, img_stream=None):
+        """TwoWayTransformer (sam/transformer.py:90-135) with one launch per token-side layer: any token count.
+        With `img_stream` the image-side work (the fused k / v / q projections of `keys`, image->token attention and its
+        output projection + norm) is enqueued there and only meets the token side where the data does: the projection of
+        layer l overlaps the token self-attention chain of layer l, the image->token block of layer l overlaps the token
+        self-attention of layer l + 1.  On return `keys` is still owned by `img_stream` (the caller continues there)."""
         w = self.w
         T = 1024
         queries = tokens
         ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
         sk = ops.gemm_skinny
+        tok = torch.cuda.current_stream()
+        par = img_stream is not None
+        img_s = img_stream if par else tok
+        if par:
+            self._handoff(img_s, tok, keys, tokens)
         for l, Lyr in enumerate(w.dec_layers):
             sa, t2i, i2t = Lyr["sa"], Lyr["t2i"], Lyr["i2t"]
+            with torch.cuda.stream(img_s):
+                img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T, tf32=True)  # [B*T, 384]
             if l == 0:
                 qkv = sk(queries, sa["qkv_w"], sa["qkv_b"])
                 o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
@@ -517,20 +583,26 @@ class Engine:
                 queries = sk(o, *sa["o"], residual=queries)
             queries = ln(queries, Lyr["norms"][0])
             q = sk(queries, *t2i["q"], x2=tokens)
-            img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T, tf32=True)  # [B*T, 384]
+            if par:
+                self._handoff(tok, img_s, img)
             o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
             queries = ln(sk(o, *t2i["o"], residual=queries), Lyr["norms"][1])
             m = sk(queries, *Lyr["mlp"][0], act=ACT_RELU)
             queries = ln(sk(m, *Lyr["mlp"][1], residual=queries), Lyr["norms"][2])
             kv2 = sk(queries, i2t["kv_w"], i2t["kv_b"], x2=tokens, x2_cols=128)  # [k (with pe) | v]
-            o = ops.attn_i2t(img[:, 256:384], kv2[:, 0:128], kv2[:, 128:256], B, T, Nt)
-            keys = ln(ops.gemm_f32(o, *i2t["o"], residual=keys, tf32=True), Lyr["norms"][3])
+            if par:
+                self._handoff(img_s, tok, kv2)
+            with torch.cuda.stream(img_s):
+                o2 = ops.attn_i2t(img[:, 256:384], kv2[:, 0:128], kv2[:, 128:256], B, T, Nt)
+                keys = ln(ops.gemm_f32(o2, *i2t["o"], residual=keys, tf32=True), Lyr["norms"][3])
         fin = w.dec_final
+        with torch.cuda.stream(img_s):
+            img = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T, tf32=True)  # [B*T, 256]
         q = sk(queries, *fin["q"], x2=tokens)
-        img = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T, tf32=True)  # [B*T, 256]
+        if par:
+            self._handoff(tok, img_s, img)
         o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
         hs = ln(sk(o, *fin["o"], residual=queries), w.dec_final_norm)  # [B*Nt, 256]
-
         return hs, keys
 
     def _two_way_transformer_chain(self, tokens, keys, B):
