@@ -160,9 +160,9 @@ def test_encoder_on_sm_partition_matches_alternating_schedule():
         assert torch.equal(feats[0][k], feats[1][k]), k
     assert len(outs[0]) == len(outs[1]) == T
     for a, b in zip(*outs):
-        assert dice(a, b) >= 0.999
+        assert dice(a, b) >= DICE_BAR  # two bf16 evaluation orders of the same frame: the parity bar applies
         same = (a != 0.1) & (b != 0.1)  # a hole filled on one side only legitimately differs (threshold at 0)
-        assert float((a - b).abs()[same].max()) <= 2e-3
+        assert float((a - b).abs()[same].max()) <= LOGIT_TOL
 
 
 def test_partition_pipeline_reverse_multi_object_and_early_exit():
@@ -204,4 +204,4 @@ def test_partition_pipeline_reverse_multi_object_and_early_exit():
     for key in base:
         for (t, a), (_, b) in zip(base[key], got[key]):
             assert a.shape == b.shape
-            assert dice(a.cpu(), b.cpu()) >= 0.998, (key, t)
+            assert dice(a.cpu(), b.cpu()) >= DICE_BAR, (key, t)

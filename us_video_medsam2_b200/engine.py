@@ -159,6 +159,10 @@ class PackedWeights:
                 l1=(w16(p + "linear1.weight"), f32(p + "linear1.bias")),
                 l2=(w16(p + "linear2.weight"), f32(p + "linear2.bias"))))
         self.ma_norm = (f32("memory_attention.norm.weight"), f32("memory_attention.norm.bias"))
+        # tracked frames feed the decoder `norm(x) + no_mask_embed` (dense prompt = no_mask_embed broadcast,
+        # prompt_encoder.py:176-180): the constant row is folded into the final norm's bias
+        self.ma_norm_nomask = (self.ma_norm[0], dev(g("memory_attention.norm.bias")
+                                                    + g("sam_prompt_encoder.no_mask_embed.weight").reshape(256)))
         # the cross-attention key / value inputs are the same for all 4 layers: project them with ONE GEMM each
         ca = "memory_attention.layers.{}.cross_attn_image."
         self.ca_k_all = (dev(torch.cat([g(ca.format(l) + "k_proj.weight") for l in range(4)]), BF16),
@@ -385,14 +389,15 @@ class Engine:
         return pair[0], pair[1]
 
     # ---------------------------------------------------------------- memory attention
-    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None):
+    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None, fold_no_mask=False):
         """feat fp32 [1024,256] (one frame, shared by the B objects); k_in / v_in bf16 [B, Nk, 64] assembled memory
         (k_in already carries the position encodings), the last n_ptr_tok rows are object-pointer tokens (no RoPE).
         Returns fp32 [B*1024, 256]  (MemoryAttention.forward, memory_attention.py:119-169; RoPEAttention,
         sam/transformer.py:311-360).  RoPE is fused into the q / k projection epilogues; the key / value
         projections of the 4 layers are batched into one GEMM each (`project_memory`).
         `bank`: callable returning (k_all, v_all) -- lets the caller produce the projected bank on a forked stream; it is
-        called right before the first cross-attention, after the first self-attention block has been enqueued."""
+        called right before the first cross-attention, after the first self-attention block has been enqueued.
+        fold_no_mask: return norm(x) + no_mask_embed, the decoder's `src` on tracked frames (sam_heads(src_ready=True))."""
         w = self.w
         T = 1024
         cs, sn = w.rope_cos, w.rope_sin
@@ -420,7 +425,7 @@ class Engine:
                                  ln=(L["n3"][0], L["n3"][1], 1e-5))
             _, m = ops.gemm_bf16(h, L["l1"][0], bias=L["l1"][1], act=ACT_RELU, bf16=True)
             x, _ = ops.gemm_bf16(m, L["l2"][0], bias=L["l2"][1], residual=x, f32=True)
-        out, _ = ops.layernorm(x, *w.ma_norm, 1e-5, f32=True)
+        out, _ = ops.layernorm(x, *(w.ma_norm_nomask if fold_no_mask else w.ma_norm), 1e-5, f32=True)
         return out
 
     def project_memory(self, k_in, v_in, Nk, n_ptr_tok, B):
@@ -462,34 +467,41 @@ class Engine:
             with torch.cuda.stream(side):
                 k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
                 kv = self.project_memory(k_in, v_in, Nk, n_tok, B)
+                # pix_feat_proj of the memory encoder only reads this frame's features: off the critical path here
+                pp, _ = ops.gemm_bf16(f["feat_bf16"], *self.w.pix_proj, f32=True)
 
             def bank():
-                self._handoff(main, side, *kv)
+                self._handoff(main, side, kv[0], kv[1], pp)
                 return kv
 
-            pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank)
+            pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank, fold_no_mask=True)
         else:
+            pp = None
             k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
-            pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B)
-        o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, self.no_point_tokens(B), multimask=True)
+            pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B, fold_no_mask=True)
+        o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, self.no_point_tokens(B), multimask=True, src_ready=True,
+                           defer_ptr=True)
         # The user-facing tail (single-CTA hole filling, store write, video-resolution resize) is independent of the
         # memory encoder: it runs on a forked stream -- a parallel branch of the captured graph -- and joins at the end.
         if self._tail_stream is None:
             self._tail_stream = torch.cuda.Stream()
         tail = self._tail_stream
-        tail.wait_stream(main)
+        self._handoff(tail, main, o["low"], o["score"], *o.get("_keep", ()))
         with torch.cuda.stream(tail):
+            if o["obj_ptr"] is None:
+                o["obj_ptr"] = o["finish_ptr"]()
             pm = ops.fill_holes(o["low"], fill_hole_area) if fill_hole_area > 0 else o["low"]
             ops.store_outputs(ctrl, o["obj_ptr"], o["score"], pm)
             vh, vw = video_hw
             video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
         mask_in = self.mem_mask_input(o["low"], False)
-        self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl)
-        main.wait_stream(tail)
+        self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl, pix_proj=pp)
+        self._handoff(main, tail, video, pm)
         return video, pm
 
     # ---------------------------------------------------------------- SAM heads
-    def sam_heads(self, pix_feat, feat_s0, feat_s1, B, sparse, dense=None, multimask=True, feat_shared=True):
+    def sam_heads(self, pix_feat, feat_s0, feat_s1, B, sparse, dense=None, multimask=True, feat_shared=True,
+                  src_ready=False, defer_ptr=False):
         """pix_feat fp32 [B*1024,256]; sparse fp32 [B,P,256] prompt tokens; dense fp32 [B*1024,256] or None
         (-> no_mask_embed).  Returns dict(low [B,1,128,128], obj_ptr [B,256], score [B,1], iou [B,1]).
         (_forward_sam_heads sam2_base.py:1010-1166 + MaskDecoder mask_decoder.py:110-295 +
@@ -497,7 +509,10 @@ class Engine:
         GEMM, image-side projections of a layer are one fused GEMM, attention on the t2i / i2t kernels."""
         w = self.w
         T = 1024
-        if dense is None:
+        if src_ready:  # pix_feat already carries the dense prompt embedding (memory_attention(fold_no_mask=True))
+            assert dense is None
+            src = pix_feat
+        elif dense is None:
             src, _ = ops.axpby(pix_feat, w.no_mask_embed, rows=B * T, y_mod=1)
         else:
             src, _ = ops.axpby(pix_feat, dense, rows=B * T)
@@ -536,6 +551,17 @@ class Engine:
                                            score_stride=192, iou_is_logit=True)
         score = y[:, 0:1].contiguous()
         P1, pb1, P2, pb2, P3, pb3 = w.obj_ptr_proj
+        if defer_ptr and not chain:
+            # the pointer (3-layer MLP on the selected mask token + no-object mix) is not needed by the memory encoder: the
+            # caller runs it on its forked tail branch
+            def finish_ptr():
+                t1 = sk(None, P1[0], pb1[0], M=B, x_ptr=hs.data_ptr() + 4 * 2 * 256, x_rs=Nt * 256, row_select=idx,
+                        x_sel_stride=256, act=ACT_RELU)
+                ptr = sk(sk(t1, P2[0], pb2[0], act=ACT_RELU), P3[0], pb3[0])
+                return ops.objptr_mix_(ptr, score, w.no_obj_ptr)
+
+            return dict(low=low, obj_ptr=None, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36],
+                        finish_ptr=finish_ptr, _keep=(hs, idx))
         if chain:
             E = lambda *shape: ops.empty(shape, F32, src)
             t1, t2, ptr = E(B, 256), E(B, 256), E(B, 256)
@@ -691,7 +717,7 @@ class Engine:
         return dict(low=low, high=high, obj_ptr=ptr, score=score)
 
     # ---------------------------------------------------------------- memory encoder
-    def encode_memory(self, feat_bf16, mask_in512, score, B, ctrl=None):
+    def encode_memory(self, feat_bf16, mask_in512, score, B, ctrl=None, pix_proj=None):
         """mask_in512 fp32 [B,512,512]: already sigmoid*20-10 / binarised (see Engine.mem_mask_input);
         feat_bf16 [1024,256] raw frame features.  Returns bf16 token-major memory [B,1024,64], or writes it into the
         frame store slot named by `ctrl`
@@ -703,7 +729,9 @@ class Engine:
             Cin = Cout
         A4 = ops.im2col_nhwc(x, B, 64, 64, 64, 3, 2, 1)
         _, c4n = ops.gemm_bf16(A4, w.md_conv3_w, bias=w.md_conv3_b, ln=(w.md_ln3[0], w.md_ln3[1], 1e-6, True))
-        pp, _ = ops.gemm_bf16(feat_bf16, *w.pix_proj, f32=True)  # pix_feat_proj, shared by all objects
+        pp = pix_proj  # pix_feat_proj, shared by all objects (precomputed by the caller on a forked branch, or here)
+        if pp is None:
+            pp, _ = ops.gemm_bf16(feat_bf16, *w.pix_proj, f32=True)
         x, _ = ops.gemm_bf16(c4n, w.md_out[0], bias=w.md_out[1], residual=pp, res_mod=1024, f32=True)
         xb = None
         for i, Lf in enumerate(w.fuser):
