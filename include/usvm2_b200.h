@@ -195,6 +195,11 @@ typedef struct usvm_frame_ctrl {
 } usvm_frame_ctrl;
 /* writes *ctrl_host into device memory through a by-value kernel parameter (asynchronous, no staging copy) */
 int usvm_set_frame_ctrl(usvm_frame_ctrl* ctrl_dev, const usvm_frame_ctrl* ctrl_host, void* stream);
+/* the same plus up to 4 device-to-device copies (src[i] -> dst[i], bytes[i] a multiple of 16, 16-byte aligned) in the
+ * same launch: the frame's backbone features (sam2_video_predictor.py:879-910 `_get_image_feature`) into the static
+ * inputs of the captured tracked-frame graph */
+int usvm_frame_prologue(usvm_frame_ctrl* ctrl_dev, const usvm_frame_ctrl* ctrl_host, const void* const* src,
+                        void* const* dst, const long long* bytes, int n_seg, void* stream);
 /* memory feature epilogue (sam2_base.py:1488-1496; sam2_video_predictor.py:956): + no_obj_embed_spatial where
  * score <= 0 (score stride in elements), rounded to bf16 into mem_bf16 [B, T, Cm], or -- when mem_bf16 is NULL --
  * into slot ctrl_dev->cur_frame of ctrl_dev->mem_store */

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "usvm_upscale2_masks": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P],
     "usvm_finalize_memory": [_P, _P, _I, _P, _P, _I, _I, _I, _P, _P],
     "usvm_set_frame_ctrl": [_P, C.POINTER(FrameCtrl), _P],
+    "usvm_frame_prologue": [_P, C.POINTER(FrameCtrl), C.POINTER(_P), C.POINTER(_P), C.POINTER(_LL), _I, _P],
     "usvm_ptr_tpos": [_P, _P, _P, _P, _I, _P],
     "usvm_build_memory_store": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "usvm_store_outputs": [_P, _P, _P, _I, _P, _I, _I, _I, _P],

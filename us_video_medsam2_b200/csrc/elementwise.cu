@@ -425,6 +425,25 @@ __global__ void set_frame_ctrl_kernel(usvm_frame_ctrl* dst, const usvm_frame_ctr
   if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
 }
 
+// Everything a replay of the tracked-frame graph needs refreshed, in ONE launch: the control block (by-value parameter)
+// and the frame's backbone features copied into the graph's static input buffers (up to 4 segments, 16-byte units).
+struct FrameSegments {
+  const uint4* src[4];
+  uint4* dst[4];
+  long long n16[4];  // 16-byte units per segment
+};
+__global__ void frame_prologue_kernel(usvm_frame_ctrl* dst, const usvm_frame_ctrl v, const FrameSegments seg) {
+  PDL_ENTRY();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const uint4* __restrict__ a = seg.src[s];
+    uint4* __restrict__ b = seg.dst[s];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < seg.n16[s]; i += stride) b[i] = __ldg(a + i);
+  }
+}
+
 // slot ctrl->cur_frame of the pointer / score / mask stores <- this frame's outputs
 __global__ void store_outputs_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ obj_ptr,
                                      const float* __restrict__ score, int score_stride, const float* __restrict__ masks,
@@ -592,6 +611,25 @@ extern "C" int usvm_store_outputs(const usvm_frame_ctrl* ctrl_dev, const float* 
   if (!ctrl_dev || !obj_ptr || !score || !masks || B <= 0) return USVM_ERR_ARG;
   usvm_launch(store_outputs_kernel, dim3(grid_for((long long)B * (ptr_dim + 1 + hw))), dim3(256), 0, STREAM, ctrl_dev, obj_ptr, score,
                                                                                        score_stride, masks, B, ptr_dim, hw);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_frame_prologue(usvm_frame_ctrl* ctrl_dev, const usvm_frame_ctrl* ctrl_host, const void* const* src,
+                                   void* const* dst, const long long* bytes, int n_seg, void* stream) {
+  if (!ctrl_dev || !ctrl_host || n_seg < 0 || n_seg > 4 || (n_seg > 0 && (!src || !dst || !bytes))) return USVM_ERR_ARG;
+  FrameSegments seg{};
+  long long total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (!src[i] || !dst[i] || bytes[i] < 0 || (bytes[i] & 15) || (reinterpret_cast<uintptr_t>(src[i]) & 15) ||
+        (reinterpret_cast<uintptr_t>(dst[i]) & 15))
+      return USVM_ERR_ARG;
+    seg.src[i] = reinterpret_cast<const uint4*>(src[i]);
+    seg.dst[i] = reinterpret_cast<uint4*>(dst[i]);
+    seg.n16[i] = bytes[i] / 16;
+    total += seg.n16[i];
+  }
+  const int grid = (int)max(1LL, min(148LL * 4, (total + 255) / 256));
+  usvm_launch(frame_prologue_kernel, dim3(grid), dim3(256), 0, STREAM, ctrl_dev, *ctrl_host, seg);
   return usvm_check_launch();
 }
 

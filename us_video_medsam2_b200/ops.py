@@ -319,9 +319,11 @@ def new_frame_ctrl(device):
     return torch.zeros(C.sizeof(FrameCtrl) // 8 + 1, dtype=torch.int64, device=device)
 
 
-def set_frame_ctrl(ctrl_dev, store, obj0, cur_frame, mem_frames, mem_tpos, ptr_frames, ptr_rel):
+def set_frame_ctrl(ctrl_dev, store, obj0, cur_frame, mem_frames, mem_tpos, ptr_frames, ptr_rel, copies=None):
     """Fill the device control block through a by-value kernel parameter (async, no staging copy).  `obj0` offsets the
-    store bases so that a per-object run (B = 1) addresses object obj0 of a multi-object store."""
+    store bases so that a per-object run (B = 1) addresses object obj0 of a multi-object store.
+    copies: up to 4 (src, dst) tensor pairs of equal size copied by the same launch (the frame's features into the static
+    inputs of the captured frame graph)."""
     c = FrameCtrl()
     c.mem_store = store.mem.data_ptr() + 2 * obj0 * store.mem.stride(1)
     c.ptr_store = store.ptr.data_ptr() + 4 * obj0 * store.ptr.stride(1)
@@ -335,7 +337,16 @@ def set_frame_ctrl(ctrl_dev, store, obj0, cur_frame, mem_frames, mem_tpos, ptr_f
         c.mem_frame[i], c.mem_tpos[i] = f, t
     for i, (f, r) in enumerate(zip(ptr_frames, ptr_rel)):
         c.ptr_frame[i], c.ptr_rel[i] = f, r
-    call("usvm_set_frame_ctrl", ctrl_dev.data_ptr(), C.byref(c), _stream())
+    if not copies:
+        call("usvm_set_frame_ctrl", ctrl_dev.data_ptr(), C.byref(c), _stream())
+        return
+    n = len(copies)
+    src, dst, nbytes = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_longlong * n)()
+    for i, (a, b) in enumerate(copies):
+        if not (a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype and a.numel() == b.numel()):
+            raise ValueError("frame prologue copies need contiguous tensors of equal type and size")
+        src[i], dst[i], nbytes[i] = a.data_ptr(), b.data_ptr(), a.numel() * a.element_size()
+    call("usvm_frame_prologue", ctrl_dev.data_ptr(), C.byref(c), src, dst, nbytes, n, _stream())
 
 
 def finalize_memory(x, score, no_obj_embed, B, T=1024, Cm=64, ctrl=None):

@@ -765,7 +765,6 @@ class SAM2VideoPredictor(nn.Module):
         look = -1 if reverse else 1
         f = self._get_image_feature(st, frame_idx, lookahead=look)
         mem_slots, tpos_rows, ptr_slots, ptr_rel = self._memory_inputs(st, frame_idx, output_dict, reverse)
-        ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
         hw = (st["video_height"], st["video_width"])
         key = (B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
         ent = self._graphs.get(key) if self.use_cuda_graphs else None
@@ -773,15 +772,18 @@ class SAM2VideoPredictor(nn.Module):
             seen = self._graph_seen.get(key, 0) + 1
             self._graph_seen[key] = seen
             if seen >= 3:  # a signature that keeps recurring is the steady state: capture it
+                ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
                 ent = self._capture_graph(key, f)
         if ent is not None:
             graph, static_f, video, n_kernels = ent
-            for k, v in static_f.items():
-                v.copy_(f[k], non_blocking=True)
+            # one launch refreshes the control block and copies this frame's features into the graph's static inputs
+            ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel,
+                               copies=[(f[k], v) for k, v in static_f.items()])
             graph.replay()
             _lib.launch_count += n_kernels  # kernels of this library replayed by the graph
             video = video.clone()
         else:
+            ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
             video, _ = eng.track_frame(f, self._ctrl, B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
         return self._slot_views(st, frame_idx), video
 
