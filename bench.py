@@ -225,7 +225,7 @@ def run_b200(args, rank, world):
         from us_video_medsam2_b200.pipeline import RemoteEncoders
 
         pred.attach_remote_encoders(RemoteEncoders(list(range(1, world)), dev))
-    out_host = torch.empty((T, B, 512, 512), dtype=torch.uint8).pin_memory()
+    out_host = torch.empty((T, B, 512, 512), dtype=torch.bool).pin_memory()  # binary masks, 1 byte per pixel
     clip_dev = ops.normalize_gray_u8(gray_host.to(dev), synth.IMG_MEAN, synth.IMG_STD)  # resident copy for `value`
 
     def one_pass(images, sink=None):
@@ -235,7 +235,7 @@ def run_b200(args, rank, world):
         n = 0
         for t, ids, logits in pred.propagate_in_video(st):
             if sink is not None:
-                sink[t].copy_((logits[:, 0] > 0).to(torch.uint8), non_blocking=True)
+                sink[t].copy_(logits[:, 0] > 0, non_blocking=True)
             n += 1
         return n
 
