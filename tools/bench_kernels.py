@@ -179,7 +179,7 @@ def phases():
     print(f"memory_attention: {timeit(lambda: eng.memory_attention(feat, k_in, v_in, Nk, 64, B), iters=4):7.1f} us", flush=True)
     pix = rnd(B * T, 256, scale=0.5)
     s0, s1 = rnd(16384, 32), rnd(4096, 64)
-    print(f"sam_heads: {timeit(lambda: eng.sam_heads(pix, s0, s1, B, eng.no_point_tokens(B), multimask=True), iters=4):7.1f} us", flush=True)
+    print(f"sam_heads: {timeit(lambda: eng.sam_heads(pix, s0, s1, B, None, multimask=True), iters=4):7.1f} us", flush=True)
     low = rnd(B, 1, 128, 128, scale=0.07)
     score = rnd(B, 1)
     fb = rnd(T, 256, dtype=torch.bfloat16)

@@ -309,6 +309,7 @@ class Engine:
         self.sm_budget = 148  # SMs the tracked frame may count on (fewer while the encoder owns an SM partition)
         self._tail_stream = None
         self._side_streams = {}
+        self._tok_const = {}
         # independent sub-chains of a frame (memory-bank projections || first self-attention block; token side || image
         # side of the two-way decoder; pix_feat projection || mask down-sampler) run on forked streams, i.e. as parallel
         # branches of the captured frame graph -- the frame is a latency chain of ~125 small kernels, not throughput bound
@@ -479,8 +480,7 @@ class Engine:
             pp = None
             k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
             pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B, fold_no_mask=True)
-        o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, self.no_point_tokens(B), multimask=True, src_ready=True,
-                           defer_ptr=True)
+        o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, None, multimask=True, src_ready=True, defer_ptr=True)
         # The user-facing tail (single-CTA hole filling, store write, video-resolution resize) is independent of the
         # memory encoder: it runs on a forked stream -- a parallel branch of the captured graph -- and joins at the end.
         if self._tail_stream is None:
@@ -500,6 +500,30 @@ class Engine:
         return video, pm
 
     # ---------------------------------------------------------------- SAM heads
+    def token_constants(self, B):
+        """Tracked frames carry no prompt: their 8 decoder tokens (6 output tokens + 2 padding points) are constants of the
+        model, and so is everything the token side computes before it first meets the image -- layer 0's self-attention,
+        norm1 and the token->image query projection (transformer.py:181-199).  Computed once per object count with the
+        same kernels the general path uses; returns (tokens, queries after norm1, layer-0 token->image query)."""
+        hit = self._tok_const.get(B)
+        if hit is not None:
+            return hit
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("token constants must be computed before the frame graph is captured")
+        w = self.w
+        sk = ops.gemm_skinny
+        Nt = 8
+        tokens = torch.cat([w.out_tokens[None].expand(B, -1, -1), self.no_point_tokens(B)], dim=1)
+        tokens = tokens.reshape(B * Nt, 256).contiguous()
+        L0 = w.dec_layers[0]
+        qkv = sk(tokens, L0["sa"]["qkv_w"], L0["sa"]["qkv_b"])
+        o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
+        queries = ops.layernorm(sk(o, *L0["sa"]["o"]), L0["norms"][0][0], L0["norms"][0][1], 1e-5, f32=True)[0]
+        q = sk(queries, *L0["t2i"]["q"], x2=tokens)
+        torch.cuda.current_stream().synchronize()  # one-off: later uses come from other streams / captured graphs
+        self._tok_const[B] = (tokens, queries, q)
+        return self._tok_const[B]
+
     def sam_heads(self, pix_feat, feat_s0, feat_s1, B, sparse, dense=None, multimask=True, feat_shared=True,
                   src_ready=False, defer_ptr=False):
         """pix_feat fp32 [B*1024,256]; sparse fp32 [B,P,256] prompt tokens; dense fp32 [B*1024,256] or None
@@ -516,9 +540,15 @@ class Engine:
             src, _ = ops.axpby(pix_feat, w.no_mask_embed, rows=B * T, y_mod=1)
         else:
             src, _ = ops.axpby(pix_feat, dense, rows=B * T)
-        P = sparse.shape[1]
-        Nt = 6 + P
-        tokens = torch.cat([w.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(B * Nt, 256).contiguous()
+        const0 = None
+        if sparse is None:  # no prompt (tracked frame): constant tokens, token-side prefix precomputed
+            Nt = 8
+            tokens, q_norm1, q_t2i = self.token_constants(B)
+            const0 = (q_norm1, q_t2i)
+        else:
+            P = sparse.shape[1]
+            Nt = 6 + P
+            tokens = torch.cat([w.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(B * Nt, 256).contiguous()
         queries, keys = tokens, src
         ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
         sk = ops.gemm_skinny
@@ -528,7 +558,7 @@ class Engine:
         if chain:
             hs, y, keys = self._two_way_transformer_chain(tokens, keys, B)
         else:
-            hs, keys = self._two_way_transformer(tokens, keys, B, Nt, img_stream=img_s)
+            hs, keys = self._two_way_transformer(tokens, keys, B, Nt, img_stream=img_s, const0=const0)
         # output upscaling (image side) || the six token heads (token side); they meet in the mask product
         with torch.cuda.stream(img_s if img_s is not None else tok):
             g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=True)
@@ -578,7 +608,7 @@ class Engine:
         ops.objptr_mix_(ptr, score, w.no_obj_ptr)
         return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36])
 
-    def _two_way_transformer(self, tokens, keys, B, Nt, img_stream=None):
+    def _two_way_transformer(self, tokens, keys, B, Nt, img_stream=None, const0=None):
         """TwoWayTransformer (sam/transformer.py:90-135) with one launch per token-side layer: any token count.
         With `img_stream` the image-side work (the fused k / v / q projections of `keys`, image->token attention and its
         output projection + norm) is enqueued there and only meets the token side where the data does: the projection of
@@ -598,17 +628,20 @@ class Engine:
             sa, t2i, i2t = Lyr["sa"], Lyr["t2i"], Lyr["i2t"]
             with torch.cuda.stream(img_s):
                 img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T, tf32=True)  # [B*T, 384]
-            if l == 0:
-                qkv = sk(queries, sa["qkv_w"], sa["qkv_b"])
-                o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
-                queries = sk(o, *sa["o"])
+            if l == 0 and const0 is not None:
+                queries, q = const0  # constants of the model on prompt-free frames (Engine.token_constants)
             else:
-                # q, k read queries + token_pe, v reads queries: one launch, the positional add limited to 512 columns
-                qkv = sk(queries, sa["qkv_w"], sa["qkv_b"], x2=tokens, x2_cols=512)
-                o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
-                queries = sk(o, *sa["o"], residual=queries)
-            queries = ln(queries, Lyr["norms"][0])
-            q = sk(queries, *t2i["q"], x2=tokens)
+                if l == 0:
+                    qkv = sk(queries, sa["qkv_w"], sa["qkv_b"])
+                    o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
+                    queries = sk(o, *sa["o"])
+                else:
+                    # q, k read queries + token_pe, v reads queries: one launch, the positional add limited to 512 columns
+                    qkv = sk(queries, sa["qkv_w"], sa["qkv_b"], x2=tokens, x2_cols=512)
+                    o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
+                    queries = sk(o, *sa["o"], residual=queries)
+                queries = ln(queries, Lyr["norms"][0])
+                q = sk(queries, *t2i["q"], x2=tokens)
             if par:
                 self._handoff(tok, img_s, img)
             o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)

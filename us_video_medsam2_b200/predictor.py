@@ -791,6 +791,7 @@ class SAM2VideoPredictor(nn.Module):
         B, n_mem, n_ptr, hw, fill = key
         eng = self.engine()
         static_f = {k: f[k].clone() for k in ("feat", "feat_bf16", "feat_s0", "feat_s1")}
+        eng.token_constants(B)  # one-off constants must exist before the capture starts
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         before = _lib.launch_count
