@@ -431,12 +431,16 @@ class Engine:
 
     def project_memory(self, k_in, v_in, Nk, n_ptr_tok, B):
         """Key / value projections of the assembled bank for all 4 layers at once: ([B*Nk, 4*256] rotated keys, values)."""
+        return self.project_keys(k_in, Nk, n_ptr_tok, B), self.project_values(v_in, Nk, B)
+
+    def project_keys(self, k_in, Nk, n_ptr_tok, B):
         w = self.w
-        k_in2, v_in2 = k_in.view(B * Nk, 64), v_in.view(B * Nk, 64)
-        _, k_all = ops.gemm_bf16(k_in2, w.ca_k_all[0], bias=w.ca_k_all[1], bf16=True,
-                                 rope=(w.rope_cos, w.rope_sin, 1024, Nk, Nk - n_ptr_tok))
-        _, v_all = ops.gemm_bf16(v_in2, w.ca_v_all[0], bias=w.ca_v_all[1], bf16=True)
-        return k_all, v_all
+        return ops.gemm_bf16(k_in.view(B * Nk, 64), w.ca_k_all[0], bias=w.ca_k_all[1], bf16=True,
+                             rope=(w.rope_cos, w.rope_sin, 1024, Nk, Nk - n_ptr_tok))[1]
+
+    def project_values(self, v_in, Nk, B):
+        w = self.w
+        return ops.gemm_bf16(v_in.view(B * Nk, 64), w.ca_v_all[0], bias=w.ca_v_all[1], bf16=True)[1]
 
     def _splits(self, B, Nk):
         """Split-KV factor: the tcgen05 kernel runs 8 query tiles of 128 per object; fill the 148 SMs."""
@@ -463,16 +467,24 @@ class Engine:
             # the bank (gather + temporal encodings + K/V projections of ~7 k rows) does not depend on this frame's
             # features, the first self-attention block does not depend on the bank: two branches, joined before the
             # first cross-attention
-            side = self._side(0)
+            side, side_v = self._side(0), self._side(2)
             side.wait_stream(main)
-            with torch.cuda.stream(side):
-                k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
-                kv = self.project_memory(k_in, v_in, Nk, n_tok, B)
+            side_v.wait_stream(main)
+            with torch.cuda.stream(side_v):
                 # pix_feat_proj of the memory encoder only reads this frame's features: off the critical path here
                 pp, _ = ops.gemm_bf16(f["feat_bf16"], *self.w.pix_proj, f32=True)
+            with torch.cuda.stream(side):
+                k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
+            self._handoff(side_v, side, v_in)
+            with torch.cuda.stream(side):
+                k_all = self.project_keys(k_in, Nk, n_tok, B)
+            with torch.cuda.stream(side_v):  # keys and values are projected side by side
+                v_all = self.project_values(v_in, Nk, B)
+            kv = (k_all, v_all)
 
             def bank():
-                self._handoff(main, side, kv[0], kv[1], pp)
+                self._handoff(main, side, k_all)
+                self._handoff(main, side_v, v_all, pp)
                 return kv
 
             pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank, fold_no_mask=True)
