@@ -31,7 +31,11 @@ os.environ.setdefault("TQDM_DISABLE", "1")
 
 import torch  # noqa: E402
 
-METRIC = "propagated frames/sec (sam2.1_hiera_t512, 512x512, 1 object, 7-frame memory bank)"
+METRIC = "propagated frames/sec (sam2.1_hiera_t512, 512x512, {objects} object{s}, 7-frame memory bank)"
+
+
+def metric_name(objects):
+    return METRIC.format(objects=objects, s="" if objects == 1 else "s")
 SEED = 19
 
 
@@ -68,46 +72,97 @@ def measured_peaks():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, from a background thread through NVML
+    (nvidia_ml_py; one-shot `nvidia-smi` calls if the module is missing).  An NVML query -- from a looping `nvidia-smi`
+    child or in-process alike -- was measured to stall this process's kernel launches for 20-470 ms.  That is harmless
+    while the host runs hundreds of frames ahead of the GPU, but at the start of the timed region the launch queue is
+    empty and the stall turned into GPU idle time in about one run out of three.  So the first in-region sample is taken
+    `lead` seconds after the region starts (the host has built its lead by then) and every `period` seconds from there."""
+    NAMES = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period=0.25, lead=0.4):
+        self.index, self.period, self.lead, self.rows = index, period, lead, []
         self.t0 = self.t1 = None
+        self._stop, self._begin = threading.Event(), threading.Event()
+        self._thread, self._nvml, self._handle, self.source = None, None, None, None
 
     def mark_begin(self):
         self.t0 = time.time()
+        self._begin.set()
 
     def mark_end(self):
         self.t1 = time.time()
+        self._stop.set()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self._handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self._handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._nvml, self.source = pynvml, "nvml"
+            self._sample()  # first query (lazy NVML state) before the warm-up
+        except Exception:
+            self._nvml, self.source = None, "nvidia-smi"
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+
+    def _sample(self):
+        if self._nvml is not None:
+            n, h = self._nvml, self._handle
+            sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((time.time(), int(sm), int(mx), int(mask)))
+            return
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+        self.rows.append((time.time(), int(out[0]), int(out[1]), int(out[2].strip(), 16)))
+
+    def _loop(self):
+        self._begin.wait()
+        if self._stop.wait(self.lead):
+            return
+        while True:
+            try:
+                self._sample()
+            except Exception:
+                pass
+            if self._stop.wait(self.period if self._nvml is not None else 1.0):
+                return
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        # only samples taken inside the timed region count (nvidia-smi is started before the warm-up so that its
-        # start-up cost -- it briefly stalls CUDA calls of other processes -- stays outside the timed region)
+        self._stop.set()
+        if self._thread is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock sampler not started"])
+        self._begin.set()
+        self._thread.join(timeout=5)
         lo = self.t0 if self.t0 is not None else 0.0
         hi = self.t1 if self.t1 is not None else float("inf")
-        rows = [r for t, r in self.rows if lo <= t <= hi + 0.25] or [r for _, r in self.rows]
-        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(sm))
+        rows = [r for r in self.rows if lo <= r[0] <= hi + 0.05]
+        if not rows:  # region shorter than `lead`: one sample right after it (the GPU is still at its load clocks)
+            try:
+                self._sample()
+            except Exception:
+                pass
+            rows = self.rows[-1:]
+        if not rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no clock samples"], source=self.source)
+        sm = sorted(r[1] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        reasons = sorted(name for name, bit in self.NAMES if mask & bit)
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in rows), reasons=reasons, samples=len(sm),
+                    source=self.source)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -152,7 +207,7 @@ def run_reference(args, rank):
     value = sample / (ms / 1000.0)
     unit = "frames/s"
     print(json.dumps({
-        "metric": METRIC, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "metric": metric_name(args.objects), "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": f"sam2.1_hiera_t512 propagate_in_video, CPU port of the reference, {sample}-frame sample "
@@ -255,7 +310,7 @@ def run_b200(args, rank, world):
 
     def timed(fn, steps, warmup):
         sampler = ClockSampler(local)
-        if rank == 0:
+        if rank == 0 and not os.environ.get("USVM2_NO_SAMPLER"):
             sampler.start()
         for _ in range(warmup):
             fn()
@@ -268,14 +323,21 @@ def run_b200(args, rank, world):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         frames = 0
+        marks = []
         for i in range(steps):
             t_host = time.perf_counter()
             frames += fn()
             if os.environ.get("USVM2_BENCH_DEBUG"):
-                print(f"[bench debug] {fn.__name__} step {i}: host loop {1e3 * (time.perf_counter() - t_host):.1f} ms",
-                      file=sys.stderr, flush=True)
+                m = torch.cuda.Event(enable_timing=True)
+                m.record()
+                marks.append((m, 1e3 * (time.perf_counter() - t_host)))
         e1.record()
         torch.cuda.synchronize()
+        prev = e0
+        for i, (m, host_ms) in enumerate(marks):
+            print(f"[bench debug] {fn.__name__} step {i}: host loop {host_ms:.1f} ms, device {prev.elapsed_time(m):.1f} ms",
+                  file=sys.stderr, flush=True)
+            prev = m
         sampler.mark_end()
         launches = _lib.launch_count - l0
         clocks = sampler.stop() if rank == 0 else None
@@ -319,7 +381,7 @@ def run_b200(args, rank, world):
                          f"{torch.__version__} CPU fp32"}
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(B), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if clip_mode else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -346,6 +408,9 @@ def run_b200(args, rank, world):
 
 def main():
     args = parse()
+    if os.environ.get("USVM2_NO_GC"):
+        import gc
+        gc.disable()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -150,7 +150,8 @@ class SmPartition:
 
 
 class PartitionProducer:
-    """Replays the captured image-encoder graph of slot (k mod 2) on the partition's stream."""
+    """Replays the captured image-encoder graph of slot (k mod 2) on the partition's stream.  The very first batch has
+    nothing to overlap with (the consumer is waiting for it), so it runs on the consumer's stream with the whole device."""
     must_drain = False
 
     def __init__(self, predictor, st, partition, n):
@@ -160,6 +161,13 @@ class PartitionProducer:
     def launch(self, k, frames, slot):
         from . import _lib
 
+        if k == 0:
+            graph, static_in, out, n_kernels = self.pred._encoder_graph(self.n)  # full-device graph, own buffers
+            self.pred._load_frames(self.st, frames, static_in)
+            graph.replay()
+            _lib.launch_count += n_kernels
+            self.pending[k] = (None, out)
+            return
         graph, static_in, out, n_kernels = self.pred._encoder_graph(self.n, slot, self.part)
         enc = self.part.stream
         free = torch.cuda.Event()
@@ -175,7 +183,8 @@ class PartitionProducer:
 
     def wait(self, k):
         done, out = self.pending.pop(k)
-        torch.cuda.current_stream().wait_event(done)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
         return out
 
 

@@ -281,8 +281,9 @@ class SAM2VideoPredictor(nn.Module):
         static_in = torch.zeros((n, 3, self.image_size, self.image_size), dtype=torch.float32, device=self.device)
         stream = partition.stream if partition is not None else None
         try:
+            # persistent grids: the partition's SMs, or the whole device for the full-device graph
+            ops.set_sm_budget(partition.sms if partition is not None else 0)
             if partition is not None:
-                ops.set_sm_budget(partition.sms)
                 stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(stream):
                     eng.encode_frames(static_in)
@@ -296,8 +297,8 @@ class SAM2VideoPredictor(nn.Module):
             n_kernels = _lib.launch_count - before
             _lib.launch_count = before
         finally:
-            if partition is not None:
-                ops.set_sm_budget(partition.total_sms - partition.sms)
+            part = self._partition_obj  # tracked frames plan for the SMs the encoder partition leaves
+            ops.set_sm_budget(part.total_sms - part.sms if part is not None else 0)
         ent = (graph, static_in, out, n_kernels)
         self._graphs[key] = ent
         return ent
@@ -384,6 +385,7 @@ class SAM2VideoPredictor(nn.Module):
         # a final partial batch replays the same n-frame graph (stale inputs in the unused rows, outputs ignored)
         plan = BatchPlan(first, last, step, n, include_tail=True)
         try:
+            self._encoder_graph(n)  # first batch of a pass: full device, nothing to overlap with
             for slot in range(2):
                 self._encoder_graph(n, slot, part)
         except Exception as e:  # the partition exists but the encoder cannot run on it: alternate as before
