@@ -324,6 +324,7 @@ def run_b200(args, rank, world):
         e0.record()
         frames = 0
         marks = []
+        allocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
         for i in range(steps):
             t_host = time.perf_counter()
             frames += fn()
@@ -333,6 +334,9 @@ def run_b200(args, rank, world):
                 marks.append((m, 1e3 * (time.perf_counter() - t_host)))
         e1.record()
         torch.cuda.synchronize()
+        if os.environ.get("USVM2_BENCH_DEBUG"):
+            print(f"[bench debug] {fn.__name__}: cudaMalloc calls inside the timed region: "
+                  f"{torch.cuda.memory_stats().get('num_device_alloc', 0) - allocs0}", file=sys.stderr, flush=True)
         prev = e0
         for i, (m, host_ms) in enumerate(marks):
             print(f"[bench debug] {fn.__name__} step {i}: host loop {host_ms:.1f} ms, device {prev.elapsed_time(m):.1f} ms",

@@ -773,7 +773,9 @@ class SAM2VideoPredictor(nn.Module):
         if self.use_cuda_graphs and ent is None:
             seen = self._graph_seen.get(key, 0) + 1
             self._graph_seen[key] = seen
-            if seen >= 3:  # a signature that keeps recurring is the steady state: capture it
+            # a signature that recurs is worth a graph: the steady state (full bank) is captured at its second frame, the
+            # ramp-up signatures of a clip (bank filling up) when a second clip / pass reaches them
+            if seen >= 2:
                 ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
                 ent = self._capture_graph(key, f)
         if ent is not None:
