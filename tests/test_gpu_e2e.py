@@ -205,3 +205,32 @@ def test_partition_pipeline_reverse_multi_object_and_early_exit():
         for (t, a), (_, b) in zip(base[key], got[key]):
             assert a.shape == b.shape
             assert dice(a.cpu(), b.cpu()) >= DICE_BAR, (key, t)
+
+
+def test_editing_session_matches_reference_fixture(golden_dir):
+    """(a16) interactive surface against the reference's own outputs: correction click on a tracked frame (previous mask
+    logits + memory-conditioned features), re-propagation, clear_all_prompts_in_frame, remove_object -- same script as
+    oracle/make_golden_edit.py ran on the unmodified reference."""
+    from oracle.make_golden_edit import SEED, T, edit_session
+
+    g = np.load(os.path.join(golden_dir, "t512_edit_session.npz"))
+    pred = _predictor(SEED)
+    got = edit_session(pred, synth.make_clip(T, kind="speckle").cuda(), synth.box_mask())
+    for key in ("frames_a", "frames_b", "frames_c", "click_ids", "cond_b", "cond_after_clear", "remove_ids",
+                "remove_updated_frames"):
+        assert got[key].tolist() == g[key].tolist(), key
+    # Tolerances: the absolute error is the same bf16 noise floor as on every tracked frame (mean |dlogit| ~ 4.5e-4,
+    # asserted below at 8e-4), but this session's logits have less contrast (std 0.03-0.06 at random init, two objects),
+    # so the same error costs more Dice than in the single-object fixtures: bar 0.99 here instead of 0.995.  The frame
+    # that received the click has steeper logits around the point: max |dlogit| bar 4 x LOGIT_TOL there.
+    for key in ("low_a", "low_b", "low_c", "click_video_s4", "clear_video_s4", "remove_video_s4"):
+        a, b = torch.from_numpy(got[key]), torch.from_numpy(g[key])
+        assert a.shape == b.shape, key
+        a, b = a.reshape(-1, *a.shape[-2:]), b.reshape(-1, *b.shape[-2:])
+        for i in range(a.shape[0]):
+            same = (a[i] != 0.1) & (b[i] != 0.1)  # hole filling rewrites to 0.1 at a threshold
+            d = (a[i] - b[i]).abs()
+            if key.startswith("low"):  # (the video-resolution samples interpolate across filled pixels)
+                assert float(d[same].max()) <= 4 * LOGIT_TOL, (key, i, float(d[same].max()))
+            assert float(d[same].mean()) <= 8e-4, (key, i, float(d[same].mean()))
+            assert dice(a[i], b[i]) >= 0.99, (key, i, dice(a[i], b[i]))
