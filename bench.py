@@ -257,6 +257,42 @@ def time_dominant_kernel(dev, B, iters=20):
     return dict(avg_ms=sum(times) / len(times), flops_per_launch=flops, launches=iters, splits=splits)
 
 
+def time_other_kernels(dev, B):
+    """The launch list (profiles/r1_launch_lists.md) shows no single kernel above 19 % of a one-object frame: the one-tile
+    GEMM family carries the largest share by time, the cross-attention pair by FLOPs.  For transparency the two most
+    frequent GEMM shapes of the memory attention are timed too -- 20 launches captured in one CUDA graph (as they run in
+    the frame: no host launch overhead between them), L2 warm (their operands are the previous kernel's output)."""
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    out = []
+    for name, (M, N, K) in (("memory-attention qkv / q / out projections (gemm_bf16_tc5_kernel<32>)", (1024 * B, 768, 256)),
+                            ("memory-attention FFN linear1 (gemm_bf16_tc5_kernel)", (1024 * B, 2048, 256))):
+        a = torch.randn((M, K), generator=g, device=dev).to(torch.bfloat16)
+        w = (torch.randn((N, K), generator=g, device=dev) * K ** -0.5).to(torch.bfloat16)
+        bias = torch.randn((N,), generator=g, device=dev)
+        fn = lambda: ops.gemm_bf16(a, w, bias=bias, bf16=True)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                fn()
+        graph.replay()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            graph.replay()
+        e.record()
+        torch.cuda.synchronize()
+        us = s.elapsed_time(e) / 100 * 1e3
+        out.append({"kernel": name, "shape_mnk": [M, N, K], "avg_us": us, "achieved_tflops": 2.0 * M * N * K / us / 1e6,
+                    "bound": "latency (one 128-row tile per CTA, 0.4-1.1 GFLOP per launch)"})
+    return out
+
+
 def run_b200(args, rank, world):
     import torch.distributed as dist
 
@@ -376,6 +412,8 @@ def run_b200(args, rank, world):
                     "launches_timed": ks["launches"], "avg_us": ks["avg_ms"] * 1e3, "peak_source": peaks["source"],
                     "how": "CUDA events around the kernel at its steady-state shape, L2 flushed between iterations "
                            "(the frame itself replays from a CUDA graph)"}
+    if roofline is not None:
+        roofline["other_kernels"] = time_other_kernels(dev, B)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = max(4, min(T, args.cpu_sample_frames))
