@@ -241,8 +241,8 @@ fmha_bf16_kernel(const usvm_fmha_params p) {
 // 128 KB per query tile), so all (max, sum) pairs are fetched up front and the partial rows in register batches of 8:
 // every load of a batch is in flight before the first one is consumed.
 constexpr int COMBINE_MAX_SPLITS = 32;
-template <int D>
-__global__ void __launch_bounds__(256)
+template <int D, int NSMAX>
+__global__ void __launch_bounds__(256, NSMAX <= 24 ? 2 : 1)
 fmha_combine_kernel(const usvm_fmha_params p) {
   PDL_ENTRY();
   constexpr int C4 = D / 4;
@@ -259,42 +259,61 @@ fmha_combine_kernel(const usvm_fmha_params p) {
   const float2* mlp = reinterpret_cast<const float2*>(p.ml_part) + row;
   const float* op = p.o_part + row * D + c4;
   const long long ostride = total_rows * D;
-  float2 ml[COMBINE_MAX_SPLITS];
+  float2 ml[NSMAX];
 #pragma unroll
-  for (int s = 0; s < COMBINE_MAX_SPLITS; ++s) ml[s] = s < ns ? __ldg(mlp + (long long)s * total_rows) : make_float2(0.f, 0.f);
+  for (int s = 0; s < NSMAX; ++s) ml[s] = s < ns ? __ldg(mlp + (long long)s * total_rows) : make_float2(0.f, 0.f);
   float M = -INFINITY;
 #pragma unroll
-  for (int s = 0; s < COMBINE_MAX_SPLITS; ++s)
+  for (int s = 0; s < NSMAX; ++s)
     if (ml[s].y > 0.f) M = fmaxf(M, ml[s].x);
   float L = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.part_bf16) {
+    // bf16 partials (8 bytes per thread and split): the first 24 splits are fetched in ONE batch -- the 18-way split of
+    // the one-object cross-attention then costs a single L2 round trip instead of three -- the rest in a second one
+    const bf16* opb = reinterpret_cast<const bf16*>(p.o_part) + row * D + c4;
+    constexpr int B0 = NSMAX < 24 ? NSMAX : 24;
+    uint2 raw[B0];
 #pragma unroll
-  for (int s0 = 0; s0 < COMBINE_MAX_SPLITS; s0 += 8) {
-    if (s0 < ns) {
-      float4 o[8];
-      if (p.part_bf16) {
-        const bf16* opb = reinterpret_cast<const bf16*>(p.o_part) + row * D + c4;
-        uint2 raw[8];
+    for (int u = 0; u < B0; ++u)
+      raw[u] = u < ns ? __ldg(reinterpret_cast<const uint2*>(opb + (long long)u * ostride)) : make_uint2(0u, 0u);
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          raw[u] = s0 + u < ns ? __ldg(reinterpret_cast<const uint2*>(opb + (long long)(s0 + u) * ostride)) : make_uint2(0u, 0u);
+    for (int u = 0; u < B0; ++u) {
+      const float2 m = ml[u];
+      const float w = m.y > 0.f ? exp2f((m.x - M) * sl2) : 0.f;
+      const float2 lo = unpack_bf16x2(raw[u].x), hi = unpack_bf16x2(raw[u].y);
+      L += m.y * w;
+      acc.x += lo.x * w; acc.y += lo.y * w; acc.z += hi.x * w; acc.w += hi.y * w;
+    }
+    if (NSMAX > 24 && ns > 24) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float2 lo = unpack_bf16x2(raw[u].x), hi = unpack_bf16x2(raw[u].y);
-          o[u] = make_float4(lo.x, lo.y, hi.x, hi.y);
-        }
-      } else {
+      for (int u = 0; u < 8; ++u)
+        raw[u] = 24 + u < ns ? __ldg(reinterpret_cast<const uint2*>(opb + (long long)(24 + u) * ostride)) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float2 m = ml[NSMAX > 24 ? 24 + u : 0];
+        const float w = m.y > 0.f ? exp2f((m.x - M) * sl2) : 0.f;
+        const float2 lo = unpack_bf16x2(raw[u].x), hi = unpack_bf16x2(raw[u].y);
+        L += m.y * w;
+        acc.x += lo.x * w; acc.y += lo.y * w; acc.z += hi.x * w; acc.w += hi.y * w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int s0 = 0; s0 < NSMAX; s0 += 8) {
+      if (s0 < ns) {
+        float4 o[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           o[u] = s0 + u < ns ? __ldg(reinterpret_cast<const float4*>(op + (long long)(s0 + u) * ostride))
                              : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float2 m = ml[s0 + u];
-        const float w = m.y > 0.f ? exp2f((m.x - M) * sl2) : 0.f;
-        L += m.y * w;
-        acc.x += o[u].x * w; acc.y += o[u].y * w; acc.z += o[u].z * w; acc.w += o[u].w * w;
+        for (int u = 0; u < 8; ++u) {
+          const float2 m = ml[s0 + u];
+          const float w = m.y > 0.f ? exp2f((m.x - M) * sl2) : 0.f;
+          L += m.y * w;
+          acc.x += o[u].x * w; acc.y += o[u].y * w; acc.z += o[u].z * w; acc.w += o[u].w * w;
+        }
       }
     }
   }
@@ -304,6 +323,14 @@ fmha_combine_kernel(const usvm_fmha_params p) {
   pk.x = pack_bf16x2(acc.x * inv, acc.y * inv);
   pk.y = pack_bf16x2(acc.z * inv, acc.w * inv);
   *reinterpret_cast<uint2*>(O) = pk;
+}
+
+template <int D>
+void launch_combine(const usvm_fmha_params* p, long long rows, cudaStream_t s) {
+  const dim3 grid(cdiv(rows * (D / 4), 256));
+  if (p->num_splits <= 8) usvm_launch(fmha_combine_kernel<D, 8>, grid, dim3(256), 0, s, *p);
+  else if (p->num_splits <= 24) usvm_launch(fmha_combine_kernel<D, 24>, grid, dim3(256), 0, s, *p);
+  else usvm_launch(fmha_combine_kernel<D, COMBINE_MAX_SPLITS>, grid, dim3(256), 0, s, *p);
 }
 
 template <int D>
@@ -319,7 +346,7 @@ int launch_fmha(const usvm_fmha_params* p, cudaStream_t s) {
   usvm_launch(fmha_bf16_kernel<D>, dim3(grid), dim3(FTHREADS), FmhaSmem<D>::BYTES, s, *p);
   if (p->num_splits > 1) {
     const long long rows = (long long)p->B * p->H * p->Nq;
-    usvm_launch(fmha_combine_kernel<D>, dim3(cdiv(rows * (D / 4), 256)), dim3(256), 0, s, *p);
+    launch_combine<D>(p, rows, s);
   }
   return usvm_check_launch();
 }
@@ -399,8 +426,8 @@ extern "C" int usvm_fmha_combine(const usvm_fmha_params* p, void* stream) {
   const long long rows = (long long)p->B * p->H * p->Nq;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if ((p->o_rs % 4) || (p->o_hs % 4) || (p->o_bs % 4)) return USVM_ERR_ARG;
-  if (p->head_dim == 96) usvm_launch(fmha_combine_kernel<96>, dim3(cdiv(rows * 24, 256)), dim3(256), 0, s, *p);
-  else if (p->head_dim == 256) usvm_launch(fmha_combine_kernel<256>, dim3(cdiv(rows * 64, 256)), dim3(256), 0, s, *p);
+  if (p->head_dim == 96) launch_combine<96>(p, rows, s);
+  else if (p->head_dim == 256) launch_combine<256>(p, rows, s);
   else return USVM_ERR_ARG;
   return usvm_check_launch();
 }
