@@ -269,6 +269,14 @@ typedef struct usvm_skinny_params {
   long long o_is, o_rs;
   int M, N, K, instances, act;
   int x2_cols; /* x2 is added for output columns < x2_cols only (a multiple of 4); 0 or >= N: for all columns */
+  /* optional LayerNorm of the input rows on load (K == 256 only; transformer.py:192-211 norm1..3, :131 norm_final_attn):
+   * x <- LN(x) * ln_w + ln_b before x2 is added; the normalised rows are also written to ln_out (row (m) of instance i at
+   * ln_out + i * ln_is + m * ln_rs) by the first CTA of each (instance, row block), bit-identical to usvm_layernorm */
+  const float* ln_w;
+  const float* ln_b;
+  float* ln_out;
+  long long ln_is, ln_rs;
+  float ln_eps;
 } usvm_skinny_params;
 int usvm_gemm_skinny_f32(const usvm_skinny_params* p_host, void* stream);
 /* token -> image attention (transformer.py:194-198): q [B*Nt, H*16], k/v rows of stride kv_rs, Nt <= 16 */

@@ -358,6 +358,21 @@ def test_skinny_gemm_and_decoder_attention():
                         x_sel_stride=256)
     want = torch.stack([hs[i, 2 + int(idx[i])] @ W[0].t() + bb[0] for i in range(B)])
     assert (y - want).abs().max().item() < 1e-4
+    # LayerNorm on load: same product as LayerNorm followed by the GEMM, and the side output equals the LayerNorm kernel
+    lw, lb = torch.randn(256, generator=g, device="cuda"), torch.randn(256, generator=g, device="cuda")
+    xn, _ = ops.layernorm(x, lw, lb, 1e-5, f32=True)
+    side = torch.empty_like(x)
+    got_ln = ops.gemm_skinny(x, w, b, x2=x2, x2_cols=128, act=ops.ACT_RELU, ln=(lw, lb, 1e-5), ln_out=side)
+    assert torch.equal(side, xn)
+    assert torch.equal(got_ln, ops.gemm_skinny(xn, w, b, x2=x2, x2_cols=128, act=ops.ACT_RELU))
+    want_ln = F.layer_norm(x, (256,), lw, lb, 1e-5)
+    assert (side - want_ln).abs().max().item() < 1e-5
+    hs_n = torch.full_like(hs, float("nan"))
+    y = ops.gemm_skinny(None, W, bb, M=B, x_ptr=hs.data_ptr(), x_rs=Nt * 256, x_is=256, instances=6,
+                        ln=(lw, lb, 1e-5), ln_out=hs_n, ln_rs=Nt * 256, ln_is=256)
+    want_hs = F.layer_norm(hs[:, :6], (256,), lw, lb, 1e-5)
+    assert (hs_n[:, :6] - want_hs).abs().max().item() < 1e-5 and bool(torch.isnan(hs_n[:, 6:]).all())
+    assert (y.view(B, 6, 30) - (torch.einsum("bik,ink->bin", want_hs, W) + bb)).abs().max().item() < 1e-4
     # token->image and image->token attention (8 heads x 16) on column views of a fused buffer
     for Nt_ in (8, 11):
         q = torch.randn((B * Nt_, 128), generator=g, device="cuda")

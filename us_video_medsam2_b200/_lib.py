@@ -47,7 +47,9 @@ class SkinnyParams(C.Structure):
                 ("residual", C.c_void_p), ("r_is", C.c_longlong), ("r_rs", C.c_longlong),
                 ("out", C.c_void_p), ("o_is", C.c_longlong), ("o_rs", C.c_longlong),
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("instances", C.c_int), ("act", C.c_int),
-                ("x2_cols", C.c_int)]
+                ("x2_cols", C.c_int),
+                ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("ln_out", C.c_void_p), ("ln_is", C.c_longlong),
+                ("ln_rs", C.c_longlong), ("ln_eps", C.c_float)]
 
 
 CHAIN_MAX_STEPS = 10

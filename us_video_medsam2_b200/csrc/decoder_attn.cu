@@ -22,16 +22,73 @@ constexpr int SK_WARPS = 8;
 template <int KSPLIT>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const usvm_skinny_params p) {
-  PDL_ENTRY();
   extern __shared__ __align__(16) float xs[];  // [8][K] x + x2, [8][32] partials, then [8][K] plain x when x2_cols < N
   const int inst = blockIdx.y;
   const int m0 = blockIdx.z * SK_ROWS;
   const int rows = min(SK_ROWS, p.M - m0);
   const int K = p.K, K4 = K >> 2;
+  // The weights are constants of the model: nothing launched before this kernel writes them, so this warp's weight
+  // rows are fetched BEFORE the programmatic-dependency wait -- their L2 / HBM latency overlaps the predecessor's tail and
+  // the staging of x instead of following it.  (256-wide k ranges: K = 256, or K = 2048 split over the 8 warps.)
+  const int pw_warp = threadIdx.x >> 5, pw_lane = threadIdx.x & 31;
+  const int pw_n0 = (KSPLIT == 1 ? (blockIdx.x * SK_WARPS + pw_warp) : blockIdx.x) * SK_COLS;
+  const int pw_chunk = KSPLIT == 1 ? K : (((K + KSPLIT - 1) / KSPLIT + 3) & ~3);
+  const bool prefetched = pw_chunk == 256 && pw_n0 < p.N && (KSPLIT == 1 || (pw_warp + 1) * 256 <= K);
+  float4 wpre[2][SK_COLS];
+  if (prefetched) {
+    const float* Wp = p.w + (long long)inst * p.w_is + (KSPLIT == 1 ? 0 : pw_warp * 256) + pw_lane * 4;
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+#pragma unroll
+      for (int c = 0; c < SK_COLS; ++c)
+        wpre[it][c] = __ldg(reinterpret_cast<const float4*>(Wp + (long long)min(pw_n0 + c, p.N - 1) * K + it * 128));
+  }
+  PDL_ENTRY();
   // x2 (the positional tokens) applies to output columns < x2_cols only: projections that read `queries + pe` and
   // projections that read `queries` share one launch, with both variants of the input staged
   const bool two = p.x2 && p.x2_cols > 0 && p.x2_cols < p.N;
   float* xs_plain = xs + SK_ROWS * K + SK_WARPS * 32;
+  if (p.ln_w) {
+    // LayerNorm on load (K == 256): warp m owns row m; same lane <-> column mapping and operation order as
+    // layernorm_reg_kernel<8>, so the result is bit-identical to the separate launch it replaces
+    const int wrow = threadIdx.x >> 5, ln_lane = threadIdx.x & 31;
+    if (wrow < rows) {
+      const long long sel = p.row_select ? (long long)p.row_select[m0 + wrow] * p.x_sel_stride : 0;
+      const float* xr = p.x + (long long)inst * p.x_is + (long long)(m0 + wrow) * p.x_rs + sel;
+      const float* x2r = p.x2 ? p.x2 + (long long)inst * p.x2_is + (long long)(m0 + wrow) * p.x2_rs : nullptr;
+      // every global load of the row is issued before the first reduction: one memory round trip, not three
+      float v[8], gw[8], gb[8], a2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = j * 32 + ln_lane;
+        v[j] = xr[col];
+        gw[j] = __ldg(p.ln_w + col);
+        gb[j] = __ldg(p.ln_b + col);
+        a2[j] = x2r ? x2r[col] : 0.f;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[j];
+      const float mean = warp_sum(sum) / 256;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] -= mean;
+        q = fmaf(v[j], v[j], q);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) / 256 + p.ln_eps);
+      float* lo = (p.ln_out && blockIdx.x == 0) ? p.ln_out + (long long)inst * p.ln_is + (long long)(m0 + wrow) * p.ln_rs
+                                                  : nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = j * 32 + ln_lane;
+        const float y = v[j] * rstd * gw[j] + gb[j];
+        if (lo) lo[col] = y;
+        if (two) xs_plain[wrow * K + col] = y;
+        xs[wrow * K + col] = x2r ? y + a2[j] : y;
+      }
+    }
+  } else
   for (int i = threadIdx.x; i < rows * K4; i += blockDim.x) {
     const int m = i / K4, k = (i - m * K4) << 2;
     const long long sel = p.row_select ? (long long)p.row_select[m0 + m] * p.x_sel_stride : 0;
@@ -58,6 +115,21 @@ gemm_skinny_kernel(const usvm_skinny_params p) {
     const int kchunk = KSPLIT == 1 ? K : (((K + KSPLIT - 1) / KSPLIT + 3) & ~3);
     const int kbeg = KSPLIT == 1 ? 0 : warp * kchunk;
     const int kend = min(K, kbeg + kchunk);
+    if (prefetched) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int k = kbeg + lane * 4 + it * 128;
+#pragma unroll
+        for (int m = 0; m < SK_ROWS; ++m) {
+          if (m < rows) {
+            const float4 xv = *reinterpret_cast<const float4*>(xin + m * K + k);
+#pragma unroll
+            for (int c = 0; c < SK_COLS; ++c)
+              acc[c][m] += xv.x * wpre[it][c].x + xv.y * wpre[it][c].y + xv.z * wpre[it][c].z + xv.w * wpre[it][c].w;
+          }
+        }
+      }
+    } else
     for (int k = kbeg + lane * 4; k < kend; k += 128) {
       float4 wv[SK_COLS];
 #pragma unroll
@@ -383,6 +455,7 @@ extern "C" int usvm_gemm_skinny_f32(const usvm_skinny_params* p, void* stream) {
   if (!p || !p->x || !p->w || !p->out || p->M <= 0 || p->N <= 0 || p->K <= 0 || p->instances <= 0) return USVM_ERR_ARG;
   if ((p->K % 4) || (reinterpret_cast<uintptr_t>(p->w) & 15) || (p->w_is % 4)) return USVM_ERR_ARG;
   if (p->x2_cols % SK_COLS) return USVM_ERR_ARG;
+  if (p->ln_w && (p->K != 256 || !p->ln_b)) return USVM_ERR_ARG;
   const size_t smem = ((size_t)SK_ROWS * p->K * 2 + SK_WARPS * 32) * sizeof(float);
   if (smem > 200 * 1024) return USVM_ERR_ARG;
   static bool configured = false;

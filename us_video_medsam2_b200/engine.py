@@ -570,7 +570,8 @@ class Engine:
         if chain:
             hs, y, keys = self._two_way_transformer_chain(tokens, keys, B)
         else:
-            hs, keys = self._two_way_transformer(tokens, keys, B, Nt, img_stream=img_s, const0=const0)
+            hs_pre, keys = self._two_way_transformer(tokens, keys, B, Nt, img_stream=img_s, const0=const0,
+                                                     defer_final_norm=True)
         # output upscaling (image side) || the six token heads (token side); they meet in the mask product
         with torch.cuda.stream(img_s if img_s is not None else tok):
             g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=True)
@@ -578,8 +579,11 @@ class Engine:
             g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=True)
         if not chain:
             # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
+            # norm_final_attn runs on load in the first head layer, which also leaves the normalised token rows 0..5 in hs
             W1, b1, W2, b2, W3, b3 = w.heads6
-            h1 = sk(None, W1, b1, M=B, x_ptr=hs.data_ptr(), x_rs=Nt * 256, x_is=256, act=ACT_RELU, instances=6)
+            hs = torch.empty_like(hs_pre)
+            h1 = sk(None, W1, b1, M=B, x_ptr=hs_pre.data_ptr(), x_rs=Nt * 256, x_is=256, act=ACT_RELU, instances=6,
+                    ln=(w.dec_final_norm[0], w.dec_final_norm[1], 1e-5), ln_out=hs, ln_rs=Nt * 256, ln_is=256)
             h2 = sk(h1, W2, b2, M=B, x_rs=6 * 256, x_is=256, act=ACT_RELU, instances=6)
             y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
         if img_s is not None:
@@ -620,7 +624,7 @@ class Engine:
         ops.objptr_mix_(ptr, score, w.no_obj_ptr)
         return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36])
 
-    def _two_way_transformer(self, tokens, keys, B, Nt, img_stream=None, const0=None):
+    def _two_way_transformer(self, tokens, keys, B, Nt, img_stream=None, const0=None, defer_final_norm=False):
         """TwoWayTransformer (sam/transformer.py:90-135) with one launch per token-side layer: any token count.
         With `img_stream` the image-side work (the fused k / v / q projections of `keys`, image->token attention and its
         output projection + norm) is enqueued there and only meets the token side where the data does: the projection of
@@ -630,6 +634,7 @@ class Engine:
         T = 1024
         queries = tokens
         ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
+        lnp = lambda nb: (nb[0], nb[1], 1e-5)
         sk = ops.gemm_skinny
         tok = torch.cuda.current_stream()
         par = img_stream is not None
@@ -646,21 +651,25 @@ class Engine:
                 if l == 0:
                     qkv = sk(queries, sa["qkv_w"], sa["qkv_b"])
                     o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
-                    queries = sk(o, *sa["o"])
+                    pre = sk(o, *sa["o"])
                 else:
                     # q, k read queries + token_pe, v reads queries: one launch, the positional add limited to 512 columns
                     qkv = sk(queries, sa["qkv_w"], sa["qkv_b"], x2=tokens, x2_cols=512)
                     o = ops.attn_small(qkv[:, 0:256], qkv[:, 256:512], qkv[:, 512:768], B, 8, Nt, Nt, 32)
-                    queries = sk(o, *sa["o"], residual=queries)
-                queries = ln(queries, Lyr["norms"][0])
-                q = sk(queries, *t2i["q"], x2=tokens)
+                    pre = sk(o, *sa["o"], residual=queries)
+                # norm1 runs inside the projection that consumes it (LayerNorm on load), which also leaves `queries`
+                queries = torch.empty_like(pre)
+                q = sk(pre, *t2i["q"], x2=tokens, ln=lnp(Lyr["norms"][0]), ln_out=queries)
             if par:
                 self._handoff(tok, img_s, img)
             o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
-            queries = ln(sk(o, *t2i["o"], residual=queries), Lyr["norms"][1])
-            m = sk(queries, *Lyr["mlp"][0], act=ACT_RELU)
-            queries = ln(sk(m, *Lyr["mlp"][1], residual=queries), Lyr["norms"][2])
-            kv2 = sk(queries, i2t["kv_w"], i2t["kv_b"], x2=tokens, x2_cols=128)  # [k (with pe) | v]
+            pre = sk(o, *t2i["o"], residual=queries)
+            queries = torch.empty_like(pre)
+            m = sk(pre, *Lyr["mlp"][0], act=ACT_RELU, ln=lnp(Lyr["norms"][1]), ln_out=queries)       # norm2 on load
+            pre = sk(m, *Lyr["mlp"][1], residual=queries)
+            queries = torch.empty_like(pre)
+            kv2 = sk(pre, i2t["kv_w"], i2t["kv_b"], x2=tokens, x2_cols=128, ln=lnp(Lyr["norms"][2]),  # norm3 on load
+                     ln_out=queries)  # [k (with pe) | v]
             if par:
                 self._handoff(img_s, tok, kv2)
             with torch.cuda.stream(img_s):
@@ -673,8 +682,10 @@ class Engine:
         if par:
             self._handoff(tok, img_s, img)
         o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
-        hs = ln(sk(o, *fin["o"], residual=queries), w.dec_final_norm)  # [B*Nt, 256]
-        return hs, keys
+        hs_pre = sk(o, *fin["o"], residual=queries)  # [B*Nt, 256]; norm_final_attn is applied by the consumer
+        if not defer_final_norm:
+            return ln(hs_pre, w.dec_final_norm), keys
+        return hs_pre, keys
 
     def _two_way_transformer_chain(self, tokens, keys, B):
         """Same math for the 8-token case of tracked frames (6 output tokens + 2 padding points), token side as five

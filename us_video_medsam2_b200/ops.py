@@ -461,9 +461,11 @@ def small_mlp3(x_ptr, x_row_stride, x_inst_stride, row_select, mlp, out_dim, row
 
 def gemm_skinny(x, w, bias=None, M=None, x_rs=None, x_is=0, x2=None, x2_rs=None, x2_is=0, act=ACT_NONE,
                 residual=None, r_rs=None, r_is=0, instances=1, row_select=None, x_sel_stride=0, x_ptr=None, out=None,
-                x2_cols=0):
+                x2_cols=0, ln=None, ln_out=None, ln_rs=None, ln_is=0):
     """fp32 GEMM for a few rows: out[i, m, :] = act((x + x2)[i, m] @ w[i].T + bias[i]) + residual[i, m].
-    x: tensor [M, K] (or raw address via x_ptr with explicit strides); w: [N, K] or [instances, N, K]."""
+    x: tensor [M, K] (or raw address via x_ptr with explicit strides); w: [N, K] or [instances, N, K].
+    ln = (weight, bias, eps): the input rows are LayerNorm-ed on load (K == 256; x2 is added afterwards) and the normalised
+    rows are also written to ln_out -- the same values a separate usvm_layernorm launch would produce."""
     N, K = w.shape[-2], w.shape[-1]
     if M is None:
         M = x.shape[0]
@@ -485,6 +487,11 @@ def gemm_skinny(x, w, bias=None, M=None, x_rs=None, x_is=0, x2=None, x2_rs=None,
     p.out, p.o_rs, p.o_is = out.data_ptr(), out.stride(0), (N if instances > 1 else 0)
     p.M, p.N, p.K, p.instances, p.act = M, N, K, instances, act
     p.x2_cols = x2_cols  # x2 only for output columns < x2_cols (0: all)
+    if ln is not None:
+        p.ln_w, p.ln_b, p.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln[2]
+        p.ln_out = _ptr(ln_out)
+        p.ln_rs = (ln_rs if ln_rs is not None else ln_out.stride(0)) if ln_out is not None else 0
+        p.ln_is = ln_is
     call("usvm_gemm_skinny_f32", C.byref(p), _stream())
     return out
 
