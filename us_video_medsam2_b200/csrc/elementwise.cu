@@ -42,10 +42,18 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
                      float eps, int gelu, float* out_f32, int ldo_f32, bf16* out_bf16, int ldo_bf16, int rows) {
-  PDL_ENTRY();
   constexpr int C = NV * 32;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // weight and bias are constants of the model: fetched before the programmatic-dependency wait, so their latency
+  // overlaps the predecessor's tail instead of following the row statistics
+  float gw[NV], gb[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    gw[j] = __ldg(w + j * 32 + lane);
+    gb[j] = __ldg(b + j * 32 + lane);
+  }
+  PDL_ENTRY();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = x + row * ldx;
   float v[NV];
@@ -66,7 +74,7 @@ layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restri
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int c = j * 32 + lane;
-    float y = v[j] * rstd * w[c] + b[c];
+    float y = v[j] * rstd * gw[j] + gb[j];
     if (gelu) y = gelu_erf(y);
     if (out_f32) out_f32[row * ldo_f32 + c] = y;
     if (out_bf16) out_bf16[row * ldo_bf16 + c] = __float2bfloat16(y);

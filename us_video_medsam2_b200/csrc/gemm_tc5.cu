@@ -72,10 +72,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // residual (skipped when the caller adds a prefetched residual itself).
 __device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_epilogue& ep, const int row,
                                                const bool row_ok, const long long rrow, const int col0, const int N,
-                                               const bool add_residual) {
+                                               const bool add_residual, const float4* bias_pre = nullptr) {
   const int ncol = min(32, N - col0);
   if (ncol == 32) {
-    if (ep.bias) {
+    if (bias_pre) {  // fetched while the mainloop was still running
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[4 * j] += bias_pre[j].x; v[4 * j + 1] += bias_pre[j].y; v[4 * j + 2] += bias_pre[j].z; v[4 * j + 3] += bias_pre[j].w;
+      }
+    } else if (ep.bias) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
@@ -251,6 +256,20 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       return true;
     };
     bool have = fetch_residual(0, rs);
+    // ... and so does the bias segment (a constant of the model: one L2 round trip less after the accumulator is ready)
+    // (only the single-block tile, BN = 32 -- the latency-bound shapes; wider tiles have no registers to spare)
+    constexpr bool PRE_BIAS = BN == 32;
+    float4 bs[PRE_BIAS ? 8 : 1];
+    bool have_b = false;
+    if constexpr (PRE_BIAS) {
+      const int col0 = tile_n * BN;
+      if (ep.bias != nullptr && col0 + 32 <= N) {
+        const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bs[j] = __ldg(bp + j);
+        have_b = true;
+      }
+    }
     // fused LayerNorm (full 256-wide rows in this tile): pass 1 below also sums the row and parks the epilogue result
     // back in TMEM; the statistics and the normalised bf16 output follow after the loop
     const bool ln_mode = BN == 256 && ep.ln_w != nullptr;
@@ -294,7 +313,7 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           v[4 * c] += pv.x; v[4 * c + 1] += pv.y; v[4 * c + 2] += pv.z; v[4 * c + 3] += pv.w;
         }
       }
-      epilogue_block(v, ep, row, row_ok, rrow, col0, N, !have);
+      epilogue_block(v, ep, row, row_ok, rrow, col0, N, !have, (PRE_BIAS && have_b && c0 == 0) ? bs : nullptr);
       if (have) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
