@@ -95,7 +95,6 @@ conv2d_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt, co
                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int gelu,
                    float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int H, int W, int k, int s, int pad, int Ho,
                    int Wo) {
-  PDL_ENTRY();
   constexpr int LPP = COUT / 4;           // lanes per pixel
   constexpr int PIX = 256 / LPP;          // pixels per CTA
   constexpr int TW = PIX == 256 ? 16 : PIX == 64 ? 8 : 4;  // square tile
@@ -121,6 +120,17 @@ conv2d_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt, co
         if (i0 + u * 256 < nv) reinterpret_cast<float4*>(s_w)[i0 + u * 256] = v[u];
     }
   }
+  const int p = tid / LPP, c4 = (tid % LPP) * 4;
+  const int py = p / TW, px = p - py * TW;
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c4));
+  float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ln_w) {
+    lw = __ldg(reinterpret_cast<const float4*>(ln_w + c4));
+    lb = __ldg(reinterpret_cast<const float4*>(ln_b + c4));
+  }
+  // everything above is a constant of the model (weights, bias, LayerNorm parameters): staged before the
+  // programmatic-dependency wait, under the predecessor's tail
+  PDL_ENTRY();
   {  // input footprint, zero outside the image; a row of the footprint is contiguous in memory (IW * CIN floats)
     const int row_f = IW * CIN, nf = IW * row_f;
     for (int i0 = tid; i0 < nf; i0 += 256 * 6) {
@@ -139,14 +149,6 @@ conv2d_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt, co
       for (int u = 0; u < 6; ++u)
         if (i0 + u * 256 < nf) s_x[i0 + u * 256] = v[u];
     }
-  }
-  const int p = tid / LPP, c4 = (tid % LPP) * 4;
-  const int py = p / TW, px = p - py * TW;
-  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c4));
-  float4 lw = make_float4(1.f, 1.f, 1.f, 1.f), lb = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ln_w) {
-    lw = __ldg(reinterpret_cast<const float4*>(ln_w + c4));
-    lb = __ldg(reinterpret_cast<const float4*>(ln_b + c4));
   }
   __syncthreads();
   float4 acc = b4;
@@ -284,12 +286,19 @@ __global__ void __launch_bounds__(256)
 dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [49][256] */,
                        const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                        float eps, bf16* __restrict__ out, int B, int H, int W) {
-  PDL_ENTRY();
   constexpr int C = 256;
   extern __shared__ __align__(16) float dw_smem[];
   float* xs = dw_smem;                       // [7][14][256]
   float* red = dw_smem + 7 * DW_FOOT * C;    // [8 warps][8 pixels]
   const int c = threadIdx.x, warp = c >> 5, lane = c & 31;
+  // constants of the model first (49 taps, bias, LayerNorm parameters of this thread's channel): before the
+  // programmatic-dependency wait
+  float w[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) w[k] = __ldg(wt + k * C + c);
+  const float bc = __ldg(bias + c);
+  const float lw = __ldg(ln_w + c), lb = __ldg(ln_b + c);
+  PDL_ENTRY();
   const int tiles_x = W / DW_TILE;
   const int tile = blockIdx.x;
   const int ox0 = (tile % tiles_x) * DW_TILE, oy = (tile / tiles_x) % H, b = tile / (tiles_x * H);
@@ -314,14 +323,9 @@ dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt
       if (i < NV) *reinterpret_cast<float4*>(xs + 4 * i) = v[u];
     }
   }
-  float w[49];
-#pragma unroll
-  for (int k = 0; k < 49; ++k) w[k] = __ldg(wt + k * C + c);
   float acc[DW_TILE];
-  const float bc = __ldg(bias + c);
 #pragma unroll
   for (int o = 0; o < DW_TILE; ++o) acc[o] = bc;
-  const float lw = __ldg(ln_w + c), lb = __ldg(ln_b + c);
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 7; ++r) {
