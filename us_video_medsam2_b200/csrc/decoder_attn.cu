@@ -43,7 +43,14 @@ gemm_skinny_kernel(const usvm_skinny_params p) {
       for (int c = 0; c < SK_COLS; ++c)
         wpre[it][c] = __ldg(reinterpret_cast<const float4*>(Wp + (long long)min(pw_n0 + c, p.N - 1) * K + it * 128));
   }
+  // epilogue operands of this lane's output element (m, n0 + c): the bias is a constant (before the wait), the residual
+  // is read right after the wait -- both long before the reduction needs them instead of after it
+  const int e_c = pw_lane >> 3, e_m = pw_lane & 7, e_n = pw_n0 + e_c;
+  const bool e_ok = e_m < rows && e_n < p.N;
+  float e_bias = 0.f, e_res = 0.f;
+  if (e_ok && p.bias) e_bias = __ldg(p.bias + (long long)inst * p.b_is + e_n);
   PDL_ENTRY();
+  if (e_ok && p.residual) e_res = p.residual[(long long)inst * p.r_is + (long long)(m0 + e_m) * p.r_rs + e_n];
   // x2 (the positional tokens) applies to output columns < x2_cols only: projections that read `queries + pe` and
   // projections that read `queries` share one launch, with both variants of the input staged
   const bool two = p.x2 && p.x2_cols > 0 && p.x2_cols < p.N;
@@ -170,11 +177,11 @@ gemm_skinny_kernel(const usvm_skinny_params p) {
     for (int w = 0; w < SK_WARPS; ++w) v += part[w * 32 + lane];
   }
   const int n = n0 + c;
-  if (m < rows && n < p.N) {
-    if (p.bias) v += p.bias[(long long)inst * p.b_is + n];
+  if (m < rows && n < p.N) {  // (c, m, n) == (e_c, e_m, e_n): the operands were fetched at the top
+    v += e_bias;
     if (p.act == USVM_ACT_RELU) v = fmaxf(v, 0.f);
     else if (p.act == USVM_ACT_GELU) v = gelu_erf(v);
-    if (p.residual) v += p.residual[(long long)inst * p.r_is + (long long)(m0 + m) * p.r_rs + n];
+    v += e_res;
     p.out[(long long)inst * p.o_is + (long long)(m0 + m) * p.o_rs + n] = v;
   }
 }

@@ -72,7 +72,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // residual (skipped when the caller adds a prefetched residual itself).
 __device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_epilogue& ep, const int row,
                                                const bool row_ok, const long long rrow, const int col0, const int N,
-                                               const bool add_residual, const float4* bias_pre = nullptr) {
+                                               const bool add_residual, const float4* bias_pre = nullptr,
+                                               const float4* rope_pre = nullptr) {
   const int ncol = min(32, N - col0);
   if (ncol == 32) {
     if (bias_pre) {  // fetched while the mainloop was still running
@@ -93,8 +94,8 @@ __device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_e
         const long long t0 = (long long)(rb % ep.rope_table_rows) * 128 + ((col0 & 255) >> 1);
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          const float4 c4 = *reinterpret_cast<const float4*>(ep.rope_cos + t0 + (j >> 1));
-          const float4 s4 = *reinterpret_cast<const float4*>(ep.rope_sin + t0 + (j >> 1));
+          const float4 c4 = rope_pre ? rope_pre[j >> 3] : *reinterpret_cast<const float4*>(ep.rope_cos + t0 + (j >> 1));
+          const float4 s4 = rope_pre ? rope_pre[4 + (j >> 3)] : *reinterpret_cast<const float4*>(ep.rope_sin + t0 + (j >> 1));
           const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -270,6 +271,24 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         have_b = true;
       }
     }
+    // ... and the rotary tables of this row (constants too)
+    float4 rp[PRE_BIAS ? 8 : 1];
+    bool have_r = false;
+    if constexpr (PRE_BIAS) {
+      const int col0 = tile_n * BN;
+      if (ep.rope_cos && col0 < ep.rope_cols && col0 + 32 <= N) {
+        const int rb = row % ep.rope_rows_per_batch;
+        if (rb < ep.rope_n_rope) {
+          const long long t0 = (long long)(rb % ep.rope_table_rows) * 128 + ((col0 & 255) >> 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rp[j] = __ldg(reinterpret_cast<const float4*>(ep.rope_cos + t0) + j);
+            rp[4 + j] = __ldg(reinterpret_cast<const float4*>(ep.rope_sin + t0) + j);
+          }
+          have_r = true;
+        }
+      }
+    }
     // fused LayerNorm (full 256-wide rows in this tile): pass 1 below also sums the row and parks the epilogue result
     // back in TMEM; the statistics and the normalised bf16 output follow after the loop
     const bool ln_mode = BN == 256 && ep.ln_w != nullptr;
@@ -313,7 +332,8 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           v[4 * c] += pv.x; v[4 * c + 1] += pv.y; v[4 * c + 2] += pv.z; v[4 * c + 3] += pv.w;
         }
       }
-      epilogue_block(v, ep, row, row_ok, rrow, col0, N, !have, (PRE_BIAS && have_b && c0 == 0) ? bs : nullptr);
+      epilogue_block(v, ep, row, row_ok, rrow, col0, N, !have, (PRE_BIAS && have_b && c0 == 0) ? bs : nullptr,
+                     (PRE_BIAS && have_r && c0 == 0) ? rp : nullptr);
       if (have) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
