@@ -22,9 +22,15 @@ __global__ void __launch_bounds__(256)
 upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, const float* __restrict__ ln_w,
                 const float* __restrict__ ln_b, float eps, float* __restrict__ out, int B, int Hc, int Wc,
                 int feat_shared) {
-  PDL_ENTRY();
   constexpr int CPL = C / 32;
   const int lane = threadIdx.x & 31;
+  float gw[CPL], gb[CPL];  // LayerNorm parameters: constants, fetched before the programmatic-dependency wait
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    gw[j] = __ldg(ln_w + j * 32 + lane);
+    gb[j] = __ldg(ln_b + j * 32 + lane);
+  }
+  PDL_ENTRY();
   const int Ho = 2 * Hc, Wo = 2 * Wc;
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (pix >= (long long)B * Ho * Wo) return;
@@ -51,7 +57,7 @@ upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, co
 #pragma unroll
   for (int j = 0; j < CPL; ++j) {
     const int c = j * 32 + lane;
-    out[pix * C + c] = gelu_erf(v[j] * rstd * ln_w[c] + ln_b[c]);
+    out[pix * C + c] = gelu_erf(v[j] * rstd * gw[j] + gb[j]);
   }
 }
 

@@ -259,7 +259,8 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     bool have = fetch_residual(0, rs);
     // ... and so does the bias segment (a constant of the model: one L2 round trip less after the accumulator is ready)
     // (only the single-block tile, BN = 32 -- the latency-bound shapes; wider tiles have no registers to spare)
-    constexpr bool PRE_BIAS = BN == 32;
+    constexpr bool PRE_BIAS = BN <= 64;   // bias of the first column block
+    constexpr bool PRE_ROPE = BN == 32;   // rotary tables: single-block tile only
     float4 bs[PRE_BIAS ? 8 : 1];
     bool have_b = false;
     if constexpr (PRE_BIAS) {
@@ -272,9 +273,9 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
     // ... and the rotary tables of this row (constants too)
-    float4 rp[PRE_BIAS ? 8 : 1];
+    float4 rp[PRE_ROPE ? 8 : 1];
     bool have_r = false;
-    if constexpr (PRE_BIAS) {
+    if constexpr (PRE_ROPE) {
       const int col0 = tile_n * BN;
       if (ep.rope_cos && col0 < ep.rope_cols && col0 + 32 <= N) {
         const int rb = row % ep.rope_rows_per_batch;
@@ -333,7 +334,7 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
       epilogue_block(v, ep, row, row_ok, rrow, col0, N, !have, (PRE_BIAS && have_b && c0 == 0) ? bs : nullptr,
-                     (PRE_BIAS && have_r && c0 == 0) ? rp : nullptr);
+                     (PRE_ROPE && have_r && c0 == 0) ? rp : nullptr);
       if (have) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
