@@ -403,20 +403,41 @@ attn_i2t_kernel(const float* __restrict__ q, int q_rs, const float* __restrict__
   float* s_k = sm;
   float* s_v = sm + Nt * C;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < Nt * C; i += blockDim.x) {
-    const int t = i / C, cc = i - t * C;
-    s_k[i] = k[((long long)b * Nt + t) * kv_rs + cc];
-    s_v[i] = v[((long long)b * Nt + t) * kv_rs + cc];
-  }
-  __syncthreads();
   const int item = blockIdx.x * blockDim.x + threadIdx.x;  // (query, head)
-  if (item >= Nq * H) return;
-  const int qi = item / H, h = item - qi * H;
-  float qr[T2I_DH];
+  const bool active = item < Nq * H;
+  const int qi = active ? item / H : 0, h = active ? item - qi * H : 0;
+  // every global load of this thread -- its query row and its share of the token keys / values -- is issued before
+  // anything waits: one memory round trip for the whole kernel
+  float4 q4[4];
   const float4* qp = reinterpret_cast<const float4*>(q + ((long long)b * Nq + qi) * q_rs + h * T2I_DH);
 #pragma unroll
+  for (int i = 0; i < 4; ++i) q4[i] = active ? qp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int STG = 8;  // staging slots per thread: Nt * C <= 16 * 128 elements, 256 threads
+  float kk[STG], vv[STG];
+#pragma unroll
+  for (int u = 0; u < STG; ++u) {
+    const int i = threadIdx.x + u * 256;
+    kk[u] = vv[u] = 0.f;
+    if (i < Nt * C) {
+      const int t = i / C, cc = i - t * C;
+      kk[u] = k[((long long)b * Nt + t) * kv_rs + cc];
+      vv[u] = v[((long long)b * Nt + t) * kv_rs + cc];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < STG; ++u) {
+    const int i = threadIdx.x + u * 256;
+    if (i < Nt * C) {
+      s_k[i] = kk[u];
+      s_v[i] = vv[u];
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float qr[T2I_DH];
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 t4 = qp[i];
+    const float4 t4 = q4[i];
     qr[4 * i] = t4.x * scale; qr[4 * i + 1] = t4.y * scale; qr[4 * i + 2] = t4.z * scale; qr[4 * i + 3] = t4.w * scale;
   }
   float sc[T2I_MAX_NT];
@@ -514,6 +535,7 @@ extern "C" int usvm_attn_i2t_f32(const float* q, int q_rs, const float* k, const
                                  int o_rs, int B, int H, int Nq, int Nt, float scale, void* stream) {
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || Nt <= 0 || Nt > T2I_MAX_NT || Nq <= 0 || (q_rs % 4) || (o_rs % 4))
     return USVM_ERR_ARG;
+  if (Nt * H * T2I_DH > 8 * 256) return USVM_ERR_ARG;  // staging slots of the kernel
   const size_t smem = (size_t)2 * Nt * H * T2I_DH * sizeof(float);
   usvm_launch(attn_i2t_kernel, dim3(dim3(cdiv((long long)Nq * H, 256), B)), dim3(256), smem, STREAM, q, q_rs, k, v, kv_rs, out, o_rs, H, Nq,
                                                                                  Nt, scale);
