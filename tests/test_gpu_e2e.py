@@ -237,3 +237,27 @@ def test_editing_session_matches_reference_fixture(golden_dir):
                 assert float(d[same].max()) <= 4 * LOGIT_TOL, (key, i, float(d[same].max()))
             assert float(d[same].mean()) <= 8e-4, (key, i, float(d[same].mean()))
             assert dice(a[i], b[i]) >= 0.99, (key, i, dice(a[i], b[i]))
+
+
+def test_autocast_and_half_precision_frames_are_accepted():
+    """Drivers of the reference wrap the calls in torch.autocast(cuda, bfloat16) and hand over frames in any float dtype
+    (medsam2_infer_3D_CT.py:256, sam2_video_predictor_npz.py:44-54): both must work and must not change the arithmetic of
+    the path (the kernels take explicit dtypes; bf16 frames are widened on the fly)."""
+    T = 12
+    clip = synth.make_clip(T, kind="speckle").cuda()
+    pred = _predictor(19, encoder_batch=4)
+
+    def run(images, autocast):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            st = pred.init_state(images, 512, 512)
+            pred.add_new_mask(st, 0, 1, synth.box_mask())
+            return [lg.clone() for _, _, lg in pred.propagate_in_video(st)]
+
+    base = run(clip, False)
+    cast = run(clip, True)
+    assert all(lg.dtype == torch.float32 for lg in cast)
+    for a, b in zip(base, cast):
+        assert torch.equal(a, b)
+    half = run(clip.to(torch.bfloat16), True)   # frames rounded to bf16 by the caller: same path, rounded input
+    assert len(half) == T and half[1].shape == (1, 1, 512, 512)
+    assert dice(half[-1].cpu(), base[-1].cpu()) > 0.97
