@@ -237,3 +237,45 @@ def test_single_clip_encoder_sharding_gloo():
     assert all(g[1] == g[0] and g[2] == g[0] and g[3] == g[0] for g in res[0])
     # pass 1: 11 frames = batches [4,4,3] -> rank1: 4+3, rank2: 4; pass 2: 10 frames = [4,4,2] -> rank1: 4+2, rank2: 4
     assert res[1] == 13 and res[2] == 8
+
+
+def test_jpeg_folder_ingest_matches_reference(tmp_path):
+    """init_state(video_path) ingest (a16 / SURVEY 8f-3): a folder of "<index>.jpg" frames -> normalised [T,3,S,S]; held to
+    the reference's own loader (sam2/utils/misc.py:204-277) where the reference tree is mounted (the build container)."""
+    import numpy as np
+    from PIL import Image
+
+    from oracle.ref_loader import reference_available
+    from us_video_medsam2_b200.frames import load_video_frames
+
+    rng = np.random.default_rng(3)
+    for i in range(3):
+        arr = (rng.random((37, 53, 3)) * 255).astype(np.uint8)
+        Image.fromarray(arr).save(tmp_path / f"{i:05d}.jpg", quality=95)
+    Image.fromarray((rng.random((37, 53)) * 255).astype(np.uint8)).save(tmp_path / "00003.jpg")  # grayscale frame
+    images, h, w = load_video_frames(str(tmp_path), 64, True, torch.device("cpu"))
+    assert images.shape == (4, 3, 64, 64) and images.dtype == torch.float32 and (h, w) == (37, 53)
+    with pytest.raises(NotImplementedError):
+        load_video_frames(str(tmp_path / "clip.mp4"), 64, True, torch.device("cpu"))
+    with pytest.raises(RuntimeError):
+        (tmp_path / "empty").mkdir()
+        load_video_frames(str(tmp_path / "empty"), 64, True, torch.device("cpu"))
+    if not reference_available():
+        pytest.skip("reference tree not mounted: shape / error behaviour checked only")
+    import subprocess
+    import sys
+
+    # the reference's sam2 package must not shadow this repo's alias package inside the test process: run it apart
+    code = (
+        "import sys, torch, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from oracle.ref_loader import _install_shims, REF_ROOT\n"
+        "_install_shims(); sys.path.insert(0, REF_ROOT)\n"
+        "from sam2.utils.misc import load_video_frames\n"
+        f"im, h, w = load_video_frames({str(tmp_path)!r}, 64, True, compute_device=torch.device('cpu'))\n"
+        f"np.save({str(tmp_path / 'ref.npy')!r}, im.numpy()); print(h, w)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = np.load(tmp_path / "ref.npy")
+    assert r.stdout.split()[-2:] == ["37", "53"]
+    assert np.abs(images.numpy() - want).max() < 1e-6
