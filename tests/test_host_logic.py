@@ -279,3 +279,54 @@ def test_jpeg_folder_ingest_matches_reference(tmp_path):
     want = np.load(tmp_path / "ref.npy")
     assert r.stdout.split()[-2:] == ["37", "53"]
     assert np.abs(images.numpy() - want).max() < 1e-6
+
+
+def test_public_signatures_match_reference():
+    """Drop-in boundary: same parameter names, order and defaults as the reference's builders and predictor
+    methods (checked against the mounted reference tree; this build adds keyword-only-by-convention extras at the end)."""
+    import inspect
+    import json
+    import subprocess
+    import sys
+
+    from oracle.ref_loader import reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not mounted")
+    methods = ["init_state", "add_new_points_or_box", "add_new_points", "add_new_mask", "propagate_in_video",
+               "propagate_in_video_preflight", "reset_state", "clear_all_prompts_in_frame", "remove_object"]
+    code = (
+        "import sys, json, inspect\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from oracle.ref_loader import _install_shims, REF_ROOT\n"
+        "_install_shims(); sys.path.insert(0, REF_ROOT)\n"
+        "import sam2.build_sam as b\n"
+        "from sam2.sam2_video_predictor import SAM2VideoPredictor as P\n"
+        "from sam2.sam2_video_predictor_npz import SAM2VideoPredictorNPZ as N\n"
+        "def sig(f):\n"
+        "    return [(p.name, None if p.default is inspect._empty else repr(p.default)) for p in inspect.signature(f).parameters.values()]\n"
+        f"out = {{'P.' + m: sig(getattr(P, m)) for m in {methods!r}}}\n"
+        "out['N.init_state'] = sig(N.init_state)\n"
+        "out['build_sam2_video_predictor'] = sig(b.build_sam2_video_predictor)\n"
+        "out['build_sam2_video_predictor_npz'] = sig(b.build_sam2_video_predictor_npz)\n"
+        "print(json.dumps(out))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    want = json.loads(r.stdout.strip().splitlines()[-1])
+
+    import sam2.build_sam as b
+    from sam2.sam2_video_predictor import SAM2VideoPredictor as P
+    from sam2.sam2_video_predictor_npz import SAM2VideoPredictorNPZ as N
+
+    def sig(f):
+        return [[p.name, None if p.default is inspect._empty else repr(p.default)]
+                for p in inspect.signature(f).parameters.values()]
+
+    got = {"P." + m: sig(getattr(P, m)) for m in methods}
+    got["N.init_state"] = sig(N.init_state)
+    got["build_sam2_video_predictor"] = sig(b.build_sam2_video_predictor)
+    got["build_sam2_video_predictor_npz"] = sig(b.build_sam2_video_predictor_npz)
+    for name, ref_params in want.items():
+        mine = [p for p in got[name] if p[0] not in ("args", "kwargs")]
+        ref_params = [p for p in ref_params if p[0] not in ("args", "kwargs")]
+        assert mine[: len(ref_params)] == ref_params, (name, mine, ref_params)
