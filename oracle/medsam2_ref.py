@@ -544,6 +544,8 @@ class RefModel:
             h = linear(h, self.p(f + "pwconv2.weight"), self.p(f + "pwconv2.bias")) * self.p(f + "gamma")
             x = x + h.permute(0, 3, 1, 2)
         x = conv2d(x, self.p(e + "out_proj.weight"), self.p(e + "out_proj.bias"))
+        if not getattr(self.cfg, "no_obj_embed_spatial", True):  # EfficientTAM: the parameter does not exist
+            return x
         absent = 1 - (score > 0).float()
         return x + absent[..., None, None] * self.p("no_obj_embed_spatial")[..., None, None]
 
@@ -596,8 +598,11 @@ class RefModel:
         if pos_ptrs:
             plist, ptrs = zip(*pos_ptrs)
             ptrs = torch.stack(ptrs, dim=1)  # [B, P, C]
-            tp = sine_pos_1d(torch.tensor(plist, dtype=torch.float32) / (max_ptrs - 1), C)
-            tp = linear(tp, self.p("obj_ptr_tpos_proj.weight"), self.p("obj_ptr_tpos_proj.bias"))
+            if getattr(cfg, "add_tpos_enc_to_obj_ptrs", True):
+                tp = sine_pos_1d(torch.tensor(plist, dtype=torch.float32) / (max_ptrs - 1), C)
+                tp = linear(tp, self.p("obj_ptr_tpos_proj.weight"), self.p("obj_ptr_tpos_proj.bias"))
+            else:  # sam2_base.py:1403-1404 / efficienttam_base.py: zero position encoding for the pointers
+                tp = torch.zeros((len(plist), cfg.mem_dim))
             split = C // cfg.mem_dim
             mem.append(ptrs.reshape(B, -1, cfg.mem_dim))
             mem_pos.append(tp.repeat_interleave(split, dim=0)[None].expand(B, -1, -1))
@@ -678,8 +683,8 @@ class RefPredictor:
     reference's CPU behaviour (the CUDA-only CC op raises and the step is skipped,
     misc.py:321-336); `True` reproduces its GPU behaviour."""
 
-    def __init__(self, state_dict, cfg=Cfg, fill_holes=True):
-        self.model = RefModel(state_dict, cfg)
+    def __init__(self, state_dict, cfg=Cfg, fill_holes=True, model_cls=None):
+        self.model = (model_cls or RefModel)(state_dict, cfg)
         self.cfg = cfg
         self.image_size = cfg.image_size
         self.fill_holes = fill_holes

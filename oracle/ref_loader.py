@@ -93,3 +93,26 @@ def load_reference_predictor(npz=True, apply_postprocessing=True, seed=0, overri
     torch.manual_seed(seed)
     model = _instantiate(cfg).eval()
     return model
+
+
+def load_reference_etam_predictor(apply_postprocessing=True, seed=0, config="efficienttam_ti_512x512.yaml"):
+    """Build the reference's EfficientTAMVideoPredictorNPZ (efficient_track_anything/build_efficienttam.py:175-222) on CPU
+    with the same shims; `compile_image_encoder` is forced off as the builder does without a capable GPU (:185-188)."""
+    assert reference_available(), "reference mount missing"
+    if REF_ROOT in sys.path:
+        sys.path.remove(REF_ROOT)
+    sys.path.insert(0, REF_ROOT)
+    _install_shims()
+    cfg = yaml.safe_load(open(os.path.join(REF_ROOT, "efficient_track_anything/configs", config)))["model"]
+    cfg["_target_"] = "efficient_track_anything.efficienttam_video_predictor_npz.EfficientTAMVideoPredictorNPZ"
+    cfg["compile_image_encoder"] = False
+    if apply_postprocessing:
+        cfg["sam_mask_decoder_extra_args"] = dict(
+            dynamic_multimask_via_stability=True,
+            dynamic_multimask_stability_delta=0.05,
+            dynamic_multimask_stability_thresh=0.98,
+        )
+        cfg["binarize_mask_from_pts_for_mem_enc"] = True
+        cfg["fill_hole_area"] = 8
+    torch.manual_seed(seed)
+    return _instantiate(cfg).eval()

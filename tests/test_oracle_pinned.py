@@ -53,3 +53,34 @@ def test_oracle_encoder_matches_reference_fixture(golden_dir):
     assert np.allclose(f["feat_s0"][0, :, ::8, ::8].numpy(), g["enc_feat_s0_s8"], atol=2e-5)
     assert np.allclose(f["feat_s1"][0, :, ::4, ::4].numpy(), g["enc_feat_s1_s4"], atol=2e-5)
     assert np.allclose(f["feat"][0, :, ::2, ::2].numpy(), g["enc_feat_s2"], atol=5e-5)
+
+
+def test_etam_oracle_matches_reference_fixture(golden_dir):
+    """EfficientTAM-ti: oracle/etam_ref.py (ViT trunk + ViTDetNeck + the three model switches) against the
+    reference's own outputs (tests/golden/etam_ti_mask_fwd.npz from oracle/make_golden_etam.py).  The CUDA path for this
+    variant is not built yet; this pins the checker it will be held to."""
+    from oracle.etam_ref import EtamCfg, RefModelETAM, etam_predictor, etam_state_dict_abi, make_etam_state_dict
+    from oracle.make_golden_etam import SEED, T
+
+    g = np.load(os.path.join(golden_dir, "etam_ti_mask_fwd.npz"))
+    abi = etam_state_dict_abi()
+    assert len(abi) == 455 and sum(int(np.prod(s)) for _, s in abi) == 17866274
+    sd = make_etam_state_dict(SEED)
+    clip = synth.make_clip(T, kind="speckle")
+    with torch.inference_mode():
+        f = RefModelETAM(sd, EtamCfg).forward_image(clip[:1])
+    assert f["feat"].shape == (1, 256, 32, 32) and float(f["feat_s0"].abs().max()) == 0.0
+    assert np.allclose(f["feat"][0, :, ::2, ::2].numpy(), g["enc_feat"], atol=5e-5)
+    pred = etam_predictor(sd, fill_holes=True)
+    with torch.inference_mode():
+        st = pred.init_state(clip, 512, 512)
+        pred.add_new_mask(st, 0, 1, synth.box_mask())
+        frames = [t for t, _, _ in pred.propagate_in_video(st)]
+    assert frames == g["frames"].tolist()
+    od = st["output_dict"]
+    get = lambda t: od["cond_frame_outputs"].get(t) or od["non_cond_frame_outputs"][t]
+    low = np.stack([get(t)["pred_masks"][:, 0].float().numpy() for t in frames])
+    assert np.abs(low - g["low_res_filled"]).max() <= FP32_TOL
+    assert np.allclose(np.stack([get(t)["obj_ptr"].numpy() for t in frames]), g["obj_ptr_filled"], atol=FP32_TOL)
+    assert np.allclose(np.stack([get(t)["object_score_logits"].numpy() for t in frames]), g["score_filled"], atol=FP32_TOL)
+    assert float(g["score"].reshape(-1)[1:].min()) > 0.1  # object-present branch with margin at this seed
