@@ -16,7 +16,8 @@ import torch.nn.functional as F
 
 from oracle.medsam2_ref import Cfg, RefModel, RefPredictor, conv2d, layer_norm_2d, linear, sdpa
 
-_ABI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "etam_ti_state_dict_abi.json")
+_ABI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "us_video_medsam2_b200",
+                    "etam_ti_state_dict_abi.json")  # names + shapes dumped from the reference's state_dict()
 
 
 class EtamCfg(Cfg):

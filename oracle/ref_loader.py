@@ -99,6 +99,11 @@ def load_reference_etam_predictor(apply_postprocessing=True, seed=0, config="eff
     """Build the reference's EfficientTAMVideoPredictorNPZ (efficient_track_anything/build_efficienttam.py:175-222) on CPU
     with the same shims; `compile_image_encoder` is forced off as the builder does without a capable GPU (:185-188)."""
     assert reference_available(), "reference mount missing"
+    # the repo ships its own drop-in `efficient_track_anything` alias package; the reference must win in this process
+    for name in [k for k in sys.modules if k == "efficient_track_anything" or k.startswith("efficient_track_anything.")]:
+        mod = sys.modules[name]
+        if not getattr(mod, "__file__", "") or not str(mod.__file__).startswith(REF_ROOT):
+            del sys.modules[name]
     if REF_ROOT in sys.path:
         sys.path.remove(REF_ROOT)
     sys.path.insert(0, REF_ROOT)

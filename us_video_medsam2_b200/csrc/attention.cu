@@ -414,6 +414,7 @@ extern "C" int usvm_fmha_bf16(const usvm_fmha_params* p, void* stream) {
       (p->v_hs % 8) || (p->q_bs % 8) || (p->k_bs % 8) || (p->v_bs % 8))
     return USVM_ERR_ARG;  // 16-byte cp.async chunks
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (p->head_dim == 64) return launch_fmha<64>(p, s);
   if (p->head_dim == 96) return launch_fmha<96>(p, s);
   if (p->head_dim == 256) return launch_fmha<256>(p, s);
   return USVM_ERR_ARG;
@@ -426,7 +427,8 @@ extern "C" int usvm_fmha_combine(const usvm_fmha_params* p, void* stream) {
   const long long rows = (long long)p->B * p->H * p->Nq;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if ((p->o_rs % 4) || (p->o_hs % 4) || (p->o_bs % 4)) return USVM_ERR_ARG;
-  if (p->head_dim == 96) launch_combine<96>(p, rows, s);
+  if (p->head_dim == 64) launch_combine<64>(p, rows, s);
+  else if (p->head_dim == 96) launch_combine<96>(p, rows, s);
   else if (p->head_dim == 256) launch_combine<256>(p, rows, s);
   else return USVM_ERR_ARG;
   return usvm_check_launch();

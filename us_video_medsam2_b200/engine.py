@@ -52,8 +52,27 @@ class ModelConfig:
     dynamic_multimask_stability_thresh = 0.98
     binarize_mask_from_pts_for_mem_enc = True
     non_overlap_masks_for_mem_enc = False
+    arch = "hiera"
+    use_high_res_features_in_sam = True
+    add_tpos_enc_to_obj_ptrs = True
+    has_no_obj_embed_spatial = True
     fill_hole_area = 8
     feat = 32  # 512 / 16
+
+
+class EtamTiConfig(ModelConfig):
+    """efficient_track_anything/configs/efficienttam_ti_512x512.yaml: plain ViT-tiny trunk + ViTDetNeck; the propagation
+    tail is the shared one with three switches off (efficienttam_base.py)."""
+    arch = "vit"
+    patch = 16
+    vit_dim = 192
+    vit_depth = 12
+    vit_heads = 3
+    vit_window = 14
+    vit_window_blocks = (0, 1, 3, 4, 6, 7, 9, 10)
+    use_high_res_features_in_sam = False
+    add_tpos_enc_to_obj_ptrs = False
+    has_no_obj_embed_spatial = False
 
 
 def hiera_plan(cfg=ModelConfig):
@@ -113,31 +132,11 @@ class PackedWeights:
         self.plan = hiera_plan(cfg)
 
         # ---- image encoder ----
-        t = "image_encoder.trunk."
-        pw = g(t + "patch_embed.proj.weight").reshape(96, 147)
-        self.patch_w = dev(F.pad(pw, (0, 13)), BF16)  # K 147 -> 160 (TMA row pitch must be 16 B aligned)
-        self.patch_b = f32(t + "patch_embed.proj.bias")
-        pe = F.interpolate(g(t + "pos_embed"), size=(128, 128), mode="bicubic")
-        win = g(t + "pos_embed_window")
-        pe = pe + win.tile(1, 1, 128 // win.shape[2], 128 // win.shape[3])
-        self.hiera_pos = dev(pe[0].permute(1, 2, 0).reshape(128 * 128, 96))
-        self.blocks = []
-        for i, (din, dout, heads, ws, pool, emit) in enumerate(self.plan):
-            p = t + f"blocks.{i}."
-            blk = dict(n1=(f32(p + "norm1.weight"), f32(p + "norm1.bias")),
-                       n2=(f32(p + "norm2.weight"), f32(p + "norm2.bias")),
-                       qkv_w=w16(p + "attn.qkv.weight"), qkv_b=f32(p + "attn.qkv.bias"),
-                       proj_w=w16(p + "attn.proj.weight"), proj_b=f32(p + "attn.proj.bias"),
-                       w1=w16(p + "mlp.layers.0.weight"), b1=f32(p + "mlp.layers.0.bias"),
-                       w2=w16(p + "mlp.layers.1.weight"), b2=f32(p + "mlp.layers.1.bias"))
-            if din != dout:
-                blk["sc_w"], blk["sc_b"] = w16(p + "proj.weight"), f32(p + "proj.bias")
-            self.blocks.append(blk)
-        n = "image_encoder.neck.convs."
-        self.neck = [(w16(n + f"{j}.conv.weight"), f32(n + f"{j}.conv.bias")) for j in range(4)]
+        if cfg.arch == "vit":
+            self._pack_vit(g, dev, w16, f32)
+        else:
+            self._pack_hiera(g, dev, w16, f32)
         d = "sam_mask_decoder."
-        self.conv_s0 = (w16(d + "conv_s0.weight"), f32(d + "conv_s0.bias"))
-        self.conv_s1 = (w16(d + "conv_s1.weight"), f32(d + "conv_s1.bias"))
         self.feat_pos = dev(_sine_pos_2d(32, 32, 256))  # vision_pos_enc of the 32x32 level, [1024, 256]
 
         # ---- memory attention ----
@@ -194,10 +193,16 @@ class PackedWeights:
         self.mem_out = (w16(e + "out_proj.weight"), f32(e + "out_proj.bias"))
         self.mem_pos = dev(_sine_pos_2d(32, 32, 64))  # [1024, 64]
         self.maskmem_tpos = dev(g("maskmem_tpos_enc").reshape(cfg.num_maskmem, cfg.mem_dim))
-        self.no_obj_embed_spatial = dev(g("no_obj_embed_spatial").reshape(cfg.mem_dim))
+        # (EfficientTAM has no such parameter: a zero vector makes the shared epilogue a no-op)
+        self.no_obj_embed_spatial = (dev(g("no_obj_embed_spatial").reshape(cfg.mem_dim)) if cfg.has_no_obj_embed_spatial
+                                     else dev(torch.zeros(cfg.mem_dim)))
         self.no_mem_embed = dev(g("no_mem_embed").reshape(1, 256))
         self.no_obj_ptr = dev(g("no_obj_ptr").reshape(256))
-        self.tpos_proj = (f32("obj_ptr_tpos_proj.weight"), f32("obj_ptr_tpos_proj.bias"))
+        # add_tpos_enc_to_obj_ptrs=false (EfficientTAM): pointer tokens get a zero position encoding and
+        # obj_ptr_tpos_proj is an Identity without parameters (sam2_base.py:1393-1404)
+        self.tpos_proj = ((f32("obj_ptr_tpos_proj.weight"), f32("obj_ptr_tpos_proj.bias"))
+                          if cfg.add_tpos_enc_to_obj_ptrs else None)
+        self.zero_ptr_pos = dev(torch.zeros(4 * cfg.max_obj_ptrs_in_encoder * 2, cfg.mem_dim))
 
         # ---- prompt encoder ----
         pe_ = "sam_prompt_encoder."
@@ -302,6 +307,62 @@ class PackedWeights:
         self.obj_ptr_proj = mlp3(["obj_ptr_proj."])
 
 
+    def _pack_hiera(self, g, dev, w16, f32):
+        cfg = self.cfg
+        t = "image_encoder.trunk."
+        pw = g(t + "patch_embed.proj.weight").reshape(96, 147)
+        self.patch_w = dev(F.pad(pw, (0, 13)), BF16)  # K 147 -> 160 (TMA row pitch must be 16 B aligned)
+        self.patch_b = f32(t + "patch_embed.proj.bias")
+        pe = F.interpolate(g(t + "pos_embed"), size=(128, 128), mode="bicubic")
+        win = g(t + "pos_embed_window")
+        pe = pe + win.tile(1, 1, 128 // win.shape[2], 128 // win.shape[3])
+        self.hiera_pos = dev(pe[0].permute(1, 2, 0).reshape(128 * 128, 96))
+        self.blocks = []
+        for i, (din, dout, heads, ws, pool, emit) in enumerate(self.plan):
+            p = t + f"blocks.{i}."
+            blk = dict(n1=(f32(p + "norm1.weight"), f32(p + "norm1.bias")),
+                       n2=(f32(p + "norm2.weight"), f32(p + "norm2.bias")),
+                       qkv_w=w16(p + "attn.qkv.weight"), qkv_b=f32(p + "attn.qkv.bias"),
+                       proj_w=w16(p + "attn.proj.weight"), proj_b=f32(p + "attn.proj.bias"),
+                       w1=w16(p + "mlp.layers.0.weight"), b1=f32(p + "mlp.layers.0.bias"),
+                       w2=w16(p + "mlp.layers.1.weight"), b2=f32(p + "mlp.layers.1.bias"))
+            if din != dout:
+                blk["sc_w"], blk["sc_b"] = w16(p + "proj.weight"), f32(p + "proj.bias")
+            self.blocks.append(blk)
+        n = "image_encoder.neck.convs."
+        self.neck = [(w16(n + f"{j}.conv.weight"), f32(n + f"{j}.conv.bias")) for j in range(4)]
+        d = "sam_mask_decoder."
+        self.conv_s0 = (w16(d + "conv_s0.weight"), f32(d + "conv_s0.bias"))
+        self.conv_s1 = (w16(d + "conv_s1.weight"), f32(d + "conv_s1.bias"))
+
+    def _pack_vit(self, g, dev, w16, f32):
+        """ViT trunk + ViTDetNeck (efficient_track_anything/modeling/backbones/vitdet.py, image_encoder.py:47-108)."""
+        cfg = self.cfg
+        t = "image_encoder.trunk."
+        self.patch_w = w16(t + "patch_embed.proj.weight")  # [192, 3*16*16], k = (c, ky, kx)
+        self.patch_b = f32(t + "patch_embed.proj.bias")
+        pe = g(t + "pos_embed")[:, 1:]  # drop the cls token (get_abs_pos, backbones/utils.py:97-128)
+        size = int(round(pe.shape[1] ** 0.5))
+        n = cfg.image_size // cfg.patch
+        pe = F.interpolate(pe.reshape(1, size, size, -1).permute(0, 3, 1, 2), size=(n, n), mode="bicubic",
+                           align_corners=False)
+        self.vit_pos = dev(pe[0].permute(1, 2, 0).reshape(n * n, cfg.vit_dim))
+        self.blocks = []
+        for i in range(cfg.vit_depth):
+            p = t + f"blocks.{i}."
+            self.blocks.append(dict(n1=(f32(p + "norm1.weight"), f32(p + "norm1.bias")),
+                                    n2=(f32(p + "norm2.weight"), f32(p + "norm2.bias")),
+                                    qkv_w=w16(p + "attn.qkv.weight"), qkv_b=f32(p + "attn.qkv.bias"),
+                                    proj_w=w16(p + "attn.proj.weight"), proj_b=f32(p + "attn.proj.bias"),
+                                    w1=w16(p + "mlp.layers.0.weight"), b1=f32(p + "mlp.layers.0.bias"),
+                                    w2=w16(p + "mlp.layers.1.weight"), b2=f32(p + "mlp.layers.1.bias")))
+        nk = "image_encoder.neck.convs.0."
+        self.neck_1x1 = w16(nk + "conv_1x1.weight")
+        self.neck_ln0 = (f32(nk + "norm_0.weight"), f32(nk + "norm_0.bias"))
+        self.neck_3x3 = dev(g(nk + "conv_3x3.weight").permute(0, 2, 3, 1).reshape(256, 9 * 256), BF16)  # k = (ky, kx, ci)
+        self.neck_ln1 = (f32(nk + "norm_1.weight"), f32(nk + "norm_1.bias"))
+
+
 class Engine:
     def __init__(self, weights: PackedWeights):
         self.w = weights
@@ -339,6 +400,8 @@ class Engine:
         feat_s0 [F,16384,32]) -- Hiera.forward + FpnNeck.forward + forward_image
         (hieradet.py:283-299, image_encoder.py:104-136, sam2_base.py:1220-1232)."""
         w = self.w
+        if self.cfg.arch == "vit":
+            return self._encode_frames_vit(imgs)
         Fr = imgs.shape[0]
         A = ops.im2col_patch(imgs.contiguous())
         x, _ = ops.gemm_bf16(A, w.patch_w, bias=w.patch_b, residual=w.hiera_pos, res_mod=128 * 128, f32=True)
@@ -388,6 +451,45 @@ class Engine:
     @staticmethod
     def _wb(pair):
         return pair[0], pair[1]
+
+    def _encode_frames_vit(self, imgs):
+        """EfficientTAM image encoder: ViT.forward + ViTDetNeck.forward (efficient_track_anything/modeling/backbones/
+        vitdet.py:282-299, image_encoder.py:93-108).  imgs fp32 [F,3,512,512] -> same dict as the Hiera path; the two
+        high-resolution levels do not exist in this variant and are constant zero maps (the shared decoder kernels add
+        them), the patch embedding is a GEMM over non-overlapping 16 x 16 patches."""
+        w, cfg = self.w, self.cfg
+        Fr, P = imgs.shape[0], cfg.patch
+        n = cfg.image_size // P
+        T, C, heads = n * n, cfg.vit_dim, cfg.vit_heads
+        hd = C // heads
+        # im2col of non-overlapping patches is a pure re-layout: [F,3,n,P,n,P] -> [F,n,n,3,P,P] (rows k = (c, ky, kx))
+        A = imgs.view(Fr, 3, n, P, n, P).permute(0, 2, 4, 1, 3, 5).reshape(Fr * T, 3 * P * P).to(BF16)
+        x, _ = ops.gemm_bf16(A, w.patch_w, bias=w.patch_b, residual=w.vit_pos, res_mod=T, f32=True)
+        for i, blk in enumerate(w.blocks):
+            _, h = ops.layernorm(x, *blk["n1"], 1e-6, bf16=True)
+            _, qkv = ops.gemm_bf16(h, blk["qkv_w"], bias=blk["qkv_b"], bf16=True)
+            if i in cfg.vit_window_blocks:
+                ws = cfg.vit_window
+                Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, n, n, ws, False, C)
+                Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, hd, (0, nq * C, C, hd), (0, nk * C, C, hd),
+                              (0, nk * C, C, hd))
+                att = ops.window_scatter(Ow, Fr, n, n, ws, C)
+            else:
+                att = ops.fmha(qkv, qkv, qkv, Fr, heads, T, T, hd, (0, T * 3 * C, 3 * C, hd),
+                               (C, T * 3 * C, 3 * C, hd), (2 * C, T * 3 * C, 3 * C, hd)).reshape(Fr * T, C)
+            x, _ = ops.gemm_bf16(att, blk["proj_w"], bias=blk["proj_b"], residual=x, f32=True)
+            _, h2 = ops.layernorm(x, *blk["n2"], 1e-6, bf16=True)
+            _, m = ops.gemm_bf16(h2, blk["w1"], bias=blk["b1"], act=ACT_GELU, bf16=True)
+            last = i == len(w.blocks) - 1
+            x, xb = ops.gemm_bf16(m, blk["w2"], bias=blk["b2"], residual=x, f32=True, bf16=last)
+        y, _ = ops.gemm_bf16(xb, w.neck_1x1, f32=True)                       # 1x1 conv, no bias
+        y, _ = ops.layernorm(y, *w.neck_ln0, 1e-6, f32=True)                 # LayerNorm2d = per-pixel norm over channels
+        A3 = ops.im2col_nhwc(y, Fr, n, n, 256, 3, 1, 1)
+        z, _ = ops.gemm_bf16(A3, w.neck_3x3, f32=True)                       # 3x3 conv, no bias
+        feat, feat_b = ops.layernorm(z, *w.neck_ln1, 1e-6, f32=True, bf16=True)
+        zeros = lambda rows, ch: torch.zeros((Fr, rows, ch), dtype=F32, device=imgs.device)
+        return dict(feat=feat.view(Fr, T, 256), feat_bf16=feat_b.view(Fr, T, 256), feat_s1=zeros(4 * T, 64),
+                    feat_s0=zeros(16 * T, 32))
 
     # ---------------------------------------------------------------- memory attention
     def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None, fold_no_mask=False):
@@ -452,7 +554,10 @@ class Engine:
         """Memory-bank assembly from the frame store named by the device control block
         (sam2_base.py:1344-1437): returns (k_in, v_in, Nk, n_ptr_tokens)."""
         w = self.w
-        ptr_pos = ops.ptr_tpos(ctrl, *w.tpos_proj, n_ptr) if n_ptr > 0 else None
+        if n_ptr > 0:
+            ptr_pos = ops.ptr_tpos(ctrl, *w.tpos_proj, n_ptr) if w.tpos_proj is not None else w.zero_ptr_pos
+        else:
+            ptr_pos = None
         k_in, v_in, Nk = ops.build_memory_store(ctrl, w.mem_pos, w.maskmem_tpos, ptr_pos, B, n_mem, n_ptr)
         return k_in, v_in, Nk, 4 * n_ptr
 
@@ -822,5 +927,7 @@ class Engine:
         dim_t = 10000.0 ** (2 * torch.div(torch.arange(pe_dim, dtype=F32), 2, rounding_mode="floor") / pe_dim)
         e = rel[:, None] / dim_t
         tp = torch.cat([e.sin(), e.cos()], dim=-1).to(dev)  # get_1d_sine_pe (sam2_utils.py:64-74), [P, 256]
+        if self.w.tpos_proj is None:
+            return ptrs, torch.zeros((P * 4, 64), dtype=F32, device=dev)
         tp = ops.gemm_f32(tp.contiguous(), *self.w.tpos_proj)  # obj_ptr_tpos_proj, [P, 64]
         return ptrs, tp.repeat_interleave(4, dim=0).contiguous()

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops, synth
-from .engine import NO_OBJ_SCORE, Engine, ModelConfig, PackedWeights
+from .engine import NO_OBJ_SCORE, Engine, EtamTiConfig, ModelConfig, PackedWeights
 
 try:  # progress bar like the reference (sam2_video_predictor.py:703); optional
     from tqdm import tqdm as _tqdm
@@ -35,8 +35,8 @@ class _Node(nn.Module):
     """Bare container used to rebuild the reference's module tree (names only, no forward)."""
 
 
-def _install_abi_parameters(root):
-    for name, shape in synth.state_dict_abi():
+def _install_abi_parameters(root, abi=None):
+    for name, shape in (abi if abi is not None else synth.state_dict_abi()):
         *path, leaf = name.split(".")
         mod = root
         for p in path:
@@ -53,11 +53,14 @@ def _install_abi_parameters(root):
 class SAM2VideoPredictor(nn.Module):
     """The predictor class to handle user interactions and manage inference states."""
 
+    _config_base = ModelConfig           # architecture constants of the shipped configuration
+    _abi = staticmethod(synth.state_dict_abi)   # [(parameter name, shape)] of the reference's state dict
+
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False,
                  encoder_batch=1, use_cuda_graphs=True, encoder_sms=0, **model_kwargs):
         super().__init__()
-        cfg = type("Cfg", (ModelConfig,), {})
+        cfg = type("Cfg", (self._config_base,), {})
         for k, v in model_kwargs.items():
             if k in ("image_encoder", "memory_attention", "memory_encoder", "sam_mask_decoder_extra_args",
                      "compile_image_encoder"):
@@ -91,7 +94,7 @@ class SAM2VideoPredictor(nn.Module):
         # green-context stream that owns this many SMs (pipeline.SmPartition); 0 = encoder and tracking alternate
         self.encoder_sms = int(os.environ.get("USVM2_ENCODER_SMS", encoder_sms))
         self._partition_obj, self._partition_error, self._remote = None, None, None
-        _install_abi_parameters(self)
+        _install_abi_parameters(self, self._abi())
         self._engine = None
         self._engine_key = None
         self._graphs, self._graph_seen, self._ctrl = {}, {}, None
@@ -1006,6 +1009,24 @@ class SAM2VideoPredictor(nn.Module):
 
 class SAM2VideoPredictorNPZ(SAM2VideoPredictor):
     """Variant whose `init_state` takes pre-normalised frames (sam2_video_predictor_npz.py:44-115)."""
+
+    @torch.inference_mode()
+    def init_state(self, images, video_height, video_width, offload_video_to_cpu=False, offload_state_to_cpu=False,
+                   async_loading_frames=False):
+        return self._new_state(images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu)
+
+
+class EfficientTAMVideoPredictor(SAM2VideoPredictor):
+    """efficient_track_anything/efficienttam_video_predictor.py: the same session API over the EfficientTAM-ti model
+    (ViT-tiny trunk + ViTDetNeck; no high-resolution decoder features, no pointer temporal encoding, no
+    no_obj_embed_spatial).  The reference runs the objects of a session one at a time (:592-628); they are independent on
+    this path, so the batched frame of the base class yields the same masks per object."""
+    _config_base = EtamTiConfig
+    _abi = staticmethod(synth.etam_state_dict_abi)
+
+
+class EfficientTAMVideoPredictorNPZ(EfficientTAMVideoPredictor):
+    """efficient_track_anything/efficienttam_video_predictor_npz.py: init_state from an in-memory image tensor."""
 
     @torch.inference_mode()
     def init_state(self, images, video_height, video_width, offload_video_to_cpu=False, offload_state_to_cpu=False,

@@ -67,6 +67,19 @@ def _draw(name, shape, g):
     raise KeyError(f"no init rule for {name} {shape}")
 
 
+def etam_state_dict_abi():
+    """[(name, shape)] of the reference's EfficientTAM-ti state dict (455 tensors, 17.87 M parameters)."""
+    with open(os.path.join(os.path.dirname(__file__), "etam_ti_state_dict_abi.json")) as f:
+        return [(k, tuple(s)) for k, s in json.load(f)]
+
+
+def make_etam_state_dict(seed=0):
+    """Seeded EfficientTAM-ti weights (same drawing rules; identical to oracle.etam_ref.make_etam_state_dict)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7000003 * (seed + 1))
+    return {name: _draw(name, shape, g) for name, shape in etam_state_dict_abi()}
+
+
 def make_state_dict(seed=0):
     """Full sam2.1_hiera_t512 state dict, fp32 CPU, deterministic in `seed`."""
     g = torch.Generator(device="cpu")
