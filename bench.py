@@ -34,9 +34,11 @@ import torch  # noqa: E402
 METRIC = "propagated frames/sec (sam2.1_hiera_t512, 512x512, {objects} object{s}, 7-frame memory bank)"
 
 
-def metric_name(objects):
-    return METRIC.format(objects=objects, s="" if objects == 1 else "s")
+def metric_name(objects, model="hiera_t512"):
+    name = METRIC.format(objects=objects, s="" if objects == 1 else "s")
+    return name if model == "hiera_t512" else name.replace("sam2.1_hiera_t512", "efficienttam_ti_512x512")
 SEED = 19
+ETAM_SEED = 18
 
 
 def parse():
@@ -54,6 +56,9 @@ def parse():
                     help="N > 1: 'videos' = one independent clip per GPU (weak scaling, no communication); 'clip' = ONE "
                          "clip, rank 0 propagates, the other ranks run the frame-parallel encoder and send features over "
                          "NCCL point-to-point (strong scaling, bounded by the sequential propagation)")
+    ap.add_argument("--model", default="hiera_t512", choices=["hiera_t512", "etam_ti"],
+                    help="hiera_t512 = MedSAM2 sam2.1_hiera_t512 (BASELINE configs[1], the default); etam_ti = EfficientTAM-ti "
+                         "512x512 (BASELINE configs[3]) on the same clips")
     ap.add_argument("--cpu-sample-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -168,17 +173,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_fps(frames, objects, passes=1):
+def cpu_reference_fps(frames, objects, passes=1, model="hiera_t512"):
     """frames/s of the CPU port of the reference (oracle/medsam2_ref.py) on a `frames`-long sample of the
     workload: same weights, same clip generator, same prompt, fill-holes skipped as the reference does on CPU."""
     from oracle.medsam2_ref import RefPredictor
     from us_video_medsam2_b200 import synth
 
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = synth.make_state_dict(SEED)
     clip = synth.make_clip(frames, kind="speckle")
     masks = [synth.box_mask()] if objects == 1 else synth.multi_object_masks(objects)
-    pred = RefPredictor(sd, fill_holes=False)
+    if model == "etam_ti":
+        from oracle.etam_ref import etam_predictor
+
+        pred = etam_predictor(synth.make_etam_state_dict(ETAM_SEED), fill_holes=False)
+    else:
+        pred = RefPredictor(synth.make_state_dict(SEED), fill_holes=False)
     best = None
     with torch.inference_mode():
         for _ in range(passes):
@@ -200,17 +209,18 @@ def run_reference(args, rank):
     times = []
     cores = os.cpu_count() or 1
     for i in range(args.warmup + args.steps):
-        fps, cores = cpu_reference_fps(sample, args.objects)
+        fps, cores = cpu_reference_fps(sample, args.objects, model=args.model)
         if i >= args.warmup:
             times.append(sample / fps)
     ms = 1000.0 * sum(times) / len(times)
     value = sample / (ms / 1000.0)
     unit = "frames/s"
     print(json.dumps({
-        "metric": metric_name(args.objects), "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+        "metric": metric_name(args.objects, args.model), "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"sam2.1_hiera_t512 propagate_in_video, CPU port of the reference, {sample}-frame sample "
+        "config": {"workload": f"{'sam2.1_hiera_t512' if args.model == 'hiera_t512' else 'efficienttam_ti_512x512'} "
+                               f"propagate_in_video, CPU port of the reference, {sample}-frame sample "
                                f"of the {args.frames}-frame synthetic echo clip, {args.objects} object(s)",
                    "frames_per_step": sample, "objects": args.objects},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
@@ -344,9 +354,18 @@ def run_b200(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.frames, args.objects
     clip_mode = args.mode == "clip" and world > 1
-    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=args.encoder_batch,
-                                          encoder_sms=0 if clip_mode else args.encoder_sms)
-    pred.load_state_dict(synth.make_state_dict(SEED), strict=True)
+    if args.model == "etam_ti":
+        from us_video_medsam2_b200.build_etam import build_efficienttam_video_predictor_npz
+
+        pred = build_efficienttam_video_predictor_npz("configs/efficienttam_ti_512x512.yaml", device=dev,
+                                                      encoder_batch=args.encoder_batch,
+                                                      encoder_sms=0 if clip_mode else args.encoder_sms)
+        pred.load_state_dict(synth.make_etam_state_dict(ETAM_SEED), strict=True)
+    else:
+        pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev,
+                                              encoder_batch=args.encoder_batch,
+                                              encoder_sms=0 if clip_mode else args.encoder_sms)
+        pred.load_state_dict(synth.make_state_dict(SEED), strict=True)
     masks = [synth.box_mask()] if B == 1 else synth.multi_object_masks(B)
     # 'clip' mode: every rank holds the SAME clip (rank 0 tracks it, the others encode their share of its frames)
     gray_host = synth.make_clip_u8(T, seed=1234 + (0 if clip_mode else rank)).pin_memory()  # [T,512,512] uint8, pinned
@@ -457,17 +476,18 @@ def run_b200(args, rank, world):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = max(4, min(T, args.cpu_sample_frames))
-        fps, cores = cpu_reference_fps(sample, B)
+        fps, cores = cpu_reference_fps(sample, B, model=args.model)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"{sample}-frame sample of the same clip, oracle port of the reference, torch "
                          f"{torch.__version__} CPU fp32"}
     if rank == 0:
         print(json.dumps({
-            "metric": metric_name(B), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(B, args.model), "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if clip_mode else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"sam2.1_hiera_t512 propagate_in_video, {T}-frame synthetic echo clip "
+            "config": {"workload": f"{'sam2.1_hiera_t512' if args.model == 'hiera_t512' else 'efficienttam_ti_512x512'} "
+                                   f"propagate_in_video, {T}-frame synthetic echo clip "
                                    f"{'(one clip for all GPUs)' if clip_mode else 'per GPU'}, "
                                    f"{B} object(s), 7-frame memory bank, mask prompt on frame 0",
                        "frames": T, "objects": B, "encoder_batch": args.encoder_batch,

@@ -159,6 +159,9 @@ int usvm_maxpool2_nhwc(const float* x, float* y, int F, int H, int W, int C, voi
 int usvm_upsample2_add(float* fine, const float* coarse, void* fine_bf16, int F, int H, int W, int C, void* stream);
 /* PatchEmbed 7x7/s4/p3 as im2col (backbones/utils.py:64-94): img fp32 [F,3,S,S] -> bf16 [F*(S/4)^2, KP>=147] */
 int usvm_im2col_patch(const float* img, void* A, int F, int S, int KP, void* stream);
+/* ViT PatchEmbed with kernel = stride = P, no padding (efficient_track_anything/modeling/backbones/vitdet.py:214-220,
+ * utils.py:64-94): img fp32 [F,3,S,S] -> bf16 [F*(S/P)^2, 3*P*P], column (c, ky, kx); P % 8 == 0 */
+int usvm_im2col_patch_grid(const float* img, void* A, int F, int S, int P, void* stream);
 /* frame ingest (sam2/utils/misc.py:253-276): uint8 gray [F,H,W] -> fp32 [F,3,H,W] (x/255 - mean)/std */
 int usvm_normalize_gray_u8(const uint8_t* gray, float* out, int F, int H, int W, const float* mean3_host,
                            const float* std3_host, void* stream);

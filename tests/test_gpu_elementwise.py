@@ -428,3 +428,13 @@ def test_frame_store_kernels():
     ops.store_outputs(ctrl, a, score, c)
     assert torch.equal(store.ptr[5], a) and torch.equal(store.score[5], score) and torch.equal(store.masks[5], c)
     assert float(store.masks[4].abs().max()) == 0
+
+
+def test_im2col_patch_grid_matches_relayout():
+    """ViT patch embedding im2col (kernel = stride = 16): equals the pure re-layout of the image."""
+    from us_video_medsam2_b200 import ops
+
+    img = torch.randn((3, 3, 64, 64), generator=_g(5), device="cuda")
+    got = ops.im2col_patch_grid(img, 16)
+    want = img.view(3, 3, 4, 16, 4, 16).permute(0, 2, 4, 1, 3, 5).reshape(3 * 16, 768).to(torch.bfloat16)
+    assert torch.equal(got, want)

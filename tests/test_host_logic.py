@@ -309,6 +309,11 @@ def test_public_signatures_match_reference():
         "out['N.init_state'] = sig(N.init_state)\n"
         "out['build_sam2_video_predictor'] = sig(b.build_sam2_video_predictor)\n"
         "out['build_sam2_video_predictor_npz'] = sig(b.build_sam2_video_predictor_npz)\n"
+        "import efficient_track_anything.build_efficienttam as eb\n"
+        "from efficient_track_anything.efficienttam_video_predictor import EfficientTAMVideoPredictor as EP\n"
+        "out['build_efficienttam_video_predictor'] = sig(eb.build_efficienttam_video_predictor)\n"
+        "out['build_efficienttam_video_predictor_npz'] = sig(eb.build_efficienttam_video_predictor_npz)\n"
+        f"out.update({{'EP.' + m: sig(getattr(EP, m)) for m in {[m for m in methods if m != 'propagate_in_video_preflight']!r}}})\n"
         "print(json.dumps(out))\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -326,6 +331,12 @@ def test_public_signatures_match_reference():
     got["N.init_state"] = sig(N.init_state)
     got["build_sam2_video_predictor"] = sig(b.build_sam2_video_predictor)
     got["build_sam2_video_predictor_npz"] = sig(b.build_sam2_video_predictor_npz)
+    import efficient_track_anything.build_efficienttam as eb
+    from efficient_track_anything.efficienttam_video_predictor import EfficientTAMVideoPredictor as EP
+
+    got["build_efficienttam_video_predictor"] = sig(eb.build_efficienttam_video_predictor)
+    got["build_efficienttam_video_predictor_npz"] = sig(eb.build_efficienttam_video_predictor_npz)
+    got.update({"EP." + m: sig(getattr(EP, m)) for m in methods if m != "propagate_in_video_preflight"})
     for name, ref_params in want.items():
         mine = [p for p in got[name] if p[0] not in ("args", "kwargs")]
         ref_params = [p for p in ref_params if p[0] not in ("args", "kwargs")]

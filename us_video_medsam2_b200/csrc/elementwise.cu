@@ -284,6 +284,27 @@ __global__ void im2col_patch_kernel(const float* __restrict__ img, bf16* __restr
   }
 }
 
+// Non-overlapping P x P patches (ViT PatchEmbed, kernel = stride = P, no padding; efficient_track_anything/modeling/
+// backbones/utils.py:64-94 with vitdet.py:214-220): img fp32 [F,3,S,S] -> bf16 [F*(S/P)^2, 3*P*P], k = (c, ky, kx).
+// One thread moves 8 consecutive kx: a 32-byte read from an image row, a 16-byte write.
+__global__ void im2col_patch_grid_kernel(const float* __restrict__ img, bf16* __restrict__ A, int F, int S, int P) {
+  PDL_ENTRY();
+  const int G = S / P, K = 3 * P * P, K8 = K >> 3, P8 = P >> 3;
+  const long long total = (long long)F * G * G * K8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k8 = (int)(i % K8);
+    const long long t = i / K8;
+    const int ox = (int)(t % G), oy = (int)((t / G) % G), f = (int)(t / ((long long)G * G));
+    const int kx0 = (k8 % P8) << 3, ky = (k8 / P8) % P, c = k8 / (P8 * P);
+    const float4* src = reinterpret_cast<const float4*>(img + (((long long)f * 3 + c) * S + (oy * P + ky)) * S + ox * P + kx0);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    uint4 pk;
+    pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w);
+    pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(A + t * K + (k8 << 3)) = pk;
+  }
+}
+
 // uint8 grayscale [F,S,S] -> normalised fp32 [F,3,S,S] ((g/255 - mean_c)/std_c, misc.py:253-276)
 __global__ void normalize_gray_kernel(const uint8_t* __restrict__ g, float* __restrict__ out, long long frames_px,
                                       long long px, float m0, float m1, float m2, float s0, float s1, float s2) {
@@ -558,6 +579,15 @@ extern "C" int usvm_im2col_patch(const float* img, void* A, int F, int S, int KP
   if (!img || !A || (S % 4) || KP < 147 || (KP % 8) || (reinterpret_cast<uintptr_t>(A) & 15)) return USVM_ERR_ARG;
   usvm_launch(im2col_patch_kernel, dim3(grid_for((long long)F * (S / 4) * (S / 4) * (KP / 8))), dim3(256), 0, STREAM, 
       img, reinterpret_cast<bf16*>(A), F, S, KP);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_im2col_patch_grid(const float* img, void* A, int F, int S, int P, void* stream) {
+  if (!img || !A || F <= 0 || S <= 0 || P <= 0 || (P % 8) || (S % P) || (reinterpret_cast<uintptr_t>(img) & 15) ||
+      (reinterpret_cast<uintptr_t>(A) & 15))
+    return USVM_ERR_ARG;
+  const long long total = (long long)F * (S / P) * (S / P) * (3 * P * P / 8);
+  usvm_launch(im2col_patch_grid_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, img, reinterpret_cast<bf16*>(A), F, S, P);
   return usvm_check_launch();
 }
 

@@ -462,8 +462,7 @@ class Engine:
         n = cfg.image_size // P
         T, C, heads = n * n, cfg.vit_dim, cfg.vit_heads
         hd = C // heads
-        # im2col of non-overlapping patches is a pure re-layout: [F,3,n,P,n,P] -> [F,n,n,3,P,P] (rows k = (c, ky, kx))
-        A = imgs.view(Fr, 3, n, P, n, P).permute(0, 2, 4, 1, 3, 5).reshape(Fr * T, 3 * P * P).to(BF16)
+        A = ops.im2col_patch_grid(imgs.contiguous(), P)  # [F*T, 3*P*P] bf16, k = (c, ky, kx)
         x, _ = ops.gemm_bf16(A, w.patch_w, bias=w.patch_b, residual=w.vit_pos, res_mod=T, f32=True)
         for i, blk in enumerate(w.blocks):
             _, h = ops.layernorm(x, *blk["n1"], 1e-6, bf16=True)

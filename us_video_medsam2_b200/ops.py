@@ -261,6 +261,15 @@ def im2col_patch(img, KP=160):
     return A
 
 
+def im2col_patch_grid(imgs, P):
+    """fp32 [F,3,S,S] -> bf16 [F*(S/P)^2, 3*P*P]: non-overlapping P x P patches, columns (c, ky, kx)."""
+    _chk(imgs, F32, "imgs")
+    Fr, _, S, _ = imgs.shape
+    A = empty((Fr * (S // P) * (S // P), 3 * P * P), BF16, imgs)
+    call("usvm_im2col_patch_grid", imgs.data_ptr(), A.data_ptr(), Fr, S, P, _stream())
+    return A
+
+
 def normalize_gray_u8(gray, mean, std):
     F, H, W = gray.shape
     out = empty((F, 3, H, W), F32, gray)
