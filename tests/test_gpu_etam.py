@@ -66,3 +66,22 @@ def test_predictor_matches_reference_fixture(golden_dir):
     assert np.sign(score).tolist() == np.sign(g["score_filled"]).tolist() and np.abs(score - g["score_filled"]).max() < 2e-2
     ptr = np.stack([get(t)["obj_ptr"].float().cpu().numpy() for t in frames])
     assert np.abs(ptr - g["obj_ptr_filled"]).max() < 5e-2
+
+
+def test_two_objects_reverse_matches_per_object_reference(golden_dir):
+    """Two objects (mask + clicks) prompted on the last frame, tracked in reverse: the batched CUDA frame against the
+    reference's one-object-at-a-time EfficientTAM predictor."""
+    from efficient_track_anything.build_efficienttam import build_efficienttam_video_predictor_npz
+    from oracle.make_golden_etam import SEED, T, run_two_objects
+
+    g = np.load(os.path.join(golden_dir, "etam_ti_two_obj_reverse.npz"))
+    pred = build_efficienttam_video_predictor_npz("configs/efficienttam_ti_512x512.yaml", device="cuda")
+    pred.load_state_dict(synth.make_etam_state_dict(SEED), strict=True)
+    got = run_two_objects(pred, synth.make_clip(T, kind="speckle").cuda())
+    assert got["frames"].tolist() == g["frames"].tolist() and got["obj_ids"].tolist() == g["obj_ids"].tolist()
+    a, b = torch.from_numpy(got["video_s4"]), torch.from_numpy(g["video_s4"])
+    assert a.shape == b.shape
+    for i in range(a.shape[0]):
+        for o in range(a.shape[1]):
+            assert dice(a[i, o], b[i, o]) >= 0.99, (i, o, dice(a[i, o], b[i, o]))
+            assert float((a[i, o] - b[i, o]).abs().mean()) <= 8e-4, (i, o)

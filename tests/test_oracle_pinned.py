@@ -84,3 +84,16 @@ def test_etam_oracle_matches_reference_fixture(golden_dir):
     assert np.allclose(np.stack([get(t)["obj_ptr"].numpy() for t in frames]), g["obj_ptr_filled"], atol=FP32_TOL)
     assert np.allclose(np.stack([get(t)["object_score_logits"].numpy() for t in frames]), g["score_filled"], atol=FP32_TOL)
     assert float(g["score"].reshape(-1)[1:].min()) > 0.1  # object-present branch with margin at this seed
+
+
+def test_etam_two_objects_reverse_matches_per_object_reference(golden_dir):
+    """The reference's EfficientTAM predictor runs the objects of a session one at a time; the oracle's batched session
+    logic must give the same masks per object (mask + click prompts on the last frame, reverse tracking)."""
+    from oracle.etam_ref import etam_predictor, make_etam_state_dict
+    from oracle.make_golden_etam import SEED, T, run_two_objects
+
+    g = np.load(os.path.join(golden_dir, "etam_ti_two_obj_reverse.npz"))
+    pred = etam_predictor(make_etam_state_dict(SEED), fill_holes=True)
+    got = run_two_objects(pred, synth.make_clip(T, kind="speckle"))
+    assert got["frames"].tolist() == g["frames"].tolist() and got["obj_ids"].tolist() == g["obj_ids"].tolist()
+    assert np.abs(got["video_s4"] - g["video_s4"]).max() <= FP32_TOL

@@ -691,6 +691,8 @@ class SAM2VideoPredictor(nn.Module):
                 pred_masks = None
             self._add_output_per_object(st, frame_idx, current_out, storage_key)
             st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
+            for tracked in st.get("frames_tracked_per_obj", {}).values():  # EfficientTAM's per-object bookkeeping
+                tracked[frame_idx] = {"reverse": reverse}
             if pred_masks is not None:
                 _, video_res_masks = self._get_orig_video_res_output(st, pred_masks)
             elif self.non_overlap_masks:
@@ -1016,6 +1018,15 @@ class SAM2VideoPredictorNPZ(SAM2VideoPredictor):
         return self._new_state(images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu)
 
 
+class _PerObjectTracked(dict):
+    """`frames_tracked_per_obj` of the EfficientTAM session state (efficienttam_video_predictor.py:103): one dict per object
+    index, created on first use."""
+
+    def __missing__(self, key):
+        self[key] = {}
+        return self[key]
+
+
 class EfficientTAMVideoPredictor(SAM2VideoPredictor):
     """efficient_track_anything/efficienttam_video_predictor.py: the same session API over the EfficientTAM-ti model
     (ViT-tiny trunk + ViTDetNeck; no high-resolution decoder features, no pointer temporal encoding, no
@@ -1023,6 +1034,20 @@ class EfficientTAMVideoPredictor(SAM2VideoPredictor):
     this path, so the batched frame of the base class yields the same masks per object."""
     _config_base = EtamTiConfig
     _abi = staticmethod(synth.etam_state_dict_abi)
+
+    def _new_state(self, *args, **kwargs):
+        st = super()._new_state(*args, **kwargs)
+        st["frames_tracked_per_obj"] = _PerObjectTracked()
+        return st
+
+    def _obj_id_to_idx(self, st, obj_id):
+        idx = super()._obj_id_to_idx(st, obj_id)
+        st["frames_tracked_per_obj"][idx]  # noqa: B018  (creates the object's entry)
+        return idx
+
+    def _reset_tracking_results(self, st):
+        super()._reset_tracking_results(st)
+        st["frames_tracked_per_obj"].clear()
 
 
 class EfficientTAMVideoPredictorNPZ(EfficientTAMVideoPredictor):
