@@ -261,3 +261,24 @@ def test_autocast_and_half_precision_frames_are_accepted():
     half = run(clip.to(torch.bfloat16), True)   # frames rounded to bf16 by the caller: same path, rounded input
     assert len(half) == T and half[1].shape == (1, 1, 512, 512)
     assert dice(half[-1].cpu(), base[-1].cpu()) > 0.97
+
+
+def test_bidirectional_ct_driver_flow_matches_reference_fixture(golden_dir):
+    """ the 3-D driver's sequence -- box prompt on a key slice under autocast, forward pass, reset_state, the
+    same box, reverse pass, union -- on a 300 x 420 volume, against the reference's own outputs."""
+    from oracle.make_golden_ct import SEED, T, ct_session
+
+    g = np.load(os.path.join(golden_dir, "t512_ct_bidirectional.npz"))
+    pred = _predictor(SEED, encoder_batch=4)
+    got = ct_session(pred, synth.make_clip(T, kind="speckle").cuda())
+    for k in ("frames_fwd", "frames_rev"):
+        assert got[k].tolist() == g[k].tolist()
+    for k in ("logits_fwd_s2", "logits_rev_s2"):
+        a, b = torch.from_numpy(got[k]), torch.from_numpy(g[k])
+        for i in range(a.shape[0]):
+            assert dice(a[i], b[i]) >= DICE_BAR, (k, i, dice(a[i], b[i]))
+            assert float((a[i] - b[i]).abs().mean()) <= 8e-4, (k, i)
+    seg_a, seg_b = got["segs"].astype(bool), g["segs"].astype(bool)
+    for t in range(T):
+        d = 2.0 * (seg_a[t] & seg_b[t]).sum() / max(1, seg_a[t].sum() + seg_b[t].sum())
+        assert d >= DICE_BAR, (t, d)
