@@ -171,3 +171,33 @@ def test_fill_holes_against_reference_kernel_composition():
         got = fill_holes_in_mask_scores(mask, 8)
         assert torch.equal(got, want)
         assert int(is_hole.sum()) > 0
+
+
+def test_postprocess_masks_against_reference_kernel_composition():
+    """SAM2Transforms.postprocess_masks (sam2/utils/transforms.py:76-115), the second caller of the CC op: hole filling and
+    sprinkle removal at a non-zero threshold, then the resize -- against the same formula evaluated with the reference's
+    own kernel."""
+    from sam2.utils.transforms import SAM2Transforms
+
+    ref = _reference_op()
+    tr = SAM2Transforms(resolution=512, mask_threshold=0.25, max_hole_area=12, max_sprinkle_area=7)
+    g = torch.Generator().manual_seed(11)
+    masks = (torch.randn((2, 3, 128, 128), generator=g) * 0.6 + 0.3).cuda()
+    masks[:, :, 30:70, 30:70] = masks[:, :, 30:70, 30:70].abs() + 0.3    # a blob with punched holes ...
+    masks[:, :, 40:42, 40:43] = -1.0
+    masks[:, :, 90:120, 10:60] = -masks[:, :, 90:120, 10:60].abs()          # ... and an empty region with sprinkles
+    masks[:, :, 100, 30] = 2.0
+    masks[:, :, 105:107, 40:42] = 1.5
+    got = tr.postprocess_masks(masks, (300, 420))
+    flat = masks.flatten(0, 1).unsqueeze(1)
+    lab, area = ref((flat <= 0.25).to(torch.uint8))
+    hole = ((lab > 0) & (area <= 12)).reshape_as(masks)
+    want = torch.where(hole, 0.25 + 10.0, masks)
+    lab, area = ref((flat > 0.25).to(torch.uint8))
+    spr = ((lab > 0) & (area <= 7)).reshape_as(masks)
+    want = torch.where(spr, 0.25 - 10.0, want)
+    assert int(hole.sum()) > 0 and int(spr.sum()) > 0
+    want = torch.nn.functional.interpolate(want, (300, 420), mode="bilinear", align_corners=False)
+    assert got.shape == (2, 3, 300, 420) and torch.equal(got, want)
+    pts = torch.tensor([[[210.0, 150.0]]])
+    assert torch.allclose(tr.transform_coords(pts, normalize=True, orig_hw=(300, 420)), torch.tensor([[[256.0, 256.0]]]))
