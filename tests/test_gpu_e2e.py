@@ -282,3 +282,37 @@ def test_bidirectional_ct_driver_flow_matches_reference_fixture(golden_dir):
     for t in range(T):
         d = 2.0 * (seg_a[t] & seg_b[t]).sum() / max(1, seg_a[t].sum() + seg_b[t].sum())
         assert d >= DICE_BAR, (t, d)
+
+
+def test_image_predictor_matches_reference_fixture(golden_dir):
+    """ SAM2ImagePredictor.set_image / predict -- a click with 3 multimask outputs, box + negative click with
+    one output (stability fallback), refinement from a previous low-res mask -- against the reference's own outputs.
+    Same noise floor as a tracked frame (bf16 image encoder, fp32-operand decoder); bars stated below."""
+    from oracle.make_golden_image import SEED, image_session
+    from sam2.sam2_image_predictor import SAM2ImagePredictor
+
+    g = np.load(os.path.join(golden_dir, "t512_image_predictor.npz"))
+    model = _predictor(SEED)
+    pred = SAM2ImagePredictor(model, max_hole_area=8, max_sprinkle_area=4)
+    with pytest.raises(RuntimeError):
+        pred.predict(point_coords=np.zeros((1, 2), np.float32), point_labels=np.ones(1, np.int32))  # no image set yet
+    got = image_session(pred)
+    assert set(got) == set(g.files)
+    for k in g.files:
+        a, b = got[k], g[k]
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        if k.endswith("_iou"):
+            assert np.abs(a - b).max() < 2e-2, (k, a, b)
+            assert int(np.argmax(a)) == int(np.argmax(b))
+        elif k == "d_binary_s2":
+            for i in range(a.shape[0]):
+                assert dice(torch.from_numpy(a[i].astype(np.float32)) - 0.5, torch.from_numpy(b[i].astype(np.float32)) - 0.5) >= 0.99
+        else:
+            for i in range(a.shape[0]):
+                x, y = torch.from_numpy(a[i]), torch.from_numpy(b[i])
+                if k.endswith("_low"):  # the decoder's own logits: the bf16 noise floor of the path
+                    assert float((x - y).abs().mean()) <= 8e-4, (k, i, float((x - y).abs().mean()))
+                    assert float((x - y).abs().max()) <= 4 * LOGIT_TOL, (k, i, float((x - y).abs().max()))
+                # (the full-resolution masks went through hole / sprinkle rewriting to +-10 at a threshold and the resize
+                # blends those spikes into their neighbours: only the binary agreement is comparable there)
+                assert dice(x, y) >= 0.99, (k, i, dice(x, y))

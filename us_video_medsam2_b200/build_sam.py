@@ -93,6 +93,16 @@ def _build(cls, config_file, ckpt_path, device, mode, hydra_overrides_extra, app
     return model
 
 
+def build_sam2(config_file, ckpt_path=None, device=None, mode="eval", hydra_overrides_extra=[],
+               apply_postprocessing=True, **kwargs):
+    """reference: sam2/build_sam.py:72-93 (returns the bare SAM2Base there).  Here the model object that owns the
+    state-dict ABI and the kernel engine is the predictor class, so the same object serves `SAM2ImagePredictor(model)`."""
+    extra = list(hydra_overrides_extra)
+    if apply_postprocessing:  # only the stability fallback here (build_sam.py:76-83), not the video overrides
+        extra = _POSTPROCESSING_OVERRIDES[:3] + extra
+    return _build(SAM2VideoPredictor, config_file, ckpt_path, device, mode, extra, False, **kwargs)
+
+
 def build_sam2_video_predictor(config_file, ckpt_path=None, device=None, mode="eval", hydra_overrides_extra=[],
                                apply_postprocessing=True, **kwargs):
     """reference: sam2/build_sam.py:95-133"""

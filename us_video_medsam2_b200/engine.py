@@ -710,7 +710,7 @@ class Engine:
                 ptr = sk(sk(t1, P2[0], pb2[0], act=ACT_RELU), P3[0], pb3[0])
                 return ops.objptr_mix_(ptr, score, w.no_obj_ptr)
 
-            return dict(low=low, obj_ptr=None, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36],
+            return dict(low=low, obj_ptr=None, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36], idx=idx,
                         finish_ptr=finish_ptr, _keep=(hs, idx))
         if chain:
             E = lambda *shape: ops.empty(shape, F32, src)
@@ -726,7 +726,7 @@ class Engine:
             t2 = sk(t1, P2[0], pb2[0], act=ACT_RELU)
             ptr = sk(t2, P3[0], pb3[0])
         ops.objptr_mix_(ptr, score, w.no_obj_ptr)
-        return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36])
+        return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36], idx=idx)
 
     def _two_way_transformer(self, tokens, keys, B, Nt, img_stream=None, const0=None, defer_final_norm=False):
         """TwoWayTransformer (sam/transformer.py:90-135) with one launch per token-side layer: any token count.
