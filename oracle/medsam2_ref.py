@@ -929,3 +929,71 @@ class RefPredictor:
             st["output_dict"][k].clear()
             st["consolidated_frame_inds"][k].clear()
         st["tracking_has_started"] = False
+
+
+# --------------------------------------------------------------------------------------
+# image predictor (sam2/sam2_image_predictor.py) -- checker for us_video_medsam2_b200/image_predictor.py
+# --------------------------------------------------------------------------------------
+class RefImagePredictor:
+    """Restatement of SAM2ImagePredictor.set_image / predict (sam2_image_predictor.py:86-131, 238-430) and of
+    SAM2Transforms.postprocess_masks (sam2/utils/transforms.py:76-115) with the CC restatement in place of sam2._C."""
+
+    def __init__(self, state_dict, cfg=Cfg, mask_threshold=0.0, max_hole_area=0.0, max_sprinkle_area=0.0):
+        self.model = RefModel(state_dict, cfg)
+        self.cfg = cfg
+        self.mask_threshold, self.max_hole_area, self.max_sprinkle_area = mask_threshold, max_hole_area, max_sprinkle_area
+        self._feats = None
+
+    def set_image(self, image):
+        from torchvision.transforms import Normalize, Resize, ToTensor  # the reference's own pre-processing ops
+
+        self._orig_hw = tuple(image.shape[:2])
+        s = self.cfg.image_size
+        x = Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])(Resize((s, s))(ToTensor()(image)))[None]
+        f = self.model.forward_image(x)
+        f["feat"] = f["feat"] + self.model.p("no_mem_embed").reshape(1, -1, 1, 1)  # directly_add_no_mem_embed (:117-121)
+        self._feats = f
+
+    def _post(self, masks):
+        from oracle.cc_ref import connected_components_ref
+
+        thr = self.mask_threshold
+        flat = masks.flatten(0, 1).unsqueeze(1)
+        if self.max_hole_area > 0:
+            lab, area = connected_components_ref((flat <= thr).to(torch.uint8).numpy())
+            hole = torch.from_numpy((lab > 0) & (area <= self.max_hole_area)).reshape_as(masks)
+            masks = torch.where(hole, torch.full_like(masks, thr + 10.0), masks)
+        if self.max_sprinkle_area > 0:
+            lab, area = connected_components_ref((flat > thr).to(torch.uint8).numpy())
+            spr = torch.from_numpy((lab > 0) & (area <= self.max_sprinkle_area)).reshape_as(masks)
+            masks = torch.where(spr, torch.full_like(masks, thr - 10.0), masks)
+        return F.interpolate(masks, self._orig_hw, mode="bilinear", align_corners=False)
+
+    def predict(self, point_coords=None, point_labels=None, box=None, mask_input=None, multimask_output=True,
+                return_logits=False, normalize_coords=True):
+        if self._feats is None:
+            raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        m, s = self.model, float(self.cfg.image_size)
+        h, w = self._orig_hw
+        scale = torch.tensor([s / w, s / h]) if normalize_coords else torch.tensor([s, s])
+        coords = labels = None
+        if point_coords is not None:
+            coords = torch.as_tensor(point_coords, dtype=torch.float32).reshape(1, -1, 2) * scale
+            labels = torch.as_tensor(point_labels, dtype=torch.int32).reshape(1, -1)
+        if box is not None:  # corners as points labelled 2 / 3, placed first (:392-404)
+            bc = torch.as_tensor(box, dtype=torch.float32).reshape(1, 2, 2) * scale
+            bl = torch.tensor([[2, 3]], dtype=torch.int32)
+            coords = bc if coords is None else torch.cat([bc, coords], dim=1)
+            labels = bl if labels is None else torch.cat([bl, labels], dim=1)
+        f = self._feats
+        sparse = m.embed_points(coords, labels) if coords is not None else torch.zeros(1, 0, 256)
+        if mask_input is not None:
+            dense = m.embed_mask(torch.as_tensor(mask_input, dtype=torch.float32).reshape(1, 1, 128, 128))
+        else:
+            dense = m.p("sam_prompt_encoder.no_mask_embed.weight").reshape(1, -1, 1, 1).expand(1, -1, 32, 32)
+        low, iou, _, _ = m.mask_decoder(f["feat"], sparse, dense, f["feat_s0"], f["feat_s1"], multimask_output)
+        masks = self._post(low.float())
+        low = low.clamp(-32.0, 32.0)
+        if not return_logits:
+            masks = masks > self.mask_threshold
+        return masks[0].float().numpy() if return_logits else masks[0].numpy(), iou[0].numpy(), low[0].numpy()

@@ -114,3 +114,21 @@ def test_oracle_matches_bidirectional_ct_driver_fixture(golden_dir):
         d = np.abs(got[k] - g[k])
         assert float(np.mean(d > FP32_TOL)) < 1e-4, (k, float(d.max()))  # (isolated hole-fill flips at the threshold)
     assert float(np.mean(got["segs"] != g["segs"])) < 1e-5
+
+
+def test_oracle_image_predictor_matches_reference_fixture(golden_dir):
+    """SAM2ImagePredictor restatement (oracle.medsam2_ref.RefImagePredictor) against the reference's own outputs."""
+    from oracle.make_golden_image import SEED, image_session
+    from oracle.medsam2_ref import RefImagePredictor
+
+    g = np.load(os.path.join(golden_dir, "t512_image_predictor.npz"))
+    pred = RefImagePredictor(synth.make_state_dict(SEED), max_hole_area=8, max_sprinkle_area=4)
+    with torch.inference_mode():
+        got = image_session(pred)
+    for k in g.files:
+        a, b = np.asarray(got[k], dtype=np.float32), g[k].astype(np.float32)
+        assert a.shape == b.shape, k
+        if k.endswith("_low") or k.endswith("_iou"):
+            assert np.abs(a - b).max() <= FP32_TOL, (k, float(np.abs(a - b).max()))
+        else:  # post-processed: a pixel within rounding of the threshold may flip a hole / sprinkle
+            assert float(np.mean(np.abs(a - b) > FP32_TOL)) < 2e-3, (k, float(np.mean(np.abs(a - b) > FP32_TOL)))
