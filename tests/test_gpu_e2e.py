@@ -316,3 +316,36 @@ def test_image_predictor_matches_reference_fixture(golden_dir):
                 # (the full-resolution masks went through hole / sprinkle rewriting to +-10 at a threshold and the resize
                 # blends those spikes into their neighbours: only the binary agreement is comparable there)
                 assert dice(x, y) >= 0.99, (k, i, dice(x, y))
+
+
+def test_interleaved_sessions_on_one_predictor():
+    """Two sessions whose propagate_in_video generators are advanced alternately on ONE predictor: the look-ahead slots and
+    the encoder graph's static outputs are shared state of the predictor, so the second session must neither steal the
+    first one's pipeline nor leave stale cached features behind.  Each session must reproduce its own solo run."""
+    T = 24
+    clips = [synth.make_clip(T, kind="speckle", seed=1234 + i).cuda() for i in range(2)]
+    for sms in (0, 48):
+        pred = _predictor(19, encoder_batch=4, encoder_sms=sms)
+
+        def solo(clip):
+            st = pred.init_state(clip, 512, 512)
+            pred.add_new_mask(st, 0, 1, synth.box_mask())
+            return [lg.clone() for _, _, lg in pred.propagate_in_video(st)]
+
+        want = [solo(c) for c in clips]
+        states = []
+        for c in clips:
+            st = pred.init_state(c, 512, 512)
+            pred.add_new_mask(st, 0, 1, synth.box_mask())
+            states.append(st)
+        gens = [pred.propagate_in_video(st) for st in states]
+        got = [[], []]
+        for _ in range(T):
+            for i, gen in enumerate(gens):
+                got[i].append(next(gen)[2].clone())
+        for gen in gens:
+            gen.close()
+        assert pred._pipeline_owner is None
+        for i in range(2):
+            for t, (a, b) in enumerate(zip(got[i], want[i])):
+                assert dice(a.cpu(), b.cpu()) >= DICE_BAR, (sms, i, t, dice(a.cpu(), b.cpu()))

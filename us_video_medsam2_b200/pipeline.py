@@ -162,11 +162,13 @@ class PartitionProducer:
         from . import _lib
 
         if k == 0:
-            graph, static_in, out, n_kernels = self.pred._encoder_graph(self.n)  # full-device graph, own buffers
+            graph, static_in, out, n_kernels = self.pred._encoder_graph(self.n)  # full-device graph
             self.pred._load_frames(self.st, frames, static_in)
             graph.replay()
+            self.pred._static_gen += 1  # (cached views of these static outputs held by any session are now stale)
             _lib.launch_count += n_kernels
-            self.pending[k] = (None, out)
+            # its static outputs are shared with every other user of that graph: this batch gets its own copy (72 MB)
+            self.pending[k] = (None, {name: t.clone() for name, t in out.items()})
             return
         graph, static_in, out, n_kernels = self.pred._encoder_graph(self.n, slot, self.part)
         enc = self.part.stream

@@ -94,6 +94,8 @@ class SAM2VideoPredictor(nn.Module):
         # green-context stream that owns this many SMs (pipeline.SmPartition); 0 = encoder and tracking alternate
         self.encoder_sms = int(os.environ.get("USVM2_ENCODER_SMS", encoder_sms))
         self._partition_obj, self._partition_error, self._remote = None, None, None
+        self._static_gen = 0            # bumped by every replay of the full-device encoder graph (static output buffers)
+        self._pipeline_owner = None     # the session whose propagate_in_video currently owns the look-ahead slots
         _install_abi_parameters(self, self._abi())
         self._engine = None
         self._engine_key = None
@@ -240,6 +242,10 @@ class SAM2VideoPredictor(nn.Module):
         propagate_in_video a FeaturePipeline may already hold them (encoded ahead on an SM partition or another GPU)."""
         cache = st["cached_features"]
         hit = cache.get(frame_idx)
+        if hit is not None and hit.get("_static") and hit.get("_gen") != self._static_gen:
+            # views of the encoder graph's static outputs that another session (or a later batch) has overwritten since
+            st["cached_features"] = cache = {t: v for t, v in cache.items() if not v.get("_static")}
+            hit = None
         if hit is not None:
             return hit
         pipe = st.get("_pipeline")
@@ -258,6 +264,7 @@ class SAM2VideoPredictor(nn.Module):
             graph, static_in, out, n_kernels = self._encoder_graph(len(idxs))
             self._load_frames(st, idxs, static_in)
             graph.replay()
+            self._static_gen += 1
             _lib.launch_count += n_kernels
             keep = {}
         else:
@@ -268,7 +275,7 @@ class SAM2VideoPredictor(nn.Module):
             keep[t] = {k: v[j] for k, v in out.items()}
         if self.use_cuda_graphs and len(idxs) == self.encoder_batch and self.encoder_batch > 1:
             for t in idxs:
-                keep[t]["_static"] = True
+                keep[t]["_static"], keep[t]["_gen"] = True, self._static_gen
         st["cached_features"] = keep
         return keep[frame_idx]
 
@@ -382,6 +389,8 @@ class SAM2VideoPredictor(nn.Module):
             return FeaturePipeline(plan, RemoteProducer(self._remote, n, self.device), depth=len(self._remote.ranks))
         if n < 2 or len(tracked) <= n:
             return None  # a single batch: nothing to overlap with
+        if self._pipeline_owner is not None and self._pipeline_owner is not st:
+            return None  # another session is mid-propagation and owns the look-ahead slots: alternate for this one
         part = self._partition()
         if part is None:
             return None
@@ -395,6 +404,7 @@ class SAM2VideoPredictor(nn.Module):
             self._partition_error = repr(e)
             warnings.warn(f"image encoder could not be captured on the SM partition ({e!r}); alternating instead")
             return None
+        self._pipeline_owner = st
         return FeaturePipeline(plan, PartitionProducer(self, st, part, n), depth=1)
 
     def _frame(self, st, t):
@@ -668,6 +678,8 @@ class SAM2VideoPredictor(nn.Module):
             pipe = st.pop("_pipeline", None)
             if pipe is not None:
                 pipe.close()
+            if self._pipeline_owner is st:
+                self._pipeline_owner = None
 
     def _propagate_loop(self, st, order, reverse, clear_non_cond_mem, B):
         output_dict = st["output_dict"]
