@@ -919,6 +919,95 @@ class RefPredictor:
             st["frames_already_tracked"][t] = {"reverse": reverse}
             yield t, st["obj_ids"], self._video_res(st, pm)
 
+    def _reset_tracking_results(self, st):
+        """sam2_video_predictor.py:860-876: every prompt and tracking result goes, the object ids stay."""
+        for k in ("point_inputs_per_obj", "mask_inputs_per_obj"):
+            for v in st[k].values():
+                v.clear()
+        for k in ("output_dict_per_obj", "temp_output_dict_per_obj"):
+            for v in st[k].values():
+                v["cond_frame_outputs"].clear()
+                v["non_cond_frame_outputs"].clear()
+        for k in ("cond_frame_outputs", "non_cond_frame_outputs"):
+            st["output_dict"][k].clear()
+            st["consolidated_frame_inds"][k].clear()
+        st["tracking_has_started"] = False
+        st["frames_already_tracked"].clear()
+
+    def clear_all_prompts_in_frame(self, st, frame_idx, obj_id, need_output=True):
+        """sam2_video_predictor.py:777-846."""
+        idx = self._obj_idx(st, obj_id)
+        st["point_inputs_per_obj"][idx].pop(frame_idx, None)
+        st["mask_inputs_per_obj"][idx].pop(frame_idx, None)
+        tmp = st["temp_output_dict_per_obj"]
+        tmp[idx]["cond_frame_outputs"].pop(frame_idx, None)
+        tmp[idx]["non_cond_frame_outputs"].pop(frame_idx, None)
+        B = len(st["obj_idx_to_id"])
+        has_input = any(frame_idx in st["point_inputs_per_obj"][i] or frame_idx in st["mask_inputs_per_obj"][i]
+                        for i in range(B))
+        if not has_input:  # the frame stops being a conditioning frame: its output is downgraded
+            od, cfi = st["output_dict"], st["consolidated_frame_inds"]
+            cfi["cond_frame_outputs"].discard(frame_idx)
+            cfi["non_cond_frame_outputs"].discard(frame_idx)
+            out = od["cond_frame_outputs"].pop(frame_idx, None)
+            if out is not None:
+                od["non_cond_frame_outputs"][frame_idx] = out
+                st["frames_already_tracked"].pop(frame_idx, None)
+            for i in range(B):
+                pod = st["output_dict_per_obj"][i]
+                o = pod["cond_frame_outputs"].pop(frame_idx, None)
+                if o is not None:
+                    pod["non_cond_frame_outputs"][frame_idx] = o
+            if len(od["cond_frame_outputs"]) == 0:
+                self._reset_tracking_results(st)
+        if not need_output:
+            return None
+        is_cond = any(frame_idx in t["cond_frame_outputs"] for t in tmp.values())
+        cons = self._consolidate(st, frame_idx, is_cond, False, True)
+        return frame_idx, st["obj_ids"], self._video_res(st, cons["pred_masks_video_res"])
+
+    def remove_object(self, st, obj_id, strict=False, need_output=True):
+        """sam2_video_predictor.py:1042-1152."""
+        rm = st["obj_id_to_idx"].get(obj_id)
+        updated = []
+        if rm is None:
+            if not strict:
+                return st["obj_ids"], updated
+            raise RuntimeError(f"Cannot remove object id {obj_id} as it doesn't exist.")
+        if len(st["obj_id_to_idx"]) == 1:
+            self.reset_state(st)
+            return st["obj_ids"], updated
+        input_frames = set(st["point_inputs_per_obj"][rm]) | set(st["mask_inputs_per_obj"][rm])
+        for t in input_frames:
+            self.clear_all_prompts_in_frame(st, t, obj_id, need_output=False)
+        old_ids = st["obj_ids"]
+        old_inds = list(range(len(old_ids)))
+        keep = [i for i in old_inds if i != rm]
+        new_ids = [old_ids[i] for i in keep]
+        remap = {o: n for n, o in enumerate(keep)}
+        st["obj_id_to_idx"] = OrderedDict((oid, n) for n, oid in enumerate(new_ids))
+        st["obj_idx_to_id"] = OrderedDict((n, oid) for n, oid in enumerate(new_ids))
+        st["obj_ids"] = new_ids
+        for k in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj"):
+            c = st[k]
+            vals = {i: c.pop(i) for i in old_inds}
+            c.update({remap[i]: v for i, v in vals.items() if i in remap})
+        for key in ("cond_frame_outputs", "non_cond_frame_outputs"):
+            for t, out in st["output_dict"][key].items():
+                out["maskmem_features"] = out["maskmem_features"][keep]
+                out["maskmem_pos_enc"] = [x[keep] for x in out["maskmem_pos_enc"]]
+                out["pred_masks"] = out["pred_masks"][keep]
+                out["obj_ptr"] = out["obj_ptr"][keep]
+                out["object_score_logits"] = out["object_score_logits"][keep]
+                self._per_object(st, t, out, key)
+        if need_output:
+            tmp = st["temp_output_dict_per_obj"]
+            for t in input_frames:
+                is_cond = any(t in d["cond_frame_outputs"] for d in tmp.values())
+                cons = self._consolidate(st, t, is_cond, False, True)
+                updated.append((t, self._video_res(st, cons["pred_masks_video_res"])))
+        return st["obj_ids"], updated
+
     def reset_state(self, st):
         """sam2_video_predictor.py:848-876."""
         for k in ("obj_id_to_idx", "obj_idx_to_id", "point_inputs_per_obj", "mask_inputs_per_obj",

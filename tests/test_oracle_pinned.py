@@ -132,3 +132,22 @@ def test_oracle_image_predictor_matches_reference_fixture(golden_dir):
             assert np.abs(a - b).max() <= FP32_TOL, (k, float(np.abs(a - b).max()))
         else:  # post-processed: a pixel within rounding of the threshold may flip a hole / sprinkle
             assert float(np.mean(np.abs(a - b) > FP32_TOL)) < 2e-3, (k, float(np.mean(np.abs(a - b) > FP32_TOL)))
+
+
+def test_oracle_editing_session_matches_reference_fixture(golden_dir):
+    """(a16) correction click on a tracked frame, re-propagation, clear_all_prompts_in_frame, remove_object: the oracle's
+    session logic against the reference's own outputs (tests/golden/t512_edit_session.npz)."""
+    from oracle.make_golden_edit import SEED, T, edit_session
+
+    g = np.load(os.path.join(golden_dir, "t512_edit_session.npz"))
+    pred = RefPredictor(synth.make_state_dict(SEED), fill_holes=True)
+    with torch.inference_mode():
+        got = edit_session(pred, synth.make_clip(T, kind="speckle"), synth.box_mask())
+    assert set(got) == set(g.files)
+    for k in g.files:
+        a, b = np.asarray(got[k]), g[k]
+        assert a.shape == b.shape, (k, a.shape, b.shape)
+        if a.dtype.kind in "iu":
+            assert a.tolist() == b.tolist(), k
+        else:  # (isolated hole-fill flips at the threshold)
+            assert float(np.mean(np.abs(a - b) > FP32_TOL)) < 1e-4, (k, float(np.abs(a - b).max()))
