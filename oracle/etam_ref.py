@@ -16,8 +16,6 @@ import torch.nn.functional as F
 
 from oracle.medsam2_ref import Cfg, RefModel, RefPredictor, conv2d, layer_norm_2d, linear, sdpa
 
-_ABI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "us_video_medsam2_b200",
-                    "etam_ti_state_dict_abi.json")  # names + shapes dumped from the reference's state_dict()
 
 
 class EtamCfg(Cfg):
@@ -34,19 +32,23 @@ class EtamCfg(Cfg):
     no_obj_embed_spatial = False
 
 
-def etam_state_dict_abi():
-    """[(name, shape)] of the reference's EfficientTAM-ti state dict (455 tensors, 17.87 M parameters)."""
-    with open(_ABI) as f:
-        return [(k, tuple(s)) for k, s in json.load(f)]
+class EtamSCfg(EtamCfg):
+    """efficient_track_anything/configs/efficienttam_s_512x512.yaml: ViT-small trunk (384-d, 6 heads of 64)."""
+    vit_dim = 384
+    vit_heads = 6
 
 
-def make_etam_state_dict(seed=0):
+def etam_state_dict_abi(variant="ti"):
+    from us_video_medsam2_b200.synth import etam_state_dict_abi as abi
+
+    return abi(variant)
+
+
+def make_etam_state_dict(seed=0, variant="ti"):
     """Seeded weights for every tensor of the ABI (same drawing rules as synth.make_state_dict)."""
-    from us_video_medsam2_b200.synth import _draw
+    from us_video_medsam2_b200.synth import make_etam_state_dict as make
 
-    g = torch.Generator(device="cpu")
-    g.manual_seed(7000003 * (seed + 1))
-    return {name: _draw(name, shape, g) for name, shape in etam_state_dict_abi()}
+    return make(seed, variant)
 
 
 class RefModelETAM(RefModel):
@@ -111,8 +113,8 @@ class RefModelETAM(RefModel):
                     pos=self.sine_pos(x.shape[2], x.shape[3], 256))
 
 
-def etam_predictor(state_dict, fill_holes=True):
+def etam_predictor(state_dict, fill_holes=True, cfg=EtamCfg):
     """RefPredictor over the EfficientTAM model.  The reference's EfficientTAM predictor keeps per-object state and runs
     objects one at a time (efficienttam_video_predictor.py:592-628); objects are independent on this path, so the batched
     session logic of RefPredictor yields the same masks per object."""
-    return RefPredictor(state_dict, cfg=EtamCfg, fill_holes=fill_holes, model_cls=RefModelETAM)
+    return RefPredictor(state_dict, cfg=cfg, fill_holes=fill_holes, model_cls=RefModelETAM)

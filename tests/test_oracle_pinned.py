@@ -151,3 +151,24 @@ def test_oracle_editing_session_matches_reference_fixture(golden_dir):
             assert a.tolist() == b.tolist(), k
         else:  # (isolated hole-fill flips at the threshold)
             assert float(np.mean(np.abs(a - b) > FP32_TOL)) < 1e-4, (k, float(np.abs(a - b).max()))
+
+
+def test_etam_small_oracle_matches_reference_fixture(golden_dir):
+    """efficienttam_s_512x512 (ViT-small trunk, 384-d / 6 heads): same restatement, second configuration."""
+    from oracle.etam_ref import EtamSCfg, etam_predictor, etam_state_dict_abi, make_etam_state_dict
+    from oracle.make_golden_etam import SEED_S, T_S
+
+    g = np.load(os.path.join(golden_dir, "etam_s_mask_fwd.npz"))
+    abi = etam_state_dict_abi("s")
+    assert len(abi) == 455 and sum(int(np.prod(s)) for _, s in abi) == 34056098
+    pred = etam_predictor(make_etam_state_dict(SEED_S, "s"), fill_holes=True, cfg=EtamSCfg)
+    with torch.inference_mode():
+        st = pred.init_state(synth.make_clip(T_S, kind="speckle"), 512, 512)
+        pred.add_new_mask(st, 0, 1, synth.box_mask())
+        frames = [t for t, _, _ in pred.propagate_in_video(st)]
+    assert frames == g["frames"].tolist()
+    od = st["output_dict"]
+    get = lambda t: od["cond_frame_outputs"].get(t) or od["non_cond_frame_outputs"][t]
+    low = np.stack([get(t)["pred_masks"][:, 0].float().numpy() for t in frames])
+    assert np.abs(low - g["low_res_filled"]).max() <= FP32_TOL
+    assert np.allclose(np.stack([get(t)["object_score_logits"].numpy() for t in frames]), g["score_filled"], atol=FP32_TOL)

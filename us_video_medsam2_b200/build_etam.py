@@ -1,5 +1,6 @@
 """Builders of the EfficientTAM variant, mirroring efficient_track_anything/build_efficienttam.py:93-222 (same names,
-arguments and post-processing overrides; Hydra is not used -- the one shipped configuration is `efficienttam_ti_512x512`).
+arguments and post-processing overrides; Hydra is not used -- shipped configurations: `efficienttam_ti_512x512` and
+`efficienttam_s_512x512`).
 `vos_optimized` selects a torch.compile'd predictor in the reference; here every kernel is already native, so the flag is
 accepted and has no effect."""
 import logging
@@ -9,13 +10,29 @@ import torch
 from .build_sam import _load_checkpoint, _parse_value
 from .predictor import EfficientTAMVideoPredictor, EfficientTAMVideoPredictorNPZ
 
-_CONFIGS = ("efficienttam_ti_512x512.yaml", "configs/efficienttam_ti_512x512.yaml",
-            "configs/efficienttam/efficienttam_ti_512x512.yaml")
+from . import synth
+from .engine import EtamSConfig
+
+_CONFIGS = {"efficienttam_ti_512x512.yaml": "ti", "efficienttam_s_512x512.yaml": "s"}
+
+
+def _variant(config_file):
+    name = str(config_file).replace("\\", "/").rsplit("/", 1)[-1]
+    if name not in _CONFIGS:
+        raise FileNotFoundError(f"unknown config {config_file!r}: this build ships {sorted(_CONFIGS)}")
+    return _CONFIGS[name]
+
+
+def _predictor_class(cls, variant):
+    """The class attributes that fix the architecture (config constants, state-dict ABI) per shipped configuration."""
+    if variant == "ti":
+        return cls
+    return type(cls.__name__ + "S", (cls,), dict(_config_base=EtamSConfig,
+                                                 _abi=staticmethod(lambda: synth.etam_state_dict_abi("s"))))
 
 
 def _kwargs(config_file, overrides, apply_postprocessing):
-    if config_file not in _CONFIGS:
-        raise FileNotFoundError(f"unknown config {config_file!r}: this build ships efficienttam_ti_512x512.yaml")
+    _variant(config_file)
     kw = {}
     if apply_postprocessing:  # build_efficienttam.py:117-128
         kw["sam_mask_decoder_extra_args"] = dict(dynamic_multimask_via_stability=True,
@@ -39,7 +56,7 @@ def _build(cls, config_file, ckpt_path, device, mode, hydra_overrides_extra, app
     logging.info(f"Using device: {device}")
     model_kwargs = _kwargs(config_file, list(hydra_overrides_extra), apply_postprocessing)
     model_kwargs.update(kwargs)
-    model = cls(**model_kwargs)
+    model = _predictor_class(cls, _variant(config_file))(**model_kwargs)
     _load_checkpoint(model, ckpt_path)
     model = model.to(device)
     if mode == "eval":

@@ -75,6 +75,12 @@ class EtamTiConfig(ModelConfig):
     has_no_obj_embed_spatial = False
 
 
+class EtamSConfig(EtamTiConfig):
+    """efficient_track_anything/configs/efficienttam_s_512x512.yaml: ViT-small trunk (384-d, 6 heads of 64)."""
+    vit_dim = 384
+    vit_heads = 6
+
+
 def hiera_plan(cfg=ModelConfig):
     """(dim_in, dim_out, heads, window, pool, emit) per block; window size lags one stage
     (hieradet.py:201-256)."""

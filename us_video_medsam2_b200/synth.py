@@ -67,17 +67,18 @@ def _draw(name, shape, g):
     raise KeyError(f"no init rule for {name} {shape}")
 
 
-def etam_state_dict_abi():
-    """[(name, shape)] of the reference's EfficientTAM-ti state dict (455 tensors, 17.87 M parameters)."""
-    with open(os.path.join(os.path.dirname(__file__), "etam_ti_state_dict_abi.json")) as f:
+def etam_state_dict_abi(variant="ti"):
+    """[(name, shape)] of the reference's EfficientTAM state dict: "ti" = efficienttam_ti_512x512 (455 tensors, 17.87 M
+    parameters), "s" = efficienttam_s_512x512 (455 tensors, 34.06 M)."""
+    with open(os.path.join(os.path.dirname(__file__), f"etam_{variant}_state_dict_abi.json")) as f:
         return [(k, tuple(s)) for k, s in json.load(f)]
 
 
-def make_etam_state_dict(seed=0):
-    """Seeded EfficientTAM-ti weights (same drawing rules; identical to oracle.etam_ref.make_etam_state_dict)."""
+def make_etam_state_dict(seed=0, variant="ti"):
+    """Seeded EfficientTAM weights (same drawing rules as make_state_dict)."""
     g = torch.Generator(device="cpu")
-    g.manual_seed(7000003 * (seed + 1))
-    return {name: _draw(name, shape, g) for name, shape in etam_state_dict_abi()}
+    g.manual_seed((7000003 if variant == "ti" else 9000011) * (seed + 1))
+    return {name: _draw(name, shape, g) for name, shape in etam_state_dict_abi(variant)}
 
 
 def make_state_dict(seed=0):
