@@ -37,10 +37,7 @@ def test_vit_encoder_matches_oracle():
     assert torch.equal(one["feat"][0], out["feat"][1])  # frame-parallel: batched == per-frame
 
 
-@pytest.mark.parametrize("variant", ["ti", pytest.param("s", marks=pytest.mark.skipif(
-    os.environ.get("USVM2_ETAM_S") != "1",
-    reason="efficienttam_s: oracle pinned on CPU; the CUDA configuration has not had its first GPU run yet "
-           "(set USVM2_ETAM_S=1 to run it)"))])
+@pytest.mark.parametrize("variant", ["ti", "s"])
 def test_predictor_matches_reference_fixture(golden_dir, variant):
     from efficient_track_anything.build_efficienttam import build_efficienttam_video_predictor_npz
     from oracle.make_golden_etam import SEED, SEED_S, T, T_S
