@@ -36,9 +36,10 @@ METRIC = "propagated frames/sec (sam2.1_hiera_t512, 512x512, {objects} object{s}
 
 def metric_name(objects, model="hiera_t512"):
     name = METRIC.format(objects=objects, s="" if objects == 1 else "s")
-    return name if model == "hiera_t512" else name.replace("sam2.1_hiera_t512", "efficienttam_ti_512x512")
+    return name.replace("sam2.1_hiera_t512", MODEL_NAMES[model])
 SEED = 19
-ETAM_SEED = 18
+ETAM_SEEDS = {"etam_ti": 18, "etam_s": 3}   # object-present branch with margin at random init
+MODEL_NAMES = {"hiera_t512": "sam2.1_hiera_t512", "etam_ti": "efficienttam_ti_512x512", "etam_s": "efficienttam_s_512x512"}
 
 
 def parse():
@@ -56,9 +57,9 @@ def parse():
                     help="N > 1: 'videos' = one independent clip per GPU (weak scaling, no communication); 'clip' = ONE "
                          "clip, rank 0 propagates, the other ranks run the frame-parallel encoder and send features over "
                          "NCCL point-to-point (strong scaling, bounded by the sequential propagation)")
-    ap.add_argument("--model", default="hiera_t512", choices=["hiera_t512", "etam_ti"],
-                    help="hiera_t512 = MedSAM2 sam2.1_hiera_t512 (BASELINE configs[1], the default); etam_ti = EfficientTAM-ti "
-                         "512x512 (BASELINE configs[3]) on the same clips")
+    ap.add_argument("--model", default="hiera_t512", choices=["hiera_t512", "etam_ti", "etam_s"],
+                    help="hiera_t512 = MedSAM2 sam2.1_hiera_t512 (BASELINE configs[1], the default); etam_ti / etam_s = "
+                         "EfficientTAM tiny / small at 512x512 (BASELINE configs[3]) on the same clips")
     ap.add_argument("--cpu-sample-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -182,10 +183,12 @@ def cpu_reference_fps(frames, objects, passes=1, model="hiera_t512"):
     torch.set_num_threads(os.cpu_count() or 1)
     clip = synth.make_clip(frames, kind="speckle")
     masks = [synth.box_mask()] if objects == 1 else synth.multi_object_masks(objects)
-    if model == "etam_ti":
-        from oracle.etam_ref import etam_predictor
+    if model != "hiera_t512":
+        from oracle.etam_ref import EtamCfg, EtamSCfg, etam_predictor
 
-        pred = etam_predictor(synth.make_etam_state_dict(ETAM_SEED), fill_holes=False)
+        v = model.split("_")[1]
+        pred = etam_predictor(synth.make_etam_state_dict(ETAM_SEEDS[model], v), fill_holes=False,
+                              cfg=EtamCfg if v == "ti" else EtamSCfg)
     else:
         pred = RefPredictor(synth.make_state_dict(SEED), fill_holes=False)
     best = None
@@ -219,7 +222,7 @@ def run_reference(args, rank):
         "metric": metric_name(args.objects, args.model), "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{'sam2.1_hiera_t512' if args.model == 'hiera_t512' else 'efficienttam_ti_512x512'} "
+        "config": {"workload": f"{MODEL_NAMES[args.model]} "
                                f"propagate_in_video, CPU port of the reference, {sample}-frame sample "
                                f"of the {args.frames}-frame synthetic echo clip, {args.objects} object(s)",
                    "frames_per_step": sample, "objects": args.objects},
@@ -354,13 +357,14 @@ def run_b200(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.frames, args.objects
     clip_mode = args.mode == "clip" and world > 1
-    if args.model == "etam_ti":
+    if args.model != "hiera_t512":
         from us_video_medsam2_b200.build_etam import build_efficienttam_video_predictor_npz
 
-        pred = build_efficienttam_video_predictor_npz("configs/efficienttam_ti_512x512.yaml", device=dev,
+        v = args.model.split("_")[1]
+        pred = build_efficienttam_video_predictor_npz(f"configs/efficienttam_{v}_512x512.yaml", device=dev,
                                                       encoder_batch=args.encoder_batch,
                                                       encoder_sms=0 if clip_mode else args.encoder_sms)
-        pred.load_state_dict(synth.make_etam_state_dict(ETAM_SEED), strict=True)
+        pred.load_state_dict(synth.make_etam_state_dict(ETAM_SEEDS[args.model], v), strict=True)
     else:
         pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev,
                                               encoder_batch=args.encoder_batch,
@@ -486,7 +490,7 @@ def run_b200(args, rank, world):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if clip_mode else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{'sam2.1_hiera_t512' if args.model == 'hiera_t512' else 'efficienttam_ti_512x512'} "
+            "config": {"workload": f"{MODEL_NAMES[args.model]} "
                                    f"propagate_in_video, {T}-frame synthetic echo clip "
                                    f"{'(one clip for all GPUs)' if clip_mode else 'per GPU'}, "
                                    f"{B} object(s), 7-frame memory bank, mask prompt on frame 0",
