@@ -124,11 +124,9 @@ int usvm_fmha_bf16(const usvm_fmha_params* p_host, void* stream);
 int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, void* out, int F, int Hg, int Wg, int ws, int pool,
                           int C, int heads, void* stream);
 /* tcgen05 / TMEM / TMA flash attention for the memory-attention shapes: head_dim 256, H == 1, Nq % 128 == 0, batches
- * contiguous (x_bs == N * x_rs).  S = QK^T (double buffered) and O accumulate in TMEM, V is consumed in place as an
+ * contiguous (x_bs == N * x_rs).  Q, S = QK^T (double buffered), P and O live in TMEM, V is consumed in place as an
  * MN-major operand.  With num_splits > 1 it writes partials only: follow with usvm_fmha_combine. */
 int usvm_fmha_tc5(const usvm_fmha_params* p_host, void* stream);
-/* 0 (default): Q and P in tensor memory, A-from-TMEM MMAs;  1: Q and P in shared memory (first implementation) */
-int usvm_fmha_tc5_set_variant(int variant);
 int usvm_fmha_combine(const usvm_fmha_params* p_host, void* stream);
 /* fp32, one warp per query; head_dim 16 or 32, Nk <= 1024 (SAM decoder two-way transformer) */
 int usvm_attn_small_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Nq, int Nk,
@@ -167,7 +165,7 @@ int usvm_normalize_gray_u8(const uint8_t* gray, float* out, int F, int H, int W,
                            const float* std3_host, void* stream);
 
 /* memory-bank assembly (sam2_base.py:1344-1437) */
-#define USVM_MAX_MEMORY_FRAMES 16
+#define USVM_MAX_MEMORY_FRAMES 32
 typedef struct usvm_memory_frames {
   const void* mem[USVM_MAX_MEMORY_FRAMES]; /* bf16 [B, T, Cm] token-major spatial memories */
   int tpos_index[USVM_MAX_MEMORY_FRAMES];  /* row of maskmem_tpos_enc to add (num_maskmem - t_pos - 1) */
@@ -182,7 +180,7 @@ int usvm_build_memory(const usvm_memory_frames* frames_host, const float* pos, c
  * session) on the steady-state tracking path -- where the frame store lives, which stored frames feed the memory bank
  * (sam2_base.py:1296-1394) and which slot this frame writes.  Kernels read it through a pointer, so ONE captured CUDA
  * graph serves every frame of every session with the same (objects, #memories, #pointers) signature. */
-#define USVM_MAX_PTRS 32
+#define USVM_MAX_PTRS 48
 typedef struct usvm_frame_ctrl {
   void* mem_store;   /* bf16 [slots][B][T][Cm]   spatial memories            */
   float* ptr_store;  /* fp32 [slots][B][4*Cm]    object pointers             */
@@ -237,6 +235,12 @@ int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* bias, const
 #define USVM_POST_BINARIZE_AFFINE 2 /* (v > 0)*scale + bias     (sam2_base.py:1472-1474) */
 int usvm_resize_bilinear(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo, int post_mode,
                          float post_scale, float post_bias, void* stream);
+/* SAM2Base._apply_non_overlapping_constraints (sam2/modeling/sam2_base.py:1663-1681) on x fp32 [B, HW]: inside each
+ * group of `group` consecutive objects (the objects of one video; group <= 0: all B) only the object with the highest
+ * logit at a pixel keeps it, the others are clamped to <= -10; then the post transform of usvm_resize_bilinear.  Ties
+ * go to the lowest object index (torch.argmax).  May run in place. */
+int usvm_non_overlap_f32(const float* x, float* y, int B, long long HW, int group, int post_mode, float post_scale,
+                         float post_bias, void* stream);
 int usvm_resize_bilinear_aa(const float* x, float* y, long long planes, int Hi, int Wi, int Ho, int Wo,
                             int binarize_half, void* stream);
 
@@ -302,55 +306,6 @@ int usvm_objptr_mix(float* ptr, const float* score, int score_stride, const floa
                     void* stream);
 int usvm_point_embed(const float* coords, const int* labels, const float* gauss, const float* table, float image_size,
                      float* out, int n_points, void* stream);
-
-/* ---- token-side chains of the mask decoder (csrc/token_chain.cu) ------------------------------------------------
- * One thread-block cluster per object runs up to USVM_CHAIN_MAX_STEPS dependent steps on that object's <= 8 rows
- * (decoder tokens, or stacked head instances); steps are separated by cluster barriers instead of kernel launches.
- * Replaces, per tracked frame, the per-layer launches of TwoWayAttentionBlock's token side (sam/transformer.py:137-212),
- * the hyper-network / IoU / object-score heads (mask_decoder.py:215-253) and obj_ptr_proj (sam2_base.py:1143-1156).
- * All strides in elements; *_os = stride between objects. */
-#define USVM_CHAIN_MAX_STEPS 10
-#define USVM_CHAIN_ROWS 8
-#define USVM_CHAIN_LINEAR 0      /* out[m,n] = act((T(x)[m] (+ x2[m] if n < x2_cols)) . w[n] + bias[n]) (+ residual[m,n]) */
-#define USVM_CHAIN_T2I_PARTIAL 1 /* token->image attention partials of this CTA's key range -> params.scratch */
-#define USVM_CHAIN_IN_ROWS 0      /* T = identity, or LayerNorm over K when ln_w != NULL (also stored to ln_out) */
-#define USVM_CHAIN_IN_SELF_ATTN 1 /* T = 8-head self-attention of the rows; q | k | v at columns attn_q/k/v of x (K = 256) */
-#define USVM_CHAIN_IN_T2I_MERGE 2 /* T = softmax merge of the preceding T2I_PARTIAL step (K = 128) */
-typedef struct usvm_chain_step {
-  const float* x;
-  long long x_os, x_rs;
-  const int* row_select; /* optional int32 [n_obj]: x += row_select[obj] * sel_stride (token chosen on the device) */
-  long long sel_stride;
-  const float* ln_w;
-  const float* ln_b;
-  float* ln_out;
-  long long ln_os, ln_rs;
-  const float* x2;
-  long long x2_os, x2_rs;
-  const float* w; /* [N,K] row-major, 16-byte aligned; w_is != 0: row m uses matrix m (stride w_is), bias stride b_is */
-  long long w_is;
-  const float* bias;
-  long long b_is;
-  const float* residual;
-  long long r_os, r_rs;
-  float* out;
-  long long o_os, o_rs;
-  const float* k; /* T2I_PARTIAL: keys / values [Nk, 8 heads x 16] with row pitch kv_rs; queries = x [rows, 128] */
-  const float* v;
-  long long kv_os, kv_rs;
-  int kind, in_kind, rows, N, K, act, x2_cols, Nk, attn_q, attn_k, attn_v;
-  float ln_eps;
-} usvm_chain_step;
-typedef struct usvm_chain_params {
-  float* scratch; /* n_obj * cluster * 8 * 144 floats (T2I partials); may be NULL when no step needs it */
-  unsigned long long* timing; /* optional profiling aid: [n_steps][8] SM-clock stamps (cycles) of object 0 / CTA 0:
-                                 step start, input ready, step done, cluster barrier passed, first weight chunk
-                                 landed, first row block's products done, its k-slices met, unused; NULL = off */
-  int n_steps, n_obj, cluster /* CTAs per object: 8 or 16 */;
-  int precise; /* 1: products as 3 x tf32 on (hi, lo) splits (fp32-level accuracy); 0: one round-to-nearest tf32 product */
-  usvm_chain_step steps[USVM_CHAIN_MAX_STEPS];
-} usvm_chain_params;
-int usvm_token_chain(const usvm_chain_params* p_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -222,10 +222,9 @@ def test_editing_session_matches_reference_fixture(golden_dir):
     for key in ("frames_a", "frames_b", "frames_c", "click_ids", "cond_b", "cond_after_clear", "remove_ids",
                 "remove_updated_frames"):
         assert got[key].tolist() == g[key].tolist(), key
-    # Tolerances: the absolute error is the same bf16 noise floor as on every tracked frame (mean |dlogit| ~ 4.5e-4,
-    # asserted below at 8e-4), but this session's logits have less contrast (std 0.03-0.06 at random init, two objects),
-    # so the same error costs more Dice than in the single-object fixtures: bar 0.99 here instead of 0.995.  The frame
-    # that received the click has steeper logits around the point: max |dlogit| bar 4 x LOGIT_TOL there.
+    # Tolerances: the bars of every tracked frame (Dice >= 0.995, mean |dlogit| <= 8e-4); the frame that received the
+    # click has steeper logits around the point: max |dlogit| bar 4 x LOGIT_TOL there.
+    worst = (1.0, None)
     for key in ("low_a", "low_b", "low_c", "click_video_s4", "clear_video_s4", "remove_video_s4"):
         a, b = torch.from_numpy(got[key]), torch.from_numpy(g[key])
         assert a.shape == b.shape, key
@@ -236,7 +235,9 @@ def test_editing_session_matches_reference_fixture(golden_dir):
             if key.startswith("low"):  # (the video-resolution samples interpolate across filled pixels)
                 assert float(d[same].max()) <= 4 * LOGIT_TOL, (key, i, float(d[same].max()))
             assert float(d[same].mean()) <= 8e-4, (key, i, float(d[same].mean()))
-            assert dice(a[i], b[i]) >= 0.99, (key, i, dice(a[i], b[i]))
+            worst = min(worst, (dice(a[i], b[i]), (key, i)))
+    print(f"editing session: worst Dice {worst[0]:.5f} at {worst[1]}")
+    assert worst[0] >= DICE_BAR, worst
 
 
 def test_autocast_and_half_precision_frames_are_accepted():
@@ -298,6 +299,7 @@ def test_image_predictor_matches_reference_fixture(golden_dir):
         pred.predict(point_coords=np.zeros((1, 2), np.float32), point_labels=np.ones(1, np.int32))  # no image set yet
     got = image_session(pred)
     assert set(got) == set(g.files)
+    worst = (1.0, None)
     for k in g.files:
         a, b = got[k], g[k]
         assert a.shape == b.shape, (k, a.shape, b.shape)
@@ -306,7 +308,8 @@ def test_image_predictor_matches_reference_fixture(golden_dir):
             assert int(np.argmax(a)) == int(np.argmax(b))
         elif k == "d_binary_s2":
             for i in range(a.shape[0]):
-                assert dice(torch.from_numpy(a[i].astype(np.float32)) - 0.5, torch.from_numpy(b[i].astype(np.float32)) - 0.5) >= 0.99
+                dc = dice(torch.from_numpy(a[i].astype(np.float32)) - 0.5, torch.from_numpy(b[i].astype(np.float32)) - 0.5)
+                worst = min(worst, (dc, (k, i)))
         else:
             for i in range(a.shape[0]):
                 x, y = torch.from_numpy(a[i]), torch.from_numpy(b[i])
@@ -315,7 +318,9 @@ def test_image_predictor_matches_reference_fixture(golden_dir):
                     assert float((x - y).abs().max()) <= 4 * LOGIT_TOL, (k, i, float((x - y).abs().max()))
                 # (the full-resolution masks went through hole / sprinkle rewriting to +-10 at a threshold and the resize
                 # blends those spikes into their neighbours: only the binary agreement is comparable there)
-                assert dice(x, y) >= 0.99, (k, i, dice(x, y))
+                worst = min(worst, (dice(x, y), (k, i)))
+    print(f"image predictor: worst Dice {worst[0]:.5f} at {worst[1]}")
+    assert worst[0] >= DICE_BAR, worst
 
 
 def test_interleaved_sessions_on_one_predictor():

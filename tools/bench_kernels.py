@@ -117,55 +117,6 @@ def misc():
     print(f"empty-ish launch (axpby 1 row): {timeit(lambda: ops.axpby(x[:1], None)):8.1f} us")
 
 
-def chain():
-    """Per-step cost of the token-chain cluster kernel: n identical LINEAR steps per launch, steady state (L2-warm)."""
-    x = rnd(8, 2048)
-    for cl in (8, 16):
-        for (N, K) in [(256, 256), (2048, 256), (256, 2048), (1024, 256), (128, 256)]:
-            w, b = rnd(N, K, scale=K ** -0.5), rnd(N)
-            bufs = [rnd(8, max(N, K)) for _ in range(2)]
-            lw, lb = rnd(K), rnd(K)
-            for variant in ("plain", "ln+pe"):
-                if variant == "ln+pe" and K > 768:
-                    continue
-                for n in (1, 5, 9):
-                    steps = []
-                    for i in range(n):
-                        kw = dict(ln=(lw, lb), x2=x[:, :K].contiguous()) if variant == "ln+pe" else {}
-                        steps.append(ops.chain_linear(bufs[i & 1][:, :K], w, b, bufs[(i + 1) & 1][:, :N], x_rs=max(N, K),
-                                                      o_rs=max(N, K), **kw))
-                    us = timeit(lambda: ops.token_chain(steps, 1, x, cluster=cl))
-                    print(f"chain cl={cl:2d} N={N:4d} K={K:4d} {variant:6s} steps={n}: {us:7.1f} us", flush=True)
-    # where a step's time goes (globaltimer stamps of CTA 0, ns relative to the first stamp)
-    for (N, K, variant) in [(128, 256, "plain"), (256, 256, "ln+pe"), (2048, 256, "plain"), (256, 2048, "plain")]:
-        w, b = rnd(N, K, scale=K ** -0.5), rnd(N)
-        bufs = [rnd(8, max(N, K)) for _ in range(2)]
-        lw, lb = rnd(K), rnd(K)
-        kw = dict(ln=(lw, lb), x2=x[:, :K].contiguous()) if variant == "ln+pe" else {}
-        steps = [ops.chain_linear(bufs[i & 1][:, :K], w, b, bufs[(i + 1) & 1][:, :N], x_rs=max(N, K), o_rs=max(N, K), **kw)
-                 for i in range(4)]
-        tm = torch.zeros((6, 8), dtype=torch.int64, device=dev)
-        for _ in range(3):
-            ops.token_chain(steps, 1, x, cluster=8, timing=tm)
-        torch.cuda.synchronize()
-        t = (tm[:4] - tm[:4, :1]).cpu().tolist()  # per step, relative to the step's start
-        names = ("input", "done", "barrier")
-        for row in t[1:3]:
-            print(f"stamps N={N} K={K} {variant}: " + " ".join(f"{n}={row[i + 1]}" for i, n in enumerate(names)), flush=True)
-    from us_video_medsam2_b200 import synth
-    from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
-    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=8)
-    pred.load_state_dict(synth.make_state_dict(19), strict=True)
-    eng = pred.engine()
-    pix = rnd(1024, 256, scale=0.5)
-    s0, s1 = rnd(16384, 32), rnd(4096, 64)
-    for use, precise in ((True, False), (True, True), (False, False)):
-        eng.use_token_chain = use
-        ops._CHAIN_PRECISE = precise
-        us = timeit(lambda: eng.sam_heads(pix, s0, s1, 1, eng.no_point_tokens(1), multimask=True), iters=5)
-        print(f"sam_heads token_chain={use} precise={precise}: {us:7.1f} us", flush=True)
-
-
 def phases():
     """GPU time of the three phases of a tracked frame (graph-captured, L2-warm), one object, full memory bank."""
     from us_video_medsam2_b200 import synth

@@ -49,13 +49,6 @@ if which == "decoder":  # SAM heads of a tracked frame (8 tokens), three times: 
     s0, s1 = rnd(16384, 32, dt=torch.float32), rnd(4096, 64, dt=torch.float32)
     for _ in range(3):
         eng.sam_heads(pix, s0, s1, 1, eng.no_point_tokens(1), multimask=True)
-if which == "chain":  # nine identical small LINEAR steps in one cluster launch (per-step latency study)
-    x = rnd(8, 256, dt=torch.float32)
-    w, b = rnd(128, 256, dt=torch.float32, sc=1 / 16), rnd(128, dt=torch.float32)
-    bufs = [rnd(8, 256, dt=torch.float32) for _ in range(2)]
-    steps = [ops.chain_linear(bufs[i & 1], w, b, bufs[(i + 1) & 1][:, :128], o_rs=256) for i in range(9)]
-    for _ in range(4):
-        ops.token_chain(steps, 1, x, cluster=8)
 if which == "frames":  # a short clip without CUDA graphs: every kernel of a tracked frame shows up in the launch list
     from us_video_medsam2_b200 import synth
     from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libusvm2_b200.so")
 
-MAX_MEMORY_FRAMES = 16
+MAX_MEMORY_FRAMES = 32
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 POST_NONE, POST_SIGMOID_AFFINE, POST_BINARIZE_AFFINE = 0, 1, 2
@@ -36,7 +36,7 @@ class FmhaParams(C.Structure):
                 ("part_bf16", C.c_int)]
 
 
-MAX_PTRS = 32
+MAX_PTRS = 48
 
 
 class SkinnyParams(C.Structure):
@@ -50,29 +50,6 @@ class SkinnyParams(C.Structure):
                 ("x2_cols", C.c_int),
                 ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("ln_out", C.c_void_p), ("ln_is", C.c_longlong),
                 ("ln_rs", C.c_longlong), ("ln_eps", C.c_float)]
-
-
-CHAIN_MAX_STEPS = 10
-
-
-class ChainStep(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("x_os", C.c_longlong), ("x_rs", C.c_longlong),
-                ("row_select", C.c_void_p), ("sel_stride", C.c_longlong),
-                ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("ln_out", C.c_void_p), ("ln_os", C.c_longlong),
-                ("ln_rs", C.c_longlong),
-                ("x2", C.c_void_p), ("x2_os", C.c_longlong), ("x2_rs", C.c_longlong),
-                ("w", C.c_void_p), ("w_is", C.c_longlong), ("bias", C.c_void_p), ("b_is", C.c_longlong),
-                ("residual", C.c_void_p), ("r_os", C.c_longlong), ("r_rs", C.c_longlong),
-                ("out", C.c_void_p), ("o_os", C.c_longlong), ("o_rs", C.c_longlong),
-                ("k", C.c_void_p), ("v", C.c_void_p), ("kv_os", C.c_longlong), ("kv_rs", C.c_longlong),
-                ("kind", C.c_int), ("in_kind", C.c_int), ("rows", C.c_int), ("N", C.c_int), ("K", C.c_int),
-                ("act", C.c_int), ("x2_cols", C.c_int), ("Nk", C.c_int), ("attn_q", C.c_int), ("attn_k", C.c_int),
-                ("attn_v", C.c_int), ("ln_eps", C.c_float)]
-
-
-class ChainParams(C.Structure):
-    _fields_ = [("scratch", C.c_void_p), ("timing", C.c_void_p), ("n_steps", C.c_int), ("n_obj", C.c_int), ("cluster", C.c_int),
-                ("precise", C.c_int), ("steps", ChainStep * CHAIN_MAX_STEPS)]
 
 
 class FrameCtrl(C.Structure):
@@ -104,7 +81,6 @@ _SIGNATURES = {
     "usvm_fmha_bf16": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_tc5": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_combine": [C.POINTER(FmhaParams), _P],
-    "usvm_fmha_tc5_set_variant": [_I],
     "usvm_attn_small_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "usvm_layernorm": [_P, _I, _P, _P, _F, _I, _P, _I, _P, _I, _I, _I, _P],
     "usvm_axpby_rows": [_P, _P, _F, _F, _I, _I, _P, _P, _LL, _I, _P],
@@ -122,6 +98,7 @@ _SIGNATURES = {
     "usvm_im2col_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "usvm_dwconv7_ln": [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
     "usvm_resize_bilinear": [_P, _P, _LL, _I, _I, _I, _I, _I, _F, _F, _P],
+    "usvm_non_overlap_f32": [_P, _P, _I, _LL, _I, _I, _F, _F, _P],
     "usvm_resize_bilinear_aa": [_P, _P, _LL, _I, _I, _I, _I, _I, _P],
     "usvm_upscale1_ln_gelu": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
     "usvm_upscale2_masks": [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P],
@@ -134,7 +111,6 @@ _SIGNATURES = {
     "usvm_small_mlp3": [_P, _LL, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _LL, _LL, _I, _I, _P],
     "usvm_window_attn_bf16": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "usvm_gemm_skinny_f32": [C.POINTER(SkinnyParams), _P],
-    "usvm_token_chain": [C.POINTER(ChainParams), _P],
     "usvm_attn_t2i_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "usvm_attn_t2i_split_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     "usvm_attn_i2t_f32": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
@@ -180,6 +156,21 @@ def lib():
             raise KernelLibraryError("libusvm2_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib
+
+
+_bound_device = None
+
+
+def bind_device(index):
+    """One process drives ONE GPU (the layout of bench.py / sharding.py: one rank per device).  The kernels' opt-in
+    shared-memory sizes (cudaFuncSetAttribute) are configured once per process on first launch, and that attribute is
+    per device -- so a second device in the same process is refused here, loudly, instead of failing at launch."""
+    global _bound_device
+    if _bound_device is None:
+        _bound_device = int(index)
+    elif _bound_device != int(index):
+        raise KernelLibraryError(f"this process already runs the kernel library on cuda:{_bound_device}; use one "
+                                 f"process per GPU (asked for cuda:{int(index)})")
 
 
 def call(name, *args):

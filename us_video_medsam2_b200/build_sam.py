@@ -23,6 +23,10 @@ _REQUIRED_TRUE = ("use_mask_input_as_output_without_sam", "directly_add_no_mem_e
                   "use_mlp_for_obj_ptr_proj")
 
 
+# architecture constants the kernels are specialised for (overriding them would silently be ignored otherwise)
+_FIXED_VALUES = {"image_size": 512, "num_maskmem": 7, "backbone_stride": 16, "max_obj_ptrs_in_encoder": 16}
+
+
 def get_best_available_device():
     """CUDA or nothing: this path has no CPU / MPS implementation (reference: build_sam.py:50-60)."""
     if torch.cuda.is_available():
@@ -48,12 +52,10 @@ def _load_model_kwargs(config_file, overrides):
     path = os.path.join(_CONFIG_DIR, name)
     if not os.path.exists(path):
         raise FileNotFoundError(f"unknown config {config_file!r}: this build ships {os.listdir(_CONFIG_DIR)}")
-    cfg = yaml.safe_load(open(path))["model"]
-    for flag in _REQUIRED_TRUE:
-        if not cfg.get(flag, False):
-            raise NotImplementedError(f"config flag {flag}=false selects a code path outside this build")
-    kwargs = {k: v for k, v in cfg.items() if not isinstance(v, dict) and k not in _REQUIRED_TRUE
-              and k not in ("backbone_stride",)}
+    with open(path) as f:
+        cfg = yaml.safe_load(f)["model"]
+    flat = {k: v for k, v in cfg.items() if not isinstance(v, dict)}
+    # overrides first (Hydra composes them into the config before anything is instantiated, build_sam.py:124-128) ...
     for ov in overrides:
         key, _, val = ov.lstrip("+").partition("=")
         parts = key.split(".")
@@ -62,10 +64,21 @@ def _load_model_kwargs(config_file, overrides):
         if parts[1] == "_target_":
             continue
         if parts[1] == "sam_mask_decoder_extra_args" and len(parts) == 3:
-            kwargs.setdefault("sam_mask_decoder_extra_args", {})[parts[2]] = _parse_value(val)
+            flat.setdefault("sam_mask_decoder_extra_args", {})[parts[2]] = _parse_value(val)
         elif len(parts) == 2:
-            kwargs[parts[1]] = _parse_value(val)
-    return kwargs
+            flat[parts[1]] = _parse_value(val)
+        else:
+            raise NotImplementedError(f"override {ov!r} changes an architecture block; this build implements the "
+                                      f"architecture of {name} as shipped")
+    # ... then validate what the composed config asks for against what this build implements
+    for flag in _REQUIRED_TRUE:
+        if not flat.get(flag, False):
+            raise NotImplementedError(f"config flag {flag}=false selects a code path outside this build")
+    for key, want in _FIXED_VALUES.items():
+        if key in flat and flat[key] != want:
+            raise NotImplementedError(f"{key}={flat[key]!r} is outside this build (the kernels are specialised for "
+                                      f"{key}={want!r}, the value in {name})")
+    return {k: v for k, v in flat.items() if k not in _REQUIRED_TRUE and k not in ("backbone_stride",)}
 
 
 _POSTPROCESSING_OVERRIDES = [
@@ -81,8 +94,8 @@ def _build(cls, config_file, ckpt_path, device, mode, hydra_overrides_extra, app
     device = device or get_best_available_device()
     logging.info(f"Using device: {device}")
     overrides = list(hydra_overrides_extra)
-    if apply_postprocessing:
-        overrides = _POSTPROCESSING_OVERRIDES + overrides
+    if apply_postprocessing:  # appended after the caller's, so they win -- as in the reference (build_sam.py:111-123)
+        overrides = overrides + _POSTPROCESSING_OVERRIDES
     model_kwargs = _load_model_kwargs(config_file, overrides)
     model_kwargs.update(kwargs)
     model = cls(**model_kwargs)
@@ -99,7 +112,7 @@ def build_sam2(config_file, ckpt_path=None, device=None, mode="eval", hydra_over
     state-dict ABI and the kernel engine is the predictor class, so the same object serves `SAM2ImagePredictor(model)`."""
     extra = list(hydra_overrides_extra)
     if apply_postprocessing:  # only the stability fallback here (build_sam.py:76-83), not the video overrides
-        extra = _POSTPROCESSING_OVERRIDES[:3] + extra
+        extra = extra + _POSTPROCESSING_OVERRIDES[:3]
     return _build(SAM2VideoPredictor, config_file, ckpt_path, device, mode, extra, False, **kwargs)
 
 

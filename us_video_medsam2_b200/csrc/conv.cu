@@ -401,6 +401,31 @@ __global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __res
   }
 }
 
+// SAM2Base._apply_non_overlapping_constraints (sam2_base.py:1663-1681): per pixel, only the object with the highest logit
+// of its group keeps it (ties: lowest index, as torch.argmax), the others are clamped to <= -10; then post_op.
+// One thread per (group, pixel): the group's objects are read with stride HW (coalesced across the warp).
+__global__ void non_overlap_kernel(const float* __restrict__ x, float* __restrict__ y, int B, long long HW, int group,
+                                   int mode, float pscale, float pbias) {
+  PDL_ENTRY();
+  const int groups = B / group;
+  const long long total = (long long)groups * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long g = i / HW, p = i - g * HW;
+    const float* xp = x + g * group * HW + p;
+    float best = xp[0];
+    int win = 0;
+    for (int b = 1; b < group; ++b) {
+      const float v = xp[(long long)b * HW];
+      if (v > best) { best = v; win = b; }
+    }
+    float* yp = y + g * group * HW + p;
+    for (int b = 0; b < group; ++b) {
+      const float v = xp[(long long)b * HW];
+      yp[(long long)b * HW] = post_op(b == win ? v : fminf(v, -10.0f), mode, pscale, pbias);
+    }
+  }
+}
+
 // antialiased bilinear (triangle filter widened by the scale), ATen _upsample_bilinear2d_aa semantics
 __device__ __forceinline__ void aa_span(int o, float scale, int in_size, int& lo, int& size, float& center,
                                         float& invscale) {
@@ -518,6 +543,15 @@ extern "C" int usvm_resize_bilinear(const float* x, float* y, long long planes, 
   if (!x || !y || planes <= 0 || Hi <= 0 || Wi <= 0 || Ho <= 0 || Wo <= 0) return USVM_ERR_ARG;
   usvm_launch(resize_bilinear_kernel, dim3(grid_for(planes * Ho * Wo)), dim3(256), 0, STREAM, x, y, planes, Hi, Wi, Ho, Wo, post_mode,
                                                                          post_scale, post_bias);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_non_overlap_f32(const float* x, float* y, int B, long long HW, int group, int post_mode,
+                                    float post_scale, float post_bias, void* stream) {
+  if (group <= 0) group = B;
+  if (!x || !y || B <= 0 || HW <= 0 || B % group) return USVM_ERR_ARG;
+  usvm_launch(non_overlap_kernel, dim3(grid_for((long long)(B / group) * HW)), dim3(256), 0, STREAM, x, y, B, HW, group,
+              post_mode, post_scale, post_bias);
   return usvm_check_launch();
 }
 

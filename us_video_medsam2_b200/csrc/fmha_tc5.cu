@@ -31,7 +31,6 @@ constexpr int KV_BYTES = NCH * KN * 128;    // 32768 per operand per stage
 constexpr int P_BYTES = QM * 128;           // 16384
 constexpr int XCH_BYTES = 4 * QM * 4;  // row max exchange between the two column halves, double buffered
 constexpr int ALIGN_SLACK = 512;  // the dynamic smem base is 1024-aligned in practice; trap if it is not
-constexpr int SMEM_BYTES = Q_BYTES + 2 * 2 * KV_BYTES + 2 * P_BYTES + XCH_BYTES + ALIGN_SLACK + 256;
 
 __device__ __forceinline__ void tc5_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -65,249 +64,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-fmha_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const usvm_fmha_params p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  if (smem - smem_raw > ALIGN_SLACK) __trap();
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Q_BYTES;                 // 2 stages
-  uint8_t* sV = sK + 2 * KV_BYTES;            // 2 stages
-  uint8_t* sP = sV + 2 * KV_BYTES;            // 2 buffers
-  float* s_xch = reinterpret_cast<float*>(sP + 2 * P_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES + XCH_BYTES);
-  uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // 2
-  uint64_t* kv_empty = bars + 3;      // 2
-  uint64_t* s_full = bars + 5;        // 2
-  uint64_t* p_full = bars + 7;        // 2 (128 arrivals each)
-  uint64_t* pv_done = bars + 9;       // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * QM;
-  const int b = blockIdx.y;  // batch (object); one head
-  const int split = blockIdx.z;
-  const int ntiles = (p.Nk + KN - 1) / KN;
-  const int per = (ntiles + p.num_splits - 1) / p.num_splits;
-  const int t_begin = split * per;
-  const int t_end = min(ntiles, t_begin + per);
-  const int n = max(0, t_end - t_begin);
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 256);
-      mbar_init(&pv_done[s], 1);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) tc5_alloc(tmem_slot, 512);
-  tc5_fence_before();
-  __syncthreads();
-  tc5_fence_after();
-  pdl_wait();  // barriers, descriptors and TMEM were set up under the previous kernel's tail
-  pdl_trigger();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_O = tmem + 128;
-
-  if (warp == 0) {
-    if (lane == 0 && n > 0) {
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      for (int c = 0; c < NCH; ++c) tma_load_2d(sQ + c * (QM * 128), &tmQ, q_full, c * 64, b * p.Nq + q0);
-      for (int j = 0; j < n; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES);
-        const int row = b * p.Nk + (t_begin + j) * KN;
-        for (int c = 0; c < NCH; ++c) {
-          tma_load_2d(sK + st * KV_BYTES + c * (KN * 128), &tmK, &kv_full[st], c * 64, row);
-          tma_load_2d(sV + st * KV_BYTES + c * (KN * 128), &tmV, &kv_full[st], c * 64, row);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0 && n > 0) {
-      constexpr uint32_t idesc_s = idesc_bf16(QM, KN, 0);
-      constexpr uint32_t idesc_o = idesc_bf16(QM, HD, 1);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        tc5_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * (QM * 128) + (kk & 3) * 32;
-          const uint32_t koff = (kk >> 2) * (KN * 128) + (kk & 3) * 32;
-          tc5_mma_f16(tmem + st * KN, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + koff), idesc_s,
-                      kk > 0 ? 1u : 0u);
-        }
-        tc5_commit(&s_full[st]);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < n; ++j) {
-        if (j + 1 < n) issue_s(j + 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc5_fence_after();
-        const uint32_t v_addr = smem_u32(sV + (j & 1) * KV_BYTES);
-        const uint32_t pj_addr = p_addr + (j & 1) * P_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < KN / 16; ++kk) {
-          tc5_mma_f16(tmem_O, umma_desc_k_sw128(pj_addr + kk * 32), umma_desc_mn_sw128(v_addr + kk * 2048, KN * 128),
-                      idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-        }
-        tc5_commit(&kv_empty[j & 1]);
-        tc5_commit(&pv_done[j & 1]);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ---- softmax: 8 warps; warps w and w + 4 share the 32 query rows of TMEM lane group (w & 3) and split the 64
-    //      key columns of a tile in halves (two warps per scheduler hide each other's latencies) ----
-    const int lane_grp = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int r = lane_grp * 32 + lane;  // query row inside the tile == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(lane_grp * 32) << 16;
-    const float sl2 = p.scale * 1.4426950408889634f;
-    float m_ref = -INFINITY, l = 0.f;  // m_ref in log2 units (raw score * sl2); l = this half's partial row sum
-    for (int j = 0; j < n; ++j) {
-      const int st = j & 1;
-      mbar_wait(&s_full[st], (j >> 1) & 1);
-      tc5_fence_after();
-      uint32_t sa[32];
-      tc5_ld_32x32(tmem + lane_addr + st * KN + half * 32, sa);
-      tc5_wait_ld();
-      const int key0 = (t_begin + j) * KN + half * 32;
-      float mx = -INFINITY;
-      if (key0 + 32 > p.Nk) {  // ragged last tile only
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (key0 + i >= p.Nk) sa[i] = 0xff800000u;  // -inf
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sa[i]));
-      // row max across the two column halves (partner warp = same lane group, other half)
-      s_xch[(st * 2 + half) * QM + r] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");
-      mx = fmaxf(mx, s_xch[(st * 2 + (half ^ 1)) * QM + r]) * sl2;
-      float corr = 1.f;
-      bool rescale = false;
-      if (j == 0) {
-        m_ref = mx;
-      } else if (mx > m_ref + 8.0f) {  // lazy rescaling: keep the stale max while exp2(s - m_ref) <= 2^8
-        corr = exp2f(m_ref - mx);
-        m_ref = mx;
-        l *= corr;
-        rescale = true;
-      }
-      float sum = 0.f;
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sa[i]), sl2, -m_ref));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sa[i + 1]), sl2, -m_ref));
-        sum += p0 + p1;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-      }
-      l += sum;
-      // P buffer j&1 was last read by O += P_{j-2} V_{j-2}
-      if (j >= 2) mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);
-      if (j > 0 && __any_sync(0xffffffffu, rescale)) {
-        // rare (lazy rescaling): O may only be touched once O += P_{j-1} V_{j-1} has completed; each half owns
-        // 128 of the 256 output columns
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc5_fence_after();
-#pragma unroll 1
-        for (int c = half * 128; c < half * 128 + 128; c += 32) {
-          uint32_t o[32];
-          tc5_ld_32x32(tmem_O + lane_addr + c, o);
-          tc5_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-          tc5_st_32x32(tmem_O + lane_addr + c, o);
-        }
-        tc5_wait_st();
-      }
-      // P row r -> swizzled K-major tile: 16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) * 16)
-      uint8_t* prow = sP + st * P_BYTES + r * 128;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 v4 = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (r & 7)) << 4)) = v4;
-      }
-      fence_proxy_async();
-      tc5_fence_before();
-      mbar_arrive(&p_full[st]);
-    }
-    // ---- epilogue: total row sum = both halves; each half stores 128 of the 256 output columns ----
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");  // partner is done with s_xch
-    s_xch[half * QM + r] = l;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + lane_grp) : "memory");
-    l += s_xch[(half ^ 1) * QM + r];
-    const int row = q0 + r;
-    const int bh = b;  // H == 1
-    if (n > 0) {
-      mbar_wait(&pv_done[(n - 1) & 1], ((n - 1) >> 1) & 1);
-      tc5_fence_after();
-    }
-    const float inv = (p.num_splits == 1 && l > 0.f) ? 1.f / l : 1.f;
-#pragma unroll 1
-    for (int c = half * 128; c < half * 128 + 128; c += 32) {
-      uint32_t o[32];
-      if (n > 0) {
-        tc5_ld_32x32(tmem_O + lane_addr + c, o);
-        tc5_wait_ld();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0u;
-      }
-      if (row >= p.Nq) continue;
-      if (p.num_splits == 1) {
-        bf16* O = reinterpret_cast<bf16*>(p.o) + (long long)b * p.o_bs + (long long)row * p.o_rs + c;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 v4;
-          v4.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
-          v4.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-          v4.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-          v4.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(O + i) = v4;
-        }
-      } else {
-        float* OP = p.o_part + (((long long)split * gridDim.y + bh) * p.Nq + row) * HD + c;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(OP + i) = make_float4(__uint_as_float(o[i]), __uint_as_float(o[i + 1]),
-                                                           __uint_as_float(o[i + 2]), __uint_as_float(o[i + 3]));
-      }
-    }
-    if (p.num_splits > 1 && row < p.Nq && half == 0) {
-      // (m, l) in the convention of fmha_combine_kernel: m in raw score units, weights exp2((m - M) * scale * log2e)
-      float* ML = p.ml_part + (((long long)split * gridDim.y + bh) * p.Nq + row) * 2;
-      ML[0] = n > 0 ? m_ref / sl2 : -INFINITY;
-      ML[1] = l;
-    }
-  }
-  tc5_fence_before();
-  __syncthreads();
-  if (warp == 1) tc5_dealloc(tmem, 512);
-}
-
 // =================================================================================================================
-// TS variant: Q and P live in TENSOR MEMORY and feed the MMAs as the A operand (tcgen05.mma with A in TMEM), so the
-// only shared-memory traffic of a tile is the K / V tile itself (TMA write + one MMA read each).  The SS kernel above
-// re-reads the 64 KB Q tile and round-trips P through shared memory for every 64 keys, which makes it shared-memory
-// bandwidth bound (~224 KB per tile at 128 B/clk); here a tile moves 128 KB.
+// Q and P live in TENSOR MEMORY and feed the MMAs as the A operand (tcgen05.mma with A in TMEM), so the only
+// shared-memory traffic of a tile is the K / V tile itself (TMA write + one MMA read each): 128 KB per tile.  (A first
+// version kept Q and P in shared memory; re-reading the 64 KB Q tile and round-tripping P for every 64 keys made it
+// shared-memory bandwidth bound at ~224 KB per tile.)
 //   TMEM columns: [0,128) Q (bf16 pairs), [128,192) / [192,256) S_j fp32 -- P_j (bf16 pairs) overwrites the first 32
 //   columns of its S buffer once both column halves have read S -- and [256,512) O.
 //   Shared memory: 3-stage K / V ring (192 KB).
@@ -615,12 +376,6 @@ int make_map(CUtensorMap* map, const void* base, long long rows, int cols, long 
 // Same parameter block as usvm_fmha_bf16.  Requirements: head_dim 256, H == 1, Nq % 128 == 0, contiguous batches
 // (q_bs == Nq * q_rs, k_bs == Nk * k_rs, v_bs == Nk * v_rs), 16-byte aligned bases, row strides % 8 == 0.
 // Partials (num_splits > 1) use the o_part / ml_part layout of usvm_fmha_bf16; call usvm_fmha_combine afterwards.
-static int fmha_tc5_variant = 0;  // 0: Q / P in TMEM (TS MMAs), 1: Q / P in shared memory (SS MMAs)
-extern "C" int usvm_fmha_tc5_set_variant(int v) {
-  fmha_tc5_variant = v ? 1 : 0;
-  return USVM_OK;
-}
-
 extern "C" int usvm_fmha_tc5(const usvm_fmha_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->o || p->B <= 0 || p->Nq <= 0 || p->Nk <= 0) return USVM_ERR_ARG;
   if (p->head_dim != HD || p->H != 1 || (p->Nq % QM) || p->num_splits < 1 || p->num_splits > 32) return USVM_ERR_ARG;
@@ -633,26 +388,19 @@ extern "C" int usvm_fmha_tc5(const usvm_fmha_params* p, void* stream) {
     return USVM_ERR_ARG;
   if (p->num_splits > 1 && (!p->o_part || !p->ml_part)) return USVM_ERR_ARG;
   if (p->num_splits > (p->Nk + KN - 1) / KN) return USVM_ERR_ARG;
-  if (p->part_bf16 && fmha_tc5_variant != 0) return USVM_ERR_ARG;  // only the TS kernel writes bf16 partials
-  CUtensorMap tq, tk, tv;
-  int rc = make_map(&tq, p->q, (long long)p->B * p->Nq, HD, p->q_rs, QM);
-  if (rc) return rc;
-  rc = make_map(&tk, p->k, (long long)p->B * p->Nk, HD, p->k_rs, KN);
+  CUtensorMap tk, tv;
+  int rc = make_map(&tk, p->k, (long long)p->B * p->Nk, HD, p->k_rs, KN);
   if (rc) return rc;
   rc = make_map(&tv, p->v, (long long)p->B * p->Nk, HD, p->v_rs, KN);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(fmha_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(fmha_tc5_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES) !=
-            cudaSuccess)
+    if (cudaFuncSetAttribute(fmha_tc5_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES) !=
+        cudaSuccess)
       return USVM_ERR_CUDA;
     attr = true;
   }
   dim3 grid(p->Nq / QM, p->B, p->num_splits);
-  if (fmha_tc5_variant == 0)
-    usvm_launch(fmha_tc5_ts_kernel, dim3(grid), dim3(THREADS), TS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tk, tv, *p);
-  else
-    usvm_launch(fmha_tc5_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tq, tk, tv, *p);
+  usvm_launch(fmha_tc5_ts_kernel, dim3(grid), dim3(THREADS), TS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tk, tv, *p);
   return usvm_check_launch();
 }

@@ -208,7 +208,7 @@ class PackedWeights:
         # obj_ptr_tpos_proj is an Identity without parameters (sam2_base.py:1393-1404)
         self.tpos_proj = ((f32("obj_ptr_tpos_proj.weight"), f32("obj_ptr_tpos_proj.bias"))
                           if cfg.add_tpos_enc_to_obj_ptrs else None)
-        self.zero_ptr_pos = dev(torch.zeros(4 * cfg.max_obj_ptrs_in_encoder * 2, cfg.mem_dim))
+        self.zero_ptr_pos = dev(torch.zeros(4 * ops._lib.MAX_PTRS, cfg.mem_dim))
 
         # ---- prompt encoder ----
         pe_ = "sam_prompt_encoder."
@@ -250,14 +250,6 @@ class PackedWeights:
             Lyr["i2t"]["kv_b"] = torch.cat([Lyr["i2t"]["k"][1], Lyr["i2t"]["v"][1]]).contiguous()
         self.dec_final = attn(tr + "final_attn_token_to_image.")
         self.dec_final_norm = lin(tr + "norm_final_attn.")
-        # token-chain packing: the projections that read the queries leaving a layer share one step -- columns that take
-        # `queries + token_pe` first ([i2t.k | next q | next k]), then the ones that take `queries` ([i2t.v | next v])
-        cat = lambda keys, kind: dev(torch.cat([g(k + kind) for k in keys]))
-        l0, l1, fa = tr + "layers.0.", tr + "layers.1.", tr + "final_attn_token_to_image."
-        b0 = [l0 + "cross_attn_image_to_token.k_proj.", l1 + "self_attn.q_proj.", l1 + "self_attn.k_proj.",
-              l0 + "cross_attn_image_to_token.v_proj.", l1 + "self_attn.v_proj."]
-        b1 = [l1 + "cross_attn_image_to_token.k_proj.", fa + "q_proj.", l1 + "cross_attn_image_to_token.v_proj."]
-        self.dec_boundary = [(cat(b0, "weight"), cat(b0, "bias")), (cat(b1, "weight"), cat(b1, "bias"))]
         # image-side projections of one layer share their input (`keys`): fuse [t2i.k | t2i.v | i2t.q] into one
         # GEMM; the `+ key_pe` of k and q becomes a constant additive table  dense_pe @ W^T  (linearity)
         dpe = self.dense_pe.detach().cpu().double()
@@ -382,7 +374,6 @@ class Engine:
         # branches of the captured frame graph -- the frame is a latency chain of ~125 small kernels, not throughput bound
         self.fork_branches = os.environ.get("USVM2_FORK", "1") != "0"
         self.fused_windows = os.environ.get("USVM2_FUSED_WINDOWS", "1") != "0"
-        self.use_token_chain = os.environ.get("USVM2_TOKEN_CHAIN", "0") == "1"
 
     # ---------------------------------------------------------------- forked branches
     def _side(self, i):
@@ -616,7 +607,9 @@ class Engine:
             ops.store_outputs(ctrl, o["obj_ptr"], o["score"], pm)
             vh, vw = video_hw
             video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
-        mask_in = self.mem_mask_input(o["low"], False)
+        # (non_overlap_masks_for_mem_enc applies on every frame in eval, sam2_base.py:1466-1471: device-side, so the frame
+        # stays one capturable graph)
+        mask_in = self.mem_mask_input(o["low"], False, non_overlap=self.cfg.non_overlap_masks_for_mem_enc)
         self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl, pix_proj=pp)
         self._handoff(main, tail, video, pm)
         return video, pm
@@ -674,28 +667,23 @@ class Engine:
         queries, keys = tokens, src
         ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
         sk = ops.gemm_skinny
-        chain = Nt == 8 and self.use_token_chain
         tok = torch.cuda.current_stream()
-        img_s = self._side(1) if (self.fork_branches and not chain) else None
-        if chain:
-            hs, y, keys = self._two_way_transformer_chain(tokens, keys, B)
-        else:
-            hs_pre, keys = self._two_way_transformer(tokens, keys, B, Nt, img_stream=img_s, const0=const0,
-                                                     defer_final_norm=True)
+        img_s = self._side(1) if self.fork_branches else None
+        hs_pre, keys = self._two_way_transformer(tokens, keys, B, Nt, img_stream=img_s, const0=const0,
+                                                 defer_final_norm=True)
         # output upscaling (image side) || the six token heads (token side); they meet in the mask product
         with torch.cuda.stream(img_s if img_s is not None else tok):
             g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=True)
             u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_shared)
             g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=True)
-        if not chain:
-            # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
-            # norm_final_attn runs on load in the first head layer, which also leaves the normalised token rows 0..5 in hs
-            W1, b1, W2, b2, W3, b3 = w.heads6
-            hs = torch.empty_like(hs_pre)
-            h1 = sk(None, W1, b1, M=B, x_ptr=hs_pre.data_ptr(), x_rs=Nt * 256, x_is=256, act=ACT_RELU, instances=6,
-                    ln=(w.dec_final_norm[0], w.dec_final_norm[1], 1e-5), ln_out=hs, ln_rs=Nt * 256, ln_is=256)
-            h2 = sk(h1, W2, b2, M=B, x_rs=6 * 256, x_is=256, act=ACT_RELU, instances=6)
-            y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
+        # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
+        # norm_final_attn runs on load in the first head layer, which also leaves the normalised token rows 0..5 in hs
+        W1, b1, W2, b2, W3, b3 = w.heads6
+        hs = torch.empty_like(hs_pre)
+        h1 = sk(None, W1, b1, M=B, x_ptr=hs_pre.data_ptr(), x_rs=Nt * 256, x_is=256, act=ACT_RELU, instances=6,
+                ln=(w.dec_final_norm[0], w.dec_final_norm[1], 1e-5), ln_out=hs, ln_rs=Nt * 256, ln_is=256)
+        h2 = sk(h1, W2, b2, M=B, x_rs=6 * 256, x_is=256, act=ACT_RELU, instances=6)
+        y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
         if img_s is not None:
             self._handoff(tok, img_s, g2, keys)
         masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 64, 64, feat_shared, hyper_bs=192)
@@ -707,7 +695,7 @@ class Engine:
                                            score_stride=192, iou_is_logit=True)
         score = y[:, 0:1].contiguous()
         P1, pb1, P2, pb2, P3, pb3 = w.obj_ptr_proj
-        if defer_ptr and not chain:
+        if defer_ptr:
             # the pointer (3-layer MLP on the selected mask token + no-object mix) is not needed by the memory encoder: the
             # caller runs it on its forked tail branch
             def finish_ptr():
@@ -718,19 +706,10 @@ class Engine:
 
             return dict(low=low, obj_ptr=None, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36], idx=idx,
                         finish_ptr=finish_ptr, _keep=(hs, idx))
-        if chain:
-            E = lambda *shape: ops.empty(shape, F32, src)
-            t1, t2, ptr = E(B, 256), E(B, 256), E(B, 256)
-            ops.token_chain([
-                ops.chain_linear(hs, P1[0], pb1[0], t1, rows=1, x_os=Nt * 256, x_off=2 * 256, row_select=idx,
-                                 sel_stride=256, act=ACT_RELU),
-                ops.chain_linear(t1, P2[0], pb2[0], t2, rows=1, act=ACT_RELU),
-                ops.chain_linear(t2, P3[0], pb3[0], ptr, rows=1)], B, src)
-        else:
-            t1 = sk(None, P1[0], pb1[0], M=B, x_ptr=hs.data_ptr() + 4 * 2 * 256, x_rs=Nt * 256, row_select=idx,
-                    x_sel_stride=256, act=ACT_RELU)
-            t2 = sk(t1, P2[0], pb2[0], act=ACT_RELU)
-            ptr = sk(t2, P3[0], pb3[0])
+        t1 = sk(None, P1[0], pb1[0], M=B, x_ptr=hs.data_ptr() + 4 * 2 * 256, x_rs=Nt * 256, row_select=idx,
+                x_sel_stride=256, act=ACT_RELU)
+        t2 = sk(t1, P2[0], pb2[0], act=ACT_RELU)
+        ptr = sk(t2, P3[0], pb3[0])
         ops.objptr_mix_(ptr, score, w.no_obj_ptr)
         return dict(low=low, obj_ptr=ptr, score=score, iou=iou_sel, masks=masks, iou_logits=y[:, 32:36], idx=idx)
 
@@ -797,55 +776,6 @@ class Engine:
             return ln(hs_pre, w.dec_final_norm), keys
         return hs_pre, keys
 
-    def _two_way_transformer_chain(self, tokens, keys, B):
-        """Same math for the 8-token case of tracked frames (6 output tokens + 2 padding points), token side as five
-        cluster kernels (csrc/token_chain.cu): [layer-0 self-attn .. t2i query] -> image GEMM -> [t2i, MLP, i2t k/v,
-        layer-1 self-attn, t2i query] -> image side -> [layer-1 t2i .. final query] -> image side -> [final t2i, norm,
-        six stacked heads].  Returns (hs [B*8,256] rows 0..5 valid, heads output y [B,192], keys)."""
-        w = self.w
-        T, R = 1024, 8
-        L0, L1 = w.dec_layers
-        fin = w.dec_final
-        lin, t2i, run = ops.chain_linear, ops.chain_t2i, ops.token_chain
-        E = lambda *shape: ops.empty(shape, F32, keys)
-        ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
-        qkv0, qa, q1, qt = E(B * R, 768), E(B * R, 256), E(B * R, 256), E(B * R, 128)
-        img0 = ops.gemm_f32(keys, L0["img_w"], L0["img_b"], residual=L0["img_pe"], res_mod=T, tf32=True)  # [B*T, 384]
-        run([lin(tokens, L0["sa"]["qkv_w"], L0["sa"]["qkv_b"], qkv0),
-             lin(qkv0, *L0["sa"]["o"], qa, in_kind=1, attn_cols=(0, 256, 512)),
-             lin(qa, *L0["t2i"]["q"], qt, ln=L0["norms"][0], ln_out=q1, x2=tokens)], B, keys)
-        a, h, b_ = E(B * R, 256), E(B * R, 2048), E(B * R, 256)
-        q2, q3, q4 = E(B * R, 256), E(B * R, 256), E(B * R, 256)
-        c, d, qt1 = E(B * R, 1024), E(B * R, 256), E(B * R, 128)
-        run([t2i(qt, img0[:, 0:128], img0[:, 128:256]),
-             lin(qt, *L0["t2i"]["o"], a, in_kind=2, residual=q1),
-             lin(a, *L0["mlp"][0], h, ln=L0["norms"][1], ln_out=q2, act=ACT_RELU),
-             lin(h, *L0["mlp"][1], b_, residual=q2),
-             lin(b_, *w.dec_boundary[0], c, ln=L0["norms"][2], ln_out=q3, x2=tokens, x2_cols=640),
-             lin(c, *L1["sa"]["o"], d, in_kind=1, attn_cols=(128, 384, 768), residual=q3),
-             lin(d, *L1["t2i"]["q"], qt1, ln=L1["norms"][0], ln_out=q4, x2=tokens)], B, keys)
-        o = ops.attn_i2t(img0[:, 256:384], c[:, 0:128], c[:, 640:768], B, T, R)
-        keys = ln(ops.gemm_f32(o, *L0["i2t"]["o"], residual=keys, tf32=True), L0["norms"][3])
-        img1 = ops.gemm_f32(keys, L1["img_w"], L1["img_b"], residual=L1["img_pe"], res_mod=T, tf32=True)
-        q5, q6, e = E(B * R, 256), E(B * R, 256), E(B * R, 384)
-        run([t2i(qt1, img1[:, 0:128], img1[:, 128:256]),
-             lin(qt1, *L1["t2i"]["o"], a, in_kind=2, residual=q4),
-             lin(a, *L1["mlp"][0], h, ln=L1["norms"][1], ln_out=q5, act=ACT_RELU),
-             lin(h, *L1["mlp"][1], b_, residual=q5),
-             lin(b_, *w.dec_boundary[1], e, ln=L1["norms"][2], ln_out=q6, x2=tokens, x2_cols=256)], B, keys)
-        o = ops.attn_i2t(img1[:, 256:384], e[:, 0:128], e[:, 256:384], B, T, R)
-        keys = ln(ops.gemm_f32(o, *L1["i2t"]["o"], residual=keys, tf32=True), L1["norms"][3])
-        imgf = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T, tf32=True)  # [B*T, 256]
-        W1, b1, W2, b2, W3, b3 = w.heads6
-        hs, h1, h2, y = E(B * R, 256), E(B * 6, 256), E(B * 6, 256), E(B, 192)
-        run([t2i(e, imgf[:, 0:128], imgf[:, 128:256], q_off=128),
-             lin(e, *fin["o"], a, in_kind=2, residual=q6),
-             lin(a, W1, b1, h1, rows=6, x_os=R * 256, ln=w.dec_final_norm, ln_out=hs, ln_os=R * 256, stacked=True,
-                 act=ACT_RELU),
-             lin(h1, W2, b2, h2, rows=6, stacked=True, act=ACT_RELU),
-             lin(h2, W3, b3, y, rows=6, stacked=True, o_os=192, o_rs=32)], B, keys)
-        return hs, y, keys
-
     def embed_points(self, coords, labels):
         """PromptEncoder._embed_points with pad=True (prompt_encoder.py:79-103): coords [B,P,2] model pixels."""
         B = coords.shape[0]
@@ -908,10 +838,15 @@ class Engine:
         out, _ = ops.gemm_bf16(xb, w.mem_out[0], bias=w.mem_out[1], f32=True)
         return ops.finalize_memory(out, score, w.no_obj_embed_spatial, B, ctrl=ctrl)
 
-    def mem_mask_input(self, masks, binarize):
-        """Upsample low-res logits [B,1,h,w] to 512^2 (if needed) fused with sigmoid*20-10 or (x>0)*20-10."""
+    def mem_mask_input(self, masks, binarize, non_overlap=False, group=0):
+        """Upsample low-res logits [B,1,h,w] to 512^2 (if needed) fused with sigmoid*20-10 or (x>0)*20-10.
+        non_overlap: the non-overlapping constraint (sam2_base.py:1466-1471, 1663-1681) is applied to the 512^2 logits
+        first, per group of `group` objects (0 = all: the objects of one video)."""
         cfg = self.cfg
         post = ops.POST_BINARIZE_AFFINE if binarize else ops.POST_SIGMOID_AFFINE
+        if non_overlap and masks.shape[0] > 1:
+            hi = masks if tuple(masks.shape[-2:]) == (512, 512) else ops.resize_bilinear(masks, 512, 512)
+            return ops.non_overlap(hi, group, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)
         return ops.resize_bilinear(masks, 512, 512, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)
 
     def memory_attention_from_tensors(self, feat, mem_frames, tpos_rows, ptrs, ptr_pos, B):

@@ -149,12 +149,10 @@ def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_
     p.num_splits = num_splits
     p.scale = 1.0 / math.sqrt(head_dim)
     which = impl or _FMHA_IMPL
-    if which in ("tc5", "tc5ss"):
-        _lib.lib().usvm_fmha_tc5_set_variant(1 if which == "tc5ss" else 0)
-    use_tc5 = (which in ("tc5", "tc5ss") and head_dim == 256 and H == 1 and Nq % 128 == 0
+    use_tc5 = (which == "tc5" and head_dim == 256 and H == 1 and Nq % 128 == 0
                and q_addr[1] == Nq * q_addr[2] and k_addr[1] == Nk * k_addr[2] and v_addr[1] == Nk * v_addr[2])
     if num_splits > 1:
-        p.part_bf16 = int(use_tc5 and which == "tc5" and _FMHA_PART_BF16)  # split partials in bf16 (TS kernel only)
+        p.part_bf16 = int(use_tc5 and _FMHA_PART_BF16)  # split partials in bf16 (tcgen05 kernel only)
         o_part = empty((num_splits, B * H, Nq, head_dim), BF16 if p.part_bf16 else F32, q)
         ml_part = empty((num_splits, B * H, Nq, 2), F32, q)
         p.o_part, p.ml_part = o_part.data_ptr(), ml_part.data_ptr()
@@ -317,6 +315,16 @@ class FrameStore:
         self.score = torch.zeros((num_frames, B, 1), dtype=F32, device=device)
         self.masks = torch.zeros((num_frames, B, 1, 128, 128), dtype=F32, device=device)
 
+    def grow(self, B):
+        """Append zero-filled columns for objects added later; the existing objects keep their results."""
+        def wider(t):
+            out = torch.zeros((t.shape[0], B) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+            out[:, : self.B].copy_(t)
+            return out
+
+        self.mem, self.ptr, self.score, self.masks = wider(self.mem), wider(self.ptr), wider(self.score), wider(self.masks)
+        self.B = B
+
     def select_objects(self, keep):
         self.mem, self.ptr = self.mem[:, keep].contiguous(), self.ptr[:, keep].contiguous()
         self.score, self.masks = self.score[:, keep].contiguous(), self.masks[:, keep].contiguous()
@@ -341,7 +349,9 @@ def set_frame_ctrl(ctrl_dev, store, obj0, cur_frame, mem_frames, mem_tpos, ptr_f
     c.mem_slot_stride, c.ptr_slot_stride = store.mem.stride(0), store.ptr.stride(0)
     c.score_slot_stride, c.mask_slot_stride = store.score.stride(0), store.masks.stride(0)
     c.cur_frame, c.n_mem, c.n_ptr = cur_frame, len(mem_frames), len(ptr_frames)
-    assert len(mem_frames) <= _lib.MAX_MEMORY_FRAMES and len(ptr_frames) <= _lib.MAX_PTRS
+    if len(mem_frames) > _lib.MAX_MEMORY_FRAMES or len(ptr_frames) > _lib.MAX_PTRS:
+        raise RuntimeError(f"memory bank of {len(mem_frames)} frames / {len(ptr_frames)} object pointers exceeds the frame "
+                           f"control block ({_lib.MAX_MEMORY_FRAMES} / {_lib.MAX_PTRS}): too many conditioning frames")
     for i, (f, t) in enumerate(zip(mem_frames, mem_tpos)):
         c.mem_frame[i], c.mem_tpos[i] = f, t
     for i, (f, r) in enumerate(zip(ptr_frames, ptr_rel)):
@@ -432,6 +442,17 @@ def resize_bilinear(x, Ho, Wo, post=POST_NONE, scale=1.0, bias=0.0):
     return out
 
 
+def non_overlap(x, group=0, post=POST_NONE, scale=1.0, bias=0.0):
+    """_apply_non_overlapping_constraints over the objects (dim 0) of x fp32 [B, ..., H, W], per group of `group`
+    consecutive objects (0: all of them), fused with the post transform of resize_bilinear; returns a new tensor."""
+    _chk(x, F32, "x")
+    x = x.contiguous()
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    call("usvm_non_overlap_f32", x.data_ptr(), out.data_ptr(), B, x.numel() // B, group, post, scale, bias, _stream())
+    return out
+
+
 def resize_bilinear_aa(x, Ho, Wo, binarize_half=False):
     _chk(x, F32, "x")
     x = x.contiguous()
@@ -503,76 +524,6 @@ def gemm_skinny(x, w, bias=None, M=None, x_rs=None, x_is=0, x2=None, x2_rs=None,
         p.ln_is = ln_is
     call("usvm_gemm_skinny_f32", C.byref(p), _stream())
     return out
-
-
-# ------------------------------------------------------------------------------------------------
-# token-side chains of the mask decoder (one cluster kernel per dependency chain)
-# ------------------------------------------------------------------------------------------------
-def chain_linear(x, w, bias, out, rows=8, x_os=None, x_rs=None, x_off=0, ln=None, ln_eps=1e-5, ln_out=None, ln_os=None,
-                 x2=None,
-                 x2_cols=None, act=ACT_NONE, residual=None, stacked=False, o_os=None, o_rs=None, row_select=None,
-                 sel_stride=0, in_kind=0, attn_cols=(0, 0, 0)):
-    """One LINEAR step of a token chain (see include/usvm2_b200.h: usvm_chain_step).  x / x2 / residual / out / ln_out
-    are [n_obj * rows, width]-shaped fp32 tensors unless explicit strides are given; `stacked`: w is [rows, N, K] and
-    row m uses matrix m; in_kind 1 = self-attention over q|k|v columns `attn_cols` of x, 2 = merge of T2I partials."""
-    st = _lib.ChainStep()
-    N, K = w.shape[-2], w.shape[-1]
-    st.kind, st.in_kind, st.rows, st.N, st.K, st.act = 0, in_kind, rows, N, K, act
-    st.x = x.data_ptr() + 4 * x_off
-    st.x_rs = x_rs if x_rs is not None else x.stride(0)
-    st.x_os = x_os if x_os is not None else rows * st.x_rs
-    if row_select is not None:
-        st.row_select, st.sel_stride = row_select.data_ptr(), sel_stride
-    if ln is not None:
-        st.ln_w, st.ln_b, st.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln_eps
-        if ln_out is not None:
-            st.ln_out, st.ln_rs = ln_out.data_ptr(), ln_out.stride(0)
-            st.ln_os = ln_os if ln_os is not None else rows * ln_out.stride(0)
-    if x2 is not None:
-        st.x2, st.x2_rs, st.x2_os = x2.data_ptr(), x2.stride(0), rows * x2.stride(0)
-        st.x2_cols = N if x2_cols is None else x2_cols
-    st.w, st.w_is = w.data_ptr(), (N * K if stacked else 0)
-    st.bias, st.b_is = _ptr(bias), (N if stacked else 0)
-    if residual is not None:
-        st.residual, st.r_rs, st.r_os = residual.data_ptr(), residual.stride(0), rows * residual.stride(0)
-    st.out = out.data_ptr()
-    st.o_rs = o_rs if o_rs is not None else out.stride(0)
-    st.o_os = o_os if o_os is not None else rows * st.o_rs
-    st.attn_q, st.attn_k, st.attn_v = attn_cols
-    return st
-
-
-def chain_t2i(q, k, v, rows=8, Nk=1024, q_off=0):
-    """T2I_PARTIAL step: q [n_obj*rows, >=128] (8 heads x 16, starting at column q_off); k, v column views [n_obj*Nk, 128]
-    of one image-side buffer."""
-    st = _lib.ChainStep()
-    st.kind, st.rows, st.Nk = 1, rows, Nk
-    st.x, st.x_rs, st.x_os = q.data_ptr() + 4 * q_off, q.stride(0), rows * q.stride(0)
-    assert k.stride(0) == v.stride(0)
-    st.k, st.v, st.kv_rs, st.kv_os = k.data_ptr(), v.data_ptr(), k.stride(0), Nk * k.stride(0)
-    return st
-
-
-_CHAIN_CLUSTER = int(os.environ.get("USVM2_CHAIN_CLUSTER", "16"))
-_CHAIN_PRECISE = os.environ.get("USVM2_CHAIN_PRECISE", "0") == "1"
-
-
-def token_chain(steps, n_obj, like, cluster=None, timing=None, precise=None):
-    """Runs the steps back to back in one cluster kernel (usvm_token_chain).  timing: optional int64 [n_steps, 8] device
-    tensor that receives %globaltimer stamps of CTA 0 (profiling aid)."""
-    cl = cluster or _CHAIN_CLUSTER
-    p = _lib.ChainParams()
-    p.n_steps, p.n_obj, p.cluster = len(steps), n_obj, cl
-    p.precise = int(_CHAIN_PRECISE if precise is None else precise)
-    p.timing = _ptr(timing)
-    scratch = None
-    if any(st.kind == 1 for st in steps):
-        scratch = empty((n_obj * cl * 8 * 144,), F32, like)
-        p.scratch = scratch.data_ptr()
-    for i, st in enumerate(steps):
-        p.steps[i] = st
-    call("usvm_token_chain", C.byref(p), _stream())
-    return scratch
 
 
 _T2I_COUNTERS = {}

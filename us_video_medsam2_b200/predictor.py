@@ -118,6 +118,7 @@ class SAM2VideoPredictor(nn.Module):
         if self.device.type != "cuda":
             raise RuntimeError("us_video_medsam2_b200 has no CPU path: move the predictor to a CUDA device "
                                "(the kernels target sm_100a)")
+        _lib.bind_device(self.device.index if self.device.index is not None else torch.cuda.current_device())
         key = self._weights_key()
         if self._engine is None or key != self._engine_key:
             sd = {k: v for k, v in self.state_dict().items()}
@@ -198,6 +199,10 @@ class SAM2VideoPredictor(nn.Module):
         st["temp_output_dict_per_obj"][idx] = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
         return idx
 
+    def _tracked_info(self, st, obj_idx, frame_idx):
+        """{"reverse": bool} if the frame was already tracked (for this object), else None (reference :238-247)."""
+        return st["frames_already_tracked"].get(frame_idx)
+
     def _obj_idx_to_id(self, st, obj_idx):
         return st["obj_idx_to_id"][obj_idx]
 
@@ -209,10 +214,38 @@ class SAM2VideoPredictor(nn.Module):
         """Device store of per-frame results (memory, pointer, score, masks), indexed by frame number."""
         B = self._get_obj_num(st)
         store = st.get("_store")
-        if store is None or store.B != B or store.num_frames != st["num_frames"]:
+        if store is not None and store.num_frames == st["num_frames"] and 0 < store.B < B and st["tracking_has_started"]:
+            # objects added after tracking started (the EfficientTAM predictor allows it): keep the existing objects'
+            # results, re-point every stored entry at the grown store
+            store.grow(B)
+            self._refresh_views(st)
+        elif store is None or store.B != B or store.num_frames != st["num_frames"]:
             store = ops.FrameStore(st["num_frames"], B, self.device)
             st["_store"] = store
         return store
+
+    def _refresh_views(self, st):
+        """Rebuild every stored output entry as views of the (re-laid-out) frame store."""
+        for storage_key in ("cond_frame_outputs", "non_cond_frame_outputs"):
+            for frame_idx, old in list(st["output_dict"][storage_key].items()):
+                st["output_dict"][storage_key][frame_idx] = self._slot_views(st, frame_idx,
+                                                                             old["maskmem_features"] is not None)
+            for obj_idx, od in st["output_dict_per_obj"].items():
+                for frame_idx, old in list(od[storage_key].items()):
+                    od[storage_key][frame_idx] = self._obj_slot_views(st, frame_idx, obj_idx,
+                                                                      old["maskmem_features"] is not None)
+
+    def _obj_slot_views(self, st, t, obj_idx, with_memory=True):
+        """One object's entry of frame t as views into the frame store (`output_dict_per_obj`, reference :747-774)."""
+        store = st["_store"]
+        s = slice(obj_idx, obj_idx + 1)
+        out = {"maskmem_features": None, "maskmem_pos_enc": None, "_mem_tok": None, "_slot": t,
+               "pred_masks": store.masks[t][s], "obj_ptr": store.ptr[t][s], "object_score_logits": store.score[t][s]}
+        if with_memory:
+            out["_mem_tok"] = store.mem[t][s]
+            out["maskmem_features"] = self._mem_view(store.mem[t][s])
+            out["maskmem_pos_enc"] = self._maskmem_pos_enc(st, 1)
+        return out
 
     def _slot_views(self, st, t, with_memory=True):
         """The `inference_state` entry of frame t as views into the frame store (reference keys :971-977)."""
@@ -377,8 +410,7 @@ class SAM2VideoPredictor(nn.Module):
         """Set up the look-ahead encoder for the frames `order` still has to track (None: nothing to overlap)."""
         from .pipeline import BatchPlan, FeaturePipeline, PartitionProducer, RemoteProducer
 
-        cfi = st["consolidated_frame_inds"]
-        done = cfi["cond_frame_outputs"] | cfi["non_cond_frame_outputs"]
+        done = self._frames_without_tracking(st)
         tracked = [t for t in order if t not in done]
         if not tracked:
             return None
@@ -457,8 +489,9 @@ class SAM2VideoPredictor(nn.Module):
         st["point_inputs_per_obj"][obj_idx][frame_idx] = point_inputs
         st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
 
-        is_init_cond_frame = frame_idx not in st["frames_already_tracked"]
-        reverse = False if is_init_cond_frame else st["frames_already_tracked"][frame_idx]["reverse"]
+        tracked = self._tracked_info(st, obj_idx, frame_idx)
+        is_init_cond_frame = tracked is None
+        reverse = False if is_init_cond_frame else tracked["reverse"]
         obj_output_dict = st["output_dict_per_obj"][obj_idx]
         obj_temp_output_dict = st["temp_output_dict_per_obj"][obj_idx]
         is_cond = is_init_cond_frame or self.add_all_frames_to_correct_as_cond
@@ -499,8 +532,9 @@ class SAM2VideoPredictor(nn.Module):
             m = ops.resize_bilinear_aa(m, self.image_size, self.image_size, binarize_half=True)
         st["mask_inputs_per_obj"][obj_idx][frame_idx] = m
         st["point_inputs_per_obj"][obj_idx].pop(frame_idx, None)
-        is_init_cond_frame = frame_idx not in st["frames_already_tracked"]
-        reverse = False if is_init_cond_frame else st["frames_already_tracked"][frame_idx]["reverse"]
+        tracked = self._tracked_info(st, obj_idx, frame_idx)
+        is_init_cond_frame = tracked is None
+        reverse = False if is_init_cond_frame else tracked["reverse"]
         obj_output_dict = st["output_dict_per_obj"][obj_idx]
         obj_temp_output_dict = st["temp_output_dict_per_obj"][obj_idx]
         is_cond = is_init_cond_frame or self.add_all_frames_to_correct_as_cond
@@ -530,12 +564,10 @@ class SAM2VideoPredictor(nn.Module):
     @staticmethod
     def _apply_non_overlapping_constraints(pred_masks):
         """Keep only the highest-scoring object per pixel (sam2_base.py:1663-1681).  Optional post-step, off in
-        the shipped config; plain tensor ops (not on the per-frame hot path)."""
+        the shipped config (usvm_non_overlap_f32)."""
         if pred_masks.size(0) == 1:
             return pred_masks
-        winner = torch.argmax(pred_masks, dim=0, keepdim=True)
-        keep = winner == torch.arange(pred_masks.size(0), device=pred_masks.device)[:, None, None, None]
-        return torch.where(keep, pred_masks, torch.clamp(pred_masks, max=-10.0))
+        return ops.non_overlap(pred_masks)
 
     def _mem_view(self, mem_tok):
         """token-major bf16 [B,1024,64] -> the reference's [B,64,32,32] layout (a view)."""
@@ -588,10 +620,7 @@ class SAM2VideoPredictor(nn.Module):
             out["obj_ptr"][obj_idx:obj_idx + 1] = o["obj_ptr"]
             out["object_score_logits"][obj_idx:obj_idx + 1] = o["object_score_logits"]
         if run_mem_encoder:
-            masks = out["pred_masks"]
-            if self.non_overlap_masks_for_mem_enc:
-                masks = self._apply_non_overlapping_constraints(ops.resize_bilinear(masks, 512, 512))
-            mem_tok = self._run_memory_encoder(st, frame_idx, B, masks, out["object_score_logits"], True)
+            mem_tok = self._run_memory_encoder(st, frame_idx, B, out["pred_masks"], out["object_score_logits"], True)
             out["_mem_tok"] = mem_tok
             out["maskmem_features"] = self._mem_view(mem_tok)
             out["maskmem_pos_enc"] = self._maskmem_pos_enc(st, B)
@@ -639,6 +668,17 @@ class SAM2VideoPredictor(nn.Module):
         for frame_idx in cfi["cond_frame_outputs"]:
             assert frame_idx in output_dict["cond_frame_outputs"]
             cfi["non_cond_frame_outputs"].discard(frame_idx)
+        # the device control block of a tracked frame names every selected memory frame and object pointer
+        # (include/usvm2_b200.h: usvm_frame_ctrl); the reference has no such bound (sam2_base.py:1296-1394)
+        n_cond = len(output_dict["cond_frame_outputs"])
+        if self.cfg.max_cond_frames_in_attn != -1:
+            n_cond = min(n_cond, self.cfg.max_cond_frames_in_attn)
+        if (n_cond + self.num_maskmem - 1 > _lib.MAX_MEMORY_FRAMES
+                or n_cond + self.cfg.max_obj_ptrs_in_encoder - 1 > _lib.MAX_PTRS):
+            lim = min(_lib.MAX_MEMORY_FRAMES - (self.num_maskmem - 1), _lib.MAX_PTRS - (self.cfg.max_obj_ptrs_in_encoder - 1))
+            raise RuntimeError(f"{n_cond} conditioning (prompted) frames take part in the memory attention, this build's "
+                               f"frame control block holds at most {lim}; set max_cond_frames_in_attn <= {lim} "
+                               "(++model.max_cond_frames_in_attn) to keep the closest ones like the reference does")
         all_consolidated = cfi["cond_frame_outputs"] | cfi["non_cond_frame_outputs"]
         input_frames = set()
         for d in st["point_inputs_per_obj"].values():
@@ -658,11 +698,12 @@ class SAM2VideoPredictor(nn.Module):
         obj_ids = st["obj_ids"]
         num_frames = st["num_frames"]
         B = self._get_obj_num(st)
-        if len(output_dict["cond_frame_outputs"]) == 0:
+        cond_frames = self._cond_frames(st)
+        if len(cond_frames) == 0:
             raise RuntimeError("No points are provided; please add points first")
         clear_non_cond_mem = self.clear_non_cond_mem_around_input and (self.clear_non_cond_mem_for_multi_obj or B <= 1)
         if start_frame_idx is None:
-            start_frame_idx = min(output_dict["cond_frame_outputs"])
+            start_frame_idx = min(cond_frames)
         if max_frame_num_to_track is None:
             max_frame_num_to_track = num_frames
         if reverse:
@@ -680,6 +721,15 @@ class SAM2VideoPredictor(nn.Module):
                 pipe.close()
             if self._pipeline_owner is st:
                 self._pipeline_owner = None
+
+    def _cond_frames(self, st):
+        """Frames that hold a conditioning output (the default start of a pass is the earliest one, reference :684-686)."""
+        return set(st["output_dict"]["cond_frame_outputs"])
+
+    def _frames_without_tracking(self, st):
+        """Frames a pass will not run the tracking step on (their consolidated outputs exist already)."""
+        cfi = st["consolidated_frame_inds"]
+        return cfi["cond_frame_outputs"] | cfi["non_cond_frame_outputs"]
 
     def _propagate_loop(self, st, order, reverse, clear_non_cond_mem, B):
         output_dict = st["output_dict"]
@@ -776,9 +826,11 @@ class SAM2VideoPredictor(nn.Module):
                 ptr_rel.append(t_diff / denom)
         return mem_slots, tpos_rows, ptr_slots, ptr_rel
 
-    def _track_frame(self, st, frame_idx, B, reverse, output_dict):
+    def _track_frame(self, st, frame_idx, B, reverse, output_dict, obj0=None):
         """One tracked (unprompted) frame of all B objects: results go straight into the frame store; the steady
-        state is replayed from a CUDA graph (one graph per (B, #memories, #pointers, video size) signature)."""
+        state is replayed from a CUDA graph (one graph per (B, #memories, #pointers, video size) signature).
+        obj0: track ONE object (B == 1) of a multi-object session against its own `output_dict` -- the control block
+        addresses that object's column of the store."""
         eng = self.engine()
         store = st["_store"]
         look = -1 if reverse else 1
@@ -793,19 +845,21 @@ class SAM2VideoPredictor(nn.Module):
             # a signature that recurs is worth a graph: the steady state (full bank) is captured at its second frame, the
             # ramp-up signatures of a clip (bank filling up) when a second clip / pass reaches them
             if seen >= 2:
-                ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
+                ops.set_frame_ctrl(self._ctrl, store, obj0 or 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
                 ent = self._capture_graph(key, f)
         if ent is not None:
             graph, static_f, video, n_kernels = ent
             # one launch refreshes the control block and copies this frame's features into the graph's static inputs
-            ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel,
+            ops.set_frame_ctrl(self._ctrl, store, obj0 or 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel,
                                copies=[(f[k], v) for k, v in static_f.items()])
             graph.replay()
             _lib.launch_count += n_kernels  # kernels of this library replayed by the graph
             video = video.clone()
         else:
-            ops.set_frame_ctrl(self._ctrl, store, 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
+            ops.set_frame_ctrl(self._ctrl, store, obj0 or 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
             video, _ = eng.track_frame(f, self._ctrl, B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
+        if obj0 is not None:
+            return self._obj_slot_views(st, frame_idx, obj0), video
         return self._slot_views(st, frame_idx), video
 
     def _capture_graph(self, key, f, stream=None):
@@ -865,11 +919,9 @@ class SAM2VideoPredictor(nn.Module):
         if run_mem_encoder and cfg.num_maskmem > 0:
             binarize = cfg.binarize_mask_from_pts_for_mem_enc and (point_inputs is not None)
             src = o.get("high", None)
-            if src is None or self.non_overlap_masks_for_mem_enc:
+            if src is None:
                 src = low
-                if self.non_overlap_masks_for_mem_enc:
-                    src = self._apply_non_overlapping_constraints(ops.resize_bilinear(low, 512, 512))
-            mask_in = eng.mem_mask_input(src, binarize)
+            mask_in = eng.mem_mask_input(src, binarize, non_overlap=self.non_overlap_masks_for_mem_enc)
             mem_tok = eng.encode_memory(f["feat_bf16"], mask_in, o["score"], B)
         pred_masks = low
         if self.fill_hole_area > 0:
@@ -885,7 +937,7 @@ class SAM2VideoPredictor(nn.Module):
         eng = self.engine()
         f = self._get_image_feature(st, frame_idx)
         binarize = self.cfg.binarize_mask_from_pts_for_mem_enc and is_mask_from_pts
-        mask_in = eng.mem_mask_input(masks, binarize)
+        mask_in = eng.mem_mask_input(masks, binarize, non_overlap=self.non_overlap_masks_for_mem_enc)
         return eng.encode_memory(f["feat_bf16"], mask_in, object_score_logits, batch_size)
 
     # ------------------------------------------------------------------ editing surface
@@ -994,13 +1046,11 @@ class SAM2VideoPredictor(nn.Module):
 
         for key in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj"):
             remap(st[key])
+        if "frames_tracked_per_obj" in st:  # EfficientTAM's per-object bookkeeping
+            remap(st["frames_tracked_per_obj"])
         if st.get("_store") is not None:
             st["_store"].select_objects(remain)
-        for storage_key in ("cond_frame_outputs", "non_cond_frame_outputs"):
-            for frame_idx in list(st["output_dict"][storage_key]):
-                out = self._slot_views(st, frame_idx)
-                st["output_dict"][storage_key][frame_idx] = out
-                self._add_output_per_object(st, frame_idx, out, storage_key)
+            self._refresh_views(st)
         if need_output:
             temp = st["temp_output_dict_per_obj"]
             for frame_idx in input_frames:
@@ -1040,10 +1090,16 @@ class _PerObjectTracked(dict):
 
 
 class EfficientTAMVideoPredictor(SAM2VideoPredictor):
-    """efficient_track_anything/efficienttam_video_predictor.py: the same session API over the EfficientTAM-ti model
-    (ViT-tiny trunk + ViTDetNeck; no high-resolution decoder features, no pointer temporal encoding, no
-    no_obj_embed_spatial).  The reference runs the objects of a session one at a time (:592-628); they are independent on
-    this path, so the batched frame of the base class yields the same masks per object."""
+    """efficient_track_anything/efficienttam_video_predictor.py: the same session API over the EfficientTAM model (ViT
+    trunk + ViTDetNeck; no high-resolution decoder features, no pointer temporal encoding, no no_obj_embed_spatial).
+
+    The reference keeps ALL state per object (conditioning frames, tracked frames) and runs the objects of a session one
+    at a time (:489-628).  Objects are independent on this path, so while every object is prompted on the same frames the
+    batched frame of the base class computes exactly the per-object results and is used.  As soon as the objects' prompt
+    frames differ (or an object is added after tracking started, or a prompt is cleared) the session switches -- for
+    good, until reset_state -- to the reference's per-object schedule: each object is tracked alone (one-object frame
+    graph addressed at its column of the frame store) against its own conditioning / non-conditioning outputs, so an
+    object without input on a frame another object is prompted on is tracked normally there."""
     _config_base = EtamTiConfig
     _abi = staticmethod(synth.etam_state_dict_abi)
 
@@ -1053,13 +1109,131 @@ class EfficientTAMVideoPredictor(SAM2VideoPredictor):
         return st
 
     def _obj_id_to_idx(self, st, obj_id):
-        idx = super()._obj_id_to_idx(st, obj_id)
+        """New objects are always allowed, also after tracking started (reference :127-159)."""
+        idx = st["obj_id_to_idx"].get(obj_id, None)
+        if idx is None and st["tracking_has_started"]:
+            started, st["tracking_has_started"] = True, False
+            try:
+                idx = super()._obj_id_to_idx(st, obj_id)
+            finally:
+                st["tracking_has_started"] = started
+            st["_per_object"] = True
+        elif idx is None:
+            idx = super()._obj_id_to_idx(st, obj_id)
         st["frames_tracked_per_obj"][idx]  # noqa: B018  (creates the object's entry)
         return idx
+
+    def _tracked_info(self, st, obj_idx, frame_idx):
+        return st["frames_tracked_per_obj"][obj_idx].get(frame_idx)  # per object (reference :238-247)
 
     def _reset_tracking_results(self, st):
         super()._reset_tracking_results(st)
         st["frames_tracked_per_obj"].clear()
+        st.pop("_per_object", None)
+
+    # ------------------------------------------------------------------ per-object schedule
+    def _per_object_mode(self, st):
+        if not st.get("_per_object"):
+            inputs = [set(st["point_inputs_per_obj"][i]) | set(st["mask_inputs_per_obj"][i])
+                      for i in range(self._get_obj_num(st))]
+            if any(s != inputs[0] for s in inputs[1:]):
+                st["_per_object"] = True
+        return bool(st.get("_per_object"))
+
+    def _cond_frames(self, st):
+        if not st.get("_per_object"):
+            return super()._cond_frames(st)
+        return {t for od in st["output_dict_per_obj"].values() for t in od["cond_frame_outputs"]}
+
+    def _frames_without_tracking(self, st):
+        if not st.get("_per_object"):
+            return super()._frames_without_tracking(st)
+        ods = list(st["output_dict_per_obj"].values())
+        return set.intersection(*[set(od["cond_frame_outputs"]) for od in ods]) if ods else set()
+
+    def _clear_obj_non_cond_mem_around_input(self, st, frame_idx, obj_idx):
+        r = self.memory_temporal_stride_for_eval
+        non_cond = st["output_dict_per_obj"][obj_idx]["non_cond_frame_outputs"]
+        for t in range(frame_idx - r * self.num_maskmem, frame_idx + r * self.num_maskmem + 1):
+            non_cond.pop(t, None)
+
+    @torch.inference_mode()
+    def propagate_in_video_preflight(self, inference_state):
+        """Per-object consolidation of the temporary outputs (reference :489-552)."""
+        st = inference_state
+        if not self._per_object_mode(st):
+            return super().propagate_in_video_preflight(st)
+        self._sync_engine()
+        B = self._get_obj_num(st)
+        if B == 0:
+            raise RuntimeError("No input points or masks are provided for any object; please add inputs first.")
+        st["tracking_has_started"] = True
+        store = self._ensure_store(st)
+        for i in range(B):
+            od, tmp = st["output_dict_per_obj"][i], st["temp_output_dict_per_obj"][i]
+            for storage_key in ("non_cond_frame_outputs", "cond_frame_outputs"):
+                for t, out in list(tmp[storage_key].items()):
+                    mem_tok = out.get("_mem_tok")
+                    if mem_tok is None:
+                        mem_tok = self._run_memory_encoder(st, t, 1, out["pred_masks"], out["object_score_logits"], True)
+                    store.mem[t, i].copy_(mem_tok[0])
+                    store.ptr[t, i].copy_(out["obj_ptr"][0])
+                    store.score[t, i].copy_(out["object_score_logits"][0])
+                    store.masks[t, i].copy_(out["pred_masks"][0])
+                    od[storage_key][t] = self._obj_slot_views(st, t, i)
+                    if self.clear_non_cond_mem_around_input:
+                        self._clear_obj_non_cond_mem_around_input(st, t, i)
+                tmp[storage_key].clear()
+            if len(od["cond_frame_outputs"]) == 0:
+                raise RuntimeError(f"No input points or masks are provided for object id {self._obj_idx_to_id(st, i)}; "
+                                   "please add inputs first.")
+            for t in od["cond_frame_outputs"]:
+                od["non_cond_frame_outputs"].pop(t, None)
+
+    def _propagate_loop(self, st, order, reverse, clear_non_cond_mem, B):
+        if not st.get("_per_object"):
+            yield from super()._propagate_loop(st, order, reverse, clear_non_cond_mem, B)
+            return
+        store, obj_ids = st["_store"], st["obj_ids"]
+        for frame_idx in _progress(order, "propagate in video"):
+            for i in range(B):  # one object at a time against its own outputs (reference :592-628)
+                od = st["output_dict_per_obj"][i]
+                if frame_idx in od["cond_frame_outputs"]:
+                    if self.clear_non_cond_mem_around_input:
+                        self._clear_obj_non_cond_mem_around_input(st, frame_idx, i)
+                else:
+                    out, _ = self._track_frame(st, frame_idx, 1, reverse, od, obj0=i)
+                    od["non_cond_frame_outputs"][frame_idx] = out
+                st["frames_tracked_per_obj"][i][frame_idx] = {"reverse": reverse}
+            st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
+            _, video_res_masks = self._get_orig_video_res_output(st, store.masks[frame_idx])
+            yield frame_idx, obj_ids, video_res_masks
+
+    @torch.inference_mode()
+    def clear_all_prompts_in_frame(self, inference_state, frame_idx, obj_id, need_output=True):
+        """Per-object removal of a frame's prompts (reference :642-682): the object's conditioning output on that frame is
+        downgraded to a non-conditioning one; nothing is reset.  The prompt sets may differ afterwards, so the session
+        continues on the per-object schedule."""
+        st = inference_state
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        st["_per_object"] = True
+        st["point_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        temp = st["temp_output_dict_per_obj"]
+        temp[obj_idx]["cond_frame_outputs"].pop(frame_idx, None)
+        temp[obj_idx]["non_cond_frame_outputs"].pop(frame_idx, None)
+        od = st["output_dict_per_obj"][obj_idx]
+        out = od["cond_frame_outputs"].pop(frame_idx, None)
+        if out is not None:
+            od["non_cond_frame_outputs"][frame_idx] = out
+            st["frames_tracked_per_obj"][obj_idx].pop(frame_idx, None)
+        if not need_output:
+            return
+        is_cond = any(frame_idx in t["cond_frame_outputs"] for t in temp.values())
+        consolidated = self._consolidate_temp_output_across_obj(st, frame_idx, is_cond, run_mem_encoder=False,
+                                                                consolidate_at_video_res=True)
+        _, video_res_masks = self._get_orig_video_res_output(st, consolidated["pred_masks_video_res"])
+        return frame_idx, st["obj_ids"], video_res_masks
 
 
 class EfficientTAMVideoPredictorNPZ(EfficientTAMVideoPredictor):
