@@ -60,8 +60,16 @@ def parse():
     ap.add_argument("--model", default="hiera_t512", choices=["hiera_t512", "etam_ti", "etam_s"],
                     help="hiera_t512 = MedSAM2 sam2.1_hiera_t512 (BASELINE configs[1], the default); etam_ti / etam_s = "
                          "EfficientTAM tiny / small at 512x512 (BASELINE configs[3]) on the same clips")
-    ap.add_argument("--cpu-sample-frames", type=int, default=24)
+    ap.add_argument("--cpu-sample-frames", type=int, default=64,
+                    help="frames of the clip the CPU arm tracks per step (the 7-frame bank is full from frame 7 on)")
+    ap.add_argument("--batched-videos", type=int, default=8,
+                    help="BASELINE configs[2] leg: independent videos per GPU tracked in lock-step as one batched frame "
+                         "graph (0 = skip the leg)")
+    ap.add_argument("--batched-objects", type=int, default=4)
+    ap.add_argument("--batched-frames", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clip-leg", action="store_true",
+                    help="N > 1, videos mode: skip the extra single-clip (strong scaling) measurement")
     return ap.parse_args()
 
 
@@ -344,6 +352,151 @@ def time_other_kernels(dev, B):
     return out
 
 
+GF_ENCODER, GF_PER_OBJECT = 62.9, 52.0  # GFLOP per frame (shared by objects) / per object-frame
+# HBM-bound pieces, algorithmic bytes per object-frame: memory encoder = 1.0 MB mask in (fp32 512^2) + 0.5 MB
+# pix_feat (bf16) + 2.8 MB weights + 0.13 MB memory out; hole filling = 64 KiB logits in + 64 KiB out
+BYTES_MEM_ENCODER = 1.048576e6 + 0.524288e6 + 2.8e6 + 0.131072e6
+BYTES_FILL_HOLES = 2 * 128 * 128 * 4
+
+
+def _event_time(fn, iters, flush=None):
+    """mean ms of fn() over `iters` launches, CUDA events on the launching (current) stream, optional L2 flush before each."""
+    fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        tot += s.elapsed_time(e)
+    return tot / iters
+
+
+def time_components(pred, dev, B, peaks, iters=10):
+    """What north_star asks besides the headline: tensor-pipe utilisation of the batched image encoder and achieved HBM GB/s
+    of the memory encoder and the hole-filling post-process, each timed with CUDA events at its in-run shape (the encoder
+    as the 16-frame captured graph the clip replays; the other two as the launches of one tracked frame), L2 flushed
+    before every repetition."""
+    from us_video_medsam2_b200 import ops
+
+    eng = pred.engine()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out = {}
+    n = pred.encoder_batch
+    if pred.use_cuda_graphs and n > 1:
+        graph, static_in, _, n_kernels = pred._encoder_graph(n)
+        static_in.normal_()
+        ms = _event_time(graph.replay, iters, flush)
+        tf = GF_ENCODER * n / ms / 1e3
+        out["image_encoder"] = {"bound": "tensor", "frames_per_launch_group": n, "kernels": n_kernels, "avg_ms": ms,
+                                "ms_per_frame": ms / n, "achieved": tf, "peak": peaks["bf16_sustained"],
+                                "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"],
+                                "flops": f"{GF_ENCODER} GFLOP per frame (SURVEY 8d)"}
+    g = torch.Generator(device=dev).manual_seed(5)
+    low = torch.randn((B, 1, 128, 128), generator=g, device=dev) * 0.07
+    score = torch.ones((B, 1), device=dev)
+    fb = torch.randn((1024, 256), generator=g, device=dev).to(torch.bfloat16)
+
+    def mem_enc():
+        eng.encode_memory(fb, eng.mem_mask_input(low, False), score, B)
+
+    for _ in range(2):
+        mem_enc()
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        mem_enc()
+    ms = _event_time(gr.replay, iters, flush)
+    gbs = BYTES_MEM_ENCODER * B / ms / 1e6
+    out["memory_encoder"] = {"bound": "hbm", "objects": B, "avg_us": ms * 1e3, "achieved": gbs, "peak": peaks["hbm"],
+                             "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                             "bytes": f"{BYTES_MEM_ENCODER / 1e6:.2f} MB per object-frame (SURVEY 8d); 15 dependent "
+                                      "launches on 16 KiB - 1 MiB operands: latency, not bandwidth, bounds it at this size"}
+    ms = _event_time(lambda: ops.fill_holes(low, 8), iters, flush)
+    gbs = BYTES_FILL_HOLES * B / ms / 1e6
+    out["fill_holes"] = {"bound": "hbm", "objects": B, "avg_us": ms * 1e3, "achieved": gbs, "peak": peaks["hbm"],
+                         "unit": "GB/s", "frac": gbs / peaks["hbm"], "bytes": "64 KiB in + 64 KiB out per object-frame"}
+    return out
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed `ncu --set full`
+    raw page (profiles/r2_roofline_kernel_ncu_raw.csv), or None when the capture is absent."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r2_roofline_kernel_ncu_raw.csv")
+    if not os.path.exists(path):
+        return None, None
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = next(r for r in rows if "Kernel Name" in r)
+        units = rows[rows.index(hdr) + 1]
+        name_i = hdr.index("Kernel Name")
+        rd_i, wr_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[rd_i].replace(",", "")) * scale.get(units[rd_i], 1.0)
+                + float(r[wr_i].replace(",", "")) * scale.get(units[wr_i], 1.0)
+                for r in rows[rows.index(hdr) + 2:] if len(r) > max(rd_i, wr_i) and kernel_substr in r[name_i]]
+        return (sum(vals) / len(vals), os.path.relpath(path, ROOT)) if vals else (None, None)
+    except Exception:
+        return None, None
+
+
+def run_batched_leg(pred, args, dev, rank, world, peaks):
+    """BASELINE configs[2] on this GPU's share: `--batched-videos` independent videos x `--batched-objects` objects each,
+    `--batched-frames` frames, tracked in lock-step by propagate_in_videos (one batched frame graph, no per-frame host
+    sync).  Device-timed (CUDA events, barrier + synchronize on both sides, max over ranks), clips resident in HBM."""
+    import torch.distributed as dist
+
+    from us_video_medsam2_b200 import ops, synth
+
+    S, Bo, T = args.batched_videos, args.batched_objects, args.batched_frames
+    clips = [ops.normalize_gray_u8(synth.make_clip_u8(T, seed=4321 + rank * S + i).to(dev), synth.IMG_MEAN, synth.IMG_STD)
+             for i in range(S)]
+    masks = [synth.box_mask()] if Bo == 1 else synth.multi_object_masks(Bo)
+
+    def one_pass():
+        states = []
+        for c in clips:
+            st = pred.init_state(c, 512, 512)
+            for j, m in enumerate(masks):
+                pred.add_new_mask(st, 0, j + 1, m)
+            states.append(st)
+        return sum(1 for _ in pred.propagate_in_videos(states))
+
+    for _ in range(2):  # the batched graphs are captured at their second sighting
+        one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    passes, steps = 2, 0
+    e0.record()
+    for _ in range(passes):
+        steps += one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    sec = float(ms) / 1e3
+    steps_s = steps / sec                      # lock-step frames per second on one GPU
+    video_fps = steps_s * S * world            # propagated video-frames/s, whole job
+    objf = video_fps * Bo
+    tflops = (GF_ENCODER * S + GF_PER_OBJECT * S * Bo) * steps_s / 1e3  # per GPU
+    return {"workload": f"{S * world} independent {T}-frame videos x {Bo} objects ({S} videos per GPU in lock-step as one "
+                        f"batched frame graph of {S * Bo} objects; BASELINE configs[2] shape, no inter-GPU communication)",
+            "videos_per_gpu": S, "objects_per_video": Bo, "frames": T, "n_gpus": world,
+            "value": video_fps, "unit": "frames/s", "object_frames_per_s": objf, "ms_per_lockstep_frame": 1e3 / steps_s,
+            "whole_path_tflops_per_gpu": tflops, "whole_path_frac": tflops / peaks["bf16_sustained"],
+            "timing": "device (CUDA events), clips resident in HBM, 2 warm-up + 2 timed passes, max over ranks"}
+
+
 def run_b200(args, rank, world):
     import torch.distributed as dist
 
@@ -356,106 +509,129 @@ def run_b200(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.frames, args.objects
-    clip_mode = args.mode == "clip" and world > 1
-    if args.model != "hiera_t512":
-        from us_video_medsam2_b200.build_etam import build_efficienttam_video_predictor_npz
 
-        v = args.model.split("_")[1]
-        pred = build_efficienttam_video_predictor_npz(f"configs/efficienttam_{v}_512x512.yaml", device=dev,
-                                                      encoder_batch=args.encoder_batch,
-                                                      encoder_sms=0 if clip_mode else args.encoder_sms)
-        pred.load_state_dict(synth.make_etam_state_dict(ETAM_SEEDS[args.model], v), strict=True)
-    else:
-        pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev,
-                                              encoder_batch=args.encoder_batch,
-                                              encoder_sms=0 if clip_mode else args.encoder_sms)
-        pred.load_state_dict(synth.make_state_dict(SEED), strict=True)
-    masks = [synth.box_mask()] if B == 1 else synth.multi_object_masks(B)
-    # 'clip' mode: every rank holds the SAME clip (rank 0 tracks it, the others encode their share of its frames)
-    gray_host = synth.make_clip_u8(T, seed=1234 + (0 if clip_mode else rank)).pin_memory()  # [T,512,512] uint8, pinned
-    if clip_mode and rank == 0:
-        from us_video_medsam2_b200.pipeline import RemoteEncoders
+    def measure(clip_mode, steps, warmup):
+        """Build a predictor for the mode, run the resident and the end-to-end timed regions; returns a dict."""
+        if args.model != "hiera_t512":
+            from us_video_medsam2_b200.build_etam import build_efficienttam_video_predictor_npz
 
-        pred.attach_remote_encoders(RemoteEncoders(list(range(1, world)), dev))
-    out_host = torch.empty((T, B, 512, 512), dtype=torch.bool).pin_memory()  # binary masks, 1 byte per pixel
-    clip_dev = ops.normalize_gray_u8(gray_host.to(dev), synth.IMG_MEAN, synth.IMG_STD)  # resident copy for `value`
+            v = args.model.split("_")[1]
+            pred = build_efficienttam_video_predictor_npz(f"configs/efficienttam_{v}_512x512.yaml", device=dev,
+                                                          encoder_batch=args.encoder_batch,
+                                                          encoder_sms=0 if clip_mode else args.encoder_sms)
+            pred.load_state_dict(synth.make_etam_state_dict(ETAM_SEEDS[args.model], v), strict=True)
+        else:
+            pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev,
+                                                  encoder_batch=args.encoder_batch,
+                                                  encoder_sms=0 if clip_mode else args.encoder_sms)
+            pred.load_state_dict(synth.make_state_dict(SEED), strict=True)
+        masks = [synth.box_mask()] if B == 1 else synth.multi_object_masks(B)
+        # 'clip' mode: every rank holds the SAME clip (rank 0 tracks it, the others encode their share of its frames)
+        gray_host = synth.make_clip_u8(T, seed=1234 + (0 if clip_mode else rank)).pin_memory()  # [T,512,512] uint8, pinned
+        if clip_mode and rank == 0:
+            from us_video_medsam2_b200.pipeline import RemoteEncoders
 
-    def one_pass(images, sink=None):
-        st = pred.init_state(images, 512, 512)
-        for i, m in enumerate(masks):
-            pred.add_new_mask(st, 0, i + 1, m)
-        n = 0
-        for t, ids, logits in pred.propagate_in_video(st):
-            if sink is not None:
-                sink[t].copy_(logits[:, 0] > 0, non_blocking=True)
-            n += 1
-        return n
+            pred.attach_remote_encoders(RemoteEncoders(list(range(1, world)), dev))
+        out_host = torch.empty((T, B, 512, 512), dtype=torch.bool).pin_memory()  # binary masks, 1 byte per pixel
+        clip_dev = ops.normalize_gray_u8(gray_host.to(dev), synth.IMG_MEAN, synth.IMG_STD)  # resident copy for `value`
 
-    def step_resident():
-        if clip_mode and rank > 0:  # encoder rank: serve the one plan rank 0 announces for this pass
-            pred.serve_encoder(clip_dev, rank - 1, world - 1, dst=0, max_plans=1)
-            return 0
-        return one_pass(clip_dev)
+        def one_pass(images, sink=None):
+            st = pred.init_state(images, 512, 512)
+            for i, m in enumerate(masks):
+                pred.add_new_mask(st, 0, i + 1, m)
+            n = 0
+            for t, ids, logits in pred.propagate_in_video(st):
+                if sink is not None:
+                    sink[t].copy_(logits[:, 0] > 0, non_blocking=True)
+                n += 1
+            return n
 
-    def step_e2e():
-        g = gray_host.to(dev, non_blocking=True)
-        imgs = ops.normalize_gray_u8(g, synth.IMG_MEAN, synth.IMG_STD)
-        if clip_mode and rank > 0:
-            pred.serve_encoder(imgs, rank - 1, world - 1, dst=0, max_plans=1)
-            return 0
-        return one_pass(imgs, out_host)
+        def step_resident():
+            if clip_mode and rank > 0:  # encoder rank: serve the one plan rank 0 announces for this pass
+                pred.serve_encoder(clip_dev, rank - 1, world - 1, dst=0, max_plans=1)
+                return 0
+            return one_pass(clip_dev)
 
-    def timed(fn, steps, warmup):
-        sampler = ClockSampler(local)
-        if rank == 0 and not os.environ.get("USVM2_NO_SAMPLER"):
-            sampler.start()
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler.mark_begin()
-        l0 = _lib.launch_count
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        frames = 0
-        marks = []
-        allocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
-        for i in range(steps):
-            t_host = time.perf_counter()
-            frames += fn()
+        def step_e2e():
+            g = gray_host.to(dev, non_blocking=True)
+            imgs = ops.normalize_gray_u8(g, synth.IMG_MEAN, synth.IMG_STD)
+            if clip_mode and rank > 0:
+                pred.serve_encoder(imgs, rank - 1, world - 1, dst=0, max_plans=1)
+                return 0
+            return one_pass(imgs, out_host)
+
+        def timed(fn, steps, warmup):
+            sampler = ClockSampler(local)
+            if rank == 0 and not os.environ.get("USVM2_NO_SAMPLER"):
+                sampler.start()
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sampler.mark_begin()
+            l0 = _lib.launch_count
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            frames = 0
+            marks = []
+            allocs0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
+            for i in range(steps):
+                t_host = time.perf_counter()
+                frames += fn()
+                if os.environ.get("USVM2_BENCH_DEBUG"):
+                    m = torch.cuda.Event(enable_timing=True)
+                    m.record()
+                    marks.append((m, 1e3 * (time.perf_counter() - t_host)))
+            e1.record()
+            torch.cuda.synchronize()
             if os.environ.get("USVM2_BENCH_DEBUG"):
-                m = torch.cuda.Event(enable_timing=True)
-                m.record()
-                marks.append((m, 1e3 * (time.perf_counter() - t_host)))
-        e1.record()
-        torch.cuda.synchronize()
-        if os.environ.get("USVM2_BENCH_DEBUG"):
-            print(f"[bench debug] {fn.__name__}: cudaMalloc calls inside the timed region: "
-                  f"{torch.cuda.memory_stats().get('num_device_alloc', 0) - allocs0}", file=sys.stderr, flush=True)
-        prev = e0
-        for i, (m, host_ms) in enumerate(marks):
-            print(f"[bench debug] {fn.__name__} step {i}: host loop {host_ms:.1f} ms, device {prev.elapsed_time(m):.1f} ms",
-                  file=sys.stderr, flush=True)
-            prev = m
-        sampler.mark_end()
-        launches = _lib.launch_count - l0
-        clocks = sampler.stop() if rank == 0 else None
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        fr = torch.tensor([float(frames)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(fr, op=dist.ReduceOp.SUM)
-        return float(ms), float(fr), launches, clocks
+                print(f"[bench debug] {fn.__name__}: cudaMalloc calls inside the timed region: "
+                      f"{torch.cuda.memory_stats().get('num_device_alloc', 0) - allocs0}", file=sys.stderr, flush=True)
+            prev = e0
+            for i, (m, host_ms) in enumerate(marks):
+                print(f"[bench debug] {fn.__name__} step {i}: host loop {host_ms:.1f} ms, device {prev.elapsed_time(m):.1f} ms",
+                      file=sys.stderr, flush=True)
+                prev = m
+            sampler.mark_end()
+            launches = _lib.launch_count - l0
+            clocks = sampler.stop() if rank == 0 else None
+            if world > 1:
+                dist.barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            fr = torch.tensor([float(frames)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+            return float(ms), float(fr), launches, clocks
 
-    with torch.inference_mode():
-        ms, frames, launches, clocks = timed(step_resident, args.steps, args.warmup)
-        ms_e2e, frames_e2e, _, _ = timed(step_e2e, max(1, args.steps), max(1, min(args.warmup, 2)))
-    value = frames / (ms / 1000.0)
-    e2e = frames_e2e / (ms_e2e / 1000.0)
+        with torch.inference_mode():
+            ms, frames, launches, clocks = timed(step_resident, steps, warmup)
+            ms_e2e, frames_e2e, _, _ = timed(step_e2e, max(1, steps), max(1, min(warmup, 2)))
+        # (encoder ranks serve exactly one plan per step -- max_plans=1 -- so no shutdown header is owed to them)
+        return dict(pred=pred, ms=ms, value=frames / (ms / 1000.0), e2e=frames_e2e / (ms_e2e / 1000.0),
+                    launches=launches, clocks=clocks)
+
+    clip_mode = args.mode == "clip" and world > 1
+    res = measure(clip_mode, args.steps, args.warmup)
+    pred, ms, value, e2e, launches, clocks = (res[k] for k in ("pred", "ms", "value", "e2e", "launches", "clocks"))
+    # Strong scaling of ONE clip (BASELINE configs[1], second half) in the same invocation: after the independent-videos
+    # measurement the same ranks track a single clip -- rank 0 propagates, the others run the frame-parallel encoder and
+    # send features point-to-point over NCCL.  speedup_vs_1gpu compares with one GPU's own clip rate measured above.
+    clip_leg = None
+    if world > 1 and not clip_mode and args.model == "hiera_t512" and not args.no_clip_leg:
+        cres = measure(True, max(2, args.steps // 4), 2)
+        clip_leg = {"workload": f"one {T}-frame clip, {B} object(s): propagation on rank 0, frame-parallel image encoder on "
+                                f"{world - 1} rank(s), features point-to-point over NCCL (4 MiB per frame)",
+                    "scaling": "strong", "n_gpus": world, "value": cres["value"], "unit": "frames/s",
+                    "e2e": cres["e2e"], "ms_per_step": cres["ms"] / max(2, args.steps // 4),
+                    "speedup_vs_1gpu": cres["value"] / (value / world),
+                    "amdahl_bound": "(encoder + tracked frame) / tracked frame: the propagation is sequential in t",
+                    "encoder_batch": args.encoder_batch}
+        del cres
+        torch.cuda.empty_cache()
+
 
     peaks = measured_peaks()
     ks = time_dominant_kernel(dev, B) if rank == 0 else None
@@ -464,10 +640,7 @@ def run_b200(args, rank, world):
         ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_sustained"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of fmha_tc5_ts_kernel at this shape from the
-                    # `ncu --set full` capture summarised in profiles/r1_fmha_tc5_ts_ncu_full.md (B = 1, 18 splits):
-                    # 7.96 MB read (K/V once + Q) + 2 KB written -- the split partials stay in L2 for the combine
-                    "traffic": 7.966e6 if B == 1 else None,
+                    "traffic": None,  # filled from the committed ncu capture below
                     "kernel": "fmha_tc5_ts_kernel + fmha_combine_kernel<256> (memory-attention cross-attention, "
                               f"1024 x 7232 keys, d=256, {ks['splits']}-way split-KV)",
                     "launches_timed": ks["launches"], "avg_us": ks["avg_ms"] * 1e3,
@@ -476,7 +649,20 @@ def run_b200(args, rank, world):
                            "the producers alone, L2 flushed before every replay: operands as warm as in the frame, which "
                            "itself replays from a CUDA graph); avg_us_cold_l2 = the pair alone after an L2 flush"}
     if roofline is not None:
+        traffic, src = ncu_traffic("fmha_tc5_ts_kernel")
+        roofline["traffic"] = traffic if B == 1 else None
+        roofline["traffic_source"] = src
         roofline["other_kernels"] = time_other_kernels(dev, B)
+        # whole path by SURVEY 8(d)'s formula: (62.9 + 52.0 * B) GFLOP per frame x the measured frames/s of one GPU
+        wp = (GF_ENCODER + GF_PER_OBJECT * B) * (value / world) / 1e3
+        roofline["whole_path"] = {"achieved": wp, "unit": "TFLOP/s", "frac": wp / peaks["bf16_sustained"],
+                                  "formula": f"({GF_ENCODER} + {GF_PER_OBJECT} x {B}) GFLOP per frame x frames/s per GPU"}
+        with torch.inference_mode():
+            roofline["components"] = time_components(pred, dev, B, peaks)
+    batched = None
+    if args.batched_videos > 0 and not clip_mode and args.model == "hiera_t512":
+        with torch.inference_mode():
+            batched = run_batched_leg(pred, args, dev, rank, world, peaks)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = max(4, min(T, args.cpu_sample_frames))
@@ -504,10 +690,9 @@ def run_b200(args, rank, world):
                        "l2": f"inputs larger than L2: {T * 3 * 512 * 512 * 4 / 1e6:.0f} MB clip streamed once per step"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": T * 512 * 512,
                     "d2h_bytes_per_step": T * B * 512 * 512},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "batched": batched,
+            "clip_mode": clip_leg,
         }))
-    if clip_mode and rank == 0:
-        pred._remote.shutdown()  # (encoder ranks are not inside a service loop any more: harmless broadcast)
     if world > 1:
         dist.destroy_process_group()
 

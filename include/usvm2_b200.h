@@ -76,6 +76,9 @@ typedef struct usvm_gemm_epilogue {
   const float* ln_b;
   float ln_eps;
   int ln_gelu;
+  /* grouped residual rows (several videos batched into one launch: the objects of video g share that video's residual
+   * block): when res_div > 0 the residual row is (row / res_div) * res_mod + row % res_mod */
+  int res_div;
 } usvm_gemm_epilogue;
 
 /* bf16 operands, fp32 accumulation in TMEM: TMA (128B swizzle) -> tcgen05.mma -> tcgen05.ld epilogue.
@@ -138,9 +141,10 @@ int usvm_attn_small_f32(const float* q, const float* k, const float* v, float* o
 /* nn.LayerNorm over C (hieradet.py:101,124; memory_attention.py:42-44; transformer.py:162-177) */
 int usvm_layernorm(const float* x, int ldx, const float* w, const float* b, float eps, int gelu, float* out_f32,
                    int ldo_f32, void* out_bf16, int ldo_bf16, int rows, int C, void* stream);
-/* out = alpha*x[row % x_mod] + beta*y[row % y_mod] (mod 0: same rows); pos-enc adds (memory_attention.py:134-135) */
-int usvm_axpby_rows(const float* x, const float* y, float alpha, float beta, int x_mod, int y_mod, float* out_f32,
-                    void* out_bf16, long long rows, int C, void* stream);
+/* out = alpha*x[row % x_mod] + beta*y[row % y_mod] (mod 0: same rows); pos-enc adds (memory_attention.py:134-135).
+ * x_div > 0: x row = (row / x_div) * x_mod + row % x_mod -- the objects of one video share that video's feature rows */
+int usvm_axpby_rows(const float* x, const float* y, float alpha, float beta, int x_mod, int y_mod, int x_div,
+                    float* out_f32, void* out_bf16, long long rows, int C, void* stream);
 int usvm_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
 /* apply_rotary_enc (position_encoding.py:194-221): rows inside each batch of rows_per_batch with index < n_rope are
  * rotated with table row (index % table_rows); cos/sin tables [table_rows, dim/2]; output bf16 */
@@ -247,11 +251,12 @@ int usvm_resize_bilinear_aa(const float* x, float* y, long long planes, int Hi, 
 /* ------------------------------------------------------------------------------------------------
  * SAM mask decoder tail (fp32)
  * ---------------------------------------------------------------------------------------------- */
-/* feat_shared != 0: feat_s1 / feat_s0 hold ONE frame that every object of the batch shares */
+/* feat_group > 0: feat_s1 / feat_s0 hold one frame per group of feat_group consecutive objects (the objects of a video
+ * share its frame; feat_group >= B: one frame for the whole batch); 0: one frame per object */
 int usvm_upscale1_ln_gelu(const float* g1, const float* feat_s1, const float* ln_w, const float* ln_b, float eps,
-                          float* out, int B, int Hc, int Wc, int C, int feat_shared, void* stream);
+                          float* out, int B, int Hc, int Wc, int C, int feat_group, void* stream);
 int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, int hyper_bs, float* masks, int B,
-                        int Hc, int Wc, int feat_shared, void* stream);
+                        int Hc, int Wc, int feat_group, void* stream);
 int usvm_small_mlp3(const float* x, long long x_row_stride, long long x_inst_stride, const int* row_select,
                     const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                     const float* b3, int out_dim, int sigmoid_out, float* y, long long y_row_stride,

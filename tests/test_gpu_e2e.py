@@ -224,7 +224,7 @@ def test_editing_session_matches_reference_fixture(golden_dir):
         assert got[key].tolist() == g[key].tolist(), key
     # Tolerances: the bars of every tracked frame (Dice >= 0.995, mean |dlogit| <= 8e-4); the frame that received the
     # click has steeper logits around the point: max |dlogit| bar 4 x LOGIT_TOL there.
-    worst = (1.0, None)
+    worst = (1.0, ("none", -1))
     for key in ("low_a", "low_b", "low_c", "click_video_s4", "clear_video_s4", "remove_video_s4"):
         a, b = torch.from_numpy(got[key]), torch.from_numpy(g[key])
         assert a.shape == b.shape, key
@@ -299,7 +299,7 @@ def test_image_predictor_matches_reference_fixture(golden_dir):
         pred.predict(point_coords=np.zeros((1, 2), np.float32), point_labels=np.ones(1, np.int32))  # no image set yet
     got = image_session(pred)
     assert set(got) == set(g.files)
-    worst = (1.0, None)
+    worst = (1.0, ("none", -1))
     for k in g.files:
         a, b = got[k], g[k]
         assert a.shape == b.shape, (k, a.shape, b.shape)

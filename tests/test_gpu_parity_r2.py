@@ -195,3 +195,56 @@ def test_etam_object_added_after_tracking_started():
     want = {t: lg.clone() for t, _, lg in pred.propagate_in_video(solo)}
     for t in range(T):
         assert dice(both[t][1][1].cpu(), want[t][0].cpu()) >= DICE_BAR, t
+
+
+def test_lockstep_sessions_match_their_solo_runs():
+    """propagate_in_videos: S sessions x Bo objects as ONE batched frame graph (per-video features indexed by
+    object // Bo, one shared frame store).  Every session must reproduce its own solo propagate_in_video run at the parity
+    bars (different batch size -> different attention kernel / split factors, so not bitwise), and its inference_state
+    must be left as a normal, independently usable session."""
+    T, S = 20, 3
+    clips = [synth.make_clip(T, kind="speckle", seed=1234 + i).cuda() for i in range(S)]
+    masks = synth.multi_object_masks(4)
+    prompts = [(masks[0], masks[1]), (masks[2], masks[3]), (masks[1], masks[2])]
+    pred = _predictor(19, encoder_batch=6)
+
+    def new_state(i):
+        st = pred.init_state(clips[i], 512, 512)
+        for j, m in enumerate(prompts[i]):
+            pred.add_new_mask(st, 0, 10 * i + j, m)
+        return st
+
+    solo = []
+    for i in range(S):
+        solo.append([lg.clone() for _, _, lg in pred.propagate_in_video(new_state(i))])
+    states = [new_state(i) for i in range(S)]
+    seen = []
+    for t, ids, lgs in pred.propagate_in_videos(states):
+        assert ids == [[10 * i, 10 * i + 1] for i in range(S)] and len(lgs) == S
+        seen.append(t)
+        for i in range(S):
+            a, b = lgs[i].float().cpu(), solo[i][t].float().cpu()
+            assert a.shape == b.shape == (2, 1, 512, 512)
+            for o in range(2):
+                if t == 0:
+                    assert torch.equal(a[o], b[o])
+                else:
+                    assert dice(a[o], b[o]) >= DICE_BAR, (t, i, o, dice(a[o], b[o]))
+    assert seen == list(range(T))
+    assert any(k[0] == 2 * S and k[-1] == 2 for k in pred._graphs if isinstance(k[0], int))  # the batched graph was captured
+    # each state is an ordinary session afterwards: stored entries are views of the shared store with reference shapes
+    out = states[1]["output_dict"]["non_cond_frame_outputs"][T - 1]
+    assert out["maskmem_features"].shape == (2, 64, 32, 32) and out["obj_ptr"].shape == (2, 256)
+    assert states[1]["output_dict_per_obj"][1]["non_cond_frame_outputs"][5]["pred_masks"].shape == (1, 1, 128, 128)
+    # ... a reverse lock-step pass over the same sessions, from fresh prompts on the last frame
+    for st in states:
+        pred.reset_state(st)
+    for i, st in enumerate(states):
+        pred.add_new_mask(st, T - 1, 7, prompts[i][0])
+    rev = [t for t, _, _ in pred.propagate_in_videos(states, reverse=True, max_frame_num_to_track=6)]
+    assert rev == list(range(T - 1, T - 8, -1))
+    # ... and sessions that do not line up are refused
+    other = pred.init_state(clips[0][:10], 512, 512)
+    pred.add_new_mask(other, 0, 1, masks[0])
+    with pytest.raises(ValueError, match="lock-step"):
+        next(pred.propagate_in_videos([new_state(0), other]))

@@ -23,7 +23,8 @@ class GemmEpilogue(C.Structure):
                 ("out_bf16", C.c_void_p), ("ldo_bf16", C.c_int),
                 ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_cols", C.c_int),
                 ("rope_rows_per_batch", C.c_int), ("rope_n_rope", C.c_int), ("rope_table_rows", C.c_int),
-                ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("ln_eps", C.c_float), ("ln_gelu", C.c_int)]
+                ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("ln_eps", C.c_float), ("ln_gelu", C.c_int),
+                ("res_div", C.c_int)]
 
 
 class FmhaParams(C.Structure):
@@ -83,7 +84,7 @@ _SIGNATURES = {
     "usvm_fmha_combine": [C.POINTER(FmhaParams), _P],
     "usvm_attn_small_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "usvm_layernorm": [_P, _I, _P, _P, _F, _I, _P, _I, _P, _I, _I, _I, _P],
-    "usvm_axpby_rows": [_P, _P, _F, _F, _I, _I, _P, _P, _LL, _I, _P],
+    "usvm_axpby_rows": [_P, _P, _F, _F, _I, _I, _I, _P, _P, _LL, _I, _P],
     "usvm_cast_f32_bf16": [_P, _P, _LL, _P],
     "usvm_rope_bf16": [_P, _I, _P, _P, _P, _I, _LL, _I, _I, _I, _I, _P],
     "usvm_window_gather": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -21,7 +21,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, const float* __restrict__ ln_w,
                 const float* __restrict__ ln_b, float eps, float* __restrict__ out, int B, int Hc, int Wc,
-                int feat_shared) {
+                int feat_group) {
   constexpr int CPL = C / 32;
   const int lane = threadIdx.x & 31;
   float gw[CPL], gb[CPL];  // LayerNorm parameters: constants, fetched before the programmatic-dependency wait
@@ -37,7 +37,8 @@ upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, co
   const int X = (int)(pix % Wo), Y = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
   const long long src = ((long long)b * Hc + (Y >> 1)) * Wc + (X >> 1);
   const int q = (Y & 1) * 2 + (X & 1);
-  const long long fpix = feat_shared ? (long long)Y * Wo + X : pix;  // one frame's features shared by all objects
+  // a video's objects share its frame of features (feat_group consecutive objects per frame; 0: one frame each)
+  const long long fpix = feat_group > 0 ? ((long long)(b / feat_group) * Ho + Y) * Wo + X : pix;
   float v[CPL];
   float s = 0.f;
 #pragma unroll
@@ -64,7 +65,7 @@ upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, co
 // g2: [B*Hc*Wc, 4*32]; feat_s0: [B, 2Hc, 2Wc, 32]; hyper: [B, 4, 32]; masks: [B, 4, 2Hc, 2Wc]
 __global__ void __launch_bounds__(256)
 upscale2_masks_kernel(const float* __restrict__ g2, const float* __restrict__ feat, const float* __restrict__ hyper,
-                      int hyper_bs, float* __restrict__ masks, int B, int Hc, int Wc, int feat_shared) {
+                      int hyper_bs, float* __restrict__ masks, int B, int Hc, int Wc, int feat_group) {
   PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int Ho = 2 * Hc, Wo = 2 * Wc;
@@ -73,7 +74,7 @@ upscale2_masks_kernel(const float* __restrict__ g2, const float* __restrict__ fe
   const int X = (int)(pix % Wo), Y = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
   const long long src = ((long long)b * Hc + (Y >> 1)) * Wc + (X >> 1);
   const int q = (Y & 1) * 2 + (X & 1);
-  const long long fpix = feat_shared ? (long long)Y * Wo + X : pix;
+  const long long fpix = feat_group > 0 ? ((long long)(b / feat_group) * Ho + Y) * Wo + X : pix;
   const float v = gelu_erf(g2[src * 128 + q * 32 + lane] + feat[fpix * 32 + lane]);
   const float* hp = hyper + (long long)b * hyper_bs;
   const float m0 = warp_sum(v * hp[lane]);
@@ -221,17 +222,17 @@ __global__ void point_embed_kernel(const float* __restrict__ coords, const int* 
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" int usvm_upscale1_ln_gelu(const float* g1, const float* feat_s1, const float* ln_w, const float* ln_b,
-                                     float eps, float* out, int B, int Hc, int Wc, int C, int feat_shared,
+                                     float eps, float* out, int B, int Hc, int Wc, int C, int feat_group,
                                      void* stream) {
   if (!g1 || !feat_s1 || !ln_w || !ln_b || !out || C != 64) return USVM_ERR_ARG;
-  usvm_launch(upscale1_kernel<64>, dim3(cdiv((long long)B * 4 * Hc * Wc, 8)), dim3(256), 0, STREAM, g1, feat_s1, ln_w, ln_b, eps, out, B, Hc, Wc, feat_shared);
+  usvm_launch(upscale1_kernel<64>, dim3(cdiv((long long)B * 4 * Hc * Wc, 8)), dim3(256), 0, STREAM, g1, feat_s1, ln_w, ln_b, eps, out, B, Hc, Wc, feat_group);
   return usvm_check_launch();
 }
 
 extern "C" int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, int hyper_bs,
-                                   float* masks, int B, int Hc, int Wc, int feat_shared, void* stream) {
+                                   float* masks, int B, int Hc, int Wc, int feat_group, void* stream) {
   if (!g2 || !feat_s0 || !hyper || !masks) return USVM_ERR_ARG;
-  usvm_launch(upscale2_masks_kernel, dim3(cdiv((long long)B * 4 * Hc * Wc, 8)), dim3(256), 0, STREAM, g2, feat_s0, hyper, hyper_bs, masks, B, Hc, Wc, feat_shared);
+  usvm_launch(upscale2_masks_kernel, dim3(cdiv((long long)B * 4 * Hc * Wc, 8)), dim3(256), 0, STREAM, g2, feat_s0, hyper, hyper_bs, masks, B, Hc, Wc, feat_group);
   return usvm_check_launch();
 }
 

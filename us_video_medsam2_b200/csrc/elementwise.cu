@@ -83,13 +83,14 @@ layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restri
 
 // out[r, c] = alpha * x[r % x_mod, c] + beta * y[r % y_mod, c]   (fp32 in; fp32 and/or bf16 out)
 __global__ void axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, float beta,
-                                  int x_mod, int y_mod, float* out_f32, bf16* out_bf16, long long rows, int C) {
+                                  int x_mod, int y_mod, int x_div, float* out_f32, bf16* out_bf16, long long rows, int C) {
   PDL_ENTRY();
   const long long total = rows * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C;
     const int c = (int)(i - r * C);
-    float v = alpha * x[(x_mod > 0 ? r % x_mod : r) * C + c];
+    const long long xr = x_div > 0 ? (r / x_div) * x_mod + r % x_mod : (x_mod > 0 ? r % x_mod : r);
+    float v = alpha * x[xr * C + c];
     if (y) v += beta * y[(y_mod > 0 ? r % y_mod : r) * C + c];
     if (out_f32) out_f32[i] = v;
     if (out_bf16) out_bf16[i] = __float2bfloat16(v);
@@ -519,10 +520,10 @@ extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const flo
   return usvm_check_launch();
 }
 
-extern "C" int usvm_axpby_rows(const float* x, const float* y, float alpha, float beta, int x_mod, int y_mod,
+extern "C" int usvm_axpby_rows(const float* x, const float* y, float alpha, float beta, int x_mod, int y_mod, int x_div,
                                float* out_f32, void* out_bf16, long long rows, int C, void* stream) {
-  if (!x || rows <= 0 || C <= 0) return USVM_ERR_ARG;
-  usvm_launch(axpby_rows_kernel, dim3(grid_for(rows * C)), dim3(256), 0, STREAM, x, y, alpha, beta, x_mod, y_mod, out_f32,
+  if (!x || rows <= 0 || C <= 0 || (x_div > 0 && x_mod <= 0)) return USVM_ERR_ARG;
+  usvm_launch(axpby_rows_kernel, dim3(grid_for(rows * C)), dim3(256), 0, STREAM, x, y, alpha, beta, x_mod, y_mod, x_div, out_f32,
                                                             reinterpret_cast<bf16*>(out_bf16), rows, C);
   return usvm_check_launch();
 }

@@ -59,7 +59,8 @@ gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, in
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
     if (row >= M) continue;
-    const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+    const long long rrow = (ep.res_div > 0 ? ((long long)(row / ep.res_div) * ep.res_mod + row % ep.res_mod)
+                                           : (ep.res_mod > 0 ? (row % ep.res_mod) : row));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + tx * 4 + j;
@@ -129,7 +130,8 @@ gemm_simt_f32_pipelined_kernel(const float* __restrict__ A, int lda, const float
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
     if (row >= M) continue;
-    const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+    const long long rrow = (ep.res_div > 0 ? ((long long)(row / ep.res_div) * ep.res_mod + row % ep.res_mod)
+                                           : (ep.res_mod > 0 ? (row % ep.res_mod) : row));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int col = n0 + tx * 4 + j;

@@ -241,7 +241,8 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int row0 = tile_m * BM + lane_grp * 32;
     const int row = row0 + lane;
     const bool row_ok = row < M;
-    const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+    const long long rrow = (ep.res_div > 0 ? ((long long)(row / ep.res_div) * ep.res_mod + row % ep.res_mod)
+                                           : (ep.res_mod > 0 ? (row % ep.res_mod) : row));
     uint8_t* stg32 = staging + lane_grp * STG_F32;
     uint8_t* stg16 = staging + 4 * STG_F32 + lane_grp * STG_BF16;
     bool pending = false;  // this warp has a TMA store in flight that still reads its staging buffers
@@ -577,7 +578,8 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
       const int row0 = tile_m * BM + lane_grp * 32;
       const int row = row0 + lane;
       const bool row_ok = row < M;
-      const long long rrow = ep.res_mod > 0 ? (row % ep.res_mod) : row;
+      const long long rrow = (ep.res_div > 0 ? ((long long)(row / ep.res_div) * ep.res_mod + row % ep.res_mod)
+                                           : (ep.res_mod > 0 ? (row % ep.res_mod) : row));
       if (row0 < M) {
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN; c0 += 64) {

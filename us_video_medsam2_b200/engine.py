@@ -23,6 +23,8 @@ from . import ops
 from .ops import ACT_GELU, ACT_RELU, BF16, F32
 
 NO_OBJ_SCORE = -1024.0
+# precision study switch: 0 = the decoder's image-side GEMMs as exact fp32 products (SIMT kernel) instead of tf32
+_DEC_TF32 = os.environ.get("USVM2_DEC_TF32", "1") != "0"
 
 
 class ModelConfig:
@@ -488,8 +490,9 @@ class Engine:
                     feat_s0=zeros(16 * T, 32))
 
     # ---------------------------------------------------------------- memory attention
-    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None, fold_no_mask=False):
-        """feat fp32 [1024,256] (one frame, shared by the B objects); k_in / v_in bf16 [B, Nk, 64] assembled memory
+    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None, fold_no_mask=False, group=0):
+        """feat fp32 [1024,256] (one frame, shared by the B objects; with group > 0: [B/group, 1024, 256], one frame per
+        `group` consecutive objects -- several videos batched into one launch); k_in / v_in bf16 [B, Nk, 64] assembled memory
         (k_in already carries the position encodings), the last n_ptr_tok rows are object-pointer tokens (no RoPE).
         Returns fp32 [B*1024, 256]  (MemoryAttention.forward, memory_attention.py:119-169; RoPEAttention,
         sam/transformer.py:311-360).  RoPE is fused into the q / k projection epilogues; the key / value
@@ -500,7 +503,7 @@ class Engine:
         w = self.w
         T = 1024
         cs, sn = w.rope_cos, w.rope_sin
-        x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T)
+        x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T, x_div=group * T)
         k_all = v_all = None
         if bank is None:
             k_all, v_all = self.project_memory(k_in, v_in, Nk, n_ptr_tok, B)
@@ -557,12 +560,14 @@ class Engine:
         k_in, v_in, Nk = ops.build_memory_store(ctrl, w.mem_pos, w.maskmem_tpos, ptr_pos, B, n_mem, n_ptr)
         return k_in, v_in, Nk, 4 * n_ptr
 
-    def track_frame(self, f, ctrl, B, n_mem, n_ptr, video_hw, fill_hole_area):
+    def track_frame(self, f, ctrl, B, n_mem, n_ptr, video_hw, fill_hole_area, group=0):
         """One steady-state tracked frame, entirely on the device and free of host-dependent control flow (so it can
         be captured in a CUDA graph): memory attention over the bank named by `ctrl`, SAM heads with multimask
         output, memory encoder, hole filling, video-resolution resize.  Everything the frame leaves behind is
         written into slot ctrl->cur_frame of the frame store.  f: dict(feat, feat_bf16, feat_s0, feat_s1) of this
-        frame.  Returns (video_res logits [B,1,H,W], hole-filled low-res logits [B,1,128,128])."""
+        frame.  group > 0: the batch holds B / group videos of `group` objects each in lock-step (same frame index, same
+        bank layout); f then carries one frame per video ([B/group, ...]) and every per-video operand is indexed by
+        object // group.  Returns (video_res logits [B,1,H,W], hole-filled low-res logits [B,1,128,128])."""
         main = torch.cuda.current_stream()
         if self.fork_branches:
             # the bank (gather + temporal encodings + K/V projections of ~7 k rows) does not depend on this frame's
@@ -573,7 +578,7 @@ class Engine:
             side_v.wait_stream(main)
             with torch.cuda.stream(side_v):
                 # pix_feat_proj of the memory encoder only reads this frame's features: off the critical path here
-                pp, _ = ops.gemm_bf16(f["feat_bf16"], *self.w.pix_proj, f32=True)
+                pp, _ = ops.gemm_bf16(f["feat_bf16"].view(-1, 256), *self.w.pix_proj, f32=True)
             with torch.cuda.stream(side):
                 k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
             self._handoff(side_v, side, v_in)
@@ -588,12 +593,13 @@ class Engine:
                 self._handoff(main, side_v, v_all, pp)
                 return kv
 
-            pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank, fold_no_mask=True)
+            pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank, fold_no_mask=True, group=group)
         else:
             pp = None
             k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
-            pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B, fold_no_mask=True)
-        o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, None, multimask=True, src_ready=True, defer_ptr=True)
+            pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B, fold_no_mask=True, group=group)
+        o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, None, multimask=True, src_ready=True, defer_ptr=True,
+                           group=group)
         # The user-facing tail (single-CTA hole filling, store write, video-resolution resize) is independent of the
         # memory encoder: it runs on a forked stream -- a parallel branch of the captured graph -- and joins at the end.
         if self._tail_stream is None:
@@ -609,8 +615,8 @@ class Engine:
             video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
         # (non_overlap_masks_for_mem_enc applies on every frame in eval, sam2_base.py:1466-1471: device-side, so the frame
         # stays one capturable graph)
-        mask_in = self.mem_mask_input(o["low"], False, non_overlap=self.cfg.non_overlap_masks_for_mem_enc)
-        self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl, pix_proj=pp)
+        mask_in = self.mem_mask_input(o["low"], False, non_overlap=self.cfg.non_overlap_masks_for_mem_enc, group=group)
+        self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl, pix_proj=pp, group=group)
         self._handoff(main, tail, video, pm)
         return video, pm
 
@@ -640,14 +646,17 @@ class Engine:
         return self._tok_const[B]
 
     def sam_heads(self, pix_feat, feat_s0, feat_s1, B, sparse, dense=None, multimask=True, feat_shared=True,
-                  src_ready=False, defer_ptr=False):
+                  src_ready=False, defer_ptr=False, group=0):
         """pix_feat fp32 [B*1024,256]; sparse fp32 [B,P,256] prompt tokens; dense fp32 [B*1024,256] or None
         (-> no_mask_embed).  Returns dict(low [B,1,128,128], obj_ptr [B,256], score [B,1], iou [B,1]).
         (_forward_sam_heads sam2_base.py:1010-1166 + MaskDecoder mask_decoder.py:110-295 +
         TwoWayTransformer transformer.py:90-212).  Token-side linears (8 rows per object) run on the skinny
-        GEMM, image-side projections of a layer are one fused GEMM, attention on the t2i / i2t kernels."""
+        GEMM, image-side projections of a layer are one fused GEMM, attention on the t2i / i2t kernels.
+        feat_s0 / feat_s1: one frame shared by all B objects (feat_shared), one per `group` consecutive objects
+        (group > 0), or one per object."""
         w = self.w
         T = 1024
+        feat_group = group if group > 0 else (B if feat_shared else 0)
         if src_ready:  # pix_feat already carries the dense prompt embedding (memory_attention(fold_no_mask=True))
             assert dense is None
             src = pix_feat
@@ -673,9 +682,9 @@ class Engine:
                                                  defer_final_norm=True)
         # output upscaling (image side) || the six token heads (token side); they meet in the mask product
         with torch.cuda.stream(img_s if img_s is not None else tok):
-            g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=True)
-            u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_shared)
-            g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=True)
+            g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=_DEC_TF32)
+            u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_group)
+            g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=_DEC_TF32)
         # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
         # norm_final_attn runs on load in the first head layer, which also leaves the normalised token rows 0..5 in hs
         W1, b1, W2, b2, W3, b3 = w.heads6
@@ -686,7 +695,7 @@ class Engine:
         y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
         if img_s is not None:
             self._handoff(tok, img_s, g2, keys)
-        masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 64, 64, feat_shared, hyper_bs=192)
+        masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 64, 64, feat_group, hyper_bs=192)
         # single-mask output without the stability fallback (apply_postprocessing=False, mask_decoder.py:160-166): a
         # threshold no stability score can miss keeps mask token 0
         stab_thresh = self.cfg.dynamic_multimask_stability_thresh if self.cfg.dynamic_multimask_via_stability else -1.0
@@ -733,7 +742,7 @@ class Engine:
         for l, Lyr in enumerate(w.dec_layers):
             sa, t2i, i2t = Lyr["sa"], Lyr["t2i"], Lyr["i2t"]
             with torch.cuda.stream(img_s):
-                img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T, tf32=True)  # [B*T, 384]
+                img = ops.gemm_f32(keys, Lyr["img_w"], Lyr["img_b"], residual=Lyr["img_pe"], res_mod=T, tf32=_DEC_TF32)  # [B*T, 384]
             if l == 0 and const0 is not None:
                 queries, q = const0  # constants of the model on prompt-free frames (Engine.token_constants)
             else:
@@ -763,10 +772,10 @@ class Engine:
                 self._handoff(img_s, tok, kv2)
             with torch.cuda.stream(img_s):
                 o2 = ops.attn_i2t(img[:, 256:384], kv2[:, 0:128], kv2[:, 128:256], B, T, Nt)
-                keys = ln(ops.gemm_f32(o2, *i2t["o"], residual=keys, tf32=True), Lyr["norms"][3])
+                keys = ln(ops.gemm_f32(o2, *i2t["o"], residual=keys, tf32=_DEC_TF32), Lyr["norms"][3])
         fin = w.dec_final
         with torch.cuda.stream(img_s):
-            img = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T, tf32=True)  # [B*T, 256]
+            img = ops.gemm_f32(keys, fin["img_w"], fin["img_b"], residual=fin["img_pe"], res_mod=T, tf32=_DEC_TF32)  # [B*T, 256]
         q = sk(queries, *fin["q"], x2=tokens)
         if par:
             self._handoff(tok, img_s, img)
@@ -813,7 +822,7 @@ class Engine:
         return dict(low=low, high=high, obj_ptr=ptr, score=score)
 
     # ---------------------------------------------------------------- memory encoder
-    def encode_memory(self, feat_bf16, mask_in512, score, B, ctrl=None, pix_proj=None):
+    def encode_memory(self, feat_bf16, mask_in512, score, B, ctrl=None, pix_proj=None, group=0):
         """mask_in512 fp32 [B,512,512]: already sigmoid*20-10 / binarised (see Engine.mem_mask_input);
         feat_bf16 [1024,256] raw frame features.  Returns bf16 token-major memory [B,1024,64], or writes it into the
         frame store slot named by `ctrl`
@@ -827,8 +836,9 @@ class Engine:
         _, c4n = ops.gemm_bf16(A4, w.md_conv3_w, bias=w.md_conv3_b, ln=(w.md_ln3[0], w.md_ln3[1], 1e-6, True))
         pp = pix_proj  # pix_feat_proj, shared by all objects (precomputed by the caller on a forked branch, or here)
         if pp is None:
-            pp, _ = ops.gemm_bf16(feat_bf16, *w.pix_proj, f32=True)
-        x, _ = ops.gemm_bf16(c4n, w.md_out[0], bias=w.md_out[1], residual=pp, res_mod=1024, f32=True)
+            pp, _ = ops.gemm_bf16(feat_bf16.view(-1, 256), *w.pix_proj, f32=True)
+        x, _ = ops.gemm_bf16(c4n, w.md_out[0], bias=w.md_out[1], residual=pp, res_mod=1024, f32=True,
+                             res_div=group * 1024)
         xb = None
         for i, Lf in enumerate(w.fuser):
             h = ops.dwconv7_ln(x, Lf["dw_w"], Lf["dw_b"], Lf["ln"][0], Lf["ln"][1], B, 32, 32)

@@ -54,8 +54,9 @@ def empty(shape, dtype, like):
 # GEMM
 # ------------------------------------------------------------------------------------------------
 def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16, like, out_f32, out_bf16, rope=None,
-              ln=None):
+              ln=None, res_div=0):
     ep = GemmEpilogue()
+    ep.res_div = res_div
     if ln is not None:  # (weight, bias, eps[, gelu])
         ep.ln_w, ep.ln_b, ep.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln[2]
         ep.ln_gelu = int(len(ln) > 3 and bool(ln[3]))
@@ -76,7 +77,7 @@ def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16
 
 
 def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, f32=False, bf16=False,
-              out_f32=None, out_bf16=None, block_n=0, simt=None, rope=None, ln=None, ln_fused=None):
+              out_f32=None, out_bf16=None, block_n=0, simt=None, rope=None, ln=None, ln_fused=None, res_div=0):
     """epi(a[M,K] @ w[N,K]^T) on the tcgen05 kernel; returns (fp32 out or None, bf16 out or None).
     rope = (cos, sin, cols, rows_per_batch, n_rope): fused rotary encoding of output columns [0, cols).
     ln = (weight, bias, eps[, gelu]): the bf16 output becomes LayerNorm(row) (then GELU) of the result.  With N == 256
@@ -90,11 +91,11 @@ def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_
     if ln is not None and ((_FORCE_SIMT if simt is None else simt) or N != 256 or
                            not (M >= 4096 if ln_fused is None else ln_fused)):  # GEMM, then the LayerNorm kernel
         o32, _ = gemm_bf16(a, w, bias, act, col_scale, residual, res_mod, f32=True, out_f32=out_f32, block_n=block_n,
-                           simt=simt, rope=rope)
+                           simt=simt, rope=rope, res_div=res_div)
         _, o16 = layernorm(o32, ln[0], ln[1], ln[2], bf16=True, gelu=len(ln) > 3 and bool(ln[3]))
         return o32, o16
     ep, o32, o16 = _epilogue(M, N, bias, act, col_scale, residual, res_mod, f32 or out_f32 is not None,
-                             bf16 or out_bf16 is not None or ln is not None, a, out_f32, out_bf16, rope, ln)
+                             bf16 or out_bf16 is not None or ln is not None, a, out_f32, out_bf16, rope, ln, res_div)
     if _FORCE_SIMT if simt is None else simt:
         call("usvm_gemm_simt", a.data_ptr(), 1, a.stride(0), w.data_ptr(), 1, w.stride(0), C.byref(ep), M, N, K,
              _stream())
@@ -186,13 +187,14 @@ def layernorm(x, w, b, eps, f32=False, bf16=False, gelu=False):
     return o32, o16
 
 
-def axpby(x, y, alpha=1.0, beta=1.0, rows=None, x_mod=0, y_mod=0, f32=True, bf16=False):
-    """alpha * x[r % x_mod] + beta * y[r % y_mod] over `rows` rows of C channels."""
+def axpby(x, y, alpha=1.0, beta=1.0, rows=None, x_mod=0, y_mod=0, f32=True, bf16=False, x_div=0):
+    """alpha * x[r % x_mod] + beta * y[r % y_mod] over `rows` rows of C channels; with x_div > 0 the x row is
+    (r // x_div) * x_mod + r % x_mod (groups of x_div output rows share one x_mod-row block of x)."""
     Cc = x.shape[-1]
     rows = rows if rows is not None else x.numel() // Cc
     o32 = empty((rows, Cc), F32, x) if f32 else None
     o16 = empty((rows, Cc), BF16, x) if bf16 else None
-    call("usvm_axpby_rows", x.data_ptr(), _ptr(y), alpha, beta, x_mod, y_mod, _ptr(o32), _ptr(o16), rows, Cc,
+    call("usvm_axpby_rows", x.data_ptr(), _ptr(y), alpha, beta, x_mod, y_mod, x_div, _ptr(o32), _ptr(o16), rows, Cc,
          _stream())
     return o32, o16
 
@@ -314,6 +316,17 @@ class FrameStore:
         self.ptr = torch.zeros((num_frames, B, ptr_dim), dtype=F32, device=device)
         self.score = torch.zeros((num_frames, B, 1), dtype=F32, device=device)
         self.masks = torch.zeros((num_frames, B, 1, 128, 128), dtype=F32, device=device)
+        self.shared, self.column0 = None, 0  # set on the column views of a store shared by lock-step sessions
+
+    def columns(self, lo, n):
+        """The store of objects [lo, lo + n) as a VIEW of this one (per-session face of a store shared by several
+        sessions tracked in lock-step); slot strides stay those of the shared store."""
+        v = FrameStore.__new__(FrameStore)
+        v.num_frames, v.B = self.num_frames, n
+        v.mem, v.ptr = self.mem[:, lo:lo + n], self.ptr[:, lo:lo + n]
+        v.score, v.masks = self.score[:, lo:lo + n], self.masks[:, lo:lo + n]
+        v.shared, v.column0 = self, lo
+        return v
 
     def grow(self, B):
         """Append zero-filled columns for objects added later; the existing objects keep their results."""
@@ -323,12 +336,12 @@ class FrameStore:
             return out
 
         self.mem, self.ptr, self.score, self.masks = wider(self.mem), wider(self.ptr), wider(self.score), wider(self.masks)
-        self.B = B
+        self.B, self.shared = B, None  # (no longer a column view of a shared store)
 
     def select_objects(self, keep):
         self.mem, self.ptr = self.mem[:, keep].contiguous(), self.ptr[:, keep].contiguous()
         self.score, self.masks = self.score[:, keep].contiguous(), self.masks[:, keep].contiguous()
-        self.B = len(keep)
+        self.B, self.shared = len(keep), None
 
 
 def new_frame_ctrl(device):
@@ -466,18 +479,19 @@ def resize_bilinear_aa(x, Ho, Wo, binarize_half=False):
 # ------------------------------------------------------------------------------------------------
 # decoder tail
 # ------------------------------------------------------------------------------------------------
-def upscale1_ln_gelu(g1, feat_s1, ln_w, ln_b, B, Hc, Wc, feat_shared, eps=1e-6):
+def upscale1_ln_gelu(g1, feat_s1, ln_w, ln_b, B, Hc, Wc, feat_group, eps=1e-6):
+    """feat_group: consecutive objects that share one frame of feat_s1 (0: every object has its own)."""
     out = empty((B * 4 * Hc * Wc, 64), F32, g1)
     call("usvm_upscale1_ln_gelu", g1.data_ptr(), feat_s1.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), eps,
-         out.data_ptr(), B, Hc, Wc, 64, int(feat_shared), _stream())
+         out.data_ptr(), B, Hc, Wc, 64, int(feat_group), _stream())
     return out
 
 
-def upscale2_masks(g2, feat_s0, hyper, B, Hc, Wc, feat_shared, hyper_bs=128):
-    """hyper: [B, 4, 32] hyper-network outputs, object stride hyper_bs elements."""
+def upscale2_masks(g2, feat_s0, hyper, B, Hc, Wc, feat_group, hyper_bs=128):
+    """hyper: [B, 4, 32] hyper-network outputs, object stride hyper_bs elements; feat_group as in upscale1_ln_gelu."""
     masks = empty((B, 4, 2 * Hc, 2 * Wc), F32, g2)
     call("usvm_upscale2_masks", g2.data_ptr(), feat_s0.data_ptr(), hyper.data_ptr(), hyper_bs, masks.data_ptr(), B, Hc,
-         Wc, int(feat_shared), _stream())
+         Wc, int(feat_group), _stream())
     return masks
 
 

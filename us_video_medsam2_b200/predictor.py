@@ -722,6 +722,123 @@ class SAM2VideoPredictor(nn.Module):
             if self._pipeline_owner is st:
                 self._pipeline_owner = None
 
+    # ------------------------------------------------------------------ several sessions in lock-step
+    @torch.inference_mode()
+    def propagate_in_videos(self, inference_states, start_frame_idx=None, max_frame_num_to_track=None, reverse=False):
+        """Propagate S independent sessions in LOCK-STEP as one batched frame: generator of
+        (frame_idx, [obj_ids of each session], [video_res_masks of each session]).
+
+        The reference's only inference parallelism is a process pool over volumes
+        (medsam2_infer_CT_lesion_npz_recist.py:454-456); on one B200 a single object's tracked frame is a latency chain
+        that leaves most of the device idle, so independent videos are stacked into the batch dimension of ONE captured
+        frame graph instead: S sessions x Bo objects run as B = S * Bo objects whose per-video operands (backbone
+        features, pix_feat projection) are indexed by object // Bo.  The sessions share one frame store (each session's
+        store becomes a column view of it) and one device control block -- they advance through the same frame indices
+        with the same memory-bank layout, which requires: equal frame count, video size and object count, prompts on the
+        same frames, and no differing earlier tracking results.  Anything else raises ValueError (track such sessions
+        one after another with propagate_in_video).  No host synchronisation happens per frame; every session's
+        `inference_state` ends up exactly as if it had been tracked alone (results are views of the shared store)."""
+        states = list(inference_states)
+        if len(states) == 0:
+            return
+        for st in states:
+            self.propagate_in_video_preflight(st)
+        self._check_lockstep(states)
+        st0 = states[0]
+        S, Bo = len(states), self._get_obj_num(st0)
+        num_frames = st0["num_frames"]
+        cond_frames = self._cond_frames(st0)
+        if len(cond_frames) == 0:
+            raise RuntimeError("No points are provided; please add points first")
+        if start_frame_idx is None:
+            start_frame_idx = min(cond_frames)
+        if max_frame_num_to_track is None:
+            max_frame_num_to_track = num_frames
+        if reverse:
+            end_frame_idx = max(start_frame_idx - max_frame_num_to_track, 0)
+            order = range(start_frame_idx, end_frame_idx - 1, -1) if start_frame_idx > 0 else []
+        else:
+            end_frame_idx = min(start_frame_idx + max_frame_num_to_track, num_frames - 1)
+            order = range(start_frame_idx, end_frame_idx + 1)
+        shared = self._merge_stores(states)
+        feats = _LockstepFeatures(self, states, -1 if reverse else 1)
+        hw = (st0["video_height"], st0["video_width"])
+        clear_non_cond_mem = self.clear_non_cond_mem_around_input and (self.clear_non_cond_mem_for_multi_obj or Bo <= 1)
+        cfi = st0["consolidated_frame_inds"]
+        for frame_idx in _progress(order, "propagate in videos"):
+            if frame_idx in cfi["cond_frame_outputs"] or frame_idx in cfi["non_cond_frame_outputs"]:
+                storage_key = "cond_frame_outputs" if frame_idx in cfi["cond_frame_outputs"] else "non_cond_frame_outputs"
+                masks = []
+                for st in states:
+                    current_out = st["output_dict"][storage_key][frame_idx]
+                    if clear_non_cond_mem and storage_key == "cond_frame_outputs":
+                        self._clear_non_cond_mem_around_input(st, frame_idx)
+                    self._add_output_per_object(st, frame_idx, current_out, storage_key)
+                    masks.append(self._get_orig_video_res_output(st, current_out["pred_masks"])[1])
+            else:
+                storage_key = "non_cond_frame_outputs"
+                f = feats.get(frame_idx)
+                mem_inputs = self._memory_inputs(st0, frame_idx, st0["output_dict"], reverse)
+                video = self._run_tracked_frame(shared, f, frame_idx, S * Bo, mem_inputs, hw, group=Bo)
+                masks = []
+                for i, st in enumerate(states):
+                    current_out = self._slot_views(st, frame_idx)
+                    st["output_dict"][storage_key][frame_idx] = current_out
+                    self._add_output_per_object(st, frame_idx, current_out, storage_key)
+                    m = video[i * Bo:(i + 1) * Bo]
+                    masks.append(self._apply_non_overlapping_constraints(m) if self.non_overlap_masks else m)
+            for st in states:
+                st["frames_already_tracked"][frame_idx] = {"reverse": reverse}
+                for tracked in st.get("frames_tracked_per_obj", {}).values():
+                    tracked[frame_idx] = {"reverse": reverse}
+            yield frame_idx, [st["obj_ids"] for st in states], masks
+
+    def _check_lockstep(self, states):
+        st0 = states[0]
+
+        def signature(st):
+            od = st["output_dict"]
+            return (st["num_frames"], st["video_height"], st["video_width"], self._get_obj_num(st),
+                    tuple(sorted(od["cond_frame_outputs"])), tuple(sorted(od["non_cond_frame_outputs"])),
+                    bool(st.get("_per_object")))
+
+        ref = signature(st0)
+        for i, st in enumerate(states[1:], 1):
+            if signature(st) != ref:
+                raise ValueError(f"session {i} cannot be tracked in lock-step with session 0: frame count, video size, "
+                                 "object count, prompted frames and earlier tracked frames must agree "
+                                 f"({signature(st)} vs {ref}); use propagate_in_video for it")
+        if ref[3] == 0:
+            raise RuntimeError("No points are provided; please add points first")
+        if ref[6]:
+            raise ValueError("sessions on the per-object (EfficientTAM) schedule cannot be batched")
+        if len({id(st) for st in states}) != len(states):
+            raise ValueError("the same inference_state was passed twice")
+
+    def _merge_stores(self, states):
+        """One frame store for all sessions (objects of session i in columns [i * Bo, (i + 1) * Bo)); each session's own
+        store becomes a column view of it, its stored entries are re-pointed."""
+        st0 = states[0]
+        S, Bo, T = len(states), self._get_obj_num(st0), st0["num_frames"]
+        owners = [st["_store"] for st in states]
+        base = getattr(owners[0], "shared", None)
+        if base is not None and base.B == S * Bo and all(getattr(o, "shared", None) is base and o.column0 == i * Bo
+                                                         for i, o in enumerate(owners)):
+            return base  # already merged by an earlier pass over the same sessions
+        shared = ops.FrameStore(T, S * Bo, self.device)
+        for i, st in enumerate(states):
+            old = st["_store"]
+            od = st["output_dict"]
+            for t in list(od["cond_frame_outputs"]) + list(od["non_cond_frame_outputs"]):
+                lo = i * Bo
+                shared.mem[t, lo:lo + Bo].copy_(old.mem[t])
+                shared.ptr[t, lo:lo + Bo].copy_(old.ptr[t])
+                shared.score[t, lo:lo + Bo].copy_(old.score[t])
+                shared.masks[t, lo:lo + Bo].copy_(old.masks[t])
+            st["_store"] = shared.columns(i * Bo, Bo)
+            self._refresh_views(st)
+        return shared
+
     def _cond_frames(self, st):
         """Frames that hold a conditioning output (the default start of a pass is the earliest one, reference :684-686)."""
         return set(st["output_dict"]["cond_frame_outputs"])
@@ -831,13 +948,22 @@ class SAM2VideoPredictor(nn.Module):
         state is replayed from a CUDA graph (one graph per (B, #memories, #pointers, video size) signature).
         obj0: track ONE object (B == 1) of a multi-object session against its own `output_dict` -- the control block
         addresses that object's column of the store."""
-        eng = self.engine()
-        store = st["_store"]
         look = -1 if reverse else 1
         f = self._get_image_feature(st, frame_idx, lookahead=look)
-        mem_slots, tpos_rows, ptr_slots, ptr_rel = self._memory_inputs(st, frame_idx, output_dict, reverse)
+        mem_inputs = self._memory_inputs(st, frame_idx, output_dict, reverse)
         hw = (st["video_height"], st["video_width"])
-        key = (B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
+        video = self._run_tracked_frame(st["_store"], f, frame_idx, B, mem_inputs, hw, obj0=obj0 or 0)
+        if obj0 is not None:
+            return self._obj_slot_views(st, frame_idx, obj0), video
+        return self._slot_views(st, frame_idx), video
+
+    def _run_tracked_frame(self, store, f, frame_idx, B, mem_inputs, hw, obj0=0, group=0):
+        """Enqueue one tracked frame of B objects whose results land in slot `frame_idx` of `store` (columns obj0 ...
+        obj0 + B - 1); returns the video-resolution logits [B,1,H,W].  group > 0: B / group videos of `group` objects
+        each in lock-step (propagate_in_videos), f holds one frame of features per video."""
+        eng = self.engine()
+        mem_slots, tpos_rows, ptr_slots, ptr_rel = mem_inputs
+        key = (B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area, group)
         ent = self._graphs.get(key) if self.use_cuda_graphs else None
         if self.use_cuda_graphs and ent is None:
             seen = self._graph_seen.get(key, 0) + 1
@@ -845,25 +971,22 @@ class SAM2VideoPredictor(nn.Module):
             # a signature that recurs is worth a graph: the steady state (full bank) is captured at its second frame, the
             # ramp-up signatures of a clip (bank filling up) when a second clip / pass reaches them
             if seen >= 2:
-                ops.set_frame_ctrl(self._ctrl, store, obj0 or 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
+                ops.set_frame_ctrl(self._ctrl, store, obj0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
                 ent = self._capture_graph(key, f)
         if ent is not None:
             graph, static_f, video, n_kernels = ent
             # one launch refreshes the control block and copies this frame's features into the graph's static inputs
-            ops.set_frame_ctrl(self._ctrl, store, obj0 or 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel,
+            ops.set_frame_ctrl(self._ctrl, store, obj0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel,
                                copies=[(f[k], v) for k, v in static_f.items()])
             graph.replay()
             _lib.launch_count += n_kernels  # kernels of this library replayed by the graph
-            video = video.clone()
-        else:
-            ops.set_frame_ctrl(self._ctrl, store, obj0 or 0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
-            video, _ = eng.track_frame(f, self._ctrl, B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area)
-        if obj0 is not None:
-            return self._obj_slot_views(st, frame_idx, obj0), video
-        return self._slot_views(st, frame_idx), video
+            return video.clone()
+        ops.set_frame_ctrl(self._ctrl, store, obj0, frame_idx, mem_slots, tpos_rows, ptr_slots, ptr_rel)
+        video, _ = eng.track_frame(f, self._ctrl, B, len(mem_slots), len(ptr_slots), hw, self.fill_hole_area, group=group)
+        return video
 
     def _capture_graph(self, key, f, stream=None):
-        B, n_mem, n_ptr, hw, fill = key
+        B, n_mem, n_ptr, hw, fill, group = key
         eng = self.engine()
         static_f = {k: f[k].clone() for k in ("feat", "feat_bf16", "feat_s0", "feat_s1")}
         eng.token_constants(B)  # one-off constants must exist before the capture starts
@@ -871,7 +994,7 @@ class SAM2VideoPredictor(nn.Module):
         torch.cuda.synchronize()
         before = _lib.launch_count
         with torch.cuda.graph(graph, stream=stream):
-            video, _ = eng.track_frame(static_f, self._ctrl, B, n_mem, n_ptr, hw, fill)
+            video, _ = eng.track_frame(static_f, self._ctrl, B, n_mem, n_ptr, hw, fill, group=group)
         n_kernels = _lib.launch_count - before
         _lib.launch_count = before  # capturing launches nothing
         ent = (graph, static_f, video, n_kernels)
@@ -1069,6 +1192,40 @@ class SAM2VideoPredictor(nn.Module):
             st["output_dict"]["non_cond_frame_outputs"].pop(t, None)
             for od in st["output_dict_per_obj"].values():
                 od["non_cond_frame_outputs"].pop(t, None)
+
+
+class _LockstepFeatures:
+    """Backbone features of S sessions at one frame index for propagate_in_videos: each batched encoder pass covers
+    `encoder_batch // S` (>= 1) consecutive time steps of all S videos, time-major, so the S frames of one time step are
+    one contiguous [S, ...] block (what the batched frame graph reads)."""
+
+    def __init__(self, pred, states, step):
+        self.pred, self.states, self.step = pred, states, step
+        self.S = len(states)
+        self.nt = max(1, pred.encoder_batch // self.S)
+        self.cache = {}
+
+    def get(self, t):
+        hit = self.cache.get(t)
+        if hit is not None:
+            return hit
+        pred, states, S = self.pred, self.states, self.S
+        T = states[0]["num_frames"]
+        ts = [x for x in (t + i * self.step for i in range(self.nt)) if 0 <= x < T]
+        n = len(ts) * S
+        if pred.use_cuda_graphs and len(ts) == self.nt and n > 1:
+            graph, static_in, out, n_kernels = pred._encoder_graph(n)
+            for j, tt in enumerate(ts):
+                for i, st in enumerate(states):
+                    static_in[j * S + i].copy_(pred._frame(st, tt), non_blocking=True)
+            graph.replay()
+            pred._static_gen += 1  # the static outputs other sessions may have cached views of are overwritten
+            _lib.launch_count += n_kernels
+        else:
+            imgs = torch.stack([pred._frame(st, tt) for tt in ts for st in states]).contiguous()
+            out = pred.engine().encode_frames(imgs)
+        self.cache = {tt: {k: v[j * S:(j + 1) * S] for k, v in out.items()} for j, tt in enumerate(ts)}
+        return self.cache[t]
 
 
 class SAM2VideoPredictorNPZ(SAM2VideoPredictor):
