@@ -391,7 +391,7 @@ def time_components(pred, dev, B, peaks, iters=10):
         graph, static_in, _, n_kernels = pred._encoder_graph(n)
         static_in.normal_()
         ms = _event_time(graph.replay, iters, flush)
-        tf = GF_ENCODER * n / ms / 1e3
+        tf = GF_ENCODER * n / ms  # GFLOP / ms = TFLOP/s
         out["image_encoder"] = {"bound": "tensor", "frames_per_launch_group": n, "kernels": n_kernels, "avg_ms": ms,
                                 "ms_per_frame": ms / n, "achieved": tf, "peak": peaks["bf16_sustained"],
                                 "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"],

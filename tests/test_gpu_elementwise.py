@@ -275,11 +275,41 @@ def test_decoder_tail_kernels():
     want_masks = (hyper @ y2.view(B, 32, -1)).view(B, 4, 128, 128)
     keys = src.permute(0, 2, 3, 1).reshape(-1, 256).contiguous()
     g1 = ops.gemm_f32(keys, w1.permute(2, 3, 1, 0).reshape(256, 256).contiguous(), b1.repeat(4))
-    u1 = ops.upscale1_ln_gelu(g1, s1.permute(0, 2, 3, 1).contiguous(), lw, lb, B, 32, 32, True)
+    u1 = ops.upscale1_ln_gelu(g1, s1.permute(0, 2, 3, 1).contiguous(), lw, lb, B, 32, 32, B)  # one frame for all B
     assert (u1.view(B, 64, 64, 64) - y.permute(0, 2, 3, 1)).abs().max().item() < 2e-4
     g2 = ops.gemm_f32(u1, w2.permute(2, 3, 1, 0).reshape(128, 64).contiguous(), b2.repeat(4))
-    masks = ops.upscale2_masks(g2, s0.permute(0, 2, 3, 1).contiguous(), hyper.contiguous(), B, 64, 64, True)
+    masks = ops.upscale2_masks(g2, s0.permute(0, 2, 3, 1).contiguous(), hyper.contiguous(), B, 64, 64, B)
     assert (masks - want_masks).abs().max().item() < 5e-4
+    # feature groups (several videos in one launch): 4 objects, 2 per video -> object b reads frame b // 2
+    B4 = 4
+    src4 = torch.randn((B4, 256, 32, 32), generator=g, device="cuda")
+    s1v = torch.randn((2, 64, 64, 64), generator=g, device="cuda")
+    s0v = torch.randn((2, 32, 128, 128), generator=g, device="cuda")
+    hyper4 = torch.randn((B4, 4, 32), generator=g, device="cuda")
+    y = F.conv_transpose2d(src4, w1, b1, stride=2) + s1v.repeat_interleave(2, dim=0)
+    u = y.mean(1, keepdim=True)
+    v = (y - u).pow(2).mean(1, keepdim=True)
+    y = F.gelu((y - u) / torch.sqrt(v + 1e-6) * lw[None, :, None, None] + lb[None, :, None, None])
+    y2 = F.gelu(F.conv_transpose2d(y, w2, b2, stride=2) + s0v.repeat_interleave(2, dim=0))
+    want4 = (hyper4 @ y2.view(B4, 32, -1)).view(B4, 4, 128, 128)
+    g1 = ops.gemm_f32(src4.permute(0, 2, 3, 1).reshape(-1, 256).contiguous(),
+                      w1.permute(2, 3, 1, 0).reshape(256, 256).contiguous(), b1.repeat(4))
+    u1 = ops.upscale1_ln_gelu(g1, s1v.permute(0, 2, 3, 1).contiguous(), lw, lb, B4, 32, 32, 2)
+    g2 = ops.gemm_f32(u1, w2.permute(2, 3, 1, 0).reshape(128, 64).contiguous(), b2.repeat(4))
+    masks4 = ops.upscale2_masks(g2, s0v.permute(0, 2, 3, 1).contiguous(), hyper4.contiguous(), B4, 64, 64, 2)
+    assert (masks4 - want4).abs().max().item() < 5e-4
+    # grouped rows of the row-broadcast kernels: axpby x_div, GEMM res_div
+    x = torch.randn((2 * 8, 64), generator=g, device="cuda")
+    pos = torch.randn((8, 64), generator=g, device="cuda")
+    got, _ = ops.axpby(x, pos, 1.0, 0.1, rows=4 * 8, x_mod=8, y_mod=8, x_div=2 * 8)
+    want = x.view(2, 1, 8, 64).expand(2, 2, 8, 64).reshape(32, 64) + 0.1 * pos.repeat(4, 1)
+    assert torch.equal(got, want)
+    a = torch.randn((4 * 128, 64), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((256, 64), generator=g, device="cuda") / 8).to(torch.bfloat16)
+    res = torch.randn((2 * 128, 256), generator=g, device="cuda")
+    o32, _ = ops.gemm_bf16(a, w, residual=res, res_mod=128, res_div=2 * 128, f32=True)
+    want = a.float() @ w.float().t() + res.view(2, 1, 128, 256).expand(2, 2, 128, 256).reshape(512, 256)
+    assert (o32 - want).abs().max().item() < 2e-3
     # small MLP, instance-stacked + row select
     Ws = [torch.randn((4, 256, 256), generator=g, device="cuda") / 16, torch.randn((4, 256), generator=g, device="cuda"),
           torch.randn((4, 256, 256), generator=g, device="cuda") / 16, torch.randn((4, 256), generator=g, device="cuda"),

@@ -101,8 +101,16 @@ def test_non_overlap_constraints_match_reference_fixture(golden_dir):
             if t == 0:
                 continue  # prompt frame: mask prompt exact, box prompt decoded once (covered by t512_two_obj_mask_box)
             _check_low(got["low"][i, o], g["low"][i, o], ("low", t, o))
-            a, b = torch.from_numpy(got["video_s4"][i, o]), torch.from_numpy(g["video_s4"][i, o])
-            assert dice(a, b) >= DICE_BAR, ("video", t, o, dice(a, b))
+        # the yielded masks went through the argmax over objects: where the two objects' logits are closer than the
+        # logit tolerance the winner is noise (random-init objects see nearly the same evidence), elsewhere it must agree
+        if t > 0:
+            a, b = torch.from_numpy(got["video_s4"][i]), torch.from_numpy(g["video_s4"][i])
+            raw = torch.from_numpy(g["low"][i])  # (video size == 4 x low-res size: stride-4 samples line up with these)
+            decided = (raw[0] - raw[1]).abs() > 4 * LOGIT_TOL
+            for o in range(2):
+                assert torch.equal((a[o] > 0) & decided, (b[o] > 0) & decided) or \
+                    float(((a[o] > 0) != (b[o] > 0))[decided].float().mean()) < 5e-3, ("video", t, o)
+                assert float((a[o] - b[o]).abs()[decided & (b[o] > -5) & (a[o] > -5)].max()) <= 4 * LOGIT_TOL
     err = np.abs(got["maskmem_last"] - g["maskmem_last"])
     assert err.max() < 0.25
     # the constraint changes the memory: without it the last memory is clearly further from the fixture's

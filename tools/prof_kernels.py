@@ -59,5 +59,19 @@ if which == "frames":  # a short clip without CUDA graphs: every kernel of a tra
     pred.add_new_mask(st, 0, 1, synth.box_mask())
     for _ in pred.propagate_in_video(st):
         pass
+if which == "batched":  # 8 videos x 4 objects in lock-step, no CUDA graphs: every kernel of the 32-object frame is listed
+    from us_video_medsam2_b200 import synth
+    from us_video_medsam2_b200.build_sam import build_sam2_video_predictor_npz
+    pred = build_sam2_video_predictor_npz("configs/sam2.1_hiera_t512.yaml", device=dev, encoder_batch=16, use_cuda_graphs=False)
+    pred.load_state_dict(synth.make_state_dict(19), strict=True)
+    clips = [ops.normalize_gray_u8(synth.make_clip_u8(20, seed=1 + i).to(dev), synth.IMG_MEAN, synth.IMG_STD) for i in range(8)]
+    states = []
+    for c in clips:
+        st = pred.init_state(c, 512, 512)
+        for j, m in enumerate(synth.multi_object_masks(4)):
+            pred.add_new_mask(st, 0, j + 1, m)
+        states.append(st)
+    for _ in pred.propagate_in_videos(states):
+        pass
 torch.cuda.synchronize()
 print("done")
