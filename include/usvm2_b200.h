@@ -168,6 +168,11 @@ int usvm_im2col_patch_grid(const float* img, void* A, int F, int S, int P, void*
 int usvm_normalize_gray_u8(const uint8_t* gray, float* out, int F, int H, int W, const float* mean3_host,
                            const float* std3_host, void* stream);
 
+/* JPEG-folder ingest (sam2/utils/misc.py:92-101, 213-277): uint8 RGB [F,H,W,3] as decoded and resized on the host ->
+ * fp32 [F,3,H,W], (x/255 - mean_c)/std_c -- the reference's arithmetic, on a quarter of the host-to-device bytes */
+int usvm_normalize_rgb_u8(const uint8_t* rgb_hwc, float* out, int F, int H, int W, const float* mean3_host,
+                          const float* std3_host, void* stream);
+
 /* memory-bank assembly (sam2_base.py:1344-1437) */
 #define USVM_MAX_MEMORY_FRAMES 32
 typedef struct usvm_memory_frames {

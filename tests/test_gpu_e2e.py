@@ -354,3 +354,77 @@ def test_interleaved_sessions_on_one_predictor():
         for i in range(2):
             for t, (a, b) in enumerate(zip(got[i], want[i])):
                 assert dice(a.cpu(), b.cpu()) >= DICE_BAR, (sms, i, t, dice(a.cpu(), b.cpu()))
+
+
+def test_jpeg_folder_ingest_on_device(tmp_path):
+    """ init_state(video_path): uint8 frames uploaded and normalised by usvm_normalize_rgb_u8 -- synchronous,
+    asynchronous (decoder thread) and offloaded variants give the same frames, equal to the reference's arithmetic
+    (sam2/utils/misc.py:92-101, 268-276) on the host-decoded pixels; and a session started from the folder tracks."""
+    from PIL import Image
+
+    from us_video_medsam2_b200.frames import VideoFrames, decode_jpeg_folder, load_video_frames
+
+    rng = np.random.default_rng(5)
+    T = 9
+    for i in range(T):
+        arr = (rng.random((96, 128, 3)) * 255).astype(np.uint8)
+        Image.fromarray(arr).save(tmp_path / f"{i:05d}.jpg", quality=92)
+    rgb, h, w = decode_jpeg_folder(str(tmp_path), 512)
+    mean = torch.tensor(synth.IMG_MEAN)[:, None, None]
+    std = torch.tensor(synth.IMG_STD)[:, None, None]
+    want = torch.from_numpy(rgb.numpy() / 255.0).permute(0, 3, 1, 2).float()  # (/255 in float64, stored as fp32)
+    want = (want - mean) / std
+    dev = torch.device("cuda")
+    sync, h1, w1 = load_video_frames(str(tmp_path), 512, False, compute_device=dev)
+    assert torch.is_tensor(sync) and sync.shape == (T, 3, 512, 512) and sync.is_cuda and (h1, w1) == (96, 128)
+    assert float((sync.cpu() - want).abs().max()) <= 2.4e-7 * 3  # same operations in fp32: at most an ulp of 2.6
+    lazy, _, _ = load_video_frames(str(tmp_path), 512, False, async_loading_frames=True, compute_device=dev)
+    assert isinstance(lazy, VideoFrames) and len(lazy) == T
+    assert torch.equal(lazy[T - 1], sync[T - 1]) and torch.equal(lazy[2], sync[2])
+    off, _, _ = load_video_frames(str(tmp_path), 512, True, compute_device=dev)
+    assert isinstance(off, VideoFrames) and off.frames is None and torch.equal(off[4], sync[4])
+    from sam2.build_sam import build_sam2_video_predictor
+
+    pred = build_sam2_video_predictor("configs/sam2.1_hiera_t512.yaml", encoder_batch=4)
+    pred.load_state_dict(synth.make_state_dict(19), strict=True)
+    outs = []
+    for kw in (dict(), dict(async_loading_frames=True), dict(offload_video_to_cpu=True)):
+        st = pred.init_state(str(tmp_path), **kw)
+        assert (st["video_height"], st["video_width"], st["num_frames"]) == (96, 128, T)
+        m = torch.zeros((96, 128), dtype=torch.bool)
+        m[30:70, 40:100] = True
+        pred.add_new_mask(st, 0, 1, m)
+        outs.append([lg.clone() for _, _, lg in pred.propagate_in_video(st)])
+        assert len(outs[-1]) == T and outs[-1][3].shape == (1, 1, 96, 128)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)
+
+
+def test_image_predictor_batch_equals_single_images():
+    """SAM2ImagePredictor.set_image_batch / predict_batch (sam2_image_predictor.py:134-236): one batched encoder pass; every
+    image's prediction must equal set_image + predict on that image alone (the encoder is frame-parallel: bit-identical)."""
+    from sam2.sam2_image_predictor import SAM2ImagePredictor
+
+    model = _predictor(26)
+    pred = SAM2ImagePredictor(model, max_hole_area=8, max_sprinkle_area=4)
+    rng = np.random.default_rng(11)
+    images = [(rng.random((200 + 40 * i, 320, 3)) * 255).astype(np.uint8) for i in range(3)]
+    pts = [np.array([[100.0 + 30 * i, 90.0]], np.float32) for i in range(3)]
+    labs = [np.array([1], np.int32)] * 3
+    boxes = [np.array([40.0, 30.0, 250.0, 180.0], np.float32)] * 3
+    single = []
+    for im, pc, pl, bx in zip(images, pts, labs, boxes):
+        pred.set_image(im)
+        single.append(pred.predict(point_coords=pc, point_labels=pl, box=bx, multimask_output=True, return_logits=True))
+    pred.set_image_batch(images)
+    with pytest.raises(AssertionError):
+        pred.predict(point_coords=pts[0], point_labels=labs[0])
+    masks, ious, lows = pred.predict_batch(pts, labs, box_batch=boxes, multimask_output=True, return_logits=True)
+    assert len(masks) == len(ious) == len(lows) == 3
+    for i in range(3):
+        assert masks[i].shape == (3,) + images[i].shape[:2]
+        assert np.array_equal(masks[i], single[i][0]) and np.array_equal(ious[i], single[i][1])
+        assert np.array_equal(lows[i], single[i][2])
+    assert pred.get_image_embedding().shape == (3, 256, 32, 32)

@@ -303,7 +303,7 @@ def test_decoder_tail_kernels():
     pos = torch.randn((8, 64), generator=g, device="cuda")
     got, _ = ops.axpby(x, pos, 1.0, 0.1, rows=4 * 8, x_mod=8, y_mod=8, x_div=2 * 8)
     want = x.view(2, 1, 8, 64).expand(2, 2, 8, 64).reshape(32, 64) + 0.1 * pos.repeat(4, 1)
-    assert torch.equal(got, want)
+    assert (got - want).abs().max().item() < 1e-6  # (the kernel fuses the multiply-add)
     a = torch.randn((4 * 128, 64), generator=g, device="cuda").to(torch.bfloat16)
     w = (torch.randn((256, 64), generator=g, device="cuda") / 8).to(torch.bfloat16)
     res = torch.randn((2 * 128, 256), generator=g, device="cuda")

@@ -101,16 +101,20 @@ def test_non_overlap_constraints_match_reference_fixture(golden_dir):
             if t == 0:
                 continue  # prompt frame: mask prompt exact, box prompt decoded once (covered by t512_two_obj_mask_box)
             _check_low(got["low"][i, o], g["low"][i, o], ("low", t, o))
-        # the yielded masks went through the argmax over objects: where the two objects' logits are closer than the
-        # logit tolerance the winner is noise (random-init objects see nearly the same evidence), elsewhere it must agree
+        # the yielded masks went through the argmax over objects at video resolution: where the two objects' (upsampled)
+        # logits are closer than the logit tolerance the winner is noise -- at random init the objects see nearly the same
+        # evidence -- elsewhere winner and value must agree.  The pre-constraint values are re-derived from the fixture's
+        # low-res logits exactly as the reference does (bilinear to the video size, sam2_video_predictor.py:404-424).
         if t > 0:
             a, b = torch.from_numpy(got["video_s4"][i]), torch.from_numpy(g["video_s4"][i])
-            raw = torch.from_numpy(g["low"][i])  # (video size == 4 x low-res size: stride-4 samples line up with these)
-            decided = (raw[0] - raw[1]).abs() > 4 * LOGIT_TOL
+            up = torch.nn.functional.interpolate(torch.from_numpy(g["low"][i])[:, None], size=(512, 512), mode="bilinear",
+                                                 align_corners=False)[:, 0, ::4, ::4]
+            decided = (up[0] - up[1]).abs() > 2 * LOGIT_TOL
             for o in range(2):
-                assert torch.equal((a[o] > 0) & decided, (b[o] > 0) & decided) or \
-                    float(((a[o] > 0) != (b[o] > 0))[decided].float().mean()) < 5e-3, ("video", t, o)
-                assert float((a[o] - b[o]).abs()[decided & (b[o] > -5) & (a[o] > -5)].max()) <= 4 * LOGIT_TOL
+                flips = ((a[o] > 0) != (b[o] > 0)) & decided
+                assert float(flips.float().sum()) <= 0.005 * float(decided.float().sum()) + 1, ("video", t, o)
+                both = decided & (a[o] > -9) & (b[o] > -9)  # kept (unclamped) on both sides
+                assert float((a[o] - b[o]).abs()[both].max()) <= LOGIT_TOL, ("video value", t, o)
     err = np.abs(got["maskmem_last"] - g["maskmem_last"])
     assert err.max() < 0.25
     # the constraint changes the memory: without it the last memory is clearly further from the fixture's

@@ -246,20 +246,27 @@ def test_jpeg_folder_ingest_matches_reference(tmp_path):
     from PIL import Image
 
     from oracle.ref_loader import reference_available
-    from us_video_medsam2_b200.frames import load_video_frames
+    from us_video_medsam2_b200.frames import decode_jpeg_folder, list_jpeg_frames, load_video_frames
+    from us_video_medsam2_b200.synth import IMG_MEAN, IMG_STD
 
     rng = np.random.default_rng(3)
     for i in range(3):
         arr = (rng.random((37, 53, 3)) * 255).astype(np.uint8)
         Image.fromarray(arr).save(tmp_path / f"{i:05d}.jpg", quality=95)
     Image.fromarray((rng.random((37, 53)) * 255).astype(np.uint8)).save(tmp_path / "00003.jpg")  # grayscale frame
-    images, h, w = load_video_frames(str(tmp_path), 64, True, torch.device("cpu"))
-    assert images.shape == (4, 3, 64, 64) and images.dtype == torch.float32 and (h, w) == (37, 53)
+    # host half (decode + resize into uint8); the device half (usvm_normalize_rgb_u8) is held to the same reference
+    # output in tests/test_gpu_e2e.py::test_jpeg_folder_ingest_on_device
+    rgb, h, w = decode_jpeg_folder(str(tmp_path), 64)
+    assert rgb.shape == (4, 64, 64, 3) and rgb.dtype == torch.uint8 and (h, w) == (37, 53)
+    mean, std = torch.tensor(IMG_MEAN)[:, None, None], torch.tensor(IMG_STD)[:, None, None]
+    images = (torch.from_numpy(rgb.numpy() / 255.0).permute(0, 3, 1, 2).float() - mean) / std
     with pytest.raises(NotImplementedError):
-        load_video_frames(str(tmp_path / "clip.mp4"), 64, True, torch.device("cpu"))
+        list_jpeg_frames(str(tmp_path / "clip.mp4"))
     with pytest.raises(RuntimeError):
         (tmp_path / "empty").mkdir()
-        load_video_frames(str(tmp_path / "empty"), 64, True, torch.device("cpu"))
+        list_jpeg_frames(str(tmp_path / "empty"))
+    with pytest.raises(RuntimeError, match="no CPU path"):  # the product path needs the GPU: it must say so, not fall back
+        load_video_frames(str(tmp_path), 64, True, compute_device=torch.device("cpu"))
     if not reference_available():
         pytest.skip("reference tree not mounted: shape / error behaviour checked only")
     import subprocess

@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out/checks
 files=("$@")
-if [ ${#files[@]} -eq 0 ]; then files=(tests/test_gpu_cc.py tests/test_gpu_gemm.py tests/test_gpu_attention.py tests/test_gpu_elementwise.py tests/test_gpu_parity_r2.py tests/test_gpu_modules.py tests/test_gpu_e2e.py tests/test_gpu_etam.py); fi
+if [ ${#files[@]} -eq 0 ]; then files=(tests/test_gpu_cc.py tests/test_gpu_gemm.py tests/test_gpu_attention.py tests/test_gpu_elementwise.py tests/test_gpu_modules.py tests/test_gpu_e2e.py tests/test_gpu_etam.py tests/test_gpu_parity_r2.py); fi
 : > gpurun_out/checks/summary.txt
 for f in "${files[@]}"; do
   name=$(basename "$f" .py)

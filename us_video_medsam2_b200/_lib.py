@@ -94,6 +94,7 @@ _SIGNATURES = {
     "usvm_im2col_patch": [_P, _P, _I, _I, _I, _P],
     "usvm_im2col_patch_grid": [_P, _P, _I, _I, _I, _P],
     "usvm_normalize_gray_u8": [_P, _P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
+    "usvm_normalize_rgb_u8": [_P, _P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
     "usvm_build_memory": [C.POINTER(MemoryFrames), _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "usvm_conv2d_small": [_P, _P, _P, _P, _P, _F, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "usvm_im2col_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

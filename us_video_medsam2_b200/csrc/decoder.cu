@@ -63,28 +63,50 @@ upscale1_kernel(const float* __restrict__ g1, const float* __restrict__ feat, co
 }
 
 // g2: [B*Hc*Wc, 4*32]; feat_s0: [B, 2Hc, 2Wc, 32]; hyper: [B, 4, 32]; masks: [B, 4, 2Hc, 2Wc]
-__global__ void __launch_bounds__(256)
+// One thread per output pixel: its 32 up-scaled channels are two 128-byte reads (GEMM row segment + feature row), the four
+// hyper-network vectors of the block's object sit in shared memory (broadcast reads), the four mask planes are written
+// coalesced along x.  (A first version gave a warp to each pixel and reduced over the lanes: 20 shuffles per pixel, 171 us
+// for 32 objects against ~75 MB of traffic.)
+constexpr int UP2_THREADS = 128;
+__global__ void __launch_bounds__(UP2_THREADS)
 upscale2_masks_kernel(const float* __restrict__ g2, const float* __restrict__ feat, const float* __restrict__ hyper,
                       int hyper_bs, float* __restrict__ masks, int B, int Hc, int Wc, int feat_group) {
+  __shared__ __align__(16) float hs[128];
   PDL_ENTRY();
-  const int lane = threadIdx.x & 31;
-  const int Ho = 2 * Hc, Wo = 2 * Wc;
-  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (pix >= (long long)B * Ho * Wo) return;
-  const int X = (int)(pix % Wo), Y = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+  const int Ho = 2 * Hc, Wo = 2 * Wc, per_obj = Ho * Wo;
+  const int blocks_per_obj = per_obj / UP2_THREADS;
+  const int b = blockIdx.x / blocks_per_obj;
+  const int p = (blockIdx.x - b * blocks_per_obj) * UP2_THREADS + threadIdx.x;
+  hs[threadIdx.x] = hyper[(long long)b * hyper_bs + threadIdx.x];
+  __syncthreads();
+  const int Y = p / Wo, X = p - Y * Wo;
   const long long src = ((long long)b * Hc + (Y >> 1)) * Wc + (X >> 1);
   const int q = (Y & 1) * 2 + (X & 1);
-  const long long fpix = feat_group > 0 ? ((long long)(b / feat_group) * Ho + Y) * Wo + X : pix;
-  const float v = gelu_erf(g2[src * 128 + q * 32 + lane] + feat[fpix * 32 + lane]);
-  const float* hp = hyper + (long long)b * hyper_bs;
-  const float m0 = warp_sum(v * hp[lane]);
-  const float m1 = warp_sum(v * hp[32 + lane]);
-  const float m2 = warp_sum(v * hp[64 + lane]);
-  const float m3 = warp_sum(v * hp[96 + lane]);
-  if (lane < 4) {
-    const float m = lane == 0 ? m0 : lane == 1 ? m1 : lane == 2 ? m2 : m3;
-    masks[(((long long)b * 4 + lane) * Ho + Y) * Wo + X] = m;
+  const long long fpix = feat_group > 0 ? ((long long)(b / feat_group) * Ho + Y) * Wo + X : (long long)b * per_obj + p;
+  const float4* gp = reinterpret_cast<const float4*>(g2 + src * 128 + q * 32);
+  const float4* fp = reinterpret_cast<const float4*>(feat + fpix * 32);
+  float4 ga[8], fa[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = gp[j];
+    fa[j] = __ldg(fp + j);
   }
+  float m[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float v0 = gelu_erf(ga[j].x + fa[j].x), v1 = gelu_erf(ga[j].y + fa[j].y);
+    const float v2 = gelu_erf(ga[j].z + fa[j].z), v3 = gelu_erf(ga[j].w + fa[j].w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 h = *reinterpret_cast<const float4*>(hs + k * 32 + 4 * j);
+      m[k] = fmaf(v0, h.x, m[k]);
+      m[k] = fmaf(v1, h.y, m[k]);
+      m[k] = fmaf(v2, h.z, m[k]);
+      m[k] = fmaf(v3, h.w, m[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) masks[(((long long)b * 4 + k) * Ho + Y) * Wo + X] = m[k];
 }
 
 // y = L3(relu(L2(relu(L1 x))))  (+ sigmoid); grid (rows, instances); 256 threads; hidden = 256
@@ -231,8 +253,11 @@ extern "C" int usvm_upscale1_ln_gelu(const float* g1, const float* feat_s1, cons
 
 extern "C" int usvm_upscale2_masks(const float* g2, const float* feat_s0, const float* hyper, int hyper_bs,
                                    float* masks, int B, int Hc, int Wc, int feat_group, void* stream) {
-  if (!g2 || !feat_s0 || !hyper || !masks) return USVM_ERR_ARG;
-  usvm_launch(upscale2_masks_kernel, dim3(cdiv((long long)B * 4 * Hc * Wc, 8)), dim3(256), 0, STREAM, g2, feat_s0, hyper, hyper_bs, masks, B, Hc, Wc, feat_group);
+  if (!g2 || !feat_s0 || !hyper || !masks || B <= 0 || ((4 * Hc * Wc) % UP2_THREADS) ||
+      (reinterpret_cast<uintptr_t>(g2) & 15) || (reinterpret_cast<uintptr_t>(feat_s0) & 15))
+    return USVM_ERR_ARG;
+  usvm_launch(upscale2_masks_kernel, dim3(B * (4 * Hc * Wc / UP2_THREADS)), dim3(UP2_THREADS), 0, STREAM, g2, feat_s0, hyper,
+              hyper_bs, masks, B, Hc, Wc, feat_group);
   return usvm_check_launch();
 }
 

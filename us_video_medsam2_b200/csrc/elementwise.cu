@@ -319,6 +319,20 @@ __global__ void normalize_gray_kernel(const uint8_t* __restrict__ g, float* __re
   }
 }
 
+// uint8 RGB frames as PIL decodes them, [F,S,S,3] interleaved -> normalised fp32 planes [F,3,S,S] (misc.py:92-101,
+// 268-276: /255, - mean, / std): one thread per pixel reads 3 bytes, writes one float to each plane (coalesced per plane)
+__global__ void normalize_rgb_kernel(const uint8_t* __restrict__ rgb, float* __restrict__ out, long long frames_px,
+                                     long long px, float m0, float m1, float m2, float s0, float s1, float s2) {
+  PDL_ENTRY();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < frames_px; i += (long long)gridDim.x * blockDim.x) {
+    const long long f = i / px, o = i - f * px;
+    const uint8_t* p = rgb + i * 3;
+    out[(f * 3 + 0) * px + o] = ((float)p[0] / 255.0f - m0) / s0;
+    out[(f * 3 + 1) * px + o] = ((float)p[1] / 255.0f - m1) / s1;
+    out[(f * 3 + 2) * px + o] = ((float)p[2] / 255.0f - m2) / s2;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Memory-bank assembly (sam2_base.py:1344-1437): for every selected memory frame f (token-major bf16
 // [B, T, 64]) write  k_in = mem + pos + tpos[f]  and  v_in = mem  into the concatenated key/value
@@ -598,6 +612,15 @@ extern "C" int usvm_normalize_gray_u8(const uint8_t* gray, float* out, int F, in
   const long long px = (long long)H * W;
   usvm_launch(normalize_gray_kernel, dim3(grid_for(F * px)), dim3(256), 0, STREAM, gray, out, F * px, px, mean3[0], mean3[1], mean3[2],
                                                               std3[0], std3[1], std3[2]);
+  return usvm_check_launch();
+}
+
+extern "C" int usvm_normalize_rgb_u8(const uint8_t* rgb, float* out, int F, int H, int W, const float* mean3,
+                                     const float* std3, void* stream) {
+  if (!rgb || !out || !mean3 || !std3 || F <= 0 || H <= 0 || W <= 0) return USVM_ERR_ARG;
+  const long long px = (long long)H * W;
+  usvm_launch(normalize_rgb_kernel, dim3(grid_for(F * px)), dim3(256), 0, STREAM, rgb, out, F * px, px, mean3[0], mean3[1],
+              mean3[2], std3[0], std3[1], std3[2]);
   return usvm_check_launch();
 }
 

@@ -762,9 +762,16 @@ class Engine:
                 self._handoff(tok, img_s, img)
             o = ops.attn_t2i(q, img[:, 0:128], img[:, 128:256], B, Nt, T)
             pre = sk(o, *t2i["o"], residual=queries)
-            queries = torch.empty_like(pre)
-            m = sk(pre, *Lyr["mlp"][0], act=ACT_RELU, ln=lnp(Lyr["norms"][1]), ln_out=queries)       # norm2 on load
-            pre = sk(m, *Lyr["mlp"][1], residual=queries)
+            if B * Nt >= 64:
+                # many objects (lock-step videos): the skinny kernel re-streams the 2 x 2 MB of MLP weights once per 8
+                # rows; from 64 rows on the tiled fp32 GEMM (weights read once per 64-row tile) is the better kernel
+                queries = ln(pre, Lyr["norms"][1])
+                m = ops.gemm_f32(queries, *Lyr["mlp"][0], act=ACT_RELU)
+                pre = ops.gemm_f32(m, *Lyr["mlp"][1], residual=queries)
+            else:
+                queries = torch.empty_like(pre)
+                m = sk(pre, *Lyr["mlp"][0], act=ACT_RELU, ln=lnp(Lyr["norms"][1]), ln_out=queries)       # norm2 on load
+                pre = sk(m, *Lyr["mlp"][1], residual=queries)
             queries = torch.empty_like(pre)
             kv2 = sk(pre, i2t["kv_w"], i2t["kv_b"], x2=tokens, x2_cols=128, ln=lnp(Lyr["norms"][2]),  # norm3 on load
                      ln_out=queries)  # [k (with pe) | v]

@@ -4,7 +4,8 @@
 the kernel engine).  The compute is the same as a prompted first frame of the video path: image encoder, `+ no_mem_embed`
 (directly_add_no_mem_embed, sam2_image_predictor.py:117-121), prompt encoder (points / box corners as labelled points /
 dense mask input), two-way mask decoder with all 3 multimask outputs or the single-mask output, then
-`SAM2Transforms.postprocess_masks`.  Not mirrored: `set_image_batch` / `predict_batch`, `from_pretrained`."""
+`SAM2Transforms.postprocess_masks`.  `set_image_batch` / `predict_batch` (reference :134-236) encode all images in one
+batched (frame-parallel) encoder pass and predict image by image, as the reference does.  Not mirrored: `from_pretrained`."""
 import numpy as np
 import torch
 
@@ -50,9 +51,51 @@ class SAM2ImagePredictor:
         self._features = dict(pix=pix, feat_s0=f["feat_s0"][0], feat_s1=f["feat_s1"][0])
         self._is_image_set = True
 
+    @torch.no_grad()
+    def set_image_batch(self, image_list):
+        """image_list: list of HWC uint8 numpy arrays (RGB) (reference :134-175): one batched encoder pass."""
+        self.reset_predictor()
+        assert isinstance(image_list, list)
+        self._orig_hw = []
+        for image in image_list:
+            assert isinstance(image, np.ndarray), "Images are expected to be an np.ndarray in RGB format, and of shape  HWC"
+            self._orig_hw.append(image.shape[:2])
+        x = torch.stack([self._transforms(im) for im in image_list]).to(self.device).float().contiguous()
+        assert x.dim() == 4 and x.shape[1] == 3, f"img_batch must be of size Bx3xHxW, got {x.shape}"
+        eng = self.model._sync_engine()
+        f = eng.encode_frames(x)
+        n = x.shape[0]
+        pix, _ = ops.axpby(f["feat"].view(n * 1024, 256), eng.w.no_mem_embed, rows=n * 1024, y_mod=1)  # + no_mem_embed
+        self._features = [dict(pix=pix[i * 1024:(i + 1) * 1024], feat_s0=f["feat_s0"][i], feat_s1=f["feat_s1"][i])
+                          for i in range(n)]
+        self._is_image_set = True
+        self._is_batch = True
+
+    def predict_batch(self, point_coords_batch=None, point_labels_batch=None, box_batch=None, mask_input_batch=None,
+                      multimask_output=True, return_logits=False, normalize_coords=True):
+        """Per-image `predict` over the batch set by `set_image_batch` -> (list of masks, list of ious, list of low-res
+        logits) (reference :177-236)."""
+        assert self._is_batch, "This function should only be used when in batched mode"
+        if not self._is_image_set:
+            raise RuntimeError("An image must be set with .set_image_batch(...) before mask prediction.")
+        all_masks, all_ious, all_low = [], [], []
+        for img_idx in range(len(self._features)):
+            pick = lambda batch: batch[img_idx] if batch is not None else None
+            mask_input, coords, labels, ubox = self._prep_prompts(pick(point_coords_batch), pick(point_labels_batch),
+                                                                   pick(box_batch), pick(mask_input_batch),
+                                                                   normalize_coords, img_idx=img_idx)
+            masks, iou, low = self._predict(coords, labels, ubox, mask_input, multimask_output,
+                                            return_logits=return_logits, img_idx=img_idx)
+            all_masks.append(masks.squeeze(0).float().cpu().numpy())
+            all_ious.append(iou.squeeze(0).float().cpu().numpy())
+            all_low.append(low.squeeze(0).float().cpu().numpy())
+        return all_masks, all_ious, all_low
+
     def get_image_embedding(self):
         if not self._is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) to generate an embedding.")
+        if self._is_batch:
+            return torch.stack([f["pix"].t().reshape(256, 32, 32) for f in self._features])
         return self._features["pix"].t().reshape(1, 256, 32, 32)
 
     def predict(self, point_coords=None, point_labels=None, box=None, mask_input=None, multimask_output=True,
@@ -60,6 +103,7 @@ class SAM2ImagePredictor:
         """-> (masks [C,H,W], iou predictions [C], low-res logits [C,S/4,S/4]) as numpy arrays (reference :238-305)."""
         if not self._is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
+        assert not self._is_batch, "use predict_batch after set_image_batch"
         mask_input, coords, labels, ubox = self._prep_prompts(point_coords, point_labels, box, mask_input, normalize_coords)
         masks, iou, low = self._predict(coords, labels, ubox, mask_input, multimask_output, return_logits=return_logits)
         return (masks.squeeze(0).float().cpu().numpy(), iou.squeeze(0).float().cpu().numpy(),
@@ -108,7 +152,7 @@ class SAM2ImagePredictor:
             if tuple(m.shape[-2:]) != (128, 128):
                 m = ops.resize_bilinear_aa(m.contiguous(), 128, 128)
             dense = eng.embed_mask_prompt(m.contiguous(), B)
-        f = self._features
+        f = self._features[img_idx] if self._is_batch else self._features
         pix = f["pix"] if B == 1 else f["pix"].repeat(B, 1)
         o = eng.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, sparse, dense=dense, multimask=multimask_output)
         if multimask_output:

@@ -145,7 +145,9 @@ class SAM2VideoPredictor(nn.Module):
         """Initialize an inference state from a JPEG folder (reference :44-111)."""
         from .frames import load_video_frames
 
-        images, vh, vw = load_video_frames(video_path, self.image_size, offload_video_to_cpu, self.device)
+        self._sync_engine()
+        images, vh, vw = load_video_frames(video_path, self.image_size, offload_video_to_cpu,
+                                           async_loading_frames=async_loading_frames, compute_device=self.device)
         return self._new_state(images, vh, vw, offload_video_to_cpu, offload_state_to_cpu)
 
     def _new_state(self, images, video_height, video_width, offload_video_to_cpu, offload_state_to_cpu):
