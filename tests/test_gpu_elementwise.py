@@ -468,3 +468,21 @@ def test_im2col_patch_grid_matches_relayout():
     got = ops.im2col_patch_grid(img, 16)
     want = img.view(3, 3, 4, 16, 4, 16).permute(0, 2, 4, 1, 3, 5).reshape(3 * 16, 768).to(torch.bfloat16)
     assert torch.equal(got, want)
+
+
+def test_gelu_epilogue_is_fp32_accurate():
+    """The GELU of every fused epilogue (common.cuh: erfc by Abramowitz-Stegun 7.1.26 on the FMA pipe + rcp / ex2) against
+    the exact erf form in float64 over [-12, 12]: within fp32 rounding of nn.GELU (torch's own fp32 kernel errs by 1.2e-6)."""
+    from us_video_medsam2_b200 import ops
+
+    n = 64 * 32768
+    x = torch.linspace(-12.0, 12.0, n, device="cuda", dtype=torch.float64).float().view(-1, 64).contiguous()
+    eye = torch.eye(64, device="cuda")
+    got = ops.gemm_f32(x, eye, act=ops.ACT_GELU).double()
+    want = F.gelu(x.double())
+    err = (got - want).abs()
+    assert err.max().item() < 1e-6, err.max().item()
+    # relative accuracy where the value is not negligible (the negative tail has no 1 - erf cancellation)
+    m = want.abs() > 1e-4
+    assert (err[m] / want[m].abs()).max().item() < 2e-5
+    assert (got - F.gelu(x).double()).abs().max().item() < 2.5e-6  # vs torch's fp32 kernel

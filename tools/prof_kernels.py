@@ -76,7 +76,9 @@ if which == "batched":  # 8 videos x 4 objects in lock-step, no CUDA graphs: eve
 if which == "r2set":  # round-2 `ncu --set full` set: throughput GEMM shapes + the kernels VERDICT r1 asked counters for
     f32 = torch.float32
 
-    def gemm(M, N, K, act=0, rope=None, f32out=False, res=False, reps=3):
+    REPS = int(os.environ.get("R2SET_REPS", "3"))
+
+    def gemm(M, N, K, act=0, rope=None, f32out=False, res=False, reps=REPS):
         a, w, b = rnd(M, K), rnd(N, K, sc=K ** -0.5), rnd(N, dt=f32)
         r = rnd(M, N, dt=f32) if res else None
         for _ in range(reps):
@@ -93,7 +95,7 @@ if which == "r2set":  # round-2 `ncu --set full` set: throughput GEMM shapes + t
     # Hiera global attention, 8 frames x 4 heads of 96 over 1024 tokens (fmha_bf16_kernel<96>)
     Fr, T, C, H = 8, 1024, 384, 4
     qkv = rnd(Fr * T, 3 * C)
-    for _ in range(3):
+    for _ in range(REPS):
         ops.fmha(qkv, qkv, qkv, Fr, H, T, T, 96, (0, T * 3 * C, 3 * C, 96), (C, T * 3 * C, 3 * C, 96),
                  (2 * C, T * 3 * C, 3 * C, 96))
     # memory-encoder depthwise 7x7 + LayerNorm at 1 and 32 objects, hole filling at 1 and 32 objects
@@ -101,13 +103,13 @@ if which == "r2set":  # round-2 `ncu --set full` set: throughput GEMM shapes + t
         x = rnd(B * 1024, 256, dt=f32)
         dw, db, lw, lb = rnd(49, 256, dt=f32), rnd(256, dt=f32), rnd(256, dt=f32), rnd(256, dt=f32)
         low = rnd(B, 1, 128, 128, dt=f32, sc=0.07)
-        for _ in range(3):
+        for _ in range(REPS):
             ops.dwconv7_ln(x, dw, db, lw, lb, B, 32, 32)
             ops.fill_holes(low, 8)
     # cross-attention at 32 objects (no split) -- the roofline kernel at the batched shape
     B, T, Nk, D = 32, 1024, 7232, 256
     q, kv = rnd(B * T, D), rnd(B * Nk, 4 * D)
-    for _ in range(3):
+    for _ in range(REPS):
         ops.fmha(q, kv, kv, B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D))
 torch.cuda.synchronize()
 print("done")

@@ -433,6 +433,8 @@ ptr_tpos_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restric
   }
 }
 
+// 8 channels per thread: one 16-byte bf16 load of the stored memory (or two float4 of a pointer token), four float4 of
+// position tables, two 16-byte stores (the scalar version moved 2 bytes per access: 89 us for 32 objects, 90 MB)
 __global__ void build_memory_store_kernel(const usvm_frame_ctrl* __restrict__ ctrl, const float* __restrict__ pos,
                                           const float* __restrict__ tpos, const float* __restrict__ ptr_pos,
                                           bf16* __restrict__ k_in, bf16* __restrict__ v_in, int B, int T, int Cm,
@@ -443,24 +445,41 @@ __global__ void build_memory_store_kernel(const usvm_frame_ctrl* __restrict__ ct
   const long long mem_frame_stride = ctrl->mem_slot_stride, ptr_frame_stride = ctrl->ptr_slot_stride;
   const int ptr_row0 = n_mem * T;
   const int Nk = ptr_row0 + n_ptr * 4;
-  const long long total = (long long)B * Nk * Cm;
+  const int C8 = Cm >> 3;
+  const long long total = (long long)B * Nk * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % Cm);
-    const long long t = i / Cm;
+    const int c = (int)(i % C8) << 3;
+    const long long t = i / C8;
     const int row = (int)(t % Nk);
     const int b = (int)(t / Nk);
-    float m, pe;
+    float m[8], pe[8];
     if (row < ptr_row0) {
       const int f = row / T, tok = row - f * T;
-      m = __bfloat162float(mem_store[(long long)ctrl->mem_frame[f] * mem_frame_stride + ((long long)b * T + tok) * Cm + c]);
-      pe = pos[tok * Cm + c] + tpos[ctrl->mem_tpos[f] * Cm + c];
+      const uint4 u = *reinterpret_cast<const uint4*>(mem_store + (long long)ctrl->mem_frame[f] * mem_frame_stride +
+                                                      ((long long)b * T + tok) * Cm + c);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      m[0] = a0.x; m[1] = a0.y; m[2] = a1.x; m[3] = a1.y; m[4] = a2.x; m[5] = a2.y; m[6] = a3.x; m[7] = a3.y;
+      const float4* pp = reinterpret_cast<const float4*>(pos + tok * Cm + c);
+      const float4* tp = reinterpret_cast<const float4*>(tpos + ctrl->mem_tpos[f] * Cm + c);
+      const float4 p0 = __ldg(pp), p1 = __ldg(pp + 1), t0 = __ldg(tp), t1 = __ldg(tp + 1);
+      pe[0] = p0.x + t0.x; pe[1] = p0.y + t0.y; pe[2] = p0.z + t0.z; pe[3] = p0.w + t0.w;
+      pe[4] = p1.x + t1.x; pe[5] = p1.y + t1.y; pe[6] = p1.z + t1.z; pe[7] = p1.w + t1.w;
     } else {
       const int pr = row - ptr_row0;  // pointer p = pr / 4 contributes channels [(pr % 4) * Cm, +Cm)
-      m = ptr_store[(long long)ctrl->ptr_frame[pr >> 2] * ptr_frame_stride + (long long)b * (4 * Cm) + (pr & 3) * Cm + c];
-      pe = ptr_pos[pr * Cm + c];
+      const float4* mp = reinterpret_cast<const float4*>(ptr_store + (long long)ctrl->ptr_frame[pr >> 2] * ptr_frame_stride +
+                                                         (long long)b * (4 * Cm) + (pr & 3) * Cm + c);
+      const float4* pp = reinterpret_cast<const float4*>(ptr_pos + pr * Cm + c);
+      const float4 m0 = mp[0], m1 = mp[1], p0 = pp[0], p1 = pp[1];
+      m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+      pe[0] = p0.x; pe[1] = p0.y; pe[2] = p0.z; pe[3] = p0.w; pe[4] = p1.x; pe[5] = p1.y; pe[6] = p1.z; pe[7] = p1.w;
     }
-    k_in[i] = __float2bfloat16(m + pe);
-    v_in[i] = __float2bfloat16(m);
+    uint4 ko, vo;
+    ko.x = pack_bf16x2(m[0] + pe[0], m[1] + pe[1]); ko.y = pack_bf16x2(m[2] + pe[2], m[3] + pe[3]);
+    ko.z = pack_bf16x2(m[4] + pe[4], m[5] + pe[5]); ko.w = pack_bf16x2(m[6] + pe[6], m[7] + pe[7]);
+    vo.x = pack_bf16x2(m[0], m[1]); vo.y = pack_bf16x2(m[2], m[3]);
+    vo.z = pack_bf16x2(m[4], m[5]); vo.w = pack_bf16x2(m[6], m[7]);
+    *reinterpret_cast<uint4*>(k_in + i * 8) = ko;
+    *reinterpret_cast<uint4*>(v_in + i * 8) = vo;
   }
 }
 
@@ -661,7 +680,7 @@ extern "C" int usvm_build_memory_store(const usvm_frame_ctrl* ctrl_dev, const fl
       n_ptr > USVM_MAX_PTRS || Cm != 64)
     return USVM_ERR_ARG;
   if (n_ptr > 0 && !ptr_pos) return USVM_ERR_ARG;
-  const long long total = (long long)B * (n_mem * T + n_ptr * 4) * Cm;
+  const long long total = (long long)B * (n_mem * T + n_ptr * 4) * (Cm / 8);
   if (total <= 0) return USVM_ERR_ARG;
   usvm_launch(build_memory_store_kernel, dim3(grid_for(total)), dim3(256), 0, STREAM, 
       ctrl_dev, pos, tpos, ptr_pos, reinterpret_cast<bf16*>(k_in), reinterpret_cast<bf16*>(v_in), B, T, Cm, n_mem, n_ptr);
