@@ -109,10 +109,17 @@ def test_non_overlap_constraints_match_reference_fixture(golden_dir):
             a, b = torch.from_numpy(got["video_s4"][i]), torch.from_numpy(g["video_s4"][i])
             up = torch.nn.functional.interpolate(torch.from_numpy(g["low"][i])[:, None], size=(512, 512), mode="bilinear",
                                                  align_corners=False)[:, 0, ::4, ::4]
-            decided = (up[0] - up[1]).abs() > 2 * LOGIT_TOL
+            # Compared where the inputs of the constraint agree: each object's logits are within LOGIT_TOL of the
+            # reference's except around a hole filled on one side only (a rewrite to 0.1 at a threshold); there the winner
+            # may legitimately differ, elsewhere a margin of 4 x LOGIT_TOL between the objects decides it on both sides.
+            up_mine = torch.nn.functional.interpolate(torch.from_numpy(got["low"][i])[:, None], size=(512, 512),
+                                                      mode="bilinear", align_corners=False)[:, 0, ::4, ::4]
+            agree = ((up_mine - up).abs() <= 2 * LOGIT_TOL).all(dim=0)
+            decided = ((up[0] - up[1]).abs() > 4 * LOGIT_TOL) & agree
+            assert float(agree.float().mean()) > 0.9
             for o in range(2):
-                flips = ((a[o] > 0) != (b[o] > 0)) & decided
-                assert float(flips.float().sum()) <= 0.02 * float(decided.float().sum()) + 1, ("video", t, o)
+                clear = decided & (up[o].abs() > 2 * LOGIT_TOL)
+                assert not bool((((a[o] > 0) != (b[o] > 0)) & clear).any()), ("video", t, o)
             # ... and exactly: the yielded masks are the constraint applied to this path's own upsampled stored masks
             from us_video_medsam2_b200 import ops
             mine = ops.resize_bilinear(torch.from_numpy(got["low"][i])[:, None].cuda().contiguous(), 512, 512)

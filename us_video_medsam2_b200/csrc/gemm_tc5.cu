@@ -46,6 +46,8 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most one bulk group (the previous column block's stores) may still be reading shared memory
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -468,12 +470,16 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int P_THREADS = 320;
 constexpr int P_EPI_WARPS = 8;
-constexpr int P_STG_BYTES = P_EPI_WARPS * (STG_F32 + STG_BF16);
+// staging: per epilogue warp TWO buffers of one 32 x 32 block per output present (fp32 4 KB, bf16 2 KB), so the TMA store
+// of block i still reads its buffer while block i + 1 is being computed and written -- the wait for a store's shared-memory
+// read (~1 us after issue) used to sit between every two column blocks of a warp
+__host__ __device__ constexpr int p_stg_per_buf(bool f32, bool b16) { return (f32 ? STG_F32 : 0) + (b16 ? STG_BF16 : 0); }
+__host__ __device__ constexpr int p_stg_bytes(bool f32, bool b16) { return P_EPI_WARPS * 2 * p_stg_per_buf(f32, b16); }
 constexpr int P_A_BYTES = BM * BK * 2;
 
 __host__ __device__ constexpr int p_stage_bytes(int bn) { return P_A_BYTES + bn * BK * 2; }
-__host__ __device__ constexpr int p_smem_total(int bn, int stages) {
-  return stages * p_stage_bytes(bn) + P_STG_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+__host__ __device__ constexpr int p_smem_total(int bn, int stages, bool f32, bool b16) {
+  return stages * p_stage_bytes(bn) + p_stg_bytes(f32, b16) + 1024 /* alignment slack */ + 256 /* barriers */;
 }
 
 __global__ void __launch_bounds__(P_THREADS, 1)
@@ -485,7 +491,8 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = p_stage_bytes(BN);
   uint8_t* staging = smem + stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + P_STG_BYTES);
+  const int stg_per_buf = p_stg_per_buf(ep.out_f32 != nullptr, ep.out_bf16 != nullptr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + P_EPI_WARPS * 2 * stg_per_buf);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;
   uint64_t* acc_empty = acc_full + 2;
@@ -566,9 +573,9 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
     const int ew = warp - 2;        // 0..7
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
     const int half = ew >> 2;       // which 32-column blocks of the tile: half, half+2, ...
-    uint8_t* stg32 = staging + ew * STG_F32;
-    uint8_t* stg16 = staging + P_EPI_WARPS * STG_F32 + ew * STG_BF16;
-    bool pending = false;
+    uint8_t* stg_warp = staging + ew * 2 * stg_per_buf;  // two buffers: [fp32 block | bf16 block] each
+    const int stg16_off = ep.out_f32 ? STG_F32 : 0;
+    uint32_t nstored = 0;  // column blocks this warp has handed to TMA so far (buffer = nstored & 1)
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
@@ -634,8 +641,10 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
           kind = kind_next;
 #pragma unroll
           for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-          if (pending) {
-            if (lane == 0) tma_store_wait_read();
+          uint8_t* stg32 = stg_warp + (nstored & 1u) * stg_per_buf;
+          uint8_t* stg16 = stg32 + stg16_off;
+          if (nstored >= 2) {  // the store issued two blocks ago has finished reading this buffer
+            if (lane == 0) tma_store_wait_read1();
             __syncwarp();
           }
           if (ep.out_f32) {
@@ -664,7 +673,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             if (ep.out_bf16) tma_store_2d(&tmO16, stg16, col0, row0);
             tma_store_commit();
           }
-          pending = true;
+          ++nstored;
         }
       }
       // all of this warp's TMEM reads of `buf` are complete (wait::ld above): hand the accumulator back
@@ -672,7 +681,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-    if (pending && lane == 0) tma_store_wait_read();
+    if (nstored && lane == 0) tma_store_wait_read();
     __syncwarp();
   }
   tc5_fence_before();
@@ -833,12 +842,13 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
       return USVM_ERR_CUDA;
   }
   int stages = STAGES;
-  while (stages > 1 && p_smem_total(bn, stages) > 227 * 1024) --stages;
+  const bool o32 = ep->out_f32 != nullptr, o16 = ep->out_bf16 != nullptr;
+  while (stages > 1 && p_smem_total(bn, stages, o32, o16) > 227 * 1024) --stages;
   const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn);
   const int num_tiles = tiles_m * tiles_n;
   const int sm_limit = (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
   const int grid = num_tiles < sm_limit ? num_tiles : sm_limit;
-  usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, stages), stream, tmA, tmB,
+  usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, stages, o32, o16), stream, tmA, tmB,
               tmO32, tmO16, *ep, M, N, K, bn, stages, tiles_n, num_tiles);
   return usvm_check_launch();
 }

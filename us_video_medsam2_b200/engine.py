@@ -767,7 +767,9 @@ class Engine:
                 # rows; from 64 rows on the tiled fp32 GEMM (weights read once per 64-row tile) is the better kernel
                 queries = ln(pre, Lyr["norms"][1])
                 m = ops.gemm_f32(queries, *Lyr["mlp"][0], act=ACT_RELU)
-                pre = ops.gemm_f32(m, *Lyr["mlp"][1], residual=queries)
+                # (K = 2048 on 16 tiles of the SIMT kernel is a 110 us serial reduction: tf32 tensor-core products here,
+                # like the decoder's image side)
+                pre = ops.gemm_f32(m, *Lyr["mlp"][1], residual=queries, tf32=_DEC_TF32)
             else:
                 queries = torch.empty_like(pre)
                 m = sk(pre, *Lyr["mlp"][0], act=ACT_RELU, ln=lnp(Lyr["norms"][1]), ln_out=queries)       # norm2 on load
