@@ -63,8 +63,10 @@ typedef struct usvm_gemm_epilogue {
   int ldo_bf16;
   /* optional fused axial RoPE (position_encoding.py:194-221) on output columns [0, rope_cols): applied after the bias
    * to adjacent column pairs of rows whose index inside their batch of rope_rows_per_batch is < rope_n_rope, with
-   * table row (index % rope_table_rows) and table column ((col % 256) / 2); tables fp32 [rope_table_rows, 128].
-   * tensor-core kernel only; rope_cos == NULL disables it */
+   * table row pos = (index % rope_table_rows) and table column tc = ((col % 256) / 2).  The tables hold
+   * rope_table_rows x 128 fp32 values in a TILED order, element (pos, tc) at
+   * ((pos / 32) * 32 + tc / 4) * 128 + (pos % 32) * 4 + tc % 4  (rope_table_rows % 32 == 0): the 32 accumulator rows an
+   * epilogue warp owns then read contiguous memory.  tensor-core kernel only; rope_cos == NULL disables it */
   const float* rope_cos;
   const float* rope_sin;
   int rope_cols, rope_rows_per_batch, rope_n_rope, rope_table_rows;

@@ -205,3 +205,34 @@ def test_tc5_gemm_cluster_split_k(M, N, K):
     assert (o16.float() - want).abs().max().item() < 3e-2
     again, _ = ops.gemm_bf16(a, w, bias=bias, act=1, residual=res, f32=True, simt=False)
     assert torch.equal(o32, again)  # slices are added in a fixed order
+
+
+@pytest.mark.parametrize("M,rows_per_batch,n_rope,N,cols,K", [
+    (1024, 1024, 1024, 768, 512, 256),          # one-object qkv projection (one-tile kernel, prefetched tables)
+    (2 * 7232, 7232, 7168, 1024, 1024, 64),     # bank key projection, 2 objects: pointer rows unrotated
+    (3 * 7180, 7180, 7168, 1024, 1024, 64),     # 3 pointers: rows per object not a multiple of 32 (lanes straddle objects)
+    (32768, 1024, 1024, 768, 512, 256),         # 32 objects: persistent kernel, tables fetched one block ahead
+])
+def test_fused_rope_epilogue_matches_rope_kernel(M, rows_per_batch, n_rope, N, cols, K):
+    """RoPE fused into the GEMM epilogue (tiled tables, ops.tile_rope_table) against the stand-alone rotation kernel
+    applied to the un-rotated fp32 GEMM output (row-major tables), both kernels of usvm_gemm_bf16_tc5."""
+    from us_video_medsam2_b200 import ops
+    from us_video_medsam2_b200.engine import _rope_tables
+
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = torch.randn((M, K), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g, device="cuda")
+    c, s = _rope_tables(256, 32, 32)
+    c, s = c.cuda(), s.cuda()
+    _, got = ops.gemm_bf16(a, w, bias=bias, bf16=True,
+                           rope=(ops.tile_rope_table(c), ops.tile_rope_table(s), cols, rows_per_batch, n_rope))
+    plain, _ = ops.gemm_bf16(a, w, bias=bias, f32=True)
+    want = plain.to(torch.bfloat16).clone()
+    for c0 in range(0, cols, 256):
+        want[:, c0:c0 + 256] = ops.rope(plain, c0, c, s, rows_per_batch, n_rope)
+    # both round (nearly) the same fp32 value to bf16: they may land one bf16 ulp (2^-7 relative) apart, not more
+    d = (got.float() - want.float()).abs()
+    assert bool((d <= 2.0 ** -7 * want.float().abs().clamp_min(1.0)).all()), d.max().item()
+    assert (d > 0).float().mean().item() < 0.02  # ... and only where the fp32 value sits on a rounding boundary
+    assert torch.equal(got[:, cols:], plain[:, cols:].to(torch.bfloat16))  # columns beyond rope_cols untouched

@@ -37,7 +37,7 @@ def case(name, M, N, K, act=0, rope=False, f32out=False, res=False, bf16out=True
     r = rnd(M, N, dt=f32) if res else None
     rp = None
     if rope:
-        cs, sn = rnd(1024, 128, dt=f32), rnd(1024, 128, dt=f32)
+        cs, sn = ops.tile_rope_table(rnd(1024, 128, dt=f32)), ops.tile_rope_table(rnd(1024, 128, dt=f32))
         rp = (cs, sn, min(N, 1024) if N >= 512 else N, M, M)
     o32 = torch.empty((M, N), dtype=f32, device=dev) if f32out else None
     o16 = torch.empty((M, N), dtype=torch.bfloat16, device=dev) if bf16out else None

@@ -89,7 +89,7 @@ if which == "r2set":  # round-2 `ncu --set full` set: throughput GEMM shapes + t
     gemm(131072, 384, 96, act=ops.ACT_GELU)    # encoder stage-1 MLP up-projection (HBM heavy)
     gemm(8192, 384, 1536, f32out=True, res=True)   # encoder stage-3 MLP down-projection + residual -> fp32
     gemm(32768, 2048, 256, act=ops.ACT_RELU)   # memory-attention FFN linear1 at 32 objects
-    cs, sn = rnd(1024, 128, dt=f32), rnd(1024, 128, dt=f32)
+    cs, sn = ops.tile_rope_table(rnd(1024, 128, dt=f32)), ops.tile_rope_table(rnd(1024, 128, dt=f32))
     gemm(32 * 7232, 1024, 64, rope=(cs, sn, 1024, 7232, 7168))  # bank key projection + RoPE at 32 objects
     gemm(1024, 768, 256, rope=(cs, sn, 512, 1024, 1024))        # gemm_bf16_tc5_kernel<32>: one-object qkv projection
     # Hiera global attention, 8 frames x 4 heads of 96 over 1024 tokens (fmha_bf16_kernel<96>)

@@ -70,6 +70,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Rotary tables are stored TILED, [pos / 32][col / 4][pos % 32][col % 4] (fp32, 128 columns per position): in the epilogue
+// a thread owns one position (accumulator row) and needs 16 consecutive table columns, so with a row-major table every
+// 16-byte load of a warp touched 32 different cache lines (256 L1 wavefronts per 32 x 32 block -- the bank key projection
+// ran 380 us against 163 us without the rotation).  Tiled, the 32 lanes of a warp -- 32 consecutive positions -- read 512
+// contiguous bytes per load.  Chunk j of the 16 columns starting at table column tcol0 (a multiple of 16):
+__device__ __forceinline__ const float4* rope_chunk(const float* table, int pos, int tcol0, int j) {
+  return reinterpret_cast<const float4*>(table + ((long long)(pos >> 5) * 32 + (tcol0 >> 2) + j) * 128 + (pos & 31) * 4);
+}
+
 // Fused epilogue of one 32-column block of one accumulator row: bias -> RoPE -> activation -> per-column scale ->
 // residual (skipped when the caller adds a prefetched residual itself).
 __device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_epilogue& ep, const int row,
@@ -93,11 +102,11 @@ __device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_e
     if (ep.rope_cos && col0 < ep.rope_cols) {
       const int rb = row % ep.rope_rows_per_batch;
       if (rb < ep.rope_n_rope) {
-        const long long t0 = (long long)(rb % ep.rope_table_rows) * 128 + ((col0 & 255) >> 1);
+        const int pos = rb % ep.rope_table_rows, tcol0 = (col0 & 255) >> 1;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          const float4 c4 = rope_pre ? rope_pre[j >> 3] : *reinterpret_cast<const float4*>(ep.rope_cos + t0 + (j >> 1));
-          const float4 s4 = rope_pre ? rope_pre[4 + (j >> 3)] : *reinterpret_cast<const float4*>(ep.rope_sin + t0 + (j >> 1));
+          const float4 c4 = rope_pre ? rope_pre[j >> 3] : __ldg(rope_chunk(ep.rope_cos, pos, tcol0, j >> 3));
+          const float4 s4 = rope_pre ? rope_pre[4 + (j >> 3)] : __ldg(rope_chunk(ep.rope_sin, pos, tcol0, j >> 3));
           const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -283,11 +292,11 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (ep.rope_cos && col0 < ep.rope_cols && col0 + 32 <= N) {
         const int rb = row % ep.rope_rows_per_batch;
         if (rb < ep.rope_n_rope) {
-          const long long t0 = (long long)(rb % ep.rope_table_rows) * 128 + ((col0 & 255) >> 1);
+          const int pos = rb % ep.rope_table_rows, tcol0 = (col0 & 255) >> 1;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            rp[j] = __ldg(reinterpret_cast<const float4*>(ep.rope_cos + t0) + j);
-            rp[4 + j] = __ldg(reinterpret_cast<const float4*>(ep.rope_sin + t0) + j);
+            rp[j] = __ldg(rope_chunk(ep.rope_cos, pos, tcol0, j));
+            rp[4 + j] = __ldg(rope_chunk(ep.rope_sin, pos, tcol0, j));
           }
           have_r = true;
         }
@@ -486,7 +495,9 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                                 const usvm_gemm_epilogue ep, const int M, const int N, const int K, const int BN,
-                                const int stages, const int tiles_n, const int num_tiles) {
+                                const int stages_flags, const int tiles_n, const int num_tiles) {
+  const int stages = stages_flags & 0xff;
+  const int dbg = stages_flags >> 8;  // experiment switches (USVM2_PGEMM_DEBUG): 1 = no TMA store, 2 = no staging either
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = p_stage_bytes(BN);
@@ -594,7 +605,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
         // critical path of every block (the bank key projection, K = 64 with RoPE, ran 379 us against 163 us for the
         // same GEMM without the rotation).
         const bool rope_row = ep.rope_cos != nullptr && (row % ep.rope_rows_per_batch) < ep.rope_n_rope;
-        const long long rope_t0 = rope_row ? (long long)((row % ep.rope_rows_per_batch) % ep.rope_table_rows) * 128 : 0;
+        const int rope_pos = rope_row ? (row % ep.rope_rows_per_batch) % ep.rope_table_rows : 0;
         float4 cur[8], nxt[8];
         // kind: 0 nothing, 1 residual, 2 rotary tables
         auto prefetch = [&](int c0, float4 (&dst)[8]) -> int {
@@ -607,11 +618,11 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             return 1;
           }
           if (rope_row && col0 < ep.rope_cols) {
-            const long long t0 = rope_t0 + ((col0 & 255) >> 1);
+            const int tcol0 = (col0 & 255) >> 1;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              dst[j] = __ldg(reinterpret_cast<const float4*>(ep.rope_cos + t0) + j);
-              dst[4 + j] = __ldg(reinterpret_cast<const float4*>(ep.rope_sin + t0) + j);
+              dst[j] = __ldg(rope_chunk(ep.rope_cos, rope_pos, tcol0, j));
+              dst[4 + j] = __ldg(rope_chunk(ep.rope_sin, rope_pos, tcol0, j));
             }
             return 2;
           }
@@ -647,14 +658,14 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             if (lane == 0) tma_store_wait_read1();
             __syncwarp();
           }
-          if (ep.out_f32) {
+          if (ep.out_f32 && !(dbg & 2)) {
             uint8_t* prow = stg32 + lane * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               *reinterpret_cast<float4*>(prow + ((c ^ (lane & 7)) << 4)) =
                   make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
-          if (ep.out_bf16) {
+          if (ep.out_bf16 && !(dbg & 2)) {
             uint8_t* prow = stg16 + lane * 64;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -666,9 +677,15 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
               *reinterpret_cast<uint4*>(prow + (c << 4)) = pk;
             }
           }
+          if (dbg & 2) {  // keep the values alive
+            float keep = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) keep += v[j];
+            if (keep == 1.2345e30f) stg_warp[0] = 1;
+          }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(dbg & 1)) {
             if (ep.out_f32) tma_store_2d(&tmO32, stg32, col0, row0);
             if (ep.out_bf16) tma_store_2d(&tmO16, stg16, col0, row0);
             tma_store_commit();
@@ -798,6 +815,15 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
 // context) so that one CTA per *partition* SM walks the tiles instead of 148 CTAs queueing in waves.
 int g_sm_budget = 0;
 
+int pgemm_debug() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("USVM2_PGEMM_DEBUG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 int persistent_block_n(int N) {
   // the widest multiple of 32 (<= 256) that wastes the fewest padded columns
   int best = 32, best_waste = 1 << 30;
@@ -849,7 +875,7 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
   const int sm_limit = (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
   const int grid = num_tiles < sm_limit ? num_tiles : sm_limit;
   usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, stages, o32, o16), stream, tmA, tmB,
-              tmO32, tmO16, *ep, M, N, K, bn, stages, tiles_n, num_tiles);
+              tmO32, tmO16, *ep, M, N, K, bn, stages | (pgemm_debug() << 8), tiles_n, num_tiles);
   return usvm_check_launch();
 }
 
@@ -869,7 +895,7 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
   if (ep->out_bf16 && ((ep->ldo_bf16 % 8) || (reinterpret_cast<uintptr_t>(ep->out_bf16) & 15))) return USVM_ERR_ARG;
   if (ep->residual && ((ep->ldr % 4) || (reinterpret_cast<uintptr_t>(ep->residual) & 15))) return USVM_ERR_ARG;
   if (ep->rope_cos && (!ep->rope_sin || (N % 32) || (ep->rope_cols % 32) || ep->rope_rows_per_batch <= 0 ||
-                       ep->rope_table_rows <= 0 || (reinterpret_cast<uintptr_t>(ep->rope_cos) & 15) ||
+                       ep->rope_table_rows <= 0 || (ep->rope_table_rows % 32) || (reinterpret_cast<uintptr_t>(ep->rope_cos) & 15) ||
                        (reinterpret_cast<uintptr_t>(ep->rope_sin) & 15)))
     return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

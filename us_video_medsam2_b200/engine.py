@@ -177,7 +177,8 @@ class PackedWeights:
         self.ca_v_all = (dev(torch.cat([g(ca.format(l) + "v_proj.weight") for l in range(4)]), BF16),
                          dev(torch.cat([g(ca.format(l) + "v_proj.bias") for l in range(4)])))
         c, s = _rope_tables(256, 32, 32)
-        self.rope_cos, self.rope_sin = dev(c), dev(s)
+        # (tiled for the GEMM epilogues: 32 consecutive positions x 4 columns contiguous, see ops.tile_rope_table)
+        self.rope_cos, self.rope_sin = ops.tile_rope_table(dev(c)), ops.tile_rope_table(dev(s))
 
         # ---- memory encoder ----
         e = "memory_encoder."

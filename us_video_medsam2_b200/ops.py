@@ -60,9 +60,12 @@ def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16
     if ln is not None:  # (weight, bias, eps[, gelu])
         ep.ln_w, ep.ln_b, ep.ln_eps = ln[0].data_ptr(), ln[1].data_ptr(), ln[2]
         ep.ln_gelu = int(len(ln) > 3 and bool(ln[3]))
-    if rope is not None:  # (cos, sin, cols, rows_per_batch, n_rope)
+    if rope is not None:  # (cos, sin, cols, rows_per_batch, n_rope); tables in the tiled order of tile_rope_table()
+        if rope[0].dim() != 4 or rope[1].dim() != 4:
+            raise ValueError("fused RoPE takes tables laid out by ops.tile_rope_table()")
         ep.rope_cos, ep.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
-        ep.rope_cols, ep.rope_rows_per_batch, ep.rope_n_rope, ep.rope_table_rows = rope[2], rope[3], rope[4], rope[0].shape[0]
+        ep.rope_cols, ep.rope_rows_per_batch, ep.rope_n_rope = rope[2], rope[3], rope[4]
+        ep.rope_table_rows = rope[0].numel() // 128
     ep.bias, ep.col_scale = _ptr(bias), _ptr(col_scale)
     ep.residual = _ptr(residual)
     ep.ldr = residual.stride(0) if residual is not None else 0
@@ -74,6 +77,14 @@ def _epilogue(M, N, bias, act, col_scale, residual, res_mod, want_f32, want_bf16
     ep.out_f32, ep.ldo_f32 = _ptr(out_f32), (out_f32.stride(0) if out_f32 is not None else 0)
     ep.out_bf16, ep.ldo_bf16 = _ptr(out_bf16), (out_bf16.stride(0) if out_bf16 is not None else 0)
     return ep, out_f32, out_bf16
+
+
+def tile_rope_table(t):
+    """Row-major rotary table fp32 [R, 128] (R % 32 == 0) -> the tiled order the GEMM epilogue reads,
+    [R / 32][128 / 4][32][4]: element (pos, tc) at ((pos // 32) * 32 + tc // 4) * 128 + (pos % 32) * 4 + tc % 4."""
+    R, Cc = t.shape
+    assert Cc == 128 and R % 32 == 0
+    return t.view(R // 32, 32, 32, 4).permute(0, 2, 1, 3).contiguous()
 
 
 def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_mod=0, f32=False, bf16=False,
