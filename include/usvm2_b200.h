@@ -40,6 +40,14 @@ int usvm_cc2d_label_u8(const uint8_t* img, int32_t* labels, int32_t* counts, int
 int usvm_fill_holes_f32(const float* scores_in, float* scores_out, int32_t* scratch_labels, int32_t* scratch_counts,
                         int N, int H, int W, int max_area, float fill_value, void* stream);
 
+/* Largest 26-connected component of a binary volume -- the CT driver's post-step
+ * `labels = skimage.measure.label(seg); seg = labels == argmax(bincount(labels.flat)[1:]) + 1`
+ * (medsam2_infer_3D_CT.py:76-79, 285).  vol, out uint8 [D,H,W] (nonzero = foreground; out is 0 / 1, all 0 for an empty
+ * volume); scratch_parent, scratch_count int32 [D,H,W]; scratch_best one 64-bit word.  Ties in area go to the component
+ * whose first voxel in raster order comes first (the lowest skimage label, np.argmax's first maximum). */
+int usvm_cc3d_largest_u8(const uint8_t* vol, uint8_t* out, int32_t* scratch_parent, int32_t* scratch_count,
+                         unsigned long long* scratch_best, int D, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM with fused epilogue:  C[M,N] = epi(A[M,K] . W[N,K]^T)
  * replaces nn.Linear / 1x1 Conv2d / ConvTranspose2d(k2,s2) / im2col convs dispatched to cuBLAS / cuDNN

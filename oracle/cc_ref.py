@@ -97,3 +97,14 @@ def connected_components_emulated(img):
                     labels[n, 0, r, c] = root + 1
                     counts[n, 0, r, c] = area[root]
     return labels, counts
+
+
+def largest_component_3d_ref(seg):
+    """getLargestCC of medsam2_infer_3D_CT.py:76-79 restated with scipy: skimage.measure.label's default connectivity for
+    a 3-D input is full (26 neighbours) and it numbers components in raster order of their first voxel, exactly like
+    scipy.ndimage.label with a 3x3x3 structure; np.argmax takes the first maximum."""
+    seg = np.asarray(seg) != 0
+    labels, k = ndimage.label(seg, structure=np.ones((3, 3, 3), np.int32))
+    if k == 0:
+        return np.zeros(seg.shape, bool)
+    return labels == (np.argmax(np.bincount(labels.ravel())[1:]) + 1)

@@ -201,3 +201,39 @@ def test_postprocess_masks_against_reference_kernel_composition():
     assert got.shape == (2, 3, 300, 420) and torch.equal(got, want)
     pts = torch.tensor([[[210.0, 150.0]]])
     assert torch.allclose(tr.transform_coords(pts, normalize=True, orig_hw=(300, 420)), torch.tensor([[[256.0, 256.0]]]))
+
+
+@pytest.mark.parametrize("shape,density,seed", [((9, 32, 40), 0.3, 0), ((16, 64, 64), 0.12, 1), ((5, 20, 28), 0.6, 2),
+                                                ((64, 128, 128), 0.05, 3), ((1, 16, 16), 0.4, 4)])
+def test_largest_component_3d_matches_scipy(shape, density, seed):
+    """usvm_cc3d_largest_u8 (the CT driver's getLargestCC on the device) bit-exact against the scipy restatement, on
+    random volumes with blobs -- including ties in area (small random components) and 26-connectivity-only links."""
+    from oracle.cc_ref import largest_component_3d_ref
+    from us_video_medsam2_b200.cc import get_largest_cc
+
+    rng = np.random.default_rng(seed)
+    vol = rng.random(shape) < density
+    D, H, W = shape
+    if D > 4:  # two solid blobs touching only through a diagonal voxel pair
+        vol[1:4, 2:8, 2:8] = True
+        vol[4:6, 8:12, 8:12] = True
+    got = get_largest_cc(torch.from_numpy(vol).cuda())
+    assert got.dtype == torch.bool and got.shape == shape
+    assert np.array_equal(got.cpu().numpy(), largest_component_3d_ref(vol))
+
+
+def test_largest_component_3d_edge_cases():
+    from oracle.cc_ref import largest_component_3d_ref
+    from us_video_medsam2_b200.cc import get_largest_cc
+
+    empty = torch.zeros((4, 8, 8), dtype=torch.uint8, device="cuda")
+    assert not bool(get_largest_cc(empty).any())
+    full = torch.ones((3, 6, 10), dtype=torch.uint8, device="cuda")
+    assert bool(get_largest_cc(full).all())
+    tie = np.zeros((3, 8, 8), bool)   # two components of equal size: the one that comes first in raster order wins
+    tie[0, 0:2, 0:2] = True
+    tie[2, 5:7, 5:7] = True
+    got = get_largest_cc(torch.from_numpy(tie).cuda()).cpu().numpy()
+    assert np.array_equal(got, largest_component_3d_ref(tie)) and got[0, 0, 0] and not got[2, 5, 5]
+    with pytest.raises(RuntimeError):
+        get_largest_cc(torch.zeros((4, 8, 8), dtype=torch.uint8))

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "usvm_device_sm": [],
     "usvm_set_sm_budget": [_I],
     "usvm_cc2d_label_u8": [_P, _P, _P, _I, _I, _I, _P],
+    "usvm_cc3d_largest_u8": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "usvm_fill_holes_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "usvm_gemm_bf16_tc5": [_P, _I, _P, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _I, _P],
     "usvm_gemm_tf32_tc5": [_P, _I, _P, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _I, _P],

@@ -302,6 +302,79 @@ fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Largest 3-D component of a binary volume (26-connectivity): the post-step of the reference's CT driver,
+//   labels = skimage.measure.label(seg);  largest = labels == argmax(bincount(labels.flat)[1:]) + 1
+// (medsam2_infer_3D_CT.py:76-79, 285).  Voxel-level union-find in global memory: every foreground voxel unites with its
+// foreground neighbours among the 13 that precede it in raster order (links point to the smaller index, so a root is the
+// component's first voxel in raster order -- the order in which skimage numbers its labels); areas are counted at the
+// roots; the winner is the largest area, ties to the smallest root (np.argmax returns the first maximum).
+// ---------------------------------------------------------------------------------------------
+__global__ void cc3_init(const uint8_t* __restrict__ vol, int32_t* __restrict__ par, int32_t* __restrict__ cnt,
+                         long long n, unsigned long long* best) {
+  PDL_ENTRY();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *best = 0ull;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    par[i] = vol[i] ? (int32_t)i : -1;
+    cnt[i] = 0;
+  }
+}
+__global__ void cc3_merge(const uint8_t* __restrict__ vol, int32_t* par, int D, int H, int W) {
+  PDL_ENTRY();
+  const long long n = (long long)D * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (!vol[i]) continue;
+    const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((long long)W * H));
+    // the 13 neighbours that precede (z, y, x) in raster order
+#pragma unroll
+    for (int dz = -1; dz <= 0; ++dz)
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          if (dz == 0 && (dy > 0 || (dy == 0 && dx >= 0))) continue;
+          const int zz = z + dz, yy = y + dy, xx = x + dx;
+          if (zz < 0 || yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+          const long long j = ((long long)zz * H + yy) * W + xx;
+          if (vol[j]) uf_union(par, (int)i, (int)j);
+        }
+  }
+}
+__global__ void cc3_count(int32_t* par, int32_t* __restrict__ cnt, long long n) {
+  PDL_ENTRY();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (par[i] < 0) continue;
+    const int root = uf_find(par, (int)i);
+    // warp-aggregated: neighbouring voxels mostly share a root
+    const unsigned peers = __match_any_sync(__activemask(), root);
+    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&cnt[root], __popc(peers));
+  }
+}
+// key = area << 32 | (0xffffffff - root): the maximum key is the largest area, ties to the smallest root
+__global__ void cc3_best(const int32_t* __restrict__ par, const int32_t* __restrict__ cnt, long long n,
+                         unsigned long long* best) {
+  PDL_ENTRY();
+  unsigned long long mine = 0ull;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (cnt[i] > 0) {
+      const unsigned long long key = ((unsigned long long)(unsigned)cnt[i] << 32) | (0xffffffffull - (unsigned)i);
+      mine = key > mine ? key : mine;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, o);
+    mine = other > mine ? other : mine;
+  }
+  if ((threadIdx.x & 31) == 0 && mine) atomicMax(best, mine);
+}
+__global__ void cc3_select(int32_t* par, uint8_t* __restrict__ out, long long n, const unsigned long long* best) {
+  PDL_ENTRY();
+  const unsigned long long key = *best;
+  const int root = key ? (int)(0xffffffffull - (key & 0xffffffffull)) : -2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (par[i] >= 0 && uf_find(par, (int)i) == root) ? 1 : 0;
+}
+
 size_t smem_bytes(int H, int W) { return (size_t)(H / 2) * (W / 2) * 8 + (size_t)H * W; }
 constexpr size_t kSmemLimit = 224 * 1024;
 
@@ -373,4 +446,20 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
   if (!scratch_labels || !scratch_counts) return USVM_ERR_ARG;  // the global path needs two int32 [N,H,W] maps
   return launch_global<FgScore, true>(FgScore{scores_in}, scratch_labels, scratch_counts, scores_in, scores_out, N,
                                       H, W, max_area, fill_value, s);
+}
+
+extern "C" int usvm_cc3d_largest_u8(const uint8_t* vol, uint8_t* out, int32_t* scratch_parent, int32_t* scratch_count,
+                                    unsigned long long* scratch_best, int D, int H, int W, void* stream) {
+  if (D <= 0 || H <= 0 || W <= 0 || !vol || !out || !scratch_parent || !scratch_count || !scratch_best)
+    return USVM_ERR_ARG;
+  const long long n = (long long)D * H * W;
+  if (n >= (1LL << 31) - 1) return USVM_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+  usvm_launch(cc3_init, dim3(grid), dim3(256), 0, s, vol, scratch_parent, scratch_count, n, scratch_best);
+  usvm_launch(cc3_merge, dim3(grid), dim3(256), 0, s, vol, scratch_parent, D, H, W);
+  usvm_launch(cc3_count, dim3(grid), dim3(256), 0, s, scratch_parent, scratch_count, n);
+  usvm_launch(cc3_best, dim3(grid), dim3(256), 0, s, scratch_parent, scratch_count, n, scratch_best);
+  usvm_launch(cc3_select, dim3(grid), dim3(256), 0, s, scratch_parent, out, n, scratch_best);
+  return usvm_check_launch();
 }

@@ -646,6 +646,21 @@ def connected_components(mask_u8):
     return labels, counts
 
 
+def largest_component_3d(vol):
+    """uint8 / bool CUDA [D,H,W] -> uint8 [D,H,W] mask of the largest 26-connected component (all zero if empty)."""
+    if not vol.is_cuda or vol.dim() != 3:
+        raise RuntimeError("largest_component_3d expects a CUDA tensor [D, H, W]")
+    v = vol.to(torch.uint8).contiguous()
+    D, H, W = v.shape
+    out = torch.empty_like(v)
+    par = torch.empty((D, H, W), dtype=torch.int32, device=v.device)
+    cnt = torch.empty_like(par)
+    best = torch.empty(1, dtype=torch.int64, device=v.device)
+    call("usvm_cc3d_largest_u8", v.data_ptr(), out.data_ptr(), par.data_ptr(), cnt.data_ptr(), best.data_ptr(), D, H, W,
+         _stream())
+    return out
+
+
 def fill_holes(scores, max_area, fill_value=0.1):
     """Fused fill_holes_in_mask_scores: fp32 CUDA [N,1,H,W] -> new tensor."""
     _chk(scores, F32, "scores")
