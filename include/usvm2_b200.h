@@ -140,6 +140,21 @@ int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, void* out, int
  * contiguous (x_bs == N * x_rs).  Q, S = QK^T (double buffered), P and O live in TMEM, V is consumed in place as an
  * MN-major operand.  With num_splits > 1 it writes partials only: follow with usvm_fmha_combine. */
 int usvm_fmha_tc5(const usvm_fmha_params* p_host, void* stream);
+/* Image-encoder attention on tcgen05 / TMEM / TMA straight from the raster-order qkv tensor (replaces window_partition +
+ * F.scaled_dot_product_attention + window_unpartition of MultiScaleAttention / the ViT blocks, hieradet.py:56-81,
+ * backbones/utils.py:17-61, efficient_track_anything/modeling/backbones/vitdet.py): qkv bf16 [F, H, W, 3*dim] with
+ * (q | k | v) x (head, channel) columns, out bf16 [F, H, W, dim]; head_dim = dim / heads in {64, 96}.
+ * window == 0: global attention, H*W % 128 == 0.  window == 14: non-overlapping 14 x 14 windows over the grid padded to a
+ * multiple of 14; the padding tokens' k / v are the projection bias (qkv_bias fp32 [3*dim]), as in the reference where the
+ * zero padding follows the LayerNorm. */
+typedef struct usvm_hiera_attn_params {
+  const void* qkv;
+  void* out;
+  const float* qkv_bias;
+  int F, H, W, dim, heads, window;
+  float scale; /* 1/sqrt(head_dim) */
+} usvm_hiera_attn_params;
+int usvm_hiera_attn_tc5(const usvm_hiera_attn_params* p_host, void* stream);
 int usvm_fmha_combine(const usvm_fmha_params* p_host, void* stream);
 /* fp32, one warp per query; head_dim 16 or 32, Nk <= 1024 (SAM decoder two-way transformer) */
 int usvm_attn_small_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Nq, int Nk,

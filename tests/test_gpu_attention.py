@@ -89,3 +89,63 @@ def test_attn_small_f32(B, Nq, Nk, dh):
     sp = lambda t, n: t.view(B, n, H, dh).permute(0, 2, 1, 3)
     want = _ref_attn(sp(q, Nq), sp(k, Nk), sp(v, Nk)).permute(0, 2, 1, 3).reshape(B * Nq, H * dh)
     assert (got - want).abs().max().item() < 2e-5
+
+
+def _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws):
+    """MultiScaleAttention on a windowed block as the reference runs it (hieradet.py:56-81, backbones/utils.py:17-61):
+    the grid is zero padded to a multiple of the window AFTER norm1, so the padding tokens' q / k / v are the projection
+    bias; windows attend among all of their ws*ws tokens; padding rows are dropped by window_unpartition."""
+    hd = dim // heads
+    x = qkv.float().view(Fr, H, W, 3 * dim)
+    if ws == 0:
+        win = x.reshape(Fr, H * W, 3, heads, hd)
+    else:
+        Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+        pad = bias.to(torch.bfloat16).float().view(1, 1, 1, 3 * dim).expand(Fr, Hp, Wp, 3 * dim).clone()
+        pad[:, :H, :W] = x
+        win = pad.view(Fr, Hp // ws, ws, Wp // ws, ws, 3 * dim).permute(0, 1, 3, 2, 4, 5)
+        win = win.reshape(-1, ws * ws, 3, heads, hd)
+    q, k, v = (win[:, :, i].transpose(1, 2) for i in range(3))
+    o = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1) @ v
+    o = o.transpose(1, 2).reshape(o.shape[0], -1, dim)
+    if ws == 0:
+        return o.reshape(Fr * H * W, dim)
+    o = o.view(Fr, Hp // ws, Wp // ws, ws, ws, dim).permute(0, 1, 3, 2, 4, 5).reshape(Fr, Hp, Wp, dim)
+    return o[:, :H, :W].reshape(Fr * H * W, dim)
+
+
+@pytest.mark.parametrize("Fr,H,W,dim,heads,ws,scale_up", [
+    (2, 32, 32, 384, 4, 0, 1.0),    # Hiera stage-3 global block
+    (3, 32, 32, 384, 4, 0, 5.0),    # ... with scores large enough for the O rescaling path
+    (2, 32, 32, 384, 4, 14, 1.0),   # Hiera stage-3 windowed block: 9 windows, 5 of them partial
+    (1, 32, 32, 384, 4, 14, 5.0),
+    (2, 32, 32, 192, 3, 0, 1.0),    # EfficientTAM-ti trunk (heads of 64)
+    (2, 32, 32, 192, 3, 14, 3.0),
+    (1, 64, 64, 384, 4, 0, 1.0),    # 4096-token global block (1024^2 input)
+    (1, 28, 42, 384, 4, 14, 1.0),   # grid that is a multiple of the window: no padding tokens at all
+    (1, 30, 17, 384, 6, 14, 2.0),   # ragged grid, heads of 64
+])
+def test_hiera_attn_tc5(Fr, H, W, dim, heads, ws, scale_up):
+    """usvm_hiera_attn_tc5 vs the reference's pad / partition / SDPA / un-partition sequence in fp32 on the same bf16 qkv,
+    and (Hiera stage-3 shapes) vs the gather + mma.sync kernel + scatter path it replaces."""
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + W + dim + ws)
+    qkv = torch.randn((Fr * H * W, 3 * dim), generator=g, device="cuda")
+    qkv[:, :2 * dim] *= math.sqrt(scale_up)
+    qkv = qkv.to(torch.bfloat16)
+    bias = torch.randn((3 * dim,), generator=g, device="cuda") * math.sqrt(scale_up)
+    if ws == 0 and (H * W) % 128:
+        pytest.skip("global mode needs a multiple of 128 tokens")
+    out = ops.hiera_attn(qkv, bias, Fr, H, W, dim, heads, window=ws)
+    torch.cuda.synchronize()
+    want = _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws)
+    err = (out.float() - want).abs().max().item()
+    assert err < (2e-2 if scale_up == 1.0 else 4e-2), err
+    if dim // heads == 96 and ws == 14 and H == W == 32:
+        Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, bias, Fr, H, W, ws, False, dim)
+        Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * dim, dim, 96), (0, nk * dim, dim, 96),
+                      (0, nk * dim, dim, 96))
+        legacy = ops.window_scatter(Ow, Fr, H, W, ws, dim)
+        # two bf16 paths: up to 2 ulp apart at the output magnitude (|out| ~ 4 at scale_up = 5)
+        assert (out.float() - legacy.float().view(-1, dim)).abs().max().item() < (2e-2 if scale_up == 1.0 else 7e-2)

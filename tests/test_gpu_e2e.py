@@ -234,7 +234,10 @@ def test_editing_session_matches_reference_fixture(golden_dir):
             d = (a[i] - b[i]).abs()
             if key.startswith("low"):  # (the video-resolution samples interpolate across filled pixels)
                 # (around the click the logits reach several units: the absolute bar plus bf16-level relative error)
-                assert bool((d[same] <= 4 * LOGIT_TOL + 4e-3 * b[i].abs()[same]).all()), (key, i, float(d[same].max()))
+                # -- relative to the local logit scale (3 x 3 neighbourhood): at the steep edge of the clicked region a
+                # pixel's own value can be near zero while its neighbours are several units
+                scale = torch.nn.functional.max_pool2d(b[i].abs()[None, None], 3, 1, 1)[0, 0]
+                assert bool((d[same] <= 4 * LOGIT_TOL + 4e-3 * scale[same]).all()), (key, i, float(d[same].max()))
             assert float(d[same].mean()) <= 8e-4, (key, i, float(d[same].mean()))
             worst = min(worst, (dice(a[i], b[i]), (key, i)))
     print(f"editing session: worst Dice {worst[0]:.5f} at {worst[1]}")

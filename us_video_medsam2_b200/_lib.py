@@ -37,6 +37,11 @@ class FmhaParams(C.Structure):
                 ("part_bf16", C.c_int)]
 
 
+class HieraAttnParams(C.Structure):
+    _fields_ = [("qkv", C.c_void_p), ("out", C.c_void_p), ("qkv_bias", C.c_void_p), ("F", C.c_int), ("H", C.c_int),
+                ("W", C.c_int), ("dim", C.c_int), ("heads", C.c_int), ("window", C.c_int), ("scale", C.c_float)]
+
+
 MAX_PTRS = 48
 
 
@@ -83,6 +88,7 @@ _SIGNATURES = {
     "usvm_fmha_bf16": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_tc5": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_combine": [C.POINTER(FmhaParams), _P],
+    "usvm_hiera_attn_tc5": [C.POINTER(HieraAttnParams), _P],
     "usvm_attn_small_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "usvm_layernorm": [_P, _I, _P, _P, _F, _I, _P, _I, _P, _I, _I, _I, _P],
     "usvm_axpby_rows": [_P, _P, _F, _F, _I, _I, _I, _P, _P, _LL, _I, _P],

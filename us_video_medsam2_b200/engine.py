@@ -377,6 +377,8 @@ class Engine:
         # branches of the captured frame graph -- the frame is a latency chain of ~125 small kernels, not throughput bound
         self.fork_branches = os.environ.get("USVM2_FORK", "1") != "0"
         self.fused_windows = os.environ.get("USVM2_FUSED_WINDOWS", "1") != "0"
+        # global / 14 x 14 windowed encoder attention on the tcgen05 kernel (0: the mma.sync kernels, kept for comparison)
+        self.tc5_encoder_attn = os.environ.get("USVM2_ENCODER_ATTN_TC5", "1") != "0"
 
     # ---------------------------------------------------------------- forked branches
     def _side(self, i):
@@ -420,6 +422,9 @@ class Engine:
             # (window, head) walking 13 query slabs is slower there than gather + flash kernel + scatter: measured.)
             if 0 < ws * ws <= 64 and self.fused_windows:
                 att = ops.window_attn(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout, heads)
+            elif self.tc5_encoder_attn and not pool and ws in (0, 14) and (ws or (H * W) % 128 == 0):
+                # stage-3 blocks (global and 14 x 14 windows): tcgen05 kernel, window (un)partition = TMA coordinates
+                att = ops.hiera_attn(qkv, blk["qkv_b"], Fr, H, W, dout, heads, window=ws)
             elif ws > 0:
                 Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout)
                 Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * dout, dout, 96),
@@ -467,7 +472,11 @@ class Engine:
         for i, blk in enumerate(w.blocks):
             _, h = ops.layernorm(x, *blk["n1"], 1e-6, bf16=True)
             _, qkv = ops.gemm_bf16(h, blk["qkv_w"], bias=blk["qkv_b"], bf16=True)
-            if i in cfg.vit_window_blocks:
+            if self.tc5_encoder_attn and hd in (64, 96) and T % 128 == 0 and (
+                    i not in cfg.vit_window_blocks or cfg.vit_window == 14):
+                att = ops.hiera_attn(qkv, blk["qkv_b"], Fr, n, n, C, heads,
+                                     window=cfg.vit_window if i in cfg.vit_window_blocks else 0)
+            elif i in cfg.vit_window_blocks:
                 ws = cfg.vit_window
                 Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, n, n, ws, False, C)
                 Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, hd, (0, nq * C, C, hd), (0, nk * C, C, hd),

@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, POST_BINARIZE_AFFINE, POST_NONE, POST_SIGMOID_AFFINE,  # noqa: F401
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, HieraAttnParams, POST_BINARIZE_AFFINE, POST_NONE, POST_SIGMOID_AFFINE,  # noqa: F401
                    FmhaParams, FrameCtrl, GemmEpilogue, MemoryFrames, SkinnyParams, call)
 
 BF16 = torch.bfloat16
@@ -176,6 +176,23 @@ def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_
             call("usvm_fmha_combine", C.byref(p), _stream())
     else:
         call("usvm_fmha_bf16", C.byref(p), _stream())
+    return out
+
+
+def hiera_attn(qkv, qkv_bias, Fr, H, W, dim, heads, window=0):
+    """Image-encoder attention on the tcgen05 kernel, straight from the projection's raster-order output:
+    qkv bf16 [Fr*H*W, 3*dim] -> bf16 [Fr*H*W, dim].  window 0 = global, 14 = the 14 x 14 windows of Hiera stage 3 / the
+    ViT trunk (padding tokens enter in closed form through qkv_bias)."""
+    _chk(qkv, BF16, "qkv")
+    _chk(qkv_bias, F32, "qkv_bias")
+    if qkv.shape != (Fr * H * W, 3 * dim):
+        raise RuntimeError(f"hiera_attn: qkv {tuple(qkv.shape)} != {(Fr * H * W, 3 * dim)}")
+    out = empty((Fr * H * W, dim), BF16, qkv)
+    p = HieraAttnParams()
+    p.qkv, p.out, p.qkv_bias = qkv.data_ptr(), out.data_ptr(), qkv_bias.data_ptr()
+    p.F, p.H, p.W, p.dim, p.heads, p.window = Fr, H, W, dim, heads, window
+    p.scale = 1.0 / math.sqrt(dim // heads)
+    call("usvm_hiera_attn_tc5", C.byref(p), _stream())
     return out
 
 
