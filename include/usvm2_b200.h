@@ -105,6 +105,8 @@ int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usv
  * block_n: 0 = auto, 32 / 64 / 128. */
 int usvm_gemm_tf32_tc5(const float* A, int lda, const float* W, int ldw, const usvm_gemm_epilogue* ep_host, int M, int N,
                        int K, int block_n, void* stream);
+/* developer aid: clock64() stamps of the persistent GEMM's first 64 tiles on CTA 0 (USVM2_PGEMM_DEBUG & 4), 64 x 16 words */
+int usvm_debug_pgemm_profile(unsigned long long* host_out_1024);
 /* fp32-accumulate SIMT GEMM, operands fp32 or bf16 (flags), any shape: fp32 decoder tail + checker. */
 int usvm_gemm_simt(const void* A, int a_is_bf16, int lda, const void* W, int w_is_bf16, int ldw,
                    const usvm_gemm_epilogue* ep_host, int M, int N, int K, void* stream);

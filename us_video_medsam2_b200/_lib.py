@@ -84,6 +84,7 @@ _SIGNATURES = {
     "usvm_fill_holes_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "usvm_gemm_bf16_tc5": [_P, _I, _P, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _I, _P],
     "usvm_gemm_tf32_tc5": [_P, _I, _P, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _I, _P],
+    "usvm_debug_pgemm_profile": [_P],
     "usvm_gemm_simt": [_P, _I, _I, _P, _I, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _P],
     "usvm_fmha_bf16": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_tc5": [C.POINTER(FmhaParams), _P],

@@ -159,6 +159,22 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  The tcgen05.mma / commit / TMA issue paths use this instead of
+// `if (lane == 0)`: inside an ordinary divergent branch ptxas wraps every uniform-datapath instruction (UTCHMMA, UTCBAR,
+// UTMALDG) in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and keeps the descriptors in vector registers -- measured on
+// the persistent GEMM: ~150 cycles of issue per tcgen05.mma, which made every tcgen05 kernel issue bound (a 128 x 192 x 16
+// MMA is 96 cycles of tensor pipe).  With elect.sync the loop control stays warp-uniform and descriptors live in
+// uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -117,9 +117,14 @@ __device__ __forceinline__ void epilogue_block(float (&v)[32], const usvm_gemm_e
         }
       }
     }
-    if (ep.act != USVM_ACT_NONE) {
+    // (one branch per block, not per element: the 32 independent GELU chains then interleave -- with the switch inside
+    // the loop every element was a serial chain of ~17 dependent instructions, 3400 cycles per block)
+    if (ep.act == USVM_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (ep.act == USVM_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     }
     if (ep.col_scale) {
 #pragma unroll
@@ -467,51 +472,94 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Persistent variant for the throughput-bound GEMMs (the batched Hiera encoder, the memory-bank K/V projections):
-// one CTA per SM walks output tiles of 128 x BN (BN a runtime multiple of 32, <= 256, chosen to divide N), the
-// accumulator is double-buffered in TMEM (columns [0,256) and [256,512)), and eight epilogue warps drain tile i while
-// the TMA / MMA warps are already running tile i+1 -- with K of only 96..1536 the epilogue (bias, exact-erf GELU,
-// residual, bf16 pack, TMA store) costs as much as the mainloop, so overlapping the two is what doubles the rate.
+// Persistent variant for the throughput-bound GEMMs (the batched Hiera encoder, the memory-bank K/V projections, the
+// batched memory attention): one CTA per SM walks output tiles of 128 x BN (BN a runtime multiple of 32, <= 256, chosen to
+// divide N), the accumulator is double-buffered in TMEM (columns [0,256) and [256,512)), and eight epilogue warps drain
+// tile i while the TMA / MMA warps are already running tile i+1.
 //   warp 0    : TMA producer, one continuous smem ring across tiles
 //   warp 1    : MMA issuer; waits acc_empty[buf], issues K/16 tcgen05.mma, commits acc_full[buf]
 //   warps 2-9 : epilogue; warp w owns TMEM lanes 32*(w%4).. and every second 32-column block of the tile
-// Tiles are ordered n-fastest so the CTAs that run concurrently share the same A rows in L2.
+// Two schedules:
+//   * WEIGHT-STATIONARY (ws_groups > 0; chosen whenever the [BN, K] slab of W fits next to a 3-stage A ring -- every
+//     Hiera / memory-attention GEMM with K <= 384): CTA c keeps column slab c % tiles_n of W resident in shared memory and
+//     walks row tiles c / tiles_n, + ws_groups, ...; only A streams.  Measured per-tile timeline of the streaming
+//     schedule (tools/pgemm_timeline.py, 128 x 192 x 384): the 24 MMAs of a tile took 5970 cycles against 2304 at the
+//     tensor pipe's rate, because A + W k-blocks (40 KB per 384 MMA cycles = 107 B/clk) exceed what one SM draws from L2
+//     (~55 B/clk sustained with all SMs loading); with W resident the feed is 16 KB per k-block = 43 B/clk.
+//   * streaming (ws_groups == 0): tiles n-fastest so the CTAs that run concurrently share the same A rows in L2.
+// Epilogue: a 32 x 32 block per warp per step.  TMEM reads are the floor (64 B/clk per SM: 128 x BN x 4 B / 64 cycles per
+// tile), so everything else overlaps them: the tcgen05.ld of block i+1 is issued before the math of block i, the
+// accumulator is handed back to the MMA warp right after the tile's last TMEM read (not after its last store), bias and
+// column scale of the warp's blocks sit in a per-warp shared-memory strip (filled before the accumulator is awaited, read
+// back as broadcast 16-byte loads), residual / rotary operands are fetched one block ahead, and the block goes out
+// through double-buffered staging + one TMA store.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int P_THREADS = 320;
-constexpr int P_EPI_WARPS = 8;
-// staging: per epilogue warp TWO buffers of one 32 x 32 block per output present (fp32 4 KB, bf16 2 KB), so the TMA store
-// of block i still reads its buffer while block i + 1 is being computed and written -- the wait for a store's shared-memory
-// read (~1 us after issue) used to sit between every two column blocks of a warp
+// USVM2_PGEMM_DEBUG & 4: CTA 0 records clock64() stamps of its first 64 tiles here (usvm_debug_pgemm_profile reads them):
+// [tile][0] MMA: accumulator free, [1] MMA: first stage full, [2] MMA: tile committed; [3] epilogue warp 0: accumulator
+// full, [4] first TMEM load done, [5] first block's math done, [6] last block handed to TMA, [7] accumulator released
+__device__ unsigned long long g_pgemm_prof[64 * 16];
+constexpr int P_EPI_WARPS = 12;  // three per scheduler (14 warps -> 128 registers each): the epilogue is a chain of
+                                 // long-latency steps, warps are what hides them
+constexpr int P_COL_GROUPS = P_EPI_WARPS / 4;  // a warp owns every P_COL_GROUPS-th 32-column block of its 32 rows
+constexpr int P_MAX_BLOCKS = (256 / 32 + P_COL_GROUPS - 1) / P_COL_GROUPS;
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
+constexpr int P_STRIP_BYTES = P_EPI_WARPS * 2 * P_MAX_BLOCKS * 32 * 4;  // per warp: bias + column scale of its blocks
+// staging: per epilogue warp one buffer of one 32 x 32 block per output present (fp32 4 KB, bf16 2 KB); a warp has at most
+// three blocks per tile, so the previous block's TMA store has long finished reading the buffer when the next one is written
 __host__ __device__ constexpr int p_stg_per_buf(bool f32, bool b16) { return (f32 ? STG_F32 : 0) + (b16 ? STG_BF16 : 0); }
-__host__ __device__ constexpr int p_stg_bytes(bool f32, bool b16) { return P_EPI_WARPS * 2 * p_stg_per_buf(f32, b16); }
+__host__ __device__ constexpr int p_stg_bytes(bool f32, bool b16) { return P_EPI_WARPS * p_stg_per_buf(f32, b16); }
 constexpr int P_A_BYTES = BM * BK * 2;
 
-__host__ __device__ constexpr int p_stage_bytes(int bn) { return P_A_BYTES + bn * BK * 2; }
-__host__ __device__ constexpr int p_smem_total(int bn, int stages, bool f32, bool b16) {
-  return stages * p_stage_bytes(bn) + p_stg_bytes(f32, b16) + 1024 /* alignment slack */ + 256 /* barriers */;
+__host__ __device__ constexpr int p_stage_bytes(int bn, bool ws) { return P_A_BYTES + (ws ? 0 : bn * BK * 2); }
+__host__ __device__ constexpr int p_slab_bytes(int bn, int num_kb, bool ws) { return ws ? num_kb * bn * BK * 2 : 0; }
+__host__ __device__ constexpr int p_smem_total(int bn, int num_kb, int stages, bool f32, bool b16, bool ws) {
+  return p_slab_bytes(bn, num_kb, ws) + stages * p_stage_bytes(bn, ws) + p_stg_bytes(f32, b16) + P_STRIP_BYTES +
+         1024 /* alignment slack */ + 256 /* barriers */;
 }
 
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                                 const usvm_gemm_epilogue ep, const int M, const int N, const int K, const int BN,
-                                const int stages_flags, const int tiles_n, const int num_tiles) {
+                                const int stages_flags, const int tiles_n, const int tiles_m, const int ws_groups) {
   const int stages = stages_flags & 0xff;
   const int dbg = stages_flags >> 8;  // experiment switches (USVM2_PGEMM_DEBUG): 1 = no TMA store, 2 = no staging either
+  const bool ws = ws_groups > 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = p_stage_bytes(BN);
-  uint8_t* staging = smem + stages * stage_bytes;
+  const int num_kb = (K + BK - 1) / BK;
+  const int b_bytes = BN * BK * 2;  // one k-block of the W slab / tile (a multiple of 1024: BN % 32 == 0)
+  const int stage_bytes = p_stage_bytes(BN, ws);
+  uint8_t* slab = smem;                                   // weight-stationary: num_kb k-blocks of W, resident
+  uint8_t* ring = smem + p_slab_bytes(BN, num_kb, ws);    // A (and, streaming, W) stages
+  uint8_t* staging = ring + stages * stage_bytes;
   const int stg_per_buf = p_stg_per_buf(ep.out_f32 != nullptr, ep.out_bf16 != nullptr);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + P_EPI_WARPS * 2 * stg_per_buf);
+  float* strips = reinterpret_cast<float*>(staging + P_EPI_WARPS * stg_per_buf);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(strips) + P_STRIP_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* slab_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = (K + BK - 1) / BK;
+  // this CTA's tiles: i-th tile -> (tile_m, tile_n)
+  const int my_n = ws ? (int)blockIdx.x % tiles_n : 0;
+  const int my_group = ws ? (int)blockIdx.x / tiles_n : 0;
+  const int num_tiles = tiles_m * tiles_n;
+  const int my_count = ws ? (tiles_m - my_group + ws_groups - 1) / ws_groups
+                          : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_at = [&](int i, int& tile_m, int& tile_n) {
+    if (ws) {
+      tile_m = my_group + i * ws_groups;
+      tile_n = my_n;
+    } else {
+      const int tile = blockIdx.x + i * gridDim.x;
+      tile_m = tile / tiles_n;
+      tile_n = tile - tile_m * tiles_n;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -526,6 +574,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], P_EPI_WARPS);
     }
+    mbar_init(slab_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) tc5_alloc(tmem_slot, 512);
@@ -538,126 +587,204 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
 
   if (warp == 0) {
     if (lane == 0) {
+      if (ws && my_count > 0) {  // the W slab of this CTA, once
+        mbar_arrive_expect_tx(slab_full, (uint32_t)(num_kb * b_bytes));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab + kb * b_bytes, &tmB, slab_full, kb * BK, my_n * BN);
+      }
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+      for (int i = 0; i < my_count; ++i) {
+        int tile_m, tile_n;
+        tile_at(i, tile_m, tile_n);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % (uint32_t)stages;
           const uint32_t ph = (it / (uint32_t)stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* a_dst = smem + s * stage_bytes;
+          uint8_t* a_dst = ring + s * stage_bytes;
+          if (dbg & 16) {  // experiment: no operand traffic at all (the MMAs run on whatever the ring holds)
+            mbar_arrive(&full_bar[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tile_m * BM);
-          tma_load_2d(a_dst + P_A_BYTES, &tmB, &full_bar[s], kb * BK, tile_n * BN);
+          if (!ws) tma_load_2d(a_dst + P_A_BYTES, &tmB, &full_bar[s], kb * BK, tile_n * BN);
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN);
-      uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t buf = lt & 1u;
-        mbar_wait(&acc_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+    // the whole warp walks the loop (uniform control flow, waits included); one elected lane issues
+    const uint32_t idesc = umma_idesc_bf16(BM, BN);
+    uint32_t it = 0;
+    if (ws && my_count > 0) {
+      mbar_wait(slab_full, 0);
+      tc5_fence_after();
+    }
+    for (int lt = 0; lt < my_count; ++lt) {
+      const uint32_t buf = lt & 1u;
+      mbar_wait(&acc_empty[buf], ((lt >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+      tc5_fence_after();
+      const bool prof = (dbg & 4) && blockIdx.x == 0 && lt < 64 && lane == 0;
+      if (prof) g_pgemm_prof[lt * 16 + 0] = clock64();
+      const uint32_t d_tmem = tmem_base + buf * 256u;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t s = it % (uint32_t)stages;
+        const uint32_t ph = (it / (uint32_t)stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
         tc5_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 256u;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)stages;
-          const uint32_t ph = (it / (uint32_t)stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          tc5_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint64_t a_desc = umma_desc_k_sw128(a_addr);
-          const uint64_t b_desc = umma_desc_k_sw128(a_addr + P_A_BYTES);
+        if (prof && kb == 0) g_pgemm_prof[lt * 16 + 1] = clock64();
+        const uint32_t a_addr = smem_u32(ring + s * stage_bytes);
+        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_k_sw128(ws ? smem_u32(slab + kb * b_bytes) : a_addr + P_A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             tc5_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
           tc5_commit(&empty_bar[s]);
+          if (kb == num_kb - 1) tc5_commit(&acc_full[buf]);
         }
-        tc5_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (prof) g_pgemm_prof[lt * 16 + 2] = clock64();
     }
-    __syncwarp();
   } else {
-    const int ew = warp - 2;        // 0..7
+    const int ew = warp - 2;        // 0..P_EPI_WARPS-1
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
-    const int half = ew >> 2;       // which 32-column blocks of the tile: half, half+2, ...
-    uint8_t* stg_warp = staging + ew * 2 * stg_per_buf;  // two buffers: [fp32 block | bf16 block] each
-    const int stg16_off = ep.out_f32 ? STG_F32 : 0;
-    uint32_t nstored = 0;  // column blocks this warp has handed to TMA so far (buffer = nstored & 1)
-    uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int tile_m = tile / tiles_n, tile_n = tile - tile_m * tiles_n;
+    const int quarter = ew >> 2;    // which 32-column blocks of the tile: quarter, quarter + P_COL_GROUPS, ...
+    uint8_t* stg32 = staging + ew * stg_per_buf;  // [fp32 block | bf16 block]
+    uint8_t* stg16 = stg32 + (ep.out_f32 ? STG_F32 : 0);
+    float* strip_bias = strips + ew * (2 * P_MAX_BLOCKS * 32);   // [blocks][32 columns]
+    float* strip_scale = strip_bias + P_MAX_BLOCKS * 32;
+    bool pending = false;  // a TMA store of this warp may still be reading its staging buffer
+    int strip_n = -1;      // tile_n the strips currently hold
+    for (int lt = 0; lt < my_count; ++lt) {
+      int tile_m, tile_n;
+      tile_at(lt, tile_m, tile_n);
       const uint32_t buf = lt & 1u;
-      mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
-      tc5_fence_after();
+      // bias / column scale of this warp's blocks -> its strip, before the accumulator is awaited
+      if (tile_n != strip_n && (ep.bias != nullptr || ep.col_scale != nullptr)) {
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < P_MAX_BLOCKS; ++b) {
+          const int col = tile_n * BN + (quarter + b * P_COL_GROUPS) * 32 + lane;
+          const bool ok = (quarter + b * P_COL_GROUPS) * 32 < BN && col < N;
+          if (ep.bias) strip_bias[b * 32 + lane] = ok ? __ldg(ep.bias + col) : 0.f;
+          if (ep.col_scale) strip_scale[b * 32 + lane] = ok ? __ldg(ep.col_scale + col) : 0.f;
+        }
+        __syncwarp();
+        strip_n = tile_n;
+      }
       const int row0 = tile_m * BM + lane_grp * 32;
       const int row = row0 + lane;
       const bool row_ok = row < M;
       const long long rrow = (ep.res_div > 0 ? ((long long)(row / ep.res_div) * ep.res_mod + row % ep.res_mod)
                                            : (ep.res_mod > 0 ? (row % ep.res_mod) : row));
-      if (row0 < M) {
-        // Operands of a column block that do not depend on the accumulator -- the residual row segment, or the rotary
-        // cos / sin of this row (the two never occur together) -- are fetched ONE BLOCK AHEAD: with K of 64..384 the
-        // mainloop of a tile is shorter than an L2 round trip, so a load issued after the TMEM read would sit on the
-        // critical path of every block (the bank key projection, K = 64 with RoPE, ran 379 us against 163 us for the
-        // same GEMM without the rotation).
-        const bool rope_row = ep.rope_cos != nullptr && (row % ep.rope_rows_per_batch) < ep.rope_n_rope;
-        const int rope_pos = rope_row ? (row % ep.rope_rows_per_batch) % ep.rope_table_rows : 0;
-        float4 cur[8], nxt[8];
-        // kind: 0 nothing, 1 residual, 2 rotary tables
-        auto prefetch = [&](int c0, float4 (&dst)[8]) -> int {
-          const int col0 = tile_n * BN + c0;
-          if (c0 >= BN || col0 + 32 > N) return 0;
-          if (ep.residual != nullptr && row_ok) {
-            const float4* r = reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0);
+      // Operands of a column block that do not depend on the accumulator -- the residual row segment, or the rotary
+      // cos / sin of this row (the two never occur together) -- are requested BEFORE the accumulator is awaited / read.
+      const bool rope_row = ep.rope_cos != nullptr && (row % ep.rope_rows_per_batch) < ep.rope_n_rope;
+      const int rope_pos = rope_row ? (row % ep.rope_rows_per_batch) % ep.rope_table_rows : 0;
+      float4 cur[8];
+      // kind: 0 nothing, 1 residual, 2 rotary tables
+      auto prefetch = [&](int c0) -> int {
+        const int col0 = tile_n * BN + c0;
+        if (c0 >= BN || col0 + 32 > N || row0 >= M) return 0;
+        if (ep.residual != nullptr && row_ok) {
+          const float4* r = reinterpret_cast<const float4*>(ep.residual + rrow * ep.ldr + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = __ldg(r + j);
-            return 1;
-          }
-          if (rope_row && col0 < ep.rope_cols) {
-            const int tcol0 = (col0 & 255) >> 1;
+          for (int j = 0; j < 8; ++j) cur[j] = __ldg(r + j);
+          return 1;
+        }
+        if (rope_row && col0 < ep.rope_cols) {
+          const int tcol0 = (col0 & 255) >> 1;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              dst[j] = __ldg(rope_chunk(ep.rope_cos, rope_pos, tcol0, j));
-              dst[4 + j] = __ldg(rope_chunk(ep.rope_sin, rope_pos, tcol0, j));
-            }
-            return 2;
+          for (int j = 0; j < 4; ++j) {
+            cur[j] = __ldg(rope_chunk(ep.rope_cos, rope_pos, tcol0, j));
+            cur[4 + j] = __ldg(rope_chunk(ep.rope_sin, rope_pos, tcol0, j));
           }
-          return 0;
-        };
-        int kind = prefetch(half * 32, cur);
+          return 2;
+        }
+        return 0;
+      };
+      int kind = prefetch(quarter * 32);
+      mbar_wait(&acc_full[buf], (lt >> 1) & 1u);
+      tc5_fence_after();
+      const bool prof = (dbg & 4) && blockIdx.x == 0 && lt < 64 && ew == 0 && lane == 0;
+      if (prof) g_pgemm_prof[lt * 16 + 3] = clock64();
+      bool released = false;
+      if (row0 < M && !(dbg & 8)) {  // (dbg & 8: experiment, the accumulator is released unread)
+        const uint32_t t_lane = tmem_base + buf * 256u + ((uint32_t)(lane_grp * 32) << 16);
+        int blk = 0;
 #pragma unroll 1
-        for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        for (int c0 = quarter * 32; c0 < BN; c0 += 32 * P_COL_GROUPS, ++blk) {
           const int col0 = tile_n * BN + c0;
           if (col0 >= N) break;  // warp-uniform
           uint32_t acc[32];
-          tc5_ld_32x32(tmem_base + buf * 256u + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0, acc);
-          const int kind_next = prefetch(c0 + 64, nxt);
-          const bool full_blk = (N - col0) >= 32;
+          tc5_ld_32x32(t_lane + (uint32_t)c0, acc);
+          if (blk > 0) kind = prefetch(c0);
           tc5_wait_ld();
+          if (!(c0 + 32 * P_COL_GROUPS < BN && col0 + 32 * P_COL_GROUPS < N)) {
+            // the tile's last TMEM read of this warp is complete: hand the accumulator back before the math / stores
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            released = true;
+          }
+          if (prof && blk == 0) g_pgemm_prof[lt * 16 + 4] = clock64();
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-          epilogue_block(v, ep, row, row_ok, rrow, col0, N, kind != 1, nullptr, kind == 2 ? cur : nullptr);
-          if (kind == 1) {
+          if (N - col0 >= 32) {
+            if (ep.bias) {
+              const float4* bs = reinterpret_cast<const float4*>(strip_bias + blk * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j] += cur[j].x; v[4 * j + 1] += cur[j].y; v[4 * j + 2] += cur[j].z; v[4 * j + 3] += cur[j].w;
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = bs[j];
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
             }
-          }
-          (void)full_blk;
-          kind = kind_next;
+            if (kind == 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-          uint8_t* stg32 = stg_warp + (nstored & 1u) * stg_per_buf;
-          uint8_t* stg16 = stg32 + stg16_off;
-          if (nstored >= 2) {  // the store issued two blocks ago has finished reading this buffer
-            if (lane == 0) tma_store_wait_read1();
+              for (int j = 0; j < 32; j += 8) {
+                const float4 c4 = cur[j >> 3], s4 = cur[4 + (j >> 3)];
+                const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float a = v[j + 2 * q], b = v[j + 2 * q + 1];
+                  v[j + 2 * q] = a * cs[q] - b * sn[q];
+                  v[j + 2 * q + 1] = a * sn[q] + b * cs[q];
+                }
+              }
+            }
+            if (ep.act == USVM_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            } else if (ep.act == USVM_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            if (ep.col_scale) {
+              const float4* ss = reinterpret_cast<const float4*>(strip_scale + blk * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = ss[j];
+                v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w;
+              }
+            }
+            if (kind == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += cur[j].x; v[4 * j + 1] += cur[j].y; v[4 * j + 2] += cur[j].z; v[4 * j + 3] += cur[j].w;
+              }
+            }
+          } else {  // ragged last column block (no rotary encoding there: N % 32 == 0 is required with rope)
+            epilogue_block(v, ep, row, row_ok, rrow, col0, N, true);
+          }
+          if (prof && blk == 0) g_pgemm_prof[lt * 16 + 5] = clock64() + (v[0] == 1.2345e30f);
+          if (pending) {  // the previous store of this warp has finished reading the staging buffer
+            if (lane == 0) tma_store_wait_read();
             __syncwarp();
           }
+          if (prof && blk == 0) g_pgemm_prof[lt * 16 + 8] = clock64();
           if (ep.out_f32 && !(dbg & 2)) {
             uint8_t* prow = stg32 + lane * 128;
 #pragma unroll
@@ -681,24 +808,31 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             float keep = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) keep += v[j];
-            if (keep == 1.2345e30f) stg_warp[0] = 1;
+            if (keep == 1.2345e30f) stg32[0] = 1;
           }
+          if (prof && blk == 0) g_pgemm_prof[lt * 16 + 9] = clock64();
           fence_async_smem();
           __syncwarp();
+          if (prof && blk == 0) g_pgemm_prof[lt * 16 + 10] = clock64();
           if (lane == 0 && !(dbg & 1)) {
             if (ep.out_f32) tma_store_2d(&tmO32, stg32, col0, row0);
             if (ep.out_bf16) tma_store_2d(&tmO16, stg16, col0, row0);
             tma_store_commit();
+            pending = true;
           }
-          ++nstored;
+          pending = __shfl_sync(0xffffffffu, pending, 0);
+          if (prof && blk == 0) g_pgemm_prof[lt * 16 + 11] = clock64();
         }
       }
-      // all of this warp's TMEM reads of `buf` are complete (wait::ld above): hand the accumulator back
-      tc5_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (prof) g_pgemm_prof[lt * 16 + 6] = clock64();
+      if (!released) {  // (row slab beyond M, or no column block of this warp inside N)
+        tc5_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      if (prof) g_pgemm_prof[lt * 16 + 7] = clock64();
     }
-    if (nstored && lane == 0) tma_store_wait_read();
+    if (pending && lane == 0) tma_store_wait_read();
     __syncwarp();
   }
   tc5_fence_before();
@@ -837,9 +971,46 @@ int persistent_block_n(int N) {
   return best;
 }
 
+int device_sm_count() {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+      sm_count = 0;
+  }
+  return sm_count;
+}
+
+// weight-stationary groups for tile width bn (0: the slab does not fit / too few row tiles per CTA)
+int ws_groups_for(int bn, int M, int N, int K, bool o32, bool o16, int sm_limit) {
+  static const int ws_mode = [] { const char* e = getenv("USVM2_PGEMM_WS"); return e ? atoi(e) : 1; }();
+  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
+  if (!ws_mode || tiles_n > sm_limit || p_smem_total(bn, num_kb, 3, o32, o16, true) > 227 * 1024) return 0;
+  const int groups = sm_limit / tiles_n;
+  return (groups >= 1 && tiles_m >= 2 * groups) ? groups : 0;
+}
+
+// bn <= 0: choose -- the widest tile among those that waste the fewest padded columns, preferring one whose W slab can
+// stay resident (weight-stationary schedule)
 int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
                       int bn, cudaStream_t stream) {
-  if (bn <= 0 || bn > 256 || (bn % 32)) return USVM_ERR_ARG;
+  const int sm_count = device_sm_count();
+  if (!sm_count) return USVM_ERR_CUDA;
+  const int sm_limit = (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
+  const bool o32 = ep->out_f32 != nullptr, o16 = ep->out_bf16 != nullptr;
+  if (bn <= 0) {
+    bn = persistent_block_n(N);
+    const int min_waste = cdiv(N, bn) * bn - N;
+    if (!ws_groups_for(bn, M, N, K, o32, o16, sm_limit)) {
+      for (int b = bn - 32; b >= 96; b -= 32)
+        if (cdiv(N, b) * b - N == min_waste && ws_groups_for(b, M, N, K, o32, o16, sm_limit)) {
+          bn = b;
+          break;
+        }
+    }
+  }
+  if (bn > 256 || (bn % 32)) return USVM_ERR_ARG;
   CUtensorMap tmA, tmB, tmO32, tmO16;
   int rc = make_map_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
@@ -857,29 +1028,27 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
                   CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
-      return USVM_ERR_CUDA;
-    if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             227 * 1024) != cudaSuccess)
-      return USVM_ERR_CUDA;
-  }
-  int stages = STAGES;
-  const bool o32 = ep->out_f32 != nullptr, o16 = ep->out_bf16 != nullptr;
-  while (stages > 1 && p_smem_total(bn, stages, o32, o16) > 227 * 1024) --stages;
-  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn);
+  if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+      cudaSuccess)
+    return USVM_ERR_CUDA;
+  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
   const int num_tiles = tiles_m * tiles_n;
-  const int sm_limit = (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
-  const int grid = num_tiles < sm_limit ? num_tiles : sm_limit;
-  usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, stages, o32, o16), stream, tmA, tmB,
-              tmO32, tmO16, *ep, M, N, K, bn, stages | (pgemm_debug() << 8), tiles_n, num_tiles);
+  const int ws_groups = ws_groups_for(bn, M, N, K, o32, o16, sm_limit);
+  const bool ws = ws_groups > 0;
+  int stages = STAGES;
+  while (stages > 1 && p_smem_total(bn, num_kb, stages, o32, o16, ws) > 227 * 1024) --stages;
+  const int grid = ws ? ws_groups * tiles_n : (num_tiles < sm_limit ? num_tiles : sm_limit);
+  usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, num_kb, stages, o32, o16, ws),
+              stream, tmA, tmB, tmO32, tmO16, *ep, M, N, K, bn, stages | (pgemm_debug() << 8), tiles_n, tiles_m, ws_groups);
   return usvm_check_launch();
 }
 
 }  // namespace
+
+extern "C" int usvm_debug_pgemm_profile(unsigned long long* host_out_1024) {
+  if (!host_out_1024) return USVM_ERR_ARG;
+  return cudaMemcpyFromSymbol(host_out_1024, g_pgemm_prof, sizeof(g_pgemm_prof)) == cudaSuccess ? USVM_OK : USVM_ERR_CUDA;
+}
 
 extern "C" int usvm_set_sm_budget(int sms) {
   g_sm_budget = sms > 0 ? sms : 0;
@@ -906,9 +1075,9 @@ extern "C" int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw
     return launch<256, false>(A, lda, W, ldw, ep, M, N, K, s);
   }
   int bn = block_n;
-  if (bn < 0) return launch_persistent(A, lda, W, ldw, ep, M, N, K, bn == -1 ? persistent_block_n(N) : -bn, s);
+  if (bn < 0) return launch_persistent(A, lda, W, ldw, ep, M, N, K, bn == -1 ? 0 : -bn, s);
   if (bn == 0 && (long long)cdiv(M, BM) * cdiv(N, 128) >= 148)  // throughput-bound: a full wave of 128 x 128 tiles or more
-    return launch_persistent(A, lda, W, ldw, ep, M, N, K, persistent_block_n(N), s);
+    return launch_persistent(A, lda, W, ldw, ep, M, N, K, 0, s);
   if (bn <= 0) {
     // latency-bound shapes: the narrowest tile (most CTAs) that still runs as a single wave -- a second wave costs a
     // whole extra tile time.  Slots per SM follow from the shared memory of the k-deep ring (<= 2 by launch bounds).
