@@ -147,21 +147,23 @@ fmha_tc5_ts_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const uint32_t tmem_Q = tmem, tmem_S = tmem + 128, tmem_O = tmem + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int j = 0; j < n; ++j) {
-        const int st = j % TS_STAGES;
-        mbar_wait(&kv_empty[st], ((j / TS_STAGES) & 1) ^ 1);
+    // (whole warp walks the loop, one elected lane issues: see elect_one() in common.cuh)
+    for (int j = 0; j < n; ++j) {
+      const int st = j % TS_STAGES;
+      mbar_wait(&kv_empty[st], ((j / TS_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * KV_BYTES);
         const int row = b * p.Nk + (t_begin + j) * KN;
+#pragma unroll
         for (int c = 0; c < NCH; ++c) {
           tma_load_2d(sK + st * KV_BYTES + c * (KN * 128), &tmK, &kv_full[st], c * 64, row);
           tma_load_2d(sV + st * KV_BYTES + c * (KN * 128), &tmV, &kv_full[st], c * 64, row);
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && n > 0) {
+    if (n > 0) {
       constexpr uint32_t idesc_s = idesc_bf16(QM, KN, 0);
       constexpr uint32_t idesc_o = idesc_bf16(QM, HD, 1);
       auto issue_s = [&](int j) {
@@ -169,13 +171,16 @@ fmha_tc5_ts_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         mbar_wait(&kv_full[st], (j / TS_STAGES) & 1);
         tc5_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * KV_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t koff = (kk >> 2) * (KN * 128) + (kk & 3) * 32;
-          tc5_mma_f16_ts(tmem_S + (j & 1) * KN, tmem_Q + kk * 8, umma_desc_k_sw128(k_addr + koff), idesc_s,
-                         kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint32_t koff = (kk >> 2) * (KN * 128) + (kk & 3) * 32;
+            tc5_mma_f16_ts(tmem_S + (j & 1) * KN, tmem_Q + kk * 8, umma_desc_k_sw128(k_addr + koff), idesc_s,
+                           kk > 0 ? 1u : 0u);
+          }
+          tc5_commit(&s_full[j & 1]);
         }
-        tc5_commit(&s_full[j & 1]);
+        __syncwarp();
       };
       mbar_wait(q_ready, 0);
       tc5_fence_after();
@@ -185,16 +190,18 @@ fmha_tc5_ts_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc5_fence_after();
         const uint32_t v_addr = smem_u32(sV + (j % TS_STAGES) * KV_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < KN / 16; ++kk) {
-          tc5_mma_f16_ts(tmem_O, tmem_S + (j & 1) * KN + kk * 8, umma_desc_mn_sw128(v_addr + kk * 2048, KN * 128),
-                         idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < KN / 16; ++kk) {
+            tc5_mma_f16_ts(tmem_O, tmem_S + (j & 1) * KN + kk * 8, umma_desc_mn_sw128(v_addr + kk * 2048, KN * 128),
+                           idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc5_commit(&kv_empty[j % TS_STAGES]);
+          tc5_commit(&pv_done[j & 1]);
         }
-        tc5_commit(&kv_empty[j % TS_STAGES]);
-        tc5_commit(&pv_done[j & 1]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     const int lane_grp = warp & 3;
     const int half = (warp - 2) >> 2;

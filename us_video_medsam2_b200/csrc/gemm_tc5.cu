@@ -209,32 +209,33 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    // (whole warp walks the loop, one elected lane issues: see elect_one() in common.cuh)
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % stages;
+      const uint32_t ph = (kb / stages) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      if (elect_one()) {
         uint8_t* a_dst = smem + s * L::STAGE_BYTES;
         uint8_t* b_dst = a_dst + L::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
         tma_load_2d(a_dst, &tmA, &full_bar[s], (kb_lo + kb) * BKE, tile_m * BM);
         tma_load_2d(b_dst, &tmB, &full_bar[s], (kb_lo + kb) * BKE, tile_n * BN);
       }
+      __syncwarp();
     }
-    __syncwarp();
     if (ksplit > 1) cluster_sync_all();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc5_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::A_BYTES;
-        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+    constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_bf16(BM, BN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % stages;
+      const uint32_t ph = (kb / stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc5_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+      const uint32_t b_addr = a_addr + L::A_BYTES;
+      const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+      const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // advance 16 bf16 (8 tf32) = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
@@ -246,9 +247,11 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         (kb > 0 || k > 0) ? 1u : 0u);
         }
         tc5_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        if (kb == num_kb - 1) tc5_commit(tmem_full_bar);  // accumulator complete
       }
-      tc5_commit(tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
+    if (num_kb == 0 && elect_one()) tc5_commit(tmem_full_bar);
     __syncwarp();
     if (ksplit > 1) cluster_sync_all();
   } else {
@@ -586,31 +589,32 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      if (ws && my_count > 0) {  // the W slab of this CTA, once
-        mbar_arrive_expect_tx(slab_full, (uint32_t)(num_kb * b_bytes));
-        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab + kb * b_bytes, &tmB, slab_full, kb * BK, my_n * BN);
-      }
-      uint32_t it = 0;
-      for (int i = 0; i < my_count; ++i) {
-        int tile_m, tile_n;
-        tile_at(i, tile_m, tile_n);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const uint32_t s = it % (uint32_t)stages;
-          const uint32_t ph = (it / (uint32_t)stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+    if (ws && my_count > 0 && elect_one()) {  // the W slab of this CTA, once
+      mbar_arrive_expect_tx(slab_full, (uint32_t)(num_kb * b_bytes));
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab + kb * b_bytes, &tmB, slab_full, kb * BK, my_n * BN);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int i = 0; i < my_count; ++i) {
+      int tile_m, tile_n;
+      tile_at(i, tile_m, tile_n);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t s = it % (uint32_t)stages;
+        const uint32_t ph = (it / (uint32_t)stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (elect_one()) {
           uint8_t* a_dst = ring + s * stage_bytes;
           if (dbg & 16) {  // experiment: no operand traffic at all (the MMAs run on whatever the ring holds)
             mbar_arrive(&full_bar[s]);
-            continue;
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tile_m * BM);
+            if (!ws) tma_load_2d(a_dst + P_A_BYTES, &tmB, &full_bar[s], kb * BK, tile_n * BN);
           }
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-          tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tile_m * BM);
-          if (!ws) tma_load_2d(a_dst + P_A_BYTES, &tmB, &full_bar[s], kb * BK, tile_n * BN);
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // the whole warp walks the loop (uniform control flow, waits included); one elected lane issues
     const uint32_t idesc = umma_idesc_bf16(BM, BN);

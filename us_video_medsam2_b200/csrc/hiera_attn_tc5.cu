@@ -160,11 +160,12 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
   const uint32_t tmem_Q = tmem, tmem_S = tmem + 64, tmem_O = tmem + 320;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx_bytes = 2u * C::NCH * (uint32_t)rows_per_tile * 128u;
-      for (int j = 0; j < n; ++j) {
-        const int st = j % STAGES;
-        mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+    // (whole warp walks the loop, one elected lane issues: see elect_one() in common.cuh)
+    const uint32_t tx_bytes = 2u * C::NCH * (uint32_t)rows_per_tile * 128u;
+    for (int j = 0; j < n; ++j) {
+      const int st = j % STAGES;
+      mbar_wait(&kv_empty[st], ((j / STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[st], tx_bytes);
 #pragma unroll
         for (int c = 0; c < C::NCH; ++c) {
@@ -181,41 +182,53 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
           }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = windowed ? idesc_bf16(QM, WIN_N, 0) : idesc_bf16(QM, KN, 0);
-      constexpr uint32_t idesc_o = idesc_bf16(QM, HD, 1);
-      const int ksteps_pv = (windowed ? WIN_N : KN) / 16;
-      auto issue_s = [&](int j) {
-        const int st = j % STAGES;
-        mbar_wait(&kv_full[st], (j / STAGES) & 1);
-        tc5_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * C::KV_BYTES);
+    const uint32_t idesc_s = windowed ? idesc_bf16(QM, WIN_N, 0) : idesc_bf16(QM, KN, 0);
+    constexpr uint32_t idesc_o = idesc_bf16(QM, HD, 1);
+    const int ksteps_pv = (windowed ? WIN_N : KN) / 16;
+    auto issue_s = [&](int j) {
+      const int st = j % STAGES;
+      mbar_wait(&kv_full[st], (j / STAGES) & 1);
+      tc5_fence_after();
+      const uint32_t k_addr = smem_u32(sK + st * C::KV_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t koff = (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32;
           mma_ts(tmem_S + (j & 1) * KN, tmem_Q + kk * 8, umma_desc_k_sw128(k_addr + koff), idesc_s, kk > 0 ? 1u : 0u);
         }
         tc5_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_ready, 0);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_ready, 0);
+    tc5_fence_after();
+    issue_s(0);
+    for (int j = 0; j < n; ++j) {
+      if (j + 1 < n) issue_s(j + 1);
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       tc5_fence_after();
-      issue_s(0);
-      for (int j = 0; j < n; ++j) {
-        if (j + 1 < n) issue_s(j + 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc5_fence_after();
-        const uint32_t v_addr = smem_u32(sV + (j % STAGES) * C::KV_BYTES);
-        for (int kk = 0; kk < ksteps_pv; ++kk)
-          mma_ts(tmem_O, tmem_S + (j & 1) * KN + kk * 8, desc_mn_sw128(v_addr + kk * 2048, CHUNK_BYTES), idesc_o,
-                 (j > 0 || kk > 0) ? 1u : 0u);
+      const uint32_t v_addr = smem_u32(sV + (j % STAGES) * C::KV_BYTES);
+      if (elect_one()) {
+        if (windowed) {
+#pragma unroll
+          for (int kk = 0; kk < WIN_N / 16; ++kk)
+            mma_ts(tmem_O, tmem_S + (j & 1) * KN + kk * 8, desc_mn_sw128(v_addr + kk * 2048, CHUNK_BYTES), idesc_o,
+                   (j > 0 || kk > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < KN / 16; ++kk)
+            mma_ts(tmem_O, tmem_S + (j & 1) * KN + kk * 8, desc_mn_sw128(v_addr + kk * 2048, CHUNK_BYTES), idesc_o,
+                   (j > 0 || kk > 0) ? 1u : 0u);
+        }
         tc5_commit(&kv_empty[j % STAGES]);
         tc5_commit(&pv_done[j & 1]);
       }
+      __syncwarp();
     }
-    __syncwarp();
+    (void)ksteps_pv;
   } else {
     const int lane_grp = warp & 3;
     const int half = (warp - 2) >> 2;
