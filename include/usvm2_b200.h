@@ -105,6 +105,13 @@ int usvm_gemm_bf16_tc5(const void* A, int lda, const void* W, int ldw, const usv
  * block_n: 0 = auto, 32 / 64 / 128. */
 int usvm_gemm_tf32_tc5(const float* A, int lda, const float* W, int ldw, const usvm_gemm_epilogue* ep_host, int M, int N,
                        int K, int block_n, void* stream);
+/* Feed-forward block of a memory-attention layer as one kernel (memory_attention.py:92-98):
+ *   out[M,256] = x + relu(h . W1^T + b1) . W2^T + b2,   h = LayerNorm(x) bf16 [M,256], x / out fp32 [M,256] (out may alias
+ * neither), W1 bf16 [2048,256], W2 bf16 [256,2048].  M % 128 == 0, d_model == 256, hidden == 2048.  A cluster of 8 CTAs per
+ * 128-row tile: the hidden activations stay in shared memory, the 8 partial outputs are reduce-scattered through
+ * distributed shared memory in rank order (deterministic). */
+int usvm_ffn_fused_tc5(const void* h_bf16, const float* x, const void* w1, const float* b1, const void* w2,
+                       const float* b2, float* out, int M, int d_model, int hidden, void* stream);
 /* developer aid: clock64() stamps of the persistent GEMM's first 64 tiles on CTA 0 (USVM2_PGEMM_DEBUG & 4), 64 x 16 words */
 int usvm_debug_pgemm_profile(unsigned long long* host_out_1024);
 /* fp32-accumulate SIMT GEMM, operands fp32 or bf16 (flags), any shape: fp32 decoder tail + checker. */

@@ -236,3 +236,28 @@ def test_fused_rope_epilogue_matches_rope_kernel(M, rows_per_batch, n_rope, N, c
     assert bool((d <= 2.0 ** -7 * want.float().abs().clamp_min(1.0)).all()), d.max().item()
     assert (d > 0).float().mean().item() < 0.02  # ... and only where the fp32 value sits on a rounding boundary
     assert torch.equal(got[:, cols:], plain[:, cols:].to(torch.bfloat16))  # columns beyond rope_cols untouched
+
+
+@pytest.mark.parametrize("M", [128, 1024, 4096])
+def test_ffn_fused_matches_two_gemms_and_fp32(M):
+    """usvm_ffn_fused_tc5 (cluster of 8 CTAs per row tile, hidden activations in shared memory, DSMEM reduce-scatter) vs
+    the fp32 composition on the same bf16 operands (hidden rounded to bf16 like the kernel does) and vs the two-launch
+    path it replaces; two runs are bit-identical (fixed summation order)."""
+    from us_video_medsam2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = torch.randn((M, 256), generator=g, device="cuda")
+    h = torch.randn((M, 256), generator=g, device="cuda").to(torch.bfloat16)
+    w1 = (torch.randn((2048, 256), generator=g, device="cuda") * 256 ** -0.5).to(torch.bfloat16)
+    w2 = (torch.randn((256, 2048), generator=g, device="cuda") * 2048 ** -0.5).to(torch.bfloat16)
+    b1 = torch.randn((2048,), generator=g, device="cuda") * 0.1
+    b2 = torch.randn((256,), generator=g, device="cuda") * 0.1
+    out = ops.ffn_fused(h, x, w1, b1, w2, b2)
+    torch.cuda.synchronize()
+    hid = torch.relu(h.float() @ w1.float().t() + b1).to(torch.bfloat16).float()
+    want = x + hid @ w2.float().t() + b2
+    assert (out - want).abs().max().item() < 2e-3
+    _, m = ops.gemm_bf16(h, w1, bias=b1, act=ops.ACT_RELU, bf16=True)
+    two, _ = ops.gemm_bf16(m, w2, bias=b2, residual=x, f32=True)
+    assert (out - two).abs().max().item() < 1e-3
+    assert torch.equal(out, ops.ffn_fused(h, x, w1, b1, w2, b2))

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "usvm_gemm_bf16_tc5": [_P, _I, _P, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _I, _P],
     "usvm_gemm_tf32_tc5": [_P, _I, _P, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _I, _P],
     "usvm_debug_pgemm_profile": [_P],
+    "usvm_ffn_fused_tc5": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "usvm_gemm_simt": [_P, _I, _I, _P, _I, _I, C.POINTER(GemmEpilogue), _I, _I, _I, _P],
     "usvm_fmha_bf16": [C.POINTER(FmhaParams), _P],
     "usvm_fmha_tc5": [C.POINTER(FmhaParams), _P],

@@ -379,6 +379,8 @@ class Engine:
         self.fused_windows = os.environ.get("USVM2_FUSED_WINDOWS", "1") != "0"
         # global / 14 x 14 windowed encoder attention on the tcgen05 kernel (0: the mma.sync kernels, kept for comparison)
         self.tc5_encoder_attn = os.environ.get("USVM2_ENCODER_ATTN_TC5", "1") != "0"
+        # memory-attention feed-forward block as one cluster kernel up to 8 objects (0: two GEMM launches)
+        self.fused_ffn = os.environ.get("USVM2_FUSED_FFN", "1") != "0"
 
     # ---------------------------------------------------------------- forked branches
     def _side(self, i):
@@ -535,8 +537,12 @@ class Engine:
                          (li * 256, Nk * 1024, 1024, 256), num_splits=self._splits(B, Nk))
             x, h = ops.gemm_bf16(o.view(B * T, 256), L["ca_o"][0], bias=L["ca_o"][1], residual=x, f32=True,
                                  ln=(L["n3"][0], L["n3"][1], 1e-5))
-            _, m = ops.gemm_bf16(h, L["l1"][0], bias=L["l1"][1], act=ACT_RELU, bf16=True)
-            x, _ = ops.gemm_bf16(m, L["l2"][0], bias=L["l2"][1], residual=x, f32=True)
+            if self.fused_ffn and B * T <= 8192:
+                # linear1 + ReLU + linear2 + residual as one cluster kernel: the hidden activations stay on the SM
+                x = ops.ffn_fused(h, x, L["l1"][0], L["l1"][1], L["l2"][0], L["l2"][1])
+            else:
+                _, m = ops.gemm_bf16(h, L["l1"][0], bias=L["l1"][1], act=ACT_RELU, bf16=True)
+                x, _ = ops.gemm_bf16(m, L["l2"][0], bias=L["l2"][1], residual=x, f32=True)
         out, _ = ops.layernorm(x, *(w.ma_norm_nomask if fold_no_mask else w.ma_norm), 1e-5, f32=True)
         return out
 

@@ -143,6 +143,18 @@ _FMHA_PART_BF16 = os.environ.get("USVM2_FMHA_PART_BF16", "1") != "0"
 _FMHA_IMPL = os.environ.get("USVM2_FMHA", "tc5")  # "tc5" (tcgen05 where the shape allows) | "mma" (mma.sync only)
 
 
+def ffn_fused(h, x, w1, b1, w2, b2):
+    """x + relu(h @ w1^T + b1) @ w2^T + b2 as one cluster kernel (memory-attention feed-forward block):
+    h bf16 [M,256] = LayerNorm(x), x fp32 [M,256]; returns a new fp32 [M,256]."""
+    _chk(h, BF16, "h"), _chk(x, F32, "x"), _chk(w1, BF16, "w1"), _chk(w2, BF16, "w2")
+    M, D = x.shape
+    Hd = w1.shape[0]
+    out = empty((M, D), F32, x)
+    call("usvm_ffn_fused_tc5", h.data_ptr(), x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+         out.data_ptr(), M, D, Hd, _stream())
+    return out
+
+
 def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_splits=1, impl=None):
     """q/k/v: bf16 tensors; *_addr = (element offset, batch stride, row stride, head stride).
     Returns bf16 [B, Nq, H*head_dim].  head_dim 256 / one head / Nq % 128 == 0 / contiguous batches run on the
