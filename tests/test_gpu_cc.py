@@ -237,3 +237,33 @@ def test_largest_component_3d_edge_cases():
     assert np.array_equal(got, largest_component_3d_ref(tie)) and got[0, 0, 0] and not got[2, 5, 5]
     with pytest.raises(RuntimeError):
         get_largest_cc(torch.zeros((4, 8, 8), dtype=torch.uint8))
+
+
+def test_fill_holes_across_tile_boundaries():
+    """The fill kernel is tiled (32 x 32 cores + a halo of max_area): small and just-too-large background structures that
+    straddle core boundaries, touch the halo's outermost ring or the image edge, and a long thin component whose fragment
+    inside a window is small (it must stay open through the foreign border)."""
+    from sam2.utils.misc import fill_holes_in_mask_scores
+
+    H, W = 128, 160
+    s = torch.ones((3, 1, H, W))
+    s[0, 0, 31, 28:36] = -1           # area 8 across x = 32            -> filled
+    s[0, 0, 40, 28:37] = -1           # area 9 across x = 32            -> kept
+    s[0, 0, 60:68, 63] = -1           # vertical bar of 8 across y = 64 -> filled
+    for i in range(8):
+        s[0, 0, 92 + i, 92 + i] = -1  # diagonal across (96, 96)        -> filled
+    s[0, 0, 0, 60:68] = -1            # on the image edge, across x = 64 -> filled
+    s[0, 0, H - 1, W - 8:W] = -1      # in the image corner              -> filled
+    s[1, 0, 33, :] = -1               # one image-wide line: every window sees a short-looking fragment -> kept
+    s[1, 0, 20:60, 70] = -1           # long vertical line                -> kept
+    s[1, 0, 100, 30:38] = -1          # area 8 next to nothing            -> filled
+    s[2, 0, 24:40, 24:40] = -1        # 16 x 16 block over a core corner  -> kept
+    s[2, 0, 31:33, 95:97] = -1        # 2 x 2 over the corner (32, 96)    -> filled
+    s[2, 0, 70, 56:64] = -1           # area 8 ending at x = 63           -> filled
+    s[2, 0, 71, 64] = -1              # ... touching it diagonally: now area 9 -> both kept
+    labels, areas = connected_components_ref((s <= 0).numpy().astype(np.uint8))
+    want = torch.where(torch.from_numpy((labels > 0) & (areas <= 8)), torch.full_like(s, 0.1), s)
+    got = fill_holes_in_mask_scores(s.cuda(), 8).cpu()
+    assert torch.equal(got, want)
+    assert float(got[0, 0, 31, 30]) == pytest.approx(0.1) and float(got[0, 0, 40, 30]) == -1.0
+    assert float(got[1, 0, 33, 5]) == -1.0 and float(got[2, 0, 70, 60]) == -1.0

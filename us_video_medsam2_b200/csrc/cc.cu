@@ -212,34 +212,49 @@ __global__ void cc_g_roots(FG fg, int32_t* labels, int32_t* counts, const float*
 // pair of different labels, which marks both groups open.  Synchronous (ping-pong) rounds also bound every group to
 // the (2 max_area + 1)^2 window around its label, so the per-label atomic counters never see more than a few hundred
 // increments (a giant component would otherwise serialise thousands of atomics on one address).
-// One CTA per image, everything in shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int kNoLabel = 0x7fffffff;
 
-// Each thread owns a 4 x 4 pixel tile (labels in registers, 6 x 6 halo read from shared memory once per round), the
-// label planes carry a one-pixel border of kNoLabel so the stencil needs no bounds checks.
-__global__ void __launch_bounds__(1024)
-fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W, int max_area, float fill_value) {
+// TILED over the image: because a component of area <= max_area containing a given pixel lies within Chebyshev
+// distance max_area - 1 of it, a CTA that owns a 32 x 32 core only needs the window core + R (R = max_area rounded up to
+// a multiple of 4) to decide its own pixels.  Window edges that are NOT image edges carry a one-pixel border of
+// kForeign: a group touching it is marked open (a fragment of a component that continues outside the window always has a
+// member on the window's outermost ring, a genuine small hole of a core pixel never reaches that ring), image edges carry
+// kNoLabel as before.  16 CTAs of 256 threads per 128 x 128 image instead of one CTA of 1024 (47 us on a single SM).
+// Each thread owns 4 x 4 pixel tiles (labels in registers, 6 x 6 halo read from shared memory once per round).
+constexpr int kForeign = 0x7ffffffe;
+constexpr int kFillCore = 32;
+
+__global__ void __launch_bounds__(256)
+fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W, int max_area, float fill_value, int R) {
   PDL_ENTRY();
   extern __shared__ int s_mem[];
-  const int HW = H * W, Wp = W + 2, plane = (H + 2) * Wp;
-  int* s_a = s_mem;             // labels, ping   [(H+2) x (W+2)]
-  int* s_b = s_mem + plane;     // labels, pong
+  // window of this CTA (clamped to the image); all coordinates multiples of 4
+  const int cx0 = blockIdx.x * kFillCore, cy0 = blockIdx.y * kFillCore;
+  const int wx0 = max(0, cx0 - R), wy0 = max(0, cy0 - R);
+  const int wx1 = min(W, cx0 + kFillCore + R), wy1 = min(H, cy0 + kFillCore + R);
+  const int ww = wx1 - wx0, wh = wy1 - wy0;
+  const int Wp = ww + 2, plane = (wh + 2) * Wp, npix = ww * wh;
+  int* s_a = s_mem;                // labels, ping   [(wh+2) x (ww+2)]
+  int* s_b = s_mem + plane;        // labels, pong
   int* s_cnt = s_mem + 2 * plane;  // per-label closed-member count (open members add 2^20)
-  const long long base = (long long)blockIdx.x * HW;
+  const long long base = (long long)blockIdx.z * H * W;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < plane; i += nt) {
-    s_a[i] = kNoLabel;
-    s_b[i] = kNoLabel;
+    const int r = i / Wp - 1, c = i - (r + 1) * Wp - 1;  // window coordinates of this plane entry (-1 / wh / ww: border)
+    int v = kNoLabel;
+    if (r < 0 || r >= wh || c < 0 || c >= ww) {
+      const int gy = wy0 + r, gx = wx0 + c;
+      v = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? kForeign : kNoLabel;
+    } else if (scores_in[base + (long long)(wy0 + r) * W + wx0 + c] <= 0.0f) {
+      v = r * ww + c;
+    }
+    s_a[i] = v;
+    s_b[i] = v;  // borders stay put in both planes; interior entries are rewritten every round
   }
-  for (int i = tid; i < HW; i += nt) s_cnt[i] = 0;
+  for (int i = tid; i < npix; i += nt) s_cnt[i] = 0;
   __syncthreads();
-  for (int i = tid; i < HW; i += nt) {
-    const int r = i / W, c = i - r * W;
-    if (scores_in[base + i] <= 0.0f) s_a[(r + 1) * Wp + c + 1] = i;
-  }
-  __syncthreads();
-  const int tiles_x = W >> 2, tiles = (H >> 2) * tiles_x;
+  const int tiles_x = ww >> 2, tiles = (wh >> 2) * tiles_x;
   int* cur = s_a;
   int* nxt = s_b;
   for (int round = 0; round < max_area; ++round) {
@@ -259,6 +274,7 @@ fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W,
           int m = min(min(min(v[y - 1][x - 1], v[y - 1][x]), min(v[y - 1][x + 1], v[y][x - 1])),
                       min(min(v[y][x + 1], v[y + 1][x - 1]), min(v[y + 1][x], v[y + 1][x + 1])));
           m = min(m, v[y][x]);
+          // (kForeign is larger than every pixel label: it never wins the minimum of a mask pixel)
           dst[(y - 1) * Wp + (x - 1)] = v[y][x] == kNoLabel ? kNoLabel : m;
         }
     }
@@ -293,12 +309,15 @@ fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W,
       }
   }
   __syncthreads();
-  for (int i = tid; i < HW; i += nt) {
-    const int r = i / W, c = i - r * W;
-    const int me = cur[(r + 1) * Wp + c + 1];
-    const float v = scores_in[base + i];
+  // write back the core only
+  const int cw = min(kFillCore, W - cx0), ch = min(kFillCore, H - cy0);
+  for (int i = tid; i < cw * ch; i += nt) {
+    const int r = i / cw, c = i - r * cw;
+    const int wr = cy0 + r - wy0, wc = cx0 + c - wx0;
+    const int me = cur[(wr + 1) * Wp + wc + 1];
+    const long long g = base + (long long)(cy0 + r) * W + cx0 + c;
     const bool hole = me != kNoLabel && s_cnt[me] <= max_area;
-    scores_out[base + i] = hole ? fill_value : v;
+    scores_out[g] = hole ? fill_value : scores_in[g];
   }
 }
 
@@ -429,8 +448,10 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
   if (!scores_in || !scores_out) return USVM_ERR_ARG;
   if ((long long)H * W >= (1LL << 31) - 1 || N > 65535) return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const size_t local_bytes = ((size_t)2 * (H + 2) * (W + 2) + (size_t)H * W) * 4;
-  if (max_area <= 32 && local_bytes <= kSmemLimit && (H % 4) == 0 && (W % 4) == 0) {  // the propagation path's case: 128 x 128, max_area 8
+  if (max_area <= 32 && (H % 4) == 0 && (W % 4) == 0) {  // the propagation path's case: 128 x 128, max_area 8
+    const int R = (max_area + 3) & ~3;
+    const int win = kFillCore + 2 * R;
+    const size_t local_bytes = ((size_t)2 * (win + 2) * (win + 2) + (size_t)win * win) * 4;
     static bool configured = false;
     if (!configured) {
       if (cudaFuncSetAttribute(fill_holes_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) !=
@@ -438,7 +459,8 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
         return USVM_ERR_CUDA;
       configured = true;
     }
-    usvm_launch(fill_holes_local_kernel, dim3(N), dim3(1024), local_bytes, s, scores_in, scores_out, H, W, max_area, fill_value);
+    usvm_launch(fill_holes_local_kernel, dim3(cdiv(W, kFillCore), cdiv(H, kFillCore), N), dim3(256), local_bytes, s, scores_in,
+                scores_out, H, W, max_area, fill_value, R);
     return usvm_check_launch();
   }
   if (smem_bytes(H, W) <= kSmemLimit)
