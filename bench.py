@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=512, help="clip length T (BASELINE config 2: 512)")
     ap.add_argument("--objects", type=int, default=1)
     ap.add_argument("--encoder-batch", type=int, default=16, help="frames per batched image-encoder pass")
-    ap.add_argument("--encoder-sms", type=int, default=64,
+    ap.add_argument("--encoder-sms", type=int, default=48,
                     help="> 0: look-ahead encoder batches run concurrently with tracking on an SM partition of this size")
     ap.add_argument("--mode", default="videos", choices=["videos", "clip"],
                     help="N > 1: 'videos' = one independent clip per GPU (weak scaling, no communication); 'clip' = ONE "
