@@ -111,5 +111,40 @@ if which == "r2set":  # round-2 `ncu --set full` set: throughput GEMM shapes + t
     q, kv = rnd(B * T, D), rnd(B * Nk, 4 * D)
     for _ in range(REPS):
         ops.fmha(q, kv, kv, B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D))
+if which == "r2b":  # second round-2 `ncu --set full` set: the kernels written after r2set (see profiles/r2b_kernel_set_ncu.md)
+    f32 = torch.float32
+
+    def gemm(M, N, K, act=0, f32out=False, res=False):
+        a, w, b = rnd(M, K), rnd(N, K, sc=K ** -0.5), rnd(N, dt=f32)
+        r = rnd(M, N, dt=f32) if res else None
+        ops.gemm_bf16(a, w, bias=b, act=act, residual=r, f32=f32out, bf16=not f32out)
+
+    # persistent GEMM, weight-stationary schedule (16 frames): stage-3 qkv / MLP up + GELU, stage-1 MLP up + GELU;
+    # streaming schedule: stage-3 MLP down (K = 1536)
+    gemm(16384, 1152, 384)
+    gemm(16384, 1536, 384, act=ops.ACT_GELU)
+    gemm(262144, 384, 96, act=ops.ACT_GELU)
+    gemm(16384, 384, 1536, f32out=True, res=True)
+    gemm(32768, 2048, 256, act=ops.ACT_RELU)   # memory-attention FFN linear1 at 32 objects
+    # encoder attention on tcgen05: global and 14 x 14 windowed, 16 frames x 4 heads of 96
+    Fr, Hh, C, heads = 16, 32, 384, 4
+    qkv = rnd(Fr * Hh * Hh, 3 * C)
+    bias = rnd(3 * C, dt=f32)
+    ops.hiera_attn(qkv, bias, Fr, Hh, Hh, C, heads, 0)
+    ops.hiera_attn(qkv, bias, Fr, Hh, Hh, C, heads, 14)
+    # fused feed-forward block at one object and at 8 objects
+    for M in (1024, 8192):
+        x, h = rnd(M, 256, dt=f32), rnd(M, 256)
+        w1, w2 = rnd(2048, 256, sc=1 / 16), rnd(256, 2048, sc=1 / 45)
+        ops.ffn_fused(h, x, w1, rnd(2048, dt=f32), w2, rnd(256, dt=f32))
+    # tiled hole filling at 1 and 32 objects
+    for B in (1, 32):
+        ops.fill_holes(rnd(B, 1, 128, 128, dt=f32, sc=0.07), 8)
+    # cross-attention: one object (12-way split, as planned beside the encoder partition) and 32 objects (no split)
+    T, Nk, D = 1024, 7232, 256
+    for B, splits in ((1, 12), (32, 1)):
+        q, kv = rnd(B * T, D), rnd(B * Nk, 4 * D)
+        ops.fmha(q, kv, kv, B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D), (2 * D, Nk * 4 * D, 4 * D, D),
+                 num_splits=splits)
 torch.cuda.synchronize()
 print("done")
