@@ -335,12 +335,12 @@ void launch_combine(const usvm_fmha_params* p, long long rows, cudaStream_t s) {
 
 template <int D>
 int launch_fmha(const usvm_fmha_params* p, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static UsvmPerDeviceOnce attr = {};
+  if (usvm_need_setup(attr)) {
     if (cudaFuncSetAttribute(fmha_bf16_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, FmhaSmem<D>::BYTES) !=
         cudaSuccess)
       return USVM_ERR_CUDA;
-    attr = true;
+    usvm_setup_done(attr);
   }
   dim3 grid(cdiv(p->Nq, FM), p->B * p->H, p->num_splits);
   usvm_launch(fmha_bf16_kernel<D>, dim3(grid), dim3(FTHREADS), FmhaSmem<D>::BYTES, s, *p);

@@ -401,12 +401,12 @@ template <bool FILL>
 int launch_smem(const uint8_t* img, const float* sin, float* sout, int32_t* labels, int32_t* counts, int N, int H,
                 int W, int max_area, float fill, cudaStream_t s) {
   const size_t bytes = smem_bytes(H, W);
-  static size_t configured = 0;
-  if (bytes > 48 * 1024 && bytes > configured) {
+  static UsvmPerDeviceOnce configured = {};
+  if (bytes > 48 * 1024 && usvm_need_setup(configured)) {
     if (cudaFuncSetAttribute(cc_smem_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) !=
         cudaSuccess)
       return USVM_ERR_CUDA;
-    configured = kSmemLimit;
+    usvm_setup_done(configured);
   }
   const int threads = (H * W >= 1024 * 4) ? 1024 : 256;
   usvm_launch(cc_smem_kernel<FILL>, dim3(N), dim3(threads), bytes, s, img, sin, sout, labels, counts, H, W, max_area, fill);
@@ -452,12 +452,12 @@ extern "C" int usvm_fill_holes_f32(const float* scores_in, float* scores_out, in
     const int R = (max_area + 3) & ~3;
     const int win = kFillCore + 2 * R;
     const size_t local_bytes = ((size_t)2 * (win + 2) * (win + 2) + (size_t)win * win) * 4;
-    static bool configured = false;
-    if (!configured) {
+    static UsvmPerDeviceOnce configured = {};
+    if (usvm_need_setup(configured)) {
       if (cudaFuncSetAttribute(fill_holes_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit) !=
           cudaSuccess)
         return USVM_ERR_CUDA;
-      configured = true;
+      usvm_setup_done(configured);
     }
     usvm_launch(fill_holes_local_kernel, dim3(cdiv(W, kFillCore), cdiv(H, kFillCore), N), dim3(256), local_bytes, s, scores_in,
                 scores_out, H, W, max_area, fill_value, R);

@@ -23,6 +23,21 @@ static inline int usvm_check_launch() {
 }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Kernel attributes (cudaFuncSetAttribute) are per DEVICE: the one-time guards are kept per device ordinal, so a process
+// that moves on to another GPU (predictor.to("cuda:1") after running on cuda:0) configures its kernels there too.
+struct UsvmPerDeviceOnce {
+  bool done[64];
+};
+static inline bool usvm_need_setup(const UsvmPerDeviceOnce& o) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+  return !o.done[d];
+}
+static inline void usvm_setup_done(UsvmPerDeviceOnce& o) {
+  int d = 0;
+  if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) o.done[d] = true;
+}
+
 // Every kernel of the library is launched with programmatic stream serialization (PDL): the next kernel of the stream
 // (or of the captured graph) is scheduled while the current one is still running and parks in `griddepcontrol.wait`
 // until its predecessor has completed and flushed, so its launch latency and prologue leave the critical path of the

@@ -199,12 +199,12 @@ int launch_conv_tile(const float* x, const float* w, const float* bias, const fl
   constexpr int TW = PIX == 256 ? 16 : PIX == 64 ? 8 : 4;
   const int IW = (TW - 1) * s + k;
   const size_t smem = ((size_t)k * k * CIN * COUT + (size_t)IW * IW * CIN) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static UsvmPerDeviceOnce configured = {};
+  if (usvm_need_setup(configured)) {
     if (cudaFuncSetAttribute(conv2d_tile_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
         cudaSuccess)
       return USVM_ERR_CUDA;
-    configured = true;
+    usvm_setup_done(configured);
   }
   if (smem > 96 * 1024) return USVM_ERR_ARG;
   usvm_launch(conv2d_tile_kernel<CIN, COUT>, dim3(B * (Ho / TW) * (Wo / TW)), dim3(256), smem, stream, x, w, bias, ln_w, ln_b,
@@ -523,11 +523,11 @@ extern "C" int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* 
   if (!x || !w_49c || !bias || !ln_w || !ln_b || !out_bf16 || C != 256) return USVM_ERR_ARG;
   if (W % DW_TILE == 0 && !(reinterpret_cast<uintptr_t>(x) & 15)) {
     const int smem = (7 * DW_FOOT * 256 + 8 * DW_TILE) * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static UsvmPerDeviceOnce configured = {};
+    if (usvm_need_setup(configured)) {
       if (cudaFuncSetAttribute(dwconv7_ln_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return USVM_ERR_CUDA;
-      configured = true;
+      usvm_setup_done(configured);
     }
     usvm_launch(dwconv7_ln_tile_kernel, dim3(B * H * (W / DW_TILE)), dim3(256), smem, STREAM, x, w_49c, bias, ln_w, ln_b,
                 eps, reinterpret_cast<bf16*>(out_bf16), B, H, W);

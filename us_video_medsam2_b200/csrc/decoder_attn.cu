@@ -486,12 +486,12 @@ extern "C" int usvm_gemm_skinny_f32(const usvm_skinny_params* p, void* stream) {
   if (p->ln_w && (p->K != 256 || !p->ln_b)) return USVM_ERR_ARG;
   const size_t smem = ((size_t)SK_ROWS * p->K * 2 + SK_WARPS * 32) * sizeof(float);
   if (smem > 200 * 1024) return USVM_ERR_ARG;
-  static bool configured = false;
-  if (!configured) {
+  static UsvmPerDeviceOnce configured = {};
+  if (usvm_need_setup(configured)) {
     if (cudaFuncSetAttribute(gemm_skinny_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_skinny_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return USVM_ERR_CUDA;
-    configured = true;
+    usvm_setup_done(configured);
   }
   if (p->K >= 1024) {  // long reduction: the CTA's 8 warps split K, one CTA per 4 columns
     dim3 grid(cdiv(p->N, SK_COLS), p->instances, cdiv(p->M, SK_ROWS));
@@ -507,12 +507,12 @@ extern "C" int usvm_attn_t2i_f32(const float* q, int q_rs, const float* k, const
                                  int o_rs, int B, int H, int Nt, int Nk, float scale, void* stream) {
   if (!q || !k || !v || !out || B <= 0 || H <= 0 || Nt <= 0 || Nt > T2I_MAX_NT || Nk <= 0 || (kv_rs % 4)) return USVM_ERR_ARG;
   const size_t smem = ((size_t)2 * Nk * T2I_LD + (size_t)Nt * Nk + Nt * T2I_DH + 16 * Nt * T2I_DH) * sizeof(float);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    if (smem > 200 * 1024) return USVM_ERR_ARG;
+  if (smem > 200 * 1024) return USVM_ERR_ARG;
+  static UsvmPerDeviceOnce configured = {};
+  if (smem > 48 * 1024 && usvm_need_setup(configured)) {
     if (cudaFuncSetAttribute(attn_t2i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return USVM_ERR_CUDA;
-    configured = 200 * 1024;
+    usvm_setup_done(configured);
   }
   usvm_launch(attn_t2i_kernel, dim3(B * H), dim3(256), smem, STREAM, q, q_rs, k, v, kv_rs, out, o_rs, H, Nt, Nk, scale);
   return usvm_check_launch();

@@ -400,12 +400,12 @@ extern "C" int usvm_fmha_tc5(const usvm_fmha_params* p, void* stream) {
   if (rc) return rc;
   rc = make_map(&tv, p->v, (long long)p->B * p->Nk, HD, p->v_rs, KN);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) {
+  static UsvmPerDeviceOnce attr = {};
+  if (usvm_need_setup(attr)) {
     if (cudaFuncSetAttribute(fmha_tc5_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES) !=
         cudaSuccess)
       return USVM_ERR_CUDA;
-    attr = true;
+    usvm_setup_done(attr);
   }
   dim3 grid(p->Nq / QM, p->B, p->num_splits);
   usvm_launch(fmha_tc5_ts_kernel, dim3(grid), dim3(THREADS), TS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), tk, tv, *p);

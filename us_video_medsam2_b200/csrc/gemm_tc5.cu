@@ -902,13 +902,13 @@ int launch(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilo
                   CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static UsvmPerDeviceOnce attr_set = {};
+  if (usvm_need_setup(attr_set)) {
     const int want = 227 * 1024;  // ring + staging (+ split-K partials) are sized per launch, always below this
     if (cudaFuncSetAttribute(gemm_bf16_tc5_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, want) !=
         cudaSuccess)
       return USVM_ERR_CUDA;
-    attr_set = true;
+    usvm_setup_done(attr_set);
   }
   const int num_kb = cdiv(K, TF32 ? BK / 2 : BK);
   dim3 grid(cdiv(M, BM), cdiv(N, BN));

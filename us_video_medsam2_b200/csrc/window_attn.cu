@@ -321,11 +321,11 @@ extern "C" int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, voi
   const int rows_k = nk <= 16 ? 16 : (nk + 63) & ~63, rows_q = (nq + 15) & ~15;
   const size_t smem = (size_t)(rows_q + 2 * rows_k) * (hc * WA_D + 8) * sizeof(bf16);
   if (smem > 200 * 1024) return USVM_ERR_ARG;
-  static bool configured = false;
-  if (!configured) {
+  static UsvmPerDeviceOnce configured = {};
+  if (usvm_need_setup(configured)) {
     if (cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return USVM_ERR_CUDA;
-    configured = true;
+    usvm_setup_done(configured);
   }
   const int nw = cdiv(Hg, ws) * cdiv(Wg, ws);
   usvm_launch(window_attn_kernel, dim3(F * nw, cdiv(heads, heads_per_cta)), dim3(WA_THREADS), smem,
