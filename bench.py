@@ -317,20 +317,16 @@ def time_dominant_kernel(dev, B, iters=20):
 
 
 def time_other_kernels(dev, B):
-    """The launch list (profiles/r1_launch_lists.md) shows no single kernel above 19 % of a one-object frame: the one-tile
-    GEMM family carries the largest share by time, the cross-attention pair by FLOPs.  For transparency the two most
-    frequent GEMM shapes of the memory attention are timed too -- 20 launches captured in one CUDA graph (as they run in
-    the frame: no host launch overhead between them), L2 warm (their operands are the previous kernel's output)."""
+    """The launch list (profiles/r2b_launches_tracked_frames.csv) shows no single kernel above 19 % of a one-object frame:
+    the one-tile GEMM family carries the largest share by time, the cross-attention pair by FLOPs.  For transparency the
+    most frequent GEMM shape of the memory attention, its fused feed-forward block and the encoder's tcgen05 attention
+    are timed too -- 20 launches captured in one CUDA graph (as they run in the frame: no host launch overhead between
+    them), L2 warm (their operands are the previous kernel's output)."""
     from us_video_medsam2_b200 import ops
 
     g = torch.Generator(device=dev).manual_seed(1)
-    out = []
-    for name, (M, N, K) in (("memory-attention qkv / q / out projections (gemm_bf16_tc5_kernel<32>)", (1024 * B, 768, 256)),
-                            ("memory-attention FFN linear1 (gemm_bf16_tc5_kernel)", (1024 * B, 2048, 256))):
-        a = torch.randn((M, K), generator=g, device=dev).to(torch.bfloat16)
-        w = (torch.randn((N, K), generator=g, device=dev) * K ** -0.5).to(torch.bfloat16)
-        bias = torch.randn((N,), generator=g, device=dev)
-        fn = lambda: ops.gemm_bf16(a, w, bias=bias, bf16=True)
+
+    def graph_us(fn):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -346,9 +342,35 @@ def time_other_kernels(dev, B):
             graph.replay()
         e.record()
         torch.cuda.synchronize()
-        us = s.elapsed_time(e) / 100 * 1e3
-        out.append({"kernel": name, "shape_mnk": [M, N, K], "avg_us": us, "achieved_tflops": 2.0 * M * N * K / us / 1e6,
-                    "bound": "latency (one 128-row tile per CTA, 0.4-1.1 GFLOP per launch)"})
+        return s.elapsed_time(e) / 100 * 1e3
+
+    out = []
+    M, N, K = 1024 * B, 768, 256
+    a = torch.randn((M, K), generator=g, device=dev).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device=dev) * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g, device=dev)
+    us = graph_us(lambda: ops.gemm_bf16(a, w, bias=bias, bf16=True))
+    out.append({"kernel": "memory-attention qkv / q / out projections (gemm_bf16_tc5_kernel<32>)", "shape_mnk": [M, N, K],
+                "avg_us": us, "achieved_tflops": 2.0 * M * N * K / us / 1e6,
+                "bound": "latency (one 128-row tile per CTA, 0.4 GFLOP per launch)"})
+    if M <= 2048:  # (the engine uses the fused kernel at one or two objects)
+        x = torch.randn((M, 256), generator=g, device=dev)
+        w1 = (torch.randn((2048, 256), generator=g, device=dev) / 16).to(torch.bfloat16)
+        w2 = (torch.randn((256, 2048), generator=g, device=dev) / 45).to(torch.bfloat16)
+        b1, b2 = torch.randn((2048,), generator=g, device=dev), torch.randn((256,), generator=g, device=dev)
+        us = graph_us(lambda: ops.ffn_fused(a, x, w1, b1, w2, b2))
+        out.append({"kernel": "memory-attention feed-forward block (ffn_fused_tc5_kernel: linear1 + ReLU + linear2 + residual)",
+                    "shape_mnk": [M, 2048, 256], "avg_us": us, "achieved_tflops": 4.0 * M * 2048 * 256 / us / 1e6,
+                    "bound": "latency (cluster of 8 CTAs per 128-row tile, reduce-scatter through distributed shared memory)"})
+    Fr, C, heads = 16, 384, 4
+    qkv = torch.randn((Fr * 1024, 3 * C), generator=g, device=dev).to(torch.bfloat16)
+    qb = torch.randn((3 * C,), generator=g, device=dev)
+    for ws, nm in ((0, "global, 1024 x 1024 per head"), (14, "14 x 14 windows, padding tokens in closed form")):
+        us = graph_us(lambda: ops.hiera_attn(qkv, qb, Fr, 32, 32, C, heads, ws))
+        fl = 4.0 * Fr * heads * (1024 * 1024 if ws == 0 else 9 * 196 * 196) * 96
+        out.append({"kernel": f"image-encoder attention, 16 frames x 4 heads of 96 (hiera_attn_tc5_kernel: {nm})",
+                    "avg_us": us, "achieved_tflops": fl / us / 1e6,
+                    "bound": "tensor (bf16), per tile softmax (MUFU) bound; FLOPs of padded windows counted"})
     return out
 
 

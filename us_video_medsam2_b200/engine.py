@@ -379,7 +379,7 @@ class Engine:
         self.fused_windows = os.environ.get("USVM2_FUSED_WINDOWS", "1") != "0"
         # global / 14 x 14 windowed encoder attention on the tcgen05 kernel (0: the mma.sync kernels, kept for comparison)
         self.tc5_encoder_attn = os.environ.get("USVM2_ENCODER_ATTN_TC5", "1") != "0"
-        # memory-attention feed-forward block as one cluster kernel up to 8 objects (0: two GEMM launches)
+        # memory-attention feed-forward block as one cluster kernel at one or two objects (0: two GEMM launches)
         self.fused_ffn = os.environ.get("USVM2_FUSED_FFN", "1") != "0"
 
     # ---------------------------------------------------------------- forked branches
@@ -537,7 +537,7 @@ class Engine:
                          (li * 256, Nk * 1024, 1024, 256), num_splits=self._splits(B, Nk))
             x, h = ops.gemm_bf16(o.view(B * T, 256), L["ca_o"][0], bias=L["ca_o"][1], residual=x, f32=True,
                                  ln=(L["n3"][0], L["n3"][1], 1e-5))
-            if self.fused_ffn and B * T <= 8192:
+            if self.fused_ffn and B * T <= 2048:  # (one wave of clusters: 8 CTAs per 128 rows; measured slower from 4 objects on)
                 # linear1 + ReLU + linear2 + residual as one cluster kernel: the hidden activations stay on the SM
                 x = ops.ffn_fused(h, x, L["l1"][0], L["l1"][1], L["l2"][0], L["l2"][1])
             else:
