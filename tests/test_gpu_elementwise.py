@@ -489,3 +489,25 @@ def test_gelu_epilogue_is_fp32_accurate():
     m = want.abs() > 1e-4
     assert (err[m] / want[m].abs()).max().item() < 1e-3
     assert (got - F.gelu(x).double()).abs().max().item() < 2.5e-6  # vs torch's fp32 kernel
+
+
+def test_tcgen05_gemm_gelu_epilogue_is_fp32_accurate():
+    """The GELU of the tcgen05 GEMM epilogues against the exact erf form in float64: an identity GEMM over every bf16 value
+    of [-12, 12] (bf16 operands are exact), both through the one-tile kernel and the persistent one."""
+    from us_video_medsam2_b200 import ops
+
+    bits = torch.arange(0, 65536, dtype=torch.int32)
+    vals = bits.to(torch.int16).view(torch.bfloat16).float()
+    vals = vals[torch.isfinite(vals) & (vals.abs() <= 12.0)]
+    n = (vals.numel() // 64) * 64
+    x = vals[:n].view(-1, 64).to(torch.bfloat16).cuda().contiguous()
+    eye = torch.eye(64, device="cuda", dtype=torch.bfloat16)
+    want = F.gelu(x.double())
+    for reps, block_n in ((1, 0), (64, -1)):  # the second case is large enough for the persistent kernel
+        xs = x.repeat(reps, 1)
+        got, _ = ops.gemm_bf16(xs, eye, act=ops.ACT_GELU, f32=True, block_n=block_n)
+        err = (got[: x.shape[0]].double() - want).abs()
+        assert err.max().item() < 1e-6, (block_n, err.max().item())
+        m = want.abs() > 1e-2
+        assert (err[m] / want[m].abs()).max().item() < 2e-5
+        assert torch.equal(got[: x.shape[0]], got[-x.shape[0]:])
