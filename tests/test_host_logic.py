@@ -114,6 +114,48 @@ def test_video_sharding_world_size_2_gloo():
     assert res[0][2] == want and res[1][2] == want
 
 
+class _StubPredictor:
+    """Stand-in with the predictor's session surface: the 'mask' of object k on frame t has k + t foreground pixels."""
+    non_overlap_masks = False
+
+    def init_state(self, images, height, width):
+        return {"ids": [], "T": images.shape[0]}
+
+    def add_new_mask(self, st, frame, obj_id, mask):
+        st["ids"].append(obj_id)
+
+    def propagate_in_video(self, st):
+        for t in range(st["T"]):
+            logits = torch.full((len(st["ids"]), 1, 4, 4), -1.0)
+            for j, k in enumerate(st["ids"]):
+                logits[j].view(-1)[: k + t] = 1.0
+            yield t, list(st["ids"]), logits
+
+
+def test_object_sharding_of_one_clip():
+    """Objects of one clip split across ranks: disjoint, covering, and each rank's result is what the
+    single-rank run gives for those objects; coupled objects (non-overlap constraint) are refused."""
+    from us_video_medsam2_b200.sharding import shard_objects, track_clip_objects
+
+    ids = [3, 5, 8, 13, 21]
+    parts = [shard_objects(ids, r, 3) for r in range(3)]
+    assert sorted(sum(parts, [])) == ids and parts[0] == [3, 13] and parts[2] == [8]
+    with pytest.raises(ValueError):
+        shard_objects(ids, 3, 3)
+    video = dict(images=torch.zeros((6, 3, 8, 8)), height=8, width=8, prompts=[(0, k, None) for k in (2, 1, 4, 3)])
+    whole = track_clip_objects(_StubPredictor(), video)
+    assert whole[4] == [4.0 + t for t in range(6)]
+    merged = {}
+    for r in range(3):
+        merged.update(track_clip_objects(_StubPredictor(), video, rank=r, world_size=3))
+    assert merged == whole
+    assert track_clip_objects(_StubPredictor(), video, rank=4, world_size=5) == {}
+    coupled = _StubPredictor()
+    coupled.non_overlap_masks = True
+    with pytest.raises(ValueError):
+        track_clip_objects(coupled, video, rank=0, world_size=2)
+
+
 # ------------------------------------------------------------------------------------------------
 # look-ahead encoder pipeline (pipeline.py): plan arithmetic, slot rotation, multi-rank protocol
 # ------------------------------------------------------------------------------------------------
