@@ -501,43 +501,95 @@ gemm_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // [tile][0] MMA: accumulator free, [1] MMA: first stage full, [2] MMA: tile committed; [3] epilogue warp 0: accumulator
 // full, [4] first TMEM load done, [5] first block's math done, [6] last block handed to TMA, [7] accumulator released
 __device__ unsigned long long g_pgemm_prof[64 * 16];
+
+// ---- CTA-pair (cta_group::2) forms: the two CTAs of a cluster run ONE 256 x BN tile; each holds its 128 rows of A and
+// HALF of the W rows in its own shared memory (the tensor pipes read the peer's half), its 128 accumulator rows in its own
+// TMEM.  The leader (rank 0) issues the MMAs; TMA loads of both CTAs complete on the leader's barrier; commits are
+// multicast to both CTAs' barriers.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc5_mma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc5_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc5_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc5_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 constexpr int P_EPI_WARPS = 12;  // three per scheduler (14 warps -> 128 registers each): the epilogue is a chain of
                                  // long-latency steps, warps are what hides them
 constexpr int P_COL_GROUPS = P_EPI_WARPS / 4;  // a warp owns every P_COL_GROUPS-th 32-column block of its 32 rows
 constexpr int P_MAX_BLOCKS = (256 / 32 + P_COL_GROUPS - 1) / P_COL_GROUPS;
 constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;
 constexpr int P_STRIP_BYTES = P_EPI_WARPS * 2 * P_MAX_BLOCKS * 32 * 4;  // per warp: bias + column scale of its blocks
-// staging: per epilogue warp one buffer of one 32 x 32 block per output present (fp32 4 KB, bf16 2 KB); a warp has at most
-// three blocks per tile, so the previous block's TMA store has long finished reading the buffer when the next one is written
+// staging: per epilogue warp TWO buffers of one 32 x 32 block per output present (fp32 4 KB, bf16 2 KB): the TMA store of
+// block i still reads its buffer while block i + 1 is computed and written (single-buffered, a warp's second block waited
+// ~1.5 k cycles for the first one's store to finish reading shared memory)
 __host__ __device__ constexpr int p_stg_per_buf(bool f32, bool b16) { return (f32 ? STG_F32 : 0) + (b16 ? STG_BF16 : 0); }
-__host__ __device__ constexpr int p_stg_bytes(bool f32, bool b16) { return P_EPI_WARPS * p_stg_per_buf(f32, b16); }
+// (the host picks one buffer instead when two would cost the W slab its residency, or for fp32 outputs: 96 KB)
+__host__ __device__ constexpr int p_stg_bytes(bool f32, bool b16, int bufs) { return P_EPI_WARPS * bufs * p_stg_per_buf(f32, b16); }
 constexpr int P_A_BYTES = BM * BK * 2;
 
+// (bn = W rows held by ONE CTA: the tile width, or half of it for a CTA pair)
 __host__ __device__ constexpr int p_stage_bytes(int bn, bool ws) { return P_A_BYTES + (ws ? 0 : bn * BK * 2); }
 __host__ __device__ constexpr int p_slab_bytes(int bn, int num_kb, bool ws) { return ws ? num_kb * bn * BK * 2 : 0; }
-__host__ __device__ constexpr int p_smem_total(int bn, int num_kb, int stages, bool f32, bool b16, bool ws) {
-  return p_slab_bytes(bn, num_kb, ws) + stages * p_stage_bytes(bn, ws) + p_stg_bytes(f32, b16) + P_STRIP_BYTES +
+__host__ __device__ constexpr int p_smem_total(int bn, int num_kb, int stages, bool f32, bool b16, bool ws, int bufs) {
+  return p_slab_bytes(bn, num_kb, ws) + stages * p_stage_bytes(bn, ws) + p_stg_bytes(f32, b16, bufs) + P_STRIP_BYTES +
          1024 /* alignment slack */ + 256 /* barriers */;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                                 const usvm_gemm_epilogue ep, const int M, const int N, const int K, const int BN,
                                 const int stages_flags, const int tiles_n, const int tiles_m, const int ws_groups) {
-  const int stages = stages_flags & 0xff;
+  const int stages = stages_flags & 0xf;
+  const int stg_bufs = (stages_flags >> 4) & 3;  // staging buffers per epilogue warp: 1 or 2
   const int dbg = stages_flags >> 8;  // experiment switches (USVM2_PGEMM_DEBUG): 1 = no TMA store, 2 = no staging either
   const bool ws = ws_groups > 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_kb = (K + BK - 1) / BK;
-  const int b_bytes = BN * BK * 2;  // one k-block of the W slab / tile (a multiple of 1024: BN % 32 == 0)
-  const int stage_bytes = p_stage_bytes(BN, ws);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // CTA pair: 0 = leader (issues the MMAs)
+  const int bnl = PAIR ? BN / 2 : BN;                       // W rows this CTA holds
+  const int tile_rows = PAIR ? 2 * BM : BM;                 // output rows of one tile
+  const int cta_id = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x;      // scheduling unit: CTA or CTA pair
+  const int num_units = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
+  const int b_bytes = bnl * BK * 2;  // one k-block of this CTA's part of the W slab / tile (a multiple of 1024)
+  const int stage_bytes = p_stage_bytes(bnl, ws);
   uint8_t* slab = smem;                                   // weight-stationary: num_kb k-blocks of W, resident
-  uint8_t* ring = smem + p_slab_bytes(BN, num_kb, ws);    // A (and, streaming, W) stages
+  uint8_t* ring = smem + p_slab_bytes(bnl, num_kb, ws);   // A (and, streaming, W) stages
   uint8_t* staging = ring + stages * stage_bytes;
   const int stg_per_buf = p_stg_per_buf(ep.out_f32 != nullptr, ep.out_bf16 != nullptr);
-  float* strips = reinterpret_cast<float*>(staging + P_EPI_WARPS * stg_per_buf);
+  float* strips = reinterpret_cast<float*>(staging + P_EPI_WARPS * stg_bufs * stg_per_buf);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(strips) + P_STRIP_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;
@@ -548,17 +600,17 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // this CTA's tiles: i-th tile -> (tile_m, tile_n)
-  const int my_n = ws ? (int)blockIdx.x % tiles_n : 0;
-  const int my_group = ws ? (int)blockIdx.x / tiles_n : 0;
+  const int my_n = ws ? cta_id % tiles_n : 0;
+  const int my_group = ws ? cta_id / tiles_n : 0;
   const int num_tiles = tiles_m * tiles_n;
   const int my_count = ws ? (tiles_m - my_group + ws_groups - 1) / ws_groups
-                          : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                          : (num_tiles - cta_id + num_units - 1) / num_units;
   auto tile_at = [&](int i, int& tile_m, int& tile_n) {
     if (ws) {
       tile_m = my_group + i * ws_groups;
       tile_n = my_n;
     } else {
-      const int tile = blockIdx.x + i * gridDim.x;
+      const int tile = cta_id + i * num_units;
       tile_m = tile / tiles_n;
       tile_n = tile - tile_m * tiles_n;
     }
@@ -575,23 +627,35 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], P_EPI_WARPS);
+      mbar_init(&acc_empty[b], PAIR ? 2 * P_EPI_WARPS : P_EPI_WARPS);  // the leader's is released by both CTAs' epilogues
     }
     mbar_init(slab_full, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tc5_alloc(tmem_slot, 512);
+  if (warp == 1) {
+    if (PAIR) tc5_alloc_2sm(tmem_slot, 512);
+    else tc5_alloc(tmem_slot, 512);
+  }
   tc5_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before either signals the other's
   tc5_fence_after();
   pdl_wait();
   pdl_trigger();
   const uint32_t tmem_base = *tmem_slot;
+  // (pair) barriers of the LEADER, as shared::cluster addresses: TMA loads of both CTAs complete there, both epilogues release there
+  const uint32_t leader_slab_full = PAIR ? mapa_shared(smem_u32(slab_full), 0) : 0u;
 
   if (warp == 0) {
-    if (ws && my_count > 0 && elect_one()) {  // the W slab of this CTA, once
-      mbar_arrive_expect_tx(slab_full, (uint32_t)(num_kb * b_bytes));
-      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab + kb * b_bytes, &tmB, slab_full, kb * BK, my_n * BN);
+    if (ws && my_count > 0 && elect_one()) {  // the W slab of this CTA (pair: this CTA's half of it), once
+      if (PAIR) {
+        if (rank == 0) mbar_arrive_expect_tx(slab_full, (uint32_t)(2 * num_kb * b_bytes));
+        for (int kb = 0; kb < num_kb; ++kb)
+          tma_load_2d_2sm(slab + kb * b_bytes, &tmB, leader_slab_full, kb * BK, my_n * BN + (int)rank * bnl);
+      } else {
+        mbar_arrive_expect_tx(slab_full, (uint32_t)(num_kb * b_bytes));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab + kb * b_bytes, &tmB, slab_full, kb * BK, my_n * BN);
+      }
     }
     __syncwarp();
     uint32_t it = 0;
@@ -604,7 +668,12 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
         mbar_wait(&empty_bar[s], ph ^ 1u);
         if (elect_one()) {
           uint8_t* a_dst = ring + s * stage_bytes;
-          if (dbg & 16) {  // experiment: no operand traffic at all (the MMAs run on whatever the ring holds)
+          if (PAIR) {
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));
+            tma_load_2d_2sm(a_dst, &tmA, leader_full, kb * BK, tile_m * tile_rows + (int)rank * BM);
+            if (!ws) tma_load_2d_2sm(a_dst + P_A_BYTES, &tmB, leader_full, kb * BK, tile_n * BN + (int)rank * bnl);
+          } else if (dbg & 16) {  // experiment: no operand traffic at all (the MMAs run on whatever the ring holds)
             mbar_arrive(&full_bar[s]);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
@@ -615,9 +684,9 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // the whole warp walks the loop (uniform control flow, waits included); one elected lane issues
-    const uint32_t idesc = umma_idesc_bf16(BM, BN);
+    const uint32_t idesc = umma_idesc_bf16(tile_rows, BN);
     uint32_t it = 0;
     if (ws && my_count > 0) {
       mbar_wait(slab_full, 0);
@@ -640,26 +709,37 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
         const uint64_t a_desc = umma_desc_k_sw128(a_addr);
         const uint64_t b_desc = umma_desc_k_sw128(ws ? smem_u32(slab + kb * b_bytes) : a_addr + P_A_BYTES);
         if (elect_one()) {
+          if (PAIR) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc5_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
-          tc5_commit(&empty_bar[s]);
-          if (kb == num_kb - 1) tc5_commit(&acc_full[buf]);
+            for (int k = 0; k < BK / 16; ++k)
+              tc5_mma_f16_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                              (kb > 0 || k > 0) ? 1u : 0u);
+            tc5_commit_2sm(&empty_bar[s]);
+            if (kb == num_kb - 1) tc5_commit_2sm(&acc_full[buf]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc5_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            tc5_commit(&empty_bar[s]);
+            if (kb == num_kb - 1) tc5_commit(&acc_full[buf]);
+          }
         }
         __syncwarp();
       }
       if (prof) g_pgemm_prof[lt * 16 + 2] = clock64();
     }
+  } else if (warp == 1) {
+    // (pair) the peer's MMA warp has nothing to issue
   } else {
     const int ew = warp - 2;        // 0..P_EPI_WARPS-1
     const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
     const int quarter = ew >> 2;    // which 32-column blocks of the tile: quarter, quarter + P_COL_GROUPS, ...
-    uint8_t* stg32 = staging + ew * stg_per_buf;  // [fp32 block | bf16 block]
-    uint8_t* stg16 = stg32 + (ep.out_f32 ? STG_F32 : 0);
+    uint8_t* stg_warp = staging + ew * stg_bufs * stg_per_buf;  // one or two buffers: [fp32 block | bf16 block] each
+    const int stg16_off = ep.out_f32 ? STG_F32 : 0;
+    uint32_t nstored = 0;  // column blocks this warp has handed to TMA so far (buffer = nstored & 1)
     float* strip_bias = strips + ew * (2 * P_MAX_BLOCKS * 32);   // [blocks][32 columns]
     float* strip_scale = strip_bias + P_MAX_BLOCKS * 32;
-    bool pending = false;  // a TMA store of this warp may still be reading its staging buffer
     int strip_n = -1;      // tile_n the strips currently hold
     for (int lt = 0; lt < my_count; ++lt) {
       int tile_m, tile_n;
@@ -678,7 +758,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
         __syncwarp();
         strip_n = tile_n;
       }
-      const int row0 = tile_m * BM + lane_grp * 32;
+      const int row0 = tile_m * tile_rows + (int)rank * BM + lane_grp * 32;
       const int row = row0 + lane;
       const bool row_ok = row < M;
       const long long rrow = (ep.res_div > 0 ? ((long long)(row / ep.res_div) * ep.res_mod + row % ep.res_mod)
@@ -730,7 +810,10 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             // the tile's last TMEM read of this warp is complete: hand the accumulator back before the math / stores
             tc5_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+              else mbar_arrive(&acc_empty[buf]);
+            }
             released = true;
           }
           if (prof && blk == 0) g_pgemm_prof[lt * 16 + 4] = clock64();
@@ -784,8 +867,16 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             epilogue_block(v, ep, row, row_ok, rrow, col0, N, true);
           }
           if (prof && blk == 0) g_pgemm_prof[lt * 16 + 5] = clock64() + (v[0] == 1.2345e30f);
-          if (pending) {  // the previous store of this warp has finished reading the staging buffer
-            if (lane == 0) tma_store_wait_read();
+          // (Stores straight from registers -- 16-byte pieces at the row pitch -- were measured 15-80 % slower than
+          // staging + one TMA store per block: partial-sector writes.)  Two staging buffers per warp: the TMA store of
+          // block i still reads its buffer while block i + 1 is written.
+          uint8_t* stg32 = stg_warp + (stg_bufs == 2 ? (nstored & 1u) : 0u) * stg_per_buf;
+          uint8_t* stg16 = stg32 + stg16_off;
+          if (nstored >= (uint32_t)stg_bufs) {  // the store that last used this buffer has finished reading it
+            if (elect_one()) {
+              if (stg_bufs == 2) tma_store_wait_read1();
+              else tma_store_wait_read();
+            }
             __syncwarp();
           }
           if (prof && blk == 0) g_pgemm_prof[lt * 16 + 8] = clock64();
@@ -812,19 +903,19 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             float keep = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) keep += v[j];
-            if (keep == 1.2345e30f) stg32[0] = 1;
+            if (keep == 1.2345e30f) stg_warp[0] = 1;
           }
           if (prof && blk == 0) g_pgemm_prof[lt * 16 + 9] = clock64();
           fence_async_smem();
           __syncwarp();
           if (prof && blk == 0) g_pgemm_prof[lt * 16 + 10] = clock64();
-          if (lane == 0 && !(dbg & 1)) {
+          if (!(dbg & 1) && elect_one()) {  // (one elected lane of the converged warp: plain UTMASTG, no ELECT loop)
             if (ep.out_f32) tma_store_2d(&tmO32, stg32, col0, row0);
             if (ep.out_bf16) tma_store_2d(&tmO16, stg16, col0, row0);
             tma_store_commit();
-            pending = true;
           }
-          pending = __shfl_sync(0xffffffffu, pending, 0);
+          __syncwarp();
+          ++nstored;
           if (prof && blk == 0) g_pgemm_prof[lt * 16 + 11] = clock64();
         }
       }
@@ -832,16 +923,23 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
       if (!released) {  // (row slab beyond M, or no column block of this warp inside N)
         tc5_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+          else mbar_arrive(&acc_empty[buf]);
+        }
       }
       if (prof) g_pgemm_prof[lt * 16 + 7] = clock64();
     }
-    if (pending && lane == 0) tma_store_wait_read();
+    if (nstored && elect_one()) tma_store_wait_read();
     __syncwarp();
   }
   tc5_fence_before();
   __syncthreads();
-  if (warp == 1) tc5_dealloc(tmem_base, 512);
+  if (PAIR) cluster_sync_all();  // the peer's shared memory / TMEM stay alive until the pair is done
+  if (warp == 1) {
+    if (PAIR) tc5_dealloc_2sm(tmem_base, 512);
+    else tc5_dealloc(tmem_base, 512);
+  }
 }
 
 // ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
@@ -986,39 +1084,72 @@ int device_sm_count() {
   return sm_count;
 }
 
-// weight-stationary groups for tile width bn (0: the slab does not fit / too few row tiles per CTA)
-int ws_groups_for(int bn, int M, int N, int K, bool o32, bool o16, int sm_limit) {
+// weight-stationary groups for tile width bn (0: the slab does not fit / too few row tiles per scheduling unit).
+// pair: the scheduling unit is a CTA pair (256-row tiles, each CTA holds bn / 2 rows of W), units = sm_limit / 2.
+int ws_groups_for(int bn, int M, int N, int K, bool o32, bool o16, int sm_limit, bool pair, int* bufs_out = nullptr) {
   static const int ws_mode = [] { const char* e = getenv("USVM2_PGEMM_WS"); return e ? atoi(e) : 1; }();
-  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
-  if (!ws_mode || tiles_n > sm_limit || p_smem_total(bn, num_kb, 3, o32, o16, true) > 227 * 1024) return 0;
-  const int groups = sm_limit / tiles_n;
+  const int tiles_m = cdiv(M, pair ? 2 * BM : BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
+  const int units = pair ? sm_limit / 2 : sm_limit;
+  if (!ws_mode || tiles_n > units) return 0;
+  int bufs = o32 ? 1 : 2;
+  if (bufs == 2 && p_smem_total(pair ? bn / 2 : bn, num_kb, 3, o32, o16, true, 2) > 227 * 1024) bufs = 1;
+  if (p_smem_total(pair ? bn / 2 : bn, num_kb, 3, o32, o16, true, bufs) > 227 * 1024) return 0;
+  if (bufs_out) *bufs_out = bufs;
+  const int groups = units / tiles_n;
   return (groups >= 1 && tiles_m >= 2 * groups) ? groups : 0;
 }
 
+int pair_mode() {
+  // opt-in (USVM2_PGEMM_PAIR=1).  Measured (tools/pgemm_timeline.py): with pairs a 256 x 192 x 16 MMA retires in ~120
+  // cycles against 183 for the one-CTA 128 x 192 x 16 form -- the predicted 1.5x per-CTA MMA rate -- but at the batch
+  // sizes of this path (16 frames, 32 objects) the tile period is then set by the epilogue (TMEM drains at 64 B/clk:
+  // 1536 cycles per 128 x 192 fp32 tile, plus staging and stores) and by ramp / tail, and kernel times come out equal
+  // (35.3 vs 32.3 us stage-3 qkv, 52.5 vs 52.2 us GELU MLP, 66.0 vs 66.4 us FFN linear2).
+  static const int v = [] { const char* e = getenv("USVM2_PGEMM_PAIR"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 // bn <= 0: choose -- the widest tile among those that waste the fewest padded columns, preferring one whose W slab can
-// stay resident (weight-stationary schedule)
+// stay resident (weight-stationary schedule).  CTA pairs (cta_group::2, 256-row tiles) whenever the problem has at least
+// two 256-row tiles per pair: each CTA then reads 4 KB of A + bn * 16 B of W per MMA instead of 4 KB + bn * 32 B.
 int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
                       int bn, cudaStream_t stream) {
   const int sm_count = device_sm_count();
   if (!sm_count) return USVM_ERR_CUDA;
   const int sm_limit = (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
   const bool o32 = ep->out_f32 != nullptr, o16 = ep->out_bf16 != nullptr;
+  // enough work for every pair to see several 256-row tiles
+  const bool pair_ok = pair_mode() && sm_limit >= 2 && (long long)cdiv(M, 2 * BM) * cdiv(N, 128) >= sm_limit;
+  bool pair = false;
   if (bn <= 0) {
+    // widest tile first: 256 (pair only: the slab halves fit), then the no-waste candidates
     bn = persistent_block_n(N);
     const int min_waste = cdiv(N, bn) * bn - N;
-    if (!ws_groups_for(bn, M, N, K, o32, o16, sm_limit)) {
+    if (pair_ok) {
+      for (int b = 256; b >= 64; b -= 32)
+        if ((b % 64) == 0 && cdiv(N, b) * b - N == min_waste && ws_groups_for(b, M, N, K, o32, o16, sm_limit, true)) {
+          bn = b;
+          pair = true;
+          break;
+        }
+    }
+    if (!pair && !ws_groups_for(bn, M, N, K, o32, o16, sm_limit, false)) {
       for (int b = bn - 32; b >= 96; b -= 32)
-        if (cdiv(N, b) * b - N == min_waste && ws_groups_for(b, M, N, K, o32, o16, sm_limit)) {
+        if (cdiv(N, b) * b - N == min_waste && ws_groups_for(b, M, N, K, o32, o16, sm_limit, false)) {
           bn = b;
           break;
         }
     }
+    if (!pair && pair_ok && (bn % 64) == 0) pair = true;  // streaming schedule on pairs
+  } else {
+    pair = pair_ok && (bn % 64) == 0;
   }
   if (bn > 256 || (bn % 32)) return USVM_ERR_ARG;
+  const int bnl = pair ? bn / 2 : bn;
   CUtensorMap tmA, tmB, tmO32, tmO16;
   int rc = make_map_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_map_bf16(&tmB, W, N, K, ldw, bn);
+  rc = make_map_bf16(&tmB, W, N, K, ldw, bnl);
   if (rc) return rc;
   tmO32 = tmA;
   tmO16 = tmA;
@@ -1032,18 +1163,46 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
                   CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
-  if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-      cudaSuccess)
-    return USVM_ERR_CUDA;
-  const int tiles_m = cdiv(M, BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
+  const int tiles_m = cdiv(M, pair ? 2 * BM : BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
   const int num_tiles = tiles_m * tiles_n;
-  const int ws_groups = ws_groups_for(bn, M, N, K, o32, o16, sm_limit);
+  const int units = pair ? sm_limit / 2 : sm_limit;
+  int bufs = o32 ? 1 : 2;
+  const int ws_groups = ws_groups_for(bn, M, N, K, o32, o16, sm_limit, pair, &bufs);
   const bool ws = ws_groups > 0;
   int stages = STAGES;
-  while (stages > 1 && p_smem_total(bn, num_kb, stages, o32, o16, ws) > 227 * 1024) --stages;
-  const int grid = ws ? ws_groups * tiles_n : (num_tiles < sm_limit ? num_tiles : sm_limit);
-  usvm_launch(gemm_bf16_tc5_persistent_kernel, dim3(grid), dim3(P_THREADS), p_smem_total(bn, num_kb, stages, o32, o16, ws),
-              stream, tmA, tmB, tmO32, tmO16, *ep, M, N, K, bn, stages | (pgemm_debug() << 8), tiles_n, tiles_m, ws_groups);
+  while (stages > 1 && p_smem_total(bnl, num_kb, stages, o32, o16, ws, bufs) > 227 * 1024) --stages;
+  const int grid_units = ws ? ws_groups * tiles_n : (num_tiles < units ? num_tiles : units);
+  const size_t smem = p_smem_total(bnl, num_kb, stages, o32, o16, ws, bufs);
+  const int flags = stages | (bufs << 4) | (pgemm_debug() << 8);
+  if (!pair) {
+    if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess)
+      return USVM_ERR_CUDA;
+    usvm_launch(gemm_bf16_tc5_persistent_kernel<false>, dim3(grid_units), dim3(P_THREADS), smem, stream, tmA, tmB, tmO32,
+                tmO16, *ep, M, N, K, bn, flags, tiles_n, tiles_m, ws_groups);
+    return usvm_check_launch();
+  }
+  if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           227 * 1024) != cudaSuccess)
+    return USVM_ERR_CUDA;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * grid_units);
+  cfg.blockDim = dim3(P_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = usvm_pdl_enabled() ? 2 : 1;
+  if (cudaLaunchKernelEx(&cfg, gemm_bf16_tc5_persistent_kernel<true>, tmA, tmB, tmO32, tmO16, *ep, M, N, K, bn, flags,
+                         tiles_n, tiles_m, ws_groups) != cudaSuccess)
+    return USVM_ERR_CUDA;
   return usvm_check_launch();
 }
 
