@@ -194,6 +194,18 @@ def test_im2col_nhwc_and_dwconv():
     y = F.layer_norm(y, (256,), lw, lb, 1e-6)
     assert (out.float().view_as(y) - y).abs().max().item() < 5e-2
     assert (out.float().view_as(y) - y.to(BF).float()).abs().max().item() < 4e-2
+    # batched path (8 x 8 output tiles from 10 images on): same taps in the same order, LayerNorm statistics reduced in a
+    # different order -> equal to the row-tile kernel's per-image results up to one bf16 rounding
+    B2 = 12
+    xb = torch.randn((B2, 32, 32, 256), generator=g, device="cuda")
+    args = (dw.reshape(256, 49).t().contiguous(), db, lw, lb)
+    big = ops.dwconv7_ln(xb.view(-1, 256), *args, B2, 32, 32).view(B2, -1)
+    yb = F.layer_norm(F.conv2d(xb.permute(0, 3, 1, 2), dw, db, padding=3, groups=256).permute(0, 2, 3, 1), (256,), lw, lb, 1e-6)
+    assert (big.float().view_as(yb) - yb).abs().max().item() < 5e-2
+    for i in (0, 5, 11):
+        one = ops.dwconv7_ln(xb[i].reshape(-1, 256).contiguous(), *args, 1, 32, 32).view(-1)
+        d = (big[i].float() - one.float()).abs()
+        assert d.max().item() <= 2 ** -5 and (d > 0).float().mean().item() < 0.02
     # width not a multiple of the 8-pixel tile: the one-warp-per-pixel kernel
     x = torch.randn((1, 256, 12, 20), generator=g, device="cuda")
     out = ops.dwconv7_ln(x.permute(0, 2, 3, 1).contiguous().view(-1, 256), dw.reshape(256, 49).t().contiguous(), db, lw,

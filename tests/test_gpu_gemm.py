@@ -139,7 +139,8 @@ def test_simt_and_tc5_agree_on_bf16_operands():
     assert (x - y).abs().max().item() < 1e-3
 
 
-@pytest.mark.parametrize("M,N,K", [(1024, 384, 256), (1024, 256, 128), (4096, 128, 64), (1000, 100, 72), (130, 40, 36)])
+@pytest.mark.parametrize("M,N,K", [(1024, 384, 256), (1024, 256, 128), (4096, 128, 64), (1000, 100, 72), (130, 40, 36),
+                                   (32768, 256, 256), (32768 + 40, 128, 72)])  # the last two: persistent tf32 kernel
 @pytest.mark.parametrize("block_n", [0, 32, 128])
 def test_tc5_tf32_gemm(M, N, K, block_n):
     """fp32 operands on the tf32 tensor-core path: within tf32 rounding (10-bit mantissa products) of the fp32 result,

@@ -230,6 +230,32 @@ __global__ void im2col_nhwc_kernel(const float* __restrict__ x, bf16* __restrict
   }
 }
 
+// same, 8 channels per thread (C % 8 == 0): two 16-byte loads, one 16-byte store, index arithmetic once per 8 elements
+// (the scalar kernel took 151 us for the 32-object mask down-sampler stage: 18.9 M two-byte stores)
+__global__ void im2col_nhwc_vec8_kernel(const float* __restrict__ x, bf16* __restrict__ A, int B, int H, int W, int C, int k,
+                                        int s, int pad, int Ho, int Wo) {
+  PDL_ENTRY();
+  const int C8 = C >> 3, K8 = k * k * C8;
+  const long long total = (long long)B * Ho * Wo * K8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(i % K8);
+    const long long pix = i / K8;
+    const int c8 = kk % C8, tap = kk / C8, ky = tap / k, kx = tap - ky * k;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+    const int y = oy * s - pad + ky, xx = ox * s - pad + kx;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H && xx >= 0 && xx < W) {
+      const float4* p = reinterpret_cast<const float4*>(x + (((long long)b * H + y) * W + xx) * C + c8 * 8);
+      const float4 a = __ldg(p), c = __ldg(p + 1);
+      o.x = pack_bf16x2(a.x, a.y);
+      o.y = pack_bf16x2(a.z, a.w);
+      o.z = pack_bf16x2(c.x, c.y);
+      o.w = pack_bf16x2(c.z, c.w);
+    }
+    reinterpret_cast<uint4*>(A)[i] = o;
+  }
+}
+
 // depthwise 7x7 (pad 3) + LayerNorm over channels; one warp per pixel, C = 256 -> 8 channels per lane
 template <int CPL>
 __global__ void __launch_bounds__(256)
@@ -280,16 +306,22 @@ dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [
 // 7 x 14 input footprint of the tile is staged in shared memory with all loads in flight at once (the one-warp-per-pixel
 // kernel above re-reads every input 49 times and waits for L2 tap by tap); the thread keeps its channel's 49 weights
 // in registers, so the inner loop is 98 conflict-free LDS and 392 FMA.  LayerNorm statistics are block reductions.
+// TR = rows of the output tile: 1 for the latency path (128 CTAs at one object), 8 for the batched path -- an 8 x 8 tile
+// reads a 14 x 14 footprint (3.1 x its output) instead of 7 x 14 per 8 pixels (12 x): the 32-object launch was bound by
+// those shared-memory / L2 re-reads (110 us).  Taps are accumulated in the same order in both, results are identical.
 constexpr int DW_TILE = 8;
 constexpr int DW_FOOT = DW_TILE + 6;
+template <int TR>
 __global__ void __launch_bounds__(256)
 dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [49][256] */,
                        const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                        float eps, bf16* __restrict__ out, int B, int H, int W) {
   constexpr int C = 256;
+  constexpr int FR = TR + 6;        // footprint rows
+  constexpr int NP = TR * DW_TILE;  // output pixels per CTA
   extern __shared__ __align__(16) float dw_smem[];
-  float* xs = dw_smem;                       // [7][14][256]
-  float* red = dw_smem + 7 * DW_FOOT * C;    // [8 warps][8 pixels]
+  float* xs = dw_smem;                        // [FR][14][256]
+  float* red = dw_smem + FR * DW_FOOT * C;    // [8 warps][NP pixels]
   const int c = threadIdx.x, warp = c >> 5, lane = c & 31;
   // constants of the model first (49 taps, bias, LayerNorm parameters of this thread's channel): before the
   // programmatic-dependency wait
@@ -299,11 +331,11 @@ dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt
   const float bc = __ldg(bias + c);
   const float lw = __ldg(ln_w + c), lb = __ldg(ln_b + c);
   PDL_ENTRY();
-  const int tiles_x = W / DW_TILE;
+  const int tiles_x = W / DW_TILE, tiles_y = H / TR;
   const int tile = blockIdx.x;
-  const int ox0 = (tile % tiles_x) * DW_TILE, oy = (tile / tiles_x) % H, b = tile / (tiles_x * H);
-  // stage the footprint: 7 * 14 * 64 float4, zero outside the image
-  constexpr int NV = 7 * DW_FOOT * (C / 4);
+  const int ox0 = (tile % tiles_x) * DW_TILE, oy0 = ((tile / tiles_x) % tiles_y) * TR, b = tile / (tiles_x * tiles_y);
+  // stage the footprint: FR * 14 * 64 float4, zero outside the image
+  constexpr int NV = FR * DW_FOOT * (C / 4);
   for (int i0 = c; i0 < NV; i0 += 256 * 7) {
     float4 v[7];
 #pragma unroll
@@ -312,7 +344,7 @@ dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < NV) {
         const int r = i / (DW_FOOT * 64), rem = i - r * (DW_FOOT * 64), px = rem >> 6, c4 = rem & 63;
-        const int y = oy - 3 + r, xx = ox0 - 3 + px;
+        const int y = oy0 - 3 + r, xx = ox0 - 3 + px;
         if (y >= 0 && y < H && xx >= 0 && xx < W)
           v[u] = __ldg(reinterpret_cast<const float4*>(x + (((long long)b * H + y) * W + xx) * C) + c4);
       }
@@ -323,53 +355,106 @@ dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt
       if (i < NV) *reinterpret_cast<float4*>(xs + 4 * i) = v[u];
     }
   }
-  float acc[DW_TILE];
+  float acc[TR][DW_TILE];
 #pragma unroll
-  for (int o = 0; o < DW_TILE; ++o) acc[o] = bc;
+  for (int q = 0; q < TR; ++q)
+#pragma unroll
+    for (int o = 0; o < DW_TILE; ++o) acc[q][o] = bc;
   __syncthreads();
 #pragma unroll
-  for (int r = 0; r < 7; ++r) {
+  for (int r = 0; r < FR; ++r) {
 #pragma unroll
     for (int px = 0; px < DW_FOOT; ++px) {
       const float xv = xs[(r * DW_FOOT + px) * C + c];
 #pragma unroll
-      for (int o = 0; o < DW_TILE; ++o) {
-        const int kx = px - o;
-        if (kx >= 0 && kx < 7) acc[o] = fmaf(xv, w[r * 7 + kx], acc[o]);
+      for (int q = 0; q < TR; ++q) {
+        const int ky = r - q;
+        if (ky >= 0 && ky < 7) {
+#pragma unroll
+          for (int o = 0; o < DW_TILE; ++o) {
+            const int kx = px - o;
+            if (kx >= 0 && kx < 7) acc[q][o] = fmaf(xv, w[ky * 7 + kx], acc[q][o]);
+          }
+        }
       }
     }
   }
-  // LayerNorm over the 256 channels of each of the 8 pixels (two-pass)
-  float mean[DW_TILE];
+  if constexpr (TR > 1) {
+    // LayerNorm of the batched tile: transpose through shared memory (the footprint is dead) so that warp w owns pixels
+    // 8w .. 8w + 7 with 8 channels per lane -- 8 loads + one warp reduction per statistic per pixel instead of every
+    // thread reducing every pixel (10 shuffles + 16 shared loads per pixel and thread: that tail cost more than the conv)
+    __syncthreads();  // every thread is done reading the footprint
 #pragma unroll
-  for (int o = 0; o < DW_TILE; ++o) {
-    const float s = warp_sum(acc[o]);
-    if (lane == 0) red[warp * DW_TILE + o] = s;
+    for (int q = 0; q < TR; ++q)
+#pragma unroll
+      for (int o = 0; o < DW_TILE; ++o) xs[(q * DW_TILE + o) * C + c] = acc[q][o];
+    __syncthreads();
+    float lwv[8], lbv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      lwv[j] = __ldg(ln_w + j * 32 + lane);
+      lbv[j] = __ldg(ln_b + j * 32 + lane);
+    }
+#pragma unroll 1
+    for (int p = warp * (NP / 8); p < (warp + 1) * (NP / 8); ++p) {
+      float v[8], s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = xs[p * C + j * 32 + lane];
+        s += v[j];
+      }
+      const float mean = warp_sum(s) / C;
+      float qq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] -= mean;
+        qq = fmaf(v[j], v[j], qq);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(qq) / C + eps);
+      const long long pix = ((long long)b * H + oy0 + p / DW_TILE) * W + ox0 + p % DW_TILE;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[pix * C + j * 32 + lane] = __float2bfloat16(v[j] * rstd * lwv[j] + lbv[j]);
+    }
+    return;
   }
+  // LayerNorm over the 256 channels of each of the NP pixels (two-pass)
+#pragma unroll
+  for (int q = 0; q < TR; ++q)
+#pragma unroll
+    for (int o = 0; o < DW_TILE; ++o) {
+      const float s = warp_sum(acc[q][o]);
+      if (lane == 0) red[warp * NP + q * DW_TILE + o] = s;
+    }
   __syncthreads();
 #pragma unroll
-  for (int o = 0; o < DW_TILE; ++o) {
-    float s = 0.f;
+  for (int q = 0; q < TR; ++q)
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) s += red[wv * DW_TILE + o];
-    mean[o] = s / C;
-    acc[o] -= mean[o];
-  }
+    for (int o = 0; o < DW_TILE; ++o) {
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) s += red[wv * NP + q * DW_TILE + o];
+      acc[q][o] -= s / C;
+    }
   __syncthreads();
 #pragma unroll
-  for (int o = 0; o < DW_TILE; ++o) {
-    const float s = warp_sum(acc[o] * acc[o]);
-    if (lane == 0) red[warp * DW_TILE + o] = s;
-  }
+  for (int q = 0; q < TR; ++q)
+#pragma unroll
+    for (int o = 0; o < DW_TILE; ++o) {
+      const float s = warp_sum(acc[q][o] * acc[q][o]);
+      if (lane == 0) red[warp * NP + q * DW_TILE + o] = s;
+    }
   __syncthreads();
-  const long long pix0 = ((long long)b * H + oy) * W + ox0;
 #pragma unroll
-  for (int o = 0; o < DW_TILE; ++o) {
-    float s = 0.f;
+  for (int q = 0; q < TR; ++q) {
+    const long long pix0 = ((long long)b * H + oy0 + q) * W + ox0;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) s += red[wv * DW_TILE + o];
-    const float rstd = 1.0f / sqrtf(s / C + eps);
-    out[(pix0 + o) * C + c] = __float2bfloat16(acc[o] * rstd * lw + lb);
+    for (int o = 0; o < DW_TILE; ++o) {
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) s += red[wv * NP + q * DW_TILE + o];
+      const float rstd = 1.0f / sqrtf(s / C + eps);
+      out[(pix0 + o) * C + c] = __float2bfloat16(acc[q][o] * rstd * lw + lb);
+    }
   }
 }
 
@@ -512,6 +597,11 @@ extern "C" int usvm_im2col_nhwc(const float* x, void* A, int B, int H, int W, in
                                 void* stream) {
   if (!x || !A) return USVM_ERR_ARG;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  if ((C % 8) == 0 && !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(A) & 15)) {
+    usvm_launch(im2col_nhwc_vec8_kernel, dim3(grid_for((long long)B * Ho * Wo * k * k * (C / 8))), dim3(256), 0, STREAM, x,
+                reinterpret_cast<bf16*>(A), B, H, W, C, k, stride, pad, Ho, Wo);
+    return usvm_check_launch();
+  }
   usvm_launch(im2col_nhwc_kernel, dim3(grid_for((long long)B * Ho * Wo * k * k * C)), dim3(256), 0, STREAM, 
       x, reinterpret_cast<bf16*>(A), B, H, W, C, k, stride, pad, Ho, Wo);
   return usvm_check_launch();
@@ -522,14 +612,27 @@ extern "C" int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* 
                                void* stream) {
   if (!x || !w_49c || !bias || !ln_w || !ln_b || !out_bf16 || C != 256) return USVM_ERR_ARG;
   if (W % DW_TILE == 0 && !(reinterpret_cast<uintptr_t>(x) & 15)) {
+    // batched path: 8 x 8 output tiles once they fill the device
+    if ((H % 8) == 0 && (long long)B * (H / 8) * (W / DW_TILE) >= 148) {
+      const int smem = (14 * DW_FOOT * 256 + 8 * 8 * DW_TILE) * (int)sizeof(float);
+      static UsvmPerDeviceOnce configured8 = {};
+      if (usvm_need_setup(configured8)) {
+        if (cudaFuncSetAttribute(dwconv7_ln_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+          return USVM_ERR_CUDA;
+        usvm_setup_done(configured8);
+      }
+      usvm_launch(dwconv7_ln_tile_kernel<8>, dim3(B * (H / 8) * (W / DW_TILE)), dim3(256), smem, STREAM, x, w_49c, bias, ln_w,
+                  ln_b, eps, reinterpret_cast<bf16*>(out_bf16), B, H, W);
+      return usvm_check_launch();
+    }
     const int smem = (7 * DW_FOOT * 256 + 8 * DW_TILE) * (int)sizeof(float);
     static UsvmPerDeviceOnce configured = {};
     if (usvm_need_setup(configured)) {
-      if (cudaFuncSetAttribute(dwconv7_ln_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      if (cudaFuncSetAttribute(dwconv7_ln_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return USVM_ERR_CUDA;
       usvm_setup_done(configured);
     }
-    usvm_launch(dwconv7_ln_tile_kernel, dim3(B * H * (W / DW_TILE)), dim3(256), smem, STREAM, x, w_49c, bias, ln_w, ln_b,
+    usvm_launch(dwconv7_ln_tile_kernel<1>, dim3(B * H * (W / DW_TILE)), dim3(256), smem, STREAM, x, w_49c, bias, ln_w, ln_b,
                 eps, reinterpret_cast<bf16*>(out_bf16), B, H, W);
     return usvm_check_launch();
   }

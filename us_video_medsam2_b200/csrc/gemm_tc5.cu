@@ -565,7 +565,8 @@ __host__ __device__ constexpr int p_smem_total(int bn, int num_kb, int stages, b
          1024 /* alignment slack */ + 256 /* barriers */;
 }
 
-template <bool PAIR>
+// TF32: fp32 operands read as tf32 (a k-block is then 32 floats, each tcgen05.mma covers K = 8) -- the batched mask decoder
+template <bool PAIR, bool TF32 = false>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
@@ -577,7 +578,8 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
   const bool ws = ws_groups > 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int num_kb = (K + BK - 1) / BK;
+  constexpr int BKE = TF32 ? BK / 2 : BK;  // elements per k-block (128 bytes)
+  const int num_kb = (K + BKE - 1) / BKE;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // CTA pair: 0 = leader (issues the MMAs)
   const int bnl = PAIR ? BN / 2 : BN;                       // W rows this CTA holds
   const int tile_rows = PAIR ? 2 * BM : BM;                 // output rows of one tile
@@ -651,10 +653,10 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
       if (PAIR) {
         if (rank == 0) mbar_arrive_expect_tx(slab_full, (uint32_t)(2 * num_kb * b_bytes));
         for (int kb = 0; kb < num_kb; ++kb)
-          tma_load_2d_2sm(slab + kb * b_bytes, &tmB, leader_slab_full, kb * BK, my_n * BN + (int)rank * bnl);
+          tma_load_2d_2sm(slab + kb * b_bytes, &tmB, leader_slab_full, kb * BKE, my_n * BN + (int)rank * bnl);
       } else {
         mbar_arrive_expect_tx(slab_full, (uint32_t)(num_kb * b_bytes));
-        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab + kb * b_bytes, &tmB, slab_full, kb * BK, my_n * BN);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(slab + kb * b_bytes, &tmB, slab_full, kb * BKE, my_n * BN);
       }
     }
     __syncwarp();
@@ -671,14 +673,14 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
           if (PAIR) {
             const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));
-            tma_load_2d_2sm(a_dst, &tmA, leader_full, kb * BK, tile_m * tile_rows + (int)rank * BM);
-            if (!ws) tma_load_2d_2sm(a_dst + P_A_BYTES, &tmB, leader_full, kb * BK, tile_n * BN + (int)rank * bnl);
+            tma_load_2d_2sm(a_dst, &tmA, leader_full, kb * BKE, tile_m * tile_rows + (int)rank * BM);
+            if (!ws) tma_load_2d_2sm(a_dst + P_A_BYTES, &tmB, leader_full, kb * BKE, tile_n * BN + (int)rank * bnl);
           } else if (dbg & 16) {  // experiment: no operand traffic at all (the MMAs run on whatever the ring holds)
             mbar_arrive(&full_bar[s]);
           } else {
             mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BK, tile_m * BM);
-            if (!ws) tma_load_2d(a_dst + P_A_BYTES, &tmB, &full_bar[s], kb * BK, tile_n * BN);
+            tma_load_2d(a_dst, &tmA, &full_bar[s], kb * BKE, tile_m * BM);
+            if (!ws) tma_load_2d(a_dst + P_A_BYTES, &tmB, &full_bar[s], kb * BKE, tile_n * BN);
           }
         }
         __syncwarp();
@@ -686,7 +688,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
     }
   } else if (warp == 1 && rank == 0) {
     // the whole warp walks the loop (uniform control flow, waits included); one elected lane issues
-    const uint32_t idesc = umma_idesc_bf16(tile_rows, BN);
+    const uint32_t idesc = TF32 ? umma_idesc_tf32(tile_rows, BN) : umma_idesc_bf16(tile_rows, BN);
     uint32_t it = 0;
     if (ws && my_count > 0) {
       mbar_wait(slab_full, 0);
@@ -718,9 +720,14 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
             if (kb == num_kb - 1) tc5_commit_2sm(&acc_full[buf]);
           } else {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              tc5_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (TF32)
+                tc5_mma_tf32(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                tc5_mma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                            (kb > 0 || k > 0) ? 1u : 0u);
+            }
             tc5_commit(&empty_bar[s]);
             if (kb == num_kb - 1) tc5_commit(&acc_full[buf]);
           }
@@ -1086,9 +1093,10 @@ int device_sm_count() {
 
 // weight-stationary groups for tile width bn (0: the slab does not fit / too few row tiles per scheduling unit).
 // pair: the scheduling unit is a CTA pair (256-row tiles, each CTA holds bn / 2 rows of W), units = sm_limit / 2.
-int ws_groups_for(int bn, int M, int N, int K, bool o32, bool o16, int sm_limit, bool pair, int* bufs_out = nullptr) {
+int ws_groups_for(int bn, int M, int N, int K, bool o32, bool o16, int sm_limit, bool pair, int* bufs_out = nullptr,
+                  bool tf32 = false) {
   static const int ws_mode = [] { const char* e = getenv("USVM2_PGEMM_WS"); return e ? atoi(e) : 1; }();
-  const int tiles_m = cdiv(M, pair ? 2 * BM : BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
+  const int tiles_m = cdiv(M, pair ? 2 * BM : BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, tf32 ? BK / 2 : BK);
   const int units = pair ? sm_limit / 2 : sm_limit;
   if (!ws_mode || tiles_n > units) return 0;
   int bufs = o32 ? 1 : 2;
@@ -1113,13 +1121,13 @@ int pair_mode() {
 // stay resident (weight-stationary schedule).  CTA pairs (cta_group::2, 256-row tiles) whenever the problem has at least
 // two 256-row tiles per pair: each CTA then reads 4 KB of A + bn * 16 B of W per MMA instead of 4 KB + bn * 32 B.
 int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm_gemm_epilogue* ep, int M, int N, int K,
-                      int bn, cudaStream_t stream) {
+                      int bn, cudaStream_t stream, bool tf32 = false) {
   const int sm_count = device_sm_count();
   if (!sm_count) return USVM_ERR_CUDA;
   const int sm_limit = (g_sm_budget > 0 && g_sm_budget < sm_count) ? g_sm_budget : sm_count;
   const bool o32 = ep->out_f32 != nullptr, o16 = ep->out_bf16 != nullptr;
   // enough work for every pair to see several 256-row tiles
-  const bool pair_ok = pair_mode() && sm_limit >= 2 && (long long)cdiv(M, 2 * BM) * cdiv(N, 128) >= sm_limit;
+  const bool pair_ok = !tf32 && pair_mode() && sm_limit >= 2 && (long long)cdiv(M, 2 * BM) * cdiv(N, 128) >= sm_limit;
   bool pair = false;
   if (bn <= 0) {
     // widest tile first: 256 (pair only: the slab halves fit), then the no-waste candidates
@@ -1133,9 +1141,9 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
           break;
         }
     }
-    if (!pair && !ws_groups_for(bn, M, N, K, o32, o16, sm_limit, false)) {
+    if (!pair && !ws_groups_for(bn, M, N, K, o32, o16, sm_limit, false, nullptr, tf32)) {
       for (int b = bn - 32; b >= 96; b -= 32)
-        if (cdiv(N, b) * b - N == min_waste && ws_groups_for(b, M, N, K, o32, o16, sm_limit, false)) {
+        if (cdiv(N, b) * b - N == min_waste && ws_groups_for(b, M, N, K, o32, o16, sm_limit, false, nullptr, tf32)) {
           bn = b;
           break;
         }
@@ -1147,9 +1155,11 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
   if (bn > 256 || (bn % 32)) return USVM_ERR_ARG;
   const int bnl = pair ? bn / 2 : bn;
   CUtensorMap tmA, tmB, tmO32, tmO16;
-  int rc = make_map_bf16(&tmA, A, M, K, lda, BM);
+  int rc = tf32 ? make_map(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, BK / 2, BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                : make_map_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_map_bf16(&tmB, W, N, K, ldw, bnl);
+  rc = tf32 ? make_map(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, W, N, K, ldw, BK / 2, bnl, CU_TENSOR_MAP_SWIZZLE_128B)
+            : make_map_bf16(&tmB, W, N, K, ldw, bnl);
   if (rc) return rc;
   tmO32 = tmA;
   tmO16 = tmA;
@@ -1163,17 +1173,25 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
                   CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
-  const int tiles_m = cdiv(M, pair ? 2 * BM : BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, BK);
+  const int tiles_m = cdiv(M, pair ? 2 * BM : BM), tiles_n = cdiv(N, bn), num_kb = cdiv(K, tf32 ? BK / 2 : BK);
   const int num_tiles = tiles_m * tiles_n;
   const int units = pair ? sm_limit / 2 : sm_limit;
   int bufs = o32 ? 1 : 2;
-  const int ws_groups = ws_groups_for(bn, M, N, K, o32, o16, sm_limit, pair, &bufs);
+  const int ws_groups = ws_groups_for(bn, M, N, K, o32, o16, sm_limit, pair, &bufs, tf32);
   const bool ws = ws_groups > 0;
   int stages = STAGES;
   while (stages > 1 && p_smem_total(bnl, num_kb, stages, o32, o16, ws, bufs) > 227 * 1024) --stages;
   const int grid_units = ws ? ws_groups * tiles_n : (num_tiles < units ? num_tiles : units);
   const size_t smem = p_smem_total(bnl, num_kb, stages, o32, o16, ws, bufs);
   const int flags = stages | (bufs << 4) | (pgemm_debug() << 8);
+  if (tf32) {
+    if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024) != cudaSuccess)
+      return USVM_ERR_CUDA;
+    usvm_launch(gemm_bf16_tc5_persistent_kernel<false, true>, dim3(grid_units), dim3(P_THREADS), smem, stream, tmA, tmB,
+                tmO32, tmO16, *ep, M, N, K, bn, flags, tiles_n, tiles_m, ws_groups);
+    return usvm_check_launch();
+  }
   if (!pair) {
     if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024) != cudaSuccess)
@@ -1288,6 +1306,9 @@ extern "C" int usvm_gemm_tf32_tc5(const float* A, int lda, const float* W, int l
   if (ep->rope_cos) return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = block_n;
+  // throughput-bound (the batched decoder): two waves of 128 x 128 tiles or more -> persistent kernel
+  if (bn == 0 && (long long)cdiv(M, BM) * cdiv(N, 128) >= 2 * 148 && (N % 32) == 0)
+    return launch_persistent(A, lda, W, ldw, ep, M, N, K, 0, s, true);
   if (bn <= 0) {
     const int mt = cdiv(M, BM);
     bn = 128;
