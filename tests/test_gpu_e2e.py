@@ -432,3 +432,43 @@ def test_image_predictor_batch_equals_single_images():
         assert np.array_equal(masks[i], single[i][0]) and np.array_equal(ious[i], single[i][1])
         assert np.array_equal(lows[i], single[i][2])
     assert pred.get_image_embedding().shape == (3, 256, 32, 32)
+
+
+def test_mp4_ingest_on_device(tmp_path):
+    """ init_state("clip.mp4"): frames decoded by OpenCV's FFmpeg backend, uploaded as uint8 and normalised on
+    the device like the JPEG route; synchronous and asynchronous loading agree and a session started from the file tracks."""
+    cv2 = pytest.importorskip("cv2")
+    from us_video_medsam2_b200.frames import VideoFrames, _Mp4Source, load_video_frames
+
+    path = str(tmp_path / "clip.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 10, (128, 96))
+    if not wr.isOpened():
+        pytest.skip("this OpenCV build cannot write mp4v")
+    rng = np.random.default_rng(9)
+    T = 7
+    base = cv2.resize((rng.random((12, 16, 3)) * 255).astype(np.uint8), (128, 96), interpolation=cv2.INTER_CUBIC)
+    for i in range(T):
+        wr.write(np.roll(base, 3 * i, axis=1))
+    wr.release()
+    dev = torch.device("cuda")
+    sync, h, w = load_video_frames(path, 512, False, compute_device=dev)
+    assert torch.is_tensor(sync) and sync.shape == (T, 3, 512, 512) and (h, w) == (96, 128)
+    src, host = _Mp4Source(path, 512), np.empty((512, 512, 3), np.uint8)
+    src.decode_into(0, host)
+    mean = torch.tensor(synth.IMG_MEAN)[:, None, None]
+    std = torch.tensor(synth.IMG_STD)[:, None, None]
+    want0 = (torch.from_numpy(host / 255.0).permute(2, 0, 1).float() - mean) / std
+    assert float((sync[0].cpu() - want0).abs().max()) <= 2.4e-7 * 3
+    lazy, _, _ = load_video_frames(path, 512, False, async_loading_frames=True, compute_device=dev)
+    assert isinstance(lazy, VideoFrames) and len(lazy) == T and torch.equal(lazy[T - 1], sync[T - 1])
+    from sam2.build_sam import build_sam2_video_predictor
+
+    pred = build_sam2_video_predictor("configs/sam2.1_hiera_t512.yaml", encoder_batch=4)
+    pred.load_state_dict(synth.make_state_dict(19), strict=True)
+    st = pred.init_state(path)
+    assert (st["video_height"], st["video_width"], st["num_frames"]) == (96, 128, T)
+    m = torch.zeros((96, 128), dtype=torch.bool)
+    m[30:70, 40:100] = True
+    pred.add_new_mask(st, 0, 1, m)
+    outs = [lg for _, _, lg in pred.propagate_in_video(st)]
+    assert len(outs) == T and outs[3].shape == (1, 1, 96, 128)

@@ -156,6 +156,37 @@ def test_object_sharding_of_one_clip():
         track_clip_objects(coupled, video, rank=0, world_size=2)
 
 
+def test_mp4_source_decodes_in_order(tmp_path):
+    """Host half of the MP4 ingest (misc.py:280-309; OpenCV's FFmpeg backend stands in for decord): frame count, original
+    size, RGB order, resize to S x S, sequential contract."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+
+    from us_video_medsam2_b200.frames import _Mp4Source
+
+    path = str(tmp_path / "clip.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 10, (64, 48))
+    if not wr.isOpened():
+        pytest.skip("this OpenCV build cannot write mp4v")
+    for i in range(5):
+        frame = np.zeros((48, 64, 3), np.uint8)
+        frame[..., 2] = 40 * i + 20   # OpenCV writes BGR: this is the RED channel
+        frame[:, 32:, 0] = 200        # blue on the right half
+        wr.write(frame)
+    wr.release()
+    src = _Mp4Source(path, 32)
+    assert len(src) == 5
+    dst = np.empty((32, 32, 3), np.uint8)
+    with pytest.raises(RuntimeError):
+        src.decode_into(2, dst)  # out of order
+    for t in range(5):
+        assert src.decode_into(t, dst) == (48, 64)
+        assert abs(float(dst[:, :12, 0].mean()) - (40 * t + 20)) < 6   # red, left half (lossy codec)
+        assert float(dst[:, 20:, 2].mean()) > 150 and float(dst[:, :12, 2].mean()) < 40  # blue on the right only
+    with pytest.raises(RuntimeError):
+        _Mp4Source(str(tmp_path / "missing.mp4"), 32)
+
+
 # ------------------------------------------------------------------------------------------------
 # look-ahead encoder pipeline (pipeline.py): plan arithmetic, slot rotation, multi-rank protocol
 # ------------------------------------------------------------------------------------------------
@@ -302,8 +333,8 @@ def test_jpeg_folder_ingest_matches_reference(tmp_path):
     assert rgb.shape == (4, 64, 64, 3) and rgb.dtype == torch.uint8 and (h, w) == (37, 53)
     mean, std = torch.tensor(IMG_MEAN)[:, None, None], torch.tensor(IMG_STD)[:, None, None]
     images = (torch.from_numpy(rgb.numpy() / 255.0).permute(0, 3, 1, 2).float() - mean) / std
-    with pytest.raises(NotImplementedError):
-        list_jpeg_frames(str(tmp_path / "clip.mp4"))
+    with pytest.raises(NotImplementedError):  # neither a folder nor a video file
+        list_jpeg_frames(str(tmp_path / "clip.avi"))
     with pytest.raises(RuntimeError):
         (tmp_path / "empty").mkdir()
         list_jpeg_frames(str(tmp_path / "empty"))

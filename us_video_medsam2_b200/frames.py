@@ -11,8 +11,9 @@ Split of the work:
 session starts; `images[t]` blocks only until frame t is decoded.  Device work stays on the caller's thread and stream:
 when a frame is asked for, every frame decoded so far is uploaded and normalised in one copy + one launch.
 `offload_video_to_cpu=True` keeps only the uint8 frames (in pinned host memory) and normalises a frame on the device
-each time it is read.  MP4 input needs `decord`, which this image does not have, and raises like the reference does
-for unsupported inputs."""
+each time it is read.  MP4 files (misc.py:280-309, `decord` in the reference) are decoded frame by frame with OpenCV's
+FFmpeg backend (bilinear resize to SxS on the host) and then take the same uint8 -> device -> normalise route; the
+reference resamples inside the decoder, so pixel values can differ by the resampling filter."""
 import os
 import threading
 
@@ -37,6 +38,46 @@ def _decode_into(path, image_size, dst):
     return h, w
 
 
+class _Mp4Source:
+    """Sequential decoder of a video file (load_video_frames_from_video_file, misc.py:280-309): frame t -> uint8 [S,S,3]
+    RGB.  OpenCV (FFmpeg backend) stands in for decord; frames must be asked for in order."""
+
+    def __init__(self, path, image_size):
+        try:
+            import cv2
+        except ImportError as e:  # pragma: no cover
+            raise NotImplementedError("MP4 input needs OpenCV (cv2) with FFmpeg; extract JPEG frames into a folder instead "
+                                      "(ffmpeg -i <video>.mp4 -q:v 2 -start_number 0 <dir>/'%05d.jpg')") from e
+        self.cv2, self.path, self.S = cv2, path, int(image_size)
+        cap = cv2.VideoCapture(path)
+        if not cap.isOpened():
+            raise RuntimeError(f"cannot open video file {path}")
+        n = 0
+        while cap.grab():  # the container's frame count is a hint, not a promise: count what decodes
+            n += 1
+        cap.release()
+        if n == 0:
+            raise RuntimeError(f"no frames found in {path}")
+        self.n, self.next, self.cap = n, 0, cv2.VideoCapture(path)
+
+    def __len__(self):
+        return self.n
+
+    def decode_into(self, t, dst):
+        if t != self.next:
+            raise RuntimeError("video frames are decoded in order")
+        ok, frame = self.cap.read()
+        if not ok:
+            raise RuntimeError(f"decoding frame {t} of {self.path} failed")
+        self.next += 1
+        h, w = frame.shape[:2]
+        rgb = self.cv2.cvtColor(frame, self.cv2.COLOR_BGR2RGB)
+        dst[...] = self.cv2.resize(rgb, (self.S, self.S), interpolation=self.cv2.INTER_LINEAR)
+        if self.next == self.n:
+            self.cap.release()
+        return h, w
+
+
 class VideoFrames:
     """List-like `inference_state["images"]`: `len()`, `images[t]` -> normalised fp32 [3,S,S] on the compute device."""
 
@@ -45,12 +86,16 @@ class VideoFrames:
         from . import ops
 
         self._ops = ops
-        self.paths, self.S, self.device = list(paths), int(image_size), torch.device(compute_device)
+        # `paths`: JPEG file names, or a source object with __len__ / decode_into(t, dst) (video files)
+        self.source = paths if hasattr(paths, "decode_into") else None
+        self.paths = [] if self.source is not None else list(paths)
+        self.T = len(self.source) if self.source is not None else len(self.paths)
+        self.S, self.device = int(image_size), torch.device(compute_device)
         if self.device.type != "cuda":
             raise RuntimeError("frame ingest normalises on the GPU (usvm_normalize_rgb_u8): compute_device must be a "
                                "CUDA device; there is no CPU path")
         self.mean, self.std = tuple(float(x) for x in img_mean), tuple(float(x) for x in img_std)
-        T = len(self.paths)
+        T = self.T
         self.host = torch.empty((T, self.S, self.S, 3), dtype=torch.uint8).pin_memory()
         self._np = self.host.numpy()
         self.keep = bool(keep_on_device)
@@ -70,7 +115,10 @@ class VideoFrames:
                 self._decode(t)
 
     def _decode(self, t):
-        h, w = _decode_into(self.paths[t], self.S, self._np[t])
+        if self.source is not None:
+            h, w = self.source.decode_into(t, self._np[t])
+        else:
+            h, w = _decode_into(self.paths[t], self.S, self._np[t])
         with self._cv:
             self.video_height, self.video_width = h, w
             self.decoded = t + 1
@@ -78,7 +126,7 @@ class VideoFrames:
 
     def _run(self):
         try:
-            for t in range(1, len(self.paths)):
+            for t in range(1, self.T):
                 self._decode(t)
         except Exception as e:  # surfaced by the next __getitem__ (misc.py:140-150)
             with self._cv:
@@ -86,7 +134,7 @@ class VideoFrames:
                 self._cv.notify_all()
 
     def __len__(self):
-        return len(self.paths)
+        return self.T
 
     def _wait_decoded(self, t):
         with self._cv:
@@ -127,9 +175,6 @@ class VideoFrames:
 def list_jpeg_frames(video_path):
     """Sorted frame paths of a JPEG folder, with the reference's input checks (misc.py:186-243)."""
     is_str = isinstance(video_path, str)
-    if isinstance(video_path, bytes) or (is_str and os.path.splitext(video_path)[-1] in (".mp4", ".MP4")):
-        raise NotImplementedError("MP4 input needs the `decord` package; extract JPEG frames into a folder instead "
-                                  "(ffmpeg -i <video>.mp4 -q:v 2 -start_number 0 <dir>/'%05d.jpg')")
     if not (is_str and os.path.isdir(video_path)):
         raise NotImplementedError("Only MP4 video and JPEG folder are supported at this moment")
     names = sorted(p for p in os.listdir(video_path) if os.path.splitext(p)[-1] in _EXTS)
@@ -152,7 +197,10 @@ def load_video_frames(video_path, image_size, offload_video_to_cpu, img_mean=IMG
     """Same signature as the reference (sam2/utils/misc.py:172-211).  -> (images, video_height, video_width); `images` is a
     device tensor [T,3,S,S] (synchronous, resident) or a `VideoFrames` loader (asynchronous and / or offloaded), both
     indexable by frame."""
-    paths = list_jpeg_frames(video_path)
+    if isinstance(video_path, str) and os.path.splitext(video_path)[-1] in (".mp4", ".MP4"):
+        paths = _Mp4Source(video_path, image_size)  # (the reference's `bytes` input is decord-specific: not mirrored)
+    else:
+        paths = list_jpeg_frames(video_path)
     frames = VideoFrames(paths, image_size, compute_device, keep_on_device=not offload_video_to_cpu,
                          background=bool(async_loading_frames), img_mean=img_mean, img_std=img_std)
     if not async_loading_frames and not offload_video_to_cpu:
