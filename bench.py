@@ -374,6 +374,37 @@ def time_other_kernels(dev, B):
     return out
 
 
+def time_dominant_kernel_batched(dev, peaks, B=32, iters=10):
+    """The roofline kernel at its THROUGHPUT shape -- the batched frame of BASELINE configs[2] on one GPU (8 videos x 4
+    objects): 32 objects x 1024 queries x 7232 keys, no split-KV, no combine.  CUDA events around single launches, L2
+    flushed before each (K / V of 32 objects are 237 MB: larger than L2 anyway)."""
+    from us_video_medsam2_b200 import ops
+
+    T, Nk, D = 1024, 7 * 1024 + 64, 256
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = torch.randn((B * T, D), generator=g, device=dev).to(torch.bfloat16)
+    kv = torch.randn((B * Nk, 4 * D), generator=g, device=dev).to(torch.bfloat16)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    fn = lambda: ops.fmha(q, kv, kv, B, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D),
+                          (2 * D, Nk * 4 * D, 4 * D, D), num_splits=1)
+    for _ in range(2):
+        fn()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        tot += s.elapsed_time(e)
+    us = tot / iters * 1e3
+    ach = 4.0 * B * T * Nk * D / us / 1e6
+    return {"kernel": "fmha_tc5_ts_kernel (memory-attention cross-attention at 32 objects, no split)", "objects": B,
+            "avg_us": us, "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": ach / peaks["bf16_sustained"], "launches_timed": iters}
+
+
 GF_ENCODER, GF_PER_OBJECT = 62.9, 52.0  # SURVEY 8(d): GFLOP per frame (shared by objects) / per object-frame
 # HBM-bound pieces, algorithmic bytes per object-frame (SURVEY 8(d)): memory encoder = 1.0 MB mask in (fp32 512^2) + 0.5 MB
 # pix_feat (bf16) + 2.8 MB weights + 0.13 MB memory out; hole filling = 64 KiB logits in + 64 KiB out
@@ -682,6 +713,8 @@ def run_b200(args, rank, world):
         roofline["traffic"] = traffic if B == 1 else None
         roofline["traffic_source"] = src
         roofline["other_kernels"] = time_other_kernels(dev, B)
+        if args.batched_videos > 0:  # the same kernel where a roofline fraction is meaningful: the batched shape
+            roofline["throughput_shape"] = time_dominant_kernel_batched(dev, peaks)
         # whole path by SURVEY 8(d)'s formula: (62.9 + 52.0 * B) GFLOP per frame x the measured frames/s of one GPU
         wp = (GF_ENCODER + GF_PER_OBJECT * B) * (value / world) / 1e3
         roofline["whole_path"] = {"achieved": wp, "unit": "TFLOP/s", "frac": wp / peaks["bf16_sustained"],
