@@ -595,15 +595,24 @@ def run_b200(args, rank, world):
         out_host = torch.empty((T, B, 512, 512), dtype=torch.bool).pin_memory()  # binary masks, 1 byte per pixel
         clip_dev = ops.normalize_gray_u8(gray_host.to(dev), synth.IMG_MEAN, synth.IMG_STD)  # resident copy for `value`
 
+        copy_stream = torch.cuda.Stream()  # device -> host result copies run beside the next frame, as a driver would do
+
         def one_pass(images, sink=None):
             st = pred.init_state(images, 512, 512)
             for i, m in enumerate(masks):
                 pred.add_new_mask(st, 0, i + 1, m)
             n = 0
+            main = torch.cuda.current_stream()
             for t, ids, logits in pred.propagate_in_video(st):
                 if sink is not None:
-                    sink[t].copy_(logits[:, 0] > 0, non_blocking=True)
+                    m = logits[:, 0] > 0            # this frame's binary masks (a fresh tensor, not the graph's static output)
+                    copy_stream.wait_stream(main)
+                    with torch.cuda.stream(copy_stream):
+                        sink[t].copy_(m, non_blocking=True)
+                    m.record_stream(copy_stream)
                 n += 1
+            if sink is not None:
+                main.wait_stream(copy_stream)       # the step ends when its last mask is in host memory
             return n
 
         def step_resident():
