@@ -153,15 +153,17 @@ int usvm_fmha_tc5(const usvm_fmha_params* p_host, void* stream);
  * F.scaled_dot_product_attention + window_unpartition of MultiScaleAttention / the ViT blocks, hieradet.py:56-81,
  * backbones/utils.py:17-61, efficient_track_anything/modeling/backbones/vitdet.py): qkv bf16 [F, H, W, 3*dim] with
  * (q | k | v) x (head, channel) columns, out bf16 [F, H, W, dim]; head_dim = dim / heads in {64, 96}.
- * window == 0: global attention, H*W % 128 == 0.  window == 14: non-overlapping 14 x 14 windows over the grid padded to a
- * multiple of 14; the padding tokens' k / v are the projection bias (qkv_bias fp32 [3*dim]), as in the reference where the
- * zero padding follows the LayerNorm. */
+ * window == 0: global attention, H*W % 128 == 0.  window == 14 or 7: non-overlapping windows over the grid padded to a
+ * multiple of the window; the padding tokens' q / k / v are the projection bias (qkv_bias fp32 [3*dim]), as in the reference
+ * where the zero padding follows the LayerNorm.  pool != 0 (window 14, even H and W): the queries are the 2 x 2 max-pool
+ * of each window's q (do_pool, hieradet.py:25-36, 60-67) and out is bf16 [F, H/2, W/2, dim]. */
 typedef struct usvm_hiera_attn_params {
   const void* qkv;
   void* out;
   const float* qkv_bias;
   int F, H, W, dim, heads, window;
   float scale; /* 1/sqrt(head_dim) */
+  int pool;
 } usvm_hiera_attn_params;
 int usvm_hiera_attn_tc5(const usvm_hiera_attn_params* p_host, void* stream);
 int usvm_fmha_combine(const usvm_fmha_params* p_host, void* stream);

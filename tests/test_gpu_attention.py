@@ -91,7 +91,7 @@ def test_attn_small_f32(B, Nq, Nk, dh):
     assert (got - want).abs().max().item() < 2e-5
 
 
-def _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws):
+def _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws, pool=False):
     """MultiScaleAttention on a windowed block as the reference runs it (hieradet.py:56-81, backbones/utils.py:17-61):
     the grid is zero padded to a multiple of the window AFTER norm1, so the padding tokens' q / k / v are the projection
     bias; windows attend among all of their ws*ws tokens; padding rows are dropped by window_unpartition."""
@@ -106,12 +106,20 @@ def _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws):
         win = pad.view(Fr, Hp // ws, ws, Wp // ws, ws, 3 * dim).permute(0, 1, 3, 2, 4, 5)
         win = win.reshape(-1, ws * ws, 3, heads, hd)
     q, k, v = (win[:, :, i].transpose(1, 2) for i in range(3))
+    wq = ws
+    if pool:  # do_pool on the window-partitioned q (hieradet.py:60-67): 2 x 2 max-pool inside every (padded) window
+        nw = q.shape[0]
+        q = q.transpose(1, 2).reshape(nw, ws, ws, heads * hd).permute(0, 3, 1, 2)
+        q = torch.nn.functional.max_pool2d(q.to(torch.bfloat16).float(), 2, 2).permute(0, 2, 3, 1)
+        wq = ws // 2
+        q = q.reshape(nw, wq * wq, heads, hd).transpose(1, 2)
     o = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1) @ v
     o = o.transpose(1, 2).reshape(o.shape[0], -1, dim)
     if ws == 0:
         return o.reshape(Fr * H * W, dim)
-    o = o.view(Fr, Hp // ws, Wp // ws, ws, ws, dim).permute(0, 1, 3, 2, 4, 5).reshape(Fr, Hp, Wp, dim)
-    return o[:, :H, :W].reshape(Fr * H * W, dim)
+    o = o.view(Fr, Hp // ws, Wp // ws, wq, wq, dim).permute(0, 1, 3, 2, 4, 5).reshape(Fr, Hp // ws * wq, Wp // ws * wq, dim)
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    return o[:, :Ho, :Wo].reshape(Fr * Ho * Wo, dim)
 
 
 @pytest.mark.parametrize("Fr,H,W,dim,heads,ws,scale_up", [
@@ -124,6 +132,10 @@ def _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws):
     (1, 64, 64, 384, 4, 0, 1.0),    # 4096-token global block (1024^2 input)
     (1, 28, 42, 384, 4, 14, 1.0),   # grid that is a multiple of the window: no padding tokens at all
     (1, 30, 17, 384, 6, 14, 2.0),   # ragged grid, heads of 64
+    (2, 16, 16, 768, 8, 7, 1.0),    # Hiera stage-4 block: 3 x 3 windows of 7 x 7 over the 16 x 16 grid
+    (1, 20, 9, 192, 2, 7, 3.0),
+    (2, 32, 32, 768, 8, -14, 1.0),  # q-pool block into stage 4: 49 pooled queries x 196 keys per window (negative = pooled)
+    (1, 28, 42, 192, 3, -14, 4.0),
 ])
 def test_hiera_attn_tc5(Fr, H, W, dim, heads, ws, scale_up):
     """usvm_hiera_attn_tc5 vs the reference's pad / partition / SDPA / un-partition sequence in fp32 on the same bf16 qkv,
@@ -137,12 +149,13 @@ def test_hiera_attn_tc5(Fr, H, W, dim, heads, ws, scale_up):
     bias = torch.randn((3 * dim,), generator=g, device="cuda") * math.sqrt(scale_up)
     if ws == 0 and (H * W) % 128:
         pytest.skip("global mode needs a multiple of 128 tokens")
-    out = ops.hiera_attn(qkv, bias, Fr, H, W, dim, heads, window=ws)
+    pool, ws = ws < 0, abs(ws)
+    out = ops.hiera_attn(qkv, bias, Fr, H, W, dim, heads, window=ws, pool=pool)
     torch.cuda.synchronize()
-    want = _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws)
+    want = _ref_window_attention(qkv, bias, Fr, H, W, dim, heads, ws, pool)
     err = (out.float() - want).abs().max().item()
     assert err < (2e-2 if scale_up == 1.0 else 4e-2), err
-    if dim // heads == 96 and ws == 14 and H == W == 32:
+    if dim // heads == 96 and ws == 14 and H == W == 32 and not pool:
         Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, bias, Fr, H, W, ws, False, dim)
         Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * dim, dim, 96), (0, nk * dim, dim, 96),
                       (0, nk * dim, dim, 96))

@@ -39,7 +39,8 @@ class FmhaParams(C.Structure):
 
 class HieraAttnParams(C.Structure):
     _fields_ = [("qkv", C.c_void_p), ("out", C.c_void_p), ("qkv_bias", C.c_void_p), ("F", C.c_int), ("H", C.c_int),
-                ("W", C.c_int), ("dim", C.c_int), ("heads", C.c_int), ("window", C.c_int), ("scale", C.c_float)]
+                ("W", C.c_int), ("dim", C.c_int), ("heads", C.c_int), ("window", C.c_int), ("scale", C.c_float),
+                ("pool", C.c_int)]
 
 
 MAX_PTRS = 48

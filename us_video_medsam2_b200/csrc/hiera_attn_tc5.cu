@@ -6,7 +6,8 @@
 // One CTA owns up to 128 queries of one (frame, head) and walks that head's key tiles:
 //     global   128 consecutive tokens x (T / 128) tiles of 128 keys             2-D tensor map [F*T, 3C], box {64, 128}
 //     window   7 rows of a 14 x 14 window (98 queries) x 1-2 tiles of 7 window   4-D tensor map [F, H, W, 3C],
-//              rows (98 keys, MMA N / K = 112)                                   box {64, 14, 7, 1}: OOB -> zero fill
+//              rows (98 keys, MMA N / K = 112); a whole 7 x 7 window (49 / 64);  box {64, ws, 7, 1}: OOB -> zero fill
+//              or the 49 max-pooled queries of a 14 x 14 window (q-pool blocks)
 // TMEM (512 columns): Q bf16 [0,64) -- S fp32 [64,192) / [192,320), double buffered; P (bf16 pairs) overwrites the first
 // 64 columns of its S buffer -- O fp32 [320, 320 + HD).  Both MMAs take their A operand (Q, P) from TMEM; K / V tiles
 // arrive by TMA (128-byte swizzle) through a 3-stage ring, V is consumed in place as an MN-major operand.  A head of 96 is
@@ -32,7 +33,8 @@ constexpr int THREADS = 320;
 constexpr int CHUNK_BYTES = KN * 128;  // one 64-column (128-byte) chunk of a K or V tile
 constexpr int XCH_BYTES = 4 * QM * 4;
 constexpr int ALIGN_SLACK = 1024;
-constexpr int WIN = 14, WIN_ROWS = 7, WIN_KEYS = WIN * WIN_ROWS /* 98 */, WIN_N = 112;
+constexpr int WIN_ROWS = 7;  // window rows per key tile / query tile: 14 x 14 windows are two tiles of 98, 7 x 7 windows one of 49
+__host__ __device__ constexpr int win_n(int ws) { return ws == 14 ? 112 : 64; }  // MMA N / K covering 7 * ws keys
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
@@ -112,18 +114,23 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
   int wx0 = 0, wy0 = 0;      // window origin (tokens)
   int qy0 = 0;               // first window row of the query tile
   int npad = 0;
+  const int ws = p.window;                                        // 0, 7 or 14
+  const bool pooled = p.pool != 0;                                // queries = 2 x 2 max-pool of the window's q (ws == 14)
+  const int qtiles = (ws == 14 && !pooled) ? 2 : 1;               // query tiles per window
+  const int nq = pooled ? 49 : WIN_ROWS * ws;                     // query rows of a tile
   if (windowed) {
-    const int nwx = (p.W + WIN - 1) / WIN;
-    const int win = blockIdx.x >> 1, qt = blockIdx.x & 1;
-    wy0 = (win / nwx) * WIN;
-    wx0 = (win % nwx) * WIN;
+    const int nwx = (p.W + ws - 1) / ws;
+    const int win = blockIdx.x / qtiles, qt = blockIdx.x % qtiles;
+    wy0 = (win / nwx) * ws;
+    wx0 = (win % nwx) * ws;
     qy0 = qt * WIN_ROWS;
     if (wy0 + qy0 >= p.H) return;  // this half of the window lies entirely in the padding: nothing to write
-    n = (wy0 + WIN_ROWS < p.H) ? 2 : 1;
-    npad = WIN * WIN - min(WIN, p.W - wx0) * min(WIN, p.H - wy0);
+    n = (ws == 14 && wy0 + WIN_ROWS < p.H) ? 2 : 1;
+    npad = ws * ws - min(ws, p.W - wx0) * min(ws, p.H - wy0);
   } else {
     n = (p.H * p.W) / KN;
   }
+  const int WIN_KEYS = WIN_ROWS * ws, WIN_N = win_n(ws);          // (window mode) keys per tile, MMA N / K
   const int rows_per_tile = windowed ? WIN_KEYS : KN;
 
   if (warp == 0 && lane == 0) {
@@ -141,8 +148,8 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
     mbar_fence_init();
   }
   if (windowed) {
-    // rows [98, 112) of every V chunk are read by the second MMA (K = 112) with P = 0: they must hold finite values.
-    // TMA never writes them (the box has 98 rows), so clearing them once is enough.
+    // rows [98, 112) / [49, 64) of every V chunk are read by the second MMA with P = 0: they must hold finite values.
+    // TMA never writes them (the box has 98 / 49 rows), so clearing them once is enough.
     for (int i = threadIdx.x; i < STAGES * C::NCH * (WIN_N - WIN_KEYS) * 8; i += THREADS) {
       const int chunk = i / ((WIN_N - WIN_KEYS) * 8), rem = i % ((WIN_N - WIN_KEYS) * 8);
       *reinterpret_cast<uint4*>(sV + chunk * CHUNK_BYTES + (WIN_KEYS + rem / 8) * 128 + (rem % 8) * 16) =
@@ -185,7 +192,7 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
       __syncwarp();
     }
   } else if (warp == 1) {
-    const uint32_t idesc_s = windowed ? idesc_bf16(QM, WIN_N, 0) : idesc_bf16(QM, KN, 0);
+    const uint32_t idesc_s = idesc_bf16(QM, windowed ? WIN_N : KN, 0);
     constexpr uint32_t idesc_o = idesc_bf16(QM, HD, 1);
     const int ksteps_pv = (windowed ? WIN_N : KN) / 16;
     auto issue_s = [&](int j) {
@@ -214,9 +221,10 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
       if (elect_one()) {
         if (windowed) {
 #pragma unroll
-          for (int kk = 0; kk < WIN_N / 16; ++kk)
-            mma_ts(tmem_O, tmem_S + (j & 1) * KN + kk * 8, desc_mn_sw128(v_addr + kk * 2048, CHUNK_BYTES), idesc_o,
-                   (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 112 / 16; ++kk)
+            if (kk < WIN_N / 16)
+              mma_ts(tmem_O, tmem_S + (j & 1) * KN + kk * 8, desc_mn_sw128(v_addr + kk * 2048, CHUNK_BYTES), idesc_o,
+                     (j > 0 || kk > 0) ? 1u : 0u);
         } else {
 #pragma unroll
           for (int kk = 0; kk < KN / 16; ++kk)
@@ -239,13 +247,25 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
     // ---- which token this query row is ----
     bool row_ok;
     long long tok;  // row of qkv / out
-    if (windowed) {
-      const int ty = wy0 + qy0 + r / WIN, tx = wx0 + r % WIN;
-      row_ok = r < WIN_KEYS && ty < p.H && tx < p.W;
+    long long tok_out;   // row of out (the pooled grid for q-pool blocks)
+    int pty = 0, ptx = 0;  // (pooled) top-left token of this query's 2 x 2 pooling cell
+    if (windowed && pooled) {
+      const int i = r / 7, j2 = r % 7;
+      pty = wy0 + 2 * i;
+      ptx = wx0 + 2 * j2;
+      const int Hp = p.H >> 1, Wp = p.W >> 1;
+      row_ok = r < nq && (pty >> 1) < Hp && (ptx >> 1) < Wp;
+      tok = ((long long)f * p.H + pty) * p.W + ptx;
+      tok_out = ((long long)f * Hp + (pty >> 1)) * Wp + (ptx >> 1);
+    } else if (windowed) {
+      const int ty = wy0 + qy0 + r / ws, tx = wx0 + r % ws;
+      row_ok = r < nq && ty < p.H && tx < p.W;
       tok = ((long long)f * p.H + ty) * p.W + tx;
+      tok_out = tok;
     } else {
       row_ok = true;
       tok = (long long)f * p.H * p.W + blockIdx.x * QM + r;
+      tok_out = tok;
     }
     // ---- Q row -> TMEM; in window mode also this row's score against a padding token, q . b_k ----
     float spad = 0.f;
@@ -258,7 +278,32 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
 #pragma unroll
       for (int i = 0; i < NW / 4; ++i) {
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (row_ok && i * 4 < nw) u = *reinterpret_cast<const uint4*>(qrow + i * 8);
+        if (row_ok && i * 4 < nw) {
+          if (!pooled) {
+            u = *reinterpret_cast<const uint4*>(qrow + i * 8);
+          } else {
+            // 2 x 2 max-pool of q over the cell; cell tokens in the zero padding carry q = bias (hieradet.py:60-67)
+            __nv_bfloat162 m[4];
+            bool first = true;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int yy = pty + (a >> 1), xx = ptx + (a & 1);
+              uint4 t;
+              if (yy < p.H && xx < p.W) {
+                t = *reinterpret_cast<const uint4*>(qrow + ((long long)(a >> 1) * p.W + (a & 1)) * ld + i * 8);
+              } else {
+                const float* bq = p.qkv_bias + h * HD + w_lo * 2 + i * 8;
+                t.x = pack_bf16x2(bq[0], bq[1]); t.y = pack_bf16x2(bq[2], bq[3]);
+                t.z = pack_bf16x2(bq[4], bq[5]); t.w = pack_bf16x2(bq[6], bq[7]);
+              }
+              const __nv_bfloat162* tp = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) m[e] = first ? tp[e] : __hmax2(m[e], tp[e]);
+              first = false;
+            }
+            u = *reinterpret_cast<const uint4*>(m);
+          }
+        }
         w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
       }
       if (npad > 0) {
@@ -284,8 +329,8 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
     }
     // ---- key masks of this thread's 64 columns, per tile (window mode) ----
     unsigned long long kmask[2] = {~0ull, ~0ull};
-    if (windowed) {  // key c of a tile is window row c / 14, column c % 14: valid columns [0, vx) of valid rows [0, vy)
-      const int vx = min(WIN, p.W - wx0);
+    if (windowed) {  // key c of a tile is window row c / ws, column c % ws: valid columns [0, vx) of valid rows [0, vy)
+      const int vx = min(ws, p.W - wx0);
       const unsigned long long rowbits = (1ull << vx) - 1ull;
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -294,10 +339,10 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
 #pragma unroll
         for (int cy = 0; cy < WIN_ROWS; ++cy) {
           if (cy < vy) {
-            const int sh = cy * WIN;
+            const int sh = cy * ws;
             if (sh < 64) {
               lo |= rowbits << sh;
-              if (sh + WIN > 64) hi |= rowbits >> (64 - sh);
+              if (sh + ws > 64) hi |= rowbits >> (64 - sh);
             } else {
               hi |= rowbits << (sh - 64);
             }
@@ -396,7 +441,7 @@ hiera_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmKV, const usvm_hiera
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaf(wpad, __bfloat162float(__float2bfloat16(bv[i])), v[i]);
       }
-      bf16* O = reinterpret_cast<bf16*>(p.out) + tok * dim + h * HD + c;
+      bf16* O = reinterpret_cast<bf16*>(p.out) + tok_out * dim + h * HD + c;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 v4;
@@ -440,7 +485,7 @@ int launch(const usvm_hiera_attn_params* p, cudaStream_t stream) {
   if (p->window > 0) {
     cuuint64_t gdim[4] = {ld, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->F};
     cuuint64_t gstr[3] = {ld * 2, ld * 2 * p->W, ld * 2 * p->W * p->H};
-    cuuint32_t box[4] = {64u, (cuuint32_t)WIN, (cuuint32_t)WIN_ROWS, 1u};
+    cuuint32_t box[4] = {64u, (cuuint32_t)p->window, (cuuint32_t)WIN_ROWS, 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p->qkv), gdim, gstr, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -460,7 +505,7 @@ int launch(const usvm_hiera_attn_params* p, cudaStream_t stream) {
     return USVM_ERR_CUDA;
   dim3 grid;
   if (p->window > 0)
-    grid = dim3(2 * cdiv(p->H, WIN) * cdiv(p->W, WIN), p->heads, p->F);
+    grid = dim3(((p->window == 14 && !p->pool) ? 2 : 1) * cdiv(p->H, p->window) * cdiv(p->W, p->window), p->heads, p->F);
   else
     grid = dim3(p->H * p->W / QM, p->heads, p->F);
   usvm_launch(hiera_attn_tc5_kernel<HD>, grid, dim3(THREADS), Cfg<HD>::SMEM, stream, tm, *p);
@@ -475,7 +520,8 @@ extern "C" int usvm_hiera_attn_tc5(const usvm_hiera_attn_params* p, void* stream
   if (p->dim % p->heads) return USVM_ERR_ARG;
   const int hd = p->dim / p->heads;
   if (hd != 96 && hd != 64) return USVM_ERR_ARG;
-  if (p->window != 0 && p->window != WIN) return USVM_ERR_ARG;
+  if (p->window != 0 && p->window != 14 && p->window != 7) return USVM_ERR_ARG;
+  if (p->pool && (p->window != 14 || (p->H & 1) || (p->W & 1))) return USVM_ERR_ARG;
   if (p->window == 0 && ((p->H * p->W) % KN)) return USVM_ERR_ARG;
   if (p->window > 0 && !p->qkv_bias) return USVM_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(p->qkv) & 15) || (reinterpret_cast<uintptr_t>(p->out) & 15) || (p->dim % 8))

@@ -422,11 +422,13 @@ class Engine:
             Ho, Wo = (H // 2, W // 2) if pool else (H, W)
             # windows of <= 64 keys: one fused kernel.  (It also handles the 14 x 14 windows of stage 3, but one CTA per
             # (window, head) walking 13 query slabs is slower there than gather + flash kernel + scatter: measured.)
-            if 0 < ws * ws <= 64 and self.fused_windows:
+            if self.tc5_encoder_attn and (ws in (7, 14) or (ws == 0 and (H * W) % 128 == 0)) and (not pool or ws == 14):
+                # stage-3 / 4 blocks (global, 14 x 14 and 7 x 7 windows, the q-pool block between them): tcgen05 kernel,
+                # window (un)partition = TMA coordinates
+                att = ops.hiera_attn(qkv, blk["qkv_b"], Fr, H, W, dout, heads, window=ws, pool=pool)
+            elif 0 < ws * ws <= 64 and self.fused_windows:
+                # stage-1 / 2 windows (64 and 16 keys): a 128-row tcgen05 tile would be >= 50 % masking; fused mma.sync kernel
                 att = ops.window_attn(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout, heads)
-            elif self.tc5_encoder_attn and not pool and ws in (0, 14) and (ws or (H * W) % 128 == 0):
-                # stage-3 blocks (global and 14 x 14 windows): tcgen05 kernel, window (un)partition = TMA coordinates
-                att = ops.hiera_attn(qkv, blk["qkv_b"], Fr, H, W, dout, heads, window=ws)
             elif ws > 0:
                 Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout)
                 Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * dout, dout, 96),

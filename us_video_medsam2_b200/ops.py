@@ -191,18 +191,19 @@ def fmha(q, k, v, B, H, Nq, Nk, head_dim, q_addr, k_addr, v_addr, out=None, num_
     return out
 
 
-def hiera_attn(qkv, qkv_bias, Fr, H, W, dim, heads, window=0):
+def hiera_attn(qkv, qkv_bias, Fr, H, W, dim, heads, window=0, pool=False):
     """Image-encoder attention on the tcgen05 kernel, straight from the projection's raster-order output:
-    qkv bf16 [Fr*H*W, 3*dim] -> bf16 [Fr*H*W, dim].  window 0 = global, 14 = the 14 x 14 windows of Hiera stage 3 / the
-    ViT trunk (padding tokens enter in closed form through qkv_bias)."""
+    qkv bf16 [Fr*H*W, 3*dim] -> bf16 [Fr*H*W, dim].  window 0 = global, 14 / 7 = the windows of Hiera stages 3 / 4 and of
+    the ViT trunk (padding tokens enter in closed form through qkv_bias); pool: 2 x 2 max-pooled queries (window 14),
+    output on the pooled grid [Fr*(H/2)*(W/2), dim]."""
     _chk(qkv, BF16, "qkv")
     _chk(qkv_bias, F32, "qkv_bias")
     if qkv.shape != (Fr * H * W, 3 * dim):
         raise RuntimeError(f"hiera_attn: qkv {tuple(qkv.shape)} != {(Fr * H * W, 3 * dim)}")
-    out = empty((Fr * H * W, dim), BF16, qkv)
+    out = empty((Fr * (H // 2) * (W // 2) if pool else Fr * H * W, dim), BF16, qkv)
     p = HieraAttnParams()
     p.qkv, p.out, p.qkv_bias = qkv.data_ptr(), out.data_ptr(), qkv_bias.data_ptr()
-    p.F, p.H, p.W, p.dim, p.heads, p.window = Fr, H, W, dim, heads, window
+    p.F, p.H, p.W, p.dim, p.heads, p.window, p.pool = Fr, H, W, dim, heads, window, int(bool(pool))
     p.scale = 1.0 / math.sqrt(dim // heads)
     call("usvm_hiera_attn_tc5", C.byref(p), _stream())
     return out
