@@ -408,7 +408,9 @@ def time_dominant_kernel_batched(dev, peaks, B=32, iters=10):
 GF_ENCODER, GF_PER_OBJECT = 62.9, 52.0  # GFLOP per frame (shared by objects) / per object-frame
 # HBM-bound pieces, algorithmic bytes per object-frame: memory encoder = 1.0 MB mask in (fp32 512^2) + 0.5 MB
 # pix_feat (bf16) + 2.8 MB weights + 0.13 MB memory out; hole filling = 64 KiB logits in + 64 KiB out
-BYTES_MEM_ENCODER = 1.048576e6 + 0.524288e6 + 2.8e6 + 0.131072e6
+BYTES_MEM_ENCODER_WEIGHTS = 2.8e6
+BYTES_MEM_ENCODER_ACT = 1.048576e6 + 0.524288e6 + 0.131072e6
+BYTES_MEM_ENCODER = BYTES_MEM_ENCODER_ACT + BYTES_MEM_ENCODER_WEIGHTS
 BYTES_FILL_HOLES = 2 * 128 * 128 * 4
 
 
@@ -429,7 +431,7 @@ def _event_time(fn, iters, flush=None):
     return tot / iters
 
 
-def time_components(pred, dev, B, peaks, iters=10):
+def time_components(pred, dev, B, peaks, iters=10, batched_objects=0):
     """What north_star asks besides the headline: tensor-pipe utilisation of the batched image encoder and achieved HBM GB/s
     of the memory encoder and the hole-filling post-process, each timed with CUDA events at its in-run shape (the encoder
     as the 16-frame captured graph the clip replays; the other two as the launches of one tracked frame), L2 flushed
@@ -450,29 +452,35 @@ def time_components(pred, dev, B, peaks, iters=10):
                                 "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"],
                                 "flops": f"{GF_ENCODER} GFLOP per frame (SURVEY 8d)"}
     g = torch.Generator(device=dev).manual_seed(5)
-    low = torch.randn((B, 1, 128, 128), generator=g, device=dev) * 0.07
-    score = torch.ones((B, 1), device=dev)
     fb = torch.randn((1024, 256), generator=g, device=dev).to(torch.bfloat16)
+    # at the benched object count (latency shapes) and, with the batched leg on, at its 32 objects (throughput shapes)
+    for nobj, sfx in [(B, "")] + ([(batched_objects, "_batched")] if batched_objects and batched_objects != B else []):
+        low = torch.randn((nobj, 1, 128, 128), generator=g, device=dev) * 0.07
+        score = torch.ones((nobj, 1), device=dev)
 
-    def mem_enc():
-        eng.encode_memory(fb, eng.mem_mask_input(low, False), score, B)
+        def mem_enc():
+            eng.encode_memory(fb, eng.mem_mask_input(low, False), score, nobj)
 
-    for _ in range(2):
-        mem_enc()
-    torch.cuda.synchronize()
-    gr = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(gr):
-        mem_enc()
-    ms = _event_time(gr.replay, iters, flush)
-    gbs = BYTES_MEM_ENCODER * B / ms / 1e6
-    out["memory_encoder"] = {"bound": "hbm", "objects": B, "avg_us": ms * 1e3, "achieved": gbs, "peak": peaks["hbm"],
-                             "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                             "bytes": f"{BYTES_MEM_ENCODER / 1e6:.2f} MB per object-frame (SURVEY 8d); 15 dependent "
-                                      "launches on 16 KiB - 1 MiB operands: latency, not bandwidth, bounds it at this size"}
-    ms = _event_time(lambda: ops.fill_holes(low, 8), iters, flush)
-    gbs = BYTES_FILL_HOLES * B / ms / 1e6
-    out["fill_holes"] = {"bound": "hbm", "objects": B, "avg_us": ms * 1e3, "achieved": gbs, "peak": peaks["hbm"],
-                         "unit": "GB/s", "frac": gbs / peaks["hbm"], "bytes": "64 KiB in + 64 KiB out per object-frame"}
+        for _ in range(2):
+            mem_enc()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            mem_enc()
+        ms = _event_time(gr.replay, iters, flush)
+        nbytes = BYTES_MEM_ENCODER_WEIGHTS + BYTES_MEM_ENCODER_ACT * nobj  # weights once per launch group
+        gbs = nbytes / ms / 1e6
+        out["memory_encoder" + sfx] = {
+            "bound": "hbm", "objects": nobj, "avg_us": ms * 1e3, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": gbs / peaks["hbm"], "achieved_tflops": 2.9 * nobj / ms,
+            "bytes": f"{BYTES_MEM_ENCODER_WEIGHTS / 1e6:.1f} MB of weights per launch group + "
+                     f"{BYTES_MEM_ENCODER_ACT / 1e6:.2f} MB per object-frame (SURVEY 8d); 15 dependent launches: latency bound "
+                     "at one object, a mix of bandwidth and fp32 / tensor math (2.9 GFLOP per object) at 32"}
+        ms = _event_time(lambda: ops.fill_holes(low, 8), iters, flush)
+        gbs = BYTES_FILL_HOLES * nobj / ms / 1e6
+        out["fill_holes" + sfx] = {"bound": "hbm", "objects": nobj, "avg_us": ms * 1e3, "achieved": gbs,
+                                   "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                   "bytes": "64 KiB in + 64 KiB out per object-frame"}
     return out
 
 
@@ -729,7 +737,8 @@ def run_b200(args, rank, world):
         roofline["whole_path"] = {"achieved": wp, "unit": "TFLOP/s", "frac": wp / peaks["bf16_sustained"],
                                   "formula": f"({GF_ENCODER} + {GF_PER_OBJECT} x {B}) GFLOP per frame x frames/s per GPU"}
         with torch.inference_mode():
-            roofline["components"] = time_components(pred, dev, B, peaks)
+            roofline["components"] = time_components(
+                pred, dev, B, peaks, batched_objects=args.batched_videos * args.batched_objects)
     batched = None
     if args.batched_videos > 0 and not clip_mode and args.model == "hiera_t512":
         with torch.inference_mode():

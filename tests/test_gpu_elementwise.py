@@ -171,6 +171,14 @@ def test_conv2d_small(Cin, Cout, k, s, p, H):
         v = (y - u).pow(2).mean(1, keepdim=True)
         y = F.gelu((y - u) / torch.sqrt(v + 1e-6) * lw[None, :, None, None] + lb[None, :, None, None])
     assert (out.view(B, Ho, Wo, Cout) - y.permute(0, 2, 3, 1)).abs().max().item() < 1e-4
+    if (Cin, Cout, k) in ((1, 4, 3), (4, 16, 3), (16, 64, 3)) and H >= 128:
+        # batched path (2 x 2 pixels per thread, four times the tile): same taps in the same order -> bit-identical
+        Bb = 40
+        xb = torch.randn((Bb, H, H, Cin), generator=g, device="cuda")
+        xb[:B] = x.permute(0, 2, 3, 1)
+        big, _, _ = ops.conv2d_small(xb, w.permute(2, 3, 1, 0).contiguous(), b, Bb, H, H, Cin, Cout, k, s, p,
+                                     ln=(lw, lb) if use_ln else None, gelu=use_ln)
+        assert torch.equal(big.view(Bb, -1)[:B], out.view(B, -1))
 
 
 def test_im2col_nhwc_and_dwconv():

@@ -42,3 +42,11 @@ for M, N, K in ((32768, 256, 256), (32768, 128, 256), (32768, 256, 128)):
     b = torch.randn((N,), device="cuda")
     t = timeit(lambda: ops.gemm_f32(a, w, b, tf32=True))
     print(f"tf32 GEMM M {M} N {N} K {K}: {t:7.1f} us  {2.0 * M * N * K / t / 1e6:7.1f} TFLOP/s")
+# mask down-sampler stages at 32 objects
+for Cin, Cout, H in ((1, 4, 512), (4, 16, 256), (16, 64, 128)):
+    for B in (1, 32):
+        x = torch.randn((B, H, H, Cin), device="cuda")
+        w = torch.randn((3, 3, Cin, Cout), device="cuda") / (9 * Cin) ** 0.5
+        b, lw, lb = (torch.randn(Cout, device="cuda") for _ in range(3))
+        t = timeit(lambda: ops.conv2d_small(x, w, b, B, H, H, Cin, Cout, 3, 2, 1, ln=(lw, lb), gelu=True))
+        print(f"conv3x3/s2 {Cin:2d}->{Cout:2d} on {H}^2, {B:2d} objects: {t:7.1f} us")
