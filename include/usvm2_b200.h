@@ -271,6 +271,13 @@ int usvm_store_outputs(const usvm_frame_ctrl* ctrl_dev, const float* obj_ptr, co
 int usvm_conv2d_small(const float* x, const float* w_kkio, const float* bias, const float* ln_w, const float* ln_b,
                       float eps, int gelu, float* out_f32, void* out_bf16, int B, int H, int W, int Cin, int Cout,
                       int k, int stride, int pad, void* stream);
+/* First stage of the MaskDownSampler (Conv2d 1 -> 4, k x k / stride, LayerNorm2d, GELU) reading a VIRTUAL H x W input: the
+ * bilinear (align_corners=False) upsampling of low [B, hi, wi] followed by post_mode (sigmoid * scale + bias or binarise,
+ * sam2_base.py:1472-1484) is evaluated while the footprint is staged, so the upsampled mask is never written.
+ * out_f32 [B, Ho, Wo, 4]; Ho, Wo multiples of 16. */
+int usvm_conv2d_mask_first(const float* low, int hi, int wi, int post_mode, float post_scale, float post_bias,
+                           const float* w_kkio, const float* bias, const float* ln_w, const float* ln_b, float eps, int gelu,
+                           float* out_f32, int B, int H, int W, int k, int stride, int pad, void* stream);
 int usvm_im2col_nhwc(const float* x, void* A, int B, int H, int W, int C, int k, int stride, int pad, void* stream);
 /* CXBlock depthwise 7x7 + LayerNorm2d (memory_encoder.py:104-108); weights [49][C]; C == 256; bf16 out */
 int usvm_dwconv7_ln(const float* x, const float* w_49c, const float* bias, const float* ln_w, const float* ln_b,

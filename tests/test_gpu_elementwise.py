@@ -531,3 +531,26 @@ def test_tcgen05_gemm_gelu_epilogue_is_fp32_accurate():
         m = want.abs() > 1e-2
         assert (err[m] / want[m].abs()).max().item() < 2e-5
         assert torch.equal(got[: x.shape[0]], got[-x.shape[0]:])
+
+
+@pytest.mark.parametrize("B,binarize", [(2, False), (3, True), (40, False)])
+def test_mask_first_conv_equals_resize_then_conv(B, binarize):
+    """usvm_conv2d_mask_first (bilinear x4 + sigmoid / binarise evaluated inside the footprint load) against
+    resize_bilinear followed by the ordinary first down-sampler stage (both the latency and the batched tile kernels):
+    identical with the binarised input, within fp32 rounding of the interpolation (FMA contraction differs between the two
+    kernels) with the sigmoid."""
+    from us_video_medsam2_b200 import ops
+
+    g = _g(B + 77)
+    low = torch.randn((B, 1, 128, 128), generator=g, device="cuda") * 3
+    w = torch.randn((3, 3, 1, 4), generator=g, device="cuda") / 3
+    b, lw, lb = (torch.randn(4, generator=g, device="cuda") for _ in range(3))
+    post = ops.POST_BINARIZE_AFFINE if binarize else ops.POST_SIGMOID_AFFINE
+    full = ops.resize_bilinear(low, 512, 512, post, 20.0, -10.0)
+    want, Ho, Wo = ops.conv2d_small(full.reshape(B, 512, 512, 1), w, b, B, 512, 512, 1, 4, 3, 2, 1, ln=(lw, lb), gelu=True)
+    got, Ho2, Wo2 = ops.conv2d_mask_first(low, post, 20.0, -10.0, w, b, B, 512, 512, 3, 2, 1, ln=(lw, lb), gelu=True)
+    assert (Ho, Wo) == (Ho2, Wo2) == (256, 256)
+    if binarize:
+        assert torch.equal(got, want)
+    else:
+        assert (got - want).abs().max().item() < 2e-5

@@ -107,6 +107,7 @@ _SIGNATURES = {
     "usvm_normalize_rgb_u8": [_P, _P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P],
     "usvm_build_memory": [C.POINTER(MemoryFrames), _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "usvm_conv2d_small": [_P, _P, _P, _P, _P, _F, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "usvm_conv2d_mask_first": [_P, _I, _I, _I, _F, _F, _P, _P, _P, _P, _F, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "usvm_im2col_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "usvm_dwconv7_ln": [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P],
     "usvm_resize_bilinear": [_P, _P, _LL, _I, _I, _I, _I, _I, _F, _F, _P],

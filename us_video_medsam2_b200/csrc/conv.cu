@@ -14,6 +14,34 @@
 
 namespace {
 
+__device__ __forceinline__ float post_op(float v, int mode, float scale, float bias) {
+  if (mode == USVM_POST_SIGMOID_AFFINE) return (1.0f / (1.0f + expf(-v))) * scale + bias;
+  if (mode == USVM_POST_BINARIZE_AFFINE) return (v > 0.f ? 1.0f : 0.0f) * scale + bias;
+  return v;
+}
+
+// Virtual input of the mask down-sampler's first stage: instead of reading a materialised [B, Ho, Wo] image, sample it
+// from the low-resolution logits -- F.interpolate(bilinear, align_corners=False) followed by post_op, the arithmetic of
+// resize_bilinear_kernel -- so the 1 MiB-per-object upsampled mask never exists (_encode_new_memory, sam2_base.py:1472-1484).
+struct UpSrc {
+  const float* src;  // [B, hi, wi] or nullptr
+  int hi, wi, mode;
+  float scale, bias;
+};
+__device__ __forceinline__ float up_sample(const UpSrc& u, int b, int oy, int ox, int Ho, int Wo) {
+  const float sh = (float)u.hi / Ho, sw = (float)u.wi / Wo;
+  float fy = sh * (oy + 0.5f) - 0.5f, fx = sw * (ox + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < u.hi - 1 ? 1 : 0), x1 = x0 + (x0 < u.wi - 1 ? 1 : 0);
+  const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float* p = u.src + (long long)b * u.hi * u.wi;
+  const float v = hy * (hx * __ldg(p + y0 * u.wi + x0) + lx * __ldg(p + y0 * u.wi + x1)) +
+                  ly * (hx * __ldg(p + y1 * u.wi + x0) + lx * __ldg(p + y1 * u.wi + x1));
+  return post_op(v, u.mode, u.scale, u.bias);
+}
+
 // lanes cover (pixel, output channel) pairs: a warp handles 32 / Cout pixels when Cout < 32 (Cout a power of two),
 // one pixel with 2 channels per lane when Cout == 64; weights [k*k*Cin][Cout] staged in shared memory
 __global__ void __launch_bounds__(256)
@@ -94,7 +122,7 @@ __global__ void __launch_bounds__(256)
 conv2d_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int gelu,
                    float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int H, int W, int k, int s, int pad, int Ho,
-                   int Wo) {
+                   int Wo, const UpSrc up) {
   constexpr int LPP = COUT / 4;           // lanes per pixel
   constexpr int PIX = 256 / LPP;          // pixels per CTA
   constexpr int TW = PIX == 256 ? 16 : PIX == 64 ? 8 : 4;  // square tile
@@ -142,7 +170,9 @@ conv2d_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt, co
         if (i < nf) {
           const int r = i / row_f, c = i - r * row_f;
           const int y = iy0 + r, xx = ix0 + c / CIN;
-          if (y >= 0 && y < H && xx >= 0 && xx < W) v[u] = __ldg(x + (((long long)b * H + y) * W + ix0) * CIN + c);
+          if (y >= 0 && y < H && xx >= 0 && xx < W)
+            v[u] = (CIN == 1 && up.src) ? up_sample(up, b, y, xx, H, W)
+                                        : __ldg(x + (((long long)b * H + y) * W + ix0) * CIN + c);
         }
       }
 #pragma unroll
@@ -199,7 +229,7 @@ __global__ void __launch_bounds__(256)
 conv2d_tile4_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                     const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, int gelu,
                     float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int H, int W, int k, int s, int pad, int Ho,
-                    int Wo) {
+                    int Wo, const UpSrc up) {
   constexpr int LPP = COUT / 4;           // lanes per pixel block
   constexpr int GRP = 256 / LPP;          // 2 x 2 pixel blocks per CTA
   constexpr int GW = GRP == 256 ? 16 : GRP == 64 ? 8 : 4;  // square arrangement of the blocks
@@ -246,7 +276,9 @@ conv2d_tile4_kernel(const float* __restrict__ x, const float* __restrict__ wt, c
         if (i < nf) {
           const int r = i / row_f, c = i - r * row_f;
           const int y = iy0 + r, xx = ix0 + c / CIN;
-          if (y >= 0 && y < H && xx >= 0 && xx < W) v[u] = __ldg(x + (((long long)b * H + y) * W + ix0) * CIN + c);
+          if (y >= 0 && y < H && xx >= 0 && xx < W)
+            v[u] = (CIN == 1 && up.src) ? up_sample(up, b, y, xx, H, W)
+                                        : __ldg(x + (((long long)b * H + y) * W + ix0) * CIN + c);
         }
       }
 #pragma unroll
@@ -308,7 +340,7 @@ conv2d_tile4_kernel(const float* __restrict__ x, const float* __restrict__ wt, c
 template <int CIN, int COUT>
 int launch_conv_tile(const float* x, const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
                      int gelu, float* out_f32, bf16* out_bf16, int B, int H, int W, int k, int s, int pad, int Ho, int Wo,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const UpSrc up = UpSrc{nullptr, 0, 0, 0, 0.f, 0.f}) {
   constexpr int PIX = 256 / (COUT / 4);
   constexpr int TW = PIX == 256 ? 16 : PIX == 64 ? 8 : 4;
   // batched path: 2 x 2 pixels per thread once the larger tiles still fill the device twice over
@@ -324,7 +356,7 @@ int launch_conv_tile(const float* x, const float* w, const float* bias, const fl
         usvm_setup_done(configured4);
       }
       usvm_launch(conv2d_tile4_kernel<CIN, COUT>, dim3(B * (Ho / (2 * TW)) * (Wo / (2 * TW))), dim3(256), smem4, stream, x, w,
-                  bias, ln_w, ln_b, eps, gelu, out_f32, out_bf16, H, W, k, s, pad, Ho, Wo);
+                  bias, ln_w, ln_b, eps, gelu, out_f32, out_bf16, H, W, k, s, pad, Ho, Wo, up);
       return usvm_check_launch();
     }
   }
@@ -339,7 +371,7 @@ int launch_conv_tile(const float* x, const float* w, const float* bias, const fl
   }
   if (smem > 96 * 1024) return USVM_ERR_ARG;
   usvm_launch(conv2d_tile_kernel<CIN, COUT>, dim3(B * (Ho / TW) * (Wo / TW)), dim3(256), smem, stream, x, w, bias, ln_w, ln_b,
-              eps, gelu, out_f32, out_bf16, H, W, k, s, pad, Ho, Wo);
+              eps, gelu, out_f32, out_bf16, H, W, k, s, pad, Ho, Wo, up);
   return usvm_check_launch();
 }
 
@@ -589,11 +621,6 @@ dwconv7_ln_tile_kernel(const float* __restrict__ x, const float* __restrict__ wt
   }
 }
 
-__device__ __forceinline__ float post_op(float v, int mode, float scale, float bias) {
-  if (mode == USVM_POST_SIGMOID_AFFINE) return (1.0f / (1.0f + expf(-v))) * scale + bias;
-  if (mode == USVM_POST_BINARIZE_AFFINE) return (v > 0.f ? 1.0f : 0.0f) * scale + bias;
-  return v;
-}
 
 // F.interpolate(mode="bilinear", align_corners=False); planes = N*C
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int Hi,
@@ -691,6 +718,21 @@ inline int grid_for(long long total, int threads = 256) {
 }  // namespace
 
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int usvm_conv2d_mask_first(const float* low, int hi, int wi, int post_mode, float post_scale, float post_bias,
+                                      const float* w_kkio, const float* bias, const float* ln_w, const float* ln_b,
+                                      float eps, int gelu, float* out_f32, int B, int H, int W, int k, int stride, int pad,
+                                      void* stream) {
+  if (!low || !w_kkio || !bias || !out_f32 || hi <= 0 || wi <= 0 || H <= 0 || W <= 0) return USVM_ERR_ARG;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  if (k > 4 || stride > 4 || (Ho % 16) || (Wo % 16)) return USVM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(w_kkio) & 15) || (reinterpret_cast<uintptr_t>(bias) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_f32) & 15) ||
+      (ln_w && ((reinterpret_cast<uintptr_t>(ln_w) & 15) || (reinterpret_cast<uintptr_t>(ln_b) & 15))))
+    return USVM_ERR_ARG;
+  return launch_conv_tile<1, 4>(low, w_kkio, bias, ln_w, ln_b, eps, gelu, out_f32, nullptr, B, H, W, k, stride, pad, Ho, Wo,
+                                STREAM, UpSrc{low, hi, wi, post_mode, post_scale, post_bias});
+}
 
 extern "C" int usvm_conv2d_small(const float* x, const float* w_kkio, const float* bias, const float* ln_w,
                                  const float* ln_b, float eps, int gelu, float* out_f32, void* out_bf16, int B, int H,

@@ -381,6 +381,8 @@ class Engine:
         self.tc5_encoder_attn = os.environ.get("USVM2_ENCODER_ATTN_TC5", "1") != "0"
         # memory-attention feed-forward block as one cluster kernel at one or two objects (0: two GEMM launches)
         self.fused_ffn = os.environ.get("USVM2_FUSED_FFN", "1") != "0"
+        # tracked frames: the mask's 512^2 upsampling + sigmoid inside the first down-sampler convolution (0: separate pass)
+        self.lazy_mask_upsample = os.environ.get("USVM2_LAZY_MASK_UPSAMPLE", "1") != "0"
 
     # ---------------------------------------------------------------- forked branches
     def _side(self, i):
@@ -633,7 +635,8 @@ class Engine:
             video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
         # (non_overlap_masks_for_mem_enc applies on every frame in eval, sam2_base.py:1466-1471: device-side, so the frame
         # stays one capturable graph)
-        mask_in = self.mem_mask_input(o["low"], False, non_overlap=self.cfg.non_overlap_masks_for_mem_enc, group=group)
+        mask_in = self.mem_mask_input(o["low"], False, non_overlap=self.cfg.non_overlap_masks_for_mem_enc, group=group,
+                                      lazy=True)
         self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl, pix_proj=pp, group=group)
         self._handoff(main, tail, video, pm)
         return video, pm
@@ -855,9 +858,19 @@ class Engine:
         frame store slot named by `ctrl`
         (_encode_new_memory sam2_base.py:1450-1498, MemoryEncoder memory_encoder.py:158-181)."""
         w = self.w
-        x, H, W, Cin = mask_in512.reshape(B, 512, 512, 1), 512, 512, 1
-        for (cw, cb, lw, lb), Cout in zip(w.md_convs, (4, 16, 64)):
-            x, H, W = ops.conv2d_small(x, cw, cb, B, H, W, Cin, Cout, 3, 2, 1, ln=(lw, lb), gelu=True)
+        H, W, Cin = 512, 512, 1
+        for si, ((cw, cb, lw, lb), Cout) in enumerate(zip(w.md_convs, (4, 16, 64))):
+            if si == 0 and isinstance(mask_in512, tuple):
+                # (low-res logits, post mode): the 512^2 upsampling + sigmoid / binarise is evaluated inside the first
+                # convolution's footprint load -- the upsampled mask is never written (see mem_mask_input(..., lazy=True))
+                low, post = mask_in512
+                x, H, W = ops.conv2d_mask_first(low, post, self.cfg.sigmoid_scale_for_mem_enc,
+                                                self.cfg.sigmoid_bias_for_mem_enc, cw, cb, B, H, W, 3, 2, 1, ln=(lw, lb),
+                                                gelu=True)
+            else:
+                if si == 0:
+                    x = mask_in512.reshape(B, 512, 512, 1)
+                x, H, W = ops.conv2d_small(x, cw, cb, B, H, W, Cin, Cout, 3, 2, 1, ln=(lw, lb), gelu=True)
             Cin = Cout
         A4 = ops.im2col_nhwc(x, B, 64, 64, 64, 3, 2, 1)
         _, c4n = ops.gemm_bf16(A4, w.md_conv3_w, bias=w.md_conv3_b, ln=(w.md_ln3[0], w.md_ln3[1], 1e-6, True))
@@ -875,12 +888,17 @@ class Engine:
         out, _ = ops.gemm_bf16(xb, w.mem_out[0], bias=w.mem_out[1], f32=True)
         return ops.finalize_memory(out, score, w.no_obj_embed_spatial, B, ctrl=ctrl)
 
-    def mem_mask_input(self, masks, binarize, non_overlap=False, group=0):
+    def mem_mask_input(self, masks, binarize, non_overlap=False, group=0, lazy=False):
         """Upsample low-res logits [B,1,h,w] to 512^2 (if needed) fused with sigmoid*20-10 or (x>0)*20-10.
         non_overlap: the non-overlapping constraint (sam2_base.py:1466-1471, 1663-1681) is applied to the 512^2 logits
-        first, per group of `group` objects (0 = all: the objects of one video)."""
+        first, per group of `group` objects (0 = all: the objects of one video).
+        lazy: return (low-res logits, post mode) for encode_memory to upsample inside its first convolution, when nothing
+        needs the materialised 512^2 mask (no non-overlap constraint)."""
         cfg = self.cfg
         post = ops.POST_BINARIZE_AFFINE if binarize else ops.POST_SIGMOID_AFFINE
+        if lazy and self.lazy_mask_upsample and not (non_overlap and masks.shape[0] > 1) \
+                and tuple(masks.shape[-2:]) != (512, 512) and masks.dtype == F32 and masks.is_contiguous():
+            return (masks, post)
         if non_overlap and masks.shape[0] > 1:
             hi = masks if tuple(masks.shape[-2:]) == (512, 512) else ops.resize_bilinear(masks, 512, 512)
             return ops.non_overlap(hi, group, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)

@@ -486,6 +486,20 @@ def conv2d_small(x, w_kkio, bias, B, H, W, Cin, Cout, k, stride, pad, ln=None, e
     return out, Ho, Wo
 
 
+def conv2d_mask_first(low, post_mode, post_scale, post_bias, w_kkio, bias, B, H, W, k, stride, pad, ln=None, eps=1e-6,
+                      gelu=False):
+    """First MaskDownSampler stage on the virtual H x W upsampling of low [B,1,h,w] (bilinear + post_mode fused into the
+    footprint load): -> (fp32 [B*Ho*Wo, 4], Ho, Wo)."""
+    _chk(low, F32, "low")
+    hi, wi = low.shape[-2:]
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = empty((B * Ho * Wo, 4), F32, low)
+    call("usvm_conv2d_mask_first", low.data_ptr(), hi, wi, post_mode, post_scale, post_bias, w_kkio.data_ptr(),
+         bias.data_ptr(), _ptr(ln[0]) if ln else 0, _ptr(ln[1]) if ln else 0, eps, int(gelu), out.data_ptr(), B, H, W, k,
+         stride, pad, _stream())
+    return out, Ho, Wo
+
+
 def im2col_nhwc(x, B, H, W, Cc, k, stride, pad):
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     A = empty((B * Ho * Wo, k * k * Cc), BF16, x)
