@@ -342,7 +342,7 @@ int usvm_gemm_skinny_f32(const usvm_skinny_params* p_host, void* stream);
 /* token -> image attention (transformer.py:194-198): q [B*Nt, H*16], k/v rows of stride kv_rs, Nt <= 16 */
 int usvm_attn_t2i_f32(const float* q, int q_rs, const float* k, const float* v, int kv_rs, float* out, int o_rs, int B,
                       int H, int Nt, int Nk, float scale, void* stream);
-/* Same attention split over the keys (128 per CTA, <= 16 splits): B*H*ceil(Nk/128) CTAs write partials
+/* Same attention split over the keys (128 per CTA, <= 64 splits): B*H*ceil(Nk/128) CTAs write partials
  * [B*H][splits][Nt][18] floats and the last CTA of each head (ticket in counters[B*H], zero before the first launch and
  * left zero afterwards) merges them in split order. */
 int usvm_attn_t2i_split_f32(const float* q, int q_rs, const float* k, const float* v, int kv_rs, float* out, int o_rs,

@@ -64,6 +64,20 @@ def _instantiate(node):
     return node
 
 
+def bplus_overrides():
+    """sam2.1_hiera_base_plus at 1024^2 (BASELINE configs[4]) as overrides of the shipped tiny-512 YAML: the reference has
+    no B+ config, its `Hiera` class defaults (hieradet.py:174-200) are the B+ stage layout; embed_dim 112 / 2 heads are
+    upstream's values (80.85 M parameters, the published size of the B+ checkpoint)."""
+    cfg = yaml.safe_load(open(os.path.join(REF_ROOT, "sam2/configs/sam2.1_hiera_t512.yaml")))["model"]
+    enc, att = cfg["image_encoder"], cfg["memory_attention"]
+    enc["trunk"].update(embed_dim=112, num_heads=2, stages=[2, 3, 16, 3], global_att_blocks=[12, 16, 20],
+                        window_pos_embed_bkg_spatial_size=[14, 14])
+    enc["neck"]["backbone_channel_list"] = [896, 448, 224, 112]
+    att["layer"]["self_attention"]["feat_sizes"] = [64, 64]
+    att["layer"]["cross_attention"]["feat_sizes"] = [64, 64]
+    return dict(image_encoder=enc, memory_attention=att, image_size=1024)
+
+
 def load_reference_predictor(npz=True, apply_postprocessing=True, seed=0, overrides=None):
     """Build the reference's SAM2VideoPredictor[NPZ] for sam2.1_hiera_t512 on CPU."""
     assert reference_available(), "reference mount missing"

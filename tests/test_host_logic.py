@@ -61,7 +61,11 @@ def test_builder_overrides_and_errors():
     assert kw["fill_hole_area"] == 8 and kw["binarize_mask_from_pts_for_mem_enc"] is True
     assert kw["sam_mask_decoder_extra_args"]["dynamic_multimask_stability_delta"] == 0.05
     with pytest.raises(FileNotFoundError):
-        _load_model_kwargs("configs/sam2.1_hiera_b+.yaml", [])
+        _load_model_kwargs("configs/sam2.1_hiera_l.yaml", [])
+    kw = _load_model_kwargs("configs/sam2.1/sam2.1_hiera_b+.yaml", [])  # BASELINE configs[4]
+    assert kw["variant"] == "hiera_b+" and kw["image_size"] == 1024
+    with pytest.raises(NotImplementedError):
+        _load_model_kwargs("configs/sam2.1_hiera_b+.yaml", ["++model.image_size=512"])
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             build_sam2_video_predictor("configs/sam2.1_hiera_t512.yaml")
@@ -78,6 +82,13 @@ def test_hiera_plan_and_cond_frame_selection():
     assert [i for i, p in enumerate(plan) if p[4]] == [1, 3, 10] and [i for i, p in enumerate(plan) if p[5]] == [0, 2, 9, 11]
     for a, b in zip(plan, hiera_block_plan()):
         assert a == (b["dim"], b["dim_out"], b["heads"], b["window"], b["pool"], b["emit"])
+    # Hiera-B+ (hieradet.py:174-200 class defaults + embed_dim 112 / 2 heads): 24 blocks, heads of 56 in every stage
+    from us_video_medsam2_b200.engine import HieraBPlusConfig
+    bp = hiera_plan(HieraBPlusConfig)
+    assert len(bp) == 24 and [p[1] for p in bp][::5] == [112, 448, 448, 448, 448]
+    assert all(p[1] // p[2] == 56 for p in bp) and [i for i, p in enumerate(bp) if p[3] == 0] == [12, 16, 20]
+    assert [i for i, p in enumerate(bp) if p[4]] == [2, 5, 21] and [i for i, p in enumerate(bp) if p[5]] == [1, 4, 20, 23]
+    assert [bp[i][3] for i in (0, 2, 3, 5, 6, 21, 22)] == [8, 8, 4, 4, 14, 14, 7]
     cond = {t: t for t in (0, 5, 9, 20, 31)}
     for frame in (1, 9, 15, 40):
         for k in (-1, 2, 3, 5):

@@ -24,7 +24,8 @@ _REQUIRED_TRUE = ("use_mask_input_as_output_without_sam", "directly_add_no_mem_e
 
 
 # architecture constants the kernels are specialised for (overriding them would silently be ignored otherwise)
-_FIXED_VALUES = {"image_size": 512, "num_maskmem": 7, "backbone_stride": 16, "max_obj_ptrs_in_encoder": 16}
+_FIXED_VALUES = {"num_maskmem": 7, "backbone_stride": 16, "max_obj_ptrs_in_encoder": 16}
+_IMAGE_SIZE = {None: 512, "hiera_b+": 1024}  # per architecture variant (the `variant` key of the shipped YAML)
 
 
 def get_best_available_device():
@@ -74,7 +75,8 @@ def _load_model_kwargs(config_file, overrides):
     for flag in _REQUIRED_TRUE:
         if not flat.get(flag, False):
             raise NotImplementedError(f"config flag {flag}=false selects a code path outside this build")
-    for key, want in _FIXED_VALUES.items():
+    fixed = dict(_FIXED_VALUES, image_size=_IMAGE_SIZE[flat.get("variant")])
+    for key, want in fixed.items():
         if key in flat and flat[key] != want:
             raise NotImplementedError(f"{key}={flat[key]!r} is outside this build (the kernels are specialised for "
                                       f"{key}={want!r}, the value in {name})")

@@ -365,6 +365,19 @@ attn_t2i_split_kernel(const float* __restrict__ q, int q_rs, const float* __rest
   const float* hp = part + (long long)bh * S * Nt * (T2I_DH + 2);
   for (int i = tid; i < Nt * T2I_DH; i += T2S_KEYS) {
     const int t = i / T2I_DH, c = i - t * T2I_DH;
+    if (S > 16) {  // 64 x 64 feature maps (32 splits): the same merge, in split order, as two loops
+      float M = -INFINITY;
+      for (int s2 = 0; s2 < S; ++s2) M = fmaxf(M, __ldcg(hp + ((long long)s2 * Nt + t) * (T2I_DH + 2) + T2I_DH));
+      float L = 0.f, acc = 0.f;
+      for (int s2 = 0; s2 < S; ++s2) {
+        const float* pp = hp + ((long long)s2 * Nt + t) * (T2I_DH + 2);
+        const float w = __expf(__ldcg(pp + T2I_DH) - M);
+        L = fmaf(__ldcg(pp + T2I_DH + 1), w, L);
+        acc = fmaf(__ldcg(pp + c), w, acc);
+      }
+      out[((long long)b * Nt + t) * o_rs + h * T2I_DH + c] = acc / L;
+      continue;
+    }
     float m[16], l[16], o[16];
 #pragma unroll
     for (int s2 = 0; s2 < 16; ++s2) {
@@ -525,7 +538,7 @@ extern "C" int usvm_attn_t2i_split_f32(const float* q, int q_rs, const float* k,
       (kv_rs % 4) || (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
     return USVM_ERR_ARG;
   const int S = cdiv(Nk, T2S_KEYS);
-  if (S > 16) return USVM_ERR_ARG;
+  if (S > 64) return USVM_ERR_ARG;
   usvm_launch(attn_t2i_split_kernel, dim3(B * H, S), dim3(T2S_KEYS), 0, STREAM, q, q_rs, k, v, kv_rs, out, o_rs, H, Nt, Nk,
               scale, partials, counters);
   return usvm_check_launch();

@@ -22,7 +22,7 @@ namespace {
 
 constexpr int WA_THREADS = 128;
 constexpr int WA_ROWS = 64;  // max keys (and max queries) per window
-constexpr int WA_D = 96;     // Hiera head dim
+// (head dim D is a template parameter: 96 = Hiera-tiny / small, 64 = Hiera-B+ heads of 56 zero-padded by the packer)
 constexpr int WA_HC = 4;     // heads per pass
 
 __device__ __forceinline__ void wa_cp_async16(void* smem_dst, const void* gsrc) {
@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 }
 
 // one (head, 16-query slab) unit; NKT = key n-tiles of 8 (2 -> 16 keys, 8 -> up to 64 keys)
-template <int NKT>
+template <int NKT, int WA_D>
 __device__ __forceinline__ void attend_unit(const bf16* sQ, const bf16* sK, const bf16* sV, int LD, int hoff, int slab,
                                             int nk, float sl2, float (&o)[WA_D / 8][4], float (&inv)[2]) {
   const int lane = threadIdx.x & 31, t = lane & 3;
@@ -124,6 +124,7 @@ __device__ __forceinline__ void attend_unit(const bf16* sQ, const bf16* sK, cons
 
 
 // the same unit over several 64-key tiles (online softmax, FlashAttention-2 recurrence)
+template <int WA_D>
 __device__ __forceinline__ void attend_unit_tiles(const bf16* sQ, const bf16* sK, const bf16* sV, int LD, int hoff,
                                                   int slab, int nk, float sl2, float (&o)[WA_D / 8][4], float (&inv)[2]) {
   const int lane = threadIdx.x & 31, t = lane & 3;
@@ -205,6 +206,7 @@ __device__ __forceinline__ void attend_unit_tiles(const bf16* sQ, const bf16* sK
   }
 }
 
+template <int WA_D>
 __global__ void __launch_bounds__(WA_THREADS)
 window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias, bf16* __restrict__ out, int F, int Hg,
                    int Wg, int ws, int pool, int C, int H, float scale, int rows_q, int rows_k, int heads_per_cta) {
@@ -283,9 +285,9 @@ window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
     for (int u = warp; u < hc * nslab; u += WA_THREADS / 32) {
       const int hh = u / nslab, slab = u - hh * nslab;
       float o[WA_D / 8][4], inv[2];
-      if (nk_pad == 16) attend_unit<2>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
-      else if (nk_pad == 64) attend_unit<8>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
-      else attend_unit_tiles(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      if (nk_pad == 16) attend_unit<2, WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      else if (nk_pad == 64) attend_unit<8, WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      else attend_unit_tiles<WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int r = slab * 16 + g + half * 8;
@@ -307,13 +309,9 @@ window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
 
 }  // namespace
 
-extern "C" int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, void* out, int F, int Hg, int Wg, int ws,
-                                     int pool, int C, int heads, void* stream) {
-  if (!qkv || !qkv_bias || !out || F <= 0 || Hg <= 0 || Wg <= 0 || ws <= 0 || heads <= 0) return USVM_ERR_ARG;
-  if (C != heads * WA_D || ws * ws > 256 || (pool && ((ws & 1) || (Hg & 1) || (Wg & 1)))) return USVM_ERR_ARG;
-  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 3) ||
-      (reinterpret_cast<uintptr_t>(qkv_bias) & 3))
-    return USVM_ERR_ARG;
+template <int WA_D>
+static int launch_window_attn(const void* qkv, const float* qkv_bias, void* out, int F, int Hg, int Wg, int ws, int pool, int C,
+                              int heads, void* stream) {
   const int nk = ws * ws, nq = pool ? nk / 4 : nk;
   const bool big = nk > WA_ROWS;                 // several key tiles: one CTA per (window, head)
   const int heads_per_cta = big ? 1 : heads;
@@ -323,14 +321,26 @@ extern "C" int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, voi
   if (smem > 200 * 1024) return USVM_ERR_ARG;
   static UsvmPerDeviceOnce configured = {};
   if (usvm_need_setup(configured)) {
-    if (cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(window_attn_kernel<WA_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return USVM_ERR_CUDA;
     usvm_setup_done(configured);
   }
   const int nw = cdiv(Hg, ws) * cdiv(Wg, ws);
-  usvm_launch(window_attn_kernel, dim3(F * nw, cdiv(heads, heads_per_cta)), dim3(WA_THREADS), smem,
+  usvm_launch(window_attn_kernel<WA_D>, dim3(F * nw, cdiv(heads, heads_per_cta)), dim3(WA_THREADS), smem,
               reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(qkv), qkv_bias,
               reinterpret_cast<bf16*>(out), F, Hg, Wg, ws, pool, C, heads, 1.0f / sqrtf((float)WA_D), rows_q, rows_k,
               heads_per_cta);
   return usvm_check_launch();
+}
+
+extern "C" int usvm_window_attn_bf16(const void* qkv, const float* qkv_bias, void* out, int F, int Hg, int Wg, int ws,
+                                     int pool, int C, int heads, void* stream) {
+  if (!qkv || !qkv_bias || !out || F <= 0 || Hg <= 0 || Wg <= 0 || ws <= 0 || heads <= 0) return USVM_ERR_ARG;
+  if ((C != heads * 96 && C != heads * 64) || ws * ws > 256 || (pool && ((ws & 1) || (Hg & 1) || (Wg & 1))))
+    return USVM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 3) ||
+      (reinterpret_cast<uintptr_t>(qkv_bias) & 3))
+    return USVM_ERR_ARG;
+  if (C == heads * 96) return launch_window_attn<96>(qkv, qkv_bias, out, F, Hg, Wg, ws, pool, C, heads, stream);
+  return launch_window_attn<64>(qkv, qkv_bias, out, F, Hg, Wg, ws, pool, C, heads, stream);
 }

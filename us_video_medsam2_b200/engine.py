@@ -33,6 +33,7 @@ class ModelConfig:
     reference's class defaults when the builder does not pass them)."""
     image_size = 512
     embed_dim = 96
+    num_heads = 1
     stages = (1, 2, 7, 2)
     global_att_blocks = (5, 7, 9)
     window_spec = (8, 4, 14, 7)
@@ -59,7 +60,20 @@ class ModelConfig:
     add_tpos_enc_to_obj_ptrs = True
     has_no_obj_embed_spatial = True
     fill_hole_area = 8
-    feat = 32  # 512 / 16
+    feat = 32  # image_size / 16: side of the stride-16 feature map the propagation tail runs on
+
+
+class HieraBPlusConfig(ModelConfig):
+    """sam2.1_hiera_base_plus at 1024^2 (BASELINE configs[4], the 3-D CT driver's model): the `Hiera` class defaults
+    (hieradet.py:174-200) + upstream's embed_dim / num_heads; the propagation tail is the shared one on a 64 x 64 feature
+    map (4096 queries, <= 7 * 4096 + 64 keys, 256^2 low-res masks).  Heads of 56 are zero-padded to 64 and the 112-channel
+    stage to 128 when the weights are packed (PackedWeights._pack_hiera), so every kernel sees multiples of 32."""
+    image_size = 1024
+    embed_dim = 112
+    num_heads = 2
+    stages = (2, 3, 16, 3)
+    global_att_blocks = (12, 16, 20)
+    feat = 64
 
 
 class EtamTiConfig(ModelConfig):
@@ -88,7 +102,7 @@ def hiera_plan(cfg=ModelConfig):
     (hieradet.py:201-256)."""
     ends = [sum(cfg.stages[:i]) - 1 for i in range(1, len(cfg.stages) + 1)]
     pool_blocks = [e + 1 for e in ends[:-1]][: cfg.q_pool]
-    plan, dim, heads, stage = [], cfg.embed_dim, 1, 1
+    plan, dim, heads, stage = [], cfg.embed_dim, cfg.num_heads, 1
     for i in range(sum(cfg.stages)):
         window = 0 if i in cfg.global_att_blocks else cfg.window_spec[stage - 1]
         dim_out = dim
@@ -97,6 +111,18 @@ def hiera_plan(cfg=ModelConfig):
         plan.append((dim, dim_out, heads, window, i in pool_blocks, i in ends))
         dim = dim_out
     return plan
+
+
+def _cpad(c):
+    """Channel counts of the Hiera residual stream as the kernels see them: multiples of 32."""
+    return (c + 31) // 32 * 32
+
+
+def _head_pad(hd):
+    """Head widths the encoder attention kernels are built for: 64 and 96."""
+    if hd > 96:
+        raise NotImplementedError(f"encoder heads of {hd} channels")
+    return hd if hd in (64, 96) else (64 if hd < 64 else 96)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -145,7 +171,9 @@ class PackedWeights:
         else:
             self._pack_hiera(g, dev, w16, f32)
         d = "sam_mask_decoder."
-        self.feat_pos = dev(_sine_pos_2d(32, 32, 256))  # vision_pos_enc of the 32x32 level, [1024, 256]
+        fs = cfg.feat         # side of the stride-16 feature map (32 at 512^2, 64 at 1024^2)
+        T = fs * fs
+        self.feat_pos = dev(_sine_pos_2d(fs, fs, 256))  # vision_pos_enc of the stride-16 level, [T, 256]
 
         # ---- memory attention ----
         self.ma_layers = []
@@ -176,7 +204,7 @@ class PackedWeights:
                          dev(torch.cat([g(ca.format(l) + "k_proj.bias") for l in range(4)])))
         self.ca_v_all = (dev(torch.cat([g(ca.format(l) + "v_proj.weight") for l in range(4)]), BF16),
                          dev(torch.cat([g(ca.format(l) + "v_proj.bias") for l in range(4)])))
-        c, s = _rope_tables(256, 32, 32)
+        c, s = _rope_tables(256, fs, fs)
         # (tiled for the GEMM epilogues: 32 consecutive positions x 4 columns contiguous, see ops.tile_rope_table)
         self.rope_cos, self.rope_sin = ops.tile_rope_table(dev(c)), ops.tile_rope_table(dev(s))
 
@@ -200,7 +228,7 @@ class PackedWeights:
                                    pw2=(w16(p + "pwconv2.weight"), f32(p + "pwconv2.bias")),
                                    gamma=f32(p + "gamma")))
         self.mem_out = (w16(e + "out_proj.weight"), f32(e + "out_proj.bias"))
-        self.mem_pos = dev(_sine_pos_2d(32, 32, 64))  # [1024, 64]
+        self.mem_pos = dev(_sine_pos_2d(fs, fs, 64))  # [T, 64]
         self.maskmem_tpos = dev(g("maskmem_tpos_enc").reshape(cfg.num_maskmem, cfg.mem_dim))
         # (EfficientTAM has no such parameter: a zero vector makes the shared epilogue a no-op)
         self.no_obj_embed_spatial = (dev(g("no_obj_embed_spatial").reshape(cfg.mem_dim)) if cfg.has_no_obj_embed_spatial
@@ -219,10 +247,10 @@ class PackedWeights:
         self.point_table = dev(torch.cat([g(pe_ + f"point_embeddings.{j}.weight") for j in range(4)]
                                          + [g(pe_ + "not_a_point_embed.weight")]))
         self.no_mask_embed = dev(g(pe_ + "no_mask_embed.weight").reshape(1, 256))
-        c01 = (torch.arange(32, dtype=F32) + 0.5) / 32
-        grid = torch.stack([c01[None, :].expand(32, 32), c01[:, None].expand(32, 32)], dim=-1).reshape(1024, 2)
+        c01 = (torch.arange(fs, dtype=F32) + 0.5) / fs
+        grid = torch.stack([c01[None, :].expand(fs, fs), c01[:, None].expand(fs, fs)], dim=-1).reshape(T, 2)
         ang = 2 * math.pi * ((2 * grid - 1) @ g(pe_ + "pe_layer.positional_encoding_gaussian_matrix"))
-        self.dense_pe = dev(torch.cat([ang.sin(), ang.cos()], dim=-1))  # [1024, 256]
+        self.dense_pe = dev(torch.cat([ang.sin(), ang.cos()], dim=-1))  # [T, 256]
         md = pe_ + "mask_downscaling."
         self.pm_convs = [(kkio(md + "0.weight"), f32(md + "0.bias"), f32(md + "1.weight"), f32(md + "1.bias")),
                          (kkio(md + "3.weight"), f32(md + "3.bias"), f32(md + "4.weight"), f32(md + "4.bias"))]
@@ -265,12 +293,12 @@ class PackedWeights:
             t2i, i2t = p + "cross_attn_token_to_image.", p + "cross_attn_image_to_token."
             Lyr["img_w"] = dev(torch.cat([g(t2i + "k_proj.weight"), g(t2i + "v_proj.weight"), g(i2t + "q_proj.weight")]))
             Lyr["img_b"] = dev(torch.cat([g(t2i + "k_proj.bias"), g(t2i + "v_proj.bias"), g(i2t + "q_proj.bias")]))
-            Lyr["img_pe"] = dev(torch.cat([pe_table(t2i + "k_proj.weight"), torch.zeros(1024, 128),
+            Lyr["img_pe"] = dev(torch.cat([pe_table(t2i + "k_proj.weight"), torch.zeros(T, 128),
                                            pe_table(i2t + "q_proj.weight")], dim=1))
         fin = tr + "final_attn_token_to_image."
         self.dec_final["img_w"] = dev(torch.cat([g(fin + "k_proj.weight"), g(fin + "v_proj.weight")]))
         self.dec_final["img_b"] = dev(torch.cat([g(fin + "k_proj.bias"), g(fin + "v_proj.bias")]))
-        self.dec_final["img_pe"] = dev(torch.cat([pe_table(fin + "k_proj.weight"), torch.zeros(1024, 128)], dim=1))
+        self.dec_final["img_pe"] = dev(torch.cat([pe_table(fin + "k_proj.weight"), torch.zeros(T, 128)], dim=1))
         self.out_tokens = dev(torch.cat([g(d + "obj_score_token.weight"), g(d + "iou_token.weight"),
                                          g(d + "mask_tokens.weight")]))  # [6, 256]
         up = d + "output_upscaling."
@@ -309,29 +337,52 @@ class PackedWeights:
 
 
     def _pack_hiera(self, g, dev, w16, f32):
+        """Hiera trunk + FpnNeck.  Channel counts that are not multiples of 32 (B+: 112) are zero-padded to the next one
+        and heads whose width no attention kernel is built for (B+: 56) to 64 -- zero weight rows / columns, so the padded
+        channels of the residual stream stay exactly zero and the padded head columns contribute nothing; LayerNorm runs
+        over the real channels only (ops.layernorm(valid=...)).  The softmax scale of a padded head (kernels use
+        1 / sqrt(padded width)) is corrected by scaling the query rows."""
         cfg = self.cfg
         t = "image_encoder.trunk."
-        pw = g(t + "patch_embed.proj.weight").reshape(96, 147)
-        self.patch_w = dev(F.pad(pw, (0, 13)), BF16)  # K 147 -> 160 (TMA row pitch must be 16 B aligned)
-        self.patch_b = f32(t + "patch_embed.proj.bias")
-        pe = F.interpolate(g(t + "pos_embed"), size=(128, 128), mode="bicubic")
+        E, Ep, S4 = cfg.embed_dim, _cpad(cfg.embed_dim), cfg.image_size // 4
+        pw = g(t + "patch_embed.proj.weight").reshape(E, 147)
+        self.patch_w = dev(F.pad(pw, (0, 13, 0, Ep - E)), BF16)  # K 147 -> 160 (TMA row pitch must be 16 B aligned)
+        self.patch_b = dev(F.pad(g(t + "patch_embed.proj.bias"), (0, Ep - E)))
+        pe = F.interpolate(g(t + "pos_embed"), size=(S4, S4), mode="bicubic")
         win = g(t + "pos_embed_window")
-        pe = pe + win.tile(1, 1, 128 // win.shape[2], 128 // win.shape[3])
-        self.hiera_pos = dev(pe[0].permute(1, 2, 0).reshape(128 * 128, 96))
+        pe = pe + win.tile(1, 1, S4 // win.shape[2], S4 // win.shape[3])
+        self.hiera_pos = dev(F.pad(pe[0].permute(1, 2, 0).reshape(S4 * S4, E), (0, Ep - E)))
         self.blocks = []
         for i, (din, dout, heads, ws, pool, emit) in enumerate(self.plan):
             p = t + f"blocks.{i}."
+            hd = dout // heads
+            hdp = _head_pad(hd)
+            dinp, doutp, da = _cpad(din), _cpad(dout), heads * hdp
+            qw = F.pad(g(p + "attn.qkv.weight").reshape(3, heads, hd, din), (0, dinp - din, 0, hdp - hd))
+            qb = F.pad(g(p + "attn.qkv.bias").reshape(3, heads, hd), (0, hdp - hd))
+            if hdp != hd:
+                qw[0] *= math.sqrt(hdp / hd)
+                qb[0] *= math.sqrt(hdp / hd)
+            pj = F.pad(g(p + "attn.proj.weight").reshape(dout, heads, hd), (0, hdp - hd, 0, 0, 0, doutp - dout))
+            padv = lambda k, n, n_pad: dev(F.pad(g(k), (0, n_pad - n)))
             blk = dict(n1=(f32(p + "norm1.weight"), f32(p + "norm1.bias")),
                        n2=(f32(p + "norm2.weight"), f32(p + "norm2.bias")),
-                       qkv_w=w16(p + "attn.qkv.weight"), qkv_b=f32(p + "attn.qkv.bias"),
-                       proj_w=w16(p + "attn.proj.weight"), proj_b=f32(p + "attn.proj.bias"),
-                       w1=w16(p + "mlp.layers.0.weight"), b1=f32(p + "mlp.layers.0.bias"),
-                       w2=w16(p + "mlp.layers.1.weight"), b2=f32(p + "mlp.layers.1.bias"))
+                       qkv_w=dev(qw.reshape(3 * da, dinp), BF16), qkv_b=dev(qb.reshape(3 * da)),
+                       proj_w=dev(pj.reshape(doutp, da), BF16), proj_b=padv(p + "attn.proj.bias", dout, doutp),
+                       w1=dev(F.pad(g(p + "mlp.layers.0.weight"), (0, doutp - dout)), BF16), b1=f32(p + "mlp.layers.0.bias"),
+                       w2=dev(F.pad(g(p + "mlp.layers.1.weight"), (0, 0, 0, doutp - dout)), BF16),
+                       b2=padv(p + "mlp.layers.1.bias", dout, doutp),
+                       dims=(din, dinp, dout, doutp, da, hdp))
             if din != dout:
-                blk["sc_w"], blk["sc_b"] = w16(p + "proj.weight"), f32(p + "proj.bias")
+                blk["sc_w"] = dev(F.pad(g(p + "proj.weight"), (0, dinp - din, 0, doutp - dout)), BF16)
+                blk["sc_b"] = padv(p + "proj.bias", dout, doutp)
             self.blocks.append(blk)
         n = "image_encoder.neck.convs."
-        self.neck = [(w16(n + f"{j}.conv.weight"), f32(n + f"{j}.conv.bias")) for j in range(4)]
+        self.neck = []
+        for j in range(4):
+            wj = g(n + f"{j}.conv.weight")
+            wj = wj.reshape(wj.shape[0], -1)
+            self.neck.append((dev(F.pad(wj, (0, _cpad(wj.shape[1]) - wj.shape[1])), BF16), f32(n + f"{j}.conv.bias")))
         d = "sam_mask_decoder."
         self.conv_s0 = (w16(d + "conv_s0.weight"), f32(d + "conv_s0.bias"))
         self.conv_s1 = (w16(d + "conv_s1.weight"), f32(d + "conv_s1.bias"))
@@ -409,15 +460,19 @@ class Engine:
         if self.cfg.arch == "vit":
             return self._encode_frames_vit(imgs)
         Fr = imgs.shape[0]
+        S4, fs = self.cfg.image_size // 4, self.cfg.feat
         A = ops.im2col_patch(imgs.contiguous())
-        x, _ = ops.gemm_bf16(A, w.patch_w, bias=w.patch_b, residual=w.hiera_pos, res_mod=128 * 128, f32=True)
-        H = W = 128
+        x, _ = ops.gemm_bf16(A, w.patch_w, bias=w.patch_b, residual=w.hiera_pos, res_mod=S4 * S4, f32=True)
+        H = W = S4
         stage_out = []
-        for blk, (din, dout, heads, ws, pool, emit) in zip(w.blocks, w.plan):
-            _, h = ops.layernorm(x, *blk["n1"], 1e-6, bf16=True)
+        for blk, (_, _, heads, ws, pool, emit) in zip(w.blocks, w.plan):
+            # (din / dout: real channel counts = LayerNorm widths; dinp / doutp: padded stream widths; da, hd: width of the
+            # attention tensors and of one head after head padding -- all equal to the real ones for Hiera-tiny)
+            din, dinp, dout, doutp, da, hd = blk["dims"]
+            _, h = ops.layernorm(x, *blk["n1"], 1e-6, bf16=True, valid=din)
             if din != dout:
                 sc, _ = ops.gemm_bf16(h, blk["sc_w"], bias=blk["sc_b"], f32=True)
-                shortcut = ops.maxpool2(sc, Fr, H, W, dout)
+                shortcut = ops.maxpool2(sc, Fr, H, W, doutp)
             else:
                 shortcut = x
             _, qkv = ops.gemm_bf16(h, blk["qkv_w"], bias=blk["qkv_b"], bf16=True)
@@ -427,37 +482,38 @@ class Engine:
             if self.tc5_encoder_attn and (ws in (7, 14) or (ws == 0 and (H * W) % 128 == 0)) and (not pool or ws == 14):
                 # stage-3 / 4 blocks (global, 14 x 14 and 7 x 7 windows, the q-pool block between them): tcgen05 kernel,
                 # window (un)partition = TMA coordinates
-                att = ops.hiera_attn(qkv, blk["qkv_b"], Fr, H, W, dout, heads, window=ws, pool=pool)
+                att = ops.hiera_attn(qkv, blk["qkv_b"], Fr, H, W, da, heads, window=ws, pool=pool)
             elif 0 < ws * ws <= 64 and self.fused_windows:
                 # stage-1 / 2 windows (64 and 16 keys): a 128-row tcgen05 tile would be >= 50 % masking; fused mma.sync kernel
-                att = ops.window_attn(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout, heads)
+                att = ops.window_attn(qkv, blk["qkv_b"], Fr, H, W, ws, pool, da, heads)
             elif ws > 0:
-                Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, H, W, ws, pool, dout)
-                Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, 96, (0, nq * dout, dout, 96),
-                              (0, nk * dout, dout, 96), (0, nk * dout, dout, 96))
-                att = ops.window_scatter(Ow, Fr, Ho, Wo, ws // 2 if pool else ws, dout)
+                Qw, Kw, Vw, nw, nq, nk = ops.window_gather(qkv, blk["qkv_b"], Fr, H, W, ws, pool, da)
+                Ow = ops.fmha(Qw, Kw, Vw, Fr * nw, heads, nq, nk, hd, (0, nq * da, da, hd),
+                              (0, nk * da, da, hd), (0, nk * da, da, hd))
+                att = ops.window_scatter(Ow, Fr, Ho, Wo, ws // 2 if pool else ws, da)
             else:
                 T = H * W
-                att = ops.fmha(qkv, qkv, qkv, Fr, heads, T, T, 96, (0, T * 3 * dout, 3 * dout, 96),
-                               (dout, T * 3 * dout, 3 * dout, 96), (2 * dout, T * 3 * dout, 3 * dout, 96))
-                att = att.reshape(Fr * T, dout)
+                att = ops.fmha(qkv, qkv, qkv, Fr, heads, T, T, hd, (0, T * 3 * da, 3 * da, hd),
+                               (da, T * 3 * da, 3 * da, hd), (2 * da, T * 3 * da, 3 * da, hd))
+                att = att.reshape(Fr * T, da)
             H, W = Ho, Wo
             x, _ = ops.gemm_bf16(att, blk["proj_w"], bias=blk["proj_b"], residual=shortcut, f32=True)
-            _, h2 = ops.layernorm(x, *blk["n2"], 1e-6, bf16=True)
+            _, h2 = ops.layernorm(x, *blk["n2"], 1e-6, bf16=True, valid=dout)
             _, m = ops.gemm_bf16(h2, blk["w1"], bias=blk["b1"], act=ACT_GELU, bf16=True)
             x, xb = ops.gemm_bf16(m, blk["w2"], bias=blk["b2"], residual=x, f32=True, bf16=emit)
             if emit:
                 stage_out.append(xb)
-        s0, s1, s2, s3 = stage_out  # 128^2x96, 64^2x192, 32^2x384, 16^2x768
+        s0, s1, s2, s3 = stage_out  # tiny: 128^2 x 96, 64^2 x 192, 32^2 x 384, 16^2 x 768
         lat3, _ = ops.gemm_bf16(s3, *self._wb(w.neck[0]), f32=True)
         lat2, _ = ops.gemm_bf16(s2, *self._wb(w.neck[1]), f32=True)
-        lat2_b = ops.upsample2_add_(lat2, lat3, Fr, 32, 32, 256, bf16=True)
+        lat2_b = ops.upsample2_add_(lat2, lat3, Fr, fs, fs, 256, bf16=True)
         _, lat1_b = ops.gemm_bf16(s1, *self._wb(w.neck[2]), bf16=True)
         _, lat0_b = ops.gemm_bf16(s0, *self._wb(w.neck[3]), bf16=True)
         feat_s1, _ = ops.gemm_bf16(lat1_b, *self._wb(w.conv_s1), f32=True)
         feat_s0, _ = ops.gemm_bf16(lat0_b, *self._wb(w.conv_s0), f32=True)
-        return dict(feat=lat2.view(Fr, 1024, 256), feat_bf16=lat2_b.view(Fr, 1024, 256),
-                    feat_s1=feat_s1.view(Fr, 4096, 64), feat_s0=feat_s0.view(Fr, 16384, 32))
+        T = fs * fs
+        return dict(feat=lat2.view(Fr, T, 256), feat_bf16=lat2_b.view(Fr, T, 256),
+                    feat_s1=feat_s1.view(Fr, 4 * T, 64), feat_s0=feat_s0.view(Fr, 16 * T, 32))
 
     @staticmethod
     def _wb(pair):
@@ -517,7 +573,7 @@ class Engine:
         called right before the first cross-attention, after the first self-attention block has been enqueued.
         fold_no_mask: return norm(x) + no_mask_embed, the decoder's `src` on tracked frames (sam_heads(src_ready=True))."""
         w = self.w
-        T = 1024
+        T = self.cfg.feat ** 2
         cs, sn = w.rope_cos, w.rope_sin
         x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T, x_div=group * T)
         k_all = v_all = None
@@ -528,7 +584,7 @@ class Engine:
             _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
             # 1024 keys are 16 key tiles: with one or two objects the mma.sync kernel (64-row query tiles, so twice the
             # CTAs per split) beats the tcgen05 kernel, whose fixed prologue / epilogue dominates such short ranges
-            sa_impl, sa_splits = ("mma", max(1, 8 // B)) if B <= 2 else (None, self._splits(B, T))
+            sa_impl, sa_splits = ("mma", max(1, 8 // B)) if B <= 2 and T <= 1024 else (None, self._splits(B, T))
             o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
                          (512, T * 768, 768, 256), num_splits=sa_splits, impl=sa_impl)
             # out-projection + residual and the next sub-block's LayerNorm in one launch (whole rows per tile)
@@ -564,9 +620,9 @@ class Engine:
         return ops.gemm_bf16(v_in.view(B * Nk, 64), w.ca_v_all[0], bias=w.ca_v_all[1], bf16=True)[1]
 
     def _splits(self, B, Nk):
-        """Split-KV factor: the tcgen05 kernel runs 8 query tiles of 128 per object; fill the 148 SMs."""
+        """Split-KV factor: the tcgen05 kernel runs T / 128 query tiles per object (8 at 512^2); fill the 148 SMs."""
         tiles = (Nk + 63) // 64
-        want = max(1, self.sm_budget // (8 * B))
+        want = max(1, self.sm_budget // (self.cfg.feat ** 2 // 128 * B))
         return max(1, min(want, tiles))
 
     def assemble_memory(self, ctrl, B, n_mem, n_ptr):
@@ -577,7 +633,8 @@ class Engine:
             ptr_pos = ops.ptr_tpos(ctrl, *w.tpos_proj, n_ptr) if w.tpos_proj is not None else w.zero_ptr_pos
         else:
             ptr_pos = None
-        k_in, v_in, Nk = ops.build_memory_store(ctrl, w.mem_pos, w.maskmem_tpos, ptr_pos, B, n_mem, n_ptr)
+        k_in, v_in, Nk = ops.build_memory_store(ctrl, w.mem_pos, w.maskmem_tpos, ptr_pos, B, n_mem, n_ptr,
+                                                T=self.cfg.feat ** 2)
         return k_in, v_in, Nk, 4 * n_ptr
 
     def track_frame(self, f, ctrl, B, n_mem, n_ptr, video_hw, fill_hole_area, group=0):
@@ -632,7 +689,7 @@ class Engine:
             pm = ops.fill_holes(o["low"], fill_hole_area) if fill_hole_area > 0 else o["low"]
             ops.store_outputs(ctrl, o["obj_ptr"], o["score"], pm)
             vh, vw = video_hw
-            video = pm if (vh, vw) == (128, 128) else ops.resize_bilinear(pm, vh, vw)
+            video = pm if (vh, vw) == tuple(pm.shape[-2:]) else ops.resize_bilinear(pm, vh, vw)
         # (non_overlap_masks_for_mem_enc applies on every frame in eval, sam2_base.py:1466-1471: device-side, so the frame
         # stays one capturable graph)
         mask_in = self.mem_mask_input(o["low"], False, non_overlap=self.cfg.non_overlap_masks_for_mem_enc, group=group,
@@ -676,7 +733,8 @@ class Engine:
         feat_s0 / feat_s1: one frame shared by all B objects (feat_shared), one per `group` consecutive objects
         (group > 0), or one per object."""
         w = self.w
-        T = 1024
+        fs = self.cfg.feat
+        T = fs * fs
         feat_group = group if group > 0 else (B if feat_shared else 0)
         if src_ready:  # pix_feat already carries the dense prompt embedding (memory_attention(fold_no_mask=True))
             assert dense is None
@@ -704,7 +762,7 @@ class Engine:
         # output upscaling (image side) || the six token heads (token side); they meet in the mask product
         with torch.cuda.stream(img_s if img_s is not None else tok):
             g1 = ops.gemm_f32(keys, w.up1_w, w.up1_b, tf32=_DEC_TF32)
-            u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, 32, 32, feat_group)
+            u1 = ops.upscale1_ln_gelu(g1, feat_s1, w.up1_ln[0], w.up1_ln[1], B, fs, fs, feat_group)
             g2 = ops.gemm_f32(u1, w.up2_w, w.up2_b, tf32=_DEC_TF32)
         # six stacked heads on token rows 0..5: [object score, IoU, hyper-network 0..3]
         # norm_final_attn runs on load in the first head layer, which also leaves the normalised token rows 0..5 in hs
@@ -716,7 +774,7 @@ class Engine:
         y = sk(h2, W3, b3, M=B, x_rs=6 * 256, x_is=256, instances=6)  # [B, 6*32]
         if img_s is not None:
             self._handoff(tok, img_s, g2, keys)
-        masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 64, 64, feat_group, hyper_bs=192)
+        masks = ops.upscale2_masks(g2, feat_s0, y[:, 64:], B, 2 * fs, 2 * fs, feat_group, hyper_bs=192)
         # single-mask output without the stability fallback (apply_postprocessing=False, mask_decoder.py:160-166): a
         # threshold no stability score can miss keeps mask token 0
         stab_thresh = self.cfg.dynamic_multimask_stability_thresh if self.cfg.dynamic_multimask_via_stability else -1.0
@@ -750,7 +808,7 @@ class Engine:
         layer l overlaps the token self-attention chain of layer l, the image->token block of layer l overlaps the token
         self-attention of layer l + 1.  On return `keys` is still owned by `img_stream` (the caller continues there)."""
         w = self.w
-        T = 1024
+        T = self.cfg.feat ** 2
         queries = tokens
         ln = lambda x, nb: ops.layernorm(x, nb[0], nb[1], 1e-5, f32=True)[0]
         lnp = lambda nb: (nb[0], nb[1], 1e-5)
@@ -828,23 +886,26 @@ class Engine:
         return self.w.point_table[4][None, None].expand(B, 2, 256)
 
     def embed_mask_prompt(self, m128, B):
-        """PromptEncoder.mask_downscaling on a [B,1,128,128] dense prompt -> fp32 [B*1024, 256]."""
+        """PromptEncoder.mask_downscaling on a [B,1,L,L] dense prompt (L = image_size / 4) -> fp32 [B*T, 256]."""
         w = self.w
-        x = m128.reshape(B, 128, 128, 1).contiguous()
+        L = self.cfg.image_size // 4
+        x = m128.reshape(B, L, L, 1).contiguous()
         (w0, b0, lw0, lb0), (w1, b1, lw1, lb1) = w.pm_convs
-        x, H, W = ops.conv2d_small(x, w0, b0, B, 128, 128, 1, 4, 2, 2, 0, ln=(lw0, lb0), gelu=True)
+        x, H, W = ops.conv2d_small(x, w0, b0, B, L, L, 1, 4, 2, 2, 0, ln=(lw0, lb0), gelu=True)
         x, H, W = ops.conv2d_small(x, w1, b1, B, H, W, 4, 16, 2, 2, 0, ln=(lw1, lb1), gelu=True)
         return ops.gemm_f32(x, *w.pm_out)
 
     def mask_as_output(self, feat, feat_s0, feat_s1, mask512, B):
         """SAM2Base._use_mask_as_output (sam2_base.py:1168-1218); mask512 fp32 {0,1} [B,1,512,512]."""
         w = self.w
+        S, T = self.cfg.image_size, self.cfg.feat ** 2
+        L = S // 4
         high = mask512 * 20.0 - 10.0
-        low = ops.resize_bilinear_aa(high, 128, 128)
-        md, _, _ = ops.conv2d_small(mask512.reshape(B, 512, 512, 1).contiguous(), *w.mask_downsample, B, 512, 512, 1,
+        low = ops.resize_bilinear_aa(high, L, L)
+        md, _, _ = ops.conv2d_small(mask512.reshape(B, S, S, 1).contiguous(), *w.mask_downsample, B, S, S, 1,
                                     1, 4, 4, 0)
-        dense = self.embed_mask_prompt(md.view(B, 1, 128, 128), B)
-        pix, _ = ops.axpby(feat, None, rows=B * 1024, x_mod=1024)
+        dense = self.embed_mask_prompt(md.view(B, 1, L, L), B)
+        pix, _ = ops.axpby(feat, None, rows=B * T, x_mod=T)
         o = self.sam_heads(pix, feat_s0, feat_s1, B, self.no_point_tokens(B), dense=dense, multimask=False)
         present = (mask512.flatten(1) > 0).any(dim=1, keepdim=True)
         score = present.to(F32) * 20.0 - 10.0
@@ -858,7 +919,9 @@ class Engine:
         frame store slot named by `ctrl`
         (_encode_new_memory sam2_base.py:1450-1498, MemoryEncoder memory_encoder.py:158-181)."""
         w = self.w
-        H, W, Cin = 512, 512, 1
+        S, fs = self.cfg.image_size, self.cfg.feat
+        T = fs * fs
+        H, W, Cin = S, S, 1
         for si, ((cw, cb, lw, lb), Cout) in enumerate(zip(w.md_convs, (4, 16, 64))):
             if si == 0 and isinstance(mask_in512, tuple):
                 # (low-res logits, post mode): the 512^2 upsampling + sigmoid / binarise is evaluated inside the first
@@ -869,24 +932,24 @@ class Engine:
                                                 gelu=True)
             else:
                 if si == 0:
-                    x = mask_in512.reshape(B, 512, 512, 1)
+                    x = mask_in512.reshape(B, S, S, 1)
                 x, H, W = ops.conv2d_small(x, cw, cb, B, H, W, Cin, Cout, 3, 2, 1, ln=(lw, lb), gelu=True)
             Cin = Cout
-        A4 = ops.im2col_nhwc(x, B, 64, 64, 64, 3, 2, 1)
+        A4 = ops.im2col_nhwc(x, B, 2 * fs, 2 * fs, 64, 3, 2, 1)
         _, c4n = ops.gemm_bf16(A4, w.md_conv3_w, bias=w.md_conv3_b, ln=(w.md_ln3[0], w.md_ln3[1], 1e-6, True))
         pp = pix_proj  # pix_feat_proj, shared by all objects (precomputed by the caller on a forked branch, or here)
         if pp is None:
             pp, _ = ops.gemm_bf16(feat_bf16.view(-1, 256), *w.pix_proj, f32=True)
-        x, _ = ops.gemm_bf16(c4n, w.md_out[0], bias=w.md_out[1], residual=pp, res_mod=1024, f32=True,
-                             res_div=group * 1024)
+        x, _ = ops.gemm_bf16(c4n, w.md_out[0], bias=w.md_out[1], residual=pp, res_mod=T, f32=True,
+                             res_div=group * T)
         xb = None
         for i, Lf in enumerate(w.fuser):
-            h = ops.dwconv7_ln(x, Lf["dw_w"], Lf["dw_b"], Lf["ln"][0], Lf["ln"][1], B, 32, 32)
+            h = ops.dwconv7_ln(x, Lf["dw_w"], Lf["dw_b"], Lf["ln"][0], Lf["ln"][1], B, fs, fs)
             _, t = ops.gemm_bf16(h, Lf["pw1"][0], bias=Lf["pw1"][1], act=ACT_GELU, bf16=True)
             x, xb = ops.gemm_bf16(t, Lf["pw2"][0], bias=Lf["pw2"][1], col_scale=Lf["gamma"], residual=x, f32=True,
                                   bf16=(i == len(w.fuser) - 1))
         out, _ = ops.gemm_bf16(xb, w.mem_out[0], bias=w.mem_out[1], f32=True)
-        return ops.finalize_memory(out, score, w.no_obj_embed_spatial, B, ctrl=ctrl)
+        return ops.finalize_memory(out, score, w.no_obj_embed_spatial, B, T=T, ctrl=ctrl)
 
     def mem_mask_input(self, masks, binarize, non_overlap=False, group=0, lazy=False):
         """Upsample low-res logits [B,1,h,w] to 512^2 (if needed) fused with sigmoid*20-10 or (x>0)*20-10.
@@ -895,14 +958,15 @@ class Engine:
         lazy: return (low-res logits, post mode) for encode_memory to upsample inside its first convolution, when nothing
         needs the materialised 512^2 mask (no non-overlap constraint)."""
         cfg = self.cfg
+        S = cfg.image_size
         post = ops.POST_BINARIZE_AFFINE if binarize else ops.POST_SIGMOID_AFFINE
         if lazy and self.lazy_mask_upsample and not (non_overlap and masks.shape[0] > 1) \
-                and tuple(masks.shape[-2:]) != (512, 512) and masks.dtype == F32 and masks.is_contiguous():
+                and tuple(masks.shape[-2:]) != (S, S) and masks.dtype == F32 and masks.is_contiguous():
             return (masks, post)
         if non_overlap and masks.shape[0] > 1:
-            hi = masks if tuple(masks.shape[-2:]) == (512, 512) else ops.resize_bilinear(masks, 512, 512)
+            hi = masks if tuple(masks.shape[-2:]) == (S, S) else ops.resize_bilinear(masks, S, S)
             return ops.non_overlap(hi, group, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)
-        return ops.resize_bilinear(masks, 512, 512, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)
+        return ops.resize_bilinear(masks, S, S, post, cfg.sigmoid_scale_for_mem_enc, cfg.sigmoid_bias_for_mem_enc)
 
     def memory_attention_from_tensors(self, feat, mem_frames, tpos_rows, ptrs, ptr_pos, B):
         """Convenience for tests / one-off calls: assemble the bank from explicit tensors (usvm_build_memory)."""

@@ -47,7 +47,8 @@ class SAM2ImagePredictor:
         assert x.shape[-3] == 3 and x.dim() == 4, f"input_image must be of size 1x3xHxW, got {x.shape}"
         eng = self.model._sync_engine()
         f = eng.encode_frames(x)
-        pix, _ = ops.axpby(f["feat"][0], eng.w.no_mem_embed, rows=1024, x_mod=1024, y_mod=1)  # + no_mem_embed
+        T = eng.cfg.feat ** 2
+        pix, _ = ops.axpby(f["feat"][0], eng.w.no_mem_embed, rows=T, x_mod=T, y_mod=1)  # + no_mem_embed
         self._features = dict(pix=pix, feat_s0=f["feat_s0"][0], feat_s1=f["feat_s1"][0])
         self._is_image_set = True
 
@@ -65,8 +66,9 @@ class SAM2ImagePredictor:
         eng = self.model._sync_engine()
         f = eng.encode_frames(x)
         n = x.shape[0]
-        pix, _ = ops.axpby(f["feat"].view(n * 1024, 256), eng.w.no_mem_embed, rows=n * 1024, y_mod=1)  # + no_mem_embed
-        self._features = [dict(pix=pix[i * 1024:(i + 1) * 1024], feat_s0=f["feat_s0"][i], feat_s1=f["feat_s1"][i])
+        T = eng.cfg.feat ** 2
+        pix, _ = ops.axpby(f["feat"].view(n * T, 256), eng.w.no_mem_embed, rows=n * T, y_mod=1)  # + no_mem_embed
+        self._features = [dict(pix=pix[i * T:(i + 1) * T], feat_s0=f["feat_s0"][i], feat_s1=f["feat_s1"][i])
                           for i in range(n)]
         self._is_image_set = True
         self._is_batch = True
@@ -94,9 +96,10 @@ class SAM2ImagePredictor:
     def get_image_embedding(self):
         if not self._is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) to generate an embedding.")
+        fs = self.model.cfg.feat
         if self._is_batch:
-            return torch.stack([f["pix"].t().reshape(256, 32, 32) for f in self._features])
-        return self._features["pix"].t().reshape(1, 256, 32, 32)
+            return torch.stack([f["pix"].t().reshape(256, fs, fs) for f in self._features])
+        return self._features["pix"].t().reshape(1, 256, fs, fs)
 
     def predict(self, point_coords=None, point_labels=None, box=None, mask_input=None, multimask_output=True,
                 return_logits=False, normalize_coords=True):
@@ -149,8 +152,9 @@ class SAM2ImagePredictor:
         dense = None
         if mask_input is not None:
             m = mask_input.float()
-            if tuple(m.shape[-2:]) != (128, 128):
-                m = ops.resize_bilinear_aa(m.contiguous(), 128, 128)
+            L = self.model.image_size // 4
+            if tuple(m.shape[-2:]) != (L, L):
+                m = ops.resize_bilinear_aa(m.contiguous(), L, L)
             dense = eng.embed_mask_prompt(m.contiguous(), B)
         f = self._features[img_idx] if self._is_batch else self._features
         pix = f["pix"] if B == 1 else f["pix"].repeat(B, 1)

@@ -220,13 +220,17 @@ def attn_small(q, k, v, B, H, Nq, Nk, head_dim):
 # ------------------------------------------------------------------------------------------------
 # normalisation / layout
 # ------------------------------------------------------------------------------------------------
-def layernorm(x, w, b, eps, f32=False, bf16=False, gelu=False):
+def layernorm(x, w, b, eps, f32=False, bf16=False, gelu=False, valid=None):
+    """valid < x.shape[1]: the rows carry `valid` real channels followed by zero padding (a channel count that is not a
+    multiple of 32, see engine._cpad); the norm runs over the real ones and the padding of the outputs is zero."""
     _chk(x, F32, "x")
     rows, Cc = x.shape
-    o32 = empty((rows, Cc), F32, x) if f32 else None
-    o16 = empty((rows, Cc), BF16, x) if bf16 else None
+    Cv = Cc if valid is None else valid
+    alloc = empty if Cv == Cc else (lambda shape, dt, like: torch.zeros(shape, dtype=dt, device=like.device))
+    o32 = alloc((rows, Cc), F32, x) if f32 else None
+    o16 = alloc((rows, Cc), BF16, x) if bf16 else None
     call("usvm_layernorm", x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), eps, int(gelu), _ptr(o32), Cc,
-         _ptr(o16), Cc, rows, Cc, _stream())
+         _ptr(o16), Cc, rows, Cv, _stream())
     return o32, o16
 
 
@@ -366,12 +370,12 @@ class FrameStore:
     """Per-session device store of everything a tracked frame leaves behind, indexed by frame number:
     spatial memory (bf16 token-major), object pointer, object score, hole-filled low-res mask logits."""
 
-    def __init__(self, num_frames, B, device, T=1024, Cm=64, ptr_dim=256, hw=128 * 128):
+    def __init__(self, num_frames, B, device, T=1024, Cm=64, ptr_dim=256, low=128):
         self.num_frames, self.B = num_frames, B
         self.mem = torch.zeros((num_frames, B, T, Cm), dtype=BF16, device=device)
         self.ptr = torch.zeros((num_frames, B, ptr_dim), dtype=F32, device=device)
         self.score = torch.zeros((num_frames, B, 1), dtype=F32, device=device)
-        self.masks = torch.zeros((num_frames, B, 1, 128, 128), dtype=F32, device=device)
+        self.masks = torch.zeros((num_frames, B, 1, low, low), dtype=F32, device=device)
         self.shared, self.column0 = None, 0  # set on the column views of a store shared by lock-step sessions
 
     def columns(self, lo, n):
@@ -618,7 +622,7 @@ def attn_t2i(q, k, v, B, Nt, Nk, H=8):
     out = empty((B * Nt, H * 16), F32, q)
     assert k.stride(0) == v.stride(0)
     splits = (Nk + 127) // 128
-    if 1 < splits <= 16:  # key-split kernel: B*H*splits CTAs, the last one per head merges the partials
+    if 1 < splits <= 64:  # key-split kernel: B*H*splits CTAs, the last one per head merges the partials
         key = (q.device, B * H)
         if key not in _T2I_COUNTERS:
             _T2I_COUNTERS[key] = torch.zeros(B * H, dtype=torch.int32, device=q.device)

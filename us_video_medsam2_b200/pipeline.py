@@ -22,8 +22,14 @@ import torch.distributed as dist
 BF16, F32 = torch.bfloat16, torch.float32
 
 # what the encoder leaves behind per frame (Engine.encode_frames): name -> (shape, dtype)
-FEATURE_SPECS = (("feat", (1024, 256), F32), ("feat_bf16", (1024, 256), BF16),
-                 ("feat_s1", (4096, 64), F32), ("feat_s0", (16384, 32), F32))
+def feature_specs(feat=32):
+    """`feat`: side of the stride-16 feature map (32 at 512^2, 64 for Hiera-B+ at 1024^2)."""
+    T = feat * feat
+    return (("feat", (T, 256), F32), ("feat_bf16", (T, 256), BF16), ("feat_s1", (4 * T, 64), F32),
+            ("feat_s0", (16 * T, 32), F32))
+
+
+FEATURE_SPECS = feature_specs(32)
 # what travels between GPUs: 4 MiB per frame.  The bf16 copy of `feat` is re-derived on the receiving side (one cast
 # kernel); the three levels stay fp32 on the wire -- the decoder reads feat_s0 / feat_s1 as fp32 operands and the Dice bar
 # leaves no room for another rounding, while 4 MiB x ~1400 frames/s is < 1 % of one NVLink 5 direction.
@@ -57,8 +63,8 @@ class BatchPlan:
         return [self.first, self.last, self.step, self.n]
 
 
-def alloc_feature_slot(n, device):
-    return {name: torch.empty((n,) + shape, dtype=dt, device=device) for name, shape, dt in FEATURE_SPECS}
+def alloc_feature_slot(n, device, feat=32):
+    return {name: torch.empty((n,) + shape, dtype=dt, device=device) for name, shape, dt in feature_specs(feat)}
 
 
 class FeaturePipeline:
@@ -222,9 +228,9 @@ class RemoteProducer:
     in the order they were issued, and every rank walks the plan in increasing k."""
     must_drain = True
 
-    def __init__(self, remote, n, device):
+    def __init__(self, remote, n, device, feat=32):
         self.remote, self.n = remote, n
-        self.slots = [alloc_feature_slot(n, device) for _ in range(len(remote.ranks) + 1)]
+        self.slots = [alloc_feature_slot(n, device, feat) for _ in range(len(remote.ranks) + 1)]
         self.pending = {}
 
     def launch(self, k, frames, slot):

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import _lib, ops, synth
-from .engine import NO_OBJ_SCORE, Engine, EtamTiConfig, ModelConfig, PackedWeights
+from .engine import NO_OBJ_SCORE, Engine, EtamTiConfig, HieraBPlusConfig, ModelConfig, PackedWeights
 
 try:  # progress bar like the reference (sam2_video_predictor.py:703); optional
     from tqdm import tqdm as _tqdm
@@ -55,11 +55,15 @@ class SAM2VideoPredictor(nn.Module):
 
     _config_base = ModelConfig           # architecture constants of the shipped configuration
     _abi = staticmethod(synth.state_dict_abi)   # [(parameter name, shape)] of the reference's state dict
+    # other architectures the same class serves (the `variant` key of their YAML): Hiera-B+ at 1024^2
+    _variants = {"hiera_b+": (HieraBPlusConfig, synth.bplus_state_dict_abi)}
 
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False,
-                 encoder_batch=1, use_cuda_graphs=True, encoder_sms=0, **model_kwargs):
+                 encoder_batch=1, use_cuda_graphs=True, encoder_sms=0, variant=None, **model_kwargs):
         super().__init__()
+        if variant is not None:
+            self._config_base, self._abi = self._variants[variant]
         cfg = type("Cfg", (self._config_base,), {})
         for k, v in model_kwargs.items():
             if k in ("image_encoder", "memory_attention", "memory_encoder", "sam_mask_decoder_extra_args",
@@ -222,7 +226,7 @@ class SAM2VideoPredictor(nn.Module):
             store.grow(B)
             self._refresh_views(st)
         elif store is None or store.B != B or store.num_frames != st["num_frames"]:
-            store = ops.FrameStore(st["num_frames"], B, self.device)
+            store = ops.FrameStore(st["num_frames"], B, self.device, T=self.cfg.feat ** 2, low=self.image_size // 4)
             st["_store"] = store
         return store
 
@@ -420,7 +424,7 @@ class SAM2VideoPredictor(nn.Module):
         if self._remote is not None:
             plan = BatchPlan(first, last, step, n, include_tail=True)
             self._remote.announce(plan)
-            return FeaturePipeline(plan, RemoteProducer(self._remote, n, self.device), depth=len(self._remote.ranks))
+            return FeaturePipeline(plan, RemoteProducer(self._remote, n, self.device, self.cfg.feat), depth=len(self._remote.ranks))
         if n < 2 or len(tracked) <= n:
             return None  # a single batch: nothing to overlap with
         if self._pipeline_owner is not None and self._pipeline_owner is not st:
@@ -572,15 +576,16 @@ class SAM2VideoPredictor(nn.Module):
         return ops.non_overlap(pred_masks)
 
     def _mem_view(self, mem_tok):
-        """token-major bf16 [B,1024,64] -> the reference's [B,64,32,32] layout (a view)."""
-        B = mem_tok.shape[0]
-        return mem_tok.view(B, 32, 32, self.mem_dim).permute(0, 3, 1, 2)
+        """token-major bf16 [B,T,64] -> the reference's [B,64,feat,feat] layout (a view)."""
+        B, fs = mem_tok.shape[0], self.cfg.feat
+        return mem_tok.view(B, fs, fs, self.mem_dim).permute(0, 3, 1, 2)
 
     def _maskmem_pos_enc(self, st, B):
         """Cached constant, expanded per object (reference :1016-1039)."""
         c = st["constants"]
         if "maskmem_pos_enc" not in c:
-            pos = self.engine().w.mem_pos.view(1, 32, 32, self.mem_dim).permute(0, 3, 1, 2)
+            fs = self.cfg.feat
+            pos = self.engine().w.mem_pos.view(1, fs, fs, self.mem_dim).permute(0, 3, 1, 2)
             c["maskmem_pos_enc"] = [pos]
         return [x.expand(B, -1, -1, -1) for x in c["maskmem_pos_enc"]]
 
@@ -827,7 +832,7 @@ class SAM2VideoPredictor(nn.Module):
         if base is not None and base.B == S * Bo and all(getattr(o, "shared", None) is base and o.column0 == i * Bo
                                                          for i, o in enumerate(owners)):
             return base  # already merged by an earlier pass over the same sessions
-        shared = ops.FrameStore(T, S * Bo, self.device)
+        shared = ops.FrameStore(T, S * Bo, self.device, T=self.cfg.feat ** 2, low=self.image_size // 4)
         for i, st in enumerate(states):
             old = st["_store"]
             od = st["output_dict"]
@@ -1016,7 +1021,8 @@ class SAM2VideoPredictor(nn.Module):
             o = eng.mask_as_output(f["feat"], f["feat_s0"], f["feat_s1"], mask_inputs, B)
         else:
             if is_init_cond_frame:
-                pix, _ = ops.axpby(f["feat"], eng.w.no_mem_embed, rows=B * 1024, x_mod=1024, y_mod=1)
+                T = cfg.feat ** 2
+                pix, _ = ops.axpby(f["feat"], eng.w.no_mem_embed, rows=B * T, x_mod=T, y_mod=1)
             else:
                 # correction clicks on an already tracked frame: condition on this object's memories in the store
                 mem_slots, tpos_rows, ptr_slots, ptr_rel = self._memory_inputs(st, frame_idx, output_dict, reverse)
@@ -1035,8 +1041,9 @@ class SAM2VideoPredictor(nn.Module):
             if prev_sam_mask_logits is not None:
                 assert point_inputs is not None
                 m = prev_sam_mask_logits
-                if tuple(m.shape[-2:]) != (128, 128):
-                    m = ops.resize_bilinear_aa(m.float(), 128, 128)
+                L = self.image_size // 4
+                if tuple(m.shape[-2:]) != (L, L):
+                    m = ops.resize_bilinear_aa(m.float(), L, L)
                 dense = eng.embed_mask_prompt(m.contiguous(), B)
             o = eng.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, sparse, dense=dense, multimask=multimask)
         low = o["low"]

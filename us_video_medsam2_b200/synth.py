@@ -81,6 +81,22 @@ def make_etam_state_dict(seed=0, variant="ti"):
     return {name: _draw(name, shape, g) for name, shape in etam_state_dict_abi(variant)}
 
 
+def bplus_state_dict_abi():
+    """[(name, shape)] of sam2.1_hiera_base_plus at 1024^2 (BASELINE configs[4]; 615 tensors, 80.85 M parameters): the
+    reference ships no such YAML, so the shapes were dumped from its own classes instantiated with the `Hiera` class
+    defaults (hieradet.py:174-200: stages (2, 3, 16, 3), global blocks (12, 16, 20), 14 x 14 background position table)
+    and upstream's embed_dim 112 / 2 heads (oracle/ref_loader.py: bplus_overrides)."""
+    with open(os.path.join(os.path.dirname(__file__), "hiera_bplus_state_dict_abi.json")) as f:
+        return [(k, tuple(s)) for k, s in json.load(f)]
+
+
+def make_bplus_state_dict(seed=0):
+    """Seeded Hiera-B+ weights (same drawing rules as make_state_dict)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(5000011 * (seed + 1))
+    return {name: _draw(name, shape, g) for name, shape in bplus_state_dict_abi()}
+
+
 def make_state_dict(seed=0):
     """Full sam2.1_hiera_t512 state dict, fp32 CPU, deterministic in `seed`."""
     g = torch.Generator(device="cpu")
