@@ -57,9 +57,11 @@ def parse():
                     help="N > 1: 'videos' = one independent clip per GPU (weak scaling, no communication); 'clip' = ONE "
                          "clip, rank 0 propagates, the other ranks run the frame-parallel encoder and send features over "
                          "NCCL point-to-point (strong scaling, bounded by the sequential propagation)")
-    ap.add_argument("--model", default="hiera_t512", choices=["hiera_t512", "etam_ti", "etam_s"],
+    ap.add_argument("--model", default="hiera_t512", choices=["hiera_t512", "etam_ti", "etam_s", "hiera_b+"],
                     help="hiera_t512 = MedSAM2 sam2.1_hiera_t512 (BASELINE configs[1], the default); etam_ti / etam_s = "
-                         "EfficientTAM tiny / small at 512x512 (BASELINE configs[3]) on the same clips")
+                         "EfficientTAM tiny / small at 512x512 (BASELINE configs[3]) on the same clips; hiera_b+ = "
+                         "sam2.1_hiera_base_plus at 1024x1024 on a 3-D CT volume, bidirectional (BASELINE configs[4]; "
+                         "tools/bench_bplus.py, one GPU, --frames = slices, default 256)")
     ap.add_argument("--cpu-sample-frames", type=int, default=64,
                     help="frames of the clip the CPU arm tracks per step (the 7-frame bank is full from frame 7 on)")
     ap.add_argument("--batched-videos", type=int, default=8,
@@ -789,6 +791,13 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    if args.model == "hiera_b+":
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_bplus
+
+            print(json.dumps(bench_bplus.run(256 if args.frames == 512 else args.frames, args.steps, max(1, args.warmup // 3))))
+        return
     run_b200(args, rank, world)
 
 

@@ -85,6 +85,7 @@ def layer_norm_2d(x, w, b, eps=1e-6):
 class Cfg:
     image_size = 512
     embed_dim = 96
+    num_heads = 1
     stages = (1, 2, 7, 2)
     global_att_blocks = (5, 7, 9)
     window_spec = (8, 4, 14, 7)
@@ -108,6 +109,17 @@ class Cfg:
     non_overlap_masks_for_mem_enc = False
 
 
+class CfgBPlus(Cfg):
+    """sam2.1_hiera_base_plus at 1024^2 (BASELINE configs[4]): the `Hiera` class defaults (hieradet.py:174-200) with
+    upstream's embed_dim 112 / 2 heads; feature map 64 x 64 (RoPEAttention feat_sizes), 256^2 low-res masks.  Pinned
+    against tests/golden/bplus1024_ct_bidirectional.npz (outputs of the reference's own classes)."""
+    image_size = 1024
+    embed_dim = 112
+    num_heads = 2
+    stages = (2, 3, 16, 3)
+    global_att_blocks = (12, 16, 20)
+
+
 class CfgNoPost(Cfg):
     """build_sam2_video_predictor(..., apply_postprocessing=False): none of the builder's overrides
     (build_sam.py:108-122), i.e. the class defaults of SAM2Base / MaskDecoder / SAM2VideoPredictor."""
@@ -121,7 +133,7 @@ def hiera_block_plan(cfg=Cfg):
     Hiera.__init__ (hieradet.py:201-256)."""
     stage_ends = [sum(cfg.stages[:i]) - 1 for i in range(1, len(cfg.stages) + 1)]
     pool_blocks = [e + 1 for e in stage_ends[:-1]][: cfg.q_pool]
-    plan, dim, heads, stage = [], cfg.embed_dim, 1, 1
+    plan, dim, heads, stage = [], cfg.embed_dim, getattr(cfg, "num_heads", 1), 1
     for i in range(sum(cfg.stages)):
         window = cfg.window_spec[stage - 1]
         if i in cfg.global_att_blocks:
@@ -203,7 +215,8 @@ class RefModel:
         self.sd = {k: v.detach().to(torch.float32).cpu() for k, v in state_dict.items()}
         self.cfg = cfg
         self.plan = hiera_block_plan(cfg)
-        self.rope_cos, self.rope_sin = axial_rope_table(cfg.d_model, 32, 32)
+        self.fs = cfg.image_size // 16  # side of the stride-16 feature map
+        self.rope_cos, self.rope_sin = axial_rope_table(cfg.d_model, self.fs, self.fs)
         self._sine_cache = {}
 
     def p(self, name):
@@ -360,8 +373,9 @@ class RefModel:
     def dense_pe(self):
         """PromptEncoder.get_dense_pe (prompt_encoder.py:68-77, position_encoding.py:136-148)."""
         g = self.p("sam_prompt_encoder.pe_layer.positional_encoding_gaussian_matrix")
-        c = (torch.arange(32, dtype=torch.float32) + 0.5) / 32
-        grid = torch.stack([c[None, :].expand(32, 32), c[:, None].expand(32, 32)], dim=-1)
+        fs = self.fs
+        c = (torch.arange(fs, dtype=torch.float32) + 0.5) / fs
+        grid = torch.stack([c[None, :].expand(fs, fs), c[:, None].expand(fs, fs)], dim=-1)
         return random_fourier_pe(grid, g).permute(2, 0, 1)[None]
 
     def embed_points(self, coords, labels):
@@ -479,17 +493,19 @@ class RefModel:
             coords, labels = torch.zeros(B, 1, 2), -torch.ones(B, 1, dtype=torch.int32)
         sparse = self.embed_points(coords.float(), labels)
         if mask_inputs is not None:
-            if tuple(mask_inputs.shape[-2:]) != (128, 128):
-                mask_inputs = F.interpolate(mask_inputs.float(), size=(128, 128), mode="bilinear",
+            low_hw = (self.cfg.image_size // 4, self.cfg.image_size // 4)
+            if tuple(mask_inputs.shape[-2:]) != low_hw:
+                mask_inputs = F.interpolate(mask_inputs.float(), size=low_hw, mode="bilinear",
                                             align_corners=False, antialias=True)
             dense = self.embed_mask(mask_inputs)
         else:
-            dense = self.p("sam_prompt_encoder.no_mask_embed.weight").reshape(1, -1, 1, 1).expand(B, -1, 32, 32)
+            dense = self.p("sam_prompt_encoder.no_mask_embed.weight").reshape(1, -1, 1, 1).expand(B, -1, self.fs, self.fs)
         low_multi, ious, tokens, score = self.mask_decoder(pix_feat, sparse, dense, feat_s0, feat_s1,
                                                            multimask_output)
         appearing = score > 0
         low_multi = torch.where(appearing[:, None, None], low_multi, torch.full_like(low_multi, NO_OBJ_SCORE))
-        high_multi = F.interpolate(low_multi, size=(512, 512), mode="bilinear", align_corners=False)
+        high_multi = F.interpolate(low_multi, size=(self.cfg.image_size, self.cfg.image_size), mode="bilinear",
+                                   align_corners=False)
         token = tokens[:, 0]
         if multimask_output:
             best = torch.argmax(ious, dim=-1)
@@ -634,7 +650,7 @@ class RefModel:
         if run_mem_encoder:
             mf = self.encode_memory(feat, o["high"], o["score"], is_mask_from_pts=point_inputs is not None)
             out["maskmem_features"] = mf
-            out["maskmem_pos_enc"] = [self.sine_pos(32, 32, 64)[None].expand(B, -1, -1, -1)]
+            out["maskmem_pos_enc"] = [self.sine_pos(self.fs, self.fs, 64)[None].expand(B, -1, -1, -1)]
         return out
 
 
@@ -848,7 +864,7 @@ class RefPredictor:
             mf = self.model.encode_memory(feats["feat"].expand(B, -1, -1, -1), high,
                                           cons["object_score_logits"], True)
             cons["maskmem_features"] = mf.to(torch.bfloat16)
-            cons["maskmem_pos_enc"] = [self.model.sine_pos(32, 32, 64)[None].expand(B, -1, -1, -1)]
+            cons["maskmem_pos_enc"] = [self.model.sine_pos(self.model.fs, self.model.fs, 64)[None].expand(B, -1, -1, -1)]
         return cons
 
     def _per_object(self, st, t, out, key):
@@ -1077,9 +1093,9 @@ class RefImagePredictor:
         f = self._feats
         sparse = m.embed_points(coords, labels) if coords is not None else torch.zeros(1, 0, 256)
         if mask_input is not None:
-            dense = m.embed_mask(torch.as_tensor(mask_input, dtype=torch.float32).reshape(1, 1, 128, 128))
+            dense = m.embed_mask(torch.as_tensor(mask_input, dtype=torch.float32).reshape(1, 1, int(s) // 4, int(s) // 4))
         else:
-            dense = m.p("sam_prompt_encoder.no_mask_embed.weight").reshape(1, -1, 1, 1).expand(1, -1, 32, 32)
+            dense = m.p("sam_prompt_encoder.no_mask_embed.weight").reshape(1, -1, 1, 1).expand(1, -1, m.fs, m.fs)
         low, iou, _, _ = m.mask_decoder(f["feat"], sparse, dense, f["feat_s0"], f["feat_s1"], multimask_output)
         masks = self._post(low.float())
         low = low.clamp(-32.0, 32.0)

@@ -13,7 +13,9 @@ def _g(seed=0):
     return torch.Generator(device="cuda").manual_seed(seed)
 
 
-@pytest.mark.parametrize("rows,C,eps", [(1000, 96, 1e-6), (4096, 768, 1e-6), (2048, 256, 1e-5), (7, 64, 1e-6)])
+@pytest.mark.parametrize("rows,C,eps", [(1000, 96, 1e-6), (4096, 768, 1e-6), (2048, 256, 1e-5), (7, 64, 1e-6),
+                                        (777, 224, 1e-6), (1030, 448, 1e-6), (515, 896, 1e-6), (333, 100, 1e-6),
+                                        (64, 1000, 1e-6)])
 def test_layernorm(rows, C, eps):
     from us_video_medsam2_b200 import ops
 
@@ -26,6 +28,21 @@ def test_layernorm(rows, C, eps):
     assert (o16.float() - want).abs().max().item() < 4e-2
     o32g, _ = ops.layernorm(x, w, b, eps, f32=True, gelu=True)
     assert (o32g - F.gelu(want)).abs().max().item() < 2e-5
+
+
+def test_layernorm_over_the_real_channels_of_a_padded_row():
+    """Hiera-B+ stage 1: 112 channels in rows of 128 (engine._cpad); the norm sees 112, the padding of the output is zero."""
+    from us_video_medsam2_b200 import ops
+
+    g = _g(5)
+    x = torch.zeros((999, 128), device="cuda")
+    x[:, :112] = torch.randn((999, 112), generator=g, device="cuda") * 2 - 0.5
+    w, b = torch.randn(112, generator=g, device="cuda"), torch.randn(112, generator=g, device="cuda")
+    o32, o16 = ops.layernorm(x, w, b, 1e-6, f32=True, bf16=True, valid=112)
+    want = F.layer_norm(x[:, :112], (112,), w, b, 1e-6)
+    assert o32.shape == (999, 128) and (o32[:, :112] - want).abs().max().item() < 2e-5
+    assert (o16[:, :112].float() - want).abs().max().item() < 4e-2
+    assert not o32[:, 112:].any() and not o16[:, 112:].any()
 
 
 def test_axpby_and_cast():

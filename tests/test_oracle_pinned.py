@@ -172,3 +172,32 @@ def test_etam_small_oracle_matches_reference_fixture(golden_dir):
     low = np.stack([get(t)["pred_masks"][:, 0].float().numpy() for t in frames])
     assert np.abs(low - g["low_res_filled"]).max() <= FP32_TOL
     assert np.allclose(np.stack([get(t)["object_score_logits"].numpy() for t in frames]), g["score_filled"], atol=FP32_TOL)
+
+
+def test_bplus_oracle_matches_reference_fixture(golden_dir):
+    """Hiera-B+ at 1024^2 (BASELINE configs[4]): the oracle restatement with CfgBPlus against the outputs of
+    the reference's own classes (tests/golden/bplus1024_ct_bidirectional.npz from oracle/make_golden_bplus.py): the three
+    encoder feature levels of the key slice and the forward pass of the CT driver's sequence, fp32 vs fp32."""
+    from oracle.make_golden_bplus import BOX, H, KEY, SEED, T, W
+    from oracle.medsam2_ref import CfgBPlus, RefModel
+
+    g = np.load(os.path.join(golden_dir, "bplus1024_ct_bidirectional.npz"))
+    sd = synth.make_bplus_state_dict(SEED)
+    clip = synth.make_clip(T, size=1024, kind="speckle")
+    with torch.inference_mode():
+        f = RefModel(sd, cfg=CfgBPlus).forward_image(clip[KEY:KEY + 1])
+        assert np.allclose(f["feat_s0"][0, :, ::8, ::8].numpy(), g["enc_feat_s0"], atol=5e-5)
+        assert np.allclose(f["feat_s1"][0, :, ::4, ::4].numpy(), g["enc_feat_s1"], atol=5e-5)
+        assert np.allclose(f["feat"][0, :, ::2, ::2].numpy(), g["enc_feat"], atol=1e-4)
+        pred = RefPredictor(sd, cfg=CfgBPlus, fill_holes=True)
+        st = pred.init_state(clip[: KEY + 2], H, W)   # key slice + one tracked slice keeps the CPU suite short
+        _, _, lg = pred.add_new_points_or_box(st, KEY, 1, box=BOX)
+        assert dice(lg[0, 0, ::2, ::2], torch.from_numpy(g["prompt_fwd_s2"])) > 0.9995
+        frames = []
+        for t, ids, lg in pred.propagate_in_video(st):
+            i = len(frames)
+            frames.append(t)
+            want = torch.from_numpy(g["logits_fwd_s2"][i])
+            got = lg[0, 0, ::2, ::2]
+            assert dice(got, want) > 0.9995 and float((got - want).abs().mean()) < FP32_TOL, (t, dice(got, want))
+    assert frames == g["frames_fwd"].tolist()[:2]

@@ -81,6 +81,52 @@ layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restri
   }
 }
 
+// the same for a channel count that is not a multiple of 32 (Hiera-B+ stage 1: 112 of 128): lanes past C hold nothing
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_regp_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
+                      float eps, int gelu, float* out_f32, int ldo_f32, bf16* out_bf16, int ldo_bf16, int rows, int C) {
+  const int lane = threadIdx.x & 31;
+  float gw[NV], gb[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const bool ok = j * 32 + lane < C;
+    gw[j] = ok ? __ldg(w + j * 32 + lane) : 0.f;
+    gb[j] = ok ? __ldg(b + j * 32 + lane) : 0.f;
+  }
+  PDL_ENTRY();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j] = j * 32 + lane < C ? xr[j * 32 + lane] : 0.f;
+    s += v[j];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (j * 32 + lane < C) {
+      v[j] -= mean;
+      q = fmaf(v[j], v[j], q);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = j * 32 + lane;
+    if (c < C) {
+      float y = v[j] * rstd * gw[j] + gb[j];
+      if (gelu) y = gelu_erf(y);
+      if (out_f32) out_f32[row * ldo_f32 + c] = y;
+      if (out_bf16) out_bf16[row * ldo_bf16 + c] = __float2bfloat16(y);
+    }
+  }
+}
+
 // out[r, c] = alpha * x[r % x_mod, c] + beta * y[r % y_mod, c]   (fp32 in; fp32 and/or bf16 out)
 __global__ void axpby_rows_kernel(const float* __restrict__ x, const float* __restrict__ y, float alpha, float beta,
                                   int x_mod, int y_mod, int x_div, float* out_f32, bf16* out_bf16, long long rows, int C) {
@@ -545,8 +591,12 @@ extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const flo
                                                                 ldo_bf16, rows);                                 \
     break;
   switch (C) {
-    LN_CASE(2) LN_CASE(3) LN_CASE(6) LN_CASE(8) LN_CASE(12) LN_CASE(24)
+    LN_CASE(2) LN_CASE(3) LN_CASE(6) LN_CASE(7) LN_CASE(8) LN_CASE(12) LN_CASE(14) LN_CASE(24) LN_CASE(28)
     default:
+      if (C < 128)
+        usvm_launch(layernorm_regp_kernel<4>, dim3(cdiv(rows, 8)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu, out_f32,
+                    ldo_f32, ob, ldo_bf16, rows, C);
+      else
       usvm_launch(layernorm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu, out_f32, ldo_f32, ob, ldo_bf16, rows, C);
   }
 #undef LN_CASE
