@@ -204,7 +204,8 @@ def test_postprocess_masks_against_reference_kernel_composition():
 
 
 @pytest.mark.parametrize("shape,density,seed", [((9, 32, 40), 0.3, 0), ((16, 64, 64), 0.12, 1), ((5, 20, 28), 0.6, 2),
-                                                ((64, 128, 128), 0.05, 3), ((1, 16, 16), 0.4, 4)])
+                                                ((64, 128, 128), 0.05, 3), ((1, 16, 16), 0.4, 4),
+                                                ((24, 96, 100), 0.93, 5), ((12, 70, 33), 0.5, 6), ((6, 40, 129), 0.8, 7)])
 def test_largest_component_3d_matches_scipy(shape, density, seed):
     """usvm_cc3d_largest_u8 (the CT driver's getLargestCC on the device) bit-exact against the scipy restatement, on
     random volumes with blobs -- including ties in area (small random components) and 26-connectivity-only links."""

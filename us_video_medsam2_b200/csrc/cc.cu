@@ -329,33 +329,52 @@ fill_holes_local_kernel(const float* scores_in, float* scores_out, int H, int W,
 // component's first voxel in raster order -- the order in which skimage numbers its labels); areas are counted at the
 // roots; the winner is the largest area, ties to the smallest root (np.argmax returns the first maximum).
 // ---------------------------------------------------------------------------------------------
+// init: a voxel's first link is the start of its run of consecutive foreground voxels along x (inside the 32 voxels its
+// warp covers), found with one ballot -- solid regions start out as a few roots per row instead of one per voxel
 __global__ void cc3_init(const uint8_t* __restrict__ vol, int32_t* __restrict__ par, int32_t* __restrict__ cnt,
-                         long long n, unsigned long long* best) {
+                         long long n, unsigned long long* best, int W) {
   PDL_ENTRY();
   if (blockIdx.x == 0 && threadIdx.x == 0) *best = 0ull;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    par[i] = vol[i] ? (int32_t)i : -1;
-    cnt[i] = 0;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long base = warp0 * 32; base < n; base += nwarps * 32) {
+    const long long i = base + lane;
+    const bool fg = i < n && vol[i];
+    const unsigned bits = __ballot_sync(0xffffffffu, fg);
+    const bool first = fg && (lane == 0 || (int)(i % W) == 0 || !((bits >> (lane - 1)) & 1u));
+    const unsigned starts = __ballot_sync(0xffffffffu, first);
+    if (i < n) {
+      const int s0 = 31 - __clz((int)(starts & (0xffffffffu >> (31 - lane))));  // nearest run start at or below this lane
+      par[i] = fg ? (int32_t)(base + s0) : -1;
+      cnt[i] = 0;
+    }
   }
 }
+// merge: unions with the 13 neighbours that precede the voxel in raster order, minus the redundant ones -- if the voxel's
+// left neighbour p' and the neighbour's left neighbour q' are both foreground, p ~ p' and q ~ q' hold through their runs and
+// p' ~ q' is the same direction's union one voxel to the left, so (p, q) adds nothing.  Inside a solid region every
+// union is skipped; work is left at region boundaries and at the 32-voxel seams of the runs.
 __global__ void cc3_merge(const uint8_t* __restrict__ vol, int32_t* par, int D, int H, int W) {
   PDL_ENTRY();
   const long long n = (long long)D * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (!vol[i]) continue;
     const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((long long)W * H));
-    // the 13 neighbours that precede (z, y, x) in raster order
+    const bool left = x > 0 && vol[i - 1];
+    if (left && (i & 31) == 0) uf_union(par, (int)i, (int)(i - 1));  // run seam between two warps' segments
 #pragma unroll
     for (int dz = -1; dz <= 0; ++dz)
 #pragma unroll
       for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
         for (int dx = -1; dx <= 1; ++dx) {
-          if (dz == 0 && (dy > 0 || (dy == 0 && dx >= 0))) continue;
+          if (dz == 0 && dy >= 0) continue;  // (0, 0, -1) is the run itself
           const int zz = z + dz, yy = y + dy, xx = x + dx;
           if (zz < 0 || yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
           const long long j = ((long long)zz * H + yy) * W + xx;
-          if (vol[j]) uf_union(par, (int)i, (int)j);
+          if (!vol[j]) continue;
+          if (left && xx > 0 && vol[j - 1]) continue;
+          uf_union(par, (int)i, (int)j);
         }
   }
 }
@@ -478,7 +497,7 @@ extern "C" int usvm_cc3d_largest_u8(const uint8_t* vol, uint8_t* out, int32_t* s
   if (n >= (1LL << 31) - 1) return USVM_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (int)(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
-  usvm_launch(cc3_init, dim3(grid), dim3(256), 0, s, vol, scratch_parent, scratch_count, n, scratch_best);
+  usvm_launch(cc3_init, dim3(grid), dim3(256), 0, s, vol, scratch_parent, scratch_count, n, scratch_best, W);
   usvm_launch(cc3_merge, dim3(grid), dim3(256), 0, s, vol, scratch_parent, D, H, W);
   usvm_launch(cc3_count, dim3(grid), dim3(256), 0, s, scratch_parent, scratch_count, n);
   usvm_launch(cc3_best, dim3(grid), dim3(256), 0, s, scratch_parent, scratch_count, n, scratch_best);
