@@ -64,6 +64,40 @@ def parse(argv=None):
     return ap.parse_args(argv)
 
 
+def time_cross_attention(dev, peaks, splits, iters=10):
+    """The dominant kernel of a B+ tracked frame -- the memory attention's cross-attention, 4096 queries x 28 736 keys
+    (7 memory frames + 16 pointers), d = 256, split over the keys as the engine does at one object -- timed alone with CUDA
+    events on the launching stream, L2 flushed before every launch (K / V of one object: 59 MB per layer set)."""
+    from us_video_medsam2_b200 import ops
+
+    T, Nk, D = 4096, 7 * 4096 + 64, 256
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = torch.randn((T, D), generator=g, device=dev).to(torch.bfloat16)
+    kv = torch.randn((Nk, 4 * D), generator=g, device=dev).to(torch.bfloat16)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    fn = lambda: ops.fmha(q, kv, kv, 1, 1, T, Nk, D, (0, T * D, D, D), (D, Nk * 4 * D, 4 * D, D),
+                          (2 * D, Nk * 4 * D, 4 * D, D), num_splits=splits)
+    for _ in range(2):
+        fn()
+    tot = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    us = tot / iters * 1e3
+    ach = 4.0 * T * Nk * D / us / 1e6
+    return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": ach / peaks["bf16_sustained"], "traffic": None,
+            "kernel": f"fmha_tc5_ts_kernel + fmha_combine_kernel<256> (memory-attention cross-attention, 4096 x {Nk} keys, "
+                      f"d=256, {splits}-way split-KV)",
+            "flops_per_launch": 4.0 * T * Nk * D, "avg_us": us, "launches_timed": iters, "peak_source": peaks["source"],
+            "how": "CUDA events around the kernel pair alone, L2 flushed before every launch"}
+
+
 def cpu_reference(sample):
     """The reference's algorithm for this configuration on the host cores (oracle port, CfgBPlus; pinned to the reference's
     own outputs by tests/test_oracle_pinned.py): box on the first slice of a `sample`-slice sub-volume, forward pass."""
@@ -171,6 +205,8 @@ def run(slices=256, steps=2, warmup=1, encoder_batch=8, encoder_sms=0, cpu_sampl
         cpu = {"value": fps, "unit": "slices/s", "cores": cores, "kind": "port",
                "sample": f"{cpu_sample}-slice sub-volume, box on its first slice, forward pass; oracle port of the reference "
                          f"(CfgBPlus), torch {torch.__version__} CPU fp32"}
+    with torch.inference_mode():
+        roofline = time_cross_attention(dev, peaks, pred.engine()._splits(1, 7 * 4096 + 64))
     GF_ENCODER_BPLUS = encoder_gflops(pred.cfg)
     enc_tf = GF_ENCODER_BPLUS / enc_ms  # GFLOP / ms = TFLOP/s
     return {
@@ -187,7 +223,7 @@ def run(slices=256, steps=2, warmup=1, encoder_batch=8, encoder_sms=0, cpu_sampl
         "propagated_frames_per_s": frames / (ms / 1e3),
         "e2e": {"value": T * steps / (ms_e2e / 1e3), "unit": "slices/s", "h2d_bytes_per_step": T * 512 * 512,
                 "d2h_bytes_per_step": T * 512 * 512, "propagated_frames_per_s": frames_e2e / (ms_e2e / 1e3)},
-        "gpu_launches": launches, "clocks": clocks, "segmented_voxels": fg, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "segmented_voxels": fg, "cpu_baseline": cpu, "roofline": roofline,
         "components": {"image_encoder": {"ms_per_slice": enc_ms, "batch": encoder_batch, "achieved": enc_tf,
                                          "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                                          "frac": enc_tf / peaks["bf16_sustained"],

@@ -92,17 +92,15 @@ def gemm_bf16(a, w, bias=None, act=ACT_NONE, col_scale=None, residual=None, res_
     """epi(a[M,K] @ w[N,K]^T) on the tcgen05 kernel; returns (fp32 out or None, bf16 out or None).
     rope = (cos, sin, cols, rows_per_batch, n_rope): fused rotary encoding of output columns [0, cols).
     ln = (weight, bias, eps[, gelu]): the bf16 output becomes LayerNorm(row) (then GELU) of the result.  With N == 256
-    the norm can run inside the GEMM epilogue (one 128 x 256 tile per CTA owns whole rows); that pays off once there are
-    enough row tiles to occupy the GPU (measured: 8 tiles at M = 1024 lose to GEMM + LayerNorm launches, which spread
-    over 64 + 128 CTAs), so ln_fused=None fuses from M >= 4096 on; True / False force it."""
+    the norm can run inside the GEMM epilogue (one 128 x 256 tile per CTA owns whole rows, ln_fused=True).  Measured with
+    the current kernels (tools/bench_lnfuse.py): a fused tile takes ~20 us whatever M is (two passes over a 128 x 256
+    accumulator by four epilogue warps), GEMM + LayerNorm launches 7.7 us at M = 4096, 18 us at 16384, 35 us against 50 at
+    32768 -- the two launches win everywhere, so ln_fused=None means not fused."""
     _chk(a, BF16, "a"), _chk(w, BF16, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
-    # (measured at 32 objects, M = 32768: the fused 128 x 256 tiles run two waves at one CTA per SM, 52 us, against
-    # 23 us for the persistent GEMM + 12 us for the LayerNorm kernel -- so the fusion is kept for the mid range only)
-    if ln is not None and ((_FORCE_SIMT if simt is None else simt) or N != 256 or
-                           not (4096 <= M < 16384 if ln_fused is None else ln_fused)):  # GEMM, then the LayerNorm kernel
+    if ln is not None and ((_FORCE_SIMT if simt is None else simt) or N != 256 or not ln_fused):  # GEMM, then LayerNorm
         o32, _ = gemm_bf16(a, w, bias, act, col_scale, residual, res_mod, f32=True, out_f32=out_f32, block_n=block_n,
                            simt=simt, rope=rope, res_div=res_div)
         _, o16 = layernorm(o32, ln[0], ln[1], ln[2], bf16=True, gelu=len(ln) > 3 and bool(ln[3]))
