@@ -88,3 +88,40 @@ def test_ct_driver_flow_matches_reference_fixture(predictor, golden):
     for t in range(T):
         d = 2.0 * (seg_a[t] & seg_b[t]).sum() / max(1, seg_a[t].sum() + seg_b[t].sum())
         assert d >= DICE_BAR, (t, d)
+
+
+def test_two_objects_and_lockstep_sessions_equal_separate_runs(predictor):
+    """Size-generic batching at 4096 queries: two objects in one session (B = 2: other split factors and kernels than
+    B = 1) and two sessions tracked in lock-step (propagate_in_videos) give each object the masks it gets on its own, up
+    to the bf16 noise of a different reduction order."""
+    T = 5
+    clip = synth.make_clip(T, size=1024, kind="speckle").cuda()
+    boxes = [np.array([190.0, 170.0, 340.0, 330.0], np.float32), np.array([60.0, 250.0, 200.0, 420.0], np.float32)]
+
+    def run(obj_boxes):
+        st = predictor.init_state(clip, 512, 512)
+        for i, bx in enumerate(obj_boxes):
+            predictor.add_new_points_or_box(st, 0, i + 1, box=bx)
+        return st, torch.stack([lg[:, 0].float().clone() for _, _, lg in predictor.propagate_in_video(st)])  # [T, B, H, W]
+
+    with torch.inference_mode():
+        alone = [run([bx])[1] for bx in boxes]
+        _, both = run(boxes)
+        for j in range(2):
+            for t in range(T):
+                assert dice(both[t, j], alone[j][t, 0]) >= 0.999, (j, t)
+            assert float((both[:, j] - alone[j][:, 0]).abs().mean()) < 1e-3
+        states = []
+        for bx in boxes:
+            st = predictor.init_state(clip, 512, 512)
+            predictor.add_new_points_or_box(st, 0, 1, box=bx)
+            states.append(st)
+        lock = [[], []]
+        for t, ids, masks in predictor.propagate_in_videos(states):
+            for j, lg in enumerate(masks):
+                lock[j].append(lg[:, 0].float().clone())
+        for j in range(2):
+            got = torch.stack(lock[j])
+            assert got.shape == alone[j].shape
+            for t in range(T):
+                assert dice(got[t, 0], alone[j][t, 0]) >= 0.999, (j, t)
