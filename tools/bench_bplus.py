@@ -90,8 +90,18 @@ def time_cross_attention(dev, peaks, splits, iters=10):
         tot += a.elapsed_time(b)
     us = tot / iters * 1e3
     ach = 4.0 * T * Nk * D / us / 1e6
+    traffic, src = None, None
+    raw = os.path.join(ROOT, "profiles", "r2_bplus_fmha_ncu_raw.csv")  # committed `ncu --set full` capture of this launch
+    if os.path.exists(raw):
+        import csv
+
+        hdr, units, vals = list(csv.reader(open(raw)))[:3]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = sum(float(vals[i]) * scale[units[i]] for i, h in enumerate(hdr)
+                      if h in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        src = "profiles/r2_bplus_fmha_ncu_raw.csv"
     return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": ach / peaks["bf16_sustained"], "traffic": None,
+            "frac": ach / peaks["bf16_sustained"], "traffic": traffic, "traffic_source": src,
             "kernel": f"fmha_tc5_ts_kernel + fmha_combine_kernel<256> (memory-attention cross-attention, 4096 x {Nk} keys, "
                       f"d=256, {splits}-way split-KV)",
             "flops_per_launch": 4.0 * T * Nk * D, "avg_us": us, "launches_timed": iters, "peak_source": peaks["source"],

@@ -38,6 +38,11 @@ def run(name, M, N, K, act=0, f32out=False, res=False):
         prev_end = r[7]
 
 
+if os.environ.get("SHAPES") == "kv":  # the output-heavy bank projections (K = 64 -> 1024 columns)
+    run("bank V projection (32 objects)", 32 * 7232, 1024, 64)
+    run("out-proj + residual -> f32 (32 objects)", 32768, 256, 256, f32out=True, res=True)
+    run("FFN linear1 ReLU (32 objects)", 32768, 2048, 256, act=ops.ACT_RELU)
+    sys.exit(0)
 run("stage-1 qkv", 262144, 288, 96)
 run("stage-1 MLP up GELU", 262144, 384, 96, act=ops.ACT_GELU)
 run("stage-3 qkv", 16384, 1152, 384)
