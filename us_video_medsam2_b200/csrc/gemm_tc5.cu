@@ -566,7 +566,9 @@ __host__ __device__ constexpr int p_smem_total(int bn, int num_kb, int stages, b
 }
 
 // TF32: fp32 operands read as tf32 (a k-block is then 32 floats, each tcgen05.mma covers K = 8) -- the batched mask decoder
-template <bool PAIR, bool TF32 = false>
+// PF = false: the variant for epilogues without residual / rotary operands -- the registers their one-block-ahead prefetch
+// would hold carry a second accumulator block instead (two column blocks per iteration, see the epilogue loop)
+template <bool PAIR, bool TF32 = false, bool PF = true>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
@@ -745,6 +747,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
     uint8_t* stg_warp = staging + ew * stg_bufs * stg_per_buf;  // one or two buffers: [fp32 block | bf16 block] each
     const int stg16_off = ep.out_f32 ? STG_F32 : 0;
     uint32_t nstored = 0;  // column blocks this warp has handed to TMA so far (buffer = nstored & 1)
+    bool full_wait = false;  // a paired store group (both buffers) is the most recent one
     float* strip_bias = strips + ew * (2 * P_MAX_BLOCKS * 32);   // [blocks][32 columns]
     float* strip_scale = strip_bias + P_MAX_BLOCKS * 32;
     int strip_n = -1;      // tile_n the strips currently hold
@@ -777,6 +780,7 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
       float4 cur[8];
       // kind: 0 nothing, 1 residual, 2 rotary tables
       auto prefetch = [&](int c0) -> int {
+        if constexpr (!PF) return 0;
         const int col0 = tile_n * BN + c0;
         if (c0 >= BN || col0 + 32 > N || row0 >= M) return 0;
         if (ep.residual != nullptr && row_ok) {
@@ -809,6 +813,118 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
         for (int c0 = quarter * 32; c0 < BN; c0 += 32 * P_COL_GROUPS, ++blk) {
           const int col0 = tile_n * BN + c0;
           if (col0 >= N) break;  // warp-uniform
+          if constexpr (!PF) {
+            // Two column blocks at a time (the warp has two staging buffers): both TMEM loads are issued before the wait and
+            // the pair shares one staging wait, one proxy fence and one bulk-store group -- the per-block chain (load
+            // latency, fence, commit), not bandwidth, bounds the output-heavy GEMMs (tools/pgemm_timeline.py).
+            const int c1 = c0 + 32 * P_COL_GROUPS, col1 = tile_n * BN + c1;
+            if (stg_bufs == 2 && !(dbg & 6) && c1 < BN && col1 + 32 <= N) {
+              uint32_t acc[32], acc2[32];
+              tc5_ld_32x32(t_lane + (uint32_t)c0, acc);
+              tc5_ld_32x32(t_lane + (uint32_t)c1, acc2);
+              tc5_wait_ld();
+              if (!(c1 + 32 * P_COL_GROUPS < BN && col1 + 32 * P_COL_GROUPS < N)) {  // the warp's last reads of this tile
+                tc5_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+                  else mbar_arrive(&acc_empty[buf]);
+                }
+                released = true;
+              }
+              float v[32], u[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                v[j] = __uint_as_float(acc[j]);
+                u[j] = __uint_as_float(acc2[j]);
+              }
+              if (ep.bias) {
+                const float4* bs = reinterpret_cast<const float4*>(strip_bias + blk * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = bs[j], b2 = bs[8 + j];
+                  v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                  u[4 * j] += b2.x; u[4 * j + 1] += b2.y; u[4 * j + 2] += b2.z; u[4 * j + 3] += b2.w;
+                }
+              }
+              if (ep.act == USVM_ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  v[j] = gelu_erf(v[j]);
+                  u[j] = gelu_erf(u[j]);
+                }
+              } else if (ep.act == USVM_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  v[j] = fmaxf(v[j], 0.0f);
+                  u[j] = fmaxf(u[j], 0.0f);
+                }
+              }
+              if (ep.col_scale) {
+                const float4* ss = reinterpret_cast<const float4*>(strip_scale + blk * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = ss[j], b2 = ss[8 + j];
+                  v[4 * j] *= b.x; v[4 * j + 1] *= b.y; v[4 * j + 2] *= b.z; v[4 * j + 3] *= b.w;
+                  u[4 * j] *= b2.x; u[4 * j + 1] *= b2.y; u[4 * j + 2] *= b2.z; u[4 * j + 3] *= b2.w;
+                }
+              }
+              if (nstored) {  // every earlier store of this warp has finished reading both staging buffers
+                if (elect_one()) tma_store_wait_read();
+                __syncwarp();
+              }
+              uint8_t* sa32 = stg_warp;
+              uint8_t* sb32 = stg_warp + stg_per_buf;
+              if (ep.out_f32) {
+                uint8_t* pa = sa32 + lane * 128;
+                uint8_t* pb = sb32 + lane * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  *reinterpret_cast<float4*>(pa + ((c ^ (lane & 7)) << 4)) =
+                      make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                  *reinterpret_cast<float4*>(pb + ((c ^ (lane & 7)) << 4)) =
+                      make_float4(u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
+                }
+              }
+              if (ep.out_bf16) {
+                uint8_t* pa = sa32 + stg16_off + lane * 64;
+                uint8_t* pb = sb32 + stg16_off + lane * 64;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  uint4 pk, pk2;
+                  pk.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+                  pk.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+                  pk.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+                  pk.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+                  pk2.x = pack_bf16x2(u[8 * c], u[8 * c + 1]);
+                  pk2.y = pack_bf16x2(u[8 * c + 2], u[8 * c + 3]);
+                  pk2.z = pack_bf16x2(u[8 * c + 4], u[8 * c + 5]);
+                  pk2.w = pack_bf16x2(u[8 * c + 6], u[8 * c + 7]);
+                  *reinterpret_cast<uint4*>(pa + (c << 4)) = pk;
+                  *reinterpret_cast<uint4*>(pb + (c << 4)) = pk2;
+                }
+              }
+              fence_async_smem();
+              __syncwarp();
+              if (!(dbg & 1) && elect_one()) {
+                if (ep.out_f32) {
+                  tma_store_2d(&tmO32, sa32, col0, row0);
+                  tma_store_2d(&tmO32, sb32, col1, row0);
+                }
+                if (ep.out_bf16) {
+                  tma_store_2d(&tmO16, sa32 + stg16_off, col0, row0);
+                  tma_store_2d(&tmO16, sb32 + stg16_off, col1, row0);
+                }
+                tma_store_commit();
+              }
+              __syncwarp();
+              nstored += 2;
+              full_wait = true;  // the next single block must not reuse a buffer this group may still be reading
+              c0 = c1;
+              ++blk;
+              continue;
+            }
+          }
           uint32_t acc[32];
           tc5_ld_32x32(t_lane + (uint32_t)c0, acc);
           if (blk > 0) kind = prefetch(c0);
@@ -879,12 +995,13 @@ gemm_bf16_tc5_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const _
           // block i still reads its buffer while block i + 1 is written.
           uint8_t* stg32 = stg_warp + (stg_bufs == 2 ? (nstored & 1u) : 0u) * stg_per_buf;
           uint8_t* stg16 = stg32 + stg16_off;
-          if (nstored >= (uint32_t)stg_bufs) {  // the store that last used this buffer has finished reading it
+          if (nstored >= (uint32_t)stg_bufs || full_wait) {  // the store that last used this buffer has finished reading it
             if (elect_one()) {
-              if (stg_bufs == 2) tma_store_wait_read1();
+              if (stg_bufs == 2 && !full_wait) tma_store_wait_read1();
               else tma_store_wait_read();
             }
             __syncwarp();
+            full_wait = false;
           }
           if (prof && blk == 0) g_pgemm_prof[lt * 16 + 8] = clock64();
           if (ep.out_f32 && !(dbg & 2)) {
@@ -1227,6 +1344,14 @@ int launch_persistent(const void* A, int lda, const void* W, int ldw, const usvm
       return USVM_ERR_CUDA;
     usvm_launch(gemm_bf16_tc5_persistent_kernel<false, true>, dim3(grid_units), dim3(P_THREADS), smem, stream, tmA, tmB,
                 tmO32, tmO16, *ep, M, N, K, bn, flags, tiles_n, tiles_m, ws_groups);
+    return usvm_check_launch();
+  }
+  if (!pair && ep->residual == nullptr && ep->rope_cos == nullptr) {  // no prefetched operands: two blocks per iteration
+    if (cudaFuncSetAttribute(gemm_bf16_tc5_persistent_kernel<false, false, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return USVM_ERR_CUDA;
+    usvm_launch(gemm_bf16_tc5_persistent_kernel<false, false, false>, dim3(grid_units), dim3(P_THREADS), smem, stream, tmA,
+                tmB, tmO32, tmO16, *ep, M, N, K, bn, flags, tiles_n, tiles_m, ws_groups);
     return usvm_check_launch();
   }
   if (!pair) {
