@@ -472,3 +472,28 @@ def test_mp4_ingest_on_device(tmp_path):
     pred.add_new_mask(st, 0, 1, m)
     outs = [lg for _, _, lg in pred.propagate_in_video(st)]
     assert len(outs) == T and outs[3].shape == (1, 1, 96, 128)
+
+
+def test_pipelined_frames_are_bit_identical():
+    """pipeline_frames=True (the graph of frame t also computes frame t + 1's bank-independent attention prefix on a forked
+    branch) changes the schedule, not the arithmetic: same logits, bit for bit, forward and reverse, and the state left
+    behind is the same."""
+    clip = synth.make_clip(40, kind="speckle").cuda()
+    outs = []
+    for flag in (False, True):
+        pred = _predictor(19, encoder_batch=8)
+        pred.pipeline_frames = flag
+        st = pred.init_state(clip, 512, 512)
+        pred.add_new_mask(st, 20, 1, synth.box_mask())
+        got = {}
+        for kw in ({}, dict(reverse=True)):
+            for t, ids, lg in pred.propagate_in_video(st, **kw):
+                got[(t, bool(kw))] = lg.clone()
+        if flag:
+            assert any(len(k) == 8 and k[6] == "pipe" for k in pred._graphs), "the pipelined graphs were never used"
+        outs.append((got, st["_store"].mem.clone(), st["_store"].ptr.clone()))
+    (a, mem_a, ptr_a), (b, mem_b, ptr_b) = outs
+    assert a.keys() == b.keys() and len(a) == 41
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(mem_a, mem_b) and torch.equal(ptr_a, ptr_b)

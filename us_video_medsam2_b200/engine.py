@@ -562,7 +562,29 @@ class Engine:
                     feat_s0=zeros(16 * T, 32))
 
     # ---------------------------------------------------------------- memory attention
-    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None, fold_no_mask=False, group=0):
+    def attention_prefix(self, feat, B, group=0, out=None):
+        """The part of the memory attention that does not depend on the memory bank: x = feat + 0.1 pos, and of layer 0 the
+        self-attention block (norm1, q / k / v projection + RoPE, attention, output projection + residual), norm2 and the
+        cross-attention's query projection + RoPE.  Returns (x fp32 [B*T,256], q bf16 [B*T,256]) -- with `out` = (x, q)
+        buffers the two are written there (the frame graph of frame t computes this for frame t + 1, see
+        SAM2VideoPredictor._run_tracked_frame)."""
+        w = self.w
+        T = self.cfg.feat ** 2
+        cs, sn = w.rope_cos, w.rope_sin
+        L = w.ma_layers[0]
+        x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T, x_div=group * T)
+        _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
+        _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
+        sa_impl, sa_splits = ("mma", max(1, 8 // B)) if B <= 2 and T <= 1024 else (None, self._splits(B, T))
+        o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
+                     (512, T * 768, 768, 256), num_splits=sa_splits, impl=sa_impl)
+        x, h = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True,
+                             ln=(L["n2"][0], L["n2"][1], 1e-5), out_f32=None if out is None else out[0])
+        _, q = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], bf16=True, rope=(cs, sn, 256, T, T),
+                             out_bf16=None if out is None else out[1])
+        return x, q
+
+    def memory_attention(self, feat, k_in, v_in, Nk, n_ptr_tok, B, bank=None, fold_no_mask=False, group=0, prefix=None):
         """feat fp32 [1024,256] (one frame, shared by the B objects; with group > 0: [B/group, 1024, 256], one frame per
         `group` consecutive objects -- several videos batched into one launch); k_in / v_in bf16 [B, Nk, 64] assembled memory
         (k_in already carries the position encodings), the last n_ptr_tok rows are object-pointer tokens (no RoPE).
@@ -571,26 +593,31 @@ class Engine:
         projections of the 4 layers are batched into one GEMM each (`project_memory`).
         `bank`: callable returning (k_all, v_all) -- lets the caller produce the projected bank on a forked stream; it is
         called right before the first cross-attention, after the first self-attention block has been enqueued.
-        fold_no_mask: return norm(x) + no_mask_embed, the decoder's `src` on tracked frames (sam_heads(src_ready=True))."""
+        fold_no_mask: return norm(x) + no_mask_embed, the decoder's `src` on tracked frames (sam_heads(src_ready=True)).
+        prefix: (x, q) from attention_prefix() for this frame, computed earlier -- layer 0 then starts at its cross-attention."""
         w = self.w
         T = self.cfg.feat ** 2
         cs, sn = w.rope_cos, w.rope_sin
-        x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T, x_div=group * T)
+        if prefix is None:
+            x, _ = ops.axpby(feat, w.feat_pos, 1.0, 0.1, rows=B * T, x_mod=T, y_mod=T, x_div=group * T)
         k_all = v_all = None
         if bank is None:
             k_all, v_all = self.project_memory(k_in, v_in, Nk, n_ptr_tok, B)
         for li, L in enumerate(w.ma_layers):
-            _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
-            _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
-            # 1024 keys are 16 key tiles: with one or two objects the mma.sync kernel (64-row query tiles, so twice the
-            # CTAs per split) beats the tcgen05 kernel, whose fixed prologue / epilogue dominates such short ranges
-            sa_impl, sa_splits = ("mma", max(1, 8 // B)) if B <= 2 and T <= 1024 else (None, self._splits(B, T))
-            o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
-                         (512, T * 768, 768, 256), num_splits=sa_splits, impl=sa_impl)
-            # out-projection + residual and the next sub-block's LayerNorm in one launch (whole rows per tile)
-            x, h = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True,
-                                 ln=(L["n2"][0], L["n2"][1], 1e-5))
-            _, q = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], bf16=True, rope=(cs, sn, 256, T, T))
+            if li == 0 and prefix is not None:
+                x, q = prefix
+            else:
+                _, h = ops.layernorm(x, *L["n1"], 1e-5, bf16=True)
+                _, qkv = ops.gemm_bf16(h, L["sa_qkv_w"], bias=L["sa_qkv_b"], bf16=True, rope=(cs, sn, 512, T, T))
+                # 1024 keys are 16 key tiles: with one or two objects the mma.sync kernel (64-row query tiles, so twice the
+                # CTAs per split) beats the tcgen05 kernel, whose fixed prologue / epilogue dominates such short ranges
+                sa_impl, sa_splits = ("mma", max(1, 8 // B)) if B <= 2 and T <= 1024 else (None, self._splits(B, T))
+                o = ops.fmha(qkv, qkv, qkv, B, 1, T, T, 256, (0, T * 768, 768, 256), (256, T * 768, 768, 256),
+                             (512, T * 768, 768, 256), num_splits=sa_splits, impl=sa_impl)
+                # out-projection + residual, then the next sub-block's LayerNorm
+                x, h = ops.gemm_bf16(o.view(B * T, 256), L["sa_o"][0], bias=L["sa_o"][1], residual=x, f32=True,
+                                     ln=(L["n2"][0], L["n2"][1], 1e-5))
+                _, q = ops.gemm_bf16(h, L["ca_q"][0], bias=L["ca_q"][1], bf16=True, rope=(cs, sn, 256, T, T))
             if k_all is None:
                 k_all, v_all = bank()
             o = ops.fmha(q, k_all, v_all, B, 1, T, Nk, 256, (0, T * 256, 256, 256), (li * 256, Nk * 1024, 1024, 256),
@@ -637,14 +664,18 @@ class Engine:
                                                 T=self.cfg.feat ** 2)
         return k_in, v_in, Nk, 4 * n_ptr
 
-    def track_frame(self, f, ctrl, B, n_mem, n_ptr, video_hw, fill_hole_area, group=0):
+    def track_frame(self, f, ctrl, B, n_mem, n_ptr, video_hw, fill_hole_area, group=0, prefix=None, next_feat=None,
+                    next_prefix_out=None):
         """One steady-state tracked frame, entirely on the device and free of host-dependent control flow (so it can
         be captured in a CUDA graph): memory attention over the bank named by `ctrl`, SAM heads with multimask
         output, memory encoder, hole filling, video-resolution resize.  Everything the frame leaves behind is
         written into slot ctrl->cur_frame of the frame store.  f: dict(feat, feat_bf16, feat_s0, feat_s1) of this
         frame.  group > 0: the batch holds B / group videos of `group` objects each in lock-step (same frame index, same
         bank layout); f then carries one frame per video ([B/group, ...]) and every per-video operand is indexed by
-        object // group.  Returns (video_res logits [B,1,H,W], hole-filled low-res logits [B,1,128,128])."""
+        object // group.  Returns (video_res logits [B,1,H,W], hole-filled low-res logits [B,1,128,128]).
+        Frame pipelining: `prefix` = this frame's attention_prefix() computed during the previous frame; `next_feat`
+        (+ `next_prefix_out` buffers) = the next frame's features, whose prefix is computed here on a forked branch beside
+        the decoder and the memory encoder -- neither depends on the other, and the frame is a latency chain."""
         main = torch.cuda.current_stream()
         if self.fork_branches:
             # the bank (gather + temporal encodings + K/V projections of ~7 k rows) does not depend on this frame's
@@ -670,11 +701,20 @@ class Engine:
                 self._handoff(main, side_v, v_all, pp)
                 return kv
 
-            pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank, fold_no_mask=True, group=group)
+            pix = self.memory_attention(f["feat"], None, None, Nk, n_tok, B, bank=bank, fold_no_mask=True, group=group,
+                                        prefix=prefix)
         else:
             pp = None
             k_in, v_in, Nk, n_tok = self.assemble_memory(ctrl, B, n_mem, n_ptr)
-            pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B, fold_no_mask=True, group=group)
+            pix = self.memory_attention(f["feat"], k_in, v_in, Nk, n_tok, B, fold_no_mask=True, group=group, prefix=prefix)
+        pre_s = None
+        if next_feat is not None:
+            # the next frame's bank-independent prefix: a parallel branch from here (the cross-attentions above want the
+            # whole device; the decoder and the memory encoder below are chains of small kernels)
+            pre_s = self._side(3)
+            pre_s.wait_stream(main)
+            with torch.cuda.stream(pre_s):
+                self.attention_prefix(next_feat, B, group=group, out=next_prefix_out)
         o = self.sam_heads(pix, f["feat_s0"], f["feat_s1"], B, None, multimask=True, src_ready=True, defer_ptr=True,
                            group=group)
         # The user-facing tail (single-CTA hole filling, store write, video-resolution resize) is independent of the
@@ -696,6 +736,8 @@ class Engine:
                                       lazy=True)
         self.encode_memory(f["feat_bf16"], mask_in, o["score"], B, ctrl=ctrl, pix_proj=pp, group=group)
         self._handoff(main, tail, video, pm)
+        if pre_s is not None:
+            main.wait_stream(pre_s)
         return video, pm
 
     # ---------------------------------------------------------------- SAM heads
