@@ -206,8 +206,11 @@ __device__ __forceinline__ void attend_unit_tiles(const bf16* sQ, const bf16* sK
   }
 }
 
-template <int WA_D>
-__global__ void __launch_bounds__(WA_THREADS)
+// TILED: the variant for windows of more than 64 keys (online softmax over key tiles) needs 168 registers; the <= 64-key
+// windows this kernel actually serves in the encoder get their own instantiation at 128 (4 CTAs per SM instead of 3: the
+// kernel is bound by load latency at 12 warps per SM, ncu: 25 % of the DRAM peak, 49 % of the cycles without an eligible warp)
+template <int WA_D, bool TILED>
+__global__ void __launch_bounds__(WA_THREADS, TILED ? 1 : 4)
 window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias, bf16* __restrict__ out, int F, int Hg,
                    int Wg, int ws, int pool, int C, int H, float scale, int rows_q, int rows_k, int heads_per_cta) {
   PDL_ENTRY();
@@ -285,9 +288,12 @@ window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
     for (int u = warp; u < hc * nslab; u += WA_THREADS / 32) {
       const int hh = u / nslab, slab = u - hh * nslab;
       float o[WA_D / 8][4], inv[2];
-      if (nk_pad == 16) attend_unit<2, WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
-      else if (nk_pad == 64) attend_unit<8, WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
-      else attend_unit_tiles<WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      if constexpr (TILED) {
+        attend_unit_tiles<WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      } else {
+        if (nk_pad == 16) attend_unit<2, WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+        else attend_unit<8, WA_D>(sQ, sK, sV, LD, hh * WA_D, slab, nk, sl2, o, inv);
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int r = slab * 16 + g + half * 8;
@@ -319,17 +325,33 @@ static int launch_window_attn(const void* qkv, const float* qkv_bias, void* out,
   const int rows_k = nk <= 16 ? 16 : (nk + 63) & ~63, rows_q = (nq + 15) & ~15;
   const size_t smem = (size_t)(rows_q + 2 * rows_k) * (hc * WA_D + 8) * sizeof(bf16);
   if (smem > 200 * 1024) return USVM_ERR_ARG;
-  static UsvmPerDeviceOnce configured = {};
-  if (usvm_need_setup(configured)) {
-    if (cudaFuncSetAttribute(window_attn_kernel<WA_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-      return USVM_ERR_CUDA;
-    usvm_setup_done(configured);
-  }
   const int nw = cdiv(Hg, ws) * cdiv(Wg, ws);
-  usvm_launch(window_attn_kernel<WA_D>, dim3(F * nw, cdiv(heads, heads_per_cta)), dim3(WA_THREADS), smem,
-              reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(qkv), qkv_bias,
-              reinterpret_cast<bf16*>(out), F, Hg, Wg, ws, pool, C, heads, 1.0f / sqrtf((float)WA_D), rows_q, rows_k,
-              heads_per_cta);
+  const dim3 grid(F * nw, cdiv(heads, heads_per_cta));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const float scale = 1.0f / sqrtf((float)WA_D);
+  if (big) {
+    static UsvmPerDeviceOnce configured = {};
+    if (usvm_need_setup(configured)) {
+      if (cudaFuncSetAttribute(window_attn_kernel<WA_D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+          cudaSuccess)
+        return USVM_ERR_CUDA;
+      usvm_setup_done(configured);
+    }
+    usvm_launch(window_attn_kernel<WA_D, true>, grid, dim3(WA_THREADS), smem, s, reinterpret_cast<const bf16*>(qkv), qkv_bias,
+                reinterpret_cast<bf16*>(out), F, Hg, Wg, ws, pool, C, heads, scale, rows_q, rows_k, heads_per_cta);
+  } else {
+    static UsvmPerDeviceOnce configured = {};
+    if (usvm_need_setup(configured)) {
+      if (cudaFuncSetAttribute(window_attn_kernel<WA_D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+              cudaSuccess ||
+          cudaFuncSetAttribute(window_attn_kernel<WA_D, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        return USVM_ERR_CUDA;
+      usvm_setup_done(configured);
+    }
+    usvm_launch(window_attn_kernel<WA_D, false>, grid, dim3(WA_THREADS), smem, s, reinterpret_cast<const bf16*>(qkv), qkv_bias,
+                reinterpret_cast<bf16*>(out), F, Hg, Wg, ws, pool, C, heads, scale, rows_q, rows_k, heads_per_cta);
+  }
   return usvm_check_launch();
 }
 
