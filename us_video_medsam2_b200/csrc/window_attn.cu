@@ -236,49 +236,63 @@ window_attn_kernel(const bf16* __restrict__ qkv, const float* __restrict__ bias,
     bf16* sQ = reinterpret_cast<bf16*>(wa_smem);
     bf16* sK = sQ + rows_q * LD;  // rows_q / rows_k: padded query / key rows of this window size
     bf16* sV = sK + rows_k * LD;
+    // (row, 16-byte chunk) of this thread: one division per pass instead of two per chunk -- the kernel is bound by
+    // instruction issue (ncu: IPC 2 with half of the cycles without an eligible warp), and the loops below were 40 % of it
+    const int rows_per_iter = WA_THREADS / CH;
+    const int r_first = tid / CH, c8 = tid - r_first * CH;
+    const bool loader = r_first < rows_per_iter;
+    const bool ws_p2 = (ws & (ws - 1)) == 0;
+    const int ws_sh = __ffs(ws) - 1;
+    const int colh = h0 * WA_D + c8 * 8;
     // ---- keys and values: rows < nk from the window (bias where the window hangs over the image), zeros up to nk_pad
-    for (int i = tid; i < 2 * nk_pad * CH; i += WA_THREADS) {
-      const int which = i >= nk_pad * CH ? 2 : 1;
-      const int j = i - (which - 1) * nk_pad * CH;
-      const int r = j / CH, c8 = j - r * CH;
-      bf16* dst = (which == 1 ? sK : sV) + r * LD + c8 * 8;
-      const int col = which * C + h0 * WA_D + c8 * 8;
-      if (r < nk) {
-        const int ly = r / ws, lx = r - ly * ws;
-        const int y = wy * ws + ly, x = wx * ws + lx;
-        if (y < Hg && x < Wg) wa_cp_async16(dst, fbase + ((long long)y * Wg + x) * 3 * C + col);
-        else *reinterpret_cast<uint4*>(dst) = bias_chunk(bias + col);
-      } else {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
-    // ---- queries: rows < nq (max over the 2 x 2 source tokens when pooling), zeros up to the end of the last slab
-    for (int i = tid; i < nslab * 16 * CH; i += WA_THREADS) {
-      const int r = i / CH, c8 = i - r * CH;
-      bf16* dst = sQ + r * LD + c8 * 8;
-      const int col = h0 * WA_D + c8 * 8;
-      if (r >= nq) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-      } else if (!pool) {
-        const int ly = r / ws, lx = r - ly * ws;
-        const int y = wy * ws + ly, x = wx * ws + lx;
-        if (y < Hg && x < Wg) wa_cp_async16(dst, fbase + ((long long)y * Wg + x) * 3 * C + col);
-        else *reinterpret_cast<uint4*>(dst) = bias_chunk(bias + col);
-      } else {
-        const int qy = r / wq, qx = r - qy * wq;
-        uint4 m = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          const int y = wy * ws + 2 * qy + (d >> 1), x = wx * ws + 2 * qx + (d & 1);
-          const uint4 u = (y < Hg && x < Wg) ? __ldg(reinterpret_cast<const uint4*>(fbase + ((long long)y * Wg + x) * 3 * C + col))
-                                             : bias_chunk(bias + col);
-          if (d == 0) m = u;
-          else {
-            m.x = max_bf16x2(m.x, u.x); m.y = max_bf16x2(m.y, u.y);
-            m.z = max_bf16x2(m.z, u.z); m.w = max_bf16x2(m.w, u.w);
+    if (loader) {
+      for (int r = r_first; r < nk_pad; r += rows_per_iter) {
+        bf16* dk = sK + r * LD + c8 * 8;
+        bf16* dv = sV + r * LD + c8 * 8;
+        if (r < nk) {
+          const int ly = ws_p2 ? r >> ws_sh : r / ws, lx = r - ly * ws;
+          const int y = wy * ws + ly, x = wx * ws + lx;
+          if (y < Hg && x < Wg) {
+            const bf16* src = fbase + ((long long)y * Wg + x) * 3 * C + colh;
+            wa_cp_async16(dk, src + C);
+            wa_cp_async16(dv, src + 2 * C);
+          } else {
+            *reinterpret_cast<uint4*>(dk) = bias_chunk(bias + C + colh);
+            *reinterpret_cast<uint4*>(dv) = bias_chunk(bias + 2 * C + colh);
           }
+        } else {
+          *reinterpret_cast<uint4*>(dk) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dv) = make_uint4(0u, 0u, 0u, 0u);
         }
-        *reinterpret_cast<uint4*>(dst) = m;
+      }
+      // ---- queries: rows < nq (max over the 2 x 2 source tokens when pooling), zeros up to the end of the last slab
+      const bool wq_p2 = (wq & (wq - 1)) == 0;
+      const int wq_sh = __ffs(wq) - 1;
+      for (int r = r_first; r < nslab * 16; r += rows_per_iter) {
+        bf16* dst = sQ + r * LD + c8 * 8;
+        if (r >= nq) {
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        } else if (!pool) {
+          const int ly = ws_p2 ? r >> ws_sh : r / ws, lx = r - ly * ws;
+          const int y = wy * ws + ly, x = wx * ws + lx;
+          if (y < Hg && x < Wg) wa_cp_async16(dst, fbase + ((long long)y * Wg + x) * 3 * C + colh);
+          else *reinterpret_cast<uint4*>(dst) = bias_chunk(bias + colh);
+        } else {
+          const int qy = wq_p2 ? r >> wq_sh : r / wq, qx = r - qy * wq;
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const int y = wy * ws + 2 * qy + (d >> 1), x = wx * ws + 2 * qx + (d & 1);
+            const uint4 u = (y < Hg && x < Wg) ? __ldg(reinterpret_cast<const uint4*>(fbase + ((long long)y * Wg + x) * 3 * C + colh))
+                                               : bias_chunk(bias + colh);
+            if (d == 0) m = u;
+            else {
+              m.x = max_bf16x2(m.x, u.x); m.y = max_bf16x2(m.y, u.y);
+              m.z = max_bf16x2(m.z, u.z); m.w = max_bf16x2(m.w, u.w);
+            }
+          }
+          *reinterpret_cast<uint4*>(dst) = m;
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
