@@ -15,7 +15,7 @@ def _g(seed=0):
 
 @pytest.mark.parametrize("rows,C,eps", [(1000, 96, 1e-6), (4096, 768, 1e-6), (2048, 256, 1e-5), (7, 64, 1e-6),
                                         (777, 224, 1e-6), (1030, 448, 1e-6), (515, 896, 1e-6), (333, 100, 1e-6),
-                                        (64, 1000, 1e-6)])
+                                        (64, 1000, 1e-6), (16390, 96, 1e-6), (4099, 192, 1e-6)])
 def test_layernorm(rows, C, eps):
     from us_video_medsam2_b200 import ops
 
