@@ -83,26 +83,26 @@ layernorm_reg_kernel(const float* __restrict__ x, int ldx, const float* __restri
 
 // narrow rows (C = 96 / 192: Hiera stages 1-2, 16 K / 4 K rows per frame): LPR lanes per row, 12 channels per lane as three
 // float4 -- 4 (2) rows per warp, reductions over 8 (16) lanes; a warp per 384-byte row was mostly shuffles and loop overhead
-template <int LPR>
+template <int LPR, int NV4 = 3>
 __global__ void __launch_bounds__(256)
 layernorm_narrow_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, const float* __restrict__ b,
                         float eps, int gelu, float* out_f32, int ldo_f32, bf16* out_bf16, int ldo_bf16, int rows) {
-  constexpr int C = LPR * 12, RPW = 32 / LPR;
+  constexpr int C = LPR * 4 * NV4, RPW = 32 / LPR;  // (LPR = 32: one row per warp, NV4 float4 per lane -- C = 384 / 768)
   const int lane = threadIdx.x & 31, sub = lane % LPR, rw = lane / LPR;
-  float4 gw[3], gb[3];
+  float4 gw[NV4], gb[NV4];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < NV4; ++j) {
     gw[j] = __ldg(reinterpret_cast<const float4*>(w) + j * LPR + sub);
     gb[j] = __ldg(reinterpret_cast<const float4*>(b) + j * LPR + sub);
   }
   PDL_ENTRY();
   const long long row = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW + rw;
   const bool ok = row < rows;  // (every lane stays for the shuffles)
-  float4 v[3];
+  float4 v[NV4];
   const float4* xr = reinterpret_cast<const float4*>(x + (ok ? row : 0) * ldx);
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < NV4; ++j) {
     v[j] = xr[j * LPR + sub];
     s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   }
@@ -111,7 +111,7 @@ layernorm_narrow_kernel(const float* __restrict__ x, int ldx, const float* __res
   const float mean = s / C;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < NV4; ++j) {
     v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
     q = fmaf(v[j].x, v[j].x, q); q = fmaf(v[j].y, v[j].y, q); q = fmaf(v[j].z, v[j].z, q); q = fmaf(v[j].w, v[j].w, q);
   }
@@ -120,7 +120,7 @@ layernorm_narrow_kernel(const float* __restrict__ x, int ldx, const float* __res
   const float rstd = 1.0f / sqrtf(q / C + eps);
   if (!ok) return;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
+  for (int j = 0; j < NV4; ++j) {
     float4 y;
     y.x = v[j].x * rstd * gw[j].x + gb[j].x; y.y = v[j].y * rstd * gw[j].y + gb[j].y;
     y.z = v[j].z * rstd * gw[j].z + gb[j].z; y.w = v[j].w * rstd * gw[j].w + gb[j].w;
@@ -649,13 +649,19 @@ extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const flo
                       !(reinterpret_cast<uintptr_t>(b) & 15) &&
                       (!out_f32 || (!(ldo_f32 & 3) && !(reinterpret_cast<uintptr_t>(out_f32) & 15))) &&
                       (!ob || (!(ldo_bf16 & 3) && !(reinterpret_cast<uintptr_t>(ob) & 7)));
-  if (vec_ok && (C == 96 || C == 192)) {
+  if (vec_ok && (C == 96 || C == 192 || C == 384 || C == 768)) {  // the Hiera-tiny / small stage widths
     if (C == 96)
       usvm_launch(layernorm_narrow_kernel<8>, dim3(cdiv(rows, 32)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu, out_f32,
                   ldo_f32, ob, ldo_bf16, rows);
-    else
+    else if (C == 192)
       usvm_launch(layernorm_narrow_kernel<16>, dim3(cdiv(rows, 16)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu, out_f32,
                   ldo_f32, ob, ldo_bf16, rows);
+    else if (C == 384)
+      usvm_launch(layernorm_narrow_kernel<32, 3>, dim3(cdiv(rows, 8)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu,
+                  out_f32, ldo_f32, ob, ldo_bf16, rows);
+    else
+      usvm_launch(layernorm_narrow_kernel<32, 6>, dim3(cdiv(rows, 8)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu,
+                  out_f32, ldo_f32, ob, ldo_bf16, rows);
     return usvm_check_launch();
   }
   switch (C) {
