@@ -649,6 +649,18 @@ extern "C" int usvm_layernorm(const float* x, int ldx, const float* w, const flo
                       !(reinterpret_cast<uintptr_t>(b) & 15) &&
                       (!out_f32 || (!(ldo_f32 & 3) && !(reinterpret_cast<uintptr_t>(out_f32) & 15))) &&
                       (!ob || (!(ldo_bf16 & 3) && !(reinterpret_cast<uintptr_t>(ob) & 7)));
+  if (vec_ok && (C == 224 || C == 448 || C == 896)) {  // Hiera-B+ stages 2-4: 7 float4 per lane
+    if (C == 224)
+      usvm_launch(layernorm_narrow_kernel<8, 7>, dim3(cdiv(rows, 32)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu,
+                  out_f32, ldo_f32, ob, ldo_bf16, rows);
+    else if (C == 448)
+      usvm_launch(layernorm_narrow_kernel<16, 7>, dim3(cdiv(rows, 16)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu,
+                  out_f32, ldo_f32, ob, ldo_bf16, rows);
+    else
+      usvm_launch(layernorm_narrow_kernel<32, 7>, dim3(cdiv(rows, 8)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu,
+                  out_f32, ldo_f32, ob, ldo_bf16, rows);
+    return usvm_check_launch();
+  }
   if (vec_ok && (C == 96 || C == 192 || C == 384 || C == 768)) {  // the Hiera-tiny / small stage widths
     if (C == 96)
       usvm_launch(layernorm_narrow_kernel<8>, dim3(cdiv(rows, 32)), dim3(256), 0, STREAM, x, ldx, w, b, eps, gelu, out_f32,
