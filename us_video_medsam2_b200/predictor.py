@@ -104,11 +104,11 @@ class SAM2VideoPredictor(nn.Module):
         self._engine = None
         self._engine_key = None
         self._graphs, self._graph_seen, self._ctrl = {}, {}, None
-        # opt-in (USVM2_PIPELINE_FRAMES=1 or the attribute): steady-state frames software-pipelined -- the graph of frame t
-        # also computes the part of frame t + 1's memory attention that does not depend on frame t's memory
-        # (Engine.attention_prefix), beside the decoder / memory encoder.  Bit-identical results; measured +1.3 % with encoder
-        # and tracking alternating, +1 % with the encoder on its SM partition, hence off by default.
-        self.pipeline_frames = os.environ.get("USVM2_PIPELINE_FRAMES", "0") != "0"
+        # steady-state frames are software-pipelined (USVM2_PIPELINE_FRAMES=0 or the attribute turns it off): the graph of
+        # frame t also computes the part of frame t + 1's memory attention that does not depend on frame t's memory
+        # (Engine.attention_prefix), beside the decoder / memory encoder.  Bit-identical results; +1.5 % frames/s
+        # (DESIGN.md section 10).
+        self.pipeline_frames = os.environ.get("USVM2_PIPELINE_FRAMES", "1") != "0"
         self._pipe_state, self._pipe_bufs, self._last_frame_key = None, {}, None
 
     # ------------------------------------------------------------------ module plumbing
