@@ -432,3 +432,29 @@ def test_public_signatures_match_reference():
         mine = [p for p in got[name] if p[0] not in ("args", "kwargs")]
         ref_params = [p for p in ref_params if p[0] not in ("args", "kwargs")]
         assert mine[: len(ref_params)] == ref_params, (name, mine, ref_params)
+
+
+def test_bplus_abi_and_flop_model():
+    """Hiera-B+ (BASELINE configs[4]): the committed state-dict ABI (dumped from the reference's own classes) and the analytic
+    encoder FLOP model the B+ bench reports against."""
+    import sys
+
+    import numpy as np
+
+    from us_video_medsam2_b200.engine import HieraBPlusConfig, ModelConfig, _cpad, _head_pad
+
+    abi = synth.bplus_state_dict_abi()
+    assert len(abi) == 615 and sum(int(np.prod(s)) for _, s in abi) == 80850434
+    tiny = dict(synth.state_dict_abi())
+    tail = [(k, s) for k, s in abi if not k.startswith("image_encoder.")]
+    assert tail and all(tiny[k] == s for k, s in tail)  # the propagation tail is the shared one
+    sd = synth.make_bplus_state_dict(3)
+    assert sd["image_encoder.trunk.blocks.2.attn.qkv.weight"].shape == (672, 112)
+    assert torch.equal(sd["no_obj_ptr"], synth.make_bplus_state_dict(3)["no_obj_ptr"])
+    assert (_cpad(112), _cpad(224), _cpad(96), _head_pad(56), _head_pad(64), _head_pad(96)) == (128, 224, 96, 64, 64, 96)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from bench_bplus import encoder_gflops
+
+    # tiny-512: SURVEY 8(d) counts 62.9 GF with padded windows and the neck; the model counts real windows: a little lower
+    assert 55.0 < encoder_gflops(ModelConfig) < 63.0
+    assert 600.0 < encoder_gflops(HieraBPlusConfig) < 650.0
